@@ -1,0 +1,187 @@
+/*
+ * ruvnb.h -- C ABI of libruvnb_b200: the B200-native RUV-III-NB alternating-IRLS path.
+ *
+ * The reference (limfuxing/ruvIIInb 0.9.2.1) is a pure-R package with NO native interface
+ * (DESCRIPTION:35 `NeedsCompilation: no`, NAMESPACE:1-6).  Its data-parallel seams are the
+ * per-gene / per-cell helper closures it dispatches through BiocParallel::bpmapply and foreach
+ * (R/ruvIIInb.R:183,239,350,356,385,439; R/estimateDisp.par.R:84-113).  Every entry point below
+ * replaces one of those seams and cites it; INTEGRATION.md shows the `.Call` shim that binds
+ * them from R and the ctypes binding used by the Python host mirror.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, a negative RUVNB_E* code on failure;
+ *     ruvnb_last_error(ctx) returns the message.  Numerical "problematic entries" (NaN/Inf in
+ *     an update) are NOT errors: the reference swallows and reverts them (R/ruvIIInb.R:368,402,
+ *     424-425) and so do we, reporting the counts.
+ *   - All matrices crossing the boundary are HOST arrays, double precision, column-major,
+ *     shaped exactly like the R objects (W: N x k, a: G x k, Mb: G x m, gmean/psi: G).
+ *     Counts are int32.  The caller owns host buffers; the library owns all device memory.
+ *   - One ctx == one GPU == one host thread.  Multi-GPU = one process (ctx) per GPU with genes
+ *     sharded across ranks; ruvnb_comm_init wires the ranks with NCCL.
+ *   - There is no CPU fallback: ruvnb_create fails if no CUDA device is usable.
+ */
+#ifndef RUVNB_H
+#define RUVNB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RUVNB_ABI_VERSION 1
+
+#define RUVNB_OK 0
+#define RUVNB_EARG (-1)    /* invalid argument */
+#define RUVNB_ECUDA (-2)   /* CUDA runtime error */
+#define RUVNB_ENCCL (-3)   /* NCCL error */
+#define RUVNB_ESTATE (-4)  /* call out of order (e.g. fit before upload) */
+#define RUVNB_ENOMEM (-5)  /* problem does not fit the device */
+
+#define RUVNB_MAX_K 8      /* unwanted factors supported by the register-resident Gram kernels */
+
+typedef struct ruvnb_ctx ruvnb_ctx;
+
+/* Layout of the count matrix handed to ruvnb_upload_counts_dense. */
+#define RUVNB_LAYOUT_GENE_MAJOR 0 /* Y[g*N + c]  (NumPy C order G x N)        */
+#define RUVNB_LAYOUT_CELL_MAJOR 1 /* Y[g + G*c]  (R integer matrix, col-major) */
+
+/* Constants the reference hard-codes or takes as arguments (R/ruvIIInb.R:27-28,155,321,374,431,
+ * 506,524,533,597).  ruvnb_opts_default fills the reference defaults. */
+typedef struct ruvnb_opts {
+  int k;               /* number of unwanted factors (ruvIII.nb `k`)                 */
+  int robust;          /* `robust`: Huber k = 1.345 if set, else 100 (:155)            */
+  double lambda_a;     /* `lambda.a` ridge on alpha (:729)                            */
+  double lambda_b;     /* `lambda.b` ridge on Mb (:420,669)                           */
+  double step_fac;     /* `step.fac` (:491)                                           */
+  int inner_maxit;     /* `inner.maxit` (:526)                                        */
+  int outer_maxit;     /* `outer.maxit` (:597)                                        */
+  double inner_tol;    /* 1e-4 (:524)                                                 */
+  double outer_tol;    /* 1e-4 (:597)                                                 */
+  double psi_tol;      /* 1e-8 (:533)                                                 */
+  int zinb;            /* fit ZINB for cells flagged zeroinf (:237-264,435-467)        */
+  int huber_fastpath;  /* 1: skip the exact per-gene/per-cell MAD when a counting      */
+                       /*    certificate proves every Huber weight is exactly 1;       */
+                       /* 0: always compute the exact MAD (results are identical)      */
+  int verbose;         /* print the reference's trace lines (:301,514,594) to stderr   */
+} ruvnb_opts;
+
+/* Per-inner-iteration record: the decisions of R/ruvIIInb.R:486-527. */
+typedef struct ruvnb_trace_rec {
+  int outer, iter, halving;
+  int degener, accepted;
+  double logl_old, logl_new, logl;
+  int bad_alpha, bad_W, bad_Mb; /* "Problematic ... entries" counts (:367,401,423) */
+} ruvnb_trace_rec;
+
+typedef struct ruvnb_fit_stats {
+  int n_outer;              /* outer iterations run                                       */
+  int n_inner;              /* inner iterations run (accepted + rejected)                 */
+  int n_trace;              /* records written to `trace` (<= trace_cap)                  */
+  double inner_seconds;     /* device time in the inner IRLS loops (CUDA events)          */
+  double disp_seconds;      /* device+host time in the dispersion step                    */
+  double total_seconds;     /* whole ruvnb_fit_nb call                                    */
+  long long kernel_launches;/* kernels launched by this library during the call           */
+  int n_exact_mad_rows;     /* gene rows that needed the exact MAD (certificate failed)   */
+  int n_exact_mad_cells;    /* cells that needed the exact MAD                            */
+} ruvnb_fit_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int ruvnb_abi_version(void);
+void ruvnb_opts_default(ruvnb_opts* o);
+/* device: CUDA ordinal.  Replaces doParallel::registerDoParallel(ncores) (R/ruvIIInb.R:34-37):
+ * the worker pool becomes one GPU. */
+int ruvnb_create(ruvnb_ctx** out, int device);
+void ruvnb_destroy(ruvnb_ctx* ctx);
+const char* ruvnb_last_error(const ruvnb_ctx* ctx);
+long long ruvnb_kernel_launches(const ruvnb_ctx* ctx);
+
+/* ---- multi-GPU wiring (gene sharding) -------------------------------- */
+/* id: 128 bytes from ruvnb_comm_unique_id on rank 0, distributed by the host (torch.distributed
+ * broadcast in the Python mirror; Rmpi or a file in an R host).  After this call the ctx owns genes
+ * [g0, g1) of the G passed to ruvnb_set_design and all-reduces/all-gathers the small per-iteration
+ * quantities over NCCL. */
+int ruvnb_comm_unique_id(unsigned char id[128]);
+int ruvnb_comm_init(ruvnb_ctx* ctx, const unsigned char id[128], int rank, int nranks);
+
+/* ---- problem set-up ------------------------------------------------------------------------- */
+/* grp_of_cell: N labels in 0..m-1 (apply(M,1,which), R/ruvIIInb.R:50); ctl: G flags (:42-45);
+ * zeroinf: N flags or NULL (:39-40).  G is the GLOBAL gene count; [g0,g1) the rows this ctx holds
+ * (g0 = 0, g1 = G on a single GPU). */
+int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t* grp_of_cell,
+                     const uint8_t* ctl, const uint8_t* zeroinf, int64_t g0, int64_t g1);
+/* Y: the (g1-g0) x N rows this ctx owns, plus -- when sharded -- Yctl: the n_ctl x N control-gene
+ * rows (replicated on every rank for the per-cell W update; NULL on a single GPU). */
+int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, const int32_t* Yctl);
+/* CSR rows (the sparse / ZINB input, BASELINE.json config 3): indptr (rows+1), indices, values. */
+int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t* indices,
+                            const int32_t* values, const int64_t* ctl_indptr,
+                            const int32_t* ctl_indices, const int32_t* ctl_values);
+
+/* H0  Winsorize + ceiling (R/ruvIIInb.R:53, DescTools::Winsorize probs=c(0,.995), type-7):
+ * caps the resident counts in place; cap_out (local rows, may be NULL) receives ceil(Q_.995);
+ * nonzero_out (local rows, may be NULL) receives rowSums(Y>0) for the zero-gene filter (:57). */
+int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out);
+
+/* ---- state (all local gene rows; column-major like the R objects) ---------------------------- */
+/* names: "W"(N x k) "alpha"(G x k) "alpha_dev"(G x k) "gmean"(G) "Mb"(G x m) "psi"(G) "step"(G)
+ *        "pi0"(G) "loglik"(G); G here = local rows. */
+int ruvnb_set_state(ruvnb_ctx* ctx, const char* name, const double* host, int k);
+int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host);
+
+/* ---- step operators: one per reference helper seam ------------------------------------------ */
+/* H2  get.coef.wt (R/ruvIIInb.R:181-198,704-706): WLS of log(Y+1) on [1,W] with weights Y+1;
+ *     sets gmean, alpha, alpha_dev, Mb = 0. */
+int ruvnb_init_coef(ruvnb_ctx* ctx, const ruvnb_opts* o);
+/* H6  per-gene log-likelihood at the current state (R/ruvIIInb.R:276-291): sets "loglik",
+ *     returns the sum over ALL genes (all ranks) in *total. */
+int ruvnb_loglik(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total);
+/* H7-H13  one pass of the inner-loop body (R/ruvIIInb.R:303-484): alpha (get.coef2 + get.adev +
+ *     clamp), W (getW + normalise), gmean, Mb (+ clamp), (ZINB: pi0 + E-step), then the candidate
+ *     log-likelihood.  The candidate becomes the current state; `bad` receives the three
+ *     problematic-entry counts; *logl_new the candidate total. */
+int ruvnb_irls_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]);
+/* H14 snapshots: best.* <- current (R/ruvIIInb.R:296,516) / current <- best.* (:492). */
+int ruvnb_snapshot_best(ruvnb_ctx* ctx);
+int ruvnb_restore_best(ruvnb_ctx* ctx);
+/* H14 per-gene step halving: step[g] *= step_fac where loglik_old[g] > loglik_new[g] (:490-491). */
+int ruvnb_halve_steps(ruvnb_ctx* ctx, const ruvnb_opts* o);
+/* H14 accept: loglik <- loglik.tmp (:512); the candidate of the last ruvnb_irls_iteration is already
+ * the current state. */
+int ruvnb_accept(ruvnb_ctx* ctx);
+
+/* H3  estimateDisp.par (R/estimateDisp.par.R:3-202) with design = 1, offset = alpha W' + Mb[,grp],
+ *     weights = wt.zinb (call sites R/ruvIIInb.R:205-221,535-565).
+ *     ruvnb_disp_apl_grid: the Cox-Reid adjusted profile likelihood on the 21-point grid
+ *     0.1*2^seq(-10,10) (:33-37,84-127) -> l0 (local rows x 21, column-major; rows with
+ *     rowSums(y) < 5 are NaN), and AveLogCPM-ready intercepts.
+ *     ruvnb_estimate_disp: grid + common + trend + prior + WLEB -> sets "psi" (tagwise). */
+int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double* rowsum);
+int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out);
+/* The north_star variant: per-gene Newton maximisation of the same Cox-Reid adjusted profile
+ * likelihood in log(psi) (digamma/trigamma on the FP64 pipe).  NOT what the reference computes
+ * (it interpolates the 21-point grid); reported separately. */
+int ruvnb_disp_newton(ruvnb_ctx* ctx, const ruvnb_opts* o, double* psi_out, int maxit);
+
+/* ---- the whole fit on device (R/ruvIIInb.R:266-609) ------------------------------------------ */
+/* W0: injected initial W (N x k, column-major) -- the reference draws it from irlba with a random
+ * start (:167), so parity runs inject it.  psi_inject: NULL -> ruvnb_estimate_disp at every psi
+ * refresh; else `n_psi` consecutive G-vectors used for the initial and subsequent refreshes (the last
+ * one repeats).  trace/trace_cap: optional per-iteration records.  logl_outer: outer_maxit doubles. */
+int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const double* psi_inject,
+                 int n_psi, ruvnb_trace_rec* trace, int trace_cap, double* logl_outer,
+                 ruvnb_fit_stats* stats);
+
+/* ---- get.res (R/get.res.R:12-129) -------------------------------------------------------------- */
+#define RUVNB_RES_PEARSON 1
+#define RUVNB_RES_LOGCOUNTS 2
+#define RUVNB_RES_QUANTILE 3 /* mid-p percentile-adjusted counts (PAC) */
+/* Mb_cells: G x N per-cell Mb (fastruvIII.nb's Mb.all) or NULL to expand the resident G x m Mb by
+ * group.  out: G x N column-major doubles (what write_block receives, :125). */
+int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUVNB_H */

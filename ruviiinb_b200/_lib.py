@@ -1,0 +1,275 @@
+"""ctypes binding of libruvnb_b200.so (include/ruvnb.h).
+
+The library is the product: there is no Python/NumPy fallback.  Importing this module never touches
+the GPU; `load()` raises if the shared object was not built (`python -c 'import __graft_entry__ as g;
+g.build()'`), and `Context()` raises if no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libruvnb_b200.so")
+MAX_K = 8
+
+# every symbol include/ruvnb.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "ruvnb_abi_version", "ruvnb_opts_default", "ruvnb_create", "ruvnb_destroy", "ruvnb_last_error",
+    "ruvnb_kernel_launches", "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
+    "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_set_state",
+    "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_snapshot_best",
+    "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp",
+    "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res",
+]
+
+
+class Opts(C.Structure):
+    """`ruvnb_opts` -- the arguments/constants of ruvIII.nb (R/ruvIIInb.R:27-28,155,524,533,597)."""
+    _fields_ = [("k", C.c_int), ("robust", C.c_int), ("lambda_a", C.c_double), ("lambda_b", C.c_double),
+                ("step_fac", C.c_double), ("inner_maxit", C.c_int), ("outer_maxit", C.c_int),
+                ("inner_tol", C.c_double), ("outer_tol", C.c_double), ("psi_tol", C.c_double),
+                ("zinb", C.c_int), ("huber_fastpath", C.c_int), ("verbose", C.c_int)]
+
+
+class TraceRec(C.Structure):
+    _fields_ = [("outer", C.c_int), ("iter", C.c_int), ("halving", C.c_int), ("degener", C.c_int),
+                ("accepted", C.c_int), ("logl_old", C.c_double), ("logl_new", C.c_double), ("logl", C.c_double),
+                ("bad_alpha", C.c_int), ("bad_W", C.c_int), ("bad_Mb", C.c_int)]
+
+
+class FitStats(C.Structure):
+    _fields_ = [("n_outer", C.c_int), ("n_inner", C.c_int), ("n_trace", C.c_int), ("inner_seconds", C.c_double),
+                ("disp_seconds", C.c_double), ("total_seconds", C.c_double), ("kernel_launches", C.c_longlong),
+                ("n_exact_mad_rows", C.c_int), ("n_exact_mad_cells", C.c_int)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); "
+                           "ruviiinb_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, cp, ip, dp = C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lib.ruvnb_abi_version.restype = C.c_int
+    lib.ruvnb_opts_default.argtypes = [C.POINTER(Opts)]
+    lib.ruvnb_opts_default.restype = None
+    lib.ruvnb_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.ruvnb_destroy.argtypes = [vp]
+    lib.ruvnb_destroy.restype = None
+    lib.ruvnb_last_error.argtypes = [vp]
+    lib.ruvnb_last_error.restype = cp
+    lib.ruvnb_kernel_launches.argtypes = [vp]
+    lib.ruvnb_kernel_launches.restype = C.c_longlong
+    lib.ruvnb_comm_unique_id.argtypes = [vp]
+    lib.ruvnb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.ruvnb_set_design.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, C.c_int64]
+    lib.ruvnb_upload_counts_dense.argtypes = [vp, vp, C.c_int, vp]
+    lib.ruvnb_upload_counts_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.ruvnb_winsorize.argtypes = [vp, vp, vp]
+    lib.ruvnb_set_state.argtypes = [vp, cp, vp, C.c_int]
+    lib.ruvnb_get_state.argtypes = [vp, cp, vp]
+    lib.ruvnb_init_coef.argtypes = [vp, C.POINTER(Opts)]
+    lib.ruvnb_loglik.argtypes = [vp, C.POINTER(Opts), dp]
+    lib.ruvnb_irls_iteration.argtypes = [vp, C.POINTER(Opts), dp, ip]
+    lib.ruvnb_snapshot_best.argtypes = [vp]
+    lib.ruvnb_restore_best.argtypes = [vp]
+    lib.ruvnb_halve_steps.argtypes = [vp, C.POINTER(Opts)]
+    lib.ruvnb_accept.argtypes = [vp]
+    lib.ruvnb_disp_apl_grid.argtypes = [vp, C.POINTER(Opts), vp, vp]
+    lib.ruvnb_estimate_disp.argtypes = [vp, C.POINTER(Opts), dp]
+    lib.ruvnb_disp_newton.argtypes = [vp, C.POINTER(Opts), vp, C.c_int]
+    lib.ruvnb_fit_nb.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(FitStats)]
+    lib.ruvnb_get_res.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
+    for s in SYMBOLS:
+        f = getattr(lib, s)
+        if f.restype is C.c_int and s not in ("ruvnb_abi_version",):
+            pass
+    _lib = lib
+    return lib
+
+
+class RuvnbError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU, one problem (`ruvnb_ctx`).  Arrays cross the boundary as host NumPy arrays shaped like
+    the R objects (column-major doubles; counts int32)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.ruvnb_create(C.byref(h), int(device))
+        if rc != 0:
+            raise RuvnbError(f"ruvnb_create(device={device}) failed with {rc}: no usable CUDA device "
+                             "(ruviiinb_b200 has no CPU fallback)")
+        self.h = h
+        self.G = self.N = self.m = self.k = 0
+        self.g0 = self.g1 = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ruvnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuvnbError(f"libruvnb_b200 error {rc}: {self.lib.ruvnb_last_error(self.h).decode()}")
+
+    # ---- set-up -----------------------------------------------------------------------------
+    def comm_init(self, uid, rank, nranks):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(uid))
+        self._ck(self.lib.ruvnb_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
+
+    def set_design(self, G, N, grp, ctl, zeroinf=None, rows=None):
+        grp = np.ascontiguousarray(grp, dtype=np.int32)
+        ctl = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
+        zi = None if zeroinf is None else np.ascontiguousarray(np.asarray(zeroinf).astype(np.uint8))
+        m = int(grp.max()) + 1 if grp.size else 0
+        g0, g1 = (0, G) if rows is None else rows
+        self._ck(self.lib.ruvnb_set_design(self.h, G, N, m, _ptr(grp), _ptr(ctl), _ptr(zi), g0, g1))
+        self.G, self.N, self.m, self.g0, self.g1 = G, N, m, g0, g1
+        self.Gl = g1 - g0
+
+    def upload_counts(self, Y, Yctl=None, layout="gene_major"):
+        """Y: local rows, int32.  layout 'gene_major' = C-order (Gl, N); 'cell_major' = R's column-major."""
+        lay = 0 if layout == "gene_major" else 1
+        Y = np.ascontiguousarray(Y, dtype=np.int32) if lay == 0 else np.asfortranarray(Y, dtype=np.int32)
+        if Yctl is not None:
+            Yctl = np.ascontiguousarray(Yctl, dtype=np.int32) if lay == 0 else np.asfortranarray(Yctl, dtype=np.int32)
+        self._ck(self.lib.ruvnb_upload_counts_dense(self.h, _ptr(Y), lay, _ptr(Yctl)))
+
+    def upload_counts_csr(self, indptr, indices, values, ctl_csr=None):
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        vl = np.ascontiguousarray(values, dtype=np.int32)
+        c = [None, None, None]
+        if ctl_csr is not None:
+            c = [np.ascontiguousarray(ctl_csr[0], dtype=np.int64), np.ascontiguousarray(ctl_csr[1], dtype=np.int32),
+                 np.ascontiguousarray(ctl_csr[2], dtype=np.int32)]
+        self._ck(self.lib.ruvnb_upload_counts_csr(self.h, _ptr(ip), _ptr(ix), _ptr(vl), _ptr(c[0]), _ptr(c[1]), _ptr(c[2])))
+
+    def winsorize(self):
+        cap = np.empty(self.Gl, dtype=np.float64)
+        nz = np.empty(self.Gl, dtype=np.int64)
+        self._ck(self.lib.ruvnb_winsorize(self.h, _ptr(cap), _ptr(nz)))
+        return cap, nz
+
+    # ---- state ------------------------------------------------------------------------------
+    def _shape(self, name):
+        return {"W": (self.N, self.k), "alpha": (self.Gl, self.k), "alpha_dev": (self.Gl, self.k),
+                "Mb": (self.Gl, self.m)}.get(name, (self.Gl,))
+
+    def set_state(self, name, a, k=0):
+        if name == "W":
+            self.k = int(np.asarray(a).shape[1]) if np.asarray(a).ndim == 2 else 1
+            k = self.k
+        a = np.asfortranarray(np.asarray(a, dtype=np.float64).reshape(self._shape(name), order="F"))
+        self._ck(self.lib.ruvnb_set_state(self.h, name.encode(), _ptr(a), k))
+
+    def get_state(self, name):
+        out = np.empty(self._shape(name), dtype=np.float64, order="F")
+        self._ck(self.lib.ruvnb_get_state(self.h, name.encode(), _ptr(out)))
+        return out
+
+    # ---- operators ----------------------------------------------------------------------------
+    def init_coef(self, opts):
+        self._ck(self.lib.ruvnb_init_coef(self.h, C.byref(opts)))
+
+    def loglik(self, opts):
+        t = C.c_double()
+        self._ck(self.lib.ruvnb_loglik(self.h, C.byref(opts), C.byref(t)))
+        return t.value
+
+    def irls_iteration(self, opts):
+        t = C.c_double()
+        bad = (C.c_int * 3)()
+        self._ck(self.lib.ruvnb_irls_iteration(self.h, C.byref(opts), C.byref(t), bad))
+        return t.value, list(bad)
+
+    def snapshot_best(self):
+        self._ck(self.lib.ruvnb_snapshot_best(self.h))
+
+    def restore_best(self):
+        self._ck(self.lib.ruvnb_restore_best(self.h))
+
+    def halve_steps(self, opts):
+        self._ck(self.lib.ruvnb_halve_steps(self.h, C.byref(opts)))
+
+    def accept(self):
+        self._ck(self.lib.ruvnb_accept(self.h))
+
+    def disp_apl_grid(self, opts):
+        l0 = np.empty((self.Gl, 21), dtype=np.float64, order="F")
+        rs = np.empty(self.Gl, dtype=np.float64)
+        self._ck(self.lib.ruvnb_disp_apl_grid(self.h, C.byref(opts), _ptr(l0), _ptr(rs)))
+        return l0, rs
+
+    def estimate_disp(self, opts):
+        c = C.c_double()
+        self._ck(self.lib.ruvnb_estimate_disp(self.h, C.byref(opts), C.byref(c)))
+        return c.value
+
+    def disp_newton(self, opts, maxit=30):
+        out = np.empty(self.Gl, dtype=np.float64)
+        self._ck(self.lib.ruvnb_disp_newton(self.h, C.byref(opts), _ptr(out), maxit))
+        return out
+
+    def fit_nb(self, opts, W0=None, psi_inject=None, trace_cap=4096):
+        """`ruvnb_fit_nb`.  psi_inject: (n_psi, Gl) array or None."""
+        if W0 is not None:
+            self.k = int(np.asarray(W0).shape[1])
+            W0 = np.asfortranarray(W0, dtype=np.float64)
+        n_psi = 0
+        if psi_inject is not None:
+            psi_inject = np.ascontiguousarray(np.atleast_2d(psi_inject), dtype=np.float64)
+            n_psi = psi_inject.shape[0]
+        trace = (TraceRec * trace_cap)()
+        logl = np.full(max(1, opts.outer_maxit), np.nan)
+        st = FitStats()
+        self._ck(self.lib.ruvnb_fit_nb(self.h, C.byref(opts), _ptr(W0), _ptr(psi_inject), n_psi,
+                                       C.cast(trace, C.c_void_p), trace_cap, _ptr(logl), C.byref(st)))
+        recs = [{f[0]: getattr(trace[i], f[0]) for f in TraceRec._fields_} for i in range(st.n_trace)]
+        stats = {f[0]: getattr(st, f[0]) for f in FitStats._fields_}
+        return logl[: st.n_outer].copy(), recs, stats
+
+    def get_res(self, kind, block_size=5000, Mb_cells=None):
+        out = np.empty((self.Gl, self.N), dtype=np.float64, order="F")
+        mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
+        self._ck(self.lib.ruvnb_get_res(self.h, int(kind), int(block_size), _ptr(mb), _ptr(out)))
+        return out
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.ruvnb_kernel_launches(self.h))
+
+
+def default_opts(**kw):
+    o = Opts()
+    load().ruvnb_opts_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o

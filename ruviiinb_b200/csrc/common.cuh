@@ -1,0 +1,73 @@
+// common.cuh -- shared device helpers for libruvnb_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_pipeline.h>
+#include <stdint.h>
+#include <math.h>
+
+#define CH 128          // cells per chunk: one warp-wide pass of 4 cells per lane
+#define NWARP 8         // warps (= gene rows) per CTA in the row-streaming kernels
+#define ROW_THREADS (NWARP * 32)
+#define LOG_DBL_MIN (-708.3964185322641)  // log(.Machine$double.xmin), R/ruvIIInb.R:290
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// Order-preserving map double -> uint64 (total order; NaN sorts above +Inf, callers count NaN apart).
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// Position of the 4 cells a lane owns inside a 128-cell chunk: {2l, 2l+1, 64+2l, 65+2l}.
+// Two 8-byte loads per lane are each a contiguous 256-byte warp access, and the matching double2
+// reads of the staged W tile are bank-conflict free (16-byte lane stride).
+__device__ __forceinline__ int lane_cell(int lane, int e) { return ((e >> 1) << 6) + 2 * lane + (e & 1); }
+
+// ---- per-element NB working quantities (R/ruvIIInb.R:303-321) -----------------------------------
+// signed deviance residual: sign(y-mu) sqrt(2 (l_sat - l)); the lgamma terms of the two dnbinom
+// calls cancel, leaving 2 [ y log(y/mu) - (y+r) log((y+r)/(mu+r)) ].
+__device__ __forceinline__ double nb_signdev(int y, double lmu, double mu, double r) {
+  double yd = (double)y;
+  double L = log(mu + r);
+  double t = -(yd + r) * (log(yd + r) - L);
+  if (y > 0) t += yd * (log(yd) - lmu);
+  double d2 = 2.0 * t;
+  double d = sqrt(fmax(d2, 0.0));
+  if (d2 != d2) d = d2;  // keep NaN
+  return (yd > mu) ? d : ((yd < mu) ? -d : (mu != mu ? mu : 0.0));
+}
+// sig.inv = 1/(exp(-lmu) + psi)
+__device__ __forceinline__ double nb_siginv(double lmu, double psi) { return 1.0 / (exp(-lmu) + psi); }
+// log dnbinom(y; mu, size = r) with +-Inf/NaN -> log(DBL_MIN) (R/ruvIIInb.R:286,290)
+__device__ __forceinline__ double nb_logpmf(int y, double lmu, double mu, double r, double lgr, double rlogr) {
+  double yd = (double)y;
+  double L = log(mu + r);
+  double v;
+  if (y == 0) {
+    v = rlogr - r * L;
+  } else {
+    v = lgamma(yd + r) - lgr - lgamma(yd + 1.0) + rlogr - r * L + yd * (lmu - L);
+  }
+  if (!(fabs(v) <= 1.79769313486231570e308)) v = LOG_DBL_MIN;  // NaN or +-Inf
+  return v;
+}

@@ -1,0 +1,158 @@
+// ctx.cuh -- host-side context of libruvnb_b200: device buffers, launch helpers, NCCL wiring.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/ruvnb.h"
+#include "kernels.cuh"
+
+// ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
+// torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string* err) {
+    if (h) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { *err = std::string("dlopen libnccl failed: ") + dlerror(); return false; }
+    GetUniqueId = (int (*)(ncclUniqueId_t*))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId_t, int))dlsym(h, "ncclCommInitRank");
+    CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { *err = "libnccl lacks a required symbol"; return false; }
+    return true;
+  }
+};
+static NcclApi g_nccl;
+enum { NCCL_INT32 = 2, NCCL_INT64 = 4, NCCL_F64 = 8 };  // ncclDataType_t values (nccl.h)
+enum { NCCL_SUM = 0 };
+
+struct StateSet {  // one parameter set on device
+  double *gmean = nullptr, *Mb = nullptr, *alpha = nullptr, *adev = nullptr, *W = nullptr, *psi = nullptr, *pi0 = nullptr;
+};
+
+struct ruvnb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  std::vector<void*> allocs;
+
+  // design -----------------------------------------------------------------------------------
+  long long G = 0, N = 0, g0 = 0, g1 = 0;
+  int Gl = 0, m = 0, K = 0;
+  bool have_design = false, have_counts = false;
+  std::vector<int> grp;
+  std::vector<uint8_t> ctl, zeroinf;
+  bool any_zeroinf = false;
+  // cell permutation: groups contiguous, each padded to whole 128-cell chunks
+  long long Np = 0;
+  int nchunks = 0;
+  std::vector<int> pos2cell, cell2pos, chunk_grp, chunk_valid, group_chunk0, group_n;
+  int *d_pos2cell = nullptr, *d_cell2pos = nullptr, *d_chunk_grp = nullptr, *d_chunk_valid = nullptr,
+      *d_group_chunk0 = nullptr, *d_group_n = nullptr;
+  // control genes
+  int n_ctl = 0;
+  std::vector<int> ctl_gene;       // global gene index of each control
+  int* d_ctl_local = nullptr;      // local row of each control gene, or -1
+  const int32_t** d_ctl_rows = nullptr;
+  // counts
+  int32_t* dY = nullptr;     // [Gl][Np]
+  int32_t* dYctl = nullptr;  // [n_ctl][Np] (sharded runs only)
+  // state
+  StateSet cur, nw, best;
+  double *step = nullptr, *loglik = nullptr, *loglik_tmp = nullptr;
+  bool have_W = false;
+  // scratch
+  double *A = nullptr, *u = nullptr, *sw = nullptr, *ZS = nullptr, *VS = nullptr, *cvec = nullptr, *Ab = nullptr,
+         *red = nullptr, *amean = nullptr, *S0 = nullptr, *S1 = nullptr, *sigma = nullptr, *Wbar = nullptr,
+         *RMW = nullptr, *sumsq = nullptr, *med = nullptr, *mad = nullptr, *ctlpack = nullptr, *alpha_full = nullptr,
+         *scal = nullptr;
+  double* D = nullptr; long long D_rows = 0;  // exact-MAD scratch [D_rows][Np]
+  int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare
+  int *faillist = nullptr;
+  int *h_flags = nullptr;    // pinned mirror
+  double* h_scal = nullptr;  // pinned [16]
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  // stats of the last iteration
+  int last_fail_rows = 0;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return ctx->fail(RUVNB_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define CKL()                                                                                      \
+  do {                                                                                             \
+    ctx->launches++;                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                           \
+    if (e_ != cudaSuccess)                                                                         \
+      return ctx->fail(RUVNB_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+#define RET(x) do { int r_ = (x); if (r_ != RUVNB_OK) return r_; } while (0)
+
+template <class T>
+static int dev_alloc(ruvnb_ctx* ctx, T** p, long long n) {
+  void* q = nullptr;
+  if (n <= 0) n = 1;
+  cudaError_t e = cudaMalloc(&q, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) return ctx->fail(RUVNB_ENOMEM, "cudaMalloc of %lld bytes failed: %s", n * (long long)sizeof(T), cudaGetErrorString(e));
+  ctx->allocs.push_back(q);
+  *p = (T*)q;
+  return RUVNB_OK;
+}
+template <class T>
+static int dev_upload(ruvnb_ctx* ctx, T** p, const std::vector<T>& v) {
+  RET(dev_alloc(ctx, p, (long long)v.size()));
+  if (!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return RUVNB_OK;
+}
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// all-reduce (sum) in place over the ranks; no-op on a single GPU
+static int allreduce(ruvnb_ctx* ctx, void* buf, size_t count, int dtype) {
+  if (ctx->nranks <= 1) return RUVNB_OK;
+  int r = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, ctx->comm, ctx->stream);
+  if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return RUVNB_OK;
+}
+
+#define DISPATCH_K(KVAL, ...)                                        \
+  switch (KVAL) {                                                    \
+    case 1: { constexpr int KT = 1; __VA_ARGS__; } break;            \
+    case 2: { constexpr int KT = 2; __VA_ARGS__; } break;            \
+    case 3: { constexpr int KT = 3; __VA_ARGS__; } break;            \
+    case 4: { constexpr int KT = 4; __VA_ARGS__; } break;            \
+    case 5: { constexpr int KT = 5; __VA_ARGS__; } break;            \
+    case 6: { constexpr int KT = 6; __VA_ARGS__; } break;            \
+    case 7: { constexpr int KT = 7; __VA_ARGS__; } break;            \
+    case 8: { constexpr int KT = 8; __VA_ARGS__; } break;            \
+    default: return ctx->fail(RUVNB_EARG, "k = %d outside 1..%d", KVAL, RUVNB_MAX_K); \
+  }

@@ -1,0 +1,990 @@
+// kernels.cuh -- the IRLS kernels of libruvnb_b200 (sm_100a).  Included by ruvnb.cu only.
+//
+// Data layout in HBM:
+//   Yp   int32 [Gl][Np]   counts, gene-major; cells permuted so that every replicate group is one
+//                         contiguous run of 128-cell chunks (tail of a group's last chunk = -1 pads)
+//   W    f64   [K][Np]    unwanted factors, factor-major (== R's column-major N x k, permuted/padded)
+//   alpha f64  [Gl][K], Mb f64 [Gl][m], gmean/psi/step f64 [Gl]
+// Row-streaming kernels: one warp per gene row, NWARP rows per CTA, all warps walk the chunks in
+// lock-step so the K x 128 tile of W (and RM_W / W_new) is staged once per CTA in shared memory with
+// cp.async double buffering and reused by the NWARP rows.
+#pragma once
+#include "common.cuh"
+#include "select.cuh"
+
+struct RowGeom {
+  const int32_t* Yp;
+  long long Np;
+  int nchunks;
+  const int* chunk_grp;
+  const int* chunk_valid;
+  int nrows;            // rows this launch walks
+  const int* rowlist;   // nullptr -> slot == row; else row = rowlist[slot] (exact-MAD batches)
+};
+
+template <int K>
+struct GeneState {  // pointers to one parameter set (current, candidate or best)
+  const double* gmean;
+  const double* Mb;     // [Gl][m]
+  const double* alpha;  // [Gl][K]
+  const double* psi;
+  const double* step;
+  const double* W;      // [K][Np]
+  int m;
+};
+
+// ------------------------------------------------------------------------------------------------
+// row-streaming skeleton
+// ------------------------------------------------------------------------------------------------
+template <int K, int NSETS>
+__device__ __forceinline__ void stage_tile(double* dst, const double* const* wsets, long long Np, int chunk, int tid) {
+  constexpr int UNITS_PER_ROW = CH / 2;  // 16-byte units
+  constexpr int UNITS = NSETS * K * UNITS_PER_ROW;
+  for (int u = tid; u < UNITS; u += ROW_THREADS) {
+    int s = u / (K * UNITS_PER_ROW);
+    int rem = u - s * (K * UNITS_PER_ROW);
+    int l = rem / UNITS_PER_ROW;
+    int e2 = rem - l * UNITS_PER_ROW;
+    const double* src = wsets[s] + (long long)l * Np + (long long)chunk * CH + 2 * e2;
+    __pipeline_memcpy_async(dst + (s * K + l) * CH + 2 * e2, src, 16);
+  }
+  __pipeline_commit();
+}
+
+// Op interface: row_begin(row, slot), group_begin(j), elem(y, chunk, ci, tile), group_end(j), row_end(row)
+template <int K, int NSETS, class Op>
+__device__ __forceinline__ void stream_rows(const RowGeom& geo, const double* const* wsets, Op& op, double* smem) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.x * NWARP + warp;
+  const bool active = slot < geo.nrows;
+  const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
+  constexpr int TILE = NSETS * K * CH;
+  if (active) op.row_begin(row, slot);
+  const int32_t* yrow = geo.Yp + (long long)row * geo.Np;
+  int curj = -1;
+  stage_tile<K, NSETS>(smem, wsets, geo.Np, 0, tid);
+  for (int c = 0; c < geo.nchunks; ++c) {
+    if (c + 1 < geo.nchunks) {
+      stage_tile<K, NSETS>(smem + ((c + 1) & 1) * TILE, wsets, geo.Np, c + 1, tid);
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+    if (active) {
+      const double* tile = smem + (c & 1) * TILE;
+      const int j = geo.chunk_grp[c];
+      const int nv = geo.chunk_valid[c];
+      if (j != curj) {
+        if (curj >= 0) op.group_end(curj);
+        curj = j;
+        op.group_begin(j);
+      }
+      const int2* yr = reinterpret_cast<const int2*>(yrow + (long long)c * CH);
+      int2 ya = yr[lane], yb = yr[32 + lane];
+      int ys[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int ci = lane_cell(lane, e);
+        if (ci < nv) op.elem(ys[e], c, ci, tile);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    if (curj >= 0) op.group_end(curj);
+    op.row_end(row);
+  }
+}
+
+template <int K>
+struct GeneRegs {
+  double gmean, psi, r, step;
+  double a[K];
+  const double* mb;
+  double mbj;
+  __device__ __forceinline__ void load(const GeneState<K>& st, int row) {
+    gmean = st.gmean[row];
+    psi = st.psi[row];
+    r = 1.0 / psi;
+    step = st.step ? st.step[row] : 1.0;
+#pragma unroll
+    for (int l = 0; l < K; ++l) a[l] = st.alpha[(long long)row * K + l];
+    mb = st.Mb + (long long)row * st.m;
+    mbj = 0.0;
+  }
+  __device__ __forceinline__ double lmu(const double* w, int ci) const {
+    double s = gmean + mbj;
+#pragma unroll
+    for (int l = 0; l < K; ++l) s = fma(a[l], w[l * CH + ci], s);
+    return s;
+  }
+};
+
+// NaN-propagating pmin(1, k/|u|)  (MASS::psi.huber; R's pmin keeps NaN, CUDA's fmin does not)
+__device__ __forceinline__ double huber_w(double khsig, double d) {
+  double q = khsig / fabs(d);
+  return (q < 1.0) ? q : ((q != q) ? q : 1.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_signdev: signed deviance residuals of every element -> scratch D (exact-MAD path)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct OpSigndev {
+  GeneState<K> st;
+  GeneRegs<K> g;
+  double* Drow;
+  double* D;
+  long long Np;
+  __device__ __forceinline__ void row_begin(int row, int slot) { g.load(st, row); Drow = D + (long long)slot * Np; }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
+    double lmu = g.lmu(tile, ci);
+    double mu = exp(lmu);
+    Drow[(long long)c * CH + ci] = nb_signdev(y, lmu, mu, g.r);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int) {}
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS) k_signdev(RowGeom geo, GeneState<K> st, double* D) {
+  extern __shared__ double smem[];
+  __shared__ const double* wsets[1];
+  if (threadIdx.x == 0) wsets[0] = st.W;
+  __syncthreads();
+  OpSigndev<K> op;
+  op.st = st; op.D = D; op.Np = geo.Np;
+  stream_rows<K, 1>(geo, wsets, op, smem);
+}
+
+// per-row sigma = mad(signdev)/0.6745 from scratch D (one CTA per row)
+__global__ void __launch_bounds__(256) k_row_sigma(const double* D, long long Np, const int* chunk_valid,
+                                                  const int* rowlist, double* sigma, double* med_out) {
+  __shared__ SelScratch sc;
+  const int row = rowlist ? rowlist[blockIdx.x] : blockIdx.x;
+  const double* d = D + (long long)blockIdx.x * Np;
+  auto val = [&](int i) { return d[i]; };
+  auto valid = [&](int i) { return (i & (CH - 1)) < chunk_valid[i >> 7]; };
+  double med, mad;
+  group_median_mad<256>((int)Np, val, valid, &sc, threadIdx.x, &med, &mad);
+  if (threadIdx.x == 0) { sigma[row] = mad / 0.6745; if (med_out) med_out[row] = med; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_devstats: the "Huber provably inactive" certificate.  The reference
+// computes sigma_g = mad(signdev_g)/0.6745 for every gene and weights pmin(1, k sigma/|d|)
+// (R/ruvIIInb.R:713-714); with k.huber = 100 (robust = FALSE, :155) those weights are all exactly 1
+// unless the row is degenerate.  One sweep builds a fixed-bin histogram of d (width 1/16 on
+// [-16,16), two overflow bins) and max|d| per row; from them a rigorous LOWER bound on the raw MAD:
+// with med in [mL, mH] (edges of the bins holding the two middle order statistics) every element
+// with |d - med| < t lies in (mL - t, mH + t), so  #bins-overlapping-that-interval <= (n-1)/2
+// proves  median|d - med| >= t.  Taking t = max|d| / (k 1.4826/0.6745) proves k sigma >= max|d|,
+// i.e. every weight is exactly 1 and the exact order statistic is not needed.  Rows that fail go to
+// the exact radix-select path (k_signdev + k_row_sigma).  sigma_out[row] = +Inf marks "certified".
+// ------------------------------------------------------------------------------------------------
+#define DS_NB 512
+#define DS_LO (-16.0)
+#define DS_INVH 16.0
+template <int K>
+struct OpDevstats {
+  GeneState<K> st;
+  GeneRegs<K> g;
+  unsigned* hist;  // this warp's DS_NB + 2 counters in shared memory
+  double maxabs; unsigned nbad; int lane;
+  double kh; double* sigma_out; int* fail_flag;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); lane = threadIdx.x & 31; maxabs = 0.0; nbad = 0;
+    for (int i = lane; i < DS_NB + 2; i += 32) hist[i] = 0;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
+    double lmu = g.lmu(tile, ci);
+    double mu = exp(lmu);
+    double d = nb_signdev(y, lmu, mu, g.r);
+    double ad = fabs(d);
+    if (!(ad <= 1.79769313486231570e308)) { nbad++; return; }
+    maxabs = fmax(maxabs, ad);
+    double fb = floor((d - DS_LO) * DS_INVH);
+    int b = fb < 0.0 ? 0 : (fb >= (double)DS_NB ? DS_NB + 1 : (int)fb + 1);
+    atomicAdd(&hist[b], 1u);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    __syncwarp();
+    double mx = warp_max(maxabs);
+    unsigned nb = (unsigned)warp_sum_ll((long long)nbad);
+    if (lane == 0) {
+      bool ok = false;
+      long long n = 0;
+      for (int i = 0; i < DS_NB + 2; ++i) n += hist[i];
+      if (nb == 0 && n > 0 && mx > 0.0) {
+        long long kl = (n - 1) / 2, ku = n / 2, acc = 0;
+        int bl = -1, bu = -1;
+        for (int i = 0; i < DS_NB + 2; ++i) {
+          long long nx = acc + hist[i];
+          if (bl < 0 && kl < nx) bl = i;
+          if (bu < 0 && ku < nx) { bu = i; break; }
+          acc = nx;
+        }
+        if (bl >= 1 && bu <= DS_NB) {  // both middles inside the binned range
+          double t = mx / (kh * (1.4826 / 0.6745)) * (1.0 + 1e-9);
+          double eL = DS_LO + (double)(bl - 1) / DS_INVH - t;
+          double eH = DS_LO + (double)bu / DS_INVH + t;
+          double fl = floor((eL - DS_LO) * DS_INVH), fh = floor((eH - DS_LO) * DS_INVH);
+          long long il = (long long)fl + 1 - 1, ih = (long long)fh + 1 + 1;  // one guard bin each side
+          if (il >= 1 && ih <= DS_NB) {
+            long long cnt = 0;
+            for (long long i = il; i <= ih; ++i) cnt += hist[i];
+            ok = cnt <= (n - 1) / 2;
+          }
+        }
+      }
+      sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
+      if (!ok) atomicAdd(fail_flag, 1);
+    }
+    __syncwarp();
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS) k_devstats(RowGeom geo, GeneState<K> st, double kh, double* sigma_out,
+                                                          int* fail_flag) {
+  extern __shared__ double smem[];
+  __shared__ const double* wsets[1];
+  __shared__ unsigned hist[NWARP][DS_NB + 2];
+  if (threadIdx.x == 0) wsets[0] = st.W;
+  __syncthreads();
+  OpDevstats<K> op;
+  op.st = st; op.kh = kh; op.sigma_out = sigma_out; op.fail_flag = fail_flag;
+  op.hist = hist[threadIdx.x >> 5];
+  stream_rows<K, 1>(geo, wsets, op, smem);
+}
+// rows whose certificate failed (sigma == 0 marker) -> compact list, ascending (one CTA, ordered scan)
+__global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigma, int* list, int* count) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int g0 = 0; g0 < Gl; g0 += 1024) {
+    int g = g0 + threadIdx.x;
+    bool f = g < Gl && !(sigma[g] > 1.79769313486231570e308);
+    unsigned bal = __ballot_sync(FULL, f);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int i = 0; i < w; ++i) off += wsum[i];
+    if (f) list[off + __popc(bal & ((1u << lane) - 1))] = g;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; base += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_pass1: per-gene weighted Gram / score of get.coef2 + get.adev (R/ruvIIInb.R:712-730) and the
+// unweighted group sums of Z for `projection` (:328-329), in one sweep of the row.
+// Outputs per gene: A (K(K+1)/2, lower triangle row-wise), u = sum w RM_W Z (K), sw = sum w,
+//                   ZS[j] = sum_{c in j} Z, VS[j][K] = sum_{c in j} w RM_W.
+// ------------------------------------------------------------------------------------------------
+template <int K, bool HUBER>
+struct OpPass1 {
+  static constexpr int KK = K * (K + 1) / 2;
+  GeneState<K> st;
+  GeneRegs<K> g;
+  const double* sigma; double kh, khsig; bool hub;
+  double A[KK], u[K], sw, gz, V[K];
+  double *A_out, *u_out, *sw_out, *ZS, *VS;
+  int row_; int lane;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); row_ = row; lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < KK; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) u[i] = 0.0;
+    sw = 0.0;
+    hub = false;
+    // sigma[row] == +Inf marks a row whose Huber weights are certified to be exactly 1
+    if (HUBER) { khsig = kh * sigma[row]; hub = !(khsig > 1.79769313486231570e308); }
+  }
+  __device__ __forceinline__ void group_begin(int j) {
+    g.mbj = g.mb[j]; gz = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) V[i] = 0.0;
+  }
+  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
+    const double* w = tile; const double* rw = tile + K * CH;
+    double lmu = g.lmu(w, ci);
+    double mu = exp(lmu);
+    double s = 1.0 / (1.0 / mu + g.psi);  // sig.inv = 1/(exp(-lmu)+psi)
+    double Z = lmu + g.step * (((double)y + 0.01) / (mu + 0.01) - 1.0);
+    double wt = s;
+    if (HUBER && hub) wt *= huber_w(khsig, nb_signdev(y, lmu, mu, g.r));  // warp-uniform branch
+    sw += wt; gz += Z;
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double wi = wt * rw[i * CH + ci];
+      V[i] += wi;
+      u[i] = fma(wi, Z, u[i]);
+#pragma unroll
+      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi, rw[jx * CH + ci], A[idx]); ++idx; }
+    }
+  }
+  __device__ __forceinline__ void group_end(int j) {
+    double z = warp_sum(gz);
+    if (lane == 0) ZS[(long long)row_ * st.m + j] = z;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double v = warp_sum(V[i]);
+      if (lane == 0) VS[((long long)row_ * st.m + j) * K + i] = v;
+    }
+  }
+  __device__ __forceinline__ void row_end(int row) {
+#pragma unroll
+    for (int i = 0; i < KK; ++i) { double v = warp_sum(A[i]); if (lane == 0) A_out[(long long)row * KK + i] = v; }
+#pragma unroll
+    for (int i = 0; i < K; ++i) { double v = warp_sum(u[i]); if (lane == 0) u_out[(long long)row * K + i] = v; }
+    double v = warp_sum(sw);
+    if (lane == 0) sw_out[row] = v;
+  }
+};
+template <int K, bool HUBER>
+__global__ void __launch_bounds__(ROW_THREADS) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
+                                                       const double* sigma, double kh, double* A_out, double* u_out,
+                                                       double* sw_out, double* ZS, double* VS) {
+  extern __shared__ double smem[];
+  __shared__ const double* wsets[2];
+  if (threadIdx.x == 0) { wsets[0] = st.W; wsets[1] = RMW; }
+  __syncthreads();
+  OpPass1<K, HUBER> op;
+  op.st = st; op.sigma = sigma; op.kh = kh;
+  op.A_out = A_out; op.u_out = u_out; op.sw_out = sw_out; op.ZS = ZS; op.VS = VS;
+  stream_rows<K, 2>(geo, wsets, op, smem);
+}
+
+// finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its
+// mean (wtvec/mean(wtvec), :715); b = c - A adev_old (:718).  One thread per gene.
+template <int K>
+__global__ void k_alpha_finish(int Gl, int m, double Nreal, const int* group_n, double* A, const double* u,
+                               const double* sw, const double* ZS, const double* VS, const double* adev_old,
+                               double* cvec, double* Ab /* [Gl][KK+K]: A | b for the global sum */) {
+  constexpr int KK = K * (K + 1) / 2;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl) return;
+  double c[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) c[i] = u[(long long)g * K + i];
+  for (int j = 0; j < m; ++j) {
+    double zbar = ZS[(long long)g * m + j] / (double)group_n[j];
+#pragma unroll
+    for (int i = 0; i < K; ++i) c[i] -= zbar * VS[((long long)g * m + j) * K + i];
+  }
+  double scale = Nreal / sw[g];  // 1/mean(w)
+  double Af[KK];
+#pragma unroll
+  for (int i = 0; i < KK; ++i) { Af[i] = A[(long long)g * KK + i] * scale; A[(long long)g * KK + i] = Af[i]; }
+#pragma unroll
+  for (int i = 0; i < K; ++i) { c[i] *= scale; cvec[(long long)g * K + i] = c[i]; }
+  // b = c - A adev_old
+  double ad[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) ad[i] = adev_old[(long long)g * K + i];
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double s = c[i];
+#pragma unroll
+    for (int jx = 0; jx < K; ++jx) {
+      int lo = i > jx ? i : jx, sm = i > jx ? jx : i;
+      s -= Af[lo * (lo + 1) / 2 + sm] * ad[jx];
+    }
+    Ab[(long long)g * (KK + K) + KK + i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < KK; ++i) Ab[(long long)g * (KK + K) + i] = Af[i];
+}
+
+// deterministic column sums of X[n][ncol] (ncol <= 64): one CTA, fixed summation order
+__global__ void __launch_bounds__(1024) k_colsum(const double* X, long long n, int ncol, double* out) {
+  __shared__ double sm[1024];
+  for (int cidx = 0; cidx < ncol; ++cidx) {
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) s += X[i * ncol + cidx];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+      if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[cidx] = sm[0];
+    __syncthreads();
+  }
+}
+
+// small dense solvers ---------------------------------------------------------------------------
+// Gaussian elimination with partial pivoting (what R's solve() / LAPACK dgesv does), n <= 9.
+template <int NMAX>
+__device__ __forceinline__ bool solve_lu(int n, double (*M)[NMAX], double* rhs) {
+  for (int col = 0; col < n; ++col) {
+    int piv = col; double best = fabs(M[col][col]);
+    for (int r2 = col + 1; r2 < n; ++r2) if (fabs(M[r2][col]) > best) { best = fabs(M[r2][col]); piv = r2; }
+    if (!(best > 0.0)) return false;
+    if (piv != col) {
+      for (int cc = 0; cc < n; ++cc) { double t = M[col][cc]; M[col][cc] = M[piv][cc]; M[piv][cc] = t; }
+      double t = rhs[col]; rhs[col] = rhs[piv]; rhs[piv] = t;
+    }
+    for (int r2 = col + 1; r2 < n; ++r2) {
+      double f = M[r2][col] / M[col][col];
+      for (int cc = col; cc < n; ++cc) M[r2][cc] -= f * M[col][cc];
+      rhs[r2] -= f * rhs[col];
+    }
+  }
+  for (int r2 = n - 1; r2 >= 0; --r2) {
+    double s = rhs[r2];
+    for (int cc = r2 + 1; cc < n; ++cc) s -= M[r2][cc] * rhs[cc];
+    rhs[r2] = s / M[r2][r2];
+  }
+  return true;
+}
+
+// alpha.mean = solve(sum_g A_g, sum_g b_g)  (R/ruvIIInb.R:351-354); one thread.
+template <int K>
+__global__ void k_alpha_mean(const double* red /* KK + K */, double* amean) {
+  constexpr int KK = K * (K + 1) / 2;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double M[K][K], rhs[K];
+  for (int i = 0; i < K; ++i) {
+    for (int j = 0; j <= i; ++j) { M[i][j] = red[i * (i + 1) / 2 + j]; M[j][i] = M[i][j]; }
+    rhs[i] = red[KK + i];
+  }
+  bool ok = solve_lu<K>(K, M, rhs);
+  for (int i = 0; i < K; ++i) amean[i] = ok ? rhs[i] : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// alpha.dev_g = solve(A_g + lambda_a I, c_g - A_g alpha.mean) (R/ruvIIInb.R:722-730);
+// alpha = alpha.dev + alpha.mean (:365); counts non-finite entries (:367).
+template <int K>
+__global__ void k_adev(int Gl, const double* A, const double* cvec, const double* amean, double lambda_a,
+                       double* alpha_new, double* adev_new, int* bad) {
+  constexpr int KK = K * (K + 1) / 2;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl) return;
+  double M[K][K], rhs[K], am[K];
+  for (int i = 0; i < K; ++i) am[i] = amean[i];
+  for (int i = 0; i < K; ++i)
+    for (int j = 0; j <= i; ++j) { double v = A[(long long)g * KK + i * (i + 1) / 2 + j]; M[i][j] = v; M[j][i] = v; }
+  for (int i = 0; i < K; ++i) {
+    double s = cvec[(long long)g * K + i];
+    for (int j = 0; j < K; ++j) s -= M[i][j] * am[j];
+    rhs[i] = s;
+  }
+  for (int i = 0; i < K; ++i) M[i][i] += lambda_a;
+  bool ok = solve_lu<K>(K, M, rhs);
+  int nb = 0;
+  for (int i = 0; i < K; ++i) {
+    double x = ok ? rhs[i] : __longlong_as_double(0x7ff8000000000000ll);
+    double a = x + am[i];
+    adev_new[(long long)g * K + i] = x;
+    alpha_new[(long long)g * K + i] = a;
+    if (!(fabs(a) <= 1.79769313486231570e308)) nb++;
+  }
+  if (nb) atomicAdd(bad, nb);
+}
+
+// if any alpha entry was non-finite, the reference reverts the WHOLE alpha (R/ruvIIInb.R:368)
+__global__ void k_revert_if(const int* flag, double* dst, const double* src, long long n) {
+  if (*flag == 0) return;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+// median / mad of strided vectors (columns of alpha: R/ruvIIInb.R:371-372), one CTA per vector
+__global__ void __launch_bounds__(256) k_strided_medmad(const double* base, long long vec_stride, long long elem_stride,
+                                                       int len, double* med, double* mad) {
+  __shared__ SelScratch sc;
+  const double* p = base + (long long)blockIdx.x * vec_stride;
+  auto val = [&](int i) { return p[(long long)i * elem_stride]; };
+  auto valid = [&](int) { return true; };
+  double me, ma;
+  group_median_mad<256>(len, val, valid, &sc, threadIdx.x, &me, &ma);
+  if (threadIdx.x == 0) { med[blockIdx.x] = me; mad[blockIdx.x] = ma; }
+}
+
+// clamp column l of X[n][K] to med[l] +- 4 mad[l]  (R/ruvIIInb.R:373-376; NaN bounds clamp nothing)
+__global__ void k_clamp_cols(double* X, long long n, int K, const double* med, const double* mad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * K) return;
+  int l = (int)(i % K);
+  double hi = med[l] + 4.0 * mad[l], lo = med[l] - 4.0 * mad[l];
+  double v = X[i];
+  if (v > hi) v = hi;
+  if (v < lo) v = lo;
+  X[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// W helpers: group means of W (projection of t(W), R/ruvIIInb.R:331-340), RM_W, norms
+// ------------------------------------------------------------------------------------------------
+// one warp per (factor l, group j): mean over the group's cells
+__global__ void k_wbar(const double* W, long long Np, int K, int m, const int* group_chunk0, const int* group_n,
+                       double* Wbar /* [m][K] */) {
+  int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= K * m) return;
+  int l = wid / m, j = wid % m;
+  long long p0 = (long long)group_chunk0[j] * CH;
+  int n = group_n[j];
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s += W[(long long)l * Np + p0 + i];
+  s = warp_sum(s);
+  if (lane == 0) Wbar[j * K + l] = s / (double)n;
+}
+__global__ void k_rmw(const double* W, long long Np, int K, const int* chunk_grp, const int* chunk_valid,
+                      const double* Wbar, double* RMW) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np * K) return;
+  int l = (int)(i / Np);
+  long long pos = i - (long long)l * Np;
+  int c = (int)(pos >> 7);
+  bool valid = (int)(pos & (CH - 1)) < chunk_valid[c];
+  RMW[i] = valid ? W[i] - Wbar[chunk_grp[c] * K + l] : 0.0;
+}
+// column sum of squares of W (one CTA per factor), deterministic
+__global__ void __launch_bounds__(1024) k_w_sumsq(const double* W, long long Np, double* out) {
+  __shared__ double sm[1024];
+  const double* w = W + (long long)blockIdx.x * Np;
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < Np; i += 1024) s = fma(w[i], w[i], s);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
+}
+// W[,l] /= sqrt(colNorm) (R/ruvIIInb.R:392-394); counts non-finite entries among real cells (:401)
+__global__ void k_w_scale(double* W, long long Np, int K, const double* sumsq, const int* chunk_valid, int* bad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np * K) return;
+  int l = (int)(i / Np);
+  long long pos = i - (long long)l * Np;
+  bool valid = (int)(pos & (CH - 1)) < chunk_valid[pos >> 7];
+  if (!valid) { W[i] = 0.0; return; }
+  double v = W[i] / sqrt(sumsq[l]);
+  W[i] = v;
+  if (!(fabs(v) <= 1.79769313486231570e308)) atomicAdd(bad, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_w_update: getW for every cell (R/ruvIIInb.R:380-390,732-744).  One CTA owns `cpc` cells and all
+// control genes: phase 1 signed deviances -> smem, phase 2 per-cell exact median/MAD (warp per cell),
+// phase 3 weighted Gram/score over control genes, phase 4 the sequential one-regressor WLS
+// (= forward substitution on the lower triangle of sum w a a').
+// ------------------------------------------------------------------------------------------------
+struct CtlPack {            // control-gene parameters, gathered (and, when sharded, all-reduced)
+  const double* gmean;      // [n_ctl]   old gmean
+  const double* psi;        // [n_ctl]
+  const double* step;       // [n_ctl]
+  const double* alpha_old;  // [n_ctl][K]
+  const double* alpha_new;  // [n_ctl][K]
+  const double* Mb;         // [n_ctl][m] old Mb
+};
+template <int K, bool HUBER>
+__global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows, int n_ctl, long long Np,
+                                                  const int* chunk_grp, const int* chunk_valid, CtlPack cp, int m,
+                                                  const double* W_old, double* W_out, int cpc, double kh,
+                                                  long long pos_begin, long long pos_end) {
+  constexpr int KK = K * (K + 1) / 2;
+  constexpr int NACC = KK + K;
+  extern __shared__ double dyn[];
+  __shared__ SelScratch sc[8];
+  __shared__ double sigma_c[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cell_i = tid % cpc, slice = tid / cpc, nsl = 256 / cpc;
+  const long long pos = pos_begin + (long long)blockIdx.x * cpc + cell_i;
+  const bool inb = pos < pos_end;
+  const int chunk = inb ? (int)(pos >> 7) : 0;
+  const bool valid = inb && (int)(pos & (CH - 1)) < chunk_valid[chunk];
+  const int j = chunk_grp[chunk];
+  const int nstr = n_ctl | 1;  // odd row stride (doubles): the per-cell deviance rows do not bank-conflict
+  double wv[K];
+#pragma unroll
+  for (int l = 0; l < K; ++l) wv[l] = valid ? W_old[(long long)l * Np + pos] : 0.0;
+
+  if (HUBER) {
+    double* dsm = dyn;  // [cpc][nstr]
+    if (valid) {
+      for (int gi = slice; gi < n_ctl; gi += nsl) {
+        int y = ctl_rows[gi][pos];
+        double lmu = cp.gmean[gi] + cp.Mb[(long long)gi * m + j];
+#pragma unroll
+        for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
+        double mu = exp(lmu);
+        dsm[(long long)cell_i * nstr + gi] = nb_signdev(y, lmu, mu, 1.0 / cp.psi[gi]);
+      }
+    }
+    __syncthreads();
+    for (int ci = warp; ci < cpc; ci += 8) {
+      long long p2 = pos_begin + (long long)blockIdx.x * cpc + ci;
+      bool v2 = p2 < pos_end && (int)(p2 & (CH - 1)) < chunk_valid[p2 >> 7];
+      if (v2) {  // warp-uniform
+        const double* d = dsm + (long long)ci * nstr;
+        auto val = [&](int i) { return d[i]; };
+        auto vld = [&](int) { return true; };
+        double med, mad;
+        group_median_mad<32>(n_ctl, val, vld, &sc[warp], lane, &med, &mad);
+        if (lane == 0) sigma_c[ci] = mad / 0.6745;
+      }
+    }
+    __syncthreads();
+  }
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  if (valid) {
+    const double khsig = HUBER ? kh * sigma_c[cell_i] : 0.0;
+    for (int gi = slice; gi < n_ctl; gi += nsl) {
+      int y = ctl_rows[gi][pos];
+      double gm = cp.gmean[gi];
+      double lmu = gm + cp.Mb[(long long)gi * m + j];
+#pragma unroll
+      for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
+      double mu = exp(lmu);
+      double psi = cp.psi[gi];
+      double s = 1.0 / (1.0 / mu + psi);
+      double z = lmu + cp.step[gi] * (((double)y + 0.01) / (mu + 0.01) - 1.0) - gm;  // (Z - gmean)[ctl], :381
+      double wt = s;
+      if (HUBER) wt *= huber_w(khsig, dyn[(long long)cell_i * nstr + gi]);
+      int idx = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double wa = wt * cp.alpha_new[(long long)gi * K + i];
+        acc[KK + i] = fma(wa, z, acc[KK + i]);
+#pragma unroll
+        for (int jx = 0; jx <= i; ++jx) { acc[idx] = fma(wa, cp.alpha_new[(long long)gi * K + jx], acc[idx]); ++idx; }
+      }
+    }
+  }
+  // reduce over the gene slices: lanes sharing a cell inside the warp, then the 8 warps (fixed order)
+  for (int o = cpc; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] += __shfl_xor_sync(FULL, acc[i], o);
+  }
+  __syncthreads();
+  double* red = dyn;  // [8][min(cpc,32)][NACC]  (reuses the deviance buffer)
+  const int cw = cpc < 32 ? cpc : 32;  // distinct cells inside one warp
+  if (lane < cw) {
+    int cidx = (cpc <= 32) ? lane : (tid % cpc);
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) red[((long long)warp * cpc + cidx) * NACC + i] = acc[i];
+  }
+  __syncthreads();
+  if (tid < cpc) {
+    double T[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) T[i] = 0.0;
+    if (cpc <= 32) {
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) T[i] += red[((long long)w * cpc + tid) * NACC + i];
+    } else {
+      // cpc in {64,128,256}: a cell lives in exactly one warp
+      int w = tid >> 5;
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) T[i] = red[((long long)w * cpc + tid) * NACC + i];
+    }
+    long long p2 = pos_begin + (long long)blockIdx.x * cpc + tid;
+    bool v2 = p2 < pos_end && (int)(p2 & (CH - 1)) < chunk_valid[p2 >> 7];
+    if (p2 < pos_end) {
+      double Wn[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double s = T[KK + i];
+#pragma unroll
+        for (int l = 0; l < i; ++l) s -= T[i * (i + 1) / 2 + l] * Wn[l];
+        Wn[i] = s / T[i * (i + 1) / 2 + i];
+        W_out[(long long)i * Np + p2] = v2 ? Wn[i] : 0.0;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_pass2: per-gene per-group S0 = sum w, S1 = sum w (Z - alpha_new . W_new) for the gmean and Mb
+// updates (R/ruvIIInb.R:405-420): Z, sig.inv and the Huber weights are those of the OLD parameters.
+// ------------------------------------------------------------------------------------------------
+template <int K, bool HUBER>
+struct OpPass2 {
+  GeneState<K> st;
+  GeneRegs<K> g;
+  const double* alpha_new; double an[K];
+  const double* sigma; double kh, khsig; bool hub;
+  double s0, s1;
+  double *S0, *S1;
+  int row_, lane;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); row_ = row; lane = threadIdx.x & 31;
+#pragma unroll
+    for (int l = 0; l < K; ++l) an[l] = alpha_new[(long long)row * K + l];
+    hub = false;
+    if (HUBER) { khsig = kh * sigma[row]; hub = !(khsig > 1.79769313486231570e308); }
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; s0 = 0.0; s1 = 0.0; }
+  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
+    const double* w = tile; const double* wn = tile + K * CH;
+    double lmu = g.lmu(w, ci);
+    double mu = exp(lmu);
+    double s = 1.0 / (1.0 / mu + g.psi);
+    double Z = lmu + g.step * (((double)y + 0.01) / (mu + 0.01) - 1.0);
+    double wt = s;
+    if (HUBER && hub) wt *= huber_w(khsig, nb_signdev(y, lmu, mu, g.r));
+    double res = Z;
+#pragma unroll
+    for (int l = 0; l < K; ++l) res = fma(-an[l], wn[l * CH + ci], res);
+    s0 += wt;
+    s1 = fma(wt, res, s1);
+  }
+  __device__ __forceinline__ void group_end(int j) {
+    double a = warp_sum(s0), b = warp_sum(s1);
+    if (lane == 0) { S0[(long long)row_ * st.m + j] = a; S1[(long long)row_ * st.m + j] = b; }
+  }
+  __device__ __forceinline__ void row_end(int) {}
+};
+template <int K, bool HUBER>
+__global__ void __launch_bounds__(ROW_THREADS) k_pass2(RowGeom geo, GeneState<K> st, const double* W_new,
+                                                       const double* alpha_new, const double* sigma,
+                                                       double kh, double* S0, double* S1) {
+  extern __shared__ double smem[];
+  __shared__ const double* wsets[2];
+  if (threadIdx.x == 0) { wsets[0] = st.W; wsets[1] = W_new; }
+  __syncthreads();
+  OpPass2<K, HUBER> op;
+  op.st = st; op.alpha_new = alpha_new; op.sigma = sigma; op.kh = kh;
+  op.S0 = S0; op.S1 = S1;
+  stream_rows<K, 2>(geo, wsets, op, smem);
+}
+
+// gmean (R/ruvIIInb.R:405-415) and Mb (:418-420, rowWtAvg :667-675) from the group sums.
+__global__ void k_gmean_mb(int Gl, int m, const double* S0, const double* S1, const double* Mb_old, double lambda_b,
+                           double* gmean_new, double* Mb_new, int* nan_flag, int* bad) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl) return;
+  double num = 0.0, den = 0.0;
+  for (int j = 0; j < m; ++j) {
+    double s0 = S0[(long long)g * m + j];
+    num += S1[(long long)g * m + j] - Mb_old[(long long)g * m + j] * s0;
+    den += s0;
+  }
+  double gm = num / den;
+  gmean_new[g] = gm;
+  int nb = 0, nn = 0;
+  for (int j = 0; j < m; ++j) {
+    double s0 = S0[(long long)g * m + j];
+    double v = (S1[(long long)g * m + j] - gm * s0) / (s0 + lambda_b);
+    Mb_new[(long long)g * m + j] = v;
+    if (v != v) nn++;
+    if (!(fabs(v) <= 1.79769313486231570e308)) nb++;
+  }
+  if (nn) atomicAdd(nan_flag, nn);
+  if (nb) atomicAdd(bad, nb);
+}
+// any NA -> whole Mb reverts (:424); NA/Inf -> 0 (:425); each row clamped to median +- 4 mad (:428-433).
+// One warp per gene.
+__global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* nan_flag, const double* Mb_old,
+                                                     double* Mb_new) {
+  __shared__ SelScratch sc[8];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int g = blockIdx.x * 8 + warp;
+  if (g >= Gl) return;
+  double* row = Mb_new + (long long)g * m;
+  const bool revert = *nan_flag != 0;
+  for (int j = lane; j < m; j += 32) {
+    double v = revert ? Mb_old[(long long)g * m + j] : row[j];
+    if (!(fabs(v) <= 1.79769313486231570e308)) v = 0.0;
+    row[j] = v;
+  }
+  __syncwarp();
+  auto val = [&](int i) { return row[i]; };
+  auto vld = [&](int) { return true; };
+  double med, mad;
+  group_median_mad<32>(m, val, vld, &sc[warp], lane, &med, &mad);
+  double hi = med + 4.0 * mad, lo = med - 4.0 * mad;
+  for (int j = lane; j < m; j += 32) {
+    double v = row[j];
+    if (v > hi) v = hi;
+    if (v < lo) v = lo;
+    row[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_loglik: per-gene NB log-likelihood (R/ruvIIInb.R:276-291)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct OpLoglik {
+  GeneState<K> st;
+  GeneRegs<K> g;
+  double acc, lgr, rlogr;
+  double* out;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); acc = 0.0; lgr = lgamma(g.r); rlogr = g.r * log(g.r);
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
+    double lmu = g.lmu(tile, ci);
+    double mu = exp(lmu);
+    acc += nb_logpmf(y, lmu, mu, g.r, lgr, rlogr);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    double v = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) out[row] = v;
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS) k_loglik(RowGeom geo, GeneState<K> st, double* out) {
+  extern __shared__ double smem[];
+  __shared__ const double* wsets[1];
+  if (threadIdx.x == 0) wsets[0] = st.W;
+  __syncthreads();
+  OpLoglik<K> op;
+  op.st = st; op.out = out;
+  stream_rows<K, 1>(geo, wsets, op, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_init_coef: get.coef.wt (R/ruvIIInb.R:181-198,704-706): WLS of log(y+1) on [1, W], weights y+1
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct OpInit {
+  static constexpr int P = K + 1;
+  static constexpr int PP = P * (P + 1) / 2;
+  double XtX[PP], Xty[P];
+  double *gmean, *alpha;
+  __device__ __forceinline__ void row_begin(int, int) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i) XtX[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) Xty[i] = 0.0;
+  }
+  __device__ __forceinline__ void group_begin(int) {}
+  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
+    double om = (double)y + 1.0;
+    double ly = log(om);
+    double x[P];
+    x[0] = 1.0;
+#pragma unroll
+    for (int l = 0; l < K; ++l) x[l + 1] = tile[l * CH + ci];
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      double wx = om * x[i];
+      Xty[i] = fma(wx, ly, Xty[i]);
+#pragma unroll
+      for (int j = 0; j <= i; ++j) { XtX[idx] = fma(wx, x[j], XtX[idx]); ++idx; }
+    }
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i) XtX[i] = warp_sum(XtX[i]);
+#pragma unroll
+    for (int i = 0; i < P; ++i) Xty[i] = warp_sum(Xty[i]);
+    if ((threadIdx.x & 31) == 0) {
+      double M[P][P], rhs[P];
+      for (int i = 0; i < P; ++i) {
+        for (int j = 0; j <= i; ++j) { M[i][j] = XtX[i * (i + 1) / 2 + j]; M[j][i] = M[i][j]; }
+        rhs[i] = Xty[i];
+      }
+      bool ok = solve_lu<P>(P, M, rhs);
+      const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+      gmean[row] = ok ? rhs[0] : qnan;
+      for (int l = 0; l < K; ++l) alpha[(long long)row * K + l] = ok ? rhs[l + 1] : qnan;
+    }
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS) k_init_coef(RowGeom geo, const double* W, double* gmean, double* alpha) {
+  extern __shared__ double smem[];
+  __shared__ const double* wsets[1];
+  if (threadIdx.x == 0) wsets[0] = W;
+  __syncthreads();
+  OpInit<K> op;
+  op.gmean = gmean; op.alpha = alpha;
+  stream_rows<K, 1>(geo, wsets, op, smem);
+}
+// alpha.dev = alpha - colMeans(alpha) from the RAW alpha (:187-188), then NaN/Inf alpha -> 0 (:195)
+__global__ void k_init_adev(long long n, int K, const double* colsum, double Gtot, double* alpha, double* adev) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * K) return;
+  int l = (int)(i % K);
+  double a = alpha[i];
+  adev[i] = a - colsum[l] / Gtot;
+  if (!(fabs(a) <= 1.79769313486231570e308)) alpha[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// misc
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill(double* p, long long n, double v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// step[g] *= fac where loglik_old[g] > loglik_new[g]  (R/ruvIIInb.R:490-491)
+__global__ void k_halve(int Gl, const double* ll_old, const double* ll_new, double fac, double* step) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < Gl && ll_old[g] > ll_new[g]) step[g] *= fac;
+}
+// gather rows: dst[i][ncol] = src[idx[i]][ncol]  (idx < 0 -> zeros)
+__global__ void k_gather_rows(const double* src, const int* idx, int n, int ncol, double* dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * ncol) return;
+  int r = (int)(i / ncol), cidx = (int)(i % ncol);
+  int s = idx[r];
+  dst[i] = s >= 0 ? src[(long long)s * ncol + cidx] : 0.0;
+}
+// permute + pad a slab of count rows: dst[r][pos] = pos2cell[pos] >= 0 ? src(r, cell) : -1
+__global__ void k_permute_rows(const int32_t* src, long long rows, long long N, long long src_row_stride,
+                               long long src_cell_stride, const int* pos2cell, long long Np, int32_t* dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Np) return;
+  long long r = i / Np, pos = i - r * Np;
+  int cidx = pos2cell[pos];
+  dst[i] = cidx >= 0 ? src[r * src_row_stride + (long long)cidx * src_cell_stride] : -1;
+}
+__global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// R-layout slab (cells [c0, c0+nc) x all Gh host rows, column-major) -> dst[r][cell2pos[c]].
+// 32 x 32 tile through shared memory: reads coalesced along genes, writes along positions of a row
+// (cells of one group are contiguous after the permutation, so mostly coalesced as well).
+__global__ void k_scatter_cellmajor(const int32_t* stage, long long Gh, const int* rowidx, long long row0, long long rows,
+                                    long long c0, long long nc, const int* cell2pos, long long Np, int32_t* dst) {
+  __shared__ int32_t tile[32][33];
+  const long long rb = (long long)blockIdx.x * 32, cb = (long long)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    long long c = cb + i, r = rb + threadIdx.x;
+    if (c < nc && r < rows) {
+      long long hr = rowidx ? (long long)rowidx[r] : row0 + r;
+      tile[i][threadIdx.x] = stage[c * Gh + hr];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    long long r = rb + i, c = cb + threadIdx.x;
+    if (c < nc && r < rows) dst[r * Np + cell2pos[c0 + c]] = tile[threadIdx.x][i];
+  }
+}
+// CSR expansion: zero the real cells / -1 the pads, then scatter the stored values (warp per row).
+__global__ void k_fill_pad(int32_t* dst, long long rows, long long Np, const int* pos2cell) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * Np) return;
+  dst[i] = pos2cell[i % Np] >= 0 ? 0 : -1;
+}
+__global__ void k_csr_scatter(const long long* indptr, const int32_t* indices, const int32_t* values, long long rows,
+                              long long base, const int* cell2pos, long long Np, int32_t* dst) {
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  for (long long e = indptr[w] - base + lane; e < indptr[w + 1] - base; e += 32) dst[w * Np + cell2pos[indices[e]]] = values[e];
+}

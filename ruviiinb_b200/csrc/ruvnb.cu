@@ -1,0 +1,782 @@
+// ruvnb.cu -- C ABI of libruvnb_b200 (include/ruvnb.h): context, data upload, the NB IRLS operators
+// and the whole-fit driver.  sm_100a only; no CPU fallback anywhere in this file.
+#include "ctx.cuh"
+
+extern "C" {
+
+int ruvnb_abi_version(void) { return RUVNB_ABI_VERSION; }
+
+void ruvnb_opts_default(ruvnb_opts* o) {
+  // defaults of ruvIII.nb (R/ruvIIInb.R:27-28) and its hard-coded constants (:524,533,597)
+  o->k = 2; o->robust = 0; o->lambda_a = 0.01; o->lambda_b = 16.0; o->step_fac = 0.5;
+  o->inner_maxit = 50; o->outer_maxit = 25; o->inner_tol = 1e-4; o->outer_tol = 1e-4; o->psi_tol = 1e-8;
+  o->zinb = 0; o->huber_fastpath = 1; o->verbose = 0;
+}
+
+int ruvnb_create(ruvnb_ctx** out, int device) {
+  if (!out) return RUVNB_EARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return RUVNB_ECUDA;  // no CPU fallback
+  ruvnb_ctx* ctx = new ruvnb_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreate(&ctx->stream) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_flags, 8 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&ctx->h_scal, 16 * sizeof(double)) != cudaSuccess) {
+    delete ctx;
+    return RUVNB_ECUDA;
+  }
+  *out = ctx;
+  return RUVNB_OK;
+}
+
+void ruvnb_destroy(ruvnb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* ruvnb_last_error(const ruvnb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+long long ruvnb_kernel_launches(const ruvnb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- multi-GPU ------------------------------------------------------------------------------------
+int ruvnb_comm_unique_id(unsigned char id[128]) {
+  std::string err;
+  if (!g_nccl.load(&err)) return RUVNB_ENCCL;
+  ncclUniqueId_t u;
+  if (g_nccl.GetUniqueId(&u) != 0) return RUVNB_ENCCL;
+  memcpy(id, u.internal, 128);
+  return RUVNB_OK;
+}
+int ruvnb_comm_init(ruvnb_ctx* ctx, const unsigned char id[128], int rank, int nranks) {
+  if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return RUVNB_EARG;
+  if (nranks == 1) { ctx->rank = 0; ctx->nranks = 1; return RUVNB_OK; }
+  if (!g_nccl.load(&ctx->err)) return RUVNB_ENCCL;
+  CK(cudaSetDevice(ctx->device));
+  ncclUniqueId_t u;
+  memcpy(u.internal, id, 128);
+  int r = g_nccl.CommInitRank(&ctx->comm, nranks, u, rank);
+  if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  ctx->rank = rank; ctx->nranks = nranks;
+  return RUVNB_OK;
+}
+
+// ---- problem set-up -------------------------------------------------------------------------------
+int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t* grp_of_cell, const uint8_t* ctl,
+                     const uint8_t* zeroinf, int64_t g0, int64_t g1) {
+  if (!ctx) return RUVNB_EARG;
+  if (ctx->have_design) return ctx->fail(RUVNB_ESTATE, "design already set: one context holds one problem");
+  if (G <= 0 || N <= 0 || m <= 0 || !grp_of_cell || !ctl || g0 < 0 || g1 > G || g0 >= g1)
+    return ctx->fail(RUVNB_EARG, "set_design: bad sizes G=%lld N=%lld m=%d rows [%lld,%lld)", (long long)G, (long long)N, m, (long long)g0, (long long)g1);
+  if (N > (1ll << 30) || (g1 - g0) > (1ll << 30)) return ctx->fail(RUVNB_EARG, "set_design: N or local G above 2^30");
+  CK(cudaSetDevice(ctx->device));
+  ctx->G = G; ctx->N = N; ctx->m = m; ctx->g0 = g0; ctx->g1 = g1; ctx->Gl = (int)(g1 - g0);
+  ctx->grp.assign(grp_of_cell, grp_of_cell + N);
+  ctx->ctl.assign(ctl, ctl + G);
+  ctx->zeroinf.assign(N, 0);
+  if (zeroinf) { ctx->zeroinf.assign(zeroinf, zeroinf + N); for (auto z : ctx->zeroinf) ctx->any_zeroinf |= (z != 0); }
+  ctx->group_n.assign(m, 0);
+  for (long long c = 0; c < N; ++c) {
+    int j = ctx->grp[c];
+    if (j < 0 || j >= m) return ctx->fail(RUVNB_EARG, "set_design: group label %d of cell %lld outside 0..%d", j, c, m - 1);
+    ctx->group_n[j]++;
+  }
+  // every column of M must be non-empty (R/fastruvIIInb.R:60 stop(); ruvIII.nb's projection would
+  // divide by zero, R/ruvIIInb.R:657-665)
+  for (int j = 0; j < m; ++j)
+    if (ctx->group_n[j] == 0) return ctx->fail(RUVNB_EARG, "set_design: replicate group %d has no cell", j);
+  ctx->group_chunk0.assign(m, 0);
+  int nch = 0;
+  for (int j = 0; j < m; ++j) { ctx->group_chunk0[j] = nch; nch += (ctx->group_n[j] + CH - 1) / CH; }
+  ctx->nchunks = nch; ctx->Np = (long long)nch * CH;
+  ctx->chunk_grp.assign(nch, 0); ctx->chunk_valid.assign(nch, 0);
+  for (int j = 0; j < m; ++j) {
+    int nc = (ctx->group_n[j] + CH - 1) / CH;
+    for (int q = 0; q < nc; ++q) {
+      ctx->chunk_grp[ctx->group_chunk0[j] + q] = j;
+      ctx->chunk_valid[ctx->group_chunk0[j] + q] = std::min(CH, ctx->group_n[j] - q * CH);
+    }
+  }
+  ctx->pos2cell.assign(ctx->Np, -1); ctx->cell2pos.assign(N, 0);
+  std::vector<long long> fill(m);
+  for (int j = 0; j < m; ++j) fill[j] = (long long)ctx->group_chunk0[j] * CH;
+  for (long long c = 0; c < N; ++c) {  // stable: cells keep their order inside a group
+    long long p = fill[ctx->grp[c]]++;
+    ctx->pos2cell[p] = (int)c; ctx->cell2pos[c] = (int)p;
+  }
+  ctx->ctl_gene.clear();
+  for (long long g = 0; g < G; ++g) if (ctx->ctl[g]) ctx->ctl_gene.push_back((int)g);
+  ctx->n_ctl = (int)ctx->ctl_gene.size();
+  if (ctx->n_ctl == 0) return ctx->fail(RUVNB_EARG, "set_design: no control gene");
+  std::vector<int> ctl_local(ctx->n_ctl);
+  for (int i = 0; i < ctx->n_ctl; ++i) {
+    long long g = ctx->ctl_gene[i];
+    ctl_local[i] = (g >= g0 && g < g1) ? (int)(g - g0) : -1;
+  }
+  RET(dev_upload(ctx, &ctx->d_pos2cell, ctx->pos2cell));
+  RET(dev_upload(ctx, &ctx->d_cell2pos, ctx->cell2pos));
+  RET(dev_upload(ctx, &ctx->d_chunk_grp, ctx->chunk_grp));
+  RET(dev_upload(ctx, &ctx->d_chunk_valid, ctx->chunk_valid));
+  RET(dev_upload(ctx, &ctx->d_group_chunk0, ctx->group_chunk0));
+  RET(dev_upload(ctx, &ctx->d_group_n, ctx->group_n));
+  RET(dev_upload(ctx, &ctx->d_ctl_local, ctl_local));
+  RET(dev_alloc(ctx, &ctx->flags, 8));
+  RET(dev_alloc(ctx, &ctx->faillist, ctx->Gl));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_design = true;
+  return RUVNB_OK;
+}
+
+// upload `rows` gene rows (host index list or contiguous range) into dst[rows][Np], permuted + padded
+static int upload_rows(ruvnb_ctx* ctx, const int32_t* Y, int layout, long long nrows_total_host, const int* rowidx,
+                       long long row0, long long rows, int32_t* dst) {
+  const long long N = ctx->N, Np = ctx->Np;
+  if (layout == RUVNB_LAYOUT_GENE_MAJOR) {
+    // slabs of whole rows through a staging buffer (<= 256 MB)
+    long long slab = std::max(1ll, (256ll << 20) / (N * 4));
+    slab = std::min(slab, rows);
+    int32_t* stage = nullptr;
+    CK(cudaMalloc((void**)&stage, (size_t)slab * N * 4));
+    for (long long r0 = 0; r0 < rows; r0 += slab) {
+      long long nr = std::min(slab, rows - r0);
+      if (rowidx) {
+        for (long long r = 0; r < nr; ++r)
+          CK(cudaMemcpyAsync(stage + r * N, Y + (long long)rowidx[r0 + r] * N, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+      } else {
+        CK(cudaMemcpyAsync(stage, Y + (row0 + r0) * N, (size_t)nr * N * 4, cudaMemcpyHostToDevice, ctx->stream));
+      }
+      k_permute_rows<<<nblk(nr * Np, 256), 256, 0, ctx->stream>>>(stage, nr, N, N, 1, ctx->d_pos2cell, Np, dst + r0 * Np);
+      CKL();
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaFree(stage));
+  } else {
+    // R layout: Y[g + Gh*c], Gh = rows of the host matrix.  Slabs of whole cells.
+    const long long Gh = nrows_total_host;
+    long long slab = std::max(1ll, (256ll << 20) / (Gh * 4));
+    slab = std::min(slab, N);
+    int32_t* stage = nullptr;
+    int* d_rowidx = nullptr;
+    CK(cudaMalloc((void**)&stage, (size_t)slab * Gh * 4));
+    if (rowidx) {
+      CK(cudaMalloc((void**)&d_rowidx, (size_t)rows * 4));
+      CK(cudaMemcpyAsync(d_rowidx, rowidx, (size_t)rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // pads first
+    k_fill_i32<<<nblk(rows * Np, 256), 256, 0, ctx->stream>>>(dst, rows * Np, -1);
+    CKL();
+    for (long long c0 = 0; c0 < N; c0 += slab) {
+      long long nc = std::min(slab, N - c0);
+      CK(cudaMemcpyAsync(stage, Y + c0 * Gh, (size_t)nc * Gh * 4, cudaMemcpyHostToDevice, ctx->stream));
+      dim3 grid(nblk(rows, 32), nblk(nc, 32));
+      k_scatter_cellmajor<<<grid, dim3(32, 8), 0, ctx->stream>>>(stage, Gh, d_rowidx, row0, rows, c0, nc, ctx->d_cell2pos, Np, dst);
+      CKL();
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaFree(stage));
+    if (d_rowidx) CK(cudaFree(d_rowidx));
+  }
+  return RUVNB_OK;
+}
+
+int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, const int32_t* Yctl) {
+  if (!ctx || !Y) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "upload_counts: call ruvnb_set_design first");
+  if (layout != RUVNB_LAYOUT_GENE_MAJOR && layout != RUVNB_LAYOUT_CELL_MAJOR) return ctx->fail(RUVNB_EARG, "upload_counts: bad layout %d", layout);
+  CK(cudaSetDevice(ctx->device));
+  const bool sharded = (ctx->Gl != ctx->G);
+  if (sharded && !Yctl) return ctx->fail(RUVNB_EARG, "upload_counts: a gene shard needs the control-gene rows (Yctl)");
+  if (!ctx->dY) RET(dev_alloc(ctx, &ctx->dY, (long long)ctx->Gl * ctx->Np));
+  // Y holds the LOCAL rows (Gl x N)
+  RET(upload_rows(ctx, Y, layout, ctx->Gl, nullptr, 0, ctx->Gl, ctx->dY));
+  std::vector<const int32_t*> rows(ctx->n_ctl);
+  if (sharded) {
+    if (!ctx->dYctl) RET(dev_alloc(ctx, &ctx->dYctl, (long long)ctx->n_ctl * ctx->Np));
+    RET(upload_rows(ctx, Yctl, layout, ctx->n_ctl, nullptr, 0, ctx->n_ctl, ctx->dYctl));
+    for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dYctl + (long long)i * ctx->Np;
+  } else {
+    for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dY + (long long)ctx->ctl_gene[i] * ctx->Np;
+  }
+  if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
+  CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_counts = true;
+  return RUVNB_OK;
+}
+
+int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t* indices, const int32_t* values,
+                            const int64_t* ctl_indptr, const int32_t* ctl_indices, const int32_t* ctl_values) {
+  // CSR rows are expanded on the device into the same padded gene-major int32 tiles the dense path
+  // uses: the IRLS sweeps touch every (gene, cell) pair whatever the sparsity (mu > 0 everywhere), so
+  // the streaming layout stays dense; CSR only saves the host->device transfer.
+  if (!ctx || !indptr || !indices || !values) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "upload_counts: call ruvnb_set_design first");
+  CK(cudaSetDevice(ctx->device));
+  const bool sharded = (ctx->Gl != ctx->G);
+  if (sharded && (!ctl_indptr || !ctl_indices || !ctl_values)) return ctx->fail(RUVNB_EARG, "upload_counts_csr: a gene shard needs the control-gene rows");
+  auto expand = [&](const int64_t* ip, const int32_t* ix, const int32_t* vl, long long rows, int32_t* dst) -> int {
+    long long nnz = ip[rows] - ip[0];
+    long long* d_ip = nullptr; int32_t *d_ix = nullptr, *d_vl = nullptr;
+    CK(cudaMalloc((void**)&d_ip, (size_t)(rows + 1) * 8));
+    CK(cudaMalloc((void**)&d_ix, (size_t)std::max(1ll, nnz) * 4));
+    CK(cudaMalloc((void**)&d_vl, (size_t)std::max(1ll, nnz) * 4));
+    CK(cudaMemcpyAsync(d_ip, ip, (size_t)(rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+      CK(cudaMemcpyAsync(d_ix, ix + ip[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(d_vl, vl + ip[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_fill_pad<<<nblk(rows * ctx->Np, 256), 256, 0, ctx->stream>>>(dst, rows, ctx->Np, ctx->d_pos2cell);
+    CKL();
+    k_csr_scatter<<<nblk(rows * 32, 256), 256, 0, ctx->stream>>>(d_ip, d_ix, d_vl, rows, ip[0], ctx->d_cell2pos, ctx->Np, dst);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d_ip)); CK(cudaFree(d_ix)); CK(cudaFree(d_vl));
+    return RUVNB_OK;
+  };
+  if (!ctx->dY) RET(dev_alloc(ctx, &ctx->dY, (long long)ctx->Gl * ctx->Np));
+  RET(expand(indptr, indices, values, ctx->Gl, ctx->dY));
+  std::vector<const int32_t*> rows(ctx->n_ctl);
+  if (sharded) {
+    if (!ctx->dYctl) RET(dev_alloc(ctx, &ctx->dYctl, (long long)ctx->n_ctl * ctx->Np));
+    RET(expand(ctl_indptr, ctl_indices, ctl_values, ctx->n_ctl, ctx->dYctl));
+    for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dYctl + (long long)i * ctx->Np;
+  } else {
+    for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dY + (long long)ctx->ctl_gene[i] * ctx->Np;
+  }
+  if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
+  CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_counts = true;
+  return RUVNB_OK;
+}
+
+}  // extern "C"
+
+// ---- state ----------------------------------------------------------------------------------------
+static int alloc_set(ruvnb_ctx* ctx, StateSet* s) {
+  const long long Gl = ctx->Gl;
+  RET(dev_alloc(ctx, &s->gmean, Gl));
+  RET(dev_alloc(ctx, &s->Mb, Gl * ctx->m));
+  RET(dev_alloc(ctx, &s->alpha, Gl * ctx->K));
+  RET(dev_alloc(ctx, &s->adev, Gl * ctx->K));
+  RET(dev_alloc(ctx, &s->W, ctx->Np * ctx->K));
+  RET(dev_alloc(ctx, &s->psi, Gl));
+  RET(dev_alloc(ctx, &s->pi0, Gl));
+  CK(cudaMemsetAsync(s->gmean, 0, Gl * 8, ctx->stream));
+  CK(cudaMemsetAsync(s->Mb, 0, Gl * ctx->m * 8, ctx->stream));
+  CK(cudaMemsetAsync(s->alpha, 0, Gl * ctx->K * 8, ctx->stream));
+  CK(cudaMemsetAsync(s->adev, 0, Gl * ctx->K * 8, ctx->stream));
+  CK(cudaMemsetAsync(s->W, 0, ctx->Np * ctx->K * 8, ctx->stream));
+  CK(cudaMemsetAsync(s->pi0, 0, Gl * 8, ctx->stream));
+  k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(s->psi, Gl, 1.0);
+  CKL();
+  return RUVNB_OK;
+}
+
+static int ensure_state(ruvnb_ctx* ctx, int K) {
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "call ruvnb_set_design first");
+  if (K < 1 || K > RUVNB_MAX_K) return ctx->fail(RUVNB_EARG, "k = %d outside 1..%d", K, RUVNB_MAX_K);
+  if (ctx->K == K) return RUVNB_OK;
+  if (ctx->K != 0) return ctx->fail(RUVNB_ESTATE, "k changed from %d to %d: one context holds one problem", ctx->K, K);
+  CK(cudaSetDevice(ctx->device));
+  ctx->K = K;
+  const long long Gl = ctx->Gl, m = ctx->m;
+  const int KK = K * (K + 1) / 2;
+  RET(alloc_set(ctx, &ctx->cur));
+  RET(alloc_set(ctx, &ctx->nw));
+  RET(alloc_set(ctx, &ctx->best));
+  RET(dev_alloc(ctx, &ctx->step, Gl));
+  RET(dev_alloc(ctx, &ctx->loglik, Gl));
+  RET(dev_alloc(ctx, &ctx->loglik_tmp, Gl));
+  k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0);
+  CKL();
+  CK(cudaMemsetAsync(ctx->loglik, 0, Gl * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->loglik_tmp, 0, Gl * 8, ctx->stream));
+  RET(dev_alloc(ctx, &ctx->A, Gl * KK));
+  RET(dev_alloc(ctx, &ctx->u, Gl * K));
+  RET(dev_alloc(ctx, &ctx->sw, Gl));
+  RET(dev_alloc(ctx, &ctx->ZS, Gl * m));
+  RET(dev_alloc(ctx, &ctx->VS, Gl * m * K));
+  RET(dev_alloc(ctx, &ctx->cvec, Gl * K));
+  RET(dev_alloc(ctx, &ctx->Ab, Gl * (KK + K)));
+  RET(dev_alloc(ctx, &ctx->red, 64));
+  RET(dev_alloc(ctx, &ctx->amean, K));
+  RET(dev_alloc(ctx, &ctx->S0, Gl * m));
+  RET(dev_alloc(ctx, &ctx->S1, Gl * m));
+  RET(dev_alloc(ctx, &ctx->sigma, Gl));
+  RET(dev_alloc(ctx, &ctx->Wbar, m * K));
+  RET(dev_alloc(ctx, &ctx->RMW, ctx->Np * K));
+  RET(dev_alloc(ctx, &ctx->sumsq, K));
+  RET(dev_alloc(ctx, &ctx->med, K));
+  RET(dev_alloc(ctx, &ctx->mad, K));
+  RET(dev_alloc(ctx, &ctx->ctlpack, (long long)ctx->n_ctl * (3 + 2 * K + m)));
+  RET(dev_alloc(ctx, &ctx->scal, 16));
+  if (ctx->nranks > 1) RET(dev_alloc(ctx, &ctx->alpha_full, ctx->G * K));
+  return RUVNB_OK;
+}
+
+enum StateKind { SK_VEC, SK_GK, SK_GM, SK_W };
+static int state_lookup(ruvnb_ctx* ctx, const char* name, double** p, StateKind* kind) {
+  StateSet& s = ctx->cur;
+  if (!strcmp(name, "W")) { *p = s.W; *kind = SK_W; }
+  else if (!strcmp(name, "alpha")) { *p = s.alpha; *kind = SK_GK; }
+  else if (!strcmp(name, "alpha_dev")) { *p = s.adev; *kind = SK_GK; }
+  else if (!strcmp(name, "gmean")) { *p = s.gmean; *kind = SK_VEC; }
+  else if (!strcmp(name, "Mb")) { *p = s.Mb; *kind = SK_GM; }
+  else if (!strcmp(name, "psi")) { *p = s.psi; *kind = SK_VEC; }
+  else if (!strcmp(name, "pi0")) { *p = s.pi0; *kind = SK_VEC; }
+  else if (!strcmp(name, "step")) { *p = ctx->step; *kind = SK_VEC; }
+  else if (!strcmp(name, "loglik")) { *p = ctx->loglik; *kind = SK_VEC; }
+  else if (!strcmp(name, "sigma")) { *p = ctx->sigma; *kind = SK_VEC; }
+  else return ctx->fail(RUVNB_EARG, "unknown state name '%s'", name);
+  return RUVNB_OK;
+}
+
+extern "C" {
+
+int ruvnb_set_state(ruvnb_ctx* ctx, const char* name, const double* host, int k) {
+  if (!ctx || !name || !host) return RUVNB_EARG;
+  if (k > 0) RET(ensure_state(ctx, k));
+  if (ctx->K == 0) return ctx->fail(RUVNB_ESTATE, "set_state: k unknown -- set \"W\" first (with k)");
+  CK(cudaSetDevice(ctx->device));
+  double* p; StateKind kind;
+  RET(state_lookup(ctx, name, &p, &kind));
+  const long long Gl = ctx->Gl, K = ctx->K, m = ctx->m, N = ctx->N, Np = ctx->Np;
+  std::vector<double> tmp;
+  switch (kind) {
+    case SK_VEC: tmp.assign(host, host + Gl); break;
+    case SK_GK: tmp.resize(Gl * K); for (long long g = 0; g < Gl; ++g) for (long long l = 0; l < K; ++l) tmp[g * K + l] = host[g + Gl * l]; break;
+    case SK_GM: tmp.resize(Gl * m); for (long long g = 0; g < Gl; ++g) for (long long j = 0; j < m; ++j) tmp[g * m + j] = host[g + Gl * j]; break;
+    case SK_W:
+      tmp.assign(Np * K, 0.0);
+      for (long long l = 0; l < K; ++l) for (long long c = 0; c < N; ++c) tmp[l * Np + ctx->cell2pos[c]] = host[c + N * l];
+      ctx->have_W = true;
+      break;
+  }
+  CK(cudaMemcpyAsync(p, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
+
+int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host) {
+  if (!ctx || !name || !host) return RUVNB_EARG;
+  if (ctx->K == 0) return ctx->fail(RUVNB_ESTATE, "get_state: no state yet");
+  CK(cudaSetDevice(ctx->device));
+  double* p; StateKind kind;
+  RET(state_lookup(ctx, name, &p, &kind));
+  const long long Gl = ctx->Gl, K = ctx->K, m = ctx->m, N = ctx->N, Np = ctx->Np;
+  long long n = kind == SK_VEC ? Gl : kind == SK_GK ? Gl * K : kind == SK_GM ? Gl * m : Np * K;
+  std::vector<double> tmp(n);
+  CK(cudaMemcpyAsync(tmp.data(), p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  switch (kind) {
+    case SK_VEC: memcpy(host, tmp.data(), Gl * 8); break;
+    case SK_GK: for (long long g = 0; g < Gl; ++g) for (long long l = 0; l < K; ++l) host[g + Gl * l] = tmp[g * K + l]; break;
+    case SK_GM: for (long long g = 0; g < Gl; ++g) for (long long j = 0; j < m; ++j) host[g + Gl * j] = tmp[g * m + j]; break;
+    case SK_W: for (long long l = 0; l < K; ++l) for (long long c = 0; c < N; ++c) host[c + N * l] = tmp[l * Np + ctx->cell2pos[c]]; break;
+  }
+  return RUVNB_OK;
+}
+
+}  // extern "C"
+
+// ---- launch helpers ---------------------------------------------------------------------------------
+static RowGeom geom(ruvnb_ctx* ctx, int nrows, const int* rowlist) {
+  RowGeom g;
+  g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid;
+  g.nrows = nrows; g.rowlist = rowlist;
+  return g;
+}
+template <int K>
+static GeneState<K> gstate(ruvnb_ctx* ctx, const StateSet& s, bool with_step) {
+  GeneState<K> st;
+  st.gmean = s.gmean; st.Mb = s.Mb; st.alpha = s.alpha; st.psi = s.psi; st.step = with_step ? ctx->step : nullptr; st.W = s.W; st.m = ctx->m;
+  return st;
+}
+static inline size_t tile_smem(int K, int nsets) { return (size_t)2 * nsets * K * CH * sizeof(double); }
+static inline unsigned row_grid(int nrows) { return (unsigned)((nrows + NWARP - 1) / NWARP); }
+
+static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
+  if (!ctx || !o) return RUVNB_EARG;
+  if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "no counts uploaded");
+  RET(ensure_state(ctx, o->k));
+  if (!ctx->have_W) return ctx->fail(RUVNB_ESTATE, "W not set: the initial W (irlba in the reference, R/ruvIIInb.R:167) is injected with ruvnb_set_state(\"W\")");
+  if (o->zinb && ctx->any_zeroinf) return ctx->fail(RUVNB_ESTATE, "ZINB kernels are not part of this build yet (SURVEY.md section 8, rows H4/H5)");
+  CK(cudaSetDevice(ctx->device));
+  return RUVNB_OK;
+}
+
+// per-gene log-likelihood of parameter set `s` into `out`; total (all ranks) into *total if non-null
+static int loglik_of(ruvnb_ctx* ctx, const StateSet& s, double* out, double* total) {
+  DISPATCH_K(ctx->K, {
+    k_loglik<KT><<<row_grid(ctx->Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), out);
+    CKL();
+  });
+  if (total) {
+    k_colsum<<<1, 1024, 0, ctx->stream>>>(out, ctx->Gl, 1, ctx->scal);
+    CKL();
+    RET(allreduce(ctx, ctx->scal, 1, NCCL_F64));
+    CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total = ctx->h_scal[0];
+  }
+  return RUVNB_OK;
+}
+
+// sigma_g for every local row of `s`: +Inf where the certificate proves all Huber weights are 1,
+// else the exact mad/0.6745 (R/ruvIIInb.R:713).  *nfail = rows that needed the exact path.
+static int row_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, const StateSet& s, double kh, int* nfail) {
+  const int Gl = ctx->Gl;
+  CK(cudaMemsetAsync(ctx->flags + 4, 0, sizeof(int), ctx->stream));
+  if (o->huber_fastpath) {
+    DISPATCH_K(ctx->K, {
+      k_devstats<KT><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, Gl, nullptr), gstate<KT>(ctx, s, false), kh, ctx->sigma, ctx->flags + 4);
+      CKL();
+    });
+  } else {
+    CK(cudaMemsetAsync(ctx->sigma, 0, (size_t)Gl * 8, ctx->stream));  // 0 == "not certified"
+  }
+  k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, ctx->sigma, ctx->faillist, ctx->flags + 4);
+  CKL();
+  CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const int nf = ctx->h_flags[4];
+  *nfail = nf;
+  if (nf == 0) return RUVNB_OK;
+  // exact path in batches of rows through the deviance scratch (<= 2 GB)
+  long long batch = std::max(8ll, (2ll << 30) / (ctx->Np * 8));
+  batch = std::min<long long>(batch, nf);
+  if (ctx->D_rows < batch) {
+    RET(dev_alloc(ctx, &ctx->D, batch * ctx->Np));  // grows at most once per problem (first call sizes it)
+    ctx->D_rows = batch;
+  }
+  for (long long r0 = 0; r0 < nf; r0 += ctx->D_rows) {
+    int nr = (int)std::min<long long>(ctx->D_rows, nf - r0);
+    DISPATCH_K(ctx->K, {
+      k_signdev<KT><<<row_grid(nr), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, nr, ctx->faillist + r0), gstate<KT>(ctx, s, false), ctx->D);
+      CKL();
+    });
+    k_row_sigma<<<nr, 256, 0, ctx->stream>>>(ctx->D, ctx->Np, ctx->d_chunk_valid, ctx->faillist + r0, ctx->sigma, nullptr);
+    CKL();
+  }
+  return RUVNB_OK;
+}
+
+// RM_W = W - groupmean(W) (R/ruvIIInb.R:331-340)
+static int make_rmw(ruvnb_ctx* ctx, const double* W) {
+  const int K = ctx->K, m = ctx->m;
+  k_wbar<<<nblk((long long)K * m * 32, 256), 256, 0, ctx->stream>>>(W, ctx->Np, K, m, ctx->d_group_chunk0, ctx->d_group_n, ctx->Wbar);
+  CKL();
+  k_rmw<<<nblk(ctx->Np * K, 256), 256, 0, ctx->stream>>>(W, ctx->Np, K, ctx->d_chunk_grp, ctx->d_chunk_valid, ctx->Wbar, ctx->RMW);
+  CKL();
+  return RUVNB_OK;
+}
+
+// one pass of the inner-loop body, R/ruvIIInb.R:303-484.  cur -> nw, then the two sets swap.
+static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
+  const int Gl = ctx->Gl, K = ctx->K, m = ctx->m, KK = K * (K + 1) / 2;
+  const double kh = o->robust ? 1.345 : 100.0;  // :155
+  StateSet& c = ctx->cur; StateSet& n = ctx->nw;
+  CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
+  // Huber scale of the current state (:713,723,409)
+  int nfail = 0;
+  RET(row_sigma(ctx, o, c, kh, &nfail));
+  ctx->last_fail_rows = nfail;
+  const bool hub = nfail > 0;
+  // alpha ------------------------------------------------------------------------------------------
+  RET(make_rmw(ctx, c.W));
+  DISPATCH_K(K, {
+    auto st = gstate<KT>(ctx, c, true);
+    if (hub) k_pass1<KT, true><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, ctx->RMW, ctx->sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    else k_pass1<KT, false><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, ctx->RMW, ctx->sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    CKL();
+    k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
+    CKL();
+    k_colsum<<<1, 1024, 0, ctx->stream>>>(ctx->Ab, Gl, KK + K, ctx->red);
+    CKL();
+    RET(allreduce(ctx, ctx->red, KK + K, NCCL_F64));
+    k_alpha_mean<KT><<<1, 32, 0, ctx->stream>>>(ctx->red, ctx->amean);
+    CKL();
+    k_adev<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, ctx->A, ctx->cvec, ctx->amean, o->lambda_a, n.alpha, n.adev, ctx->flags + 0);
+    CKL();
+  });
+  RET(allreduce(ctx, ctx->flags, 1, NCCL_INT32));
+  k_revert_if<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(ctx->flags + 0, n.alpha, c.alpha, (long long)Gl * K);  // :368
+  CKL();
+  // clamp each column to median +- 4 mad over ALL genes (:371-376)
+  if (ctx->nranks > 1) {
+    CK(cudaMemsetAsync(ctx->alpha_full, 0, (size_t)ctx->G * K * 8, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->alpha_full + ctx->g0 * K, n.alpha, (size_t)Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    RET(allreduce(ctx, ctx->alpha_full, (size_t)ctx->G * K, NCCL_F64));
+    k_strided_medmad<<<K, 256, 0, ctx->stream>>>(ctx->alpha_full, 1, K, (int)ctx->G, ctx->med, ctx->mad);
+  } else {
+    k_strided_medmad<<<K, 256, 0, ctx->stream>>>(n.alpha, 1, K, Gl, ctx->med, ctx->mad);
+  }
+  CKL();
+  k_clamp_cols<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(n.alpha, Gl, K, ctx->med, ctx->mad);
+  CKL();
+  // W ------------------------------------------------------------------------------------------------
+  {
+    const int nc = ctx->n_ctl;
+    double* pk = ctx->ctlpack;
+    CtlPack cp;
+    double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
+    double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
+    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.gmean, ctx->d_ctl_local, nc, 1, p_gmean); CKL();
+    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.psi, ctx->d_ctl_local, nc, 1, p_psi); CKL();
+    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(ctx->step, ctx->d_ctl_local, nc, 1, p_step); CKL();
+    k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(c.alpha, ctx->d_ctl_local, nc, K, p_aold); CKL();
+    k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(n.alpha, ctx->d_ctl_local, nc, K, p_anew); CKL();
+    k_gather_rows<<<nblk((long long)nc * m, 256), 256, 0, ctx->stream>>>(c.Mb, ctx->d_ctl_local, nc, m, p_mb); CKL();
+    RET(allreduce(ctx, pk, (size_t)nc * (3 + 2 * K + m), NCCL_F64));
+    cp.gmean = p_gmean; cp.psi = p_psi; cp.step = p_step; cp.alpha_old = p_aold; cp.alpha_new = p_anew; cp.Mb = p_mb;
+    // cells per CTA: the per-cell deviance rows of all control genes must fit shared memory
+    const int NACC = KK + K;
+    int cpc = 32;
+    const long long nstr = nc | 1;
+    while (cpc > 1 && (size_t)cpc * nstr * 8 > (size_t)200 * 1024) cpc >>= 1;
+    if ((size_t)cpc * nstr * 8 > (size_t)200 * 1024) return ctx->fail(RUVNB_ENOMEM, "n_ctl = %d control genes exceed the per-cell shared-memory tile (max 25600)", nc);
+    size_t smem = std::max<size_t>((size_t)cpc * (size_t)nstr * 8, (size_t)8 * cpc * NACC * 8);
+    // cells are sharded over the ranks in whole chunks; the slices are summed (disjoint) afterwards
+    long long ch_per = (ctx->nchunks + ctx->nranks - 1) / ctx->nranks;
+    long long pb = std::min<long long>(ctx->Np, ch_per * ctx->rank * CH), pe = std::min<long long>(ctx->Np, ch_per * (ctx->rank + 1) * CH);
+    if (ctx->nranks > 1) CK(cudaMemsetAsync(n.W, 0, (size_t)ctx->Np * K * 8, ctx->stream));
+    if (pe > pb) {
+      DISPATCH_K(K, {
+        CK(cudaFuncSetAttribute(k_w_update<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_w_update<KT, true><<<nblk(pe - pb, cpc), 256, smem, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, m, c.W, n.W, cpc, kh, pb, pe);
+        CKL();
+      });
+    }
+    RET(allreduce(ctx, n.W, (size_t)ctx->Np * K, NCCL_F64));
+    k_w_sumsq<<<K, 1024, 0, ctx->stream>>>(n.W, ctx->Np, ctx->sumsq); CKL();
+    k_w_scale<<<nblk(ctx->Np * K, 256), 256, 0, ctx->stream>>>(n.W, ctx->Np, K, ctx->sumsq, ctx->d_chunk_valid, ctx->flags + 1); CKL();
+    k_revert_if<<<nblk(ctx->Np * K, 256), 256, 0, ctx->stream>>>(ctx->flags + 1, n.W, c.W, ctx->Np * K); CKL();  // :402
+  }
+  // gmean, Mb ------------------------------------------------------------------------------------------
+  DISPATCH_K(K, {
+    auto st = gstate<KT>(ctx, c, true);
+    if (hub) k_pass2<KT, true><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, n.W, n.alpha, ctx->sigma, kh, ctx->S0, ctx->S1);
+    else k_pass2<KT, false><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, n.W, n.alpha, ctx->sigma, kh, ctx->S0, ctx->S1);
+    CKL();
+  });
+  k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
+  RET(allreduce(ctx, ctx->flags + 2, 2, NCCL_INT32));
+  k_mb_finalize<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, m, ctx->flags + 3, c.Mb, n.Mb); CKL();
+  // psi, pi0 unchanged inside the inner loop
+  CK(cudaMemcpyAsync(n.psi, c.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  // candidate log-likelihood (:469-484)
+  RET(loglik_of(ctx, n, ctx->loglik_tmp, logl_new));
+  CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad) { bad[0] = ctx->h_flags[0]; bad[1] = ctx->h_flags[1]; bad[2] = ctx->h_flags[2]; }
+  std::swap(ctx->cur, ctx->nw);
+  return RUVNB_OK;
+}
+
+static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
+  const size_t Gl = ctx->Gl, K = ctx->K, m = ctx->m;
+  CK(cudaMemcpyAsync(dst.gmean, src.gmean, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.Mb, src.Mb, Gl * m * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.alpha, src.alpha, Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.adev, src.adev, Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.W, src.W, (size_t)ctx->Np * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.psi, src.psi, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.pi0, src.pi0, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return RUVNB_OK;
+}
+
+extern "C" {
+
+int ruvnb_init_coef(ruvnb_ctx* ctx, const ruvnb_opts* o) {
+  RET(check_ready(ctx, o));
+  const int Gl = ctx->Gl, K = ctx->K;
+  StateSet& c = ctx->cur;
+  DISPATCH_K(K, {
+    k_init_coef<KT><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, Gl, nullptr), c.W, c.gmean, c.alpha);
+    CKL();
+  });
+  // alpha.dev = alpha - colMeans(alpha) over ALL genes (:187-188), then NaN/Inf alpha -> 0 (:195)
+  k_colsum<<<1, 1024, 0, ctx->stream>>>(c.alpha, Gl, K, ctx->red); CKL();
+  RET(allreduce(ctx, ctx->red, K, NCCL_F64));
+  k_init_adev<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(Gl, K, ctx->red, (double)ctx->G, c.alpha, c.adev); CKL();
+  CK(cudaMemsetAsync(c.Mb, 0, (size_t)Gl * ctx->m * 8, ctx->stream));  // :191
+  CK(cudaMemsetAsync(c.pi0, 0, (size_t)Gl * 8, ctx->stream));         // :202
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
+
+int ruvnb_loglik(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total) {
+  RET(check_ready(ctx, o));
+  return loglik_of(ctx, ctx->cur, ctx->loglik, total);
+}
+
+int ruvnb_irls_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
+  RET(check_ready(ctx, o));
+  double t = 0.0;
+  RET(irls_body(ctx, o, &t, bad));
+  if (logl_new) *logl_new = t;
+  return RUVNB_OK;
+}
+
+int ruvnb_snapshot_best(ruvnb_ctx* ctx) {
+  if (!ctx || ctx->K == 0) return RUVNB_EARG;
+  CK(cudaSetDevice(ctx->device));
+  RET(copy_set(ctx, ctx->best, ctx->cur));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
+int ruvnb_restore_best(ruvnb_ctx* ctx) {
+  if (!ctx || ctx->K == 0) return RUVNB_EARG;
+  CK(cudaSetDevice(ctx->device));
+  RET(copy_set(ctx, ctx->cur, ctx->best));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
+int ruvnb_halve_steps(ruvnb_ctx* ctx, const ruvnb_opts* o) {
+  if (!ctx || !o || ctx->K == 0) return RUVNB_EARG;
+  CK(cudaSetDevice(ctx->device));
+  k_halve<<<nblk(ctx->Gl, 256), 256, 0, ctx->stream>>>(ctx->Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();
+  return RUVNB_OK;
+}
+// accept the candidate: loglik <- loglik.tmp (:512)
+int ruvnb_accept(ruvnb_ctx* ctx) {
+  if (!ctx || ctx->K == 0) return RUVNB_EARG;
+  std::swap(ctx->loglik, ctx->loglik_tmp);
+  return RUVNB_OK;
+}
+
+// ---- the whole fit: R/ruvIIInb.R:266-609 ------------------------------------------------------------
+int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const double* psi_inject, int n_psi,
+                 ruvnb_trace_rec* trace, int trace_cap, double* logl_outer, ruvnb_fit_stats* stats) {
+  if (!ctx || !o) return RUVNB_EARG;
+  if (W0) RET(ruvnb_set_state(ctx, "W", W0, o->k));
+  RET(check_ready(ctx, o));
+  cudaEvent_t e0, e1, t0, t1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1));
+  const long long launches0 = ctx->launches;
+  CK(cudaEventRecord(t0, ctx->stream));
+  const int Gl = ctx->Gl;
+  double inner_ms = 0.0, disp_ms = 0.0;
+  int n_trace = 0, n_inner = 0, psi_used = 0, exact_rows = 0;
+  auto refresh_psi = [&](StateSet& target) -> int {
+    // the dispersion routine is an injection seam (edgeR/limma/locfit arithmetic)
+    if (psi_inject && n_psi > 0) {
+      const double* src = psi_inject + (long long)std::min(psi_used, n_psi - 1) * Gl;
+      psi_used++;
+      std::vector<double> tmp(Gl), old(Gl);
+      CK(cudaMemcpyAsync(old.data(), target.psi, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      for (int g = 0; g < Gl; ++g) tmp[g] = std::isfinite(src[g]) ? src[g] : old[g];  // :564
+      CK(cudaMemcpyAsync(target.psi, tmp.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      return RUVNB_OK;
+    }
+    cudaEvent_t d0, d1;
+    CK(cudaEventCreate(&d0)); CK(cudaEventCreate(&d1));
+    CK(cudaEventRecord(d0, ctx->stream));
+    // estimate on the parameters held in `target` (offset = alpha W' + Mb[,grp], :535-536)
+    if (&target != &ctx->cur) std::swap(ctx->cur, target);
+    int r = ruvnb_estimate_disp(ctx, o, nullptr);
+    if (&target != &ctx->cur) std::swap(ctx->cur, target);
+    RET(r);
+    CK(cudaEventRecord(d1, ctx->stream));
+    CK(cudaEventSynchronize(d1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, d0, d1)); disp_ms += ms;
+    CK(cudaEventDestroy(d0)); CK(cudaEventDestroy(d1));
+    return RUVNB_OK;
+  };
+  // initial estimates (:173-221)
+  RET(ruvnb_init_coef(ctx, o));
+  RET(refresh_psi(ctx->cur));
+  k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :270
+  bool conv = false;
+  int iter_outer = 0;
+  std::vector<double> lo;
+  while (!conv) {
+    iter_outer++;
+    std::vector<double> logl_beta;
+    double s_old = 0.0;
+    RET(loglik_of(ctx, ctx->cur, ctx->loglik, &s_old));  // :276-291
+    k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :293
+    RET(copy_set(ctx, ctx->best, ctx->cur));                                    // :296
+    int iter = 1, halving = 0;
+    bool conv_beta = false;
+    CK(cudaEventRecord(e0, ctx->stream));
+    while (!conv_beta) {
+      if (o->verbose) fprintf(stderr, "Inner iter:%d\n", iter);
+      double s_new = 0.0; int bad[3] = {0, 0, 0};
+      RET(irls_body(ctx, o, &s_new, bad));
+      n_inner++;
+      exact_rows += ctx->last_fail_rows;
+      bool degener = !(std::isfinite(s_old) && std::isfinite(s_new)) || (s_old > s_new);  // :487-488
+      ruvnb_trace_rec rec;
+      rec.outer = iter_outer; rec.iter = iter; rec.halving = halving; rec.degener = degener ? 1 : 0;
+      rec.logl_old = s_old; rec.logl_new = s_new; rec.bad_alpha = bad[0]; rec.bad_W = bad[1]; rec.bad_Mb = bad[2];
+      if (degener) {
+        k_halve<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();  // :490-491
+        RET(copy_set(ctx, ctx->cur, ctx->best));  // :492
+        halving++;
+        if (halving >= 3) { degener = false; }    // :506-509: loglik.tmp <- loglik, accept the restored state
+      } else {
+        std::swap(ctx->loglik, ctx->loglik_tmp);  // :512
+        s_old = s_new;
+      }
+      if (!degener) {
+        logl_beta.push_back(s_old);               // :513
+        RET(copy_set(ctx, ctx->best, ctx->cur));  // :516
+        iter++; halving = 0;
+        if (o->verbose) fprintf(stderr, "Outer Iter %d, Inner iter %d logl-likelihood:%.10g\n", iter_outer, iter - 1, s_old);
+      }
+      rec.accepted = degener ? 0 : 1;
+      rec.logl = logl_beta.empty() ? NAN : logl_beta.back();
+      if (trace && n_trace < trace_cap) trace[n_trace++] = rec;
+      bool conv_logl = false;
+      if (iter > 2) {  // :523-525
+        size_t L = logl_beta.size();
+        conv_logl = (logl_beta[L - 1] - logl_beta[L - 2]) / fabs(logl_beta[L - 2]) < o->inner_tol;
+      }
+      conv_beta = iter >= o->inner_maxit || conv_logl;
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    { float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1)); inner_ms += ms; }
+    // psi update (:529-565)
+    double logl_outer_tmp = s_old;
+    bool updt = true;
+    if (iter_outer > 1) updt = fabs(lo.back() - logl_outer_tmp) / fabs(lo.back()) > o->psi_tol;
+    RET(copy_set(ctx, ctx->cur, ctx->best));  // :568-573
+    if (updt) RET(refresh_psi(ctx->cur));
+    double s = 0.0;
+    RET(loglik_of(ctx, ctx->cur, ctx->loglik, &s));  // :577-593
+    lo.push_back(s);
+    if (logl_outer && iter_outer <= o->outer_maxit) logl_outer[iter_outer - 1] = s;
+    if (o->verbose) fprintf(stderr, "Outer Iter %d logl-likelihood:%.10g\n", iter_outer, s);
+    if (iter_outer > 1) {
+      size_t L = lo.size();
+      conv = ((lo[L - 1] - lo[L - 2]) / fabs(lo[L - 2]) < o->outer_tol) || iter_outer >= o->outer_maxit;  // :596-598
+    }
+  }
+  CK(cudaEventRecord(t1, ctx->stream));
+  CK(cudaEventSynchronize(t1));
+  if (stats) {
+    float ms = 0; CK(cudaEventElapsedTime(&ms, t0, t1));
+    stats->n_outer = iter_outer; stats->n_inner = n_inner; stats->n_trace = n_trace;
+    stats->inner_seconds = inner_ms * 1e-3; stats->disp_seconds = disp_ms * 1e-3; stats->total_seconds = ms * 1e-3;
+    stats->kernel_launches = ctx->launches - launches0;
+    stats->n_exact_mad_rows = exact_rows; stats->n_exact_mad_cells = (int)std::min<long long>(ctx->N * (long long)n_inner, 2147483647ll);
+  }
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1)); CK(cudaEventDestroy(t0)); CK(cudaEventDestroy(t1));
+  return RUVNB_OK;
+}
+
+}  // extern "C"
+#include "stubs.cuh"

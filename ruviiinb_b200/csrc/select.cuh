@@ -1,0 +1,127 @@
+// select.cuh -- exact order statistics (median, MAD) by 8-bit radix select on order-preserving
+// 64-bit keys.  R semantics restated: stats::median (mean of the two middle order statistics for
+// even n, NA if any NaN) and stats::mad = 1.4826 * median(|x - median(x)|), as used at
+// R/ruvIIInb.R:371-372,409,428-429,713,723,734.
+#pragma once
+#include "common.cuh"
+
+#define MAD_CONST 1.4826
+
+template <int NT>
+__device__ __forceinline__ void group_sync() {
+  if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
+// Scratch a group needs in shared memory.
+struct SelScratch {
+  unsigned int hist[256];
+  unsigned long long s0, s1;
+  unsigned long long red[32];
+};
+
+template <int NT>
+__device__ __forceinline__ unsigned long long group_max_ull(unsigned long long v, SelScratch* sc, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t = __shfl_xor_sync(FULL, v, o);
+    v = t > v ? t : v;
+  }
+  if (NT == 32) return v;
+  group_sync<NT>();
+  if ((tid & 31) == 0) sc->red[tid >> 5] = v;
+  group_sync<NT>();
+  unsigned long long r = 0;
+  for (int w = 0; w < NT / 32; ++w) r = sc->red[w] > r ? sc->red[w] : r;
+  group_sync<NT>();
+  return r;
+}
+template <int NT>
+__device__ __forceinline__ unsigned long long group_sum_ull(unsigned long long v, SelScratch* sc, int tid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  if (NT == 32) return v;
+  group_sync<NT>();
+  if ((tid & 31) == 0) sc->red[tid >> 5] = v;
+  group_sync<NT>();
+  unsigned long long r = 0;
+  for (int w = 0; w < NT / 32; ++w) r += sc->red[w];
+  group_sync<NT>();
+  return r;
+}
+
+// kth (0-based) smallest key among the valid items i in [0,len); get(i, key) returns false for
+// items to skip.  All NT threads of the group call it with the same arguments.
+template <int NT, class Get>
+__device__ unsigned long long group_select_kth(int len, long long kth, Get get, SelScratch* sc, int tid) {
+  unsigned long long prefix = 0, pmask = 0;
+  for (int pass = 7; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    for (int i = tid; i < 256; i += NT) sc->hist[i] = 0;
+    group_sync<NT>();
+    for (int i0 = 0; i0 < len; i0 += NT) {
+      int i = i0 + tid;
+      unsigned long long key = 0;
+      bool ok = (i < len) && get(i, key) && ((key & pmask) == prefix);
+      int b = ok ? (int)((key >> shift) & 255ull) : 256 + (tid & 31);  // distinct dummy per lane
+      // warp-aggregated histogram update: one atomic per distinct bucket in the warp
+      unsigned peers = __match_any_sync(FULL, b);
+      if (ok && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
+    }
+    group_sync<NT>();
+    if (tid == 0) {
+      long long acc = 0;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (acc + (long long)sc->hist[b] > kth) break;
+        acc += sc->hist[b];
+      }
+      sc->s0 = (unsigned long long)b;
+      sc->s1 = (unsigned long long)acc;
+    }
+    group_sync<NT>();
+    prefix |= sc->s0 << shift;
+    pmask |= 0xffull << shift;
+    kth -= (long long)sc->s1;
+    group_sync<NT>();
+  }
+  return prefix;
+}
+
+// R median of the valid items (n = number of valid items; caller guarantees no NaN among them).
+template <int NT, class Get>
+__device__ double group_median(int len, long long n, Get get, SelScratch* sc, int tid) {
+  if (n <= 0) return __longlong_as_double(0x7ff8000000000000ll);
+  unsigned long long up = group_select_kth<NT>(len, n / 2, get, sc, tid);
+  double hi = key_f64(up);
+  if (n & 1) return hi;
+  // lower middle: the largest key below `up` if exactly n/2 keys are below it, else `up` itself
+  unsigned long long cl = 0, ml = 0;
+  for (int i = tid; i < len; i += NT) {
+    unsigned long long key;
+    if (get(i, key) && key < up) { cl++; ml = key > ml ? key : ml; }
+  }
+  cl = group_sum_ull<NT>(cl, sc, tid);
+  ml = group_max_ull<NT>(ml, sc, tid);
+  double lo = (cl == (unsigned long long)(n / 2)) ? key_f64(ml) : hi;
+  return (lo + hi) / 2.0;  // R: mean(c(lo, hi))
+}
+
+// median and mad (already x1.4826) of items val(i), i in [0,len) with valid(i); NaN if any NaN.
+template <int NT, class Val, class Valid>
+__device__ void group_median_mad(int len, Val val, Valid valid, SelScratch* sc, int tid, double* med_out,
+                                 double* mad_out) {
+  unsigned long long n = 0, nnan = 0;
+  for (int i = tid; i < len; i += NT) {
+    if (valid(i)) { n++; double v = val(i); if (v != v) nnan++; }
+  }
+  n = group_sum_ull<NT>(n, sc, tid);
+  nnan = group_sum_ull<NT>(nnan, sc, tid);
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  if (nnan > 0 || n == 0) { *med_out = qnan; *mad_out = qnan; return; }
+  auto get1 = [&](int i, unsigned long long& key) { if (!valid(i)) return false; key = f64_key(val(i)); return true; };
+  double med = group_median<NT>(len, (long long)n, get1, sc, tid);
+  auto get2 = [&](int i, unsigned long long& key) { if (!valid(i)) return false; key = f64_key(fabs(val(i) - med)); return true; };
+  double mad = group_median<NT>(len, (long long)n, get2, sc, tid);
+  *med_out = med;
+  *mad_out = MAD_CONST * mad;
+}
