@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- NB IRLS gene-fits/sec on BASELINE.json config 2 (ruvIII.nb NB, k=5, 20k genes x 100k cells,
+50 replicate groups), 1..8 B200, beside the CPU restatement of the reference.
+
+A "step" is one inner IRLS iteration of ruvIII.nb (R/ruvIIInb.R:303-527): Huber certificate sweep, alpha
+(get.coef2/get.adev), W (getW), gmean, Mb, candidate log-likelihood, accept.  gene-fits/sec = G x steps / time.
+
+  value  counts resident in HBM, K calls of ruvnb_irls_iteration, CUDA events on the library's stream,
+         max over ranks.
+  e2e    the same metric through the public host API with HOST buffers: upload of the count matrix from
+         pinned host memory, initial coefficients, log-likelihood, K iterations (each returns its
+         log-likelihood to the host) and the read-back of W, alpha, gmean, Mb -- wall clock, max over ranks.
+  N > 1  genes sharded over the ranks (strong scaling: the 20k x 100k problem is fixed), control-gene rows
+         replicated, cells sharded for the W update, NCCL all-reduces for the exchange steps.
+
+`--impl reference` times the reference's CPU algorithm (oracle/: C/OpenMP restatement when built, else the
+NumPy restatement) on a bounded sample of the same workload, on rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: G, N, k, m, n_ctl
+    "cfg2_nb_20kx100k": (20000, 100000, 5, 50, 1000),
+    "small_2kx10k": (2000, 10000, 5, 50, 200),
+    "prof_2kx100k": (2368, 100000, 5, 50, 256),  # ncu captures: same row length as cfg2, 16 rows per SM
+    "tiny_256x2k": (256, 2048, 2, 3, 64),
+}
+SEED = 20261019 + 2
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data, generated on the GPU by torch in gene chunks: plumbing only
+# ------------------------------------------------------------------------------------------------
+def truth_params(G, N, k, m, n_ctl, seed=SEED):
+    from ruviiinb_b200 import synth
+    rng = np.random.Generator(np.random.PCG64(seed))
+    grp = synth.draw_groups(rng, N, m)
+    W = rng.standard_normal((N, k))
+    alpha = 0.3 * rng.standard_normal((G, k))
+    gmean = np.clip(-0.5 + 1.5 * rng.standard_normal(G), -4.0, 5.0)
+    Mb = 0.5 * rng.standard_normal((G, m))
+    Mb[:n_ctl] = 0.0
+    psi = np.exp(np.log(0.3) + 0.5 * rng.standard_normal(G))
+    ctl = np.zeros(G, dtype=bool)
+    ctl[:n_ctl] = True
+    # bench start state: a perturbed truth (the fit itself starts from irlba + WLS; the throughput of an
+    # iteration does not depend on where in the trajectory it is taken)
+    W0 = W + 0.3 * rng.standard_normal((N, k))
+    W0 /= np.sqrt((W0 ** 2).sum(axis=0))[None, :]
+    return dict(grp=grp, W=W, alpha=alpha, gmean=gmean, Mb=Mb, psi=psi, ctl=ctl, W0=W0)
+
+
+def gen_rows_gpu(tp, rows, out, device, chunk=500, seed=SEED):
+    """Y[rows] ~ Poisson(Gamma(1/psi, mu psi)), log mu = gmean + Mb[,grp] + alpha W'; one torch generator
+    seed per 500-gene chunk so the matrix does not depend on how genes are sharded."""
+    import torch
+    Wt = torch.as_tensor(tp["W"], device=device)
+    grp = torch.as_tensor(tp["grp"].astype(np.int64), device=device)
+    rows = np.asarray(rows)
+    i = 0
+    while i < len(rows):
+        c = rows[i] // chunk
+        j = i
+        while j < len(rows) and rows[j] // chunk == c:
+            j += 1
+        g0, g1 = c * chunk, min((c + 1) * chunk, len(tp["gmean"]))
+        a = torch.as_tensor(tp["alpha"][g0:g1], device=device)
+        lmu = torch.as_tensor(tp["gmean"][g0:g1], device=device)[:, None] + torch.as_tensor(tp["Mb"][g0:g1], device=device)[:, grp] + a @ Wt.T
+        psi = torch.as_tensor(tp["psi"][g0:g1], device=device)[:, None]
+        shape = (1.0 / psi).expand_as(lmu).contiguous()
+        torch.manual_seed(seed * 1000 + int(c))  # default CUDA generator: one seed per gene chunk
+        lam = torch._standard_gamma(shape) * torch.exp(lmu) * psi
+        y = torch.poisson(lam).to(torch.int32)
+        sel = torch.as_tensor(rows[i:j] - g0, device=device)
+        out[i:j] = y[sel].cpu().numpy()
+        i = j
+    return out
+
+
+def gen_rows_cpu(tp, rows, seed=SEED, chunk=500):
+    rows = np.asarray(rows)
+    out = np.empty((len(rows), tp["W"].shape[0]), dtype=np.int32)
+    for i, g in enumerate(rows):
+        rng = np.random.Generator(np.random.PCG64(seed * 100003 + int(g)))
+        lmu = tp["gmean"][g] + tp["Mb"][g][tp["grp"]] + tp["W"] @ tp["alpha"][g]
+        lam = rng.gamma(1.0 / tp["psi"][g], np.exp(lmu) * tp["psi"][g])
+        out[i] = rng.poisson(lam)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the restated reference algorithm on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_run(workload, steps, warmup, target_seconds=20.0):
+    """One inner IRLS iteration of the oracle on a bounded sample of the workload: all N cells, the control
+    genes needed for W cut to n_ctl_s, G_s genes in total.  Returns (gene-fits/sec, description dict)."""
+    G, N, k, m, n_ctl = WORKLOADS[workload]
+    from oracle import cport
+    tp = truth_params(G, N, k, m, n_ctl)
+    cores = os.cpu_count() or 1
+    have_c = cport.available()
+    Gs = min(G, 2048, 64 * cores if have_c else 96)
+    ncs = min(n_ctl, max(8, Gs // 4))
+    rows = np.concatenate([np.arange(ncs), np.arange(n_ctl, n_ctl + Gs - ncs)])
+    Y = gen_rows_cpu(tp, rows)
+    ctl = np.zeros(Gs, dtype=bool)
+    ctl[:ncs] = True
+    state = dict(gmean=tp["gmean"][rows].copy(), Mb=tp["Mb"][rows].copy(), alpha=tp["alpha"][rows].copy(),
+                 alpha_dev=tp["alpha"][rows] - tp["alpha"][rows].mean(axis=0), W=tp["W0"].copy(), psi=tp["psi"][rows].copy(),
+                 step=np.ones(Gs))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        state, ll = cport.inner_iteration(Y, state, tp["grp"], ctl, k_huber=100.0, lambda_a=0.01, lambda_b=16.0)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    kind = "port"
+    sample = (f"{Gs} genes ({ncs} controls) x all {N} cells of {workload}, {steps} inner iterations, "
+              f"{'C/OpenMP' if have_c else 'NumPy'} restatement of R/ruvIIInb.R:303-484")
+    return Gs * steps / tot, dict(kind=kind, cores=cores if have_c else 1, sample=sample), 1e3 * tot / steps
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    G, N, k, m, n_ctl = WORKLOADS[args.workload]
+    config = {"workload": f"ruvIII.nb NB inner IRLS iteration, k={k}, {G} genes x {N} cells, {m} replicate groups, "
+                          f"{n_ctl} control genes ({args.workload})",
+              "l2": "inputs larger than L2 (int32 counts %.1f GB per pass)" % (4.0 * G * N / 1e9),
+              "sharding": "genes" if world > 1 else "none"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, desc, ms = cpu_sample_run(args.workload, args.steps, max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": "NB IRLS gene-fits/sec", "value": v, "unit": "gene-fits/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": dict(value=v, unit="gene-fits/s", **desc),
+                "e2e": {"value": v, "unit": "gene-fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ruviiinb_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    tp = truth_params(G, N, k, m, n_ctl)
+    # gene shard of this rank (strong scaling)
+    per = (G + world - 1) // world
+    g0, g1 = min(G, rank * per), min(G, (rank + 1) * per)
+    Gl = g1 - g0
+    t_gen = time.perf_counter()
+    Yh_t = torch.empty((Gl, N), dtype=torch.int32, pin_memory=True)
+    Yh = Yh_t.numpy()
+    gen_rows_gpu(tp, np.arange(g0, g1), Yh, dev)
+    Yctl = None
+    if world > 1:
+        Yctl_t = torch.empty((n_ctl, N), dtype=torch.int32, pin_memory=True)
+        Yctl = Yctl_t.numpy()
+        gen_rows_gpu(tp, np.arange(n_ctl), Yctl, dev)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    t_gen = time.perf_counter() - t_gen
+
+    opts = _lib.default_opts(k=k)
+    uid = None
+    if world > 1:
+        import ctypes as C
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = _lib.load().ruvnb_comm_unique_id(C.cast(buf, C.c_void_p))
+            assert rc == 0, "ruvnb_comm_unique_id failed"
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().tolist())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_ctx():
+        ctx = _lib.Context(local)
+        if world > 1:
+            ctx.comm_init(uid, rank, world)
+        ctx.set_design(G, N, tp["grp"], tp["ctl"], rows=(g0, g1))
+        return ctx
+
+    def set_start_state(ctx):
+        ctx.set_state("W", tp["W0"])
+        ctx.init_coef(opts)
+        ctx.set_state("psi", tp["psi"][g0:g1])
+
+    # ---- device-resident leg ------------------------------------------------------------------
+    ctx = make_ctx()
+    ctx.upload_counts(Yh, Yctl=Yctl)
+    set_start_state(ctx)
+    ctx.loglik(opts)
+    for _ in range(args.warmup):
+        ctx.irls_iteration(opts)
+        ctx.accept()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.kernel_time_reset()
+    l0 = ctx.kernel_launches
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0.record(stream)
+    logls = []
+    for _ in range(args.steps):
+        ll, bad = ctx.irls_iteration(opts)
+        ctx.accept()
+        logls.append(ll)
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    exact_rows = ctx.last_exact_rows
+    ktimes = ctx.kernel_times()
+    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = G * args.steps / (ms_max * 1e-3)
+    ctx.close()
+
+    # ---- end-to-end leg: host buffers through the public API ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        ctx = make_ctx()
+        ctx.upload_counts(Yh, Yctl=Yctl)
+        set_start_state(ctx)
+        ctx.loglik(opts)
+        for _ in range(args.steps):
+            ctx.irls_iteration(opts)
+            ctx.accept()
+        out = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb")}
+        barrier()
+        dt = time.perf_counter() - t0
+        ctx.close()
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        dt = float(tdt.item())
+        h2d = Yh.nbytes + (Yctl.nbytes if Yctl is not None else 0) + tp["W0"].nbytes + 8 * Gl + 4 * N + G
+        d2h = sum(v.nbytes for v in out.values()) + 8 * args.steps
+        e2e = {"value": G * args.steps / dt, "unit": "gene-fits/s", "h2d_bytes_per_step": int(h2d * world / args.steps),
+               "d2h_bytes_per_step": int(d2h * world / args.steps),
+               "what": "Context + upload_counts (pinned host int32) + init_coef + loglik + K irls_iteration + get_state(W, alpha, gmean, Mb); wall clock"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sweep_bytes = {"devstats": 4.0 * Gl * N, "pass1": 4.0 * Gl * N, "pass2": 4.0 * Gl * N, "loglik": 4.0 * Gl * N,
+                   "w_update": 4.0 * n_ctl * N / world, "exact_mad": 0.0}
+    kern = {}
+    for name, (tot, cnt) in ktimes.items():
+        if cnt:
+            kern[name] = {"ms": tot / cnt, "launches_per_step": cnt / args.steps,
+                          "GBps": sweep_bytes[name] / (tot / cnt * 1e-3) / 1e9 if sweep_bytes[name] else None}
+    dom = max((n for n in kern if sweep_bytes[n] > 0), key=lambda n: kern[n]["ms"] * kern[n]["launches_per_step"])
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        tr = json.load(open(tr_path))
+        traffic = tr.get(args.workload, {}).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sweep_bytes[dom],
+                "note": "FP64-pipe-bound sweep (DESIGN.md section 5): ~130 DFMA-equivalents per element against an HBM budget of ~11",
+                "kernels": kern}
+
+    line = {"metric": "NB IRLS gene-fits/sec", "value": value, "unit": "gene-fits/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk,
+            "gpu_launches": int(launches), "exact_mad_rows_last_step": exact_rows, "roofline": roofline, "logl_trace": logls, "datagen_seconds": t_gen}
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        v, desc, _ = cpu_sample_run(args.workload, 2, 1)
+        line["cpu_baseline"] = dict(value=v, unit="gene-fits/s", **desc)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

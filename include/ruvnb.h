@@ -96,6 +96,18 @@ int ruvnb_create(ruvnb_ctx** out, int device);
 void ruvnb_destroy(ruvnb_ctx* ctx);
 const char* ruvnb_last_error(const ruvnb_ctx* ctx);
 long long ruvnb_kernel_launches(const ruvnb_ctx* ctx);
+/* Device time of the Y-streaming sweep kernels, measured with CUDA events on the library's own stream
+ * (bench.py's roofline line).  which: 0 devstats (Huber certificate sweep), 1 pass1 (Gram/score),
+ * 2 w_update (per-cell), 3 pass2 (group sums), 4 loglik, 5 exact-MAD (signdev + select).
+ * Accumulated since ruvnb_kernel_time_reset. */
+#define RUVNB_NKERN 6
+int ruvnb_kernel_time(const ruvnb_ctx* ctx, int which, double* ms_total, long long* launches);
+void ruvnb_kernel_time_reset(ruvnb_ctx* ctx);
+/* The CUDA stream every kernel of this context is launched on (a cudaStream_t), so a host can
+ * bracket calls with its own events. */
+void* ruvnb_stream(const ruvnb_ctx* ctx);
+/* Gene rows of the last ruvnb_irls_iteration whose Huber certificate failed (exact MAD computed). */
+int ruvnb_last_exact_rows(const ruvnb_ctx* ctx);
 
 /* ---- multi-GPU wiring (gene sharding) -------------------------------- */
 /* id: 128 bytes from ruvnb_comm_unique_id on rank 0, distributed by the host (torch.distributed

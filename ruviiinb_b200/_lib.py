@@ -16,7 +16,8 @@ MAX_K = 8
 # every symbol include/ruvnb.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "ruvnb_abi_version", "ruvnb_opts_default", "ruvnb_create", "ruvnb_destroy", "ruvnb_last_error",
-    "ruvnb_kernel_launches", "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
+    "ruvnb_kernel_launches", "ruvnb_kernel_time", "ruvnb_kernel_time_reset", "ruvnb_stream", "ruvnb_last_exact_rows",
+    "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
     "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_set_state",
     "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_snapshot_best",
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp",
@@ -67,6 +68,12 @@ def load():
     lib.ruvnb_last_error.restype = cp
     lib.ruvnb_kernel_launches.argtypes = [vp]
     lib.ruvnb_kernel_launches.restype = C.c_longlong
+    lib.ruvnb_kernel_time.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_longlong)]
+    lib.ruvnb_kernel_time_reset.argtypes = [vp]
+    lib.ruvnb_kernel_time_reset.restype = None
+    lib.ruvnb_stream.argtypes = [vp]
+    lib.ruvnb_stream.restype = vp
+    lib.ruvnb_last_exact_rows.argtypes = [vp]
     lib.ruvnb_comm_unique_id.argtypes = [vp]
     lib.ruvnb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.ruvnb_set_design.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, C.c_int64]
@@ -261,6 +268,28 @@ class Context:
         mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
         self._ck(self.lib.ruvnb_get_res(self.h, int(kind), int(block_size), _ptr(mb), _ptr(out)))
         return out
+
+    KERNELS = ("devstats", "pass1", "w_update", "pass2", "loglik", "exact_mad")
+
+    def kernel_times(self):
+        """{name: (total_ms, launches)} of the sweep kernels since the last reset (CUDA events, lib stream)."""
+        out = {}
+        for i, n in enumerate(self.KERNELS):
+            ms, cnt = C.c_double(), C.c_longlong()
+            self._ck(self.lib.ruvnb_kernel_time(self.h, i, C.byref(ms), C.byref(cnt)))
+            out[n] = (ms.value, cnt.value)
+        return out
+
+    def kernel_time_reset(self):
+        self.lib.ruvnb_kernel_time_reset(self.h)
+
+    @property
+    def last_exact_rows(self):
+        return int(self.lib.ruvnb_last_exact_rows(self.h))
+
+    @property
+    def stream(self):
+        return self.lib.ruvnb_stream(self.h)
 
     @property
     def kernel_launches(self):

@@ -94,6 +94,12 @@ struct ruvnb_ctx {
   int rank = 0, nranks = 1;
   // stats of the last iteration
   int last_fail_rows = 0;
+  // per-kernel device timing of the sweep kernels (CUDA events on ctx->stream, read at the
+  // end-of-iteration sync): 0 devstats 1 pass1 2 w_update 3 pass2 4 loglik 5 exact-MAD
+  cudaEvent_t kev[RUVNB_NKERN][2] = {};
+  bool kev_armed[RUVNB_NKERN] = {};
+  double kms[RUVNB_NKERN] = {};
+  long long kcnt[RUVNB_NKERN] = {};
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -142,6 +148,18 @@ static int allreduce(ruvnb_ctx* ctx, void* buf, size_t count, int dtype) {
   int r = g_nccl.AllReduce(buf, buf, count, dtype, NCCL_SUM, ctx->comm, ctx->stream);
   if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return RUVNB_OK;
+}
+
+// bracket a sweep kernel with events; collected by kev_collect() after the next stream sync
+#define KEV_BEGIN(id) do { if (ctx->kev[id][0]) { CK(cudaEventRecord(ctx->kev[id][0], ctx->stream)); } } while (0)
+#define KEV_END(id) do { if (ctx->kev[id][0]) { CK(cudaEventRecord(ctx->kev[id][1], ctx->stream)); ctx->kev_armed[id] = true; } } while (0)
+static void kev_collect(ruvnb_ctx* ctx) {
+  for (int i = 0; i < RUVNB_NKERN; ++i) {
+    if (!ctx->kev_armed[i]) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->kev[i][0], ctx->kev[i][1]) == cudaSuccess) { ctx->kms[i] += ms; ctx->kcnt[i]++; }
+    ctx->kev_armed[i] = false;
+  }
 }
 
 #define DISPATCH_K(KVAL, ...)                                        \

@@ -27,6 +27,7 @@ int ruvnb_create(ruvnb_ctx** out, int device) {
     delete ctx;
     return RUVNB_ECUDA;
   }
+  for (int i = 0; i < RUVNB_NKERN; ++i) { cudaEventCreate(&ctx->kev[i][0]); cudaEventCreate(&ctx->kev[i][1]); }
   *out = ctx;
   return RUVNB_OK;
 }
@@ -39,11 +40,24 @@ void ruvnb_destroy(ruvnb_ctx* ctx) {
   for (void* p : ctx->allocs) cudaFree(p);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  for (int i = 0; i < RUVNB_NKERN; ++i) { if (ctx->kev[i][0]) cudaEventDestroy(ctx->kev[i][0]); if (ctx->kev[i][1]) cudaEventDestroy(ctx->kev[i][1]); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 const char* ruvnb_last_error(const ruvnb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int ruvnb_kernel_time(const ruvnb_ctx* ctx, int which, double* ms_total, long long* launches) {
+  if (!ctx || which < 0 || which >= RUVNB_NKERN) return RUVNB_EARG;
+  if (ms_total) *ms_total = ctx->kms[which];
+  if (launches) *launches = ctx->kcnt[which];
+  return RUVNB_OK;
+}
+int ruvnb_last_exact_rows(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_rows : -1; }
+void* ruvnb_stream(const ruvnb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void ruvnb_kernel_time_reset(ruvnb_ctx* ctx) {
+  if (!ctx) return;
+  for (int i = 0; i < RUVNB_NKERN; ++i) { ctx->kms[i] = 0.0; ctx->kcnt[i] = 0; }
+}
 long long ruvnb_kernel_launches(const ruvnb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------
@@ -415,16 +429,19 @@ static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
 
 // per-gene log-likelihood of parameter set `s` into `out`; total (all ranks) into *total if non-null
 static int loglik_of(ruvnb_ctx* ctx, const StateSet& s, double* out, double* total) {
+  KEV_BEGIN(4);
   DISPATCH_K(ctx->K, {
     k_loglik<KT><<<row_grid(ctx->Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), out);
     CKL();
   });
+  KEV_END(4);
   if (total) {
     k_colsum<<<1, 1024, 0, ctx->stream>>>(out, ctx->Gl, 1, ctx->scal);
     CKL();
     RET(allreduce(ctx, ctx->scal, 1, NCCL_F64));
     CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    kev_collect(ctx);
     *total = ctx->h_scal[0];
   }
   return RUVNB_OK;
@@ -436,10 +453,12 @@ static int row_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, const StateSet& s, dou
   const int Gl = ctx->Gl;
   CK(cudaMemsetAsync(ctx->flags + 4, 0, sizeof(int), ctx->stream));
   if (o->huber_fastpath) {
+    KEV_BEGIN(0);
     DISPATCH_K(ctx->K, {
       k_devstats<KT><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, Gl, nullptr), gstate<KT>(ctx, s, false), kh, ctx->sigma, ctx->flags + 4);
       CKL();
     });
+    KEV_END(0);
   } else {
     CK(cudaMemsetAsync(ctx->sigma, 0, (size_t)Gl * 8, ctx->stream));  // 0 == "not certified"
   }
@@ -447,6 +466,7 @@ static int row_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, const StateSet& s, dou
   CKL();
   CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  kev_collect(ctx);
   const int nf = ctx->h_flags[4];
   *nfail = nf;
   if (nf == 0) return RUVNB_OK;
@@ -457,6 +477,7 @@ static int row_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, const StateSet& s, dou
     RET(dev_alloc(ctx, &ctx->D, batch * ctx->Np));  // grows at most once per problem (first call sizes it)
     ctx->D_rows = batch;
   }
+  KEV_BEGIN(5);
   for (long long r0 = 0; r0 < nf; r0 += ctx->D_rows) {
     int nr = (int)std::min<long long>(ctx->D_rows, nf - r0);
     DISPATCH_K(ctx->K, {
@@ -466,6 +487,7 @@ static int row_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, const StateSet& s, dou
     k_row_sigma<<<nr, 256, 0, ctx->stream>>>(ctx->D, ctx->Np, ctx->d_chunk_valid, ctx->faillist + r0, ctx->sigma, nullptr);
     CKL();
   }
+  KEV_END(5);
   return RUVNB_OK;
 }
 
@@ -494,9 +516,11 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   RET(make_rmw(ctx, c.W));
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
+    KEV_BEGIN(1);
     if (hub) k_pass1<KT, true><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, ctx->RMW, ctx->sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
     else k_pass1<KT, false><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, ctx->RMW, ctx->sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
     CKL();
+    KEV_END(1);
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
     CKL();
     k_colsum<<<1, 1024, 0, ctx->stream>>>(ctx->Ab, Gl, KK + K, ctx->red);
@@ -549,11 +573,13 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     long long pb = std::min<long long>(ctx->Np, ch_per * ctx->rank * CH), pe = std::min<long long>(ctx->Np, ch_per * (ctx->rank + 1) * CH);
     if (ctx->nranks > 1) CK(cudaMemsetAsync(n.W, 0, (size_t)ctx->Np * K * 8, ctx->stream));
     if (pe > pb) {
+      KEV_BEGIN(2);
       DISPATCH_K(K, {
         CK(cudaFuncSetAttribute(k_w_update<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_w_update<KT, true><<<nblk(pe - pb, cpc), 256, smem, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, m, c.W, n.W, cpc, kh, pb, pe);
         CKL();
       });
+      KEV_END(2);
     }
     RET(allreduce(ctx, n.W, (size_t)ctx->Np * K, NCCL_F64));
     k_w_sumsq<<<K, 1024, 0, ctx->stream>>>(n.W, ctx->Np, ctx->sumsq); CKL();
@@ -563,9 +589,11 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   // gmean, Mb ------------------------------------------------------------------------------------------
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
+    KEV_BEGIN(3);
     if (hub) k_pass2<KT, true><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, n.W, n.alpha, ctx->sigma, kh, ctx->S0, ctx->S1);
     else k_pass2<KT, false><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, n.W, n.alpha, ctx->sigma, kh, ctx->S0, ctx->S1);
     CKL();
+    KEV_END(3);
   });
   k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
   RET(allreduce(ctx, ctx->flags + 2, 2, NCCL_INT32));
