@@ -1,0 +1,71 @@
+"""Golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle -- parity unpinned,
+see that script's header).  CPU: the oracle still reproduces them.  GPU: the CUDA path matches them through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(name):
+    return dict(np.load(os.path.join(HERE, "golden", name)))
+
+
+def _rel(a, b, floor=1e-300):
+    return float(np.abs(a - b).max() / max(floor, np.abs(b).max()))
+
+
+@pytest.mark.parametrize("name", ["iter_k2_m3.npz", "iter_k3_m4_robust.npz"])
+def test_oracle_reproduces_iteration_golden(name):
+    from oracle import ruviiinb as orc
+    g = _load(name)
+    Y, grp, ctl = g["Y"].astype(np.float64), g["grp"], g["ctl"]
+    G, N = Y.shape
+    m = int(grp.max()) + 1
+    state = dict(gmean=g["init_gmean"], Mb=np.zeros((G, m)), alpha=g["init_alpha"], alpha_dev=g["init_adev"], W=g["W0"],
+                 psi=g["psi"], step=np.ones(G), wt_zinb=np.ones((G, N)), pi0=np.zeros(G))
+    rep_ind = [np.where(grp == j)[0] for j in range(m)]
+    new, ll1, _ = orc.inner_iteration(Y, state, grp, rep_ind, ctl, 1.345 if bool(g["robust"]) else 100.0, 0.01, 16.0)
+    for n in ("alpha", "alpha_dev", "W", "gmean", "Mb"):
+        assert _rel(new[n], g[n], 1e-6) < 1e-12, n
+    assert np.allclose(ll1, g["loglik1"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["iter_k2_m3.npz", "iter_k3_m4_robust.npz"])
+def test_cuda_matches_iteration_golden(name):
+    from ruviiinb_b200 import _lib
+    from tests.parity import make_ctx
+    g = _load(name)
+    k = g["W0"].shape[1]
+    opts = _lib.default_opts(k=k, robust=int(bool(g["robust"])))
+    with make_ctx(g["Y"], g["grp"], g["ctl"]) as ctx:
+        ctx.set_state("W", g["W0"])
+        ctx.init_coef(opts)
+        assert _rel(ctx.get_state("gmean"), g["init_gmean"]) < 1e-9
+        assert _rel(ctx.get_state("alpha"), g["init_alpha"]) < 1e-9
+        ctx.set_state("psi", g["psi"])
+        tot0 = ctx.loglik(opts)
+        assert abs(tot0 - g["loglik0"].sum()) <= 1e-9 * abs(g["loglik0"].sum())
+        tot1, _ = ctx.irls_iteration(opts)
+        for n in ("alpha", "alpha_dev", "W", "gmean", "Mb"):
+            assert _rel(ctx.get_state(n), g[n], 1e-6) < 1e-8, n
+        assert abs(tot1 - g["loglik1"].sum()) <= 1e-9 * abs(g["loglik1"].sum())
+
+
+@pytest.mark.gpu
+def test_cuda_matches_fit_golden():
+    """Whole NB fit with injected W0 / psi schedule: same accept/halve decisions, 1e-6 (north_star) on the outputs."""
+    from ruviiinb_b200 import _lib
+    from tests.parity import make_ctx
+    g = _load("fit_k2_m3.npz")
+    opts = _lib.default_opts(k=2, outer_maxit=3)
+    with make_ctx(g["Y"], g["grp"], g["ctl"]) as ctx:
+        logl, recs, stats = ctx.fit_nb(opts, W0=g["W0"], psi_inject=g["psi_sched"])
+        dec = np.array([(r["outer"], r["iter"], r["degener"], r["accepted"]) for r in recs], dtype=np.int32)
+        assert np.array_equal(dec, g["decisions"])
+        assert np.allclose([r["logl_new"] for r in recs], g["logl_new"], rtol=1e-6, atol=0)
+        assert np.allclose(logl, g["logl_outer"], rtol=1e-6, atol=0)
+        for n, key in (("W", "W"), ("alpha", "alpha"), ("gmean", "gmean"), ("Mb", "Mb"), ("psi", "psi")):
+            assert _rel(ctx.get_state(n), g[key], 1e-6) < 1e-6, n
