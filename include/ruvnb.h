@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RUVNB_ABI_VERSION 1
+#define RUVNB_ABI_VERSION 2
 
 #define RUVNB_OK 0
 #define RUVNB_EARG (-1)    /* invalid argument */
@@ -106,8 +106,12 @@ void ruvnb_kernel_time_reset(ruvnb_ctx* ctx);
 /* The CUDA stream every kernel of this context is launched on (a cudaStream_t), so a host can
  * bracket calls with its own events. */
 void* ruvnb_stream(const ruvnb_ctx* ctx);
-/* Gene rows of the last ruvnb_irls_iteration whose Huber certificate failed (exact MAD computed). */
+/* Gene rows / cells of the last ruvnb_irls_iteration whose Huber certificate failed (exact MAD computed). */
 int ruvnb_last_exact_rows(const ruvnb_ctx* ctx);
+int ruvnb_last_exact_cells(const ruvnb_ctx* ctx);
+/* Host evaluation of the table-driven exp (which = 0) / log (which = 1) the kernels use (csrc/fastmath.cuh is
+ * __host__ __device__): lets the CPU test-suite check the very source the GPU runs.  No device needed. */
+int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n);
 
 /* ---- multi-GPU wiring (gene sharding) -------------------------------- */
 /* id: 128 bytes from ruvnb_comm_unique_id on rank 0, distributed by the host (torch.distributed
@@ -135,6 +139,9 @@ int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t
  * caps the resident counts in place; cap_out (local rows, may be NULL) receives ceil(Q_.995);
  * nonzero_out (local rows, may be NULL) receives rowSums(Y>0) for the zero-gene filter (:57). */
 int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out);
+/* The resident counts of the local rows (after ruvnb_winsorize: the winsorized ones), gene-major Gl x N int32:
+ * the `counts` element of the reference's return list (R/ruvIIInb.R:611,627). */
+int ruvnb_get_counts(ruvnb_ctx* ctx, int32_t* Y_out);
 
 /* ---- state (all local gene rows; column-major like the R objects) ---------------------------- */
 /* names: "W"(N x k) "alpha"(G x k) "alpha_dev"(G x k) "gmean"(G) "Mb"(G x m) "psi"(G) "step"(G)

@@ -17,8 +17,9 @@ MAX_K = 8
 SYMBOLS = [
     "ruvnb_abi_version", "ruvnb_opts_default", "ruvnb_create", "ruvnb_destroy", "ruvnb_last_error",
     "ruvnb_kernel_launches", "ruvnb_kernel_time", "ruvnb_kernel_time_reset", "ruvnb_stream", "ruvnb_last_exact_rows",
+    "ruvnb_last_exact_cells", "ruvnb_selftest_math",
     "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
-    "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_set_state",
+    "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_get_counts", "ruvnb_set_state",
     "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_snapshot_best",
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp",
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res",
@@ -74,12 +75,15 @@ def load():
     lib.ruvnb_stream.argtypes = [vp]
     lib.ruvnb_stream.restype = vp
     lib.ruvnb_last_exact_rows.argtypes = [vp]
+    lib.ruvnb_last_exact_cells.argtypes = [vp]
+    lib.ruvnb_selftest_math.argtypes = [C.c_int, vp, vp, C.c_int64]
     lib.ruvnb_comm_unique_id.argtypes = [vp]
     lib.ruvnb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.ruvnb_set_design.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, C.c_int64]
     lib.ruvnb_upload_counts_dense.argtypes = [vp, vp, C.c_int, vp]
     lib.ruvnb_upload_counts_csr.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.ruvnb_winsorize.argtypes = [vp, vp, vp]
+    lib.ruvnb_get_counts.argtypes = [vp, vp]
     lib.ruvnb_set_state.argtypes = [vp, cp, vp, C.c_int]
     lib.ruvnb_get_state.argtypes = [vp, cp, vp]
     lib.ruvnb_init_coef.argtypes = [vp, C.POINTER(Opts)]
@@ -185,6 +189,11 @@ class Context:
         self._ck(self.lib.ruvnb_winsorize(self.h, _ptr(cap), _ptr(nz)))
         return cap, nz
 
+    def get_counts(self):
+        out = np.empty((self.Gl, self.N), dtype=np.int32)
+        self._ck(self.lib.ruvnb_get_counts(self.h, _ptr(out)))
+        return out
+
     # ---- state ------------------------------------------------------------------------------
     def _shape(self, name):
         return {"W": (self.N, self.k), "alpha": (self.Gl, self.k), "alpha_dev": (self.Gl, self.k),
@@ -288,12 +297,26 @@ class Context:
         return int(self.lib.ruvnb_last_exact_rows(self.h))
 
     @property
+    def last_exact_cells(self):
+        return int(self.lib.ruvnb_last_exact_cells(self.h))
+
+    @property
     def stream(self):
         return self.lib.ruvnb_stream(self.h)
 
     @property
     def kernel_launches(self):
         return int(self.lib.ruvnb_kernel_launches(self.h))
+
+
+def selftest_math(which, x):
+    """Host evaluation of the kernels' table-driven exp ('exp') / log ('log') -- csrc/fastmath.cuh."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    rc = load().ruvnb_selftest_math({"exp": 0, "log": 1}[which], _ptr(x), _ptr(out), x.size)
+    if rc != 0:
+        raise RuvnbError(f"ruvnb_selftest_math failed with {rc}")
+    return out
 
 
 def default_opts(**kw):

@@ -4,9 +4,12 @@
 #include <cuda_pipeline.h>
 #include <stdint.h>
 #include <math.h>
+#include "fastmath.cuh"
 
 #define CH 128          // cells per chunk: one warp-wide pass of 4 cells per lane
+#define CHPAD 4         // the chunk count is padded to a multiple of this (tiles of up to 4 chunks per stage)
 #define NWARP 8         // warps (= gene rows) per CTA in the row-streaming kernels
+#define YT 128          // per-gene count tables cover y < YT (larger counts take the libdevice path)
 #define ROW_THREADS (NWARP * 32)
 #define LOG_DBL_MIN (-708.3964185322641)  // log(.Machine$double.xmin), R/ruvIIInb.R:290
 
@@ -70,4 +73,58 @@ __device__ __forceinline__ double nb_logpmf(int y, double lmu, double mu, double
   }
   if (!(fabs(v) <= 1.79769313486231570e308)) v = LOG_DBL_MIN;  // NaN or +-Inf
   return v;
+}
+
+// ---- table-driven per-element quantities ----------------------------------
+// ly: log(y) for y < YT (MathTabs.ly, shared by all genes); tr: the gene's log(y + r) for y < YT.
+// Half deviance  y (log y - lmu) - (y + r)(log(y + r) - L),  L = log(mu + r): the same conditioned form
+// as nb_signdev above with the two logs of integer arguments looked up.
+// out-of-table counts (y >= YT): libdevice, kept out of line so that the hot loops stay small
+__device__ __noinline__ void nb_slow_logs(double yd, double r, double* lyr, double* lyy) { *lyr = log(yd + r); *lyy = log(yd); }
+__device__ __noinline__ double nb_slow_lgterm(double yd, double r, double lgr) { return lgamma(yd + r) - lgr - lgamma(yd + 1.0); }
+__device__ __forceinline__ double nb_devhalf_t(int y, double yd, double lmu, double L, double r,
+                                               const double* __restrict__ tr, const double* __restrict__ ly) {
+  double lyr, lyy;
+  if (y < YT) { lyr = tr[y]; lyy = ly[y]; } else { nb_slow_logs(yd, r, &lyr, &lyy); }
+  double t = -(yd + r) * (lyr - L);
+  if (y > 0) t = fma(yd, lyy - lmu, t);
+  return t;
+}
+// signed deviance residual from the half deviance (same sign / NaN conventions as nb_signdev)
+__device__ __forceinline__ double nb_signdev_from_half(double t, double yd, double mu) {
+  double d2 = 2.0 * t;
+  double d = sqrt(fmax(d2, 0.0));
+  if (d2 != d2) d = d2;
+  return (yd > mu) ? d : ((yd < mu) ? -d : (mu != mu ? mu : 0.0));
+}
+// MASS::psi.huber weight pmin(1, k sigma / |d|) from the half deviance, NaN-propagating like R's pmin
+__device__ __forceinline__ double huber_w_half(double khsig, double t) {
+  double d2 = 2.0 * t;
+  double q = khsig * rsqrt(fmax(d2, 0.0));
+  if (d2 != d2) q = d2;
+  return (q < 1.0) ? q : ((q != q) ? q : 1.0);
+}
+// log dnbinom(y; mu, size = r): tl = the gene's lgamma(y+r) - lgamma(r) - lgamma(y+1) for y < YT
+__device__ __forceinline__ double nb_logpmf_t(int y, double yd, double lmu, double L, double r, double lgr, double rlogr,
+                                              const double* __restrict__ tl) {
+  double v = fma(-r, L, rlogr);
+  if (y > 0) {
+    double g = (y < YT) ? tl[y] : nb_slow_lgterm(yd, r, lgr);
+    v += fma(yd, lmu - L, g);
+  }
+  if (!(fabs(v) <= 1.79769313486231570e308)) v = LOG_DBL_MIN;  // NaN or +-Inf (R/ruvIIInb.R:290)
+  return v;
+}
+// sig.inv = 1/(exp(-lmu) + psi) = mu/(1 + psi mu) and the working-response ratio (y + .01)/(mu + .01)
+// (R/ruvIIInb.R:305,321) with ONE reciprocal: both share the denominator (1 + psi mu)(mu + .01).
+__device__ __forceinline__ void nb_siginv_ratio(double yd, double mu, double psi, double* s, double* q) {
+  if (!(mu < 1e100)) {  // overflowed / NaN mu: the reference's own formulas (rare, warp-divergent)
+    *s = 1.0 / (1.0 / mu + psi);
+    *q = (yd + 0.01) / (mu + 0.01);
+    return;
+  }
+  double a = fma(psi, mu, 1.0), b = mu + 0.01;
+  double inv = frcp(a * b);
+  *s = (mu * b) * inv;
+  *q = ((yd + 0.01) * a) * inv;
 }

@@ -45,6 +45,11 @@ enum { NCCL_SUM = 0 };
 
 struct StateSet {  // one parameter set on device
   double *gmean = nullptr, *Mb = nullptr, *alpha = nullptr, *adev = nullptr, *W = nullptr, *psi = nullptr, *pi0 = nullptr;
+  // Huber scale of THIS parameter set, written by the log-likelihood sweep (certificate) and completed by the
+  // exact path: +Inf = every weight provably 1, 0 = not evaluated yet, else mad(signdev)/0.6745
+  double* sigma = nullptr;
+  bool sig_valid = false;   // sigma was produced for the parameters currently held
+  bool maybe_active = false; // some rows went through the exact path: their sigma may be finite (live Huber weights)
 };
 
 struct ruvnb_ctx {
@@ -81,10 +86,19 @@ struct ruvnb_ctx {
   bool have_W = false;
   // scratch
   double *A = nullptr, *u = nullptr, *sw = nullptr, *ZS = nullptr, *VS = nullptr, *cvec = nullptr, *Ab = nullptr,
-         *red = nullptr, *amean = nullptr, *S0 = nullptr, *S1 = nullptr, *sigma = nullptr, *Wbar = nullptr,
+         *red = nullptr, *amean = nullptr, *S0 = nullptr, *S1 = nullptr, *Wbar = nullptr,
          *RMW = nullptr, *sumsq = nullptr, *med = nullptr, *mad = nullptr, *ctlpack = nullptr, *alpha_full = nullptr,
          *scal = nullptr;
   double* D = nullptr; long long D_rows = 0;  // exact-MAD scratch [D_rows][Np]
+  double* rowmax = nullptr; int* rownan = nullptr;  // per scratch slot: max|d|, NaN flag
+  double* hint = nullptr;        // [Gl][3] certificate hints lo, hi, tg (k_row_sigma -> k_loglik)
+  double* sigma_exact = nullptr; // [Gl] last exact sigma of each row (diagnostics / tests)
+  // table-driven math (fastmath.cuh, kernels.cuh k_build_ytabs)
+  MathTabs* d_mtabs = nullptr;
+  double *tabL = nullptr, *tabR = nullptr, *lgr = nullptr;   // [Gl][YT], [Gl][YT], [Gl]
+  double* ctl_tabR = nullptr;                                 // [n_ctl][YT]
+  const double* ytab_psi = nullptr; long long ytab_ver = -1, psi_ver = 0;  // which psi the tables were built from
+  int *w_fail = nullptr;         // [1 + Np] fast-W failures: count, then positions
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare
   int *faillist = nullptr;
   int *h_flags = nullptr;    // pinned mirror
@@ -93,7 +107,7 @@ struct ruvnb_ctx {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   // stats of the last iteration
-  int last_fail_rows = 0;
+  int last_fail_rows = 0, last_active_rows = 0, last_fail_cells = 0;
   // per-kernel device timing of the sweep kernels (CUDA events on ctx->stream, read at the
   // end-of-iteration sync): 0 devstats 1 pass1 2 w_update 3 pass2 4 loglik 5 exact-MAD
   cudaEvent_t kev[RUVNB_NKERN][2] = {};

@@ -15,11 +15,15 @@
 struct RowGeom {
   const int32_t* Yp;
   long long Np;
-  int nchunks;
+  int nchunks;          // multiple of CHPAD; trailing chunks may be empty (chunk_valid == 0)
   const int* chunk_grp;
   const int* chunk_valid;
   int nrows;            // rows this launch walks
   const int* rowlist;   // nullptr -> slot == row; else row = rowlist[slot] (exact-MAD batches)
+  const MathTabs* mtabs;  // exp / log / log(y) tables (global copy, staged into shared memory per CTA)
+  const double* tabL;   // [Gl][YT] lgamma(y+r) - lgamma(r) - lgamma(y+1)
+  const double* tabR;   // [Gl][YT] log(y + r)
+  const double* lgr;    // [Gl] lgamma(r)
 };
 
 template <int K>
@@ -33,76 +37,51 @@ struct GeneState {  // pointers to one parameter set (current, candidate or best
   int m;
 };
 
+// chunks per shared-memory stage: 512 cells for k <= 5, 256 above (tile bytes = 2 x NSETS x K x 8 x cells)
+template <int K> struct TileCfg { static constexpr int SC = (K <= 5) ? 4 : 2; static constexpr int CELLS = SC * CH; };
+
+// per-CTA shared tables of the row-streaming kernels
+struct RowShared {
+  MathTabs mt;              // 4 KB
+  double tl[NWARP][YT];     // this warp's row: lgamma table
+  double tr[NWARP][YT];     // this warp's row: log(y + r)
+  const double* wsets[2];
+};
+
 // ------------------------------------------------------------------------------------------------
 // row-streaming skeleton
 // ------------------------------------------------------------------------------------------------
 template <int K, int NSETS>
-__device__ __forceinline__ void stage_tile(double* dst, const double* const* wsets, long long Np, int chunk, int tid) {
-  constexpr int UNITS_PER_ROW = CH / 2;  // 16-byte units
+__device__ __forceinline__ void stage_tile(double* dst, const double* const* wsets, long long Np, int tile, int tid) {
+  constexpr int CELLS = TileCfg<K>::CELLS;
+  constexpr int UNITS_PER_ROW = CELLS / 2;  // 16-byte units
   constexpr int UNITS = NSETS * K * UNITS_PER_ROW;
   for (int u = tid; u < UNITS; u += ROW_THREADS) {
     int s = u / (K * UNITS_PER_ROW);
     int rem = u - s * (K * UNITS_PER_ROW);
     int l = rem / UNITS_PER_ROW;
     int e2 = rem - l * UNITS_PER_ROW;
-    const double* src = wsets[s] + (long long)l * Np + (long long)chunk * CH + 2 * e2;
-    __pipeline_memcpy_async(dst + (s * K + l) * CH + 2 * e2, src, 16);
+    const double* src = wsets[s] + (long long)l * Np + (long long)tile * CELLS + 2 * e2;
+    __pipeline_memcpy_async(dst + (s * K + l) * CELLS + 2 * e2, src, 16);
   }
   __pipeline_commit();
 }
 
-// Op interface: row_begin(row, slot), group_begin(j), elem(y, chunk, ci, tile), group_end(j), row_end(row)
-template <int K, int NSETS, class Op>
-__device__ __forceinline__ void stream_rows(const RowGeom& geo, const double* const* wsets, Op& op, double* smem) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = blockIdx.x * NWARP + warp;
-  const bool active = slot < geo.nrows;
-  const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
-  constexpr int TILE = NSETS * K * CH;
-  if (active) op.row_begin(row, slot);
-  const int32_t* yrow = geo.Yp + (long long)row * geo.Np;
-  int curj = -1;
-  stage_tile<K, NSETS>(smem, wsets, geo.Np, 0, tid);
-  for (int c = 0; c < geo.nchunks; ++c) {
-    if (c + 1 < geo.nchunks) {
-      stage_tile<K, NSETS>(smem + ((c + 1) & 1) * TILE, wsets, geo.Np, c + 1, tid);
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
-    if (active) {
-      const double* tile = smem + (c & 1) * TILE;
-      const int j = geo.chunk_grp[c];
-      const int nv = geo.chunk_valid[c];
-      if (j != curj) {
-        if (curj >= 0) op.group_end(curj);
-        curj = j;
-        op.group_begin(j);
-      }
-      const int2* yr = reinterpret_cast<const int2*>(yrow + (long long)c * CH);
-      int2 ya = yr[lane], yb = yr[32 + lane];
-      int ys[4] = {ya.x, ya.y, yb.x, yb.y};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        int ci = lane_cell(lane, e);
-        if (ci < nv) op.elem(ys[e], c, ci, tile);
-      }
-    }
-    __syncthreads();
-  }
-  if (active) {
-    if (curj >= 0) op.group_end(curj);
-    op.row_end(row);
-  }
+// NaN-propagating pmin(1, k/|u|)  (MASS::psi.huber; R's pmin keeps NaN, CUDA's fmin does not)
+__device__ __forceinline__ double huber_w(double khsig, double d) {
+  double q = khsig / fabs(d);
+  return (q < 1.0) ? q : ((q != q) ? q : 1.0);
 }
 
 template <int K>
 struct GeneRegs {
-  double gmean, psi, r, step;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
+  double gmean, psi, r, step, lgr;
   double a[K];
   const double* mb;
   double mbj;
+  const double *tl, *tr;      // this warp's count tables (shared memory)
+  const MathTabs* mt;         // shared memory
   __device__ __forceinline__ void load(const GeneState<K>& st, int row) {
     gmean = st.gmean[row];
     psi = st.psi[row];
@@ -116,159 +95,199 @@ struct GeneRegs {
   __device__ __forceinline__ double lmu(const double* w, int ci) const {
     double s = gmean + mbj;
 #pragma unroll
-    for (int l = 0; l < K; ++l) s = fma(a[l], w[l * CH + ci], s);
+    for (int l = 0; l < K; ++l) s = fma(a[l], w[l * CELLS + ci], s);
     return s;
   }
+  __device__ __forceinline__ double expm(double x) const { return fexp(x, mt->ex); }
+  __device__ __forceinline__ double logL(double mu) const { return flog(mu + r, mt->rc, mt->lc); }
 };
 
-// NaN-propagating pmin(1, k/|u|)  (MASS::psi.huber; R's pmin keeps NaN, CUDA's fmin does not)
-__device__ __forceinline__ double huber_w(double khsig, double d) {
-  double q = khsig / fabs(d);
-  return (q < 1.0) ? q : ((q != q) ? q : 1.0);
+// Op interface: row_begin(row, slot), group_begin(j), elem(y, chunk, idx_in_tile, tile), pad(chunk, ci),
+//               group_end(j), row_end(row); Op::PADS says whether pad() must be called for padding cells.
+template <int K, int NSETS, class Op>
+__device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, Op& op, double* smem) {
+  constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.x * NWARP + warp;
+  const bool active = slot < geo.nrows;
+  const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
+  constexpr int TILE = NSETS * K * CELLS;
+  // shared tables: math tables for the CTA, count tables for this warp's row
+  {
+    const double* src = reinterpret_cast<const double*>(geo.mtabs);
+    double* dst = reinterpret_cast<double*>(&sh->mt);
+    for (int i = tid; i < (int)(sizeof(MathTabs) / 8); i += ROW_THREADS) dst[i] = src[i];
+    if (active && geo.tabL) {
+      for (int i = lane; i < YT; i += 32) {
+        sh->tl[warp][i] = geo.tabL[(long long)row * YT + i];
+        sh->tr[warp][i] = geo.tabR[(long long)row * YT + i];
+      }
+    }
+  }
+  op.g.tl = sh->tl[warp]; op.g.tr = sh->tr[warp]; op.g.mt = &sh->mt;
+  op.g.lgr = (active && geo.lgr) ? geo.lgr[row] : 0.0;
+  __syncthreads();
+  if (active) op.row_begin(row, slot);
+  const int32_t* yrow = geo.Yp + (long long)row * geo.Np;
+  const int ntiles = geo.nchunks / SC;
+  int curj = -1;
+  stage_tile<K, NSETS>(smem, sh->wsets, geo.Np, 0, tid);
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) {
+      stage_tile<K, NSETS>(smem + ((t + 1) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid);
+      __pipeline_wait_prior(1);
+    } else {
+      __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+    if (active) {
+      const double* tile = smem + (t & 1) * TILE;
+#pragma unroll
+      for (int sc = 0; sc < SC; ++sc) {
+        const int c = t * SC + sc;
+        const int nv = geo.chunk_valid[c];
+        if (nv == 0 && !Op::PADS) continue;
+        const int j = geo.chunk_grp[c];
+        if (j != curj && nv > 0) {
+          if (curj >= 0) op.group_end(curj);
+          curj = j;
+          op.group_begin(j);
+        }
+        const int2* yr = reinterpret_cast<const int2*>(yrow + (long long)c * CH);
+        int2 ya = yr[lane], yb = yr[32 + lane];
+        int ys[4] = {ya.x, ya.y, yb.x, yb.y};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int ci = lane_cell(lane, e);
+          if (ci < nv) op.elem(ys[e], c, sc * CH + ci, tile);
+          else if constexpr (Op::PADS) op.pad(c, ci);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    if (curj >= 0) op.group_end(curj);
+    op.row_end(row);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_signdev: signed deviance residuals of every element -> scratch D (exact-MAD path)
+// K_build_ytabs: per-gene count tables (rebuilt whenever psi changes -- once per outer iteration):
+//   tabL[y] = lgamma(y+r) - lgamma(r) - lgamma(y+1) = sum_{j<y} [log(r+j) - log(j+1)]   (no cancellation)
+//   tabR[y] = log(y + r),  lgr = lgamma(r).   One CTA of YT threads per gene.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(YT) k_build_ytabs(const double* psi, int rows, double* tabL, double* tabR, double* lgr) {
+  __shared__ double term[YT];
+  const int row = blockIdx.x, y = threadIdx.x;
+  if (row >= rows) return;
+  const double r = 1.0 / psi[row];
+  const double lr = log((double)y + r);
+  term[y] = lr - log((double)y + 1.0);
+  __syncthreads();
+  if (tabL) {
+    double s = 0.0;
+    for (int j = 0; j < y; ++j) s += term[j];
+    tabL[(long long)row * YT + y] = s;
+  }
+  tabR[(long long)row * YT + y] = lr;
+  if (y == 0 && lgr) lgr[row] = lgamma(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_signdev: signed deviance residuals of every element -> scratch D (exact-MAD path); pads = +Inf
+// (they sort last and never reach the middle ranks).  Also per-slot max|d| and a NaN flag.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct OpSigndev {
+  static constexpr bool PADS = true;
   GeneState<K> st;
   GeneRegs<K> g;
   double* Drow;
   double* D;
   long long Np;
-  __device__ __forceinline__ void row_begin(int row, int slot) { g.load(st, row); Drow = D + (long long)slot * Np; }
+  double mx; int nan_; int slot_;
+  double* rowmax; int* rownan;
+  __device__ __forceinline__ void row_begin(int row, int slot) { g.load(st, row); Drow = D + (long long)slot * Np; mx = 0.0; nan_ = 0; slot_ = slot; }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
-    double lmu = g.lmu(tile, ci);
-    double mu = exp(lmu);
-    Drow[(long long)c * CH + ci] = nb_signdev(y, lmu, mu, g.r);
+  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
+    double lmu = g.lmu(tile, ti);
+    double mu = g.expm(lmu);
+    double yd = (double)y;
+    double d = nb_signdev_from_half(nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt->ly), yd, mu);
+    Drow[(long long)c * CH + (ti & (CH - 1))] = d;
+    if (d != d) nan_ = 1;
+    mx = fmax(mx, fabs(d));
   }
+  __device__ __forceinline__ void pad(int c, int ci) { Drow[(long long)c * CH + ci] = __longlong_as_double(0x7ff0000000000000ll); }
   __device__ __forceinline__ void group_end(int) {}
-  __device__ __forceinline__ void row_end(int) {}
+  __device__ __forceinline__ void row_end(int) {
+    double v = warp_max(mx);
+    int nn = __any_sync(FULL, nan_);
+    if ((threadIdx.x & 31) == 0) { rowmax[slot_] = v; rownan[slot_] = nn; }
+  }
 };
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS) k_signdev(RowGeom geo, GeneState<K> st, double* D) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_signdev(RowGeom geo, GeneState<K> st, double* D, double* rowmax, int* rownan) {
   extern __shared__ double smem[];
-  __shared__ const double* wsets[1];
-  if (threadIdx.x == 0) wsets[0] = st.W;
-  __syncthreads();
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
   OpSigndev<K> op;
-  op.st = st; op.D = D; op.Np = geo.Np;
-  stream_rows<K, 1>(geo, wsets, op, smem);
+  op.st = st; op.D = D; op.Np = geo.Np; op.rowmax = rowmax; op.rownan = rownan;
+  stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
-// per-row sigma = mad(signdev)/0.6745 from scratch D (one CTA per row)
-__global__ void __launch_bounds__(256) k_row_sigma(const double* D, long long Np, const int* chunk_valid,
-                                                  const int* rowlist, double* sigma, double* med_out) {
-  __shared__ SelScratch sc;
-  const int row = rowlist ? rowlist[blockIdx.x] : blockIdx.x;
-  const double* d = D + (long long)blockIdx.x * Np;
-  auto val = [&](int i) { return d[i]; };
-  auto valid = [&](int i) { return (i & (CH - 1)) < chunk_valid[i >> 7]; };
-  double med, mad;
-  group_median_mad<256>((int)Np, val, valid, &sc, threadIdx.x, &med, &mad);
-  if (threadIdx.x == 0) { sigma[row] = mad / 0.6745; if (med_out) med_out[row] = med; }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K_devstats: the "Huber provably inactive" certificate.  The reference
-// computes sigma_g = mad(signdev_g)/0.6745 for every gene and weights pmin(1, k sigma/|d|)
-// (R/ruvIIInb.R:713-714); with k.huber = 100 (robust = FALSE, :155) those weights are all exactly 1
-// unless the row is degenerate.  One sweep builds a fixed-bin histogram of d (width 1/16 on
-// [-16,16), two overflow bins) and max|d| per row; from them a rigorous LOWER bound on the raw MAD:
-// with med in [mL, mH] (edges of the bins holding the two middle order statistics) every element
-// with |d - med| < t lies in (mL - t, mH + t), so  #bins-overlapping-that-interval <= (n-1)/2
-// proves  median|d - med| >= t.  Taking t = max|d| / (k 1.4826/0.6745) proves k sigma >= max|d|,
-// i.e. every weight is exactly 1 and the exact order statistic is not needed.  Rows that fail go to
-// the exact radix-select path (k_signdev + k_row_sigma).  sigma_out[row] = +Inf marks "certified".
-// ------------------------------------------------------------------------------------------------
-#define DS_NB 512
-#define DS_LO (-16.0)
-#define DS_INVH 16.0
-template <int K>
-struct OpDevstats {
-  GeneState<K> st;
-  GeneRegs<K> g;
-  unsigned* hist;  // this warp's DS_NB + 2 counters in shared memory
-  double maxabs; unsigned nbad; int lane;
-  double kh; double* sigma_out; int* fail_flag;
-  __device__ __forceinline__ void row_begin(int row, int) {
-    g.load(st, row); lane = threadIdx.x & 31; maxabs = 0.0; nbad = 0;
-    for (int i = lane; i < DS_NB + 2; i += 32) hist[i] = 0;
-    __syncwarp();
+// Exact sigma = mad(signdev)/0.6745 of one row from scratch D (one CTA of RS_NT threads per row), the
+// certificate hints for later sweeps, and -- with the fast path on -- promotion to "certified" (+Inf)
+// when k sigma >= max|d|, i.e. every Huber weight pmin(1, k sigma/|d|) is exactly 1.
+__global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long Np, long long n, const int* rowlist,
+                                                    const double* rowmax, const int* rownan, double kh, int fastpath,
+                                                    double* sigma, double* sigma_exact, double* hint /* [Gl][3] lo, hi, tg */) {
+  __shared__ RowSelScratch sc;
+  const int slot = blockIdx.x;
+  const int row = rowlist ? rowlist[slot] : slot;
+  const double* d = D + (long long)slot * Np;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  double med = qnan, madraw = qnan;
+  if (!rownan[slot] && n > 0) {
+    unsigned long long klo, khi;
+    auto key1 = [&](int i) { return f64_key(d[i]); };
+    cta_two_middles((int)Np, n, key1, &sc, &klo, &khi);
+    med = (n & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0;
+    auto key2 = [&](int i) { return f64_key(fabs(d[i] - med)); };
+    cta_two_middles((int)Np, n, key2, &sc, &klo, &khi);
+    madraw = (n & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0;
   }
-  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
-    double lmu = g.lmu(tile, ci);
-    double mu = exp(lmu);
-    double d = nb_signdev(y, lmu, mu, g.r);
-    double ad = fabs(d);
-    if (!(ad <= 1.79769313486231570e308)) { nbad++; return; }
-    maxabs = fmax(maxabs, ad);
-    double fb = floor((d - DS_LO) * DS_INVH);
-    int b = fb < 0.0 ? 0 : (fb >= (double)DS_NB ? DS_NB + 1 : (int)fb + 1);
-    atomicAdd(&hist[b], 1u);
-  }
-  __device__ __forceinline__ void group_end(int) {}
-  __device__ __forceinline__ void row_end(int row) {
-    __syncwarp();
-    double mx = warp_max(maxabs);
-    unsigned nb = (unsigned)warp_sum_ll((long long)nbad);
-    if (lane == 0) {
-      bool ok = false;
-      long long n = 0;
-      for (int i = 0; i < DS_NB + 2; ++i) n += hist[i];
-      if (nb == 0 && n > 0 && mx > 0.0) {
-        long long kl = (n - 1) / 2, ku = n / 2, acc = 0;
-        int bl = -1, bu = -1;
-        for (int i = 0; i < DS_NB + 2; ++i) {
-          long long nx = acc + hist[i];
-          if (bl < 0 && kl < nx) bl = i;
-          if (bu < 0 && ku < nx) { bu = i; break; }
-          acc = nx;
-        }
-        if (bl >= 1 && bu <= DS_NB) {  // both middles inside the binned range
-          double t = mx / (kh * (1.4826 / 0.6745)) * (1.0 + 1e-9);
-          double eL = DS_LO + (double)(bl - 1) / DS_INVH - t;
-          double eH = DS_LO + (double)bu / DS_INVH + t;
-          double fl = floor((eL - DS_LO) * DS_INVH), fh = floor((eH - DS_LO) * DS_INVH);
-          long long il = (long long)fl + 1 - 1, ih = (long long)fh + 1 + 1;  // one guard bin each side
-          if (il >= 1 && ih <= DS_NB) {
-            long long cnt = 0;
-            for (long long i = il; i <= ih; ++i) cnt += hist[i];
-            ok = cnt <= (n - 1) / 2;
-          }
-        }
-      }
-      sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
-      if (!ok) atomicAdd(fail_flag, 1);
+  if (threadIdx.x == 0) {
+    const double C = MAD_CONST / 0.6745;
+    double sg = MAD_CONST * madraw / 0.6745;
+    double mx = rowmax[slot];
+    if (sigma_exact) sigma_exact[row] = sg;
+    double out = sg;
+    double lo = qnan, hi = qnan, tg = -1.0;
+    if (fastpath && sg == sg) {
+      double t_now = mx / (kh * C) * (1.0 + 1e-9);
+      if (sg > 0.0 && kh * sg >= mx * (1.0 + 1e-9)) out = __longlong_as_double(0x7ff0000000000000ll);
+      double slack = madraw - t_now;
+      if (slack > 0.0 && mx < 1.79769313486231570e308) { tg = t_now + 0.5 * slack; lo = med - 0.25 * slack; hi = med + 0.25 * slack; }
     }
-    __syncwarp();
+    sigma[row] = out;
+    hint[(long long)row * 3 + 0] = lo; hint[(long long)row * 3 + 1] = hi; hint[(long long)row * 3 + 2] = tg;
   }
-};
-template <int K>
-__global__ void __launch_bounds__(ROW_THREADS) k_devstats(RowGeom geo, GeneState<K> st, double kh, double* sigma_out,
-                                                          int* fail_flag) {
-  extern __shared__ double smem[];
-  __shared__ const double* wsets[1];
-  __shared__ unsigned hist[NWARP][DS_NB + 2];
-  if (threadIdx.x == 0) wsets[0] = st.W;
-  __syncthreads();
-  OpDevstats<K> op;
-  op.st = st; op.kh = kh; op.sigma_out = sigma_out; op.fail_flag = fail_flag;
-  op.hist = hist[threadIdx.x >> 5];
-  stream_rows<K, 1>(geo, wsets, op, smem);
 }
+
 // rows whose certificate failed (sigma == 0 marker) -> compact list, ascending (one CTA, ordered scan)
-__global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigma, int* list, int* count) {
+__global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigma, int* list, int* count, int* n_active) {
   __shared__ int wsum[32];
-  __shared__ int base;
-  if (threadIdx.x == 0) base = 0;
+  __shared__ int base, act;
+  if (threadIdx.x == 0) { base = 0; act = 0; }
   __syncthreads();
+  int myact = 0;
   for (int g0 = 0; g0 < Gl; g0 += 1024) {
     int g = g0 + threadIdx.x;
-    bool f = g < Gl && !(sigma[g] > 1.79769313486231570e308);
+    double sg = g < Gl ? sigma[g] : 0.0;
+    bool f = g < Gl && sg == 0.0;
+    if (g < Gl && !f && !(sg > 1.79769313486231570e308)) myact++;  // finite or NaN sigma: Huber weights are live
     unsigned bal = __ballot_sync(FULL, f);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) wsum[w] = __popc(bal);
@@ -280,7 +299,94 @@ __global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigm
     if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; base += t; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count = base;
+  if (myact) atomicAdd(&act, myact);
+  __syncthreads();
+  if (threadIdx.x == 0) { *count = base; if (n_active) *n_active = act; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_loglik: per-gene NB log-likelihood (R/ruvIIInb.R:276-291) fused with the "Huber provably inactive"
+// certificate for the same parameter set.  The reference computes
+// sigma_g = mad(signdev_g)/0.6745 for every gene and weights pmin(1, k sigma/|d|) (:713-714); with
+// k.huber = 100 (robust = FALSE, :155) those weights are all exactly 1 unless the row is degenerate.
+// Given hints lo <= hi and tg (from the last exact evaluation of the row), one sweep counts
+//   c1 = #{d < lo}, c2 = #{d > hi}, c3 = #{lo - tg < d < hi + tg}  and max|d|:
+//   c1 <= (n-1)/2 and c2 <= n-1-n/2   =>  both middle order statistics, hence med, lie in [lo, hi];
+//   t := max|d| / (k 1.4826/0.6745) <= tg  =>  every element with |d - med| < t lies in (lo - tg, hi + tg);
+//   c3 <= (n-1)/2                      =>  median|d - med| >= t  =>  k sigma >= max|d|: all weights are 1.
+// Comparisons are done on u = sign(d) d^2/2 (monotone in d): no square root per element.  Rows that
+// fail (or have no hint yet) get sigma = 0 and go to the exact path (k_signdev + k_row_sigma).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double u_of_d(double d) { return copysign(0.5 * d * d, d); }
+__device__ __forceinline__ double d_of_u(double u) { return copysign(sqrt(2.0 * fabs(u)), u); }
+template <int K>
+struct OpLoglik {
+  static constexpr bool PADS = false;
+  GeneState<K> st;
+  GeneRegs<K> g;
+  double acc, rlogr;
+  double* out;
+  // certificate
+  const double* hint; double* sigma_out; double kh; int fastpath; long long n;
+  double u_lo, u_hi, u_wl, u_wh, hmax; int c1, c2, c3, bad; bool cert;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); acc = 0.0; rlogr = g.r * log(g.r);
+    cert = false; c1 = c2 = c3 = 0; bad = 0; hmax = 0.0; u_lo = u_hi = u_wl = u_wh = 0.0;
+    if (fastpath && sigma_out) {
+      double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1], tg = hint[(long long)row * 3 + 2];
+      cert = tg > 0.0 && lo <= hi;
+      if (cert) { u_lo = u_of_d(lo); u_hi = u_of_d(hi); u_wl = u_of_d(lo - tg); u_wh = u_of_d(hi + tg); }
+    }
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
+    double lmu = g.lmu(tile, ti);
+    double mu = g.expm(lmu);
+    double L = g.logL(mu);
+    double yd = (double)y;
+    acc += nb_logpmf_t(y, yd, lmu, L, g.r, g.lgr, rlogr, g.tl);
+    if (cert) {  // warp-uniform
+      double h = nb_devhalf_t(y, yd, lmu, L, g.r, g.tr, g.mt->ly);
+      double hc = fmax(h, 0.0);
+      double u = (yd > mu) ? hc : -hc;
+      c1 += (u < u_lo); c2 += (u > u_hi); c3 += (u > u_wl) & (u < u_wh);
+      hmax = fmax(hmax, hc);
+      bad |= !(h == h);
+    }
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    double v = warp_sum(acc);
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) out[row] = v;
+    if (!sigma_out) return;
+    bool ok = false;
+    if (cert) {
+      int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
+      int nb = __any_sync(FULL, bad);
+      double hm = warp_max(hmax);
+      if (lane == 0 && !nb) {
+        const double C = MAD_CONST / 0.6745;
+        double mx = sqrt(2.0 * hm);
+        double t = mx / (kh * C) * (1.0 + 1e-9);
+        // margins actually realised by the u-space thresholds
+        double room = fmin(d_of_u(u_lo) - d_of_u(u_wl), d_of_u(u_wh) - d_of_u(u_hi));
+        long long kl = (n - 1) / 2, ku = n / 2;
+        ok = (mx > 0.0) && (t <= room) && ((long long)a1 <= kl) && ((long long)a2 <= n - 1 - ku) && ((long long)a3 <= kl);
+      }
+    }
+    if (lane == 0) sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneState<K> st, double* out, const double* hint,
+                                                           double* sigma_out, double kh, int fastpath, long long n) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  OpLoglik<K> op;
+  op.st = st; op.out = out; op.hint = hint; op.sigma_out = sigma_out; op.kh = kh; op.fastpath = fastpath; op.n = n;
+  stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,7 +397,9 @@ __global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigm
 // ------------------------------------------------------------------------------------------------
 template <int K, bool HUBER>
 struct OpPass1 {
+  static constexpr bool PADS = false;
   static constexpr int KK = K * (K + 1) / 2;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
   GeneRegs<K> g;
   const double* sigma; double kh, khsig; bool hub;
@@ -314,23 +422,25 @@ struct OpPass1 {
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0.0;
   }
-  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
-    const double* w = tile; const double* rw = tile + K * CH;
-    double lmu = g.lmu(w, ci);
-    double mu = exp(lmu);
-    double s = 1.0 / (1.0 / mu + g.psi);  // sig.inv = 1/(exp(-lmu)+psi)
-    double Z = lmu + g.step * (((double)y + 0.01) / (mu + 0.01) - 1.0);
+  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
+    const double* w = tile; const double* rw = tile + K * CELLS;
+    double lmu = g.lmu(w, ti);
+    double mu = g.expm(lmu);
+    double yd = (double)y;
+    double s, q;
+    nb_siginv_ratio(yd, mu, g.psi, &s, &q);
+    double Z = fma(g.step, q - 1.0, lmu);
     double wt = s;
-    if (HUBER && hub) wt *= huber_w(khsig, nb_signdev(y, lmu, mu, g.r));  // warp-uniform branch
+    if (HUBER && hub) wt *= huber_w_half(khsig, nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt->ly));  // warp-uniform branch
     sw += wt; gz += Z;
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      double wi = wt * rw[i * CH + ci];
+      double wi = wt * rw[i * CELLS + ti];
       V[i] += wi;
       u[i] = fma(wi, Z, u[i]);
 #pragma unroll
-      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi, rw[jx * CH + ci], A[idx]); ++idx; }
+      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi, rw[jx * CELLS + ti], A[idx]); ++idx; }
     }
   }
   __device__ __forceinline__ void group_end(int j) {
@@ -352,17 +462,16 @@ struct OpPass1 {
   }
 };
 template <int K, bool HUBER>
-__global__ void __launch_bounds__(ROW_THREADS) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
-                                                       const double* sigma, double kh, double* A_out, double* u_out,
-                                                       double* sw_out, double* ZS, double* VS) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
+                                                          const double* sigma, double kh, double* A_out, double* u_out,
+                                                          double* sw_out, double* ZS, double* VS) {
   extern __shared__ double smem[];
-  __shared__ const double* wsets[2];
-  if (threadIdx.x == 0) { wsets[0] = st.W; wsets[1] = RMW; }
-  __syncthreads();
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
   OpPass1<K, HUBER> op;
   op.st = st; op.sigma = sigma; op.kh = kh;
   op.A_out = A_out; op.u_out = u_out; op.sw_out = sw_out; op.ZS = ZS; op.VS = VS;
-  stream_rows<K, 2>(geo, wsets, op, smem);
+  stream_rows<K, 2>(geo, &sh, op, smem);
 }
 
 // finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its
@@ -592,7 +701,8 @@ template <int K, bool HUBER>
 __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows, int n_ctl, long long Np,
                                                   const int* chunk_grp, const int* chunk_valid, CtlPack cp, int m,
                                                   const double* W_old, double* W_out, int cpc, double kh,
-                                                  long long pos_begin, long long pos_end) {
+                                                  long long pos_begin, long long pos_end, const int* cell_list,
+                                                  const int* cell_count) {
   constexpr int KK = K * (K + 1) / 2;
   constexpr int NACC = KK + K;
   extern __shared__ double dyn[];
@@ -600,7 +710,15 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
   __shared__ double sigma_c[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cell_i = tid % cpc, slice = tid / cpc, nsl = 256 / cpc;
-  const long long pos = pos_begin + (long long)blockIdx.x * cpc + cell_i;
+  // cells of this CTA: a contiguous run of positions, or entries of the fast kernel's failure list
+  const long long ncell = cell_list ? (long long)*cell_count : pos_end - pos_begin;
+  if ((long long)blockIdx.x * cpc >= ncell) return;
+  auto cell_pos = [&](int ci) -> long long {
+    long long idx = (long long)blockIdx.x * cpc + ci;
+    if (idx >= ncell) return pos_end;
+    return cell_list ? (long long)cell_list[idx] : pos_begin + idx;
+  };
+  const long long pos = cell_pos(cell_i);
   const bool inb = pos < pos_end;
   const int chunk = inb ? (int)(pos >> 7) : 0;
   const bool valid = inb && (int)(pos & (CH - 1)) < chunk_valid[chunk];
@@ -624,7 +742,7 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
     }
     __syncthreads();
     for (int ci = warp; ci < cpc; ci += 8) {
-      long long p2 = pos_begin + (long long)blockIdx.x * cpc + ci;
+      long long p2 = cell_pos(ci);
       bool v2 = p2 < pos_end && (int)(p2 & (CH - 1)) < chunk_valid[p2 >> 7];
       if (v2) {  // warp-uniform
         const double* d = dsm + (long long)ci * nstr;
@@ -692,7 +810,7 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
 #pragma unroll
       for (int i = 0; i < NACC; ++i) T[i] = red[((long long)w * cpc + tid) * NACC + i];
     }
-    long long p2 = pos_begin + (long long)blockIdx.x * cpc + tid;
+    long long p2 = cell_pos(tid);
     bool v2 = p2 < pos_end && (int)(p2 & (CH - 1)) < chunk_valid[p2 >> 7];
     if (p2 < pos_end) {
       double Wn[K];
@@ -709,11 +827,140 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
 }
 
 // ------------------------------------------------------------------------------------------------
+// K_w_update_fast: getW (R/ruvIIInb.R:380-390,732-744) for the cells whose per-cell Huber weights are
+// provably all 1 -- with k.huber = 100 that is every non-degenerate cell.  8 cells x 4 gene slices per
+// warp (a 32-byte sector of each control-gene row per load); no per-cell staging of the n_ctl deviances:
+//   sweep A  max|d| over the control genes  ->  t = max|d| / (k 1.4826/0.6745), bin width max|d|/64;
+//   sweep B  recomputes d, fills a 128-bin histogram on [-max, max] and accumulates the Gram / score
+//            with Huber weight 1;
+//   certificate: 2t < bin width, so (med - t, med + t) meets at most 2 bins (3 with rounding of edge
+//            elements); if no 3 adjacent bins hold more than (n-1)/2 elements then median|d - med| >= t,
+//            i.e. k sigma >= max|d| and every weight is exactly 1.
+// Cells that fail are appended to fail_list and redone by the exact kernel (k_w_update with a list).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl_rows, int n_ctl, long long Np,
+                                                       const int* chunk_grp, const int* chunk_valid, CtlPack cp,
+                                                       const double* ctl_tabR, const MathTabs* gtabs, int m,
+                                                       const double* W_old, double* W_out, double kh,
+                                                       long long pos_begin, long long pos_end, int* fail_count,
+                                                       int* fail_list) {
+  constexpr int KK = K * (K + 1) / 2;
+  constexpr int NACC = KK + K;
+  __shared__ MathTabs mt;
+  __shared__ unsigned hist[8][8][64];  // [warp][cell][128 bins x 16 bit]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const double* src = reinterpret_cast<const double*>(gtabs);
+    double* dst = reinterpret_cast<double*>(&mt);
+    for (int i = tid; i < (int)(sizeof(MathTabs) / 8); i += 256) dst[i] = src[i];
+    unsigned* h = &hist[0][0][0];
+    for (int i = tid; i < 8 * 8 * 64; i += 256) h[i] = 0;
+  }
+  __syncthreads();
+  const int cell = lane & 7, slice = lane >> 3;
+  const long long pos = pos_begin + ((long long)blockIdx.x * 8 + warp) * 8 + cell;
+  const bool inb = pos < pos_end;
+  const int chunk = inb ? (int)(pos >> 7) : 0;
+  const bool valid = inb && (int)(pos & (CH - 1)) < chunk_valid[chunk];
+  const int j = chunk_grp[chunk];
+  double wv[K];
+#pragma unroll
+  for (int l = 0; l < K; ++l) wv[l] = valid ? W_old[(long long)l * Np + pos] : 0.0;
+  // sweep A: max half deviance
+  double hmax = 0.0; int bad = 0;
+  if (valid) {
+    for (int gi = slice; gi < n_ctl; gi += 4) {
+      int y = ctl_rows[gi][pos];
+      double lmu = cp.gmean[gi] + cp.Mb[(long long)gi * m + j];
+#pragma unroll
+      for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
+      double mu = fexp(lmu, mt.ex);
+      double r = 1.0 / cp.psi[gi];
+      double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, mt.ly);
+      hmax = fmax(hmax, fmax(h, 0.0));
+      bad |= !(h == h);
+    }
+  }
+  hmax = fmax(hmax, __shfl_xor_sync(FULL, hmax, 8)); hmax = fmax(hmax, __shfl_xor_sync(FULL, hmax, 16));
+  bad |= __shfl_xor_sync(FULL, bad, 8); bad |= __shfl_xor_sync(FULL, bad, 16);
+  const double C = MAD_CONST / 0.6745;
+  const double mx = sqrt(2.0 * hmax);
+  const double t = mx / (kh * C) * (1.0 + 1e-9);
+  const double binw = mx / 64.0;
+  const bool certp = valid && !bad && mx > 0.0 && mx < 1.79769313486231570e308 && (2.0 * t < 0.98 * binw) && n_ctl < 65536;
+  const double scale = certp ? 64.0 / mx : 0.0;
+  // sweep B: histogram + Gram / score with weight sig.inv
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+  if (valid) {
+    unsigned* myh = hist[warp][cell];
+    for (int gi = slice; gi < n_ctl; gi += 4) {
+      int y = ctl_rows[gi][pos];
+      double yd = (double)y;
+      double gm = cp.gmean[gi];
+      double lmu = gm + cp.Mb[(long long)gi * m + j];
+#pragma unroll
+      for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
+      double mu = fexp(lmu, mt.ex);
+      double psi = cp.psi[gi];
+      if (certp) {
+        double r = 1.0 / psi;
+        double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, mt.ly);
+        double d = nb_signdev_from_half(h, yd, mu);
+        int b = (int)floor((d + mx) * scale);
+        b = b < 0 ? 0 : (b > 127 ? 127 : b);
+        atomicAdd(&myh[b >> 1], (b & 1) ? 65536u : 1u);
+      }
+      double s, q;
+      nb_siginv_ratio(yd, mu, psi, &s, &q);
+      double z = fma(cp.step[gi], q - 1.0, lmu) - gm;  // (Z - gmean)[ctl], :381
+      int idx = 0;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        double wa = s * cp.alpha_new[(long long)gi * K + i];
+        acc[KK + i] = fma(wa, z, acc[KK + i]);
+#pragma unroll
+        for (int jx = 0; jx <= i; ++jx) { acc[idx] = fma(wa, cp.alpha_new[(long long)gi * K + jx], acc[idx]); ++idx; }
+      }
+    }
+  }
+  __syncwarp();
+  // certificate: largest 3-adjacent-bin count of this cell; slice s scans bins [32 s, 32 s + 32)
+  unsigned best = 0;
+  if (certp) {
+    const unsigned* myh = hist[warp][cell];
+    auto cnt = [&](int b) -> unsigned { if (b < 0 || b > 127) return 0u; unsigned w = myh[b >> 1]; return (b & 1) ? (w >> 16) : (w & 0xffffu); };
+    for (int b = slice * 32; b < slice * 32 + 32; ++b) { unsigned v = cnt(b - 1) + cnt(b) + cnt(b + 1); best = v > best ? v : best; }
+  }
+  { unsigned o = __shfl_xor_sync(FULL, best, 8); best = o > best ? o : best; o = __shfl_xor_sync(FULL, best, 16); best = o > best ? o : best; }
+  const bool ok = certp && (long long)best <= ((long long)n_ctl - 1) / 2;
+  if (valid && !ok && slice == 0) { int p = atomicAdd(fail_count, 1); fail_list[p] = (int)pos; }
+  // reduce the gene slices, solve the sequential one-regressor WLS (forward substitution)
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) { acc[i] += __shfl_xor_sync(FULL, acc[i], 8); acc[i] += __shfl_xor_sync(FULL, acc[i], 16); }
+  if (slice == 0 && inb) {
+    double Wn[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double sN = acc[KK + i];
+#pragma unroll
+      for (int l = 0; l < i; ++l) sN -= acc[i * (i + 1) / 2 + l] * Wn[l];
+      Wn[i] = sN / acc[i * (i + 1) / 2 + i];
+      W_out[(long long)i * Np + pos] = valid ? Wn[i] : 0.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_pass2: per-gene per-group S0 = sum w, S1 = sum w (Z - alpha_new . W_new) for the gmean and Mb
 // updates (R/ruvIIInb.R:405-420): Z, sig.inv and the Huber weights are those of the OLD parameters.
 // ------------------------------------------------------------------------------------------------
 template <int K, bool HUBER>
 struct OpPass2 {
+  static constexpr bool PADS = false;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
   GeneRegs<K> g;
   const double* alpha_new; double an[K];
@@ -729,17 +976,19 @@ struct OpPass2 {
     if (HUBER) { khsig = kh * sigma[row]; hub = !(khsig > 1.79769313486231570e308); }
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; s0 = 0.0; s1 = 0.0; }
-  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
-    const double* w = tile; const double* wn = tile + K * CH;
-    double lmu = g.lmu(w, ci);
-    double mu = exp(lmu);
-    double s = 1.0 / (1.0 / mu + g.psi);
-    double Z = lmu + g.step * (((double)y + 0.01) / (mu + 0.01) - 1.0);
+  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
+    const double* w = tile; const double* wn = tile + K * CELLS;
+    double lmu = g.lmu(w, ti);
+    double mu = g.expm(lmu);
+    double yd = (double)y;
+    double s, q;
+    nb_siginv_ratio(yd, mu, g.psi, &s, &q);
+    double Z = fma(g.step, q - 1.0, lmu);
     double wt = s;
-    if (HUBER && hub) wt *= huber_w(khsig, nb_signdev(y, lmu, mu, g.r));
+    if (HUBER && hub) wt *= huber_w_half(khsig, nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt->ly));
     double res = Z;
 #pragma unroll
-    for (int l = 0; l < K; ++l) res = fma(-an[l], wn[l * CH + ci], res);
+    for (int l = 0; l < K; ++l) res = fma(-an[l], wn[l * CELLS + ti], res);
     s0 += wt;
     s1 = fma(wt, res, s1);
   }
@@ -750,17 +999,16 @@ struct OpPass2 {
   __device__ __forceinline__ void row_end(int) {}
 };
 template <int K, bool HUBER>
-__global__ void __launch_bounds__(ROW_THREADS) k_pass2(RowGeom geo, GeneState<K> st, const double* W_new,
-                                                       const double* alpha_new, const double* sigma,
-                                                       double kh, double* S0, double* S1) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState<K> st, const double* W_new,
+                                                          const double* alpha_new, const double* sigma,
+                                                          double kh, double* S0, double* S1) {
   extern __shared__ double smem[];
-  __shared__ const double* wsets[2];
-  if (threadIdx.x == 0) { wsets[0] = st.W; wsets[1] = W_new; }
-  __syncthreads();
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = W_new; }
   OpPass2<K, HUBER> op;
   op.st = st; op.alpha_new = alpha_new; op.sigma = sigma; op.kh = kh;
   op.S0 = S0; op.S1 = S1;
-  stream_rows<K, 2>(geo, wsets, op, smem);
+  stream_rows<K, 2>(geo, &sh, op, smem);
 }
 
 // gmean (R/ruvIIInb.R:405-415) and Mb (:418-420, rowWtAvg :667-675) from the group sums.
@@ -817,45 +1065,13 @@ __global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* n
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_loglik: per-gene NB log-likelihood (R/ruvIIInb.R:276-291)
-// ------------------------------------------------------------------------------------------------
-template <int K>
-struct OpLoglik {
-  GeneState<K> st;
-  GeneRegs<K> g;
-  double acc, lgr, rlogr;
-  double* out;
-  __device__ __forceinline__ void row_begin(int row, int) {
-    g.load(st, row); acc = 0.0; lgr = lgamma(g.r); rlogr = g.r * log(g.r);
-  }
-  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
-    double lmu = g.lmu(tile, ci);
-    double mu = exp(lmu);
-    acc += nb_logpmf(y, lmu, mu, g.r, lgr, rlogr);
-  }
-  __device__ __forceinline__ void group_end(int) {}
-  __device__ __forceinline__ void row_end(int row) {
-    double v = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) out[row] = v;
-  }
-};
-template <int K>
-__global__ void __launch_bounds__(ROW_THREADS) k_loglik(RowGeom geo, GeneState<K> st, double* out) {
-  extern __shared__ double smem[];
-  __shared__ const double* wsets[1];
-  if (threadIdx.x == 0) wsets[0] = st.W;
-  __syncthreads();
-  OpLoglik<K> op;
-  op.st = st; op.out = out;
-  stream_rows<K, 1>(geo, wsets, op, smem);
-}
-
-// ------------------------------------------------------------------------------------------------
 // K_init_coef: get.coef.wt (R/ruvIIInb.R:181-198,704-706): WLS of log(y+1) on [1, W], weights y+1
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct OpInit {
+  static constexpr bool PADS = false;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
+  GeneRegs<K> g;  // only the shared-table pointers are used
   static constexpr int P = K + 1;
   static constexpr int PP = P * (P + 1) / 2;
   double XtX[PP], Xty[P];
@@ -869,11 +1085,11 @@ struct OpInit {
   __device__ __forceinline__ void group_begin(int) {}
   __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
     double om = (double)y + 1.0;
-    double ly = log(om);
+    double ly = (y + 1 < YT) ? g.mt->ly[y + 1] : log(om);
     double x[P];
     x[0] = 1.0;
 #pragma unroll
-    for (int l = 0; l < K; ++l) x[l + 1] = tile[l * CH + ci];
+    for (int l = 0; l < K; ++l) x[l + 1] = tile[l * CELLS + ci];
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
@@ -903,14 +1119,13 @@ struct OpInit {
   }
 };
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS) k_init_coef(RowGeom geo, const double* W, double* gmean, double* alpha) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_init_coef(RowGeom geo, const double* W, double* gmean, double* alpha) {
   extern __shared__ double smem[];
-  __shared__ const double* wsets[1];
-  if (threadIdx.x == 0) wsets[0] = W;
-  __syncthreads();
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = W;
   OpInit<K> op;
   op.gmean = gmean; op.alpha = alpha;
-  stream_rows<K, 1>(geo, wsets, op, smem);
+  stream_rows<K, 1>(geo, &sh, op, smem);
 }
 // alpha.dev = alpha - colMeans(alpha) from the RAW alpha (:187-188), then NaN/Inf alpha -> 0 (:195)
 __global__ void k_init_adev(long long n, int K, const double* colsum, double Gtot, double* alpha, double* adev) {

@@ -1,6 +1,7 @@
 // ruvnb.cu -- C ABI of libruvnb_b200 (include/ruvnb.h): context, data upload, the NB IRLS operators
 // and the whole-fit driver.  sm_100a only; no CPU fallback anywhere in this file.
 #include "ctx.cuh"
+#include "winsor.cuh"
 
 extern "C" {
 
@@ -53,6 +54,15 @@ int ruvnb_kernel_time(const ruvnb_ctx* ctx, int which, double* ms_total, long lo
   return RUVNB_OK;
 }
 int ruvnb_last_exact_rows(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_rows : -1; }
+int ruvnb_last_exact_cells(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_cells : -1; }
+int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n) {
+  if (!x || !out || n < 0 || which < 0 || which > 1) return RUVNB_EARG;
+  static MathTabs mt;
+  static bool built = false;
+  if (!built) { build_math_tabs(&mt); built = true; }
+  for (int64_t i = 0; i < n; ++i) out[i] = which == 0 ? fexp(x[i], mt.ex) : flog(x[i], mt.rc, mt.lc);
+  return RUVNB_OK;
+}
 void* ruvnb_stream(const ruvnb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 void ruvnb_kernel_time_reset(ruvnb_ctx* ctx) {
   if (!ctx) return;
@@ -109,8 +119,11 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   ctx->group_chunk0.assign(m, 0);
   int nch = 0;
   for (int j = 0; j < m; ++j) { ctx->group_chunk0[j] = nch; nch += (ctx->group_n[j] + CH - 1) / CH; }
+  const int nch_real = nch;
+  nch = (nch + CHPAD - 1) / CHPAD * CHPAD;  // whole tiles: trailing chunks are empty (valid = 0)
   ctx->nchunks = nch; ctx->Np = (long long)nch * CH;
-  ctx->chunk_grp.assign(nch, 0); ctx->chunk_valid.assign(nch, 0);
+  ctx->chunk_grp.assign(nch, ctx->m - 1); ctx->chunk_valid.assign(nch, 0);
+  (void)nch_real;
   for (int j = 0; j < m; ++j) {
     int nc = (ctx->group_n[j] + CH - 1) / CH;
     for (int q = 0; q < nc; ++q) {
@@ -271,6 +284,51 @@ int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t
   return RUVNB_OK;
 }
 
+// H0: Winsorize + ceiling on the resident counts (R/ruvIIInb.R:53), rowSums(Y > 0) (:57)
+int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out) {
+  if (!ctx) return RUVNB_EARG;
+  if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "winsorize: no counts uploaded");
+  CK(cudaSetDevice(ctx->device));
+  const int Gl = ctx->Gl;
+  double* d_cap = nullptr; long long* d_nz = nullptr;
+  CK(cudaMalloc((void**)&d_cap, (size_t)Gl * 8));
+  CK(cudaMalloc((void**)&d_nz, (size_t)Gl * 8));
+  k_winsorize<<<Gl, WZ_NT, 0, ctx->stream>>>(ctx->dY, ctx->Np, ctx->N, 0.995, d_cap, d_nz);
+  CKL();
+  if (ctx->dYctl) {  // the replicated control-gene rows get the same treatment (same rows, same caps)
+    k_winsorize<<<ctx->n_ctl, WZ_NT, 0, ctx->stream>>>(ctx->dYctl, ctx->Np, ctx->N, 0.995, nullptr, nullptr);
+    CKL();
+  }
+  if (cap_out) CK(cudaMemcpyAsync(cap_out, d_cap, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nonzero_out) CK(cudaMemcpyAsync(nonzero_out, d_nz, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(d_cap)); CK(cudaFree(d_nz));
+  ctx->cur.sig_valid = false;
+  return RUVNB_OK;
+}
+
+// the resident (winsorized) counts of the local rows, gene-major Gl x N: the `counts` element of the
+// reference's return list (R/ruvIIInb.R:611,627)
+int ruvnb_get_counts(ruvnb_ctx* ctx, int32_t* Y_out) {
+  if (!ctx || !Y_out) return RUVNB_EARG;
+  if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "get_counts: no counts uploaded");
+  CK(cudaSetDevice(ctx->device));
+  const long long N = ctx->N;
+  long long slab = std::max(1ll, (256ll << 20) / (N * 4));
+  slab = std::min<long long>(slab, ctx->Gl);
+  int32_t* stage = nullptr;
+  CK(cudaMalloc((void**)&stage, (size_t)slab * N * 4));
+  for (long long r0 = 0; r0 < ctx->Gl; r0 += slab) {
+    long long nr = std::min<long long>(slab, ctx->Gl - r0);
+    k_unpermute_rows<<<nblk(nr * N, 256), 256, 0, ctx->stream>>>(ctx->dY + r0 * ctx->Np, nr, N, ctx->Np, ctx->d_cell2pos, stage);
+    CKL();
+    CK(cudaMemcpyAsync(Y_out + r0 * N, stage, (size_t)nr * N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(cudaFree(stage));
+  return RUVNB_OK;
+}
+
 }  // extern "C"
 
 // ---- state ----------------------------------------------------------------------------------------
@@ -283,6 +341,9 @@ static int alloc_set(ruvnb_ctx* ctx, StateSet* s) {
   RET(dev_alloc(ctx, &s->W, ctx->Np * ctx->K));
   RET(dev_alloc(ctx, &s->psi, Gl));
   RET(dev_alloc(ctx, &s->pi0, Gl));
+  RET(dev_alloc(ctx, &s->sigma, Gl));
+  CK(cudaMemsetAsync(s->sigma, 0, Gl * 8, ctx->stream));
+  s->sig_valid = false;
   CK(cudaMemsetAsync(s->gmean, 0, Gl * 8, ctx->stream));
   CK(cudaMemsetAsync(s->Mb, 0, Gl * ctx->m * 8, ctx->stream));
   CK(cudaMemsetAsync(s->alpha, 0, Gl * ctx->K * 8, ctx->stream));
@@ -324,7 +385,23 @@ static int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->amean, K));
   RET(dev_alloc(ctx, &ctx->S0, Gl * m));
   RET(dev_alloc(ctx, &ctx->S1, Gl * m));
-  RET(dev_alloc(ctx, &ctx->sigma, Gl));
+  RET(dev_alloc(ctx, &ctx->sigma_exact, Gl));
+  RET(dev_alloc(ctx, &ctx->hint, Gl * 3));
+  k_fill<<<nblk(Gl * 3, 256), 256, 0, ctx->stream>>>(ctx->hint, Gl * 3, -1.0);  // tg < 0: no hint yet
+  CKL();
+  RET(dev_alloc(ctx, &ctx->tabL, Gl * YT));
+  RET(dev_alloc(ctx, &ctx->tabR, Gl * YT));
+  RET(dev_alloc(ctx, &ctx->lgr, Gl));
+  RET(dev_alloc(ctx, &ctx->ctl_tabR, (long long)ctx->n_ctl * YT));
+  RET(dev_alloc(ctx, &ctx->w_fail, ctx->Np + 1));
+  CK(cudaMemsetAsync(ctx->w_fail, 0, sizeof(int), ctx->stream));
+  {
+    MathTabs mt;
+    build_math_tabs(&mt);
+    RET(dev_alloc(ctx, &ctx->d_mtabs, 1));
+    CK(cudaMemcpyAsync(ctx->d_mtabs, &mt, sizeof(MathTabs), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // mt is a stack object
+  }
   RET(dev_alloc(ctx, &ctx->Wbar, m * K));
   RET(dev_alloc(ctx, &ctx->RMW, ctx->Np * K));
   RET(dev_alloc(ctx, &ctx->sumsq, K));
@@ -348,7 +425,7 @@ static int state_lookup(ruvnb_ctx* ctx, const char* name, double** p, StateKind*
   else if (!strcmp(name, "pi0")) { *p = s.pi0; *kind = SK_VEC; }
   else if (!strcmp(name, "step")) { *p = ctx->step; *kind = SK_VEC; }
   else if (!strcmp(name, "loglik")) { *p = ctx->loglik; *kind = SK_VEC; }
-  else if (!strcmp(name, "sigma")) { *p = ctx->sigma; *kind = SK_VEC; }
+  else if (!strcmp(name, "sigma")) { *p = ctx->sigma_exact; *kind = SK_VEC; }
   else return ctx->fail(RUVNB_EARG, "unknown state name '%s'", name);
   return RUVNB_OK;
 }
@@ -376,6 +453,8 @@ int ruvnb_set_state(ruvnb_ctx* ctx, const char* name, const double* host, int k)
   }
   CK(cudaMemcpyAsync(p, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cur.sig_valid = false;                  // the Huber scale belongs to the parameters it was computed for
+  if (!strcmp(name, "psi")) ctx->psi_ver++;    // count tables follow psi
   return RUVNB_OK;
 }
 
@@ -406,6 +485,7 @@ static RowGeom geom(ruvnb_ctx* ctx, int nrows, const int* rowlist) {
   RowGeom g;
   g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid;
   g.nrows = nrows; g.rowlist = rowlist;
+  g.mtabs = ctx->d_mtabs; g.tabL = ctx->tabL; g.tabR = ctx->tabR; g.lgr = ctx->lgr;
   return g;
 }
 template <int K>
@@ -414,8 +494,17 @@ static GeneState<K> gstate(ruvnb_ctx* ctx, const StateSet& s, bool with_step) {
   st.gmean = s.gmean; st.Mb = s.Mb; st.alpha = s.alpha; st.psi = s.psi; st.step = with_step ? ctx->step : nullptr; st.W = s.W; st.m = ctx->m;
   return st;
 }
-static inline size_t tile_smem(int K, int nsets) { return (size_t)2 * nsets * K * CH * sizeof(double); }
+template <int K>
+static inline size_t tile_smem(int nsets) { return (size_t)2 * nsets * K * TileCfg<K>::CELLS * sizeof(double); }
 static inline unsigned row_grid(int nrows) { return (unsigned)((nrows + NWARP - 1) / NWARP); }
+// row-streaming launch: the double-buffered W tiles exceed the 48 KB default dynamic shared memory
+#define LAUNCH_ROWS(KERNEL, NSETS, NROWS, ...)                                                                   \
+  do {                                                                                                           \
+    const size_t smem_ = tile_smem<KT>(NSETS);                                                                   \
+    CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));                   \
+    KERNEL<<<row_grid(NROWS), ROW_THREADS, smem_, ctx->stream>>>(__VA_ARGS__);                                   \
+    CKL();                                                                                                       \
+  } while (0)
 
 static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   if (!ctx || !o) return RUVNB_EARG;
@@ -427,14 +516,28 @@ static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   return RUVNB_OK;
 }
 
-// per-gene log-likelihood of parameter set `s` into `out`; total (all ranks) into *total if non-null
-static int loglik_of(ruvnb_ctx* ctx, const StateSet& s, double* out, double* total) {
+// per-gene count tables for the dispersions in `psi` (rebuilt only when psi changed)
+static int ensure_ytabs(ruvnb_ctx* ctx, const double* psi) {
+  if (ctx->ytab_ver == ctx->psi_ver && ctx->ytab_psi != nullptr) return RUVNB_OK;
+  k_build_ytabs<<<ctx->Gl, YT, 0, ctx->stream>>>(psi, ctx->Gl, ctx->tabL, ctx->tabR, ctx->lgr);
+  CKL();
+  ctx->ytab_ver = ctx->psi_ver; ctx->ytab_psi = psi;
+  return RUVNB_OK;
+}
+
+// per-gene log-likelihood of parameter set `s` into `out` (R/ruvIIInb.R:276-291) and, in the same sweep, the
+// Huber certificate of `s` (s.sigma: +Inf certified / 0 to be evaluated exactly); total (all ranks) into
+// *total if non-null
+static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* out, double* total) {
+  const double kh = o->robust ? 1.345 : 100.0;  // :155
+  RET(ensure_ytabs(ctx, s.psi));
   KEV_BEGIN(4);
   DISPATCH_K(ctx->K, {
-    k_loglik<KT><<<row_grid(ctx->Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), out);
-    CKL();
+    LAUNCH_ROWS(k_loglik<KT>, 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), out, ctx->hint, s.sigma, kh,
+                o->huber_fastpath, (long long)ctx->N);
   });
   KEV_END(4);
+  s.sig_valid = true; s.maybe_active = false;
   if (total) {
     k_colsum<<<1, 1024, 0, ctx->stream>>>(out, ctx->Gl, 1, ctx->scal);
     CKL();
@@ -447,47 +550,43 @@ static int loglik_of(ruvnb_ctx* ctx, const StateSet& s, double* out, double* tot
   return RUVNB_OK;
 }
 
-// sigma_g for every local row of `s`: +Inf where the certificate proves all Huber weights are 1,
-// else the exact mad/0.6745 (R/ruvIIInb.R:713).  *nfail = rows that needed the exact path.
-static int row_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, const StateSet& s, double kh, int* nfail) {
+// complete s.sigma: rows the certificate sweep left at 0 get the exact mad/0.6745 (R/ruvIIInb.R:713) -- or +Inf
+// when that exact value proves every weight is 1.  *nfail = rows evaluated exactly, *nactive = rows whose
+// Huber weights are live (finite sigma) afterwards.
+static int complete_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double kh, int* nfail, int* nactive) {
   const int Gl = ctx->Gl;
-  CK(cudaMemsetAsync(ctx->flags + 4, 0, sizeof(int), ctx->stream));
-  if (o->huber_fastpath) {
-    KEV_BEGIN(0);
-    DISPATCH_K(ctx->K, {
-      k_devstats<KT><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, Gl, nullptr), gstate<KT>(ctx, s, false), kh, ctx->sigma, ctx->flags + 4);
-      CKL();
-    });
-    KEV_END(0);
-  } else {
-    CK(cudaMemsetAsync(ctx->sigma, 0, (size_t)Gl * 8, ctx->stream));  // 0 == "not certified"
-  }
-  k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, ctx->sigma, ctx->faillist, ctx->flags + 4);
+  k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, s.sigma, ctx->faillist, ctx->flags + 4, nullptr);
   CKL();
   CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   kev_collect(ctx);
   const int nf = ctx->h_flags[4];
   *nfail = nf;
-  if (nf == 0) return RUVNB_OK;
-  // exact path in batches of rows through the deviance scratch (<= 2 GB)
-  long long batch = std::max(8ll, (2ll << 30) / (ctx->Np * 8));
-  batch = std::min<long long>(batch, nf);
-  if (ctx->D_rows < batch) {
-    RET(dev_alloc(ctx, &ctx->D, batch * ctx->Np));  // grows at most once per problem (first call sizes it)
-    ctx->D_rows = batch;
-  }
-  KEV_BEGIN(5);
-  for (long long r0 = 0; r0 < nf; r0 += ctx->D_rows) {
-    int nr = (int)std::min<long long>(ctx->D_rows, nf - r0);
-    DISPATCH_K(ctx->K, {
-      k_signdev<KT><<<row_grid(nr), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, nr, ctx->faillist + r0), gstate<KT>(ctx, s, false), ctx->D);
+  if (nf > 0) {
+    // exact path in batches of rows through the deviance scratch (<= 2 GB)
+    long long batch = std::max(8ll, (2ll << 30) / (ctx->Np * 8));
+    batch = std::min<long long>(batch, Gl);
+    if (ctx->D_rows < std::min<long long>(batch, nf)) {
+      // first call sizes the scratch for a full batch so that it never grows again
+      RET(dev_alloc(ctx, &ctx->D, batch * ctx->Np));
+      RET(dev_alloc(ctx, &ctx->rowmax, batch));
+      RET(dev_alloc(ctx, &ctx->rownan, batch));
+      ctx->D_rows = batch;
+    }
+    KEV_BEGIN(5);
+    for (long long r0 = 0; r0 < nf; r0 += ctx->D_rows) {
+      int nr = (int)std::min<long long>(ctx->D_rows, nf - r0);
+      DISPATCH_K(ctx->K, {
+        LAUNCH_ROWS(k_signdev<KT>, 1, nr, geom(ctx, nr, ctx->faillist + r0), gstate<KT>(ctx, s, false), ctx->D, ctx->rowmax, ctx->rownan);
+      });
+      k_row_sigma<<<nr, RS_NT, 0, ctx->stream>>>(ctx->D, ctx->Np, (long long)ctx->N, ctx->faillist + r0, ctx->rowmax, ctx->rownan, kh,
+                                                 o->huber_fastpath, s.sigma, ctx->sigma_exact, ctx->hint);
       CKL();
-    });
-    k_row_sigma<<<nr, 256, 0, ctx->stream>>>(ctx->D, ctx->Np, ctx->d_chunk_valid, ctx->faillist + r0, ctx->sigma, nullptr);
-    CKL();
+    }
+    KEV_END(5);
   }
-  KEV_END(5);
+  if (nf > 0) s.maybe_active = true;  // finite sigmas can only come from the exact path
+  *nactive = s.maybe_active ? 1 : 0;
   return RUVNB_OK;
 }
 
@@ -507,19 +606,20 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   const double kh = o->robust ? 1.345 : 100.0;  // :155
   StateSet& c = ctx->cur; StateSet& n = ctx->nw;
   CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
-  // Huber scale of the current state (:713,723,409)
-  int nfail = 0;
-  RET(row_sigma(ctx, o, c, kh, &nfail));
-  ctx->last_fail_rows = nfail;
-  const bool hub = nfail > 0;
+  RET(ensure_ytabs(ctx, c.psi));
+  // Huber scale of the current state (:713,723,409): normally left by the log-likelihood sweep that scored it
+  if (!c.sig_valid) RET(loglik_of(ctx, o, c, ctx->loglik, nullptr));
+  int nfail = 0, nactive = 0;
+  RET(complete_sigma(ctx, o, c, kh, &nfail, &nactive));
+  ctx->last_fail_rows = nfail; ctx->last_active_rows = nactive;
+  const bool hub = nactive > 0;
   // alpha ------------------------------------------------------------------------------------------
   RET(make_rmw(ctx, c.W));
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(1);
-    if (hub) k_pass1<KT, true><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, ctx->RMW, ctx->sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
-    else k_pass1<KT, false><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, ctx->RMW, ctx->sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
-    CKL();
+    if (hub) LAUNCH_ROWS((k_pass1<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    else LAUNCH_ROWS((k_pass1<KT, false>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
     KEV_END(1);
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
     CKL();
@@ -561,23 +661,39 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     k_gather_rows<<<nblk((long long)nc * m, 256), 256, 0, ctx->stream>>>(c.Mb, ctx->d_ctl_local, nc, m, p_mb); CKL();
     RET(allreduce(ctx, pk, (size_t)nc * (3 + 2 * K + m), NCCL_F64));
     cp.gmean = p_gmean; cp.psi = p_psi; cp.step = p_step; cp.alpha_old = p_aold; cp.alpha_new = p_anew; cp.Mb = p_mb;
-    // cells per CTA: the per-cell deviance rows of all control genes must fit shared memory
+    // cells are sharded over the ranks in whole chunks; the slices are summed (disjoint) afterwards
+    long long ch_per = (ctx->nchunks + ctx->nranks - 1) / ctx->nranks;
+    long long pb = std::min<long long>(ctx->Np, ch_per * ctx->rank * CH), pe = std::min<long long>(ctx->Np, ch_per * (ctx->rank + 1) * CH);
+    if (ctx->nranks > 1) CK(cudaMemsetAsync(n.W, 0, (size_t)ctx->Np * K * 8, ctx->stream));
+    // exact kernel geometry: the per-cell deviance rows of all control genes must fit shared memory
     const int NACC = KK + K;
     int cpc = 32;
     const long long nstr = nc | 1;
     while (cpc > 1 && (size_t)cpc * nstr * 8 > (size_t)200 * 1024) cpc >>= 1;
     if ((size_t)cpc * nstr * 8 > (size_t)200 * 1024) return ctx->fail(RUVNB_ENOMEM, "n_ctl = %d control genes exceed the per-cell shared-memory tile (max 25600)", nc);
     size_t smem = std::max<size_t>((size_t)cpc * (size_t)nstr * 8, (size_t)8 * cpc * NACC * 8);
-    // cells are sharded over the ranks in whole chunks; the slices are summed (disjoint) afterwards
-    long long ch_per = (ctx->nchunks + ctx->nranks - 1) / ctx->nranks;
-    long long pb = std::min<long long>(ctx->Np, ch_per * ctx->rank * CH), pe = std::min<long long>(ctx->Np, ch_per * (ctx->rank + 1) * CH);
-    if (ctx->nranks > 1) CK(cudaMemsetAsync(n.W, 0, (size_t)ctx->Np * K * 8, ctx->stream));
     if (pe > pb) {
       KEV_BEGIN(2);
+      const bool fast = o->huber_fastpath && !o->robust;
+      if (fast) {
+        k_build_ytabs<<<nc, YT, 0, ctx->stream>>>(p_psi, nc, nullptr, ctx->ctl_tabR, nullptr); CKL();
+        CK(cudaMemsetAsync(ctx->w_fail, 0, sizeof(int), ctx->stream));
+      }
       DISPATCH_K(K, {
         CK(cudaFuncSetAttribute(k_w_update<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_w_update<KT, true><<<nblk(pe - pb, cpc), 256, smem, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, m, c.W, n.W, cpc, kh, pb, pe);
-        CKL();
+        if (fast) {
+          k_w_update_fast<KT><<<nblk(pe - pb, 64), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, ctx->ctl_tabR,
+                                                                        ctx->d_mtabs, m, c.W, n.W, kh, pb, pe, ctx->w_fail, ctx->w_fail + 1);
+          CKL();
+          // cells whose certificate failed: exact per-cell MAD (CTAs beyond the failure count exit at once)
+          k_w_update<KT, true><<<nblk(pe - pb, cpc), 256, smem, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, m, c.W, n.W,
+                                                                              cpc, kh, pb, pe, ctx->w_fail + 1, ctx->w_fail);
+          CKL();
+        } else {
+          k_w_update<KT, true><<<nblk(pe - pb, cpc), 256, smem, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, m, c.W, n.W,
+                                                                              cpc, kh, pb, pe, nullptr, nullptr);
+          CKL();
+        }
       });
       KEV_END(2);
     }
@@ -590,9 +706,8 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(3);
-    if (hub) k_pass2<KT, true><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, n.W, n.alpha, ctx->sigma, kh, ctx->S0, ctx->S1);
-    else k_pass2<KT, false><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 2), ctx->stream>>>(geom(ctx, Gl, nullptr), st, n.W, n.alpha, ctx->sigma, kh, ctx->S0, ctx->S1);
-    CKL();
+    if (hub) LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+    else LAUNCH_ROWS((k_pass2<KT, false>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
     KEV_END(3);
   });
   k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
@@ -601,11 +716,13 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   // psi, pi0 unchanged inside the inner loop
   CK(cudaMemcpyAsync(n.psi, c.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  // candidate log-likelihood (:469-484)
-  RET(loglik_of(ctx, n, ctx->loglik_tmp, logl_new));
+  // candidate log-likelihood (:469-484) + its Huber certificate for the next iteration
+  RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new));
   CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_flags + 6, ctx->w_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (bad) { bad[0] = ctx->h_flags[0]; bad[1] = ctx->h_flags[1]; bad[2] = ctx->h_flags[2]; }
+  ctx->last_fail_cells = ctx->h_flags[6];
   std::swap(ctx->cur, ctx->nw);
   return RUVNB_OK;
 }
@@ -619,6 +736,8 @@ static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
   CK(cudaMemcpyAsync(dst.W, src.W, (size_t)ctx->Np * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.psi, src.psi, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.pi0, src.pi0, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.sigma, src.sigma, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active;
   return RUVNB_OK;
 }
 
@@ -629,8 +748,7 @@ int ruvnb_init_coef(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   const int Gl = ctx->Gl, K = ctx->K;
   StateSet& c = ctx->cur;
   DISPATCH_K(K, {
-    k_init_coef<KT><<<row_grid(Gl), ROW_THREADS, tile_smem(KT, 1), ctx->stream>>>(geom(ctx, Gl, nullptr), c.W, c.gmean, c.alpha);
-    CKL();
+    LAUNCH_ROWS(k_init_coef<KT>, 1, Gl, geom(ctx, Gl, nullptr), c.W, c.gmean, c.alpha);
   });
   // alpha.dev = alpha - colMeans(alpha) over ALL genes (:187-188), then NaN/Inf alpha -> 0 (:195)
   k_colsum<<<1, 1024, 0, ctx->stream>>>(c.alpha, Gl, K, ctx->red); CKL();
@@ -639,12 +757,13 @@ int ruvnb_init_coef(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   CK(cudaMemsetAsync(c.Mb, 0, (size_t)Gl * ctx->m * 8, ctx->stream));  // :191
   CK(cudaMemsetAsync(c.pi0, 0, (size_t)Gl * 8, ctx->stream));         // :202
   CK(cudaStreamSynchronize(ctx->stream));
+  c.sig_valid = false;
   return RUVNB_OK;
 }
 
 int ruvnb_loglik(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total) {
   RET(check_ready(ctx, o));
-  return loglik_of(ctx, ctx->cur, ctx->loglik, total);
+  return loglik_of(ctx, o, ctx->cur, ctx->loglik, total);
 }
 
 int ruvnb_irls_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
@@ -706,6 +825,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
       for (int g = 0; g < Gl; ++g) tmp[g] = std::isfinite(src[g]) ? src[g] : old[g];  // :564
       CK(cudaMemcpyAsync(target.psi, tmp.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
+      ctx->psi_ver++; target.sig_valid = false;
       return RUVNB_OK;
     }
     cudaEvent_t d0, d1;
@@ -716,6 +836,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
     int r = ruvnb_estimate_disp(ctx, o, nullptr);
     if (&target != &ctx->cur) std::swap(ctx->cur, target);
     RET(r);
+    ctx->psi_ver++; target.sig_valid = false;
     CK(cudaEventRecord(d1, ctx->stream));
     CK(cudaEventSynchronize(d1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, d0, d1)); disp_ms += ms;
@@ -733,7 +854,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
     iter_outer++;
     std::vector<double> logl_beta;
     double s_old = 0.0;
-    RET(loglik_of(ctx, ctx->cur, ctx->loglik, &s_old));  // :276-291
+    RET(loglik_of(ctx, o, ctx->cur, ctx->loglik, &s_old));  // :276-291
     k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :293
     RET(copy_set(ctx, ctx->best, ctx->cur));                                    // :296
     int iter = 1, halving = 0;
@@ -784,7 +905,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
     RET(copy_set(ctx, ctx->cur, ctx->best));  // :568-573
     if (updt) RET(refresh_psi(ctx->cur));
     double s = 0.0;
-    RET(loglik_of(ctx, ctx->cur, ctx->loglik, &s));  // :577-593
+    RET(loglik_of(ctx, o, ctx->cur, ctx->loglik, &s));  // :577-593
     lo.push_back(s);
     if (logl_outer && iter_outer <= o->outer_maxit) logl_outer[iter_outer - 1] = s;
     if (o->verbose) fprintf(stderr, "Outer Iter %d logl-likelihood:%.10g\n", iter_outer, s);

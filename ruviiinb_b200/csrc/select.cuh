@@ -125,3 +125,117 @@ __device__ void group_median_mad(int len, Val val, Valid valid, SelScratch* sc, 
   *med_out = med;
   *mad_out = MAD_CONST * mad;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CTA-wide exact selection over a long global array (the exact-MAD path of a gene row, N ~ 1e5):
+// 12-bit radix descent that stops as soon as the bucket holding the wanted rank has <= RS_CAP keys,
+// gathers that bucket into shared memory and ranks it there.  Typical cost: 2 histogram passes +
+// 1 gather pass over the row (the previous 8-bit select took 9).  Returns BOTH middle order
+// statistics (ranks (n-1)/2 and n/2) so that R's even-n median needs no extra pass.
+// ------------------------------------------------------------------------------------------------
+#define RS_NT 512
+#define RS_BINS 4096
+#define RS_CAP 1024
+struct RowSelScratch {
+  unsigned hist[RS_BINS];
+  unsigned long long buf[RS_CAP];
+  unsigned wtot[RS_NT / 32];
+  unsigned long long red[RS_NT / 32];
+  unsigned bucket, below, cnt, nbuf;
+  unsigned long long out_hi, out_lo;
+};
+
+// key(i) for i in [0, len), len a multiple of RS_NT; n = number of real items (the rest are +Inf pads
+// that sort last); ranks are 0-based.  All RS_NT threads call with identical arguments.
+template <class KeyFn>
+__device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* sc, unsigned long long* klo_out,
+                                unsigned long long* khi_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long prefix = 0, pmask = 0;
+  long long rank = n / 2;
+  unsigned cnt = 0;
+  int shift = 64;
+  for (int level = 0; level < 6; ++level) {
+    const int bits = (level < 5) ? 12 : 4;
+    shift -= bits;
+    const int nb = 1 << bits;
+    for (int i = tid; i < nb; i += RS_NT) sc->hist[i] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < len; i0 += RS_NT) {
+      unsigned long long kx = key(i0 + tid);
+      bool ok = (kx & pmask) == prefix;
+      int b = ok ? (int)((kx >> shift) & (unsigned long long)(nb - 1)) : nb + lane;
+      unsigned peers = __match_any_sync(FULL, b);
+      if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    // locate the bucket holding `rank`: thread t owns bins [t*per, (t+1)*per)
+    const int per = (nb + RS_NT - 1) / RS_NT;  // 8 (or 1 for the 16-bin level; threads >= nb own nothing)
+    unsigned loc = 0;
+    for (int q = 0; q < per; ++q) { int bi = tid * per + q; if (bi < nb) loc += sc->hist[bi]; }
+    unsigned inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) sc->wtot[warp] = inc;
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < warp; ++w) base += sc->wtot[w];
+    unsigned excl = base + inc - loc;
+    if ((long long)excl <= rank && rank < (long long)excl + loc) {
+      unsigned acc = excl;
+      for (int q = 0; q < per; ++q) {
+        int bi = tid * per + q;
+        unsigned h = (bi < nb) ? sc->hist[bi] : 0;
+        if (rank < (long long)acc + h) { sc->bucket = (unsigned)bi; sc->below = acc; sc->cnt = h; break; }
+        acc += h;
+      }
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)sc->bucket << shift;
+    pmask |= (unsigned long long)(nb - 1) << shift;
+    rank -= (long long)sc->below;
+    cnt = sc->cnt;
+    __syncthreads();
+    if (cnt <= RS_CAP) break;
+  }
+  // gather the bucket; largest key below it
+  if (tid == 0) sc->nbuf = 0;
+  __syncthreads();
+  unsigned long long bmax = 0;
+  const bool fits = cnt <= RS_CAP;
+  for (int i0 = 0; i0 < len; i0 += RS_NT) {
+    unsigned long long kx = key(i0 + tid);
+    unsigned long long mk = kx & pmask;
+    if (mk == prefix) {
+      if (fits) { unsigned p = atomicAdd(&sc->nbuf, 1u); sc->buf[p] = kx; }
+    } else if (mk < prefix) {
+      bmax = kx > bmax ? kx : bmax;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(FULL, bmax, o); bmax = t > bmax ? t : bmax; }
+  if (lane == 0) sc->red[warp] = bmax;
+  __syncthreads();
+  bmax = 0;
+  for (int w = 0; w < RS_NT / 32; ++w) bmax = sc->red[w] > bmax ? sc->red[w] : bmax;
+  if (!fits) {
+    // > RS_CAP identical keys: all 64 bits are resolved and the bucket is one value
+    *khi_out = prefix;
+    *klo_out = rank >= 1 ? prefix : bmax;
+    __syncthreads();
+    return;
+  }
+  if (tid == 0) { sc->out_lo = bmax; sc->out_hi = 0; }
+  __syncthreads();
+  for (unsigned i = tid; i < cnt; i += RS_NT) {
+    unsigned long long x = sc->buf[i];
+    unsigned lt = 0, eq = 0;
+    for (unsigned j = 0; j < cnt; ++j) { unsigned long long yk = sc->buf[j]; lt += yk < x; eq += yk == x; }
+    if ((long long)lt <= rank && rank < (long long)lt + eq) sc->out_hi = x;
+    if (rank >= 1 && (long long)lt <= rank - 1 && rank - 1 < (long long)lt + eq) sc->out_lo = x;
+  }
+  __syncthreads();
+  *khi_out = sc->out_hi;
+  *klo_out = sc->out_lo;
+  __syncthreads();
+}
