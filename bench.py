@@ -37,6 +37,8 @@ WORKLOADS = {
     "tiny_256x2k": (256, 2048, 2, 3, 64),
 }
 SEED = 20261019 + 2
+# FP64-pipe instructions per element of each sweep at k = 5 (ncu smsp__inst_executed_pipe_fp64 / elements, profiles/)
+FP64_INSTR = {"pass1": 68.0, "pass2": 40.0, "loglik": 45.0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -290,11 +292,13 @@ def main():
     if rank == 0:
         clocks.start()
     e0.record(stream)
-    logls = []
+    logls, exact_rows_steps, exact_cells_steps = [], [], []
     for _ in range(args.steps):
         ll, bad = ctx.irls_iteration(opts)
         ctx.accept()
         logls.append(ll)
+        exact_rows_steps.append(ctx.last_exact_rows)
+        exact_cells_steps.append(ctx.last_exact_cells)
     e1.record(stream)
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -302,6 +306,7 @@ def main():
     launches = ctx.kernel_launches - l0
     exact_rows = ctx.last_exact_rows
     ktimes = ctx.kernel_times()
+    fp64_peak = ctx.measure_fp64() if rank == 0 else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -363,13 +368,17 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sweep_bytes[dom],
-                "note": "FP64-pipe-bound sweep (DESIGN.md section 5): ~130 DFMA-equivalents per element against an HBM budget of ~11",
+                "note": "FP64-pipe-bound sweep (DESIGN.md section 5): the HBM budget is ~11 FP64 instructions per element",
+                "fp64": {"peak_tflops_measured": fp64_peak, "instr_per_element": FP64_INSTR.get(dom),
+                         "achieved_tflops": (2.0 * FP64_INSTR[dom] * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12) if dom in FP64_INSTR else None,
+                         "frac": (2.0 * FP64_INSTR[dom] * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12 / fp64_peak) if dom in FP64_INSTR and fp64_peak else None,
+                         "what": "FP64-pipe instructions per element counted from ncu (profiles/), 2 flops each, against the DFMA-chain peak measured in this run"},
                 "kernels": kern}
 
     line = {"metric": "NB IRLS gene-fits/sec", "value": value, "unit": "gene-fits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk,
-            "gpu_launches": int(launches), "exact_mad_rows_last_step": exact_rows, "roofline": roofline, "logl_trace": logls, "datagen_seconds": t_gen}
+            "gpu_launches": int(launches), "exact_mad_rows_per_step": exact_rows_steps, "exact_mad_cells_per_step": exact_cells_steps, "roofline": roofline, "logl_trace": logls, "datagen_seconds": t_gen}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

@@ -109,6 +109,9 @@ void* ruvnb_stream(const ruvnb_ctx* ctx);
 /* Gene rows / cells of the last ruvnb_irls_iteration whose Huber certificate failed (exact MAD computed). */
 int ruvnb_last_exact_rows(const ruvnb_ctx* ctx);
 int ruvnb_last_exact_cells(const ruvnb_ctx* ctx);
+/* Measured FP64 FMA throughput of the context's device in TFLOP/s (2 flops per DFMA; a register-only DFMA-chain
+ * kernel, best of 5): the denominator of the FP64 roofline bench.py reports beside the HBM one. */
+int ruvnb_measure_fp64(ruvnb_ctx* ctx, double* tflops);
 /* Host evaluation of the table-driven exp (which = 0) / log (which = 1) the kernels use (csrc/fastmath.cuh is
  * __host__ __device__): lets the CPU test-suite check the very source the GPU runs.  No device needed. */
 int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n);

@@ -79,13 +79,21 @@ __device__ __forceinline__ double nb_logpmf(int y, double lmu, double mu, double
 // ly: log(y) for y < YT (MathTabs.ly, shared by all genes); tr: the gene's log(y + r) for y < YT.
 // Half deviance  y (log y - lmu) - (y + r)(log(y + r) - L),  L = log(mu + r): the same conditioned form
 // as nb_signdev above with the two logs of integer arguments looked up.
-// out-of-table counts (y >= YT): libdevice, kept out of line so that the hot loops stay small
-__device__ __noinline__ void nb_slow_logs(double yd, double r, double* lyr, double* lyy) { *lyr = log(yd + r); *lyy = log(yd); }
+// out-of-table counts (y >= YT): table-driven logs + Stirling (lgamma_big); libdevice only outside their range
+__device__ __forceinline__ void nb_big_logs(double yd, double r, const MathTabs* mt, double* lyr, double* lyy) {
+  *lyr = flog(yd + r, mt->rc, mt->lc);
+  *lyy = flog(yd, mt->rc, mt->lc);
+}
 __device__ __noinline__ double nb_slow_lgterm(double yd, double r, double lgr) { return lgamma(yd + r) - lgr - lgamma(yd + 1.0); }
+__device__ __forceinline__ double nb_big_lgterm(double yd, double r, double lgr, const MathTabs* mt) {
+  if (!(r < 1e100 && yd < 1e15)) return nb_slow_lgterm(yd, r, lgr);
+  double a = yd + r, b = yd + 1.0;
+  return lgamma_big(a, flog_nc(a, mt->rc, mt->lc)) - lgr - lgamma_big(b, flog_nc(b, mt->rc, mt->lc));
+}
 __device__ __forceinline__ double nb_devhalf_t(int y, double yd, double lmu, double L, double r,
-                                               const double* __restrict__ tr, const double* __restrict__ ly) {
+                                               const double* __restrict__ tr, const MathTabs* mt) {
   double lyr, lyy;
-  if (y < YT) { lyr = tr[y]; lyy = ly[y]; } else { nb_slow_logs(yd, r, &lyr, &lyy); }
+  if (y < YT) { lyr = tr[y]; lyy = mt->ly[y]; } else { nb_big_logs(yd, r, mt, &lyr, &lyy); }
   double t = -(yd + r) * (lyr - L);
   if (y > 0) t = fma(yd, lyy - lmu, t);
   return t;
@@ -106,10 +114,10 @@ __device__ __forceinline__ double huber_w_half(double khsig, double t) {
 }
 // log dnbinom(y; mu, size = r): tl = the gene's lgamma(y+r) - lgamma(r) - lgamma(y+1) for y < YT
 __device__ __forceinline__ double nb_logpmf_t(int y, double yd, double lmu, double L, double r, double lgr, double rlogr,
-                                              const double* __restrict__ tl) {
+                                              const double* __restrict__ tl, const MathTabs* mt) {
   double v = fma(-r, L, rlogr);
   if (y > 0) {
-    double g = (y < YT) ? tl[y] : nb_slow_lgterm(yd, r, lgr);
+    double g = (y < YT) ? tl[y] : nb_big_lgterm(yd, r, lgr, mt);
     v += fma(yd, lmu - L, g);
   }
   if (!(fabs(v) <= 1.79769313486231570e308)) v = LOG_DBL_MIN;  // NaN or +-Inf (R/ruvIIInb.R:290)
@@ -117,6 +125,25 @@ __device__ __forceinline__ double nb_logpmf_t(int y, double yd, double lmu, doub
 }
 // sig.inv = 1/(exp(-lmu) + psi) = mu/(1 + psi mu) and the working-response ratio (y + .01)/(mu + .01)
 // (R/ruvIIInb.R:305,321) with ONE reciprocal: both share the denominator (1 + psi mu)(mu + .01).
+struct SQ { double mu, s, q; };
+// the reference's own formulas with libdevice: out-of-range arguments (rare), kept out of line
+__device__ __noinline__ SQ nb_sq_slow(double yd, double lmu, double psi) {
+  SQ o;
+  o.mu = exp(lmu);
+  o.s = 1.0 / (1.0 / o.mu + psi);
+  o.q = (yd + 0.01) / (o.mu + 0.01);
+  return o;
+}
+// fast form; the caller guarantees |lmu| < 230 and psi in [1e-100, 1e100]
+__device__ __forceinline__ void nb_sq_fast(double yd, double lmu, double psi, const double* __restrict__ ex, double* mu,
+                                           double* s, double* q) {
+  double m = fexp_nc(lmu, ex);
+  double a = fma(psi, m, 1.0), b = m + 0.01;
+  double inv = frcp(a * b);
+  *mu = m;
+  *s = (m * b) * inv;
+  *q = ((yd + 0.01) * a) * inv;
+}
 __device__ __forceinline__ void nb_siginv_ratio(double yd, double mu, double psi, double* s, double* q) {
   if (!(mu < 1e100)) {  // overflowed / NaN mu: the reference's own formulas (rare, warp-divergent)
     *s = 1.0 / (1.0 / mu + psi);

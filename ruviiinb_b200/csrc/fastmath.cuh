@@ -55,8 +55,13 @@ static inline double fm_mk_(int h, int l) { int64_t b = (int64_t)(((uint64_t)(ui
 __host__ __device__ FM_NOINLINE static double fm_slow_exp(double x) { return exp(x); }
 __host__ __device__ FM_NOINLINE static double fm_slow_log(double v) { return log(v); }
 
+__host__ __device__ __forceinline__ double fexp_nc(double x, const double* __restrict__ ex);
 __host__ __device__ __forceinline__ double fexp(double x, const double* __restrict__ ex) {
   if (!(fabs(x) < 700.0)) return fm_slow_exp(x);  // overflow / underflow / NaN: libm path (rare), out of line
+  return fexp_nc(x, ex);
+}
+// no range check: the caller guarantees |x| < 700
+__host__ __device__ __forceinline__ double fexp_nc(double x, const double* __restrict__ ex) {
   const double MAGIC = 6755399441055744.0;     // 1.5 * 2^52: the integer lands in the low word
   const double L2E128 = 184.6649652337873;     // 128 / ln 2
   const double C_HI = 0.005415212333900854;    // ln2/128 with the low 24 mantissa bits zero (0x3f762e42fe000000)
@@ -76,8 +81,13 @@ __host__ __device__ __forceinline__ double fexp(double x, const double* __restri
   return FM_MK(FM_HI(v) + (e << 20), FM_LO(v));
 }
 
+__host__ __device__ __forceinline__ double flog_nc(double v, const double* __restrict__ rc, const double* __restrict__ lc);
 __host__ __device__ __forceinline__ double flog(double v, const double* __restrict__ rc, const double* __restrict__ lc) {
   if (!(v > 1e-300 && v < 1e300)) return fm_slow_log(v);  // zero, subnormal, negative, Inf, NaN: libm path
+  return flog_nc(v, rc, lc);
+}
+// no range check: the caller guarantees a normal positive finite v
+__host__ __device__ __forceinline__ double flog_nc(double v, const double* __restrict__ rc, const double* __restrict__ lc) {
   int hi = FM_HI(v);
   int e = (hi >> 20) - 1023;
   int j = (hi >> 13) & (FM_NT - 1);
@@ -105,4 +115,11 @@ __host__ __device__ __forceinline__ double frcp(double x) {
 #else
   return 1.0 / x;
 #endif
+}
+
+// lgamma(x) for x >= 128 from its logarithm lx = log(x): Stirling series, truncation 1/(1680 x^7) < 2e-18
+__host__ __device__ __forceinline__ double lgamma_big(double x, double lx) {
+  double ix = frcp(x), ix2 = ix * ix;
+  double ser = fma(ix2, fma(ix2, 1.0 / 1260.0, -1.0 / 360.0), 1.0 / 12.0) * ix;
+  return fma(x - 0.5, lx, -x) + (0.91893853320467274178 + ser);
 }

@@ -77,6 +77,7 @@ template <int K>
 struct GeneRegs {
   static constexpr int CELLS = TileCfg<K>::CELLS;
   double gmean, psi, r, step, lgr;
+  bool rok;                   // psi in [1e-100, 1e100]
   double a[K];
   const double* mb;
   double mbj;
@@ -86,6 +87,7 @@ struct GeneRegs {
     gmean = st.gmean[row];
     psi = st.psi[row];
     r = 1.0 / psi;
+    rok = (psi > 1e-100) & (psi < 1e100);
     step = st.step ? st.step[row] : 1.0;
 #pragma unroll
     for (int l = 0; l < K; ++l) a[l] = st.alpha[(long long)row * K + l];
@@ -98,12 +100,26 @@ struct GeneRegs {
     for (int l = 0; l < K; ++l) s = fma(a[l], w[l * CELLS + ci], s);
     return s;
   }
+  // two adjacent cells (ti even) with one 16-byte shared-memory load per factor
+  __device__ __forceinline__ void lmu_pair(const double* w, int ti, double& l0, double& l1) const {
+    double s0 = gmean + mbj, s1 = s0;
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      double2 v = *reinterpret_cast<const double2*>(w + l * CELLS + ti);
+      s0 = fma(a[l], v.x, s0);
+      s1 = fma(a[l], v.y, s1);
+    }
+    l0 = s0; l1 = s1;
+  }
+  // both linear predictors inside the range where fexp_nc / flog_nc / frcp need no checks
+  __device__ __forceinline__ bool fast_range(double l0, double l1) const { return rok & (fabs(l0) < 230.0) & (fabs(l1) < 230.0); }
   __device__ __forceinline__ double expm(double x) const { return fexp(x, mt->ex); }
   __device__ __forceinline__ double logL(double mu) const { return flog(mu + r, mt->rc, mt->lc); }
 };
 
-// Op interface: row_begin(row, slot), group_begin(j), elem(y, chunk, idx_in_tile, tile), pad(chunk, ci),
-//               group_end(j), row_end(row); Op::PADS says whether pad() must be called for padding cells.
+// Op interface: row_begin(row, slot), group_begin(j), pair<FULLCHUNK>(y0, y1, chunk, ti, tile, m0, m1) -- two
+// adjacent cells at tile index ti (even), masks m0/m1 false for padding cells (always true when FULLCHUNK) --
+// group_end(j), row_end(row).  Op::PADS: pair() must also see chunks that hold no real cell.
 template <int K, int NSETS, class Op>
 __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, Op& op, double* smem) {
   constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS;
@@ -128,9 +144,12 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   op.g.lgr = (active && geo.lgr) ? geo.lgr[row] : 0.0;
   __syncthreads();
   if (active) op.row_begin(row, slot);
-  const int32_t* yrow = geo.Yp + (long long)row * geo.Np;
+  const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
   const int ntiles = geo.nchunks / SC;
   int curj = -1;
+  // the counts of the next chunk are fetched one chunk ahead (HBM latency hides behind ~4 elements of math)
+  int2 ya = make_int2(0, 0), yb = ya;
+  if (active) { ya = yrow2[lane]; yb = yrow2[32 + lane]; }
   stage_tile<K, NSETS>(smem, sh->wsets, geo.Np, 0, tid);
   for (int t = 0; t < ntiles; ++t) {
     if (t + 1 < ntiles) {
@@ -142,9 +161,11 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
     __syncthreads();
     if (active) {
       const double* tile = smem + (t & 1) * TILE;
-#pragma unroll
+#pragma unroll 1
       for (int sc = 0; sc < SC; ++sc) {
         const int c = t * SC + sc;
+        const int2 y01 = ya, y23 = yb;
+        if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; }
         const int nv = geo.chunk_valid[c];
         if (nv == 0 && !Op::PADS) continue;
         const int j = geo.chunk_grp[c];
@@ -153,14 +174,14 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
           curj = j;
           op.group_begin(j);
         }
-        const int2* yr = reinterpret_cast<const int2*>(yrow + (long long)c * CH);
-        int2 ya = yr[lane], yb = yr[32 + lane];
-        int ys[4] = {ya.x, ya.y, yb.x, yb.y};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int ci = lane_cell(lane, e);
-          if (ci < nv) op.elem(ys[e], c, sc * CH + ci, tile);
-          else if constexpr (Op::PADS) op.pad(c, ci);
+        const int ti = sc * CH + 2 * lane;
+        if (nv == CH) {
+          op.template pair<true>(y01.x, y01.y, c, ti, tile, true, true);
+          op.template pair<true>(y23.x, y23.y, c, ti + 64, tile, true, true);
+        } else {
+          const int ci = 2 * lane;
+          op.template pair<false>(y01.x, y01.y, c, ti, tile, ci < nv, ci + 1 < nv);
+          op.template pair<false>(y23.x, y23.y, c, ti + 64, tile, ci + 64 < nv, ci + 65 < nv);
         }
       }
     }
@@ -210,16 +231,24 @@ struct OpSigndev {
   double* rowmax; int* rownan;
   __device__ __forceinline__ void row_begin(int row, int slot) { g.load(st, row); Drow = D + (long long)slot * Np; mx = 0.0; nan_ = 0; slot_ = slot; }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
-    double lmu = g.lmu(tile, ti);
+  __device__ __forceinline__ double one(int y, double lmu) {
     double mu = g.expm(lmu);
     double yd = (double)y;
-    double d = nb_signdev_from_half(nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt->ly), yd, mu);
-    Drow[(long long)c * CH + (ti & (CH - 1))] = d;
+    double d = nb_signdev_from_half(nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt), yd, mu);
     if (d != d) nan_ = 1;
     mx = fmax(mx, fabs(d));
+    return d;
   }
-  __device__ __forceinline__ void pad(int c, int ci) { Drow[(long long)c * CH + ci] = __longlong_as_double(0x7ff0000000000000ll); }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double l0, l1;
+    g.lmu_pair(tile, ti, l0, l1);
+    double2 d;
+    d.x = m0 ? one(y0, l0) : inf;
+    d.y = m1 ? one(y1, l1) : inf;
+    *reinterpret_cast<double2*>(Drow + (long long)c * CH + (ti & (CH - 1))) = d;
+  }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int) {
     double v = warp_max(mx);
@@ -269,7 +298,9 @@ __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long 
       double t_now = mx / (kh * C) * (1.0 + 1e-9);
       if (sg > 0.0 && kh * sg >= mx * (1.0 + 1e-9)) out = __longlong_as_double(0x7ff0000000000000ll);
       double slack = madraw - t_now;
-      if (slack > 0.0 && mx < 1.79769313486231570e308) { tg = t_now + 0.5 * slack; lo = med - 0.25 * slack; hi = med + 0.25 * slack; }
+      // window: the median may move by 0.4 slack and max|d| may grow by (1 + 0.15 slack / t) before the row needs
+      // another exact evaluation; (hi - lo)/2 + tg stays below madraw so that c3 <= (n-1)/2 is attainable
+      if (slack > 0.0 && mx < 1.79769313486231570e308) { tg = t_now + 0.15 * slack; lo = med - 0.4 * slack; hi = med + 0.4 * slack; }
     }
     sigma[row] = out;
     hint[(long long)row * 3 + 0] = lo; hint[(long long)row * 3 + 1] = hi; hint[(long long)row * 3 + 2] = tg;
@@ -327,7 +358,7 @@ struct OpLoglik {
   double acc, rlogr;
   double* out;
   // certificate
-  const double* hint; double* sigma_out; double kh; int fastpath; long long n;
+  double* hint; double* sigma_out; double kh; int fastpath; long long n;
   double u_lo, u_hi, u_wl, u_wh, hmax; int c1, c2, c3, bad; bool cert;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); acc = 0.0; rlogr = g.r * log(g.r);
@@ -339,19 +370,46 @@ struct OpLoglik {
     }
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
-    double lmu = g.lmu(tile, ti);
+  // generic element: any count, any argument range
+  __device__ __forceinline__ void one(int y, double lmu, bool m) {
     double mu = g.expm(lmu);
     double L = g.logL(mu);
     double yd = (double)y;
-    acc += nb_logpmf_t(y, yd, lmu, L, g.r, g.lgr, rlogr, g.tl);
+    double v = nb_logpmf_t(y, yd, lmu, L, g.r, g.lgr, rlogr, g.tl, g.mt);
+    acc += m ? v : 0.0;
     if (cert) {  // warp-uniform
-      double h = nb_devhalf_t(y, yd, lmu, L, g.r, g.tr, g.mt->ly);
-      double hc = fmax(h, 0.0);
-      double u = (yd > mu) ? hc : -hc;
-      c1 += (u < u_lo); c2 += (u > u_hi); c3 += (u > u_wl) & (u < u_wh);
-      hmax = fmax(hmax, hc);
-      bad |= !(h == h);
+      double h = nb_devhalf_t(y, yd, lmu, L, g.r, g.tr, g.mt);
+      count(h, yd, mu, m);
+    }
+  }
+  __device__ __forceinline__ void count(double h, double yd, double mu, bool m) {
+    double hc = fmax(h, 0.0);
+    double u = (yd > mu) ? hc : -hc;
+    c1 += m & (u < u_lo); c2 += m & (u > u_hi); c3 += m & (u > u_wl) & (u < u_wh);
+    hmax = fmax(hmax, m ? hc : 0.0);
+    bad |= m & !(h == h);
+  }
+  // in-table counts and in-range arguments: branch-free (tl[0] = 0 and yd = 0 make the y = 0 case fall out)
+  __device__ __forceinline__ void one_fast(int y, double lmu) {
+    double mu = fexp_nc(lmu, g.mt->ex);
+    double L = flog_nc(mu + g.r, g.mt->rc, g.mt->lc);
+    double yd = (double)y;
+    acc += fma(-g.r, L, rlogr) + fma(yd, lmu - L, g.tl[y]);
+    if (cert) {  // warp-uniform
+      double h = fma(yd, g.mt->ly[y] - lmu, -(yd + g.r) * (g.tr[y] - L));
+      count(h, yd, mu, true);
+    }
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    double l0, l1;
+    g.lmu_pair(tile, ti, l0, l1);
+    if (FULLCHUNK && g.fast_range(l0, l1) && (unsigned)(y0 | y1) < (unsigned)YT) {
+      one_fast(y0, l0);
+      one_fast(y1, l1);
+    } else {
+      if (m0) one(y0, l0, true);
+      if (m1) one(y1, l1, true);
     }
   }
   __device__ __forceinline__ void group_end(int) {}
@@ -373,13 +431,26 @@ struct OpLoglik {
         double room = fmin(d_of_u(u_lo) - d_of_u(u_wl), d_of_u(u_wh) - d_of_u(u_hi));
         long long kl = (n - 1) / 2, ku = n / 2;
         ok = (mx > 0.0) && (t <= room) && ((long long)a1 <= kl) && ((long long)a2 <= n - 1 - ku) && ((long long)a3 <= kl);
+        if (ok) {
+          // recentre the hint on the median estimated from the counts (density inside [lo, hi] taken as uniform).
+          // Hints never affect results -- the certificate re-verifies them -- they only decide how often the exact
+          // path is needed while the parameters are still moving.
+          double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1];
+          double pin = 1.0 - (double)(a1 + a2) / (double)n;
+          if (pin > 0.05) {
+            double w = hi - lo;
+            double ctr = lo + (0.5 - (double)a1 / (double)n) * w / pin;
+            hint[(long long)row * 3 + 0] = ctr - 0.5 * w;
+            hint[(long long)row * 3 + 1] = ctr + 0.5 * w;
+          }
+        }
       }
     }
     if (lane == 0) sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
   }
 };
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneState<K> st, double* out, const double* hint,
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneState<K> st, double* out, double* hint,
                                                            double* sigma_out, double kh, int fastpath, long long n) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
@@ -422,25 +493,39 @@ struct OpPass1 {
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0.0;
   }
-  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     const double* w = tile; const double* rw = tile + K * CELLS;
-    double lmu = g.lmu(w, ti);
-    double mu = g.expm(lmu);
-    double yd = (double)y;
-    double s, q;
-    nb_siginv_ratio(yd, mu, g.psi, &s, &q);
-    double Z = fma(g.step, q - 1.0, lmu);
-    double wt = s;
-    if (HUBER && hub) wt *= huber_w_half(khsig, nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt->ly));  // warp-uniform branch
-    sw += wt; gz += Z;
+    double l0, l1;
+    g.lmu_pair(w, ti, l0, l1);
+    const double yd0 = (double)y0, yd1 = (double)y1;
+    double mu0, s0, q0, mu1, s1, q1;
+    if (g.fast_range(l0, l1)) {
+      nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &s0, &q0);
+      nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &s1, &q1);
+    } else {
+      SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
+      mu0 = a.mu; s0 = a.s; q0 = a.q; mu1 = b.mu; s1 = b.s; q1 = b.q;
+    }
+    double Z0 = fma(g.step, q0 - 1.0, l0), Z1 = fma(g.step, q1 - 1.0, l1);
+    double wt0 = s0, wt1 = s1;
+    if (HUBER && hub) {  // warp-uniform branch
+      wt0 *= huber_w_half(khsig, nb_devhalf_t(y0, yd0, l0, g.logL(mu0), g.r, g.tr, g.mt));
+      wt1 *= huber_w_half(khsig, nb_devhalf_t(y1, yd1, l1, g.logL(mu1), g.r, g.tr, g.mt));
+    }
+    if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
+    sw += wt0 + wt1; gz += Z0 + Z1;
+    double2 r[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
     int idx = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-      double wi = wt * rw[i * CELLS + ti];
-      V[i] += wi;
-      u[i] = fma(wi, Z, u[i]);
+      double wi0 = wt0 * r[i].x, wi1 = wt1 * r[i].y;
+      V[i] += wi0 + wi1;
+      u[i] = fma(wi1, Z1, fma(wi0, Z0, u[i]));
 #pragma unroll
-      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi, rw[jx * CELLS + ti], A[idx]); ++idx; }
+      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi1, r[jx].y, fma(wi0, r[jx].x, A[idx])); ++idx; }
     }
   }
   __device__ __forceinline__ void group_end(int j) {
@@ -461,8 +546,8 @@ struct OpPass1 {
     if (lane == 0) sw_out[row] = v;
   }
 };
-template <int K, bool HUBER>
-__global__ void __launch_bounds__(ROW_THREADS, 2) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
+template <int K, bool HUBER, int MINB>
+__global__ void __launch_bounds__(ROW_THREADS, MINB) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
                                                           const double* sigma, double kh, double* A_out, double* u_out,
                                                           double* sw_out, double* ZS, double* VS) {
   extern __shared__ double smem[];
@@ -877,7 +962,7 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
       for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
       double mu = fexp(lmu, mt.ex);
       double r = 1.0 / cp.psi[gi];
-      double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, mt.ly);
+      double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, &mt);
       hmax = fmax(hmax, fmax(h, 0.0));
       bad |= !(h == h);
     }
@@ -907,7 +992,7 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
       double psi = cp.psi[gi];
       if (certp) {
         double r = 1.0 / psi;
-        double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, mt.ly);
+        double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, &mt);
         double d = nb_signdev_from_half(h, yd, mu);
         int b = (int)floor((d + mx) * scale);
         b = b < 0 ? 0 : (b > 127 ? 127 : b);
@@ -976,21 +1061,35 @@ struct OpPass2 {
     if (HUBER) { khsig = kh * sigma[row]; hub = !(khsig > 1.79769313486231570e308); }
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; s0 = 0.0; s1 = 0.0; }
-  __device__ __forceinline__ void elem(int y, int c, int ti, const double* tile) {
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     const double* w = tile; const double* wn = tile + K * CELLS;
-    double lmu = g.lmu(w, ti);
-    double mu = g.expm(lmu);
-    double yd = (double)y;
-    double s, q;
-    nb_siginv_ratio(yd, mu, g.psi, &s, &q);
-    double Z = fma(g.step, q - 1.0, lmu);
-    double wt = s;
-    if (HUBER && hub) wt *= huber_w_half(khsig, nb_devhalf_t(y, yd, lmu, g.logL(mu), g.r, g.tr, g.mt->ly));
-    double res = Z;
+    double l0, l1;
+    g.lmu_pair(w, ti, l0, l1);
+    const double yd0 = (double)y0, yd1 = (double)y1;
+    double mu0, sa, q0, mu1, sb, q1;
+    if (g.fast_range(l0, l1)) {
+      nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &sa, &q0);
+      nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &sb, &q1);
+    } else {
+      SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
+      mu0 = a.mu; sa = a.s; q0 = a.q; mu1 = b.mu; sb = b.s; q1 = b.q;
+    }
+    double res0 = fma(g.step, q0 - 1.0, l0), res1 = fma(g.step, q1 - 1.0, l1);  // Z
+    double wt0 = sa, wt1 = sb;
+    if (HUBER && hub) {  // warp-uniform branch
+      wt0 *= huber_w_half(khsig, nb_devhalf_t(y0, yd0, l0, g.logL(mu0), g.r, g.tr, g.mt));
+      wt1 *= huber_w_half(khsig, nb_devhalf_t(y1, yd1, l1, g.logL(mu1), g.r, g.tr, g.mt));
+    }
 #pragma unroll
-    for (int l = 0; l < K; ++l) res = fma(-an[l], wn[l * CELLS + ti], res);
-    s0 += wt;
-    s1 = fma(wt, res, s1);
+    for (int l = 0; l < K; ++l) {
+      double2 v = *reinterpret_cast<const double2*>(wn + l * CELLS + ti);
+      res0 = fma(-an[l], v.x, res0);
+      res1 = fma(-an[l], v.y, res1);
+    }
+    if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; res0 = m0 ? res0 : 0.0; wt1 = m1 ? wt1 : 0.0; res1 = m1 ? res1 : 0.0; }
+    s0 += wt0 + wt1;
+    s1 = fma(wt1, res1, fma(wt0, res0, s1));
   }
   __device__ __forceinline__ void group_end(int j) {
     double a = warp_sum(s0), b = warp_sum(s1);
@@ -1083,6 +1182,11 @@ struct OpInit {
     for (int i = 0; i < P; ++i) Xty[i] = 0.0;
   }
   __device__ __forceinline__ void group_begin(int) {}
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    if (m0) elem(y0, c, ti, tile);
+    if (m1) elem(y1, c, ti + 1, tile);
+  }
   __device__ __forceinline__ void elem(int y, int c, int ci, const double* tile) {
     double om = (double)y + 1.0;
     double ly = (y + 1 < YT) ? g.mt->ly[y + 1] : log(om);
@@ -1202,4 +1306,24 @@ __global__ void k_csr_scatter(const long long* indptr, const int32_t* indices, c
   int lane = threadIdx.x & 31;
   if (w >= rows) return;
   for (long long e = indptr[w] - base + lane; e < indptr[w + 1] - base; e += 32) dst[w * Np + cell2pos[indices[e]]] = values[e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 FMA peak of this device (the governing roofline of the sweeps): 8 independent
+// DFMA chains per thread, 1024 x 8 x 2 flops per thread per call.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, double a, double b, int iters) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = a + (double)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 16; ++rep)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], b, a);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;  // keeps the chains alive
 }

@@ -1,5 +1,6 @@
 // ruvnb.cu -- C ABI of libruvnb_b200 (include/ruvnb.h): context, data upload, the NB IRLS operators
 // and the whole-fit driver.  sm_100a only; no CPU fallback anywhere in this file.
+#include <stdlib.h>
 #include "ctx.cuh"
 #include "winsor.cuh"
 
@@ -54,6 +55,32 @@ int ruvnb_kernel_time(const ruvnb_ctx* ctx, int which, double* ms_total, long lo
   return RUVNB_OK;
 }
 int ruvnb_last_exact_rows(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_rows : -1; }
+// measured FP64 FMA throughput of the device (TFLOP/s, 2 flops per DFMA), best of 5
+int ruvnb_measure_fp64(ruvnb_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return RUVNB_EARG;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, 8));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 2048, grid = prop.multiProcessorCount * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(e0, ctx->stream));
+    k_fp64_peak<<<grid, 256, 0, ctx->stream>>>(d, 1e-9, 0.999999, iters);
+    CKL();
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double fl = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1)); CK(cudaFree(d));
+  *tflops = best;
+  return RUVNB_OK;
+}
 int ruvnb_last_exact_cells(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_cells : -1; }
 int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n) {
   if (!x || !out || n < 0 || which < 0 || which > 1) return RUVNB_EARG;
@@ -618,8 +645,14 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(1);
-    if (hub) LAUNCH_ROWS((k_pass1<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
-    else LAUNCH_ROWS((k_pass1<KT, false>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    static const int p1_minb = getenv("RUVNB_P1_MINB") ? atoi(getenv("RUVNB_P1_MINB")) : 2;  // tuning knob
+    if (p1_minb == 1) {
+      if (hub) LAUNCH_ROWS((k_pass1<KT, true, 1>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      else LAUNCH_ROWS((k_pass1<KT, false, 1>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    } else {
+      if (hub) LAUNCH_ROWS((k_pass1<KT, true, 2>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      else LAUNCH_ROWS((k_pass1<KT, false, 2>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    }
     KEV_END(1);
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
     CKL();
