@@ -181,6 +181,11 @@ int ruvnb_accept(ruvnb_ctx* ctx);
  *     ruvnb_estimate_disp: grid + common + trend + prior + WLEB -> sets "psi" (tagwise). */
 int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double* rowsum);
 int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out);
+/* Same with the outputs of estimateDisp.par exposed: prior_df_in >= 0 injects prior.df (the reference derives it with
+ * limma::squeezeVar(robust = TRUE, covariate), third-party arithmetic that is only approximated here by limma's plain
+ * fitFDist moments); < 0 estimates it.  trended_out: local rows; prior_df_out: the prior d.f. used. */
+int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_in, double* common_out, double* trended_out,
+                           double* prior_df_out);
 /* The north_star variant: per-gene Newton maximisation of the same Cox-Reid adjusted profile
  * likelihood in log(psi) (digamma/trigamma on the FP64 pipe).  NOT what the reference computes
  * (it interpolates the 21-point grid); reported separately. */

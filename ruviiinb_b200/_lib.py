@@ -21,7 +21,7 @@ SYMBOLS = [
     "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
     "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_get_counts", "ruvnb_set_state",
     "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_snapshot_best",
-    "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp",
+    "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp", "ruvnb_estimate_disp_ex",
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res",
 ]
 
@@ -96,6 +96,7 @@ def load():
     lib.ruvnb_accept.argtypes = [vp]
     lib.ruvnb_disp_apl_grid.argtypes = [vp, C.POINTER(Opts), vp, vp]
     lib.ruvnb_estimate_disp.argtypes = [vp, C.POINTER(Opts), dp]
+    lib.ruvnb_estimate_disp_ex.argtypes = [vp, C.POINTER(Opts), C.c_double, dp, vp, dp]
     lib.ruvnb_disp_newton.argtypes = [vp, C.POINTER(Opts), vp, C.c_int]
     lib.ruvnb_fit_nb.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(FitStats)]
     lib.ruvnb_get_res.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
@@ -249,6 +250,14 @@ class Context:
         c = C.c_double()
         self._ck(self.lib.ruvnb_estimate_disp(self.h, C.byref(opts), C.byref(c)))
         return c.value
+
+    def estimate_disp_ex(self, opts, prior_df=None):
+        """estimateDisp.par on the current parameters -> dict(common, trended, prior_df); sets "psi" (tagwise)."""
+        c, pdf = C.c_double(), C.c_double()
+        tr = np.empty(self.Gl, dtype=np.float64)
+        self._ck(self.lib.ruvnb_estimate_disp_ex(self.h, C.byref(opts), -1.0 if prior_df is None else float(prior_df), C.byref(c), _ptr(tr),
+                                                 C.byref(pdf)))
+        return dict(common=c.value, trended=tr, prior_df=pdf.value)
 
     def disp_newton(self, opts, maxit=30):
         out = np.empty(self.Gl, dtype=np.float64)

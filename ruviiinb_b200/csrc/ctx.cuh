@@ -13,6 +13,7 @@
 
 #include "../../include/ruvnb.h"
 #include "kernels.cuh"
+#include "disp.cuh"
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------
@@ -99,6 +100,13 @@ struct ruvnb_ctx {
   double* ctl_tabR = nullptr;                                 // [n_ctl][YT]
   const double* ytab_psi = nullptr; long long ytab_ver = -1, psi_ver = 0;  // which psi the tables were built from
   int *w_fail = nullptr;         // [1 + Np] fast-W failures: count, then positions
+  // dispersion scratch (disp.cuh), allocated on first use
+  double *dp_beta = nullptr, *dp_beta0 = nullptr, *dp_rowsum = nullptr, *dp_emean = nullptr, *dp_l0 = nullptr, *dp_phi_grid = nullptr,
+         *dp_tabG = nullptr, *dp_tabRg = nullptr, *dp_lgr_grid = nullptr, *dp_zeros = nullptr, *dp_beta1 = nullptr, *dp_phi_row = nullptr,
+         *dp_dev = nullptr, *dp_tabR2 = nullptr;
+  int* dp_flag = nullptr;
+  bool dp_ready = false;
+  int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare
   int *faillist = nullptr;
   int *h_flags = nullptr;    // pinned mirror

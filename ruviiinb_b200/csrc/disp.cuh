@@ -1,0 +1,420 @@
+// disp.cuh -- H3: estimateDisp.par (reference R/estimateDisp.par.R:3-202) with design = 1 column of ones,
+// offset = alpha W' + Mb[, grp] (no gmean) -- the call sites R/ruvIIInb.R:205-221,535-565.
+//
+// Device: the work that is O(G N) per dispersion value --
+//   k_disp_init   start value of edgeR's one-group Newton-Raphson (log(sum y e^-o / n)), rowSums(y), mean e^o
+//   k_disp_nr     one Newton-Raphson step of the intercept for ND dispersion values per sweep (edgeR C++
+//                 glm_one_group: step = sum (y-mu)/(1+phi mu) / sum mu/(1+phi mu), tol 1e-10, maxit 50)
+//   k_disp_apl    Cox-Reid adjusted profile likelihood for ND dispersion values per sweep (edgeR compute_apl):
+//                 sum l_NB(y; mu, phi) - 1/2 log sum mu/(1+phi mu); lgamma(y + 1/phi_d) comes from a 21 x 128 table
+//   k_disp_dev    NB deviance at a per-gene dispersion (for the prior d.f.)
+//   k_tricube     local-constant tricube smoother of the 21 columns of l0 against AveLogCPM (locfit stand-in)
+// Host: spline maximisation (FMM spline + edgeR interpolator::find_max), limma fitFDist moments, the control flow.
+// The restatement these follow is oracle/edger.py (parity unpinned: edgeR/limma/locfit are not under /root/reference).
+#pragma once
+#include "kernels.cuh"
+
+#define DISP_NG 21
+#define DISP_ND 7   // dispersion values per sweep (3 sweeps cover the grid)
+
+template <int K, int ND>
+struct DispRowShared {
+  RowShared base;
+  double tg[ND][YT];  // lgamma(y + r_d) - lgamma(r_d) - lgamma(y + 1)
+};
+
+struct DispArgs {
+  const double* phi_grid;   // [ND] dispersions of this sweep, or nullptr
+  const double* phi_row;    // [Gl] per-gene dispersion (ND == 1), or nullptr
+  double* beta;             // [Gl][ldb] intercepts; this sweep uses columns d0 .. d0+ND-1
+  int ldb, d0;
+  const double* emean;      // [Gl] mean_c exp(offset) (ave_log_cpm prior) or nullptr
+  double prior_count;       // aveLogCPM: y + p_c, offset log(e^o + 2 p_c), p_c = prior_count e^o / mean e^o
+  double tol;
+  int* notconv;             // set to 1 when some |step| >= tol
+  double n;                 // number of cells
+};
+
+// ---- start values ---------------------------------------------------------------------------------------------
+template <int K>
+struct OpDispInit {
+  static constexpr bool PADS = false;
+  GeneState<K> st; GeneRegs<K> g;
+  double s_ye, s_y, s_e; int nz;
+  double *beta0, *rowsum, *emean; double n;
+  __device__ __forceinline__ void row_begin(int row, int) { g.load(st, row); s_ye = s_y = s_e = 0.0; nz = 0; }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void one(int y, double off, bool m) {
+    if (!m) return;
+    double E = g.expm(off);
+    double yd = (double)y;
+    s_e += E; s_y += yd;
+    if (y > 0) { s_ye += yd / E; nz = 1; }
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    double o0, o1;
+    g.lmu_pair(tile, ti, o0, o1);
+    one(y0, o0, m0); one(y1, o1, m1);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    double a = warp_sum(s_ye), b = warp_sum(s_y), e = warp_sum(s_e);
+    int any = __any_sync(FULL, nz);
+    if ((threadIdx.x & 31) == 0) {
+      beta0[row] = any ? log(a / n) : -__longlong_as_double(0x7ff0000000000000ll);
+      rowsum[row] = b; emean[row] = e / n;
+    }
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_init(RowGeom geo, GeneState<K> st, double* beta0, double* rowsum,
+                                                              double* emean, double n) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  OpDispInit<K> op;
+  op.st = st; op.beta0 = beta0; op.rowsum = rowsum; op.emean = emean; op.n = n;
+  stream_rows<K, 1>(geo, &sh, op, smem);
+}
+
+// ---- one Newton-Raphson step for ND dispersions ------------------------------------------------------------------
+template <int K, int ND>
+struct OpDispNR {
+  static constexpr bool PADS = false;
+  GeneState<K> st; GeneRegs<K> g; DispArgs a;
+  double eb[ND], phi[ND], dl[ND], info[ND];
+  double yadd, escale; bool live;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row);
+    live = false;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double b = a.beta[(long long)row * a.ldb + a.d0 + d];
+      eb[d] = exp(b);
+      live |= (b > -1.79769313486231570e308) & (b < 1.79769313486231570e308);
+      phi[d] = a.phi_row ? a.phi_row[row] : a.phi_grid[d];
+      dl[d] = 0.0; info[d] = 0.0;
+    }
+    yadd = 0.0; escale = 1.0;
+    if (a.emean) { double pcm = a.prior_count / a.emean[row]; yadd = pcm; escale = fma(2.0, pcm, 1.0); }
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void one(int y, double off, bool m) {
+    if (!m) return;
+    double E = g.expm(off);
+    double yd = fma(yadd, E, (double)y);
+    E *= escale;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double mu = eb[d] * E;
+      double w = 1.0 / fma(mu, phi[d], 1.0);
+      dl[d] = fma(yd - mu, w, dl[d]);
+      info[d] = fma(mu, w, info[d]);
+    }
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    if (!live) return;  // all-zero gene: beta = -Inf stays (edgeR returns R_NegInf)
+    double o0, o1;
+    g.lmu_pair(tile, ti, o0, o1);
+    one(y0, o0, m0); one(y1, o1, m1);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    if (!live) return;
+    bool nc = false;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double s1 = warp_sum(dl[d]), s2 = warp_sum(info[d]);
+      if ((threadIdx.x & 31) == 0) {
+        double step = s1 / s2;
+        double* bp = a.beta + (long long)row * a.ldb + a.d0 + d;
+        if (step == step) { *bp += step; nc |= !(fabs(step) < a.tol); }
+      }
+    }
+    if (nc) atomicExch(a.notconv, 1);
+  }
+};
+template <int K, int ND>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr(RowGeom geo, GeneState<K> st, DispArgs a) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  OpDispNR<K, ND> op;
+  op.st = st; op.a = a;
+  stream_rows<K, 1>(geo, &sh, op, smem);
+}
+
+// ---- adjusted profile likelihood for ND dispersions ---------------------------------------------------------------
+template <int K, int ND>
+struct OpDispAPL {
+  static constexpr bool PADS = false;
+  GeneState<K> st; GeneRegs<K> g; DispArgs a;
+  const double (*tg)[YT];   // shared: [ND][YT]
+  const double* lgr_grid;   // [ND] lgamma(r_d)
+  double eb[ND], r[ND], ll[ND], ww[ND];
+  double syo, sy;           // sum y * offset, sum y: y log mu = y (beta_d + offset) is assembled at the end of the row
+  double* l0; int ld0;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      eb[d] = exp(fmax(a.beta[(long long)row * a.ldb + a.d0 + d], -1e8));  // mglmOneWay: pmax(beta, -1e8)
+      r[d] = 1.0 / a.phi_grid[d];
+      ll[d] = 0.0; ww[d] = 0.0;
+    }
+    syo = 0.0; sy = 0.0;
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void one(int y, double off, bool m) {
+    if (!m) return;
+    double E = g.expm(off);
+    double yd = (double)y;
+    syo = fma(yd, off, syo); sy += yd;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double mu = eb[d] * E;
+      double mr = mu + r[d];
+      double t = -(yd + r[d]) * flog(mr, g.mt->rc, g.mt->lc);
+      if (y > 0) t += (y < YT) ? tg[d][y] : nb_big_lgterm(yd, r[d], lgr_grid[d], g.mt);
+      ll[d] += t;
+      ww[d] = fma(mu * r[d], 1.0 / mr, ww[d]);   // mu / (1 + phi mu)
+    }
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    double o0, o1;
+    g.lmu_pair(tile, ti, o0, o1);
+    one(y0, o0, m0); one(y1, o1, m1);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    double tyo = warp_sum(syo), ty = warp_sum(sy);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      double s1 = warp_sum(ll[d]), s2 = warp_sum(ww[d]);
+      if ((threadIdx.x & 31) == 0) {
+        const double low = 1e-10;  // edgeR adj_coxreid low_value
+        double adj = 0.5 * log(s2 < low ? low : s2);
+        double beta = fmax(a.beta[(long long)row * a.ldb + a.d0 + d], -1e8);
+        double ylogmu = ty > 0.0 ? fma(beta, ty, tyo) : 0.0;
+        l0[(long long)row * ld0 + a.d0 + d] = s1 + ylogmu + a.n * r[d] * log(r[d]) - adj;
+      }
+    }
+  }
+};
+template <int K, int ND>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl(RowGeom geo, GeneState<K> st, DispArgs a, const double* tabG /* [ND][YT] */,
+                                                             const double* lgr_grid, double* l0, int ld0) {
+  extern __shared__ double smem[];
+  __shared__ DispRowShared<K, ND> sh;
+  if (threadIdx.x == 0) sh.base.wsets[0] = st.W;
+  for (int i = threadIdx.x; i < ND * YT; i += ROW_THREADS) (&sh.tg[0][0])[i] = tabG[i];
+  OpDispAPL<K, ND> op;
+  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.l0 = l0; op.ld0 = ld0;
+  stream_rows<K, 1>(geo, &sh.base, op, smem);
+}
+
+// ---- NB deviance at a per-gene dispersion and intercept (prior d.f.) ------------------------------------------------
+template <int K>
+struct OpDispDev {
+  static constexpr bool PADS = false;
+  GeneState<K> st; GeneRegs<K> g;
+  const double *beta, *phi_row; double* dev;
+  double b, eb, r, acc;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); b = fmax(beta[row], -1e8); eb = exp(b); r = 1.0 / phi_row[row]; acc = 0.0;
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void one(int y, double off, bool m) {
+    if (!m) return;
+    double mu = eb * g.expm(off);
+    double yd = (double)y;
+    // unit deviance / 2 = y log(y/mu) - (y + r) log((y + r)/(mu + r)); the tables of the row were built for phi_row
+    acc += nb_devhalf_t(y, yd, b + off, flog(mu + r, g.mt->rc, g.mt->lc), r, g.tr, g.mt);
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    double o0, o1;
+    g.lmu_pair(tile, ti, o0, o1);
+    one(y0, o0, m0); one(y1, o1, m1);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    double s = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) dev[row] = 2.0 * s;
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_dev(RowGeom geo, GeneState<K> st, const double* beta, const double* phi_row,
+                                                             double* dev) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  OpDispDev<K> op;
+  op.st = st; op.beta = beta; op.phi_row = phi_row; op.dev = dev;
+  stream_rows<K, 1>(geo, &sh, op, smem);
+}
+
+// ---- local-constant tricube smoother (locfit deg = 0 stand-in) -------------------------------------------------------
+// xs: covariate sorted ascending (n), perm: row of l0 for each sorted position; one CTA per sorted position i.  The q
+// nearest neighbours of xs[i] are a contiguous window of the sorted order; bandwidth h = distance to the q-th nearest.
+__global__ void __launch_bounds__(128) k_tricube(const double* xs, const int* perm, int n, int q, const double* l0, int ld0,
+                                                 double* m0 /* [n][DISP_NG] in sorted order */) {
+  __shared__ double red[4][DISP_NG + 1];
+  __shared__ int s_lo;
+  __shared__ double s_h;
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    const double xi = xs[i];
+    // window [lo, lo+q) with lo in [max(0, i-q+1), min(i, n-q)] minimising max(xi - xs[lo], xs[lo+q-1] - xi)
+    int a = max(0, i - q + 1), b = min(i, n - q);
+    while (a < b) {  // the left distance decreases and the right distance increases with lo
+      int mid = (a + b) >> 1;
+      if (xi - xs[mid] > xs[mid + q - 1] - xi) a = mid + 1; else b = mid;
+    }
+    int lo = a;
+    if (lo > max(0, i - q + 1)) {  // the optimum is at lo or lo-1
+      double ca = fmax(xi - xs[lo], xs[lo + q - 1] - xi), cb = fmax(xi - xs[lo - 1], xs[lo + q - 2] - xi);
+      if (cb < ca) lo = lo - 1;
+    }
+    s_lo = lo;
+    s_h = fmax(xi - xs[lo], xs[lo + q - 1] - xi);
+  }
+  __syncthreads();
+  const int lo = s_lo; const double h = s_h, xi = xs[i];
+  double acc[DISP_NG + 1];
+#pragma unroll
+  for (int d = 0; d <= DISP_NG; ++d) acc[d] = 0.0;
+  // points outside the window may tie at distance h (weight 0) -- only strictly closer points have weight
+  for (int jj = lo + tid; jj < lo + q; jj += 128) {
+    double dist = fabs(xs[jj] - xi);
+    double w;
+    if (h > 0.0) { double u = fmin(dist / h, 1.0); double v = 1.0 - u * u * u; w = v * v * v; }
+    else w = 1.0;
+    const double* row = l0 + (long long)perm[jj] * ld0;
+#pragma unroll
+    for (int d = 0; d < DISP_NG; ++d) acc[d] = fma(w, row[d], acc[d]);
+    acc[DISP_NG] += w;
+  }
+#pragma unroll
+  for (int d = 0; d <= DISP_NG; ++d) { double v = warp_sum(acc[d]); if (lane == 0) red[warp][d] = v; }
+  __syncthreads();
+  if (tid <= DISP_NG) {
+    double v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    red[0][tid] = v;
+  }
+  __syncthreads();
+  if (tid < DISP_NG) m0[(long long)i * DISP_NG + tid] = red[0][tid] / red[0][DISP_NG];
+}
+
+// ---- host: FMM spline + edgeR interpolator::find_max --------------------------------------------------------------------
+static void fmm_spline_h(int n, const double* x, const double* y, double* b, double* c, double* d) {
+  if (n < 3) { double t = y[1] - y[0]; b[0] = t / (x[1] - x[0]); b[1] = b[0]; c[0] = c[1] = d[0] = d[1] = 0.0; return; }
+  const int nm1 = n - 1;
+  d[0] = x[1] - x[0];
+  c[1] = (y[1] - y[0]) / d[0];
+  for (int i = 1; i < nm1; ++i) {
+    d[i] = x[i + 1] - x[i];
+    b[i] = 2.0 * (d[i - 1] + d[i]);
+    c[i + 1] = (y[i + 1] - y[i]) / d[i];
+    c[i] = c[i + 1] - c[i];
+  }
+  b[0] = -d[0]; b[nm1] = -d[nm1 - 1];
+  c[0] = c[nm1] = 0.0;
+  if (n > 3) {
+    c[0] = c[2] / (x[3] - x[1]) - c[1] / (x[2] - x[0]);
+    c[nm1] = c[nm1 - 1] / (x[nm1] - x[nm1 - 2]) - c[nm1 - 2] / (x[nm1 - 1] - x[nm1 - 3]);
+    c[0] = c[0] * d[0] * d[0] / (x[3] - x[0]);
+    c[nm1] = -c[nm1] * d[nm1 - 1] * d[nm1 - 1] / (x[nm1] - x[nm1 - 3]);
+  }
+  for (int i = 1; i < n; ++i) { double t = d[i - 1] / b[i - 1]; b[i] -= t * d[i - 1]; c[i] -= t * c[i - 1]; }
+  c[nm1] = c[nm1] / b[nm1];
+  for (int i = nm1 - 1; i >= 0; --i) c[i] = (c[i] - d[i] * c[i + 1]) / b[i];
+  b[nm1] = (y[nm1] - y[nm1 - 1]) / d[nm1 - 1] + d[nm1 - 1] * (c[nm1 - 1] + 2.0 * c[nm1]);
+  for (int i = 0; i < nm1; ++i) {
+    b[i] = (y[i + 1] - y[i]) / d[i] - d[i] * (c[i + 1] + 2.0 * c[i]);
+    d[i] = (c[i + 1] - c[i]) / d[i];
+    c[i] = 3.0 * c[i];
+  }
+  c[nm1] = 3.0 * c[nm1];
+  d[nm1] = d[nm1 - 1];
+}
+static bool quad_first_root(double a, double b, double c, double* sol) {
+  double back = b * b - 4.0 * a * c;
+  if (!(back >= 0.0) || a == 0.0) return false;
+  *sol = -b / (2.0 * a) - sqrt(back) / (2.0 * a);
+  return true;
+}
+static double maximize_interpolant_h(int n, const double* x, const double* y) {
+  int at = 0;
+  for (int i = 1; i < n; ++i) if (y[i] > y[at]) at = i;
+  double maxed = y[at], xmax = x[at];
+  double b[DISP_NG], c[DISP_NG], d[DISP_NG];
+  fmm_spline_h(n, x, y, b, c, d);
+  double s;
+  if (at > 0 && quad_first_root(3 * d[at - 1], 2 * c[at - 1], b[at - 1], &s) && s > 0 && s < x[at] - x[at - 1]) {
+    double t = ((d[at - 1] * s + c[at - 1]) * s + b[at - 1]) * s + y[at - 1];
+    if (t > maxed) { maxed = t; xmax = s + x[at - 1]; }
+  }
+  if (at < n - 1 && quad_first_root(3 * d[at], 2 * c[at], b[at], &s) && s > 0 && s < x[at + 1] - x[at]) {
+    double t = ((d[at] * s + c[at]) * s + b[at]) * s + y[at];
+    if (t > maxed) { maxed = t; xmax = s + x[at]; }
+  }
+  return xmax;
+}
+
+// ---- host: digamma / trigamma / limma fitFDist ------------------------------------------------------------------------------
+static double digamma_h(double x) {
+  double r = 0.0;
+  while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+  double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x - f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132)))));
+}
+static double trigamma_h(double x) {
+  double r = 0.0;
+  while (x < 6.0) { r += 1.0 / (x * x); x += 1.0; }
+  double f = 1.0 / (x * x);
+  return r + 1.0 / x + f / 2 + f / x * (1.0 / 6 - f * (1.0 / 30 - f * (1.0 / 42 - f * (1.0 / 30 - f * (5.0 / 66)))));
+}
+static double tetragamma_h(double x) {  // psi''(x)
+  double r = 0.0;
+  while (x < 6.0) { r -= 2.0 / (x * x * x); x += 1.0; }
+  double f = 1.0 / (x * x);
+  return r - f - f / x - f * f * (0.5 - f * (1.0 / 6 - f * (1.0 / 6 - f * (3.0 / 10))));
+}
+static double trigamma_inverse_h(double x) {  // limma::trigammaInverse
+  if (x > 1e7) return 1.0 / sqrt(x);
+  if (x < 1e-6) return 1.0 / x;
+  double y = 0.5 + 1.0 / x;
+  for (int it = 0; it < 50; ++it) {
+    double tri = trigamma_h(y);
+    double dif = tri * (1.0 - tri / x) / tetragamma_h(y);
+    y += dif;
+    if (-dif / y < 1e-8) break;
+  }
+  return y;
+}
+// limma::fitFDist(x, df1) without covariate -> df2 (Inf when the log-variances are no more variable than chi-square noise)
+static double fit_f_dist_df2(const std::vector<double>& s2, double df1) {
+  std::vector<double> x;
+  for (double v : s2) if (std::isfinite(v) && v > -1e-15) x.push_back(std::max(v, 0.0));
+  const size_t n = x.size();
+  if (n == 0) return NAN;
+  if (n == 1) return 0.0;
+  std::vector<double> srt(x);
+  std::sort(srt.begin(), srt.end());
+  double m = (n & 1) ? srt[n / 2] : 0.5 * (srt[n / 2 - 1] + srt[n / 2]);
+  if (m == 0.0) m = 1.0;
+  double emean = 0.0;
+  std::vector<double> e(n);
+  const double cst = -digamma_h(df1 / 2.0) + log(df1 / 2.0);
+  for (size_t i = 0; i < n; ++i) { e[i] = log(std::max(x[i], 1e-5 * m)) + cst; emean += e[i]; }
+  emean /= (double)n;
+  double evar = 0.0;
+  for (size_t i = 0; i < n; ++i) evar += (e[i] - emean) * (e[i] - emean);
+  evar = evar / (double)(n - 1) - trigamma_h(df1 / 2.0);
+  if (evar > 0.0) return 2.0 * trigamma_inverse_h(evar);
+  return INFINITY;
+}

@@ -961,4 +961,241 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
 }
 
 }  // extern "C"
+
+// ---- H3: dispersion (R/estimateDisp.par.R) ------------------------------------------------------------------------------
+__global__ void k_bcast_cols(const double* src, long long n, int ld, int d0, int nd, double* dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * nd) return;
+  long long r = i / nd; int d = (int)(i % nd);
+  dst[r * ld + d0 + d] = src[r];
+}
+static int disp_ensure(ruvnb_ctx* ctx) {
+  if (ctx->dp_ready) return RUVNB_OK;
+  const long long Gl = ctx->Gl;
+  RET(dev_alloc(ctx, &ctx->dp_beta, Gl * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_beta0, Gl)); RET(dev_alloc(ctx, &ctx->dp_rowsum, Gl));
+  RET(dev_alloc(ctx, &ctx->dp_emean, Gl)); RET(dev_alloc(ctx, &ctx->dp_l0, Gl * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_phi_grid, DISP_NG));
+  RET(dev_alloc(ctx, &ctx->dp_tabG, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_tabRg, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_lgr_grid, DISP_NG));
+  RET(dev_alloc(ctx, &ctx->dp_zeros, Gl)); RET(dev_alloc(ctx, &ctx->dp_beta1, Gl)); RET(dev_alloc(ctx, &ctx->dp_phi_row, Gl));
+  RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 1));
+  CK(cudaMemsetAsync(ctx->dp_zeros, 0, (size_t)Gl * 8, ctx->stream));
+  double grid[DISP_NG];
+  for (int i = 0; i < DISP_NG; ++i) grid[i] = 0.1 * exp2(-10.0 + (double)i);  // spline.disp, R/estimateDisp.par.R:33-35
+  CK(cudaMemcpyAsync(ctx->dp_phi_grid, grid, sizeof grid, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  k_build_ytabs<<<DISP_NG, YT, 0, ctx->stream>>>(ctx->dp_phi_grid, DISP_NG, ctx->dp_tabG, ctx->dp_tabRg, ctx->dp_lgr_grid);
+  CKL();
+  ctx->dp_ready = true;
+  return RUVNB_OK;
+}
+// offset = alpha W' + Mb[, grp] (no gmean): the parameter set `s` with a zero gmean
+template <int K>
+static GeneState<K> disp_state(ruvnb_ctx* ctx, const StateSet& s) {
+  GeneState<K> st = gstate<K>(ctx, s, false);
+  st.gmean = ctx->dp_zeros;
+  return st;
+}
+// Newton-Raphson to convergence (edgeR glm_one_group: |step| < 1e-10, at most 50 iterations) for columns d0..d0+nd-1
+static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
+  for (int it = 0; it < 50; ++it) {
+    CK(cudaMemsetAsync(ctx->dp_flag, 0, sizeof(int), ctx->stream));
+    DISPATCH_K(ctx->K, {
+      if (nd == DISP_ND) LAUNCH_ROWS((k_disp_nr<KT, DISP_ND>), 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), disp_state<KT>(ctx, s), a);
+      else LAUNCH_ROWS((k_disp_nr<KT, 1>), 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), disp_state<KT>(ctx, s), a);
+    });
+    ctx->disp_nr_sweeps++;
+    CK(cudaMemcpyAsync(ctx->h_flags + 7, ctx->dp_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[7] == 0) break;
+  }
+  return RUVNB_OK;
+}
+// l0 (device, [Gl][21] row-major), rowsum, emean, beta0 for the parameter set `s`
+static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
+  RET(disp_ensure(ctx));
+  const int Gl = ctx->Gl;
+  ctx->disp_nr_sweeps = 0;
+  DISPATCH_K(ctx->K, {
+    LAUNCH_ROWS(k_disp_init<KT>, 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), ctx->dp_beta0, ctx->dp_rowsum, ctx->dp_emean, (double)ctx->N);
+  });
+  for (int d0 = 0; d0 < DISP_NG; d0 += DISP_ND) {
+    k_bcast_cols<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta0, Gl, DISP_NG, d0, DISP_ND, ctx->dp_beta);
+    CKL();
+    DispArgs a;
+    a.phi_grid = ctx->dp_phi_grid + d0; a.phi_row = nullptr; a.beta = ctx->dp_beta; a.ldb = DISP_NG; a.d0 = d0;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = (double)ctx->N;
+    RET(disp_nr(ctx, s, a, DISP_ND));
+    DISPATCH_K(ctx->K, {
+      LAUNCH_ROWS((k_disp_apl<KT, DISP_ND>), 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)d0 * YT,
+                  ctx->dp_lgr_grid + d0, ctx->dp_l0, DISP_NG);
+    });
+  }
+  return RUVNB_OK;
+}
+
+extern "C" {
+
+int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double* rowsum) {
+  RET(check_ready(ctx, o));
+  RET(disp_grid(ctx, ctx->cur));
+  const int Gl = ctx->Gl;
+  std::vector<double> h((size_t)Gl * DISP_NG), rs(Gl);
+  CK(cudaMemcpyAsync(h.data(), ctx->dp_l0, h.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(rs.data(), ctx->dp_rowsum, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (l0) for (int g = 0; g < Gl; ++g) for (int d = 0; d < DISP_NG; ++d) l0[g + (size_t)Gl * d] = rs[g] >= 5.0 ? h[(size_t)g * DISP_NG + d] : NAN;  // sel, :29
+  if (rowsum) memcpy(rowsum, rs.data(), (size_t)Gl * 8);
+  return RUVNB_OK;
+}
+
+// The whole of estimateDisp.par for design = 1 (R/estimateDisp.par.R:27-201): sets "psi" of the current parameter set to
+// the tagwise dispersion.  prior_df < 0: estimate it (limma fitFDist moments; the reference's robust squeezeVar with a
+// covariate trend is not restated); prior_df >= 0: use it (injection seam).
+int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_in, double* common_out, double* trended_out,
+                           double* prior_df_out) {
+  RET(check_ready(ctx, o));
+  StateSet& s = ctx->cur;
+  RET(disp_grid(ctx, s));
+  const int Gl = ctx->Gl; const long long G = ctx->G, g0 = ctx->g0;
+  const double N = (double)ctx->N;
+  // gather l0 / rowsum of all genes on every rank (zero-padded sum over the ranks)
+  std::vector<double> l0((size_t)G * DISP_NG, 0.0), rowsum(G, 0.0);
+  double* d_l0_full = ctx->dp_l0; double* d_rs_full = ctx->dp_rowsum;
+  double *tmpA = nullptr, *tmpB = nullptr;
+  if (ctx->nranks > 1) {
+    CK(cudaMalloc((void**)&tmpA, (size_t)G * DISP_NG * 8)); CK(cudaMalloc((void**)&tmpB, (size_t)G * 8));
+    CK(cudaMemsetAsync(tmpA, 0, (size_t)G * DISP_NG * 8, ctx->stream)); CK(cudaMemsetAsync(tmpB, 0, (size_t)G * 8, ctx->stream));
+    CK(cudaMemcpyAsync(tmpA + g0 * DISP_NG, ctx->dp_l0, (size_t)Gl * DISP_NG * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(tmpB + g0, ctx->dp_rowsum, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    RET(allreduce(ctx, tmpA, (size_t)G * DISP_NG, NCCL_F64)); RET(allreduce(ctx, tmpB, (size_t)G, NCCL_F64));
+    d_l0_full = tmpA; d_rs_full = tmpB;
+  }
+  CK(cudaMemcpyAsync(l0.data(), d_l0_full, l0.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(rowsum.data(), d_rs_full, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double pts[DISP_NG];
+  for (int i = 0; i < DISP_NG; ++i) pts[i] = -10.0 + (double)i;
+  std::vector<int> sel;  // :29 rowSums(y) >= 5
+  for (long long g = 0; g < G; ++g) if (rowsum[g] >= 5.0) sel.push_back((int)g);
+  const int ns = (int)sel.size();
+  if (ns == 0) return ctx->fail(RUVNB_EARG, "estimate_disp: no gene has rowSums(y) >= 5");
+  // common dispersion (:130-132)
+  double colsum[DISP_NG] = {0};
+  for (int i : sel) for (int d = 0; d < DISP_NG; ++d) colsum[d] += l0[(size_t)i * DISP_NG + d];
+  const double common = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, colsum));
+  if (common_out) *common_out = common;
+  // AveLogCPM (:134): one-group fit of y + prior at the common dispersion
+  {
+    k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->dp_phi_row, Gl, common); CKL();
+    // start: log(sum (y + p)/(e^o + 2p) / n) = log((exp(beta0) + pcm) / (1 + 2 pcm)), pcm = prior.count / mean e^o
+    std::vector<double> b0(Gl), em(Gl);
+    CK(cudaMemcpyAsync(b0.data(), ctx->dp_beta0, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(em.data(), ctx->dp_emean, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int g = 0; g < Gl; ++g) { double pcm = 2.0 / em[g]; b0[g] = log((exp(b0[g]) + pcm) / (1.0 + 2.0 * pcm)); }
+    CK(cudaMemcpyAsync(ctx->dp_beta1, b0.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    DispArgs a;
+    a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0;
+    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N;
+    RET(disp_nr(ctx, s, a, 1));
+  }
+  std::vector<double> alc(G, 0.0);
+  {
+    std::vector<double> b1(Gl);
+    CK(cudaMemcpyAsync(b1.data(), ctx->dp_beta1, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int g = 0; g < Gl; ++g) alc[g0 + g] = (b1[g] + log(1e6)) / log(2.0);
+    if (ctx->nranks > 1) {
+      CK(cudaMemcpyAsync(tmpB, alc.data(), (size_t)G * 8, cudaMemcpyHostToDevice, ctx->stream));
+      RET(allreduce(ctx, tmpB, (size_t)G, NCCL_F64));
+      CK(cudaMemcpyAsync(alc.data(), tmpB, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  // trend: local-constant tricube smoother of l0 against AveLogCPM over the selected genes (:136-139, locfit stand-in)
+  const double span = ns <= 50 ? 1.0 : 0.25 + 0.75 * sqrt(50.0 / (double)ns);  // edgeR::WLEB default
+  const int q = std::min(ns, std::max(1, (int)ceil(span * (double)ns)));
+  std::vector<int> order(ns);
+  for (int i = 0; i < ns; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return alc[sel[a]] < alc[sel[b]]; });
+  std::vector<double> xs(ns); std::vector<int> perm(ns);
+  for (int i = 0; i < ns; ++i) { xs[i] = alc[sel[order[i]]]; perm[i] = sel[order[i]]; }
+  std::vector<double> m0s((size_t)ns * DISP_NG);
+  {
+    double *d_xs = nullptr, *d_m0 = nullptr, *d_l0g = nullptr; int* d_perm = nullptr;
+    CK(cudaMalloc((void**)&d_xs, (size_t)ns * 8)); CK(cudaMalloc((void**)&d_m0, (size_t)ns * DISP_NG * 8)); CK(cudaMalloc((void**)&d_perm, (size_t)ns * 4));
+    if (ctx->nranks > 1) d_l0g = tmpA; else d_l0g = ctx->dp_l0;
+    CK(cudaMemcpyAsync(d_xs, xs.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_perm, perm.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_tricube<<<ns, 128, 0, ctx->stream>>>(d_xs, d_perm, ns, q, d_l0g, DISP_NG, d_m0); CKL();
+    CK(cudaMemcpyAsync(m0s.data(), d_m0, m0s.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d_xs)); CK(cudaFree(d_m0)); CK(cudaFree(d_perm));
+  }
+  // m0 back to gene order; trended dispersion (:140-145)
+  std::vector<double> m0((size_t)G * DISP_NG, 0.0), trended(G, 0.0);
+  int i_min = 0;
+  for (int i = 0; i < ns; ++i) {
+    memcpy(&m0[(size_t)perm[i] * DISP_NG], &m0s[(size_t)i * DISP_NG], DISP_NG * 8);
+    trended[perm[i]] = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, &m0s[(size_t)i * DISP_NG]));
+  }
+  for (int i = 1; i < ns; ++i) if (alc[sel[i]] < alc[sel[i_min]]) i_min = i;   // which.min(AveLogCPM[sel])
+  { std::vector<char> issel(G, 0); for (int i : sel) issel[i] = 1; for (long long g = 0; g < G; ++g) if (!issel[g]) trended[g] = trended[sel[i_min]]; }
+  if (trended_out) memcpy(trended_out, trended.data() + g0, (size_t)Gl * 8);
+  // prior d.f. (:156-169): deviance at the trended dispersion -> limma fitFDist moments
+  double prior_df = prior_df_in;
+  if (!(prior_df >= 0.0)) {
+    CK(cudaMemcpyAsync(ctx->dp_phi_row, trended.data() + g0, (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dp_beta1, ctx->dp_beta0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    DispArgs a;
+    a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N;
+    RET(disp_nr(ctx, s, a, 1));
+    k_build_ytabs<<<Gl, YT, 0, ctx->stream>>>(ctx->dp_phi_row, Gl, nullptr, ctx->dp_tabR2, nullptr); CKL();
+    DISPATCH_K(ctx->K, {
+      RowGeom gg = geom(ctx, Gl, nullptr);
+      gg.tabR = ctx->dp_tabR2;  // log(y + r) for r = 1/trended
+      LAUNCH_ROWS(k_disp_dev<KT>, 1, Gl, gg, disp_state<KT>(ctx, s), ctx->dp_beta1, ctx->dp_phi_row, ctx->dp_dev);
+    });
+    std::vector<double> dev(G, 0.0);
+    CK(cudaMemcpyAsync(dev.data() + g0, ctx->dp_dev, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->nranks > 1) {
+      CK(cudaMemcpyAsync(tmpB, dev.data(), (size_t)G * 8, cudaMemcpyHostToDevice, ctx->stream));
+      RET(allreduce(ctx, tmpB, (size_t)G, NCCL_F64));
+      CK(cudaMemcpyAsync(dev.data(), tmpB, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    std::vector<double> s2(ns);
+    for (int i = 0; i < ns; ++i) s2[i] = std::max(dev[sel[i]] / (N - 1.0), 0.0);
+    prior_df = fit_f_dist_df2(s2, N - 1.0);
+  }
+  if (prior_df_out) *prior_df_out = prior_df;
+  const double prior_n = prior_df / (N - 1.0);  // :171 (ncoefs = 1)
+  // tagwise (:172-190): per gene, maximise the spline through l0 + prior.n m0
+  std::vector<double> tag(trended);
+  if (!(prior_n > 1e6)) {
+    double l0a[DISP_NG];
+    for (int i : sel) {
+      for (int d = 0; d < DISP_NG; ++d) l0a[d] = l0[(size_t)i * DISP_NG + d] + prior_n * m0[(size_t)i * DISP_NG + d];
+      tag[i] = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, l0a));
+    }
+  }
+  // psi <- tagwise where finite (R/ruvIIInb.R:564)
+  std::vector<double> old(Gl);
+  CK(cudaMemcpyAsync(old.data(), s.psi, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int g = 0; g < Gl; ++g) if (std::isfinite(tag[g0 + g])) old[g] = tag[g0 + g];
+  CK(cudaMemcpyAsync(s.psi, old.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->psi_ver++; s.sig_valid = false;
+  if (tmpA) CK(cudaFree(tmpA));
+  if (tmpB) CK(cudaFree(tmpB));
+  return RUVNB_OK;
+}
+
+int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out) {
+  return ruvnb_estimate_disp_ex(ctx, o, -1.0, common_out, nullptr, nullptr);
+}
+
+}  // extern "C"
 #include "stubs.cuh"

@@ -1,0 +1,61 @@
+"""GPU parity of the dispersion step (H3, R/estimateDisp.par.R) against oracle/edger.py on the same inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(G=150, N=900, k=2, m=3, n_ctl=40, seed=31, gmean_mu=0.5):
+    from ruviiinb_b200 import synth
+    Y, M, ctl, truth = synth.make_counts(G, N, k, m, n_ctl, seed=seed, gmean_mu=gmean_mu)
+    rng = np.random.default_rng(seed)
+    W = truth["W"] / np.sqrt((truth["W"] ** 2).sum(axis=0))
+    alpha = truth["alpha"] * np.sqrt((truth["W"] ** 2).sum(axis=0)) + 0.05 * rng.standard_normal((G, k))
+    Mb = truth["Mb"] + 0.05 * rng.standard_normal((G, m))
+    offs = alpha @ W.T + Mb[:, truth["grp"]]
+    return Y, ctl, truth, W, alpha, Mb, offs
+
+
+def _ctx(Y, ctl, truth, W, alpha, Mb, k):
+    from ruviiinb_b200 import _lib
+    from tests.parity import make_ctx
+    ctx = make_ctx(Y, truth["grp"], ctl)
+    ctx.set_state("W", W)
+    ctx.set_state("alpha", alpha)
+    ctx.set_state("Mb", Mb)
+    ctx.set_state("gmean", truth["gmean"])  # must NOT enter the offset (R/ruvIIInb.R:206)
+    return ctx, _lib.default_opts(k=k)
+
+
+def test_apl_grid_matches_oracle():
+    from oracle import edger
+    Y, ctl, truth, W, alpha, Mb, offs = _case()
+    Y[7] = 0            # all-zero gene: rowSums < 5 -> not selected
+    Y[8, :] = 0
+    Y[8, 3] = 2         # rowSums = 2 < 5
+    Y[9] = np.random.default_rng(1).poisson(700.0, Y.shape[1])   # counts beyond the 128-entry tables
+    ctx, opts = _ctx(Y, ctl, truth, W, alpha, Mb, 2)
+    with ctx:
+        l0, rs = ctx.disp_apl_grid(opts)
+    assert np.array_equal(rs, Y.sum(axis=1))
+    sel = rs >= 5
+    assert np.isnan(l0[~sel]).all() and not sel[7] and not sel[8]
+    ref = edger.apl_grid(Y[sel].astype(float), offs[sel])
+    err = np.abs(l0[sel] - ref) / np.abs(ref)
+    assert err.max() < 1e-9, err.max()
+
+
+@pytest.mark.parametrize("prior_df", [None, 0.0, 7.5])
+def test_estimate_disp_matches_oracle(prior_df):
+    from oracle import edger
+    Y, ctl, truth, W, alpha, Mb, offs = _case(G=180, N=700, seed=33)
+    ref = edger.estimate_disp(Y.astype(float), offs, prior_df=prior_df)
+    ctx, opts = _ctx(Y, ctl, truth, W, alpha, Mb, 2)
+    with ctx:
+        out = ctx.estimate_disp_ex(opts, prior_df=prior_df)
+        psi = ctx.get_state("psi")
+    assert abs(out["common"] / ref["common"] - 1) < 1e-8
+    assert np.abs(out["trended"] / ref["trended"] - 1).max() < 1e-7
+    if prior_df is None:
+        assert abs(out["prior_df"] / ref["prior_df"] - 1) < 1e-6
+    assert np.abs(psi / ref["tagwise"] - 1).max() < 1e-6   # north_star tolerance on psi
