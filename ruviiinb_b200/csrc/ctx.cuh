@@ -14,6 +14,7 @@
 #include "../../include/ruvnb.h"
 #include "kernels.cuh"
 #include "disp.cuh"
+#include "res.cuh"
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------

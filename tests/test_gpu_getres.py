@@ -1,0 +1,54 @@
+"""GPU parity of get.res (R1-R4, R/get.res.R:12-129) against oracle/getres.py: Pearson (block-wise clip), logcounts,
+percentile-adjusted counts (exact integers)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _fitted(G=96, N=1100, k=2, m=3, seed=51):
+    from ruviiinb_b200 import synth
+    Y, M, ctl, truth = synth.make_counts(G, N, k, m, 24, seed=seed, gmean_mu=0.3)
+    rng = np.random.default_rng(seed)
+    Y[5] = rng.poisson(1500.0, N)           # counts far beyond the pmf-recurrence's short range
+    W = truth["W"] / np.sqrt((truth["W"] ** 2).sum(axis=0))
+    a = truth["alpha"] * np.sqrt((truth["W"] ** 2).sum(axis=0))
+    gmean = truth["gmean"].copy()
+    gmean[5] = np.log(1500.0)
+    return Y, ctl, truth, W, a, gmean
+
+
+def _run(kind, block_size, per_cell_mb):
+    from oracle import getres
+    from ruviiinb_b200 import _lib
+    from tests.parity import make_ctx
+    Y, ctl, truth, W, a, gmean = _fitted()
+    grp = truth["grp"]
+    Mb = truth["Mb"]
+    Mb_cells = Mb[:, grp]
+    if per_cell_mb:  # fastruvIII.nb's Mb.all: a genuinely per-cell matrix
+        Mb_cells = Mb_cells + 0.1 * np.random.default_rng(9).standard_normal(Mb_cells.shape)
+    ref = getres.get_res(dict(counts=Y, a=a, W=W, gmean=gmean, Mb=Mb_cells, psi=truth["psi"]), kind, block_size=block_size)
+    with make_ctx(Y, grp, ctl) as ctx:
+        ctx.set_state("W", W); ctx.set_state("alpha", a); ctx.set_state("gmean", gmean)
+        ctx.set_state("Mb", Mb); ctx.set_state("psi", truth["psi"])
+        got = ctx.get_res(kind, block_size=block_size, Mb_cells=Mb_cells if per_cell_mb else None)
+    return got, ref
+
+
+@pytest.mark.parametrize("per_cell_mb", [False, True])
+def test_pearson(per_cell_mb):
+    got, ref = _run(1, 256, per_cell_mb)
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+
+
+def test_logcounts():
+    got, ref = _run(2, 5000, False)
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("per_cell_mb", [False, True])
+def test_pac_exact(per_cell_mb):
+    got, ref = _run(3, 300, per_cell_mb)
+    mism = (got != ref)
+    assert mism.mean() <= 1e-5, (mism.sum(), got[mism][:5], ref[mism][:5])   # quantile-boundary ties only
