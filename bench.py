@@ -185,7 +185,17 @@ def cpu_sample_run(workload, steps, warmup, target_seconds=20.0):
 
 
 # ------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Keep the real stdout for the ONE JSON line: native libraries (NCCL prints its version banner on stdout) and
+    anything else writing to fd 1 go to stderr instead."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -213,7 +223,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": dict(value=v, unit="gene-fits/s", **desc),
                 "e2e": {"value": v, "unit": "gene-fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return
 
     import torch
@@ -293,6 +303,7 @@ def main():
         clocks.start()
     e0.record(stream)
     logls, exact_rows_steps, exact_cells_steps = [], [], []
+    ctx.cert_diag()
     for _ in range(args.steps):
         ll, bad = ctx.irls_iteration(opts)
         ctx.accept()
@@ -306,6 +317,7 @@ def main():
     launches = ctx.kernel_launches - l0
     exact_rows = ctx.last_exact_rows
     ktimes = ctx.kernel_times()
+    cert_diag = ctx.cert_diag()
     fp64_peak = ctx.measure_fp64() if rank == 0 else None
     tms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -378,13 +390,13 @@ def main():
     line = {"metric": "NB IRLS gene-fits/sec", "value": value, "unit": "gene-fits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clk,
-            "gpu_launches": int(launches), "exact_mad_rows_per_step": exact_rows_steps, "exact_mad_cells_per_step": exact_cells_steps, "roofline": roofline, "logl_trace": logls, "datagen_seconds": t_gen}
+            "gpu_launches": int(launches), "exact_mad_rows_per_step": exact_rows_steps, "exact_mad_cells_per_step": exact_cells_steps, "cert_fail_reasons": cert_diag, "roofline": roofline, "logl_trace": logls, "datagen_seconds": t_gen}
     if e2e:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         v, desc, _ = cpu_sample_run(args.workload, 2, 1)
         line["cpu_baseline"] = dict(value=v, unit="gene-fits/s", **desc)
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

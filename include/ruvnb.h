@@ -109,6 +109,10 @@ void* ruvnb_stream(const ruvnb_ctx* ctx);
 /* Gene rows / cells of the last ruvnb_irls_iteration whose Huber certificate failed (exact MAD computed). */
 int ruvnb_last_exact_rows(const ruvnb_ctx* ctx);
 int ruvnb_last_exact_cells(const ruvnb_ctx* ctx);
+/* Why gene rows failed the Huber certificate since the last call (tuning aid; resets the counters): [0] no usable
+ * hint, [1] NaN deviance, [2] max|d| = 0, [3] max|d| outgrew the hint, [4]/[5] the median left the hint window
+ * below/above, [6] more than half of the row inside the window, [7] fast path off. */
+int ruvnb_cert_diag(ruvnb_ctx* ctx, int out[8]);
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (2 flops per DFMA; a register-only DFMA-chain
  * kernel, best of 5): the denominator of the FP64 roofline bench.py reports beside the HBM one. */
 int ruvnb_measure_fp64(ruvnb_ctx* ctx, double* tflops);

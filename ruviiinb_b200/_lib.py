@@ -17,7 +17,7 @@ MAX_K = 8
 SYMBOLS = [
     "ruvnb_abi_version", "ruvnb_opts_default", "ruvnb_create", "ruvnb_destroy", "ruvnb_last_error",
     "ruvnb_kernel_launches", "ruvnb_kernel_time", "ruvnb_kernel_time_reset", "ruvnb_stream", "ruvnb_last_exact_rows",
-    "ruvnb_last_exact_cells", "ruvnb_selftest_math", "ruvnb_measure_fp64",
+    "ruvnb_last_exact_cells", "ruvnb_selftest_math", "ruvnb_measure_fp64", "ruvnb_cert_diag",
     "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
     "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_get_counts", "ruvnb_set_state",
     "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_snapshot_best",
@@ -77,6 +77,7 @@ def load():
     lib.ruvnb_last_exact_rows.argtypes = [vp]
     lib.ruvnb_last_exact_cells.argtypes = [vp]
     lib.ruvnb_measure_fp64.argtypes = [vp, dp]
+    lib.ruvnb_cert_diag.argtypes = [vp, ip]
     lib.ruvnb_selftest_math.argtypes = [C.c_int, vp, vp, C.c_int64]
     lib.ruvnb_comm_unique_id.argtypes = [vp]
     lib.ruvnb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
@@ -305,6 +306,11 @@ class Context:
     @property
     def last_exact_rows(self):
         return int(self.lib.ruvnb_last_exact_rows(self.h))
+
+    def cert_diag(self):
+        out = (C.c_int * 8)()
+        self._ck(self.lib.ruvnb_cert_diag(self.h, out))
+        return list(out)
 
     def measure_fp64(self):
         t = C.c_double()

@@ -101,6 +101,7 @@ struct ruvnb_ctx {
   double* ctl_tabR = nullptr;                                 // [n_ctl][YT]
   const double* ytab_psi = nullptr; long long ytab_ver = -1, psi_ver = 0;  // which psi the tables were built from
   int *w_fail = nullptr;         // [1 + Np] fast-W failures: count, then positions
+  int *cert_diag = nullptr;      // [8] certificate failure reasons (ruvnb_cert_diag)
   // dispersion scratch (disp.cuh), allocated on first use
   double *dp_beta = nullptr, *dp_beta0 = nullptr, *dp_rowsum = nullptr, *dp_emean = nullptr, *dp_l0 = nullptr, *dp_phi_grid = nullptr,
          *dp_tabG = nullptr, *dp_tabRg = nullptr, *dp_lgr_grid = nullptr, *dp_zeros = nullptr, *dp_beta1 = nullptr, *dp_phi_row = nullptr,

@@ -10,7 +10,7 @@
 //   k_disp_dev    NB deviance at a per-gene dispersion (for the prior d.f.)
 //   k_tricube     local-constant tricube smoother of the 21 columns of l0 against AveLogCPM (locfit stand-in)
 // Host: spline maximisation (FMM spline + edgeR interpolator::find_max), limma fitFDist moments, the control flow.
-// The restatement these follow is oracle/edger.py (parity unpinned: edgeR/limma/locfit are not under /root/reference).
+// The CPU checker restates the same arithmetic in its `edger` module (parity unpinned: edgeR/limma/locfit are not under /root/reference).
 #pragma once
 #include "kernels.cuh"
 

@@ -358,7 +358,7 @@ struct OpLoglik {
   double acc, rlogr;
   double* out;
   // certificate
-  double* hint; double* sigma_out; double kh; int fastpath; long long n;
+  double* hint; double* sigma_out; double kh; int fastpath; long long n; int* diag;
   double u_lo, u_hi, u_wl, u_wh, hmax; int c1, c2, c3, bad; bool cert;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); acc = 0.0; rlogr = g.r * log(g.r);
@@ -431,6 +431,10 @@ struct OpLoglik {
         double room = fmin(d_of_u(u_lo) - d_of_u(u_wl), d_of_u(u_wh) - d_of_u(u_hi));
         long long kl = (n - 1) / 2, ku = n / 2;
         ok = (mx > 0.0) && (t <= room) && ((long long)a1 <= kl) && ((long long)a2 <= n - 1 - ku) && ((long long)a3 <= kl);
+        if (!ok && diag) {  // why the certificate failed (tuning aid; ruvnb_cert_diag)
+          int why = !(mx > 0.0) ? 2 : !(t <= room) ? 3 : ((long long)a1 > kl) ? 4 : ((long long)a2 > n - 1 - ku) ? 5 : 6;
+          atomicAdd(diag + why, 1);
+        }
         if (ok) {
           // recentre the hint on the median estimated from the counts (density inside [lo, hi] taken as uniform).
           // Hints never affect results -- the certificate re-verifies them -- they only decide how often the exact
@@ -446,17 +450,21 @@ struct OpLoglik {
         }
       }
     }
-    if (lane == 0) sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
+    if (lane == 0) {
+      sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
+      if (diag && !cert) atomicAdd(diag + (fastpath ? 0 : 7), 1);   // 0: no usable hint (first visit or live Huber weights)
+      if (diag && cert && __any_sync(1u, bad)) atomicAdd(diag + 1, 1);
+    }
   }
 };
 template <int K>
 __global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneState<K> st, double* out, double* hint,
-                                                           double* sigma_out, double kh, int fastpath, long long n) {
+                                                           double* sigma_out, double kh, int fastpath, long long n, int* diag) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) sh.wsets[0] = st.W;
   OpLoglik<K> op;
-  op.st = st; op.out = out; op.hint = hint; op.sigma_out = sigma_out; op.kh = kh; op.fastpath = fastpath; op.n = n;
+  op.st = st; op.out = out; op.hint = hint; op.sigma_out = sigma_out; op.kh = kh; op.fastpath = fastpath; op.n = n; op.diag = diag;
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
@@ -694,15 +702,32 @@ __global__ void k_revert_if(const int* flag, double* dst, const double* src, lon
   if (i < n) dst[i] = src[i];
 }
 
-// median / mad of strided vectors (columns of alpha: R/ruvIIInb.R:371-372), one CTA per vector
-__global__ void __launch_bounds__(256) k_strided_medmad(const double* base, long long vec_stride, long long elem_stride,
-                                                       int len, double* med, double* mad) {
-  __shared__ SelScratch sc;
+// median / mad of strided vectors (columns of alpha: R/ruvIIInb.R:371-372), one CTA of RS_NT threads per vector:
+// 12-bit radix descent with early gather (select.cuh: cta_two_middles); NaN anywhere -> NaN (R's median)
+__global__ void __launch_bounds__(RS_NT) k_strided_medmad(const double* base, long long vec_stride, long long elem_stride,
+                                                         int len, double* med, double* mad) {
+  __shared__ RowSelScratch sc;
+  __shared__ int s_nan;
   const double* p = base + (long long)blockIdx.x * vec_stride;
-  auto val = [&](int i) { return p[(long long)i * elem_stride]; };
-  auto valid = [&](int) { return true; };
-  double me, ma;
-  group_median_mad<256>(len, val, valid, &sc, threadIdx.x, &me, &ma);
+  const int lenp = (len + RS_NT - 1) / RS_NT * RS_NT;
+  const unsigned long long kinf = f64_key(__longlong_as_double(0x7ff0000000000000ll));
+  if (threadIdx.x == 0) s_nan = 0;
+  __syncthreads();
+  int nn = 0;
+  for (int i = threadIdx.x; i < len; i += RS_NT) { double v = p[(long long)i * elem_stride]; nn |= (v != v); }
+  if (nn) atomicOr(&s_nan, 1);
+  __syncthreads();
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  double me = qnan, ma = qnan;
+  if (!s_nan && len > 0) {
+    unsigned long long klo, khi;
+    auto key1 = [&](int i) { return i < len ? f64_key(p[(long long)i * elem_stride]) : kinf; };
+    cta_two_middles(lenp, (long long)len, key1, &sc, &klo, &khi);
+    me = (len & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0;
+    auto key2 = [&](int i) { return i < len ? f64_key(fabs(p[(long long)i * elem_stride] - me)) : kinf; };
+    cta_two_middles(lenp, (long long)len, key2, &sc, &klo, &khi);
+    ma = MAD_CONST * ((len & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0);
+  }
   if (threadIdx.x == 0) { med[blockIdx.x] = me; mad[blockIdx.x] = ma; }
 }
 
@@ -1134,6 +1159,25 @@ __global__ void k_gmean_mb(int Gl, int m, const double* S0, const double* S1, co
   if (nn) atomicAdd(nan_flag, nn);
   if (nb) atomicAdd(bad, nb);
 }
+// R median of m <= 64 finite values held two per lane (x0: item lane, x1: item lane + 32), by rank counting
+__device__ __forceinline__ double warp_small_median(double x0, double x1, int m, int lane) {
+  int lt0 = 0, eq0 = 0, lt1 = 0, eq1 = 0;
+  for (int i = 0; i < m; ++i) {
+    double a = __shfl_sync(FULL, x0, i & 31), b = __shfl_sync(FULL, x1, i & 31);
+    double v = i < 32 ? a : b;
+    lt0 += v < x0; eq0 += v == x0; lt1 += v < x1; eq1 += v == x1;
+  }
+  const int kl = (m - 1) / 2, ku = m / 2;
+  double lo = 0.0, hi = 0.0;   // exactly one distinct value covers each rank; sum the (identical) candidates' max
+  bool has0 = lane < m, has1 = lane + 32 < m;
+  double clo = -1.79769313486231570e308, chi = -1.79769313486231570e308;
+  if (has0 && lt0 <= kl && kl < lt0 + eq0) clo = x0;
+  if (has1 && lt1 <= kl && kl < lt1 + eq1) clo = fmax(clo, x1);
+  if (has0 && lt0 <= ku && ku < lt0 + eq0) chi = x0;
+  if (has1 && lt1 <= ku && ku < lt1 + eq1) chi = fmax(chi, x1);
+  lo = warp_max(clo); hi = warp_max(chi);
+  return (m & 1) ? hi : (lo + hi) / 2.0;
+}
 // any NA -> whole Mb reverts (:424); NA/Inf -> 0 (:425); each row clamped to median +- 4 mad (:428-433).
 // One warp per gene.
 __global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* nan_flag, const double* Mb_old,
@@ -1150,10 +1194,17 @@ __global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* n
     row[j] = v;
   }
   __syncwarp();
-  auto val = [&](int i) { return row[i]; };
-  auto vld = [&](int) { return true; };
   double med, mad;
-  group_median_mad<32>(m, val, vld, &sc[warp], lane, &med, &mad);
+  if (m <= 64) {
+    // rank by counting: each lane holds up to two values, every value is broadcast once
+    double v0 = lane < m ? row[lane] : 0.0, v1 = lane + 32 < m ? row[lane + 32] : 0.0;
+    med = warp_small_median(v0, v1, m, lane);
+    mad = MAD_CONST * warp_small_median(fabs(v0 - med), fabs(v1 - med), m, lane);
+  } else {
+    auto val = [&](int i) { return row[i]; };
+    auto vld = [&](int) { return true; };
+    group_median_mad<32>(m, val, vld, &sc[warp], lane, &med, &mad);
+  }
   double hi = med + 4.0 * mad, lo = med - 4.0 * mad;
   for (int j = lane; j < m; j += 32) {
     double v = row[j];

@@ -81,6 +81,19 @@ int ruvnb_measure_fp64(ruvnb_ctx* ctx, double* tflops) {
   *tflops = best;
   return RUVNB_OK;
 }
+// why rows failed the Huber certificate since the last call (tuning aid): [0] no usable hint, [1] NaN deviance,
+// [2] max|d| = 0, [3] max|d| grew past the hint's margin, [4]/[5] the median left [lo, hi] below/above,
+// [6] more than half of the row inside the window, [7] fast path off.  Resets the counters.
+int ruvnb_cert_diag(ruvnb_ctx* ctx, int out[8]) {
+  if (!ctx || !out) return RUVNB_EARG;
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  if (!ctx->cert_diag) return RUVNB_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(out, ctx->cert_diag, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(ctx->cert_diag, 0, 8 * sizeof(int), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
 int ruvnb_last_exact_cells(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_cells : -1; }
 int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n) {
   if (!x || !out || n < 0 || which < 0 || which > 1) return RUVNB_EARG;
@@ -421,6 +434,8 @@ static int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->lgr, Gl));
   RET(dev_alloc(ctx, &ctx->ctl_tabR, (long long)ctx->n_ctl * YT));
   RET(dev_alloc(ctx, &ctx->w_fail, ctx->Np + 1));
+  RET(dev_alloc(ctx, &ctx->cert_diag, 8));
+  CK(cudaMemsetAsync(ctx->cert_diag, 0, 8 * sizeof(int), ctx->stream));
   CK(cudaMemsetAsync(ctx->w_fail, 0, sizeof(int), ctx->stream));
   {
     MathTabs mt;
@@ -561,7 +576,7 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
   KEV_BEGIN(4);
   DISPATCH_K(ctx->K, {
     LAUNCH_ROWS(k_loglik<KT>, 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), out, ctx->hint, s.sigma, kh,
-                o->huber_fastpath, (long long)ctx->N);
+                o->huber_fastpath, (long long)ctx->N, ctx->cert_diag);
   });
   KEV_END(4);
   s.sig_valid = true; s.maybe_active = false;
@@ -672,9 +687,9 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     CK(cudaMemsetAsync(ctx->alpha_full, 0, (size_t)ctx->G * K * 8, ctx->stream));
     CK(cudaMemcpyAsync(ctx->alpha_full + ctx->g0 * K, n.alpha, (size_t)Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     RET(allreduce(ctx, ctx->alpha_full, (size_t)ctx->G * K, NCCL_F64));
-    k_strided_medmad<<<K, 256, 0, ctx->stream>>>(ctx->alpha_full, 1, K, (int)ctx->G, ctx->med, ctx->mad);
+    k_strided_medmad<<<K, RS_NT, 0, ctx->stream>>>(ctx->alpha_full, 1, K, (int)ctx->G, ctx->med, ctx->mad);
   } else {
-    k_strided_medmad<<<K, 256, 0, ctx->stream>>>(n.alpha, 1, K, Gl, ctx->med, ctx->mad);
+    k_strided_medmad<<<K, RS_NT, 0, ctx->stream>>>(n.alpha, 1, K, Gl, ctx->med, ctx->mad);
   }
   CKL();
   k_clamp_cols<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(n.alpha, Gl, K, ctx->med, ctx->mad);
