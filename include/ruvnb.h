@@ -168,6 +168,10 @@ int ruvnb_loglik(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total);
  *     log-likelihood.  The candidate becomes the current state; `bad` receives the three
  *     problematic-entry counts; *logl_new the candidate total. */
 int ruvnb_irls_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]);
+/* H4/H5  ZINB (opts.zinb and cells flagged zeroinf): pi0 of the current parameter set by optim()'s one-dimensional
+ *     Nelder-Mead from p = -2 (R/ruvIIInb.R:237-251,770-772), then the E-step -- the weights wt.zinb (:254-264) are
+ *     never stored: every sweep recomputes them from (pi0, the psi of this call).  bad: non-finite pi0 entries (:453). */
+int ruvnb_zinb_pi0(ruvnb_ctx* ctx, const ruvnb_opts* o, int* bad);
 /* H14 snapshots: best.* <- current (R/ruvIIInb.R:296,516) / current <- best.* (:492). */
 int ruvnb_snapshot_best(ruvnb_ctx* ctx);
 int ruvnb_restore_best(ruvnb_ctx* ctx);

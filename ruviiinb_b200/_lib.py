@@ -20,7 +20,7 @@ SYMBOLS = [
     "ruvnb_last_exact_cells", "ruvnb_selftest_math", "ruvnb_measure_fp64", "ruvnb_cert_diag",
     "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
     "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_get_counts", "ruvnb_set_state",
-    "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_snapshot_best",
+    "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_zinb_pi0", "ruvnb_snapshot_best",
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp", "ruvnb_estimate_disp_ex",
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res",
 ]
@@ -91,6 +91,7 @@ def load():
     lib.ruvnb_init_coef.argtypes = [vp, C.POINTER(Opts)]
     lib.ruvnb_loglik.argtypes = [vp, C.POINTER(Opts), dp]
     lib.ruvnb_irls_iteration.argtypes = [vp, C.POINTER(Opts), dp, ip]
+    lib.ruvnb_zinb_pi0.argtypes = [vp, C.POINTER(Opts), ip]
     lib.ruvnb_snapshot_best.argtypes = [vp]
     lib.ruvnb_restore_best.argtypes = [vp]
     lib.ruvnb_halve_steps.argtypes = [vp, C.POINTER(Opts)]
@@ -228,6 +229,11 @@ class Context:
         bad = (C.c_int * 3)()
         self._ck(self.lib.ruvnb_irls_iteration(self.h, C.byref(opts), C.byref(t), bad))
         return t.value, list(bad)
+
+    def zinb_pi0(self, opts):
+        bad = C.c_int()
+        self._ck(self.lib.ruvnb_zinb_pi0(self.h, C.byref(opts), C.byref(bad)))
+        return bad.value
 
     def snapshot_best(self):
         self._ck(self.lib.ruvnb_snapshot_best(self.h))

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "disp.cuh"
 #include "res.cuh"
+#include "zinb.cuh"
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------
@@ -50,6 +51,7 @@ struct StateSet {  // one parameter set on device
   // Huber scale of THIS parameter set, written by the log-likelihood sweep (certificate) and completed by the
   // exact path: +Inf = every weight provably 1, 0 = not evaluated yet, else mad(signdev)/0.6745
   double* sigma = nullptr;
+  double* psi_w = nullptr;  // ZINB: the dispersion the last E-step (wt.zinb update) used -- R/ruvIIInb.R:262,465,502
   bool sig_valid = false;   // sigma was produced for the parameters currently held
   bool maybe_active = false; // some rows went through the exact path: their sigma may be finite (live Huber weights)
 };
@@ -102,6 +104,13 @@ struct ruvnb_ctx {
   const double* ytab_psi = nullptr; long long ytab_ver = -1, psi_ver = 0;  // which psi the tables were built from
   int *w_fail = nullptr;         // [1 + Np] fast-W failures: count, then positions
   int *cert_diag = nullptr;      // [8] certificate failure reasons (ruvnb_cert_diag)
+  // ZINB (zinb.cuh)
+  bool zinb_on = false;          // opts.zinb && some cell is flagged zero-inflated
+  uint8_t* d_zinf = nullptr;     // [Np] zero-inflated cells, permuted like the counts
+  double *zq = nullptr, *z_spos = nullptr, *z_xeval = nullptr, *z_feval = nullptr;  // q rows [Gl][Np], S_pos, NM points / values
+  int *z_npos = nullptr, *z_active = nullptr;
+  NMState* z_nm = nullptr;
+  int last_nm_rounds = 0;
   // dispersion scratch (disp.cuh), allocated on first use
   double *dp_beta = nullptr, *dp_beta0 = nullptr, *dp_rowsum = nullptr, *dp_emean = nullptr, *dp_l0 = nullptr, *dp_phi_grid = nullptr,
          *dp_tabG = nullptr, *dp_tabRg = nullptr, *dp_lgr_grid = nullptr, *dp_zeros = nullptr, *dp_beta1 = nullptr, *dp_phi_row = nullptr,

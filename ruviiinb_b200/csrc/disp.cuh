@@ -33,6 +33,7 @@ struct DispArgs {
   double tol;
   int* notconv;             // set to 1 when some |step| >= tol
   double n;                 // number of cells
+  const double* gm_real;    // [Gl] gmean of the parameter set: the ZINB weights wt.zinb need mu = exp(offset + gmean)
 };
 
 // ---- start values ---------------------------------------------------------------------------------------------
@@ -40,41 +41,43 @@ template <int K>
 struct OpDispInit {
   static constexpr bool PADS = false;
   GeneState<K> st; GeneRegs<K> g;
-  double s_ye, s_y, s_e; int nz;
-  double *beta0, *rowsum, *emean; double n;
-  __device__ __forceinline__ void row_begin(int row, int) { g.load(st, row); s_ye = s_y = s_e = 0.0; nz = 0; }
+  double s_ye, s_y, s_e, s_w; int nz;
+  double *beta0, *rowsum, *emean; double n; const double* gm_real; double gmr;
+  __device__ __forceinline__ void row_begin(int row, int) { g.load(st, row); s_ye = s_y = s_e = s_w = 0.0; nz = 0; gmr = gm_real[row]; }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m) {
+  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
     if (!m) return;
     double E = g.expm(off);
     double yd = (double)y;
-    s_e += E; s_y += yd;
-    if (y > 0) { s_ye += yd / E; nz = 1; }
+    double w = g.zi ? g.wz(y, E * exp(gmr), pos) : 1.0;   // weights = wt.zinb (R/ruvIIInb.R:211)
+    s_e += E; s_y += yd; s_w += w;
+    if (y > 0) { s_ye += yd / E * w; nz = 1; }
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     double o0, o1;
     g.lmu_pair(tile, ti, o0, o1);
-    one(y0, o0, m0); one(y1, o1, m1);
+    const long long pos = (long long)c * CH + (ti & (CH - 1));
+    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
-    double a = warp_sum(s_ye), b = warp_sum(s_y), e = warp_sum(s_e);
+    double a = warp_sum(s_ye), b = warp_sum(s_y), e = warp_sum(s_e), tw = warp_sum(s_w);
     int any = __any_sync(FULL, nz);
     if ((threadIdx.x & 31) == 0) {
-      beta0[row] = any ? log(a / n) : -__longlong_as_double(0x7ff0000000000000ll);
+      beta0[row] = any ? log(a / tw) : -__longlong_as_double(0x7ff0000000000000ll);   // glm_one_group start
       rowsum[row] = b; emean[row] = e / n;
     }
   }
 };
 template <int K>
 __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_init(RowGeom geo, GeneState<K> st, double* beta0, double* rowsum,
-                                                              double* emean, double n) {
+                                                              double* emean, double n, const double* gm_real) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) sh.wsets[0] = st.W;
   OpDispInit<K> op;
-  op.st = st; op.beta0 = beta0; op.rowsum = rowsum; op.emean = emean; op.n = n;
+  op.st = st; op.beta0 = beta0; op.rowsum = rowsum; op.emean = emean; op.n = n; op.gm_real = gm_real;
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
@@ -84,10 +87,11 @@ struct OpDispNR {
   static constexpr bool PADS = false;
   GeneState<K> st; GeneRegs<K> g; DispArgs a;
   double eb[ND], phi[ND], dl[ND], info[ND];
-  double yadd, escale; bool live;
+  double yadd, escale, egm; bool live;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
     live = false;
+    egm = g.zi ? exp(a.gm_real[row]) : 1.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double b = a.beta[(long long)row * a.ldb + a.d0 + d];
@@ -100,15 +104,16 @@ struct OpDispNR {
     if (a.emean) { double pcm = a.prior_count / a.emean[row]; yadd = pcm; escale = fma(2.0, pcm, 1.0); }
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m) {
+  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
     if (!m) return;
     double E = g.expm(off);
+    const double wzv = g.zi ? g.wz(y, E * egm, pos) : 1.0;
     double yd = fma(yadd, E, (double)y);
     E *= escale;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double mu = eb[d] * E;
-      double w = 1.0 / fma(mu, phi[d], 1.0);
+      double w = wzv / fma(mu, phi[d], 1.0);
       dl[d] = fma(yd - mu, w, dl[d]);
       info[d] = fma(mu, w, info[d]);
     }
@@ -118,7 +123,8 @@ struct OpDispNR {
     if (!live) return;  // all-zero gene: beta = -Inf stays (edgeR returns R_NegInf)
     double o0, o1;
     g.lmu_pair(tile, ti, o0, o1);
-    one(y0, o0, m0); one(y1, o1, m1);
+    const long long pos = (long long)c * CH + (ti & (CH - 1));
+    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
@@ -154,10 +160,11 @@ struct OpDispAPL {
   const double (*tg)[YT];   // shared: [ND][YT]
   const double* lgr_grid;   // [ND] lgamma(r_d)
   double eb[ND], r[ND], ll[ND], ww[ND];
-  double syo, sy;           // sum y * offset, sum y: y log mu = y (beta_d + offset) is assembled at the end of the row
+  double syo, sy, sw, egm;  // sum w y offset, sum w y (y log mu = y (beta_d + offset) is assembled at the row end), sum w
   double* l0; int ld0;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
+    egm = g.zi ? exp(a.gm_real[row]) : 1.0; sw = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       eb[d] = exp(fmax(a.beta[(long long)row * a.ldb + a.d0 + d], -1e8));  // mglmOneWay: pmax(beta, -1e8)
@@ -167,30 +174,32 @@ struct OpDispAPL {
     syo = 0.0; sy = 0.0;
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m) {
+  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
     if (!m) return;
     double E = g.expm(off);
     double yd = (double)y;
-    syo = fma(yd, off, syo); sy += yd;
+    const double wzv = g.zi ? g.wz(y, E * egm, pos) : 1.0;
+    syo = fma(yd * wzv, off, syo); sy = fma(yd, wzv, sy); sw += wzv;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double mu = eb[d] * E;
       double mr = mu + r[d];
       double t = -(yd + r[d]) * flog(mr, g.mt->rc, g.mt->lc);
       if (y > 0) t += (y < YT) ? tg[d][y] : nb_big_lgterm(yd, r[d], lgr_grid[d], g.mt);
-      ll[d] += t;
-      ww[d] = fma(mu * r[d], 1.0 / mr, ww[d]);   // mu / (1 + phi mu)
+      ll[d] = fma(wzv, t, ll[d]);
+      ww[d] = fma(wzv * mu * r[d], 1.0 / mr, ww[d]);   // w mu / (1 + phi mu)
     }
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     double o0, o1;
     g.lmu_pair(tile, ti, o0, o1);
-    one(y0, o0, m0); one(y1, o1, m1);
+    const long long pos = (long long)c * CH + (ti & (CH - 1));
+    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
-    double tyo = warp_sum(syo), ty = warp_sum(sy);
+    double tyo = warp_sum(syo), ty = warp_sum(sy), tw = warp_sum(sw);
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double s1 = warp_sum(ll[d]), s2 = warp_sum(ww[d]);
@@ -199,7 +208,7 @@ struct OpDispAPL {
         double adj = 0.5 * log(s2 < low ? low : s2);
         double beta = fmax(a.beta[(long long)row * a.ldb + a.d0 + d], -1e8);
         double ylogmu = ty > 0.0 ? fma(beta, ty, tyo) : 0.0;
-        l0[(long long)row * ld0 + a.d0 + d] = s1 + ylogmu + a.n * r[d] * log(r[d]) - adj;
+        l0[(long long)row * ld0 + a.d0 + d] = s1 + ylogmu + tw * r[d] * log(r[d]) - adj;   // tw = n when all weights are 1
       }
     }
   }
@@ -221,24 +230,28 @@ template <int K>
 struct OpDispDev {
   static constexpr bool PADS = false;
   GeneState<K> st; GeneRegs<K> g;
-  const double *beta, *phi_row; double* dev;
-  double b, eb, r, acc;
+  const double *beta, *phi_row, *gm_real; double* dev;
+  double b, eb, r, acc, egm;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); b = fmax(beta[row], -1e8); eb = exp(b); r = 1.0 / phi_row[row]; acc = 0.0;
+    egm = g.zi ? exp(gm_real[row]) : 1.0;
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m) {
+  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
     if (!m) return;
-    double mu = eb * g.expm(off);
+    double E = g.expm(off);
+    double mu = eb * E;
     double yd = (double)y;
+    const double wzv = g.zi ? g.wz(y, E * egm, pos) : 1.0;
     // unit deviance / 2 = y log(y/mu) - (y + r) log((y + r)/(mu + r)); the tables of the row were built for phi_row
-    acc += nb_devhalf_t(y, yd, b + off, flog(mu + r, g.mt->rc, g.mt->lc), r, g.tr, g.mt);
+    acc = fma(wzv, nb_devhalf_t(y, yd, b + off, flog(mu + r, g.mt->rc, g.mt->lc), r, g.tr, g.mt), acc);
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     double o0, o1;
     g.lmu_pair(tile, ti, o0, o1);
-    one(y0, o0, m0); one(y1, o1, m1);
+    const long long pos = (long long)c * CH + (ti & (CH - 1));
+    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
@@ -248,12 +261,12 @@ struct OpDispDev {
 };
 template <int K>
 __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_dev(RowGeom geo, GeneState<K> st, const double* beta, const double* phi_row,
-                                                             double* dev) {
+                                                             const double* gm_real, double* dev) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) sh.wsets[0] = st.W;
   OpDispDev<K> op;
-  op.st = st; op.beta = beta; op.phi_row = phi_row; op.dev = dev;
+  op.st = st; op.beta = beta; op.phi_row = phi_row; op.dev = dev; op.gm_real = gm_real;
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 

@@ -24,6 +24,7 @@ struct RowGeom {
   const double* tabL;   // [Gl][YT] lgamma(y+r) - lgamma(r) - lgamma(y+1)
   const double* tabR;   // [Gl][YT] log(y + r)
   const double* lgr;    // [Gl] lgamma(r)
+  const uint8_t* zinf;  // [Np] zero-inflated cells (permuted like the counts) or nullptr (plain NB)
 };
 
 template <int K>
@@ -35,6 +36,10 @@ struct GeneState {  // pointers to one parameter set (current, candidate or best
   const double* step;
   const double* W;      // [K][Np]
   int m;
+  // ZINB (R/ruvIIInb.R:237-264,435-467): pi0 and the dispersion the last E-step used; zinb = 0 -> plain NB
+  const double* pi0;
+  const double* psi_w;
+  int zinb;
 };
 
 // chunks per shared-memory stage: 512 cells for k <= 5, 256 above (tile bytes = 2 x NSETS x K x 8 x cells)
@@ -78,6 +83,9 @@ struct GeneRegs {
   static constexpr int CELLS = TileCfg<K>::CELLS;
   double gmean, psi, r, step, lgr;
   bool rok;                   // psi in [1e-100, 1e100]
+  bool zi;                    // zero-inflation on for this launch
+  double pi0, rw, lrw;        // ZINB: pi0_g, size 1/psi_w and its log
+  const uint8_t* zinf;
   double a[K];
   const double* mb;
   double mbj;
@@ -88,6 +96,9 @@ struct GeneRegs {
     psi = st.psi[row];
     r = 1.0 / psi;
     rok = (psi > 1e-100) & (psi < 1e100);
+    zi = st.zinb != 0;
+    pi0 = 0.0; rw = r; lrw = 0.0;
+    if (zi) { pi0 = st.pi0[row]; rw = 1.0 / st.psi_w[row]; lrw = log(rw); }
     step = st.step ? st.step[row] : 1.0;
 #pragma unroll
     for (int l = 0; l < K; ++l) a[l] = st.alpha[(long long)row * K + l];
@@ -110,6 +121,13 @@ struct GeneRegs {
       s1 = fma(a[l], v.y, s1);
     }
     l0 = s0; l1 = s1;
+  }
+  // E-step weight of a zero count in a zero-inflated cell: 1 - pi0 / (pi0 + (1 - pi0) dnbinom(0; mu, size = rw))
+  // (R/ruvIIInb.R:262,465,502); 1 elsewhere.  pos = position of the cell in the permuted row.
+  __device__ __forceinline__ double wz(int y, double mu, long long pos) const {
+    if (y != 0 || !zinf[pos]) return 1.0;
+    double q = fexp(-rw * (flog(mu + rw, mt->rc, mt->lc) - lrw), mt->ex);
+    return 1.0 - pi0 / (pi0 + (1.0 - pi0) * q);
   }
   // both linear predictors inside the range where fexp_nc / flog_nc / frcp need no checks
   __device__ __forceinline__ bool fast_range(double l0, double l1) const { return rok & (fabs(l0) < 230.0) & (fabs(l1) < 230.0); }
@@ -142,6 +160,7 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   }
   op.g.tl = sh->tl[warp]; op.g.tr = sh->tr[warp]; op.g.mt = &sh->mt;
   op.g.lgr = (active && geo.lgr) ? geo.lgr[row] : 0.0;
+  op.g.zinf = geo.zinf;
   __syncthreads();
   if (active) op.row_begin(row, slot);
   const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
@@ -371,11 +390,18 @@ struct OpLoglik {
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
   // generic element: any count, any argument range
-  __device__ __forceinline__ void one(int y, double lmu, bool m) {
+  __device__ __forceinline__ void one(int y, double lmu, bool m, long long pos) {
     double mu = g.expm(lmu);
     double L = g.logL(mu);
     double yd = (double)y;
     double v = nb_logpmf_t(y, yd, lmu, L, g.r, g.lgr, rlogr, g.tl, g.mt);
+    if (g.zi && m && g.zinf[pos]) {
+      // ZIM::dzinb(log = TRUE): log(omega 1[y = 0] + (1 - omega) dnbinom(y)), non-finite -> log(DBL_MIN) (:282,290)
+      double d = (1.0 - g.pi0) * exp(v);
+      if (y == 0) d += g.pi0;
+      v = log(d);
+      if (!(fabs(v) <= 1.79769313486231570e308)) v = LOG_DBL_MIN;
+    }
     acc += m ? v : 0.0;
     if (cert) {  // warp-uniform
       double h = nb_devhalf_t(y, yd, lmu, L, g.r, g.tr, g.mt);
@@ -404,12 +430,13 @@ struct OpLoglik {
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     double l0, l1;
     g.lmu_pair(tile, ti, l0, l1);
-    if (FULLCHUNK && g.fast_range(l0, l1) && (unsigned)(y0 | y1) < (unsigned)YT) {
+    if (FULLCHUNK && !g.zi && g.fast_range(l0, l1) && (unsigned)(y0 | y1) < (unsigned)YT) {
       one_fast(y0, l0);
       one_fast(y1, l1);
     } else {
-      if (m0) one(y0, l0, true);
-      if (m1) one(y1, l1, true);
+      const long long pos = (long long)c * CH + (ti & (CH - 1));
+      if (m0) one(y0, l0, true, pos);
+      if (m1) one(y1, l1, true, pos + 1);
     }
   }
   __device__ __forceinline__ void group_end(int) {}
@@ -520,6 +547,11 @@ struct OpPass1 {
     if (HUBER && hub) {  // warp-uniform branch
       wt0 *= huber_w_half(khsig, nb_devhalf_t(y0, yd0, l0, g.logL(mu0), g.r, g.tr, g.mt));
       wt1 *= huber_w_half(khsig, nb_devhalf_t(y1, yd1, l1, g.logL(mu1), g.r, g.tr, g.mt));
+    }
+    if (HUBER && g.zi) {  // launch-uniform: the general (HUBER) instantiation also carries the ZINB weights
+      const long long pos = (long long)c * CH + (ti & (CH - 1));
+      if (m0) wt0 *= g.wz(y0, mu0, pos);
+      if (m1) wt1 *= g.wz(y1, mu1, pos + 1);
     }
     if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
     sw += wt0 + wt1; gz += Z0 + Z1;
@@ -806,6 +838,10 @@ struct CtlPack {            // control-gene parameters, gathered (and, when shar
   const double* alpha_old;  // [n_ctl][K]
   const double* alpha_new;  // [n_ctl][K]
   const double* Mb;         // [n_ctl][m] old Mb
+  const double* pi0;        // [n_ctl] ZINB only
+  const double* psi_w;      // [n_ctl] ZINB only
+  const uint8_t* zinf;      // [Np] or nullptr
+  int zinb;
 };
 template <int K, bool HUBER>
 __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows, int n_ctl, long long Np,
@@ -881,6 +917,11 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
       double s = 1.0 / (1.0 / mu + psi);
       double z = lmu + cp.step[gi] * (((double)y + 0.01) / (mu + 0.01) - 1.0) - gm;  // (Z - gmean)[ctl], :381
       double wt = s;
+      if (cp.zinb && y == 0 && cp.zinf[pos]) {  // wt.zinb of a zero count in a zero-inflated cell (:262,382)
+        double rw = 1.0 / cp.psi_w[gi], p0 = cp.pi0[gi];
+        double q = exp(-rw * (log(mu + rw) - log(rw)));
+        wt *= 1.0 - p0 / (p0 + (1.0 - p0) * q);
+      }
       if (HUBER) wt *= huber_w(khsig, dyn[(long long)cell_i * nstr + gi]);
       int idx = 0;
 #pragma unroll
@@ -1105,6 +1146,11 @@ struct OpPass2 {
     if (HUBER && hub) {  // warp-uniform branch
       wt0 *= huber_w_half(khsig, nb_devhalf_t(y0, yd0, l0, g.logL(mu0), g.r, g.tr, g.mt));
       wt1 *= huber_w_half(khsig, nb_devhalf_t(y1, yd1, l1, g.logL(mu1), g.r, g.tr, g.mt));
+    }
+    if (HUBER && g.zi) {
+      const long long pos = (long long)c * CH + (ti & (CH - 1));
+      if (m0) wt0 *= g.wz(y0, mu0, pos);
+      if (m1) wt1 *= g.wz(y1, mu1, pos + 1);
     }
 #pragma unroll
     for (int l = 0; l < K; ++l) {

@@ -194,6 +194,11 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   RET(dev_upload(ctx, &ctx->d_group_chunk0, ctx->group_chunk0));
   RET(dev_upload(ctx, &ctx->d_group_n, ctx->group_n));
   RET(dev_upload(ctx, &ctx->d_ctl_local, ctl_local));
+  if (ctx->any_zeroinf) {
+    std::vector<uint8_t> zp(ctx->Np, 0);
+    for (long long c = 0; c < N; ++c) zp[ctx->cell2pos[c]] = ctx->zeroinf[c] ? 1 : 0;
+    RET(dev_upload(ctx, &ctx->d_zinf, zp));
+  }
   RET(dev_alloc(ctx, &ctx->flags, 8));
   RET(dev_alloc(ctx, &ctx->faillist, ctx->Gl));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -382,6 +387,9 @@ static int alloc_set(ruvnb_ctx* ctx, StateSet* s) {
   RET(dev_alloc(ctx, &s->psi, Gl));
   RET(dev_alloc(ctx, &s->pi0, Gl));
   RET(dev_alloc(ctx, &s->sigma, Gl));
+  RET(dev_alloc(ctx, &s->psi_w, Gl));
+  k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(s->psi_w, Gl, 1.0);
+  CKL();
   CK(cudaMemsetAsync(s->sigma, 0, Gl * 8, ctx->stream));
   s->sig_valid = false;
   CK(cudaMemsetAsync(s->gmean, 0, Gl * 8, ctx->stream));
@@ -449,7 +457,7 @@ static int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->sumsq, K));
   RET(dev_alloc(ctx, &ctx->med, K));
   RET(dev_alloc(ctx, &ctx->mad, K));
-  RET(dev_alloc(ctx, &ctx->ctlpack, (long long)ctx->n_ctl * (3 + 2 * K + m)));
+  RET(dev_alloc(ctx, &ctx->ctlpack, (long long)ctx->n_ctl * (5 + 2 * K + m)));
   RET(dev_alloc(ctx, &ctx->scal, 16));
   if (ctx->nranks > 1) RET(dev_alloc(ctx, &ctx->alpha_full, ctx->G * K));
   return RUVNB_OK;
@@ -465,6 +473,7 @@ static int state_lookup(ruvnb_ctx* ctx, const char* name, double** p, StateKind*
   else if (!strcmp(name, "Mb")) { *p = s.Mb; *kind = SK_GM; }
   else if (!strcmp(name, "psi")) { *p = s.psi; *kind = SK_VEC; }
   else if (!strcmp(name, "pi0")) { *p = s.pi0; *kind = SK_VEC; }
+  else if (!strcmp(name, "psi_w")) { *p = s.psi_w; *kind = SK_VEC; }
   else if (!strcmp(name, "step")) { *p = ctx->step; *kind = SK_VEC; }
   else if (!strcmp(name, "loglik")) { *p = ctx->loglik; *kind = SK_VEC; }
   else if (!strcmp(name, "sigma")) { *p = ctx->sigma_exact; *kind = SK_VEC; }
@@ -528,12 +537,14 @@ static RowGeom geom(ruvnb_ctx* ctx, int nrows, const int* rowlist) {
   g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid;
   g.nrows = nrows; g.rowlist = rowlist;
   g.mtabs = ctx->d_mtabs; g.tabL = ctx->tabL; g.tabR = ctx->tabR; g.lgr = ctx->lgr;
+  g.zinf = ctx->zinb_on ? ctx->d_zinf : nullptr;
   return g;
 }
 template <int K>
 static GeneState<K> gstate(ruvnb_ctx* ctx, const StateSet& s, bool with_step) {
   GeneState<K> st;
   st.gmean = s.gmean; st.Mb = s.Mb; st.alpha = s.alpha; st.psi = s.psi; st.step = with_step ? ctx->step : nullptr; st.W = s.W; st.m = ctx->m;
+  st.pi0 = s.pi0; st.psi_w = s.psi_w; st.zinb = ctx->zinb_on ? 1 : 0;
   return st;
 }
 template <int K>
@@ -553,7 +564,7 @@ static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "no counts uploaded");
   RET(ensure_state(ctx, o->k));
   if (!ctx->have_W) return ctx->fail(RUVNB_ESTATE, "W not set: the initial W (irlba in the reference, R/ruvIIInb.R:167) is injected with ruvnb_set_state(\"W\")");
-  if (o->zinb && ctx->any_zeroinf) return ctx->fail(RUVNB_ESTATE, "ZINB kernels are not part of this build yet (SURVEY.md section 8, rows H4/H5)");
+  ctx->zinb_on = o->zinb && ctx->any_zeroinf;   // ZINB only matters for cells flagged zeroinf (:237,254)
   CK(cudaSetDevice(ctx->device));
   return RUVNB_OK;
 }
@@ -642,6 +653,40 @@ static int make_rmw(ruvnb_ctx* ctx, const double* W) {
   return RUVNB_OK;
 }
 
+// H4: pi0 of parameter set `s` by R's one-dimensional Nelder-Mead (zinb.cuh); pi0_new may alias s.pi0.  *nbad = non-finite entries.
+static int zinb_update_pi0(ruvnb_ctx* ctx, StateSet& s, const double* pi0_old, double* pi0_new, int* nbad) {
+  const int Gl = ctx->Gl;
+  if (!ctx->zq) {
+    RET(dev_alloc(ctx, &ctx->zq, (long long)Gl * ctx->Np)); RET(dev_alloc(ctx, &ctx->z_spos, Gl)); RET(dev_alloc(ctx, &ctx->z_npos, Gl));
+    RET(dev_alloc(ctx, &ctx->z_xeval, Gl)); RET(dev_alloc(ctx, &ctx->z_feval, Gl)); RET(dev_alloc(ctx, &ctx->z_nm, Gl)); RET(dev_alloc(ctx, &ctx->z_active, 2));
+  }
+  RET(ensure_ytabs(ctx, s.psi));
+  DISPATCH_K(ctx->K, {
+    LAUNCH_ROWS(k_zinb_q<KT>, 1, Gl, geom(ctx, Gl, nullptr), gstate<KT>(ctx, s, false), ctx->zq, ctx->z_spos, ctx->z_npos);
+  });
+  k_nm_init<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, ctx->z_nm, ctx->z_xeval); CKL();
+  int rounds = 0;
+  for (;; ++rounds) {
+    if (rounds > 2 * NM_MAXIT + 8) return ctx->fail(RUVNB_ESTATE, "zinb: Nelder-Mead state machines did not stop");
+    k_nm_eval<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, ctx->Np, ctx->zq, ctx->z_spos, ctx->z_npos, ctx->z_nm, ctx->z_xeval, ctx->d_mtabs, ctx->z_feval); CKL();
+    CK(cudaMemsetAsync(ctx->z_active, 0, sizeof(int), ctx->stream));
+    k_nm_step<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, ctx->z_nm, ctx->z_feval, ctx->z_xeval, ctx->z_active); CKL();
+    if ((rounds & 3) == 3) {  // look at the number of running genes every 4 rounds
+      CK(cudaMemcpyAsync(ctx->h_flags + 7, ctx->z_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_flags[7] == 0) break;
+    }
+  }
+  ctx->last_nm_rounds = rounds + 1;
+  CK(cudaMemsetAsync(ctx->z_active + 1, 0, sizeof(int), ctx->stream));
+  k_nm_finish<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, ctx->z_nm, pi0_old, pi0_new, ctx->z_active + 1); CKL();
+  RET(allreduce(ctx, ctx->z_active + 1, 1, NCCL_INT32));
+  CK(cudaMemcpyAsync(ctx->h_flags + 7, ctx->z_active + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *nbad = ctx->h_flags[7];
+  return RUVNB_OK;
+}
+
 // one pass of the inner-loop body, R/ruvIIInb.R:303-484.  cur -> nw, then the two sets swap.
 static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
   const int Gl = ctx->Gl, K = ctx->K, m = ctx->m, KK = K * (K + 1) / 2;
@@ -654,7 +699,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   int nfail = 0, nactive = 0;
   RET(complete_sigma(ctx, o, c, kh, &nfail, &nactive));
   ctx->last_fail_rows = nfail; ctx->last_active_rows = nactive;
-  const bool hub = nactive > 0;
+  const bool hub = nactive > 0 || ctx->zinb_on;   // the general instantiation also carries the ZINB weights
   // alpha ------------------------------------------------------------------------------------------
   RET(make_rmw(ctx, c.W));
   DISPATCH_K(K, {
@@ -701,14 +746,18 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     CtlPack cp;
     double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
     double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
+    double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
     k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.gmean, ctx->d_ctl_local, nc, 1, p_gmean); CKL();
     k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.psi, ctx->d_ctl_local, nc, 1, p_psi); CKL();
     k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(ctx->step, ctx->d_ctl_local, nc, 1, p_step); CKL();
     k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(c.alpha, ctx->d_ctl_local, nc, K, p_aold); CKL();
     k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(n.alpha, ctx->d_ctl_local, nc, K, p_anew); CKL();
     k_gather_rows<<<nblk((long long)nc * m, 256), 256, 0, ctx->stream>>>(c.Mb, ctx->d_ctl_local, nc, m, p_mb); CKL();
-    RET(allreduce(ctx, pk, (size_t)nc * (3 + 2 * K + m), NCCL_F64));
+    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.pi0, ctx->d_ctl_local, nc, 1, p_pi0); CKL();
+    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.psi_w, ctx->d_ctl_local, nc, 1, p_psiw); CKL();
+    RET(allreduce(ctx, pk, (size_t)nc * (5 + 2 * K + m), NCCL_F64));
     cp.gmean = p_gmean; cp.psi = p_psi; cp.step = p_step; cp.alpha_old = p_aold; cp.alpha_new = p_anew; cp.Mb = p_mb;
+    cp.pi0 = p_pi0; cp.psi_w = p_psiw; cp.zinf = ctx->d_zinf; cp.zinb = ctx->zinb_on ? 1 : 0;
     // cells are sharded over the ranks in whole chunks; the slices are summed (disjoint) afterwards
     long long ch_per = (ctx->nchunks + ctx->nranks - 1) / ctx->nranks;
     long long pb = std::min<long long>(ctx->Np, ch_per * ctx->rank * CH), pe = std::min<long long>(ctx->Np, ch_per * (ctx->rank + 1) * CH);
@@ -722,7 +771,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     size_t smem = std::max<size_t>((size_t)cpc * (size_t)nstr * 8, (size_t)8 * cpc * NACC * 8);
     if (pe > pb) {
       KEV_BEGIN(2);
-      const bool fast = o->huber_fastpath && !o->robust;
+      const bool fast = o->huber_fastpath && !o->robust && !ctx->zinb_on;
       if (fast) {
         k_build_ytabs<<<nc, YT, 0, ctx->stream>>>(p_psi, nc, nullptr, ctx->ctl_tabR, nullptr); CKL();
         CK(cudaMemsetAsync(ctx->w_fail, 0, sizeof(int), ctx->stream));
@@ -761,9 +810,20 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
   RET(allreduce(ctx, ctx->flags + 2, 2, NCCL_INT32));
   k_mb_finalize<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, m, ctx->flags + 3, c.Mb, n.Mb); CKL();
-  // psi, pi0 unchanged inside the inner loop
+  // psi is fixed inside the inner loop
   CK(cudaMemcpyAsync(n.psi, c.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->zinb_on) {
+    // step 4a (:435-467): pi0 at the NEW parameters, then the E-step weights -- recomputed on the fly from (pi0, psi_w)
+    CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(n.psi_w, c.psi_w, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    int nbad_pi0 = 0;
+    RET(zinb_update_pi0(ctx, n, c.pi0, n.pi0, &nbad_pi0));
+    if (nbad_pi0) CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :454
+    CK(cudaMemcpyAsync(n.psi_w, n.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));             // :457-467
+  } else {
+    CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(n.psi_w, c.psi_w, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   // candidate log-likelihood (:469-484) + its Huber certificate for the next iteration
   RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new));
   CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -785,6 +845,7 @@ static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
   CK(cudaMemcpyAsync(dst.psi, src.psi, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.pi0, src.pi0, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.sigma, src.sigma, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.psi_w, src.psi_w, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active;
   return RUVNB_OK;
 }
@@ -822,6 +883,18 @@ int ruvnb_irls_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, 
   return RUVNB_OK;
 }
 
+int ruvnb_zinb_pi0(ruvnb_ctx* ctx, const ruvnb_opts* o, int* bad) {
+  RET(check_ready(ctx, o));
+  if (!ctx->zinb_on) return ctx->fail(RUVNB_ESTATE, "zinb_pi0: needs opts.zinb and zeroinf flags in ruvnb_set_design");
+  int nb = 0;
+  RET(zinb_update_pi0(ctx, ctx->cur, ctx->cur.pi0, ctx->cur.pi0, &nb));
+  CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cur.sig_valid = false;
+  if (bad) *bad = nb;
+  return RUVNB_OK;
+}
+
 int ruvnb_snapshot_best(ruvnb_ctx* ctx) {
   if (!ctx || ctx->K == 0) return RUVNB_EARG;
   CK(cudaSetDevice(ctx->device));
@@ -833,6 +906,8 @@ int ruvnb_restore_best(ruvnb_ctx* ctx) {
   if (!ctx || ctx->K == 0) return RUVNB_EARG;
   CK(cudaSetDevice(ctx->device));
   RET(copy_set(ctx, ctx->cur, ctx->best));
+  // "revert zinb weight" (:494-504): the weights are recomputed from the restored parameters with the CURRENT psi
+  if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return RUVNB_OK;
 }
@@ -894,6 +969,12 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
   // initial estimates (:173-221)
   RET(ruvnb_init_coef(ctx, o));
   RET(refresh_psi(ctx->cur));
+  if (ctx->zinb_on) {  // :237-264: initial pi0 (from pi0 = 0) and E-step
+    int nbad_pi0 = 0;
+    RET(zinb_update_pi0(ctx, ctx->cur, ctx->cur.pi0, ctx->cur.pi0, &nbad_pi0));
+    CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->cur.sig_valid = false;
+  }
   k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :270
   bool conv = false;
   int iter_outer = 0;
@@ -921,6 +1002,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
       if (degener) {
         k_halve<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();  // :490-491
         RET(copy_set(ctx, ctx->cur, ctx->best));  // :492
+        if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :494-504
         halving++;
         if (halving >= 3) { degener = false; }    // :506-509: loglik.tmp <- loglik, accept the restored state
       } else {
@@ -1030,14 +1112,15 @@ static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
   const int Gl = ctx->Gl;
   ctx->disp_nr_sweeps = 0;
   DISPATCH_K(ctx->K, {
-    LAUNCH_ROWS(k_disp_init<KT>, 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), ctx->dp_beta0, ctx->dp_rowsum, ctx->dp_emean, (double)ctx->N);
+    LAUNCH_ROWS(k_disp_init<KT>, 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), ctx->dp_beta0, ctx->dp_rowsum, ctx->dp_emean, (double)ctx->N,
+                s.gmean);
   });
   for (int d0 = 0; d0 < DISP_NG; d0 += DISP_ND) {
     k_bcast_cols<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta0, Gl, DISP_NG, d0, DISP_ND, ctx->dp_beta);
     CKL();
     DispArgs a;
     a.phi_grid = ctx->dp_phi_grid + d0; a.phi_row = nullptr; a.beta = ctx->dp_beta; a.ldb = DISP_NG; a.d0 = d0;
-    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = (double)ctx->N;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = (double)ctx->N; a.gm_real = s.gmean;
     RET(disp_nr(ctx, s, a, DISP_ND));
     DISPATCH_K(ctx->K, {
       LAUNCH_ROWS((k_disp_apl<KT, DISP_ND>), 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)d0 * YT,
@@ -1110,7 +1193,7 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
     CK(cudaMemcpyAsync(ctx->dp_beta1, b0.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
     DispArgs a;
     a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0;
-    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N;
+    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean;
     RET(disp_nr(ctx, s, a, 1));
   }
   std::vector<double> alc(G, 0.0);
@@ -1163,13 +1246,13 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
     CK(cudaMemcpyAsync(ctx->dp_beta1, ctx->dp_beta0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     DispArgs a;
     a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0;
-    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean;
     RET(disp_nr(ctx, s, a, 1));
     k_build_ytabs<<<Gl, YT, 0, ctx->stream>>>(ctx->dp_phi_row, Gl, nullptr, ctx->dp_tabR2, nullptr); CKL();
     DISPATCH_K(ctx->K, {
       RowGeom gg = geom(ctx, Gl, nullptr);
       gg.tabR = ctx->dp_tabR2;  // log(y + r) for r = 1/trended
-      LAUNCH_ROWS(k_disp_dev<KT>, 1, Gl, gg, disp_state<KT>(ctx, s), ctx->dp_beta1, ctx->dp_phi_row, ctx->dp_dev);
+      LAUNCH_ROWS(k_disp_dev<KT>, 1, Gl, gg, disp_state<KT>(ctx, s), ctx->dp_beta1, ctx->dp_phi_row, s.gmean, ctx->dp_dev);
     });
     std::vector<double> dev(G, 0.0);
     CK(cudaMemcpyAsync(dev.data() + g0, ctx->dp_dev, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));

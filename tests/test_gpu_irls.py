@@ -83,3 +83,15 @@ def test_winsorize_matches_oracle():
         assert np.array_equal(got_cap, cap)
         assert np.array_equal(nz, (Yw > 0).sum(axis=1))
         assert np.array_equal(ctx.get_counts(), Yw.astype(np.int32))
+
+
+def test_csr_upload_equals_dense():
+    """BASELINE config 3 feeds CSR rows (ruvnb_upload_counts_csr): same resident counts as the dense upload."""
+    import scipy.sparse as sp
+    from ruviiinb_b200 import _lib, synth
+    Y, M, ctl, truth = synth.make_counts(90, 777, 2, 4, 20, seed=71, zinb=True, gmean_mu=-1.0)
+    csr = sp.csr_matrix(Y)
+    with _lib.Context(0) as ctx:
+        ctx.set_design(Y.shape[0], Y.shape[1], truth["grp"], ctl)
+        ctx.upload_counts_csr(csr.indptr, csr.indices, csr.data)
+        assert np.array_equal(ctx.get_counts(), Y)
