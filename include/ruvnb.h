@@ -208,6 +208,18 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
                  int n_psi, ruvnb_trace_rec* trace, int trace_cap, double* logl_outer,
                  ruvnb_fit_stats* stats);
 
+/* ---- fastruvIII.nb streaming passes (R/fastruvIIInb.R) ------------------------------------------------------------ */
+/* F5 (:632-716) W for ALL cells from the control genes.  The current state supplies alpha and gmean; wt_ctl: n_ctl
+ * weights (best.wtctl); W_init: N x k (zeros with the Wsub rows filled in, :635-636); W_med/W_mad: colMedians/colMads of
+ * Wsub (:653-654); max_sweeps = 8, tol = 1e-5 in the reference (:709-712).  W_out (N x k, may be NULL) and "W". */
+int ruvnb_fast_W_all(ruvnb_ctx* ctx, int k, double lambda_a, const double* wt_ctl, const double* W_init, const double* W_med,
+                     const double* W_mad, int max_sweeps, double tol, double* W_out, int* n_sweeps, double* crit_out);
+/* F6 (:719-748) Mb.all, G x N column-major doubles streamed to the host in blocks of block_size cells.  annot_grp[c]:
+ * replicate group of cell c (0-based) or -1 for unannotated cells; "Mb" holds the subsample fit's G x m matrix. */
+int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp, int64_t block_size, double* Mb_all_out);
+/* F7 (:765-770) psi capped at exp(median(log psi) + 3 mad(log psi)), in place (host vector; no device needed). */
+int ruvnb_fast_cap_psi(double* psi, int64_t G);
+
 /* ---- get.res (R/get.res.R:12-129) -------------------------------------------------------------- */
 #define RUVNB_RES_PEARSON 1
 #define RUVNB_RES_LOGCOUNTS 2

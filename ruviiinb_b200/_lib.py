@@ -22,7 +22,7 @@ SYMBOLS = [
     "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_get_counts", "ruvnb_set_state",
     "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_zinb_pi0", "ruvnb_snapshot_best",
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp", "ruvnb_estimate_disp_ex",
-    "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res",
+    "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
 ]
 
 
@@ -102,6 +102,9 @@ def load():
     lib.ruvnb_disp_newton.argtypes = [vp, C.POINTER(Opts), vp, C.c_int]
     lib.ruvnb_fit_nb.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(FitStats)]
     lib.ruvnb_get_res.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
+    lib.ruvnb_fast_W_all.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, C.c_int, C.c_double, vp, ip, dp]
+    lib.ruvnb_fast_Mb_all.argtypes = [vp, C.c_double, vp, C.c_int64, vp]
+    lib.ruvnb_fast_cap_psi.argtypes = [vp, C.c_int64]
     for s in SYMBOLS:
         f = getattr(lib, s)
         if f.restype is C.c_int and s not in ("ruvnb_abi_version",):
@@ -295,6 +298,26 @@ class Context:
         self._ck(self.lib.ruvnb_get_res(self.h, int(kind), int(block_size), _ptr(mb), _ptr(out)))
         return out
 
+    def fast_W_all(self, W_init, wt_ctl, W_med, W_mad, lambda_a=0.01, max_sweeps=8, tol=1e-5):
+        """F5 (R/fastruvIIInb.R:632-716): returns (W, sweeps, crit)."""
+        W_init = np.asfortranarray(W_init, dtype=np.float64)
+        self.k = W_init.shape[1]
+        out = np.empty_like(W_init, order="F")
+        ns, cr = C.c_int(), C.c_double()
+        wt = np.ascontiguousarray(wt_ctl, dtype=np.float64)
+        med = np.ascontiguousarray(W_med, dtype=np.float64)
+        mad = np.ascontiguousarray(W_mad, dtype=np.float64)
+        self._ck(self.lib.ruvnb_fast_W_all(self.h, self.k, lambda_a, _ptr(wt), _ptr(W_init), _ptr(med), _ptr(mad), max_sweeps, tol,
+                                           _ptr(out), C.byref(ns), C.byref(cr)))
+        return out, ns.value, cr.value
+
+    def fast_Mb_all(self, annot_grp, lambda_b=16.0, block_size=5000):
+        """F6 (R/fastruvIIInb.R:719-748): G x N per-cell Mb."""
+        ag = np.ascontiguousarray(annot_grp, dtype=np.int32)
+        out = np.empty((self.Gl, self.N), dtype=np.float64, order="F")
+        self._ck(self.lib.ruvnb_fast_Mb_all(self.h, lambda_b, _ptr(ag), int(block_size), _ptr(out)))
+        return out
+
     KERNELS = ("devstats", "pass1", "w_update", "pass2", "loglik", "exact_mad")
 
     def kernel_times(self):
@@ -334,6 +357,15 @@ class Context:
     @property
     def kernel_launches(self):
         return int(self.lib.ruvnb_kernel_launches(self.h))
+
+
+def fast_cap_psi(psi):
+    """F7 (R/fastruvIIInb.R:765-770): psi capped at exp(median(log psi) + 3 mad(log psi))."""
+    p = np.ascontiguousarray(psi, dtype=np.float64).copy()
+    rc = load().ruvnb_fast_cap_psi(_ptr(p), p.size)
+    if rc != 0:
+        raise RuvnbError(f"ruvnb_fast_cap_psi failed with {rc}")
+    return p
 
 
 def selftest_math(which, x):

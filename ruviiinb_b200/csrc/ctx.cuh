@@ -16,6 +16,7 @@
 #include "disp.cuh"
 #include "res.cuh"
 #include "zinb.cuh"
+#include "fast.cuh"
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------

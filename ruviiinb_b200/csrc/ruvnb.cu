@@ -1369,4 +1369,135 @@ extern "C" int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const
   if (mbblk) CK(cudaFree(mbblk));
   return RUVNB_OK;
 }
+
+// ---- fastruvIII.nb streaming passes (R/fastruvIIInb.R:632-748) -----------------------------------------------------------
+// R median of values v[i] each repeated cnt[i] times (host; m is small)
+static double weighted_median_h(std::vector<std::pair<double, long long>> vc) {
+  std::sort(vc.begin(), vc.end());
+  long long n = 0;
+  for (auto& p : vc) n += p.second;
+  if (n == 0) return NAN;
+  auto kth = [&](long long k) { long long acc = 0; for (auto& p : vc) { acc += p.second; if (k < acc) return p.first; } return vc.back().first; };
+  return (n & 1) ? kth(n / 2) : 0.5 * (kth(n / 2 - 1) + kth(n / 2));
+}
+
+extern "C" {
+
+// F5: W for all cells.  The current state supplies alpha and gmean (all genes); wt_ctl: n_ctl gene weights
+// (best.wtctl = rowMeans(sig.inv[ctl,]) of the subsample fit); W_init: N x k (zeros, Wsub rows filled in, :635-636);
+// W_med / W_mad: colMedians / colMads of Wsub (:653-654).  W_out: N x k; the resident "W" is updated too.
+int ruvnb_fast_W_all(ruvnb_ctx* ctx, int k, double lambda_a, const double* wt_ctl, const double* W_init, const double* W_med,
+                     const double* W_mad, int max_sweeps, double tol, double* W_out, int* n_sweeps, double* crit_out) {
+  if (!ctx || !wt_ctl || !W_init || !W_med || !W_mad) return RUVNB_EARG;
+  if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "fast_W_all: no counts uploaded");
+  if (ctx->nranks > 1) return ctx->fail(RUVNB_ESTATE, "fast_W_all: single-GPU only in this build (cells are independent: shard N across contexts)");
+  RET(ensure_state(ctx, k));
+  CK(cudaSetDevice(ctx->device));
+  RET(ruvnb_set_state(ctx, "W", W_init, k));
+  const int K = ctx->K, nc = ctx->n_ctl, KK = K * (K + 1) / 2;
+  StateSet& s = ctx->cur;
+  double *d_gm = nullptr, *d_al = nullptr, *d_wt = nullptr, *d_A = nullptr, *d_med = nullptr, *d_mad = nullptr, *d_crit = nullptr;
+  const unsigned grid = nblk(ctx->Np, 64);
+  CK(cudaMalloc((void**)&d_gm, (size_t)nc * 8)); CK(cudaMalloc((void**)&d_al, (size_t)nc * K * 8)); CK(cudaMalloc((void**)&d_wt, (size_t)nc * 8));
+  CK(cudaMalloc((void**)&d_A, KK * 8)); CK(cudaMalloc((void**)&d_med, K * 8)); CK(cudaMalloc((void**)&d_mad, K * 8)); CK(cudaMalloc((void**)&d_crit, (size_t)grid * 8));
+  k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(s.gmean, ctx->d_ctl_local, nc, 1, d_gm); CKL();
+  k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(s.alpha, ctx->d_ctl_local, nc, K, d_al); CKL();
+  CK(cudaMemcpyAsync(d_wt, wt_ctl, (size_t)nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_med, W_med, K * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_mad, W_mad, K * 8, cudaMemcpyHostToDevice, ctx->stream));
+  DISPATCH_K(K, { k_fast_gram<KT><<<1, 32, 0, ctx->stream>>>(nc, d_al, d_wt, d_A); CKL(); });
+  std::vector<double> part(grid);
+  int sweeps = 0; double crit = NAN;
+  // the initial pass (:637-651) plus up to max_sweeps refinement sweeps (:664-713)
+  for (int it = 0; it <= max_sweeps; ++it) {
+    DISPATCH_K(K, {
+      k_fast_w_sweep<KT><<<grid, 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_valid, d_gm, d_al, d_wt, d_A, lambda_a, d_med, d_mad,
+                                                      ctx->d_mtabs, s.W, ctx->nw.W, d_crit);
+      CKL();
+    });
+    std::swap(s.W, ctx->nw.W);
+    sweeps++;
+    CK(cudaMemcpyAsync(part.data(), d_crit, (size_t)grid * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double t = 0.0;
+    for (double v : part) t += v;
+    crit = t / ((double)ctx->N * K);                       // mean over all N x k entries (:709)
+    if (it >= 1 && crit < tol) break;                      // the initial pass has no convergence test
+  }
+  s.sig_valid = false;
+  if (n_sweeps) *n_sweeps = sweeps;
+  if (crit_out) *crit_out = crit;
+  CK(cudaFree(d_gm)); CK(cudaFree(d_al)); CK(cudaFree(d_wt)); CK(cudaFree(d_A)); CK(cudaFree(d_med)); CK(cudaFree(d_mad)); CK(cudaFree(d_crit));
+  if (W_out) RET(ruvnb_get_state(ctx, "W", W_out));
+  return RUVNB_OK;
+}
+
+// F6: Mb.all (G x N, column-major, streamed to the host in blocks of block_size cells).  annot_grp[c] = replicate group
+// of cell c or -1; the current state supplies alpha, gmean, psi, W and the subsample fit's Mb (G x m).
+int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp, int64_t block_size, double* Mb_all_out) {
+  if (!ctx || !annot_grp || !Mb_all_out) return RUVNB_EARG;
+  if (!ctx->have_counts || ctx->K == 0 || !ctx->have_W) return ctx->fail(RUVNB_ESTATE, "fast_Mb_all: needs counts and a state (W, alpha, gmean, Mb, psi)");
+  CK(cudaSetDevice(ctx->device));
+  const int Gl = ctx->Gl, m = ctx->m; const long long N = ctx->N;
+  StateSet& s = ctx->cur;
+  // row median / mad over the annotated columns (:744-745): values Mb[g, j] with multiplicity = annotated cells of group j
+  std::vector<long long> cnt(m, 0);
+  for (long long c = 0; c < N; ++c) { int j = annot_grp[c]; if (j >= m) return ctx->fail(RUVNB_EARG, "fast_Mb_all: group %d outside 0..%d", j, m - 1); if (j >= 0) cnt[j]++; }
+  std::vector<double> Mbh((size_t)Gl * m), rmed(Gl), rmad(Gl);
+  CK(cudaMemcpyAsync(Mbh.data(), s.Mb, Mbh.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint8_t> ctl_local(Gl);
+  for (int g = 0; g < Gl; ++g) ctl_local[g] = ctx->ctl[ctx->g0 + g];
+  for (int g = 0; g < Gl; ++g) {
+    std::vector<std::pair<double, long long>> vc(m);
+    for (int j = 0; j < m; ++j) vc[j] = {ctl_local[g] ? 0.0 : Mbh[(size_t)g * m + j], cnt[j]};
+    double med = weighted_median_h(vc);
+    for (int j = 0; j < m; ++j) vc[j].first = fabs(vc[j].first - med);
+    rmed[g] = med; rmad[g] = 1.4826 * weighted_median_h(vc);
+  }
+  long long bs = std::min<long long>(block_size > 0 ? block_size : 5000, N);
+  double *d_rmed = nullptr, *d_rmad = nullptr, *slab[2] = {nullptr, nullptr}; int* d_annot = nullptr; uint8_t* d_ctl = nullptr;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t done[2], copied[2];
+  CK(cudaMalloc((void**)&d_rmed, (size_t)Gl * 8)); CK(cudaMalloc((void**)&d_rmad, (size_t)Gl * 8)); CK(cudaMalloc((void**)&d_annot, (size_t)N * 4));
+  CK(cudaMalloc((void**)&d_ctl, Gl));
+  for (int i = 0; i < 2; ++i) { CK(cudaMalloc((void**)&slab[i], (size_t)Gl * bs * 8)); CK(cudaEventCreate(&done[i])); CK(cudaEventCreate(&copied[i])); }
+  CK(cudaStreamCreate(&copy_stream));
+  CK(cudaMemcpyAsync(d_rmed, rmed.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_rmad, rmad.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_annot, annot_grp, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ctl, ctl_local.data(), Gl, cudaMemcpyHostToDevice, ctx->stream));
+  int blk = 0;
+  for (long long c0 = 0; c0 < N; c0 += bs, ++blk) {
+    const int B = (int)std::min<long long>(bs, N - c0), sl = blk & 1;
+    if (blk >= 2) CK(cudaStreamWaitEvent(ctx->stream, copied[sl], 0));
+    FastMbArgs a;
+    a.Gl = Gl; a.K = ctx->K; a.m = m; a.B = B; a.Np = ctx->Np; a.c0 = c0; a.Yp = ctx->dY; a.alpha = s.alpha; a.gmean = s.gmean; a.psi = s.psi;
+    a.W = s.W; a.Mb = s.Mb; a.cell2pos = ctx->d_cell2pos; a.annot = d_annot; a.ctl_local = d_ctl; a.rmed = d_rmed; a.rmad = d_rmad; a.lambda_b = lambda_b;
+    k_fast_mb<<<dim3(nblk(Gl, 32), nblk(B, 32)), 1024, 0, ctx->stream>>>(a, slab[sl]); CKL();
+    CK(cudaEventRecord(done[sl], ctx->stream));
+    CK(cudaStreamWaitEvent(copy_stream, done[sl], 0));
+    CK(cudaMemcpyAsync(Mb_all_out + (size_t)c0 * Gl, slab[sl], (size_t)Gl * B * 8, cudaMemcpyDeviceToHost, copy_stream));
+    CK(cudaEventRecord(copied[sl], copy_stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(copy_stream));
+  CK(cudaStreamDestroy(copy_stream));
+  for (int i = 0; i < 2; ++i) { CK(cudaFree(slab[i])); CK(cudaEventDestroy(done[i])); CK(cudaEventDestroy(copied[i])); }
+  CK(cudaFree(d_rmed)); CK(cudaFree(d_rmad)); CK(cudaFree(d_annot)); CK(cudaFree(d_ctl));
+  return RUVNB_OK;
+}
+
+// F7: psi capped at exp(median(log psi) + 3 mad(log psi)) (R/fastruvIIInb.R:765-770); host-side, in place
+int ruvnb_fast_cap_psi(double* psi, int64_t G) {
+  if (!psi || G <= 0) return RUVNB_EARG;
+  std::vector<double> l(G);
+  for (int64_t i = 0; i < G; ++i) l[i] = log(psi[i]);
+  auto median = [](std::vector<double> v) { size_t n = v.size(); std::sort(v.begin(), v.end()); return (n & 1) ? v[n / 2] : 0.5 * (v[n / 2 - 1] + v[n / 2]); };
+  double med = median(l);
+  for (auto& v : l) v = fabs(v - med);
+  double cap = exp(med + 3.0 * 1.4826 * median(l));
+  for (int64_t i = 0; i < G; ++i) if (psi[i] > cap) psi[i] = cap;
+  return RUVNB_OK;
+}
+
+}  // extern "C"
 #include "stubs.cuh"
