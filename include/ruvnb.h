@@ -194,9 +194,10 @@ int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out)
  * fitFDist moments); < 0 estimates it.  trended_out: local rows; prior_df_out: the prior d.f. used. */
 int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_in, double* common_out, double* trended_out,
                            double* prior_df_out);
-/* The north_star variant: per-gene Newton maximisation of the same Cox-Reid adjusted profile
- * likelihood in log(psi) (digamma/trigamma on the FP64 pipe).  NOT what the reference computes
- * (it interpolates the 21-point grid); reported separately. */
+/* The north_star variant: per-gene Newton on log(psi) of the NB log-likelihood at the CURRENT fitted means, with the
+ * digamma / trigamma differences psi0(y + r) - psi0(r), psi1(y + r) - psi1(r) tabulated per gene and iteration (one
+ * sweep per Newton iteration, FP64 pipe).  NOT what the reference computes (it interpolates the 21-point APL grid and
+ * shrinks towards a trend); reported separately.  Starts from the current "psi", which it leaves untouched. */
 int ruvnb_disp_newton(ruvnb_ctx* ctx, const ruvnb_opts* o, double* psi_out, int maxit);
 
 /* ---- the whole fit on device (R/ruvIIInb.R:266-609) ------------------------------------------ */

@@ -431,3 +431,107 @@ static double fit_f_dist_df2(const std::vector<double>& s2, double df1) {
   if (evar > 0.0) return 2.0 * trigamma_inverse_h(evar);
   return INFINITY;
 }
+
+// ---- the north_star variant: per-gene Newton on log psi with digamma / trigamma differences ---------------------------
+// NOT what the reference computes (it interpolates the 21-point APL grid and shrinks, see above).  Maximises over
+// theta = log psi_g the NB log-likelihood of the gene at the CURRENT fitted means mu_gc = exp(gmean + Mb + alpha W):
+//   dl/dr   = sum_c [ psi0(y + r) - psi0(r) + log r + 1 - log(mu + r) - (y + r)/(mu + r) ],
+//   d2l/dr2 = sum_c [ psi1(y + r) - psi1(r) + 1/r - 2/(mu + r) + (y + r)/(mu + r)^2 ],       r = exp(-theta),
+// with psi0(y + r) - psi0(r) = sum_{j<y} 1/(r + j) and psi1(y + r) - psi1(r) = -sum_{j<y} 1/(r + j)^2 tabulated per gene
+// and per iteration for y < YT by a warp scan (asymptotic series beyond the table).  One sweep per Newton iteration.
+__device__ __forceinline__ double digamma_d(double x) {
+  double r = 0.0;
+  while (x < 8.0) { r -= 1.0 / x; x += 1.0; }
+  double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x - f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132)))));
+}
+__device__ __forceinline__ double trigamma_d(double x) {
+  double r = 0.0;
+  while (x < 8.0) { r += 1.0 / (x * x); x += 1.0; }
+  double f = 1.0 / (x * x);
+  return r + 1.0 / x + f / 2 + f / x * (1.0 / 6 - f * (1.0 / 30 - f * (1.0 / 42 - f * (1.0 / 30 - f * (5.0 / 66)))));
+}
+template <int K>
+struct OpPsiNewton {
+  static constexpr bool PADS = false;
+  GeneState<K> st; GeneRegs<K> g;
+  double *theta; int* notconv; double tol;
+  double r, lr, ir, dg_r, tg_r, g1, g2; bool live;
+  double *t0, *t1;   // this warp's tables (shared memory)
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row);
+    const int lane = threadIdx.x & 31;
+    double th = theta[row];
+    live = (th == th);
+    r = exp(-th); lr = -th; ir = 1.0 / r;
+    dg_r = digamma_d(r); tg_r = trigamma_d(r);
+    g1 = 0.0; g2 = 0.0;
+    t0 = const_cast<double*>(g.tl); t1 = const_cast<double*>(g.tr);
+    // exclusive prefix sums of 1/(r + j) and -1/(r + j)^2, j = 0..YT-1
+    double c0 = 0.0, c1 = 0.0;
+    for (int base = 0; base < YT; base += 32) {
+      double inv = 1.0 / (r + (double)(base + lane));
+      double a = inv, b = -inv * inv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        double ta = __shfl_up_sync(FULL, a, o), tb = __shfl_up_sync(FULL, b, o);
+        if (lane >= o) { a += ta; b += tb; }
+      }
+      t0[base + lane] = c0 + a - inv; t1[base + lane] = c1 + b + inv * inv;
+      c0 += __shfl_sync(FULL, a, 31); c1 += __shfl_sync(FULL, b, 31);
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
+  __device__ __forceinline__ void one(int y, double lmu, bool m) {
+    if (!m) return;
+    double mu = g.expm(lmu);
+    double mr = mu + r, imr = 1.0 / mr, yd = (double)y;
+    double d0, d1;
+    if (y < YT) { d0 = t0[y]; d1 = t1[y]; } else { d0 = digamma_d(yd + r) - dg_r; d1 = trigamma_d(yd + r) - tg_r; }
+    double q = (yd + r) * imr;
+    g1 += d0 + lr + 1.0 - flog(mr, g.mt->rc, g.mt->lc) - q;
+    g2 += d1 + ir - 2.0 * imr + q * imr;
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    if (!live) return;
+    double l0, l1;
+    g.lmu_pair(tile, ti, l0, l1);
+    one(y0, l0, m0); one(y1, l1, m1);
+  }
+  __device__ __forceinline__ void group_end(int) {}
+  __device__ __forceinline__ void row_end(int row) {
+    if (!live) return;
+    double s1 = warp_sum(g1), s2 = warp_sum(g2);
+    if ((threadIdx.x & 31) == 0) {
+      double dth = -r * s1, d2th = r * r * s2 + r * s1;
+      double step = (d2th < 0.0) ? -dth / d2th : (dth > 0.0 ? 1.0 : -1.0);
+      if (step > 2.0) step = 2.0;
+      if (step < -2.0) step = -2.0;
+      if (step == step) {
+        theta[row] += step;
+        if (!(fabs(step) < tol)) atomicExch(notconv, 1);
+      } else {
+        theta[row] = step;  // NaN: give up on this gene
+      }
+    }
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_psi_newton(RowGeom geo, GeneState<K> st, double* theta, double tol, int* notconv) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  OpPsiNewton<K> op;
+  op.st = st; op.theta = theta; op.tol = tol; op.notconv = notconv;
+  stream_rows<K, 1>(geo, &sh, op, smem);
+}
+__global__ void k_log_vec(const double* x, long long n, double* y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = log(x[i]);
+}
+__global__ void k_exp_vec(const double* x, long long n, double* y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = exp(x[i]);
+}

@@ -1500,4 +1500,32 @@ int ruvnb_fast_cap_psi(double* psi, int64_t G) {
 }
 
 }  // extern "C"
-#include "stubs.cuh"
+
+// the north_star variant of the dispersion step: per-gene Newton on log psi at the current fitted means (disp.cuh)
+extern "C" int ruvnb_disp_newton(ruvnb_ctx* ctx, const ruvnb_opts* o, double* psi_out, int maxit) {
+  RET(check_ready(ctx, o));
+  if (!psi_out) return RUVNB_EARG;
+  RET(disp_ensure(ctx));
+  const int Gl = ctx->Gl;
+  StateSet& s = ctx->cur;
+  double* theta = ctx->dp_beta1;
+  k_log_vec<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(s.psi, Gl, theta); CKL();   // start from the current psi
+  if (maxit <= 0) maxit = 30;
+  int it = 0;
+  for (; it < maxit; ++it) {
+    CK(cudaMemsetAsync(ctx->dp_flag, 0, sizeof(int), ctx->stream));
+    DISPATCH_K(ctx->K, {
+      RowGeom gg = geom(ctx, Gl, nullptr);
+      gg.tabL = nullptr;   // the op fills its own per-iteration tables in the warp's shared-memory slots
+      LAUNCH_ROWS(k_psi_newton<KT>, 1, Gl, gg, gstate<KT>(ctx, s, false), theta, 1e-8, ctx->dp_flag);
+    });
+    CK(cudaMemcpyAsync(ctx->h_flags + 7, ctx->dp_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[7] == 0) { ++it; break; }
+  }
+  ctx->disp_nr_sweeps = it;
+  k_exp_vec<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(theta, Gl, ctx->dp_phi_row); CKL();
+  CK(cudaMemcpyAsync(psi_out, ctx->dp_phi_row, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "ruvnb.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ruvnb_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ruvnb_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported(lib):
