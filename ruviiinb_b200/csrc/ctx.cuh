@@ -83,6 +83,8 @@ struct ruvnb_ctx {
   int* d_ctl_local = nullptr;      // local row of each control gene, or -1
   const int32_t** d_ctl_rows = nullptr;
   // counts
+  int* d_roworder = nullptr; // [Gl] launch order of the gene rows: heavy rows (many counts >= YT) first
+  bool roworder_ready = false;
   int32_t* dY = nullptr;     // [Gl][Np]
   int32_t* dYctl = nullptr;  // [n_ctl][Np] (sharded runs only)
   // state
@@ -121,6 +123,7 @@ struct ruvnb_ctx {
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare
   int *faillist = nullptr;
+  int *list_inf = nullptr, *list_fin = nullptr, *part_counts = nullptr;  // rows by Huber status (k_partition_sigma)
   int *h_flags = nullptr;    // pinned mirror
   double* h_scal = nullptr;  // pinned [16]
   // multi-GPU

@@ -18,8 +18,9 @@ struct RowGeom {
   int nchunks;          // multiple of CHPAD; trailing chunks may be empty (chunk_valid == 0)
   const int* chunk_grp;
   const int* chunk_valid;
-  int nrows;            // rows this launch walks
-  const int* rowlist;   // nullptr -> slot == row; else row = rowlist[slot] (exact-MAD batches)
+  int nrows;            // rows this launch walks (upper bound when nrows_dev is set)
+  const int* rowlist;   // nullptr -> slot == row; else row = rowlist[slot] (exact-MAD batches, partitions)
+  const int* nrows_dev; // optional device-side row count: slots >= *nrows_dev idle (lists built on the device)
   const MathTabs* mtabs;  // exp / log / log(y) tables (global copy, staged into shared memory per CTA)
   const double* tabL;   // [Gl][YT] lgamma(y+r) - lgamma(r) - lgamma(y+1)
   const double* tabR;   // [Gl][YT] log(y + r)
@@ -143,7 +144,9 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = blockIdx.x * NWARP + warp;
-  const bool active = slot < geo.nrows;
+  const int nrows = geo.nrows_dev ? min(geo.nrows, *geo.nrows_dev) : geo.nrows;
+  if (blockIdx.x * NWARP >= nrows) return;   // whole CTA beyond the (device-side) list: nothing to do
+  const bool active = slot < nrows;
   const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
   constexpr int TILE = NSETS * K * CELLS;
   // shared tables: math tables for the CTA, count tables for this warp's row
@@ -326,6 +329,36 @@ __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long 
   }
 }
 
+// rows split by their Huber status: sigma = +Inf (every weight provably 1) -> list_inf, anything else (finite or NaN
+// sigma: live weights) -> list_fin; both in launch order `order` (or natural order); one CTA, ordered scan
+__global__ void __launch_bounds__(1024) k_partition_sigma(int Gl, const double* sigma, const int* order, int* list_inf, int* list_fin,
+                                                         int* counts /* [2] */) {
+  __shared__ int wsum[32];
+  __shared__ int base_inf, base_fin;
+  if (threadIdx.x == 0) { base_inf = 0; base_fin = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int g0 = 0; g0 < Gl; g0 += 1024) {
+    const int i = g0 + threadIdx.x;
+    const int g = i < Gl ? (order ? order[i] : i) : 0;
+    const bool inf = i < Gl && sigma[g] > 1.79769313486231570e308;
+    const bool fin = i < Gl && !inf;
+    unsigned bi = __ballot_sync(FULL, inf);
+    if (lane == 0) wsum[w] = __popc(bi);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int q = 0; q < 32; ++q) { if (q < w) off += wsum[q]; tot += wsum[q]; }
+    const int nvalid = min(1024, Gl - g0);
+    const int pre_inf = off + __popc(bi & ((1u << lane) - 1));
+    if (inf) list_inf[base_inf + pre_inf] = g;
+    if (fin) list_fin[base_fin + (int)threadIdx.x - pre_inf] = g;   // rank among the non-inf = position - #inf before
+    __syncthreads();
+    if (threadIdx.x == 0) { base_inf += tot; base_fin += nvalid - tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { counts[0] = base_inf; counts[1] = base_fin; }
+}
+
 // rows whose certificate failed (sigma == 0 marker) -> compact list, ascending (one CTA, ordered scan)
 __global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigma, int* list, int* count, int* n_active) {
   __shared__ int wsum[32];
@@ -378,14 +411,22 @@ struct OpLoglik {
   double* out;
   // certificate
   double* hint; double* sigma_out; double kh; int fastpath; long long n; int* diag;
-  double u_lo, u_hi, u_wl, u_wh, hmax; int c1, c2, c3, bad; bool cert;
+  double u_lo, u_hi, u_wl, u_wh; int k_lo, k_hi, k_wl, k_wh, hmaxk; int c1, c2, c3; bool cert;
+  // The counting runs on 32-bit integer keys: the high word of u mapped so that integer order = floating order
+  // (monotone non-decreasing under the truncation of the low word).  u < u_lo implies key(u) <= key(u_lo), etc., so the
+  // integer counts can only OVER-count c1, c2, c3 -- the certificate stays rigorous -- and the FP64 pipe is spared five
+  // compares per element.
+  __device__ __forceinline__ static int okey(double u) { int h = __double2hiint(u); return h ^ ((h >> 31) & 0x7fffffff); }
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); acc = 0.0; rlogr = g.r * log(g.r);
-    cert = false; c1 = c2 = c3 = 0; bad = 0; hmax = 0.0; u_lo = u_hi = u_wl = u_wh = 0.0;
+    cert = false; c1 = c2 = c3 = 0; hmaxk = 0; u_lo = u_hi = u_wl = u_wh = 0.0; k_lo = k_hi = k_wl = k_wh = 0;
     if (fastpath && sigma_out) {
       double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1], tg = hint[(long long)row * 3 + 2];
       cert = tg > 0.0 && lo <= hi;
-      if (cert) { u_lo = u_of_d(lo); u_hi = u_of_d(hi); u_wl = u_of_d(lo - tg); u_wh = u_of_d(hi + tg); }
+      if (cert) {
+        u_lo = u_of_d(lo); u_hi = u_of_d(hi); u_wl = u_of_d(lo - tg); u_wh = u_of_d(hi + tg);
+        k_lo = okey(u_lo); k_hi = okey(u_hi); k_wl = okey(u_wl); k_wh = okey(u_wh);
+      }
     }
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
@@ -409,11 +450,12 @@ struct OpLoglik {
     }
   }
   __device__ __forceinline__ void count(double h, double yd, double mu, bool m) {
-    double hc = fmax(h, 0.0);
-    double u = (yd > mu) ? hc : -hc;
-    c1 += m & (u < u_lo); c2 += m & (u > u_hi); c3 += m & (u > u_wl) & (u < u_wh);
-    hmax = fmax(hmax, m ? hc : 0.0);
-    bad |= m & !(h == h);
+    const int hi = __double2hiint(h);
+    const int kraw = m ? (hi & 0x7fffffff) : 0;   // |h| key; NaN / Inf land at >= 0x7ff00000 and are caught at the row end
+    hmaxk = max(hmaxk, kraw);
+    const int kpos = max(hi, 0);                  // h < 0 only by rounding when y ~ mu: deviance 0
+    const int ks = (yd > mu) ? kpos : ~kpos;      // ordered key of u = sign(y - mu) h
+    c1 += m & (ks <= k_lo); c2 += m & (ks >= k_hi); c3 += m & (ks >= k_wl) & (ks <= k_wh);
   }
   // in-table counts and in-range arguments: branch-free (tl[0] = 0 and yd = 0 make the y = 0 case fall out)
   __device__ __forceinline__ void one_fast(int y, double lmu) {
@@ -448,8 +490,9 @@ struct OpLoglik {
     bool ok = false;
     if (cert) {
       int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
-      int nb = __any_sync(FULL, bad);
-      double hm = warp_max(hmax);
+      const int hk = __reduce_max_sync(FULL, hmaxk);
+      const int nb = hk >= 0x7ff00000;                       // some deviance was NaN or infinite
+      const double hm = __hiloint2double(hk + 1, 0);         // upper bound of max |h| (one unit of the high word)
       if (lane == 0 && !nb) {
         const double C = MAD_CONST / 0.6745;
         double mx = sqrt(2.0 * hm);
@@ -457,9 +500,9 @@ struct OpLoglik {
         // margins actually realised by the u-space thresholds
         double room = fmin(d_of_u(u_lo) - d_of_u(u_wl), d_of_u(u_wh) - d_of_u(u_hi));
         long long kl = (n - 1) / 2, ku = n / 2;
-        ok = (mx > 0.0) && (t <= room) && ((long long)a1 <= kl) && ((long long)a2 <= n - 1 - ku) && ((long long)a3 <= kl);
+        ok = (hk > 0) && (mx > 0.0) && (t <= room) && ((long long)a1 <= kl) && ((long long)a2 <= n - 1 - ku) && ((long long)a3 <= kl);
         if (!ok && diag) {  // why the certificate failed (tuning aid; ruvnb_cert_diag)
-          int why = !(mx > 0.0) ? 2 : !(t <= room) ? 3 : ((long long)a1 > kl) ? 4 : ((long long)a2 > n - 1 - ku) ? 5 : 6;
+          int why = !(hk > 0 && mx > 0.0) ? 2 : !(t <= room) ? 3 : ((long long)a1 > kl) ? 4 : ((long long)a2 > n - 1 - ku) ? 5 : 6;
           atomicAdd(diag + why, 1);
         }
         if (ok) {
@@ -480,7 +523,6 @@ struct OpLoglik {
     if (lane == 0) {
       sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
       if (diag && !cert) atomicAdd(diag + (fastpath ? 0 : 7), 1);   // 0: no usable hint (first visit or live Huber weights)
-      if (diag && cert && __any_sync(1u, bad)) atomicAdd(diag + 1, 1);
     }
   }
 };
@@ -1423,4 +1465,16 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, double a, double
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += x[i];
   if (s == 12345.678) out[0] = s;  // keeps the chains alive
+}
+
+// counts beyond the per-gene tables, per row: rows that hold many of them cost ~2.5x per element in the log-likelihood
+// sweep; the host launches those rows FIRST (RowGeom.rowlist) so that they do not form the tail of a sweep
+__global__ void __launch_bounds__(256) k_count_big(const int32_t* Yp, int rows, long long Np, int* nbig) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int4* y4 = reinterpret_cast<const int4*>(Yp + (long long)row * Np);
+  int c = 0;
+  for (long long i = lane; i < Np / 4; i += 32) { int4 v = y4[i]; c += (v.x >= YT) + (v.y >= YT) + (v.z >= YT) + (v.w >= YT); }
+  c = __reduce_add_sync(FULL, c);
+  if (lane == 0) nbig[row] = c;
 }

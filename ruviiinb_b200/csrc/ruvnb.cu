@@ -201,6 +201,7 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   }
   RET(dev_alloc(ctx, &ctx->flags, 8));
   RET(dev_alloc(ctx, &ctx->faillist, ctx->Gl));
+  RET(dev_alloc(ctx, &ctx->list_inf, ctx->Gl)); RET(dev_alloc(ctx, &ctx->list_fin, ctx->Gl)); RET(dev_alloc(ctx, &ctx->part_counts, 2));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->have_design = true;
   return RUVNB_OK;
@@ -279,7 +280,7 @@ int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, cons
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true;
+  ctx->have_counts = true; ctx->roworder_ready = false;
   return RUVNB_OK;
 }
 
@@ -325,7 +326,7 @@ int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true;
+  ctx->have_counts = true; ctx->roworder_ready = false;
   return RUVNB_OK;
 }
 
@@ -348,7 +349,7 @@ int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out) {
   if (nonzero_out) CK(cudaMemcpyAsync(nonzero_out, d_nz, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(d_cap)); CK(cudaFree(d_nz));
-  ctx->cur.sig_valid = false;
+  ctx->cur.sig_valid = false; ctx->roworder_ready = false;
   return RUVNB_OK;
 }
 
@@ -535,7 +536,8 @@ int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host) {
 static RowGeom geom(ruvnb_ctx* ctx, int nrows, const int* rowlist) {
   RowGeom g;
   g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid;
-  g.nrows = nrows; g.rowlist = rowlist;
+  g.nrows = nrows; g.rowlist = rowlist; g.nrows_dev = nullptr;
+  if (!rowlist && nrows == ctx->Gl && ctx->roworder_ready) g.rowlist = ctx->d_roworder;   // full sweeps: heavy rows first
   g.mtabs = ctx->d_mtabs; g.tabL = ctx->tabL; g.tabR = ctx->tabR; g.lgr = ctx->lgr;
   g.zinf = ctx->zinb_on ? ctx->d_zinf : nullptr;
   return g;
@@ -569,8 +571,29 @@ static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   return RUVNB_OK;
 }
 
+// launch order of the rows (load balance of the sweeps): rows with many counts beyond the tables go first
+static int ensure_roworder(ruvnb_ctx* ctx) {
+  if (ctx->roworder_ready) return RUVNB_OK;
+  const int Gl = ctx->Gl;
+  int* d_nbig = nullptr;
+  CK(cudaMalloc((void**)&d_nbig, (size_t)Gl * 4));
+  k_count_big<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(ctx->dY, Gl, ctx->Np, d_nbig); CKL();
+  std::vector<int> nbig(Gl), order(Gl);
+  CK(cudaMemcpyAsync(nbig.data(), d_nbig, (size_t)Gl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(d_nbig));
+  for (int i = 0; i < Gl; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nbig[a] > nbig[b]; });
+  if (!ctx->d_roworder) RET(dev_alloc(ctx, &ctx->d_roworder, Gl));
+  CK(cudaMemcpyAsync(ctx->d_roworder, order.data(), (size_t)Gl * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->roworder_ready = true;
+  return RUVNB_OK;
+}
+
 // per-gene count tables for the dispersions in `psi` (rebuilt only when psi changed)
 static int ensure_ytabs(ruvnb_ctx* ctx, const double* psi) {
+  RET(ensure_roworder(ctx));
   if (ctx->ytab_ver == ctx->psi_ver && ctx->ytab_psi != nullptr) return RUVNB_OK;
   k_build_ytabs<<<ctx->Gl, YT, 0, ctx->stream>>>(psi, ctx->Gl, ctx->tabL, ctx->tabR, ctx->lgr);
   CKL();
@@ -700,18 +723,24 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   RET(complete_sigma(ctx, o, c, kh, &nfail, &nactive));
   ctx->last_fail_rows = nfail; ctx->last_active_rows = nactive;
   const bool hub = nactive > 0 || ctx->zinb_on;   // the general instantiation also carries the ZINB weights
+  k_partition_sigma<<<1, 1024, 0, ctx->stream>>>(Gl, c.sigma, ctx->roworder_ready ? ctx->d_roworder : nullptr, ctx->list_inf, ctx->list_fin, ctx->part_counts);
+  CKL();
   // alpha ------------------------------------------------------------------------------------------
   RET(make_rmw(ctx, c.W));
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(1);
-    static const int p1_minb = getenv("RUVNB_P1_MINB") ? atoi(getenv("RUVNB_P1_MINB")) : 2;  // tuning knob
-    if (p1_minb == 1) {
-      if (hub) LAUNCH_ROWS((k_pass1<KT, true, 1>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
-      else LAUNCH_ROWS((k_pass1<KT, false, 1>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+    // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
+    // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
+    if (ctx->zinb_on) {
+      LAUNCH_ROWS((k_pass1<KT, true, 2>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
     } else {
-      if (hub) LAUNCH_ROWS((k_pass1<KT, true, 2>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
-      else LAUNCH_ROWS((k_pass1<KT, false, 2>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
+      LAUNCH_ROWS((k_pass1<KT, false, 2>), 2, Gl, gi, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      if (hub) {
+        RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
+        LAUNCH_ROWS((k_pass1<KT, true, 2>), 2, Gl, gf, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      }
     }
     KEV_END(1);
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
@@ -803,8 +832,16 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(3);
-    if (hub) LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
-    else LAUNCH_ROWS((k_pass2<KT, false>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+    if (ctx->zinb_on) {
+      LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+    } else {
+      RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
+      LAUNCH_ROWS((k_pass2<KT, false>), 2, Gl, gi, st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+      if (hub) {
+        RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
+        LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, gf, st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+      }
+    }
     KEV_END(3);
   });
   k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
