@@ -161,12 +161,18 @@ __device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* 
     const int nb = 1 << bits;
     for (int i = tid; i < nb; i += RS_NT) sc->hist[i] = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < len; i0 += RS_NT) {
-      unsigned long long kx = key(i0 + tid);
-      bool ok = (kx & pmask) == prefix;
-      int b = ok ? (int)((kx >> shift) & (unsigned long long)(nb - 1)) : nb + lane;
-      unsigned peers = __match_any_sync(FULL, b);
-      if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
+    // four independent loads in flight per thread (the pass is latency-bound: load -> match -> atomic)
+    for (int i0 = 0; i0 < len; i0 += 4 * RS_NT) {
+      unsigned long long kx[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) kx[q] = (i0 + q * RS_NT < len) ? key(i0 + q * RS_NT + tid) : ~pmask;  // ~pmask never matches a non-empty prefix mask
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        bool ok = (i0 + q * RS_NT < len) && (kx[q] & pmask) == prefix;
+        int b = ok ? (int)((kx[q] >> shift) & (unsigned long long)(nb - 1)) : nb + lane;
+        unsigned peers = __match_any_sync(FULL, b);
+        if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
+      }
     }
     __syncthreads();
     // locate the bucket holding `rank`: thread t owns bins [t*per, (t+1)*per)
