@@ -40,6 +40,7 @@ struct DispArgs {
 template <int K>
 struct OpDispInit {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g;
   double s_ye, s_y, s_e, s_w; int nz;
   double *beta0, *rowsum, *emean; double n; const double* gm_real; double gmr;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_init(RowGeom geo, GeneS
 template <int K, int ND>
 struct OpDispNR {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g; DispArgs a;
   double eb[ND], phi[ND], dl[ND], info[ND];
   double yadd, escale, egm; bool live;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr(RowGeom geo, GeneSta
 template <int K, int ND>
 struct OpDispAPL {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g; DispArgs a;
   const double (*tg)[YT];   // shared: [ND][YT]
   const double* lgr_grid;   // [ND] lgamma(r_d)
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl(RowGeom geo, GeneSt
 template <int K>
 struct OpDispDev {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g;
   const double *beta, *phi_row, *gm_real; double* dev;
   double b, eb, r, acc, egm;
@@ -454,6 +458,7 @@ __device__ __forceinline__ double trigamma_d(double x) {
 template <int K>
 struct OpPsiNewton {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g;
   double *theta; int* notconv; double tol;
   double r, lr, ir, dg_r, tg_r, g1, g2; bool live;

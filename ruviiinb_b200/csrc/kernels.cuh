@@ -51,18 +51,19 @@ struct RowShared {
   MathTabs mt;              // 4 KB
   double tl[NWARP][YT];     // this warp's row: lgamma table
   double tr[NWARP][YT];     // this warp's row: log(y + r)
+  double al[NWARP][8];      // this warp's row: alpha_g (kept out of the register file)
   const double* wsets[2];
 };
 
 // ------------------------------------------------------------------------------------------------
 // row-streaming skeleton
 // ------------------------------------------------------------------------------------------------
-template <int K, int NSETS>
+template <int K, int NSETS, int NW = NWARP>
 __device__ __forceinline__ void stage_tile(double* dst, const double* const* wsets, long long Np, int tile, int tid) {
   constexpr int CELLS = TileCfg<K>::CELLS;
   constexpr int UNITS_PER_ROW = CELLS / 2;  // 16-byte units
   constexpr int UNITS = NSETS * K * UNITS_PER_ROW;
-  for (int u = tid; u < UNITS; u += ROW_THREADS) {
+  for (int u = tid; u < UNITS; u += NW * 32) {
     int s = u / (K * UNITS_PER_ROW);
     int rem = u - s * (K * UNITS_PER_ROW);
     int l = rem / UNITS_PER_ROW;
@@ -87,7 +88,7 @@ struct GeneRegs {
   bool zi;                    // zero-inflation on for this launch
   double pi0, rw, lrw;        // ZINB: pi0_g, size 1/psi_w and its log
   const uint8_t* zinf;
-  double a[K];
+  double* as;                 // alpha_g of the row in shared memory (RowShared::al)
   const double* mb;
   double mbj;
   const double *tl, *tr;      // this warp's count tables (shared memory)
@@ -101,15 +102,18 @@ struct GeneRegs {
     pi0 = 0.0; rw = r; lrw = 0.0;
     if (zi) { pi0 = st.pi0[row]; rw = 1.0 / st.psi_w[row]; lrw = log(rw); }
     step = st.step ? st.step[row] : 1.0;
-#pragma unroll
-    for (int l = 0; l < K; ++l) a[l] = st.alpha[(long long)row * K + l];
+    {
+      const int lane = threadIdx.x & 31;
+      if (lane < K) as[lane] = st.alpha[(long long)row * K + lane];
+      __syncwarp();
+    }
     mb = st.Mb + (long long)row * st.m;
     mbj = 0.0;
   }
   __device__ __forceinline__ double lmu(const double* w, int ci) const {
     double s = gmean + mbj;
 #pragma unroll
-    for (int l = 0; l < K; ++l) s = fma(a[l], w[l * CELLS + ci], s);
+    for (int l = 0; l < K; ++l) s = fma(as[l], w[l * CELLS + ci], s);
     return s;
   }
   // two adjacent cells (ti even) with one 16-byte shared-memory load per factor
@@ -118,8 +122,9 @@ struct GeneRegs {
 #pragma unroll
     for (int l = 0; l < K; ++l) {
       double2 v = *reinterpret_cast<const double2*>(w + l * CELLS + ti);
-      s0 = fma(a[l], v.x, s0);
-      s1 = fma(a[l], v.y, s1);
+      const double al = as[l];
+      s0 = fma(al, v.x, s0);
+      s1 = fma(al, v.y, s1);
     }
     l0 = s0; l1 = s1;
   }
@@ -139,13 +144,13 @@ struct GeneRegs {
 // Op interface: row_begin(row, slot), group_begin(j), pair<FULLCHUNK>(y0, y1, chunk, ti, tile, m0, m1) -- two
 // adjacent cells at tile index ti (even), masks m0/m1 false for padding cells (always true when FULLCHUNK) --
 // group_end(j), row_end(row).  Op::PADS: pair() must also see chunks that hold no real cell.
-template <int K, int NSETS, class Op>
+template <int K, int NSETS, class Op, int NW = NWARP>
 __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, Op& op, double* smem) {
   constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = blockIdx.x * NWARP + warp;
+  const int slot = blockIdx.x * NW + warp;
   const int nrows = geo.nrows_dev ? min(geo.nrows, *geo.nrows_dev) : geo.nrows;
-  if (blockIdx.x * NWARP >= nrows) return;   // whole CTA beyond the (device-side) list: nothing to do
+  if (blockIdx.x * NW >= nrows) return;   // whole CTA beyond the (device-side) list: nothing to do
   const bool active = slot < nrows;
   const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
   constexpr int TILE = NSETS * K * CELLS;
@@ -153,7 +158,7 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   {
     const double* src = reinterpret_cast<const double*>(geo.mtabs);
     double* dst = reinterpret_cast<double*>(&sh->mt);
-    for (int i = tid; i < (int)(sizeof(MathTabs) / 8); i += ROW_THREADS) dst[i] = src[i];
+    for (int i = tid; i < (int)(sizeof(MathTabs) / 8); i += NW * 32) dst[i] = src[i];
     if (active && geo.tabL) {
       for (int i = lane; i < YT; i += 32) {
         sh->tl[warp][i] = geo.tabL[(long long)row * YT + i];
@@ -161,7 +166,7 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
       }
     }
   }
-  op.g.tl = sh->tl[warp]; op.g.tr = sh->tr[warp]; op.g.mt = &sh->mt;
+  op.g.tl = sh->tl[warp]; op.g.tr = sh->tr[warp]; op.g.mt = &sh->mt; op.g.as = sh->al[warp];
   op.g.lgr = (active && geo.lgr) ? geo.lgr[row] : 0.0;
   op.g.zinf = geo.zinf;
   __syncthreads();
@@ -172,10 +177,10 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   // the counts of the next chunk are fetched one chunk ahead (HBM latency hides behind ~4 elements of math)
   int2 ya = make_int2(0, 0), yb = ya;
   if (active) { ya = yrow2[lane]; yb = yrow2[32 + lane]; }
-  stage_tile<K, NSETS>(smem, sh->wsets, geo.Np, 0, tid);
+  stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, 0, tid);
   for (int t = 0; t < ntiles; ++t) {
     if (t + 1 < ntiles) {
-      stage_tile<K, NSETS>(smem + ((t + 1) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid);
+      stage_tile<K, NSETS, NW>(smem + ((t + 1) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid);
       __pipeline_wait_prior(1);
     } else {
       __pipeline_wait_prior(0);
@@ -198,8 +203,12 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
         }
         const int ti = sc * CH + 2 * lane;
         if (nv == CH) {
-          op.template pair<true>(y01.x, y01.y, c, ti, tile, true, true);
-          op.template pair<true>(y23.x, y23.y, c, ti + 64, tile, true, true);
+          if constexpr (Op::QUAD) {
+            op.quad(y01.x, y01.y, y23.x, y23.y, c, ti, tile);   // the lane's four cells in one branch-free block
+          } else {
+            op.template pair<true>(y01.x, y01.y, c, ti, tile, true, true);
+            op.template pair<true>(y23.x, y23.y, c, ti + 64, tile, true, true);
+          }
         } else {
           const int ci = 2 * lane;
           op.template pair<false>(y01.x, y01.y, c, ti, tile, ci < nv, ci + 1 < nv);
@@ -244,6 +253,7 @@ __global__ void __launch_bounds__(YT) k_build_ytabs(const double* psi, int rows,
 template <int K>
 struct OpSigndev {
   static constexpr bool PADS = true;
+  static constexpr bool QUAD = false;
   GeneState<K> st;
   GeneRegs<K> g;
   double* Drow;
@@ -405,6 +415,7 @@ __device__ __forceinline__ double d_of_u(double u) { return copysign(sqrt(2.0 * 
 template <int K>
 struct OpLoglik {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = true;
   GeneState<K> st;
   GeneRegs<K> g;
   double acc, rlogr;
@@ -466,6 +477,17 @@ struct OpLoglik {
     if (cert) {  // warp-uniform
       double h = fma(yd, g.mt->ly[y] - lmu, -(yd + g.r) * (g.tr[y] - L));
       count(h, yd, mu, true);
+    }
+  }
+  __device__ __forceinline__ void quad(int y0, int y1, int y2, int y3, int c, int ti, const double* tile) {
+    double l0, l1, l2, l3;
+    g.lmu_pair(tile, ti, l0, l1);
+    g.lmu_pair(tile, ti + 64, l2, l3);
+    if (!g.zi && (g.fast_range(l0, l1) & g.fast_range(l2, l3)) && (unsigned)(y0 | y1 | y2 | y3) < (unsigned)YT) {
+      one_fast(y0, l0); one_fast(y1, l1); one_fast(y2, l2); one_fast(y3, l3);
+    } else {
+      const long long pos = (long long)c * CH + (ti & (CH - 1));
+      one(y0, l0, true, pos); one(y1, l1, true, pos + 1); one(y2, l2, true, pos + 64); one(y3, l3, true, pos + 65);
     }
   }
   template <bool FULLCHUNK>
@@ -546,6 +568,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneStat
 template <int K, bool HUBER>
 struct OpPass1 {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   static constexpr int KK = K * (K + 1) / 2;
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
@@ -628,8 +651,10 @@ struct OpPass1 {
     if (lane == 0) sw_out[row] = v;
   }
 };
-template <int K, bool HUBER, int MINB>
-__global__ void __launch_bounds__(ROW_THREADS, MINB) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
+// NW warps (= rows) per CTA.  Measured at cfg 2: NW = 6 (170 registers, no spill, 12 warps/SM) 16.7 ms vs NW = 8 (128
+// registers, 60 bytes of spill, 16 warps/SM) 16.3 ms -- the sweep is bound by FP64 issue, not by the spills.
+template <int K, bool HUBER, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
                                                           const double* sigma, double kh, double* A_out, double* u_out,
                                                           double* sw_out, double* ZS, double* VS) {
   extern __shared__ double smem[];
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(ROW_THREADS, MINB) k_pass1(RowGeom geo, GeneSt
   OpPass1<K, HUBER> op;
   op.st = st; op.sigma = sigma; op.kh = kh;
   op.A_out = A_out; op.u_out = u_out; op.sw_out = sw_out; op.ZS = ZS; op.VS = VS;
-  stream_rows<K, 2>(geo, &sh, op, smem);
+  stream_rows<K, 2, OpPass1<K, HUBER>, NW>(geo, &sh, op, smem);
 }
 
 // finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its
@@ -1153,6 +1178,7 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
 template <int K, bool HUBER>
 struct OpPass2 {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = !HUBER;   // certified rows: the four cells of a lane in one branch-free block
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
   GeneRegs<K> g;
@@ -1203,6 +1229,31 @@ struct OpPass2 {
     if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; res0 = m0 ? res0 : 0.0; wt1 = m1 ? wt1 : 0.0; res1 = m1 ? res1 : 0.0; }
     s0 += wt0 + wt1;
     s1 = fma(wt1, res1, fma(wt0, res0, s1));
+  }
+  __device__ __forceinline__ void quad(int y0, int y1, int y2, int y3, int c, int ti, const double* tile) {
+    const double* w = tile; const double* wn = tile + K * CELLS;
+    double l0, l1, l2, l3;
+    g.lmu_pair(w, ti, l0, l1);
+    g.lmu_pair(w, ti + 64, l2, l3);
+    const double yd0 = (double)y0, yd1 = (double)y1, yd2 = (double)y2, yd3 = (double)y3;
+    double mu, sa, sb, sc, sd, q0, q1, q2, q3;
+    if (g.fast_range(l0, l1) & g.fast_range(l2, l3)) {
+      nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu, &sa, &q0);
+      nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu, &sb, &q1);
+      nb_sq_fast(yd2, l2, g.psi, g.mt->ex, &mu, &sc, &q2);
+      nb_sq_fast(yd3, l3, g.psi, g.mt->ex, &mu, &sd, &q3);
+    } else {
+      SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi), cc = nb_sq_slow(yd2, l2, g.psi), d = nb_sq_slow(yd3, l3, g.psi);
+      sa = a.s; q0 = a.q; sb = b.s; q1 = b.q; sc = cc.s; q2 = cc.q; sd = d.s; q3 = d.q;
+    }
+    double r0 = fma(g.step, q0 - 1.0, l0), r1 = fma(g.step, q1 - 1.0, l1), r2 = fma(g.step, q2 - 1.0, l2), r3 = fma(g.step, q3 - 1.0, l3);
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      double2 va = *reinterpret_cast<const double2*>(wn + l * CELLS + ti), vb = *reinterpret_cast<const double2*>(wn + l * CELLS + ti + 64);
+      r0 = fma(-an[l], va.x, r0); r1 = fma(-an[l], va.y, r1); r2 = fma(-an[l], vb.x, r2); r3 = fma(-an[l], vb.y, r3);
+    }
+    s0 += (sa + sb) + (sc + sd);
+    s1 = fma(sd, r3, fma(sc, r2, fma(sb, r1, fma(sa, r0, s1))));
   }
   __device__ __forceinline__ void group_end(int j) {
     double a = warp_sum(s0), b = warp_sum(s1);
@@ -1308,6 +1359,7 @@ __global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* n
 template <int K>
 struct OpInit {
   static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneRegs<K> g;  // only the shared-table pointers are used
   static constexpr int P = K + 1;

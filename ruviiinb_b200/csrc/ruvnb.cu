@@ -549,10 +549,18 @@ static GeneState<K> gstate(ruvnb_ctx* ctx, const StateSet& s, bool with_step) {
   st.pi0 = s.pi0; st.psi_w = s.psi_w; st.zinb = ctx->zinb_on ? 1 : 0;
   return st;
 }
+#define P1_NW 8   // rows per CTA of k_pass1 (register budget, see kernels.cuh)
 template <int K>
 static inline size_t tile_smem(int nsets) { return (size_t)2 * nsets * K * TileCfg<K>::CELLS * sizeof(double); }
 static inline unsigned row_grid(int nrows) { return (unsigned)((nrows + NWARP - 1) / NWARP); }
 // row-streaming launch: the double-buffered W tiles exceed the 48 KB default dynamic shared memory
+#define LAUNCH_ROWS_NW(KERNEL, NW_, NSETS, NROWS, ...)                                                           \
+  do {                                                                                                           \
+    const size_t smem_ = tile_smem<KT>(NSETS);                                                                   \
+    CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));                   \
+    KERNEL<<<(unsigned)(((NROWS) + (NW_) - 1) / (NW_)), (NW_) * 32, smem_, ctx->stream>>>(__VA_ARGS__);          \
+    CKL();                                                                                                       \
+  } while (0)
 #define LAUNCH_ROWS(KERNEL, NSETS, NROWS, ...)                                                                   \
   do {                                                                                                           \
     const size_t smem_ = tile_smem<KT>(NSETS);                                                                   \
@@ -733,13 +741,13 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
     // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
     if (ctx->zinb_on) {
-      LAUNCH_ROWS((k_pass1<KT, true, 2>), 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      LAUNCH_ROWS_NW((k_pass1<KT, true, P1_NW>), P1_NW, 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
     } else {
       RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
-      LAUNCH_ROWS((k_pass1<KT, false, 2>), 2, Gl, gi, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      LAUNCH_ROWS_NW((k_pass1<KT, false, P1_NW>), P1_NW, 2, Gl, gi, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
       if (hub) {
         RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
-        LAUNCH_ROWS((k_pass1<KT, true, 2>), 2, Gl, gf, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+        LAUNCH_ROWS_NW((k_pass1<KT, true, P1_NW>), P1_NW, 2, Gl, gf, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
       }
     }
     KEV_END(1);

@@ -16,6 +16,7 @@
 template <int K>
 struct OpZinbQ {
   static constexpr bool PADS = true;
+  static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g;
   double* Q; long long Np; double* qrow;
   double spos, rlogr; int npos, row_;
