@@ -123,6 +123,10 @@ struct ruvnb_ctx {
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare
   int *faillist = nullptr;
+  int nparts = 1;            // row parts of the IRLS sweeps (kernels.cuh RowGeom::nparts), chosen from the shard size
+  int launch_parts = 1;      // parts of the launch being issued (geom() and LAUNCH_ROWS read it)
+  double* llparts = nullptr; // [nparts][Gl] partial log-likelihoods
+  int* certc = nullptr;      // [nparts][Gl][4] certificate counters
   int *list_inf = nullptr, *list_fin = nullptr, *part_counts = nullptr;  // rows by Huber status (k_partition_sigma)
   int *h_flags = nullptr;    // pinned mirror
   double* h_scal = nullptr;  // pinned [16]

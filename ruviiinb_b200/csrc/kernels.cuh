@@ -21,6 +21,9 @@ struct RowGeom {
   int nrows;            // rows this launch walks (upper bound when nrows_dev is set)
   const int* rowlist;   // nullptr -> slot == row; else row = rowlist[slot] (exact-MAD batches, partitions)
   const int* nrows_dev; // optional device-side row count: slots >= *nrows_dev idle (lists built on the device)
+  int nparts;           // each row is cut into nparts runs of whole tiles, one CTA per (8-row block, part): small gene shards
+                        // (several GPUs) would otherwise fill a fraction of a wave; partial sums land in part-major buffers
+  int Gl;               // rows of the local shard = stride between the parts of an output buffer
   const MathTabs* mtabs;  // exp / log / log(y) tables (global copy, staged into shared memory per CTA)
   const double* tabL;   // [Gl][YT] lgamma(y+r) - lgamma(r) - lgamma(y+1)
   const double* tabR;   // [Gl][YT] log(y + r)
@@ -148,9 +151,10 @@ template <int K, int NSETS, class Op, int NW = NWARP>
 __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, Op& op, double* smem) {
   constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = blockIdx.x * NW + warp;
+  const int part = blockIdx.x % geo.nparts, rblk = blockIdx.x / geo.nparts;
+  const int slot = rblk * NW + warp;
   const int nrows = geo.nrows_dev ? min(geo.nrows, *geo.nrows_dev) : geo.nrows;
-  if (blockIdx.x * NW >= nrows) return;   // whole CTA beyond the (device-side) list: nothing to do
+  if (rblk * NW >= nrows) return;   // whole CTA beyond the (device-side) list: nothing to do
   const bool active = slot < nrows;
   const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
   constexpr int TILE = NSETS * K * CELLS;
@@ -172,22 +176,24 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   __syncthreads();
   if (active) op.row_begin(row, slot);
   const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
-  const int ntiles = geo.nchunks / SC;
+  const int ntiles_all = geo.nchunks / SC;
+  const int tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;           // tiles per part
+  const int t0 = min(ntiles_all, part * tpp), ntiles = min(ntiles_all, t0 + tpp);
   int curj = -1;
   // the counts of the next chunk are fetched one chunk ahead (HBM latency hides behind ~4 elements of math)
   int2 ya = make_int2(0, 0), yb = ya;
-  if (active) { ya = yrow2[lane]; yb = yrow2[32 + lane]; }
-  stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, 0, tid);
-  for (int t = 0; t < ntiles; ++t) {
+  if (active && t0 < ntiles) { ya = yrow2[t0 * SC * (CH / 2) + lane]; yb = yrow2[t0 * SC * (CH / 2) + 32 + lane]; }
+  if (t0 < ntiles) stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, t0, tid);
+  for (int t = t0; t < ntiles; ++t) {
     if (t + 1 < ntiles) {
-      stage_tile<K, NSETS, NW>(smem + ((t + 1) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid);
+      stage_tile<K, NSETS, NW>(smem + ((t + 1 - t0) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid);
       __pipeline_wait_prior(1);
     } else {
       __pipeline_wait_prior(0);
     }
     __syncthreads();
     if (active) {
-      const double* tile = smem + (t & 1) * TILE;
+      const double* tile = smem + ((t - t0) & 1) * TILE;
 #pragma unroll 1
       for (int sc = 0; sc < SC; ++sc) {
         const int c = t * SC + sc;
@@ -285,7 +291,11 @@ struct OpSigndev {
   __device__ __forceinline__ void row_end(int) {
     double v = warp_max(mx);
     int nn = __any_sync(FULL, nan_);
-    if ((threadIdx.x & 31) == 0) { rowmax[slot_] = v; rownan[slot_] = nn; }
+    // max and or are order-independent: the parts of a row combine with atomics (buffers zeroed by the host)
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(reinterpret_cast<unsigned long long*>(rowmax + slot_), (unsigned long long)__double_as_longlong(v));  // v >= 0
+      if (nn) atomicOr(rownan + slot_, 1);
+    }
   }
 };
 template <int K>
@@ -421,7 +431,7 @@ struct OpLoglik {
   double acc, rlogr;
   double* out;
   // certificate
-  double* hint; double* sigma_out; double kh; int fastpath; long long n; int* diag;
+  const double* hint; int* certc; int fastpath;   // certc: this part's [Gl][4] counters c1, c2, c3, max key (or nullptr)
   double u_lo, u_hi, u_wl, u_wh; int k_lo, k_hi, k_wl, k_wh, hmaxk; int c1, c2, c3; bool cert;
   // The counting runs on 32-bit integer keys: the high word of u mapped so that integer order = floating order
   // (monotone non-decreasing under the truncation of the low word).  u < u_lo implies key(u) <= key(u_lo), etc., so the
@@ -431,7 +441,7 @@ struct OpLoglik {
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); acc = 0.0; rlogr = g.r * log(g.r);
     cert = false; c1 = c2 = c3 = 0; hmaxk = 0; u_lo = u_hi = u_wl = u_wh = 0.0; k_lo = k_hi = k_wl = k_wh = 0;
-    if (fastpath && sigma_out) {
+    if (fastpath && certc) {
       double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1], tg = hint[(long long)row * 3 + 2];
       cert = tg > 0.0 && lo <= hi;
       if (cert) {
@@ -508,54 +518,80 @@ struct OpLoglik {
     double v = warp_sum(acc);
     const int lane = threadIdx.x & 31;
     if (lane == 0) out[row] = v;
-    if (!sigma_out) return;
-    bool ok = false;
+    if (!certc) return;
+    int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
+    const int hk = __reduce_max_sync(FULL, hmaxk);
+    if (lane == 0) { int4 o = make_int4(a1, a2, a3, hk); reinterpret_cast<int4*>(certc)[row] = o; }
+  }
+};
+// The certificate decision of a row from the counters of its parts (see the comment above OpLoglik): sigma = +Inf
+// (certified) or 0 (exact path), hint recentring, failure diagnostics.  One thread per row.
+__global__ void k_cert_finish(int Gl, int nparts, const int* certc /* [nparts][Gl][4] */, double* hint, double* sigma_out, double kh,
+                              int fastpath, long long n, int* diag) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= Gl) return;
+  bool ok = false, cert = false;
+  if (fastpath) {
+    const double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1], tg = hint[(long long)row * 3 + 2];
+    cert = tg > 0.0 && lo <= hi;
     if (cert) {
-      int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
-      const int hk = __reduce_max_sync(FULL, hmaxk);
-      const int nb = hk >= 0x7ff00000;                       // some deviance was NaN or infinite
-      const double hm = __hiloint2double(hk + 1, 0);         // upper bound of max |h| (one unit of the high word)
-      if (lane == 0 && !nb) {
+      long long a1 = 0, a2 = 0, a3 = 0; int hk = 0;
+      for (int p = 0; p < nparts; ++p) {
+        const int4 c = reinterpret_cast<const int4*>(certc)[(long long)p * Gl + row];
+        a1 += c.x; a2 += c.y; a3 += c.z; hk = max(hk, c.w);
+      }
+      const bool nb = hk >= 0x7ff00000;                     // some deviance was NaN or infinite
+      if (!nb) {
+        const double hm = __hiloint2double(hk + 1, 0);      // upper bound of max |h| (one unit of the high word)
         const double C = MAD_CONST / 0.6745;
-        double mx = sqrt(2.0 * hm);
-        double t = mx / (kh * C) * (1.0 + 1e-9);
+        const double mx = sqrt(2.0 * hm);
+        const double t = mx / (kh * C) * (1.0 + 1e-9);
+        const double u_lo = u_of_d(lo), u_hi = u_of_d(hi), u_wl = u_of_d(lo - tg), u_wh = u_of_d(hi + tg);
         // margins actually realised by the u-space thresholds
-        double room = fmin(d_of_u(u_lo) - d_of_u(u_wl), d_of_u(u_wh) - d_of_u(u_hi));
-        long long kl = (n - 1) / 2, ku = n / 2;
-        ok = (hk > 0) && (mx > 0.0) && (t <= room) && ((long long)a1 <= kl) && ((long long)a2 <= n - 1 - ku) && ((long long)a3 <= kl);
+        const double room = fmin(d_of_u(u_lo) - d_of_u(u_wl), d_of_u(u_wh) - d_of_u(u_hi));
+        const long long kl = (n - 1) / 2, ku = n / 2;
+        ok = (hk > 0) && (mx > 0.0) && (t <= room) && (a1 <= kl) && (a2 <= n - 1 - ku) && (a3 <= kl);
         if (!ok && diag) {  // why the certificate failed (tuning aid; ruvnb_cert_diag)
-          int why = !(hk > 0 && mx > 0.0) ? 2 : !(t <= room) ? 3 : ((long long)a1 > kl) ? 4 : ((long long)a2 > n - 1 - ku) ? 5 : 6;
+          int why = !(hk > 0 && mx > 0.0) ? 2 : !(t <= room) ? 3 : (a1 > kl) ? 4 : (a2 > n - 1 - ku) ? 5 : 6;
           atomicAdd(diag + why, 1);
         }
         if (ok) {
           // recentre the hint on the median estimated from the counts (density inside [lo, hi] taken as uniform).
           // Hints never affect results -- the certificate re-verifies them -- they only decide how often the exact
           // path is needed while the parameters are still moving.
-          double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1];
-          double pin = 1.0 - (double)(a1 + a2) / (double)n;
+          const double pin = 1.0 - (double)(a1 + a2) / (double)n;
           if (pin > 0.05) {
-            double w = hi - lo;
-            double ctr = lo + (0.5 - (double)a1 / (double)n) * w / pin;
+            const double w = hi - lo;
+            const double ctr = lo + (0.5 - (double)a1 / (double)n) * w / pin;
             hint[(long long)row * 3 + 0] = ctr - 0.5 * w;
             hint[(long long)row * 3 + 1] = ctr + 0.5 * w;
           }
         }
+      } else if (diag) {
+        atomicAdd(diag + 1, 1);
       }
     }
-    if (lane == 0) {
-      sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
-      if (diag && !cert) atomicAdd(diag + (fastpath ? 0 : 7), 1);   // 0: no usable hint (first visit or live Huber weights)
-    }
   }
-};
+  sigma_out[row] = ok ? __longlong_as_double(0x7ff0000000000000ll) : 0.0;
+  if (diag && !cert) atomicAdd(diag + (fastpath ? 0 : 7), 1);   // 0: no usable hint (first visit or live Huber weights)
+}
+// dst[i] = sum over the parts of src[p * n + i], fixed order (deterministic); in place on part 0 when dst == src
+__global__ void k_sum_parts(double* dst, const double* src, long long n, int nparts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = src[i];
+  for (int p = 1; p < nparts; ++p) s += src[(long long)p * n + i];
+  dst[i] = s;
+}
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneState<K> st, double* out, double* hint,
-                                                           double* sigma_out, double kh, int fastpath, long long n, int* diag) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_loglik(RowGeom geo, GeneState<K> st, double* out /* [nparts][Gl] */, const double* hint,
+                                                           int* certc /* [nparts][Gl][4] or nullptr */, int fastpath) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
   OpLoglik<K> op;
-  op.st = st; op.out = out; op.hint = hint; op.sigma_out = sigma_out; op.kh = kh; op.fastpath = fastpath; op.n = n; op.diag = diag;
+  op.st = st; op.out = out + poff; op.hint = hint; op.certc = certc ? certc + poff * 4 : nullptr; op.fastpath = fastpath;
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
@@ -660,9 +696,11 @@ __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> 
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
+  constexpr int KK = K * (K + 1) / 2;
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;   // part-major partial sums
   OpPass1<K, HUBER> op;
   op.st = st; op.sigma = sigma; op.kh = kh;
-  op.A_out = A_out; op.u_out = u_out; op.sw_out = sw_out; op.ZS = ZS; op.VS = VS;
+  op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
   stream_rows<K, 2, OpPass1<K, HUBER>, NW>(geo, &sh, op, smem);
 }
 
@@ -1268,9 +1306,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = W_new; }
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
   OpPass2<K, HUBER> op;
   op.st = st; op.alpha_new = alpha_new; op.sigma = sigma; op.kh = kh;
-  op.S0 = S0; op.S1 = S1;
+  op.S0 = S0 + poff * st.m; op.S1 = S1 + poff * st.m;
   stream_rows<K, 2>(geo, &sh, op, smem);
 }
 

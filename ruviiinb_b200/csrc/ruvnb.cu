@@ -423,17 +423,28 @@ static int ensure_state(ruvnb_ctx* ctx, int K) {
   CKL();
   CK(cudaMemsetAsync(ctx->loglik, 0, Gl * 8, ctx->stream));
   CK(cudaMemsetAsync(ctx->loglik_tmp, 0, Gl * 8, ctx->stream));
-  RET(dev_alloc(ctx, &ctx->A, Gl * KK));
-  RET(dev_alloc(ctx, &ctx->u, Gl * K));
-  RET(dev_alloc(ctx, &ctx->sw, Gl));
-  RET(dev_alloc(ctx, &ctx->ZS, Gl * m));
-  RET(dev_alloc(ctx, &ctx->VS, Gl * m * K));
+  // row parts: enough CTAs for >= 6 waves of 296 (2 CTAs x 148 SMs) so that a small gene shard does not leave most
+  // of a wave empty (20000 rows on one GPU: 1 part; 2500 rows per GPU on eight: 8 parts)
+  {
+    const long long ctas = (Gl + NWARP - 1) / NWARP;
+    int P = 1;
+    while (P < 8 && ctas * P < 6 * 296) P *= 2;
+    ctx->nparts = P;
+  }
+  const long long P = ctx->nparts;
+  RET(dev_alloc(ctx, &ctx->A, P * Gl * KK));
+  RET(dev_alloc(ctx, &ctx->u, P * Gl * K));
+  RET(dev_alloc(ctx, &ctx->sw, P * Gl));
+  RET(dev_alloc(ctx, &ctx->ZS, P * Gl * m));
+  RET(dev_alloc(ctx, &ctx->VS, P * Gl * m * K));
+  RET(dev_alloc(ctx, &ctx->llparts, P * Gl));
+  RET(dev_alloc(ctx, &ctx->certc, P * Gl * 4));
   RET(dev_alloc(ctx, &ctx->cvec, Gl * K));
   RET(dev_alloc(ctx, &ctx->Ab, Gl * (KK + K)));
   RET(dev_alloc(ctx, &ctx->red, 64));
   RET(dev_alloc(ctx, &ctx->amean, K));
-  RET(dev_alloc(ctx, &ctx->S0, Gl * m));
-  RET(dev_alloc(ctx, &ctx->S1, Gl * m));
+  RET(dev_alloc(ctx, &ctx->S0, P * Gl * m));
+  RET(dev_alloc(ctx, &ctx->S1, P * Gl * m));
   RET(dev_alloc(ctx, &ctx->sigma_exact, Gl));
   RET(dev_alloc(ctx, &ctx->hint, Gl * 3));
   k_fill<<<nblk(Gl * 3, 256), 256, 0, ctx->stream>>>(ctx->hint, Gl * 3, -1.0);  // tg < 0: no hint yet
@@ -536,7 +547,7 @@ int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host) {
 static RowGeom geom(ruvnb_ctx* ctx, int nrows, const int* rowlist) {
   RowGeom g;
   g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid;
-  g.nrows = nrows; g.rowlist = rowlist; g.nrows_dev = nullptr;
+  g.nrows = nrows; g.rowlist = rowlist; g.nrows_dev = nullptr; g.nparts = ctx->launch_parts; g.Gl = ctx->Gl;
   if (!rowlist && nrows == ctx->Gl && ctx->roworder_ready) g.rowlist = ctx->d_roworder;   // full sweeps: heavy rows first
   g.mtabs = ctx->d_mtabs; g.tabL = ctx->tabL; g.tabR = ctx->tabR; g.lgr = ctx->lgr;
   g.zinf = ctx->zinb_on ? ctx->d_zinf : nullptr;
@@ -558,14 +569,14 @@ static inline unsigned row_grid(int nrows) { return (unsigned)((nrows + NWARP - 
   do {                                                                                                           \
     const size_t smem_ = tile_smem<KT>(NSETS);                                                                   \
     CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));                   \
-    KERNEL<<<(unsigned)(((NROWS) + (NW_) - 1) / (NW_)), (NW_) * 32, smem_, ctx->stream>>>(__VA_ARGS__);          \
+    KERNEL<<<(unsigned)(((NROWS) + (NW_) - 1) / (NW_)) * ctx->launch_parts, (NW_) * 32, smem_, ctx->stream>>>(__VA_ARGS__); \
     CKL();                                                                                                       \
   } while (0)
 #define LAUNCH_ROWS(KERNEL, NSETS, NROWS, ...)                                                                   \
   do {                                                                                                           \
     const size_t smem_ = tile_smem<KT>(NSETS);                                                                   \
     CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));                   \
-    KERNEL<<<row_grid(NROWS), ROW_THREADS, smem_, ctx->stream>>>(__VA_ARGS__);                                   \
+    KERNEL<<<row_grid(NROWS) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(__VA_ARGS__);               \
     CKL();                                                                                                       \
   } while (0)
 
@@ -615,11 +626,17 @@ static int ensure_ytabs(ruvnb_ctx* ctx, const double* psi) {
 static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* out, double* total) {
   const double kh = o->robust ? 1.345 : 100.0;  // :155
   RET(ensure_ytabs(ctx, s.psi));
+  const int P = ctx->nparts;
   KEV_BEGIN(4);
+  ctx->launch_parts = P;
   DISPATCH_K(ctx->K, {
-    LAUNCH_ROWS(k_loglik<KT>, 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), out, ctx->hint, s.sigma, kh,
-                o->huber_fastpath, (long long)ctx->N, ctx->cert_diag);
+    LAUNCH_ROWS(k_loglik<KT>, 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), gstate<KT>(ctx, s, false), P > 1 ? ctx->llparts : out, ctx->hint, ctx->certc,
+                o->huber_fastpath);
   });
+  ctx->launch_parts = 1;
+  if (P > 1) { k_sum_parts<<<nblk(ctx->Gl, 256), 256, 0, ctx->stream>>>(out, ctx->llparts, ctx->Gl, P); CKL(); }
+  k_cert_finish<<<nblk(ctx->Gl, 128), 128, 0, ctx->stream>>>(ctx->Gl, P, ctx->certc, ctx->hint, s.sigma, kh, o->huber_fastpath, (long long)ctx->N, ctx->cert_diag);
+  CKL();
   KEV_END(4);
   s.sig_valid = true; s.maybe_active = false;
   if (total) {
@@ -660,9 +677,17 @@ static int complete_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, doub
     KEV_BEGIN(5);
     for (long long r0 = 0; r0 < nf; r0 += ctx->D_rows) {
       int nr = (int)std::min<long long>(ctx->D_rows, nf - r0);
+      CK(cudaMemsetAsync(ctx->rowmax, 0, (size_t)nr * 8, ctx->stream));   // combined across the parts with atomicMax / atomicOr
+      CK(cudaMemsetAsync(ctx->rownan, 0, (size_t)nr * 4, ctx->stream));
+      {
+        int Ps = 1;
+        while (Ps < 8 && (long long)((nr + NWARP - 1) / NWARP) * Ps < 2 * 296) Ps *= 2;   // few failing rows: cut them into parts
+        ctx->launch_parts = Ps;
+      }
       DISPATCH_K(ctx->K, {
         LAUNCH_ROWS(k_signdev<KT>, 1, nr, geom(ctx, nr, ctx->faillist + r0), gstate<KT>(ctx, s, false), ctx->D, ctx->rowmax, ctx->rownan);
       });
+      ctx->launch_parts = 1;
       k_row_sigma<<<nr, RS_NT, 0, ctx->stream>>>(ctx->D, ctx->Np, (long long)ctx->N, ctx->faillist + r0, ctx->rowmax, ctx->rownan, kh,
                                                  o->huber_fastpath, s.sigma, ctx->sigma_exact, ctx->hint);
       CKL();
@@ -738,6 +763,12 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(1);
+    const int P = ctx->nparts;
+    ctx->launch_parts = P;
+    if (P > 1) {  // groups that a part never meets must read as zero
+      CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * m * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * KT * 8, ctx->stream));
+    }
     // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
     // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
     if (ctx->zinb_on) {
@@ -749,6 +780,15 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
         RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
         LAUNCH_ROWS_NW((k_pass1<KT, true, P1_NW>), P1_NW, 2, Gl, gf, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
       }
+    }
+    ctx->launch_parts = 1;
+    if (P > 1) {
+      constexpr int KKT = KT * (KT + 1) / 2;
+      k_sum_parts<<<nblk((long long)Gl * KKT, 256), 256, 0, ctx->stream>>>(ctx->A, ctx->A, (long long)Gl * KKT, P); CKL();
+      k_sum_parts<<<nblk((long long)Gl * KT, 256), 256, 0, ctx->stream>>>(ctx->u, ctx->u, (long long)Gl * KT, P); CKL();
+      k_sum_parts<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->sw, ctx->sw, Gl, P); CKL();
+      k_sum_parts<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(ctx->ZS, ctx->ZS, (long long)Gl * m, P); CKL();
+      k_sum_parts<<<nblk((long long)Gl * m * KT, 256), 256, 0, ctx->stream>>>(ctx->VS, ctx->VS, (long long)Gl * m * KT, P); CKL();
     }
     KEV_END(1);
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
@@ -840,6 +880,12 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   DISPATCH_K(K, {
     auto st = gstate<KT>(ctx, c, true);
     KEV_BEGIN(3);
+    const int P = ctx->nparts;
+    ctx->launch_parts = P;
+    if (P > 1) {
+      CK(cudaMemsetAsync(ctx->S0, 0, (size_t)P * Gl * m * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->S1, 0, (size_t)P * Gl * m * 8, ctx->stream));
+    }
     if (ctx->zinb_on) {
       LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
     } else {
@@ -849,6 +895,11 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
         RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
         LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, gf, st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
       }
+    }
+    ctx->launch_parts = 1;
+    if (P > 1) {
+      k_sum_parts<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(ctx->S0, ctx->S0, (long long)Gl * m, P); CKL();
+      k_sum_parts<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(ctx->S1, ctx->S1, (long long)Gl * m, P); CKL();
     }
     KEV_END(3);
   });
