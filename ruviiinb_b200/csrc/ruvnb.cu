@@ -129,6 +129,14 @@ int ruvnb_comm_init(ruvnb_ctx* ctx, const unsigned char id[128], int rank, int n
   int r = g_nccl.CommInitRank(&ctx->comm, nranks, u, rank);
   if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   ctx->rank = rank; ctx->nranks = nranks;
+  // NCCL connects its rings / trees lazily at the first collective (hundreds of ms at 8 ranks): do that here, as part
+  // of the one-time set-up, not inside the first IRLS iteration
+  int* warm = nullptr;
+  CK(cudaMalloc((void**)&warm, 4));
+  CK(cudaMemsetAsync(warm, 0, 4, ctx->stream));
+  RET(allreduce(ctx, warm, 1, NCCL_INT32));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaFree(warm));
   return RUVNB_OK;
 }
 
