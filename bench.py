@@ -38,7 +38,7 @@ WORKLOADS = {
 }
 SEED = 20261019 + 2
 # FP64-pipe instructions per element of each sweep at k = 5 (ncu smsp__inst_executed_pipe_fp64 / elements, profiles/)
-FP64_INSTR = {"pass1": 68.0, "pass2": 40.0, "loglik": 45.0}
+FP64_INSTR = {"pass1": 67.8, "pass2": 41.5, "loglik": 40.8}
 
 
 # ------------------------------------------------------------------------------------------------
