@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's exported R functions (NAMESPACE:3-6) over the C ABI of libruvnb_b200.
+
+    ruvIII_nb(Y, M, ctl, k=2, ...)      R/ruvIIInb.R:27-629     -> dict with the reference's list elements
+    get_res(out, type=..., ...)         R/get.res.R:12-129      -> G x N array
+    makeSCE(obj, cData, batch, assays)  R/makeSCE.R:12-43       -> dict standing in for the SingleCellExperiment
+    fastruvIII_nb_finish(...)           R/fastruvIIInb.R:625-792 (the full-data passes after the subsample fit)
+
+Same argument names (dots become underscores), defaults and error behaviour: invalid input raises ValueError where the R
+code calls stop(); numerical "problematic entries" are reverted inside the library, never raised.  `ncores` is accepted and
+ignored (the fork pool is replaced by the GPU).  Everything numerical happens in the CUDA library: there is no CPU
+fallback, and this module never imports the test oracle.
+"""
+import numpy as np
+
+from . import _lib
+
+_UNSUPPORTED = "is not part of the B200 path (SURVEY.md section 2: out of scope, off by default in the reference)"
+
+
+def _as_logical_ctl(ctl, G, rownames=None):
+    """R/ruvIIInb.R:42-45: a logical vector, or indices / names of the control genes."""
+    ctl = np.asarray(ctl)
+    if ctl.dtype == bool:
+        if ctl.size != G:
+            raise ValueError("ctl must have one entry per gene")
+        return ctl.copy()
+    out = np.zeros(G, dtype=bool)
+    if ctl.dtype.kind in "iu":
+        out[ctl] = True      # 0-based positions (R: 1-based)
+        return out
+    if rownames is None:
+        raise ValueError("character ctl needs rownames")
+    out[np.isin(np.asarray(rownames), ctl)] = True
+    return out
+
+
+def init_W(Y, ctl, k):
+    """R/ruvIIInb.R:160-168: the k leading right singular vectors of log(Y[ctl,]/rowMeans(Y[ctl,]) + 1).  The reference
+    uses irlba (random start, arbitrary signs); here a dense eigen-decomposition of the n_ctl x n_ctl Gram with the sign of
+    each vector fixed so that its largest entry is positive."""
+    Yc = np.asarray(Y)[np.asarray(ctl, bool)].astype(np.float64)
+    A = np.log(Yc / Yc.mean(axis=1, keepdims=True) + 1.0)
+    w, U = np.linalg.eigh(A @ A.T)
+    order = np.argsort(w)[::-1][:k]
+    V = (A.T @ U[:, order]) / np.sqrt(w[order])[None, :]
+    for j in range(k):
+        if V[np.argmax(np.abs(V[:, j])), j] < 0:
+            V[:, j] = -V[:, j]
+    return V
+
+
+def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda_b=16, batch=None, step_fac=0.5,
+              inner_maxit=50, outer_maxit=25, ncores=2, use_pseudosample=False, nc_pool=20, batch_disp=False,
+              zeroinf=None, W0=None, psi=None, device=0, rownames=None, return_trace=False):
+    """`ruvIII.nb` (R/ruvIIInb.R:27-629).  Y: G x N counts; M: N x m replicate matrix with exactly one TRUE per row
+    (:206); ctl: logical / index vector of control genes.  Extra arguments of the mirror: W0 (injects the initial W
+    instead of the SVD), psi (injects a dispersion vector or schedule instead of estimateDisp), device.
+    Returns the reference's list as a dict: counts, W, M, ctl, logl, a, Mb, gmean, pi0, psi, L.a, L.b, batch."""
+    if use_pseudosample:
+        raise NotImplementedError("use.pseudosample " + _UNSUPPORTED)
+    if ortho_W:
+        raise NotImplementedError("ortho.W " + _UNSUPPORTED)
+    Y = np.asarray(Y)
+    if Y.ndim != 2:
+        raise ValueError("Y must be a genes x cells matrix")
+    G, N = Y.shape
+    M = np.asarray(M).astype(bool)                                   # :46-49
+    if M.shape[0] != N:
+        raise ValueError("M must have one row per cell")
+    if (M.sum(axis=1) != 1).any():
+        raise ValueError("every cell must belong to exactly one replicate group (R/ruvIIInb.R:206 indexes Mb[, apply(M, 1, which)])")
+    if (M.sum(axis=0) == 0).any():
+        raise ValueError("Each column of M matrix must have at least one non-zero entry")   # R/fastruvIIInb.R:60
+    ctl = _as_logical_ctl(ctl, G, rownames)
+    batch = np.ones(N, dtype=np.int64) if batch is None else np.asarray(batch)              # :64-66
+    if batch_disp and len(np.unique(batch)) > 1:
+        raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
+    zi = np.zeros(N, dtype=bool) if zeroinf is None else np.asarray(zeroinf).astype(bool)   # :39-40
+    # :53-62 Winsorize + ceiling happen on the device; all-zero genes are dropped before the upload (a gene is all zero
+    # after the cap iff it was before)
+    keep = (Y > 0).sum(axis=1) > 0
+    Yk = np.ascontiguousarray(np.ceil(Y[keep]), dtype=np.int32)
+    ctlk = ctl[keep]
+    grp = np.argmax(M, axis=1).astype(np.int32)                      # apply(M, 1, which), :50
+    opts = _lib.default_opts(k=int(k), robust=int(bool(robust)), lambda_a=float(lambda_a), lambda_b=float(lambda_b),
+                             step_fac=float(step_fac), inner_maxit=int(inner_maxit), outer_maxit=int(outer_maxit),
+                             zinb=int(zi.any()))
+    with _lib.Context(device) as ctx:
+        ctx.set_design(Yk.shape[0], N, grp, ctlk, zeroinf=zi if zi.any() else None)
+        ctx.upload_counts(Yk)
+        ctx.winsorize()
+        counts = ctx.get_counts()
+        if W0 is None:
+            W0 = init_W(counts, ctlk, int(k))
+        psi_inject = None if psi is None else np.atleast_2d(np.asarray(psi, dtype=np.float64))[:, keep]
+        logl, recs, stats = ctx.fit_nb(opts, W0=np.asarray(W0, dtype=np.float64), psi_inject=psi_inject)
+        out = {"counts": counts, "W": ctx.get_state("W"), "M": M, "ctl": ctlk, "logl": logl, "a": ctx.get_state("alpha"),
+               "Mb": ctx.get_state("Mb"), "gmean": ctx.get_state("gmean"), "psi": ctx.get_state("psi"),
+               "L.a": lambda_a, "L.b": lambda_b, "batch": batch}
+        pi0 = ctx.get_state("pi0")
+    out["pi0"] = np.outer(pi0, zi.astype(np.float64)) if zi.any() else None   # :611-626
+    out["zero_genes"] = ~keep
+    if return_trace:
+        out["trace"], out["stats"] = recs, stats
+    return out
+
+
+def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_size=5000, device=0):
+    """`get.res` (R/get.res.R:12-129).  `type`: like the reference, every requested kind is evaluated in the order
+    pearson, logcounts, quantile and the LAST one is returned (:49,68,75), so the default returns the percentile-adjusted
+    counts.  out["Mb"] may be G x N (fastruvIII.nb's Mb.all) or G x m (a ruvIII.nb fit: expanded by replicate group --
+    the reference indexes Mb by cell, :35, and would need the caller to expand it)."""
+    kinds = [type] if isinstance(type, str) else list(type)
+    for t in kinds:
+        if t not in ("pearson", "logcounts", "quantile"):
+            raise ValueError(f"unknown type '{t}'")
+    last = [t for t in ("pearson", "logcounts", "quantile") if t in kinds][-1]
+    if out.get("pi0") is not None:
+        raise NotImplementedError("get.res for zero-inflated fits (ZIM::pzinb / qzinb branch, R/get.res.R:84-105)")
+    if np.ndim(out["psi"]) != 1:
+        raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
+    Y = np.ascontiguousarray(out["counts"], dtype=np.int32)
+    G, N = Y.shape
+    M = np.asarray(out["M"]).astype(bool)
+    Mb = np.asarray(out["Mb"], dtype=np.float64)
+    per_cell = Mb.shape[1] == N and Mb.shape[1] != M.shape[1]
+    grp = np.argmax(M, axis=1).astype(np.int32) if (M.sum(axis=1) == 1).all() else np.zeros(N, dtype=np.int32)
+    m = int(grp.max()) + 1
+    with _lib.Context(device) as ctx:
+        ctx.set_design(G, N, grp, np.asarray(out["ctl"], bool))
+        ctx.upload_counts(Y)
+        ctx.set_state("W", out["W"])
+        ctx.set_state("alpha", out["a"])
+        ctx.set_state("gmean", out["gmean"])
+        ctx.set_state("psi", out["psi"])
+        ctx.set_state("Mb", np.zeros((G, m)) if per_cell else Mb)
+        return ctx.get_res({"pearson": 1, "logcounts": 2, "quantile": 3}[last], block_size=block_size,
+                           Mb_cells=Mb if per_cell else None)
+
+
+def makeSCE(obj, cData=None, batch=None, assays=("pearson", "logPAC")):
+    """`makeSCE` (R/makeSCE.R:12-43): a dict standing in for the SingleCellExperiment -- assays 'counts', and per request
+    'pearson' (Pearson residuals) and 'logPAC' (log(PAC + 1))."""
+    sce = {"assays": {"counts": obj["counts"]}, "colData": cData, "W": obj["W"]}
+    want = [assays] if isinstance(assays, str) else list(assays)
+    if "pearson" in want:
+        sce["assays"]["pearson"] = get_res(obj, type="pearson", batch=batch)
+    if "logPAC" in want:
+        sce["assays"]["logPAC"] = np.log(get_res(obj, type="quantile", batch=batch) + 1.0)   # R/makeSCE.R:36-38
+    return sce
+
+
+def fastruvIII_nb_finish(Y, M, ctl, alpha, gmean, psi, Mb_sub, Wsub, subsamples, wt_ctl, lambda_a=0.01, lambda_b=16,
+                         block_size=5000, device=0):
+    """The full-data tail of `fastruvIII.nb` (R/fastruvIIInb.R:625-792) given the subsample fit (alpha, gmean, psi,
+    Mb_sub G x m, Wsub rows for the cells `subsamples`, wt_ctl = best.wtctl): W for all cells, Mb.all, the psi cap.
+    The subsample fit itself (:118-623) is not built yet."""
+    from . import _lib as L
+    Y = np.ascontiguousarray(Y, dtype=np.int32)
+    G, N = Y.shape
+    M = np.asarray(M).astype(bool)
+    annotated = M.sum(axis=1) > 0
+    if annotated.mean() < 0.01:
+        raise ValueError("Less than 1% of cells have replicate annotation")                 # R/fastruvIIInb.R:53
+    if (M.sum(axis=0) == 0).any():
+        raise ValueError("Each column of M matrix must have at least one non-zero entry")   # :60
+    grp = np.where(annotated, np.argmax(M, axis=1), 0).astype(np.int32)
+    annot = np.where(annotated, np.argmax(M, axis=1), -1).astype(np.int32)
+    k = Wsub.shape[1]
+    W_init = np.zeros((N, k))
+    W_init[np.asarray(subsamples)] = Wsub                                                    # :635-636
+    med = np.median(Wsub, axis=0)
+    mad = 1.4826 * np.median(np.abs(Wsub - med[None, :]), axis=0)                            # :653-654
+    with L.Context(device) as ctx:
+        ctx.set_design(G, N, grp, np.asarray(ctl, bool))
+        ctx.upload_counts(Y)
+        ctx.set_state("W", W_init)
+        ctx.set_state("alpha", alpha)
+        ctx.set_state("gmean", gmean)
+        ctx.set_state("psi", psi)
+        ctx.set_state("Mb", Mb_sub)
+        W, sweeps, crit = ctx.fast_W_all(W_init, wt_ctl, med, mad, lambda_a=lambda_a)
+        Mb_all = ctx.fast_Mb_all(annot, lambda_b=lambda_b, block_size=block_size)
+    return {"counts": Y, "W": W, "M": M, "ctl": np.asarray(ctl, bool), "a": alpha, "Mb": Mb_all, "gmean": gmean,
+            "psi": L.fast_cap_psi(psi), "L.a": lambda_a, "L.b": lambda_b, "subsamples": subsamples, "Wsub": Wsub,
+            "Mb.sub": Mb_sub, "W_sweeps": sweeps}

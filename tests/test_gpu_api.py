@@ -1,0 +1,59 @@
+"""The host mirror of the reference's exported functions (ruviiinb_b200/api.py) used the way the reference is used:
+ruvIII.nb end to end -- Winsorize, initial W, dispersion estimation, alternating IRLS -- against the oracle, then get.res."""
+import numpy as np
+import pytest
+
+
+def _data(G=90, N=700, k=2, m=3, n_ctl=24, seed=91):
+    from ruviiinb_b200 import synth
+    Y, M, ctl, truth = synth.make_counts(G, N, k, m, n_ctl, seed=seed, gmean_mu=0.8, gmean_sd=0.9)
+    Y[7] = 0                      # an all-zero gene is dropped (R/ruvIIInb.R:57-62)
+    Y[11, 5] = 4000               # an outlier count is winsorised (:53)
+    return Y, M, ctl, truth
+
+
+@pytest.mark.gpu
+def test_ruvIII_nb_end_to_end_matches_oracle():
+    from oracle import edger, ruviiinb as orc
+    from ruviiinb_b200 import api
+    from tests.parity import relerr
+    Y, M, ctl, truth = _data()
+    # the SAME initial W on both sides (irlba's start is random in the reference)
+    Yw, _ = __import__("oracle.rstats", fromlist=["x"]).winsorize_counts(Y.astype(np.float64))
+    keep = (Yw > 0).sum(axis=1) > 0
+    W0 = api.init_W(Yw[keep], ctl[keep], 2)
+
+    def psi_fn(Yx, offs, wt, psi_old):   # estimateDisp.par(Y, 1, offset = offs, weights = wt, tagwise, robust) restated
+        return edger.estimate_disp(Yx, offs)["tagwise"]
+
+    trace = []
+    ref = orc.ruvIII_nb(Y.astype(np.float64), M, ctl, k=2, outer_maxit=3, W0=W0, psi_fn=psi_fn, trace=trace)
+    out = api.ruvIII_nb(Y, M, ctl, k=2, outer_maxit=3, W0=W0, return_trace=True)
+    assert out["zero_genes"][7] and out["counts"].shape[0] == Y.shape[0] - 1
+    assert np.array_equal(out["counts"], ref["counts"].astype(np.int32))
+    dec = [(r["outer"], r["iter"], r["degener"], r["accepted"]) for r in out["trace"]]
+    assert dec == [(r["outer"], r["iter"], int(r["degener"]), int(r["accepted"])) for r in trace]
+    err = dict(W=relerr(out["W"], ref["W"]), a=relerr(out["a"], ref["a"]), gmean=relerr(out["gmean"], ref["gmean"]),
+               Mb=relerr(out["Mb"], ref["Mb"], floor=1e-6), psi=relerr(out["psi"], ref["psi"]), logl=relerr(out["logl"], ref["logl"]))
+    assert all(v < 1e-6 for v in err.values()), err     # north_star tolerance
+    # get.res on the fit, the way makeSCE calls it (default type: the percentile-adjusted counts win)
+    from oracle import getres
+    grp = np.argmax(M, axis=1)
+    ref_out = dict(counts=ref["counts"], a=ref["a"], W=ref["W"], gmean=ref["gmean"], Mb=ref["Mb"][:, grp], psi=ref["psi"])
+    pac = api.get_res(out, block_size=256)
+    ref_pac = getres.get_res(ref_out, getres.QUANTILE, block_size=256)
+    assert (pac != ref_pac).mean() < 1e-3      # integer counts; the two fits differ at 1e-7, so a few boundary ties may flip
+    pear = api.get_res(out, type="pearson", block_size=256)
+    assert np.abs(pear - getres.get_res(ref_out, getres.PEARSON, block_size=256)).max() < 1e-5
+
+
+def test_api_argument_errors_mirror_stop():
+    from ruviiinb_b200 import api
+    Y, M, ctl, truth = _data(G=20, N=50, n_ctl=5)
+    bad = M.copy(); bad[:, 0] = 0
+    with pytest.raises(ValueError, match="exactly one replicate group|non-zero entry"):
+        api.ruvIII_nb(Y, bad, ctl)
+    with pytest.raises(NotImplementedError):
+        api.ruvIII_nb(Y, M, ctl, use_pseudosample=True)
+    with pytest.raises(ValueError, match="unknown type"):
+        api.get_res(dict(pi0=None, psi=np.ones(3)), type="foo")
