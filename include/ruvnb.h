@@ -210,6 +210,20 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
                  ruvnb_fit_stats* stats);
 
 /* ---- fastruvIII.nb streaming passes (R/fastruvIIInb.R) ------------------------------------------------------------ */
+/* F3/F4 (:223-623) the subsample fit, on a context that holds the SUBSAMPLED cells (every cell annotated; the caller draws
+ * `subsamples`, :118-137, and passes U0 = irlba(RM_Z)$v, :228 -- both are R-RNG dependent and therefore injected).
+ *   ruvnb_fast_init         F3: gmean, alpha, Wsub, Mb from Z = log(Y + 1); "psi" is then set by the caller (estimateDisp
+ *                           on <= 100 cells, :273-311: a second context over those columns + ruvnb_estimate_disp)
+ *   ruvnb_fast_begin_outer  per-cell log-likelihood and wt.ctl of the current parameters, steps <- 1 (:322-352)
+ *   ruvnb_fast_iteration    one inner iteration (:357-531): candidate becomes current; *total_new = sum of its per-cell
+ *                           log-likelihoods; bad = problematic alpha / W / Mb entries
+ *   ruvnb_fast_halve_steps  per-CELL step halving (:538-539);  ruvnb_fast_accept  loglik <- loglik.tmp (:548)
+ * ruvnb_snapshot_best / ruvnb_restore_best carry best.wtctl as well.  State names: "cell_loglik", "cell_step" (N), "wt_ctl". */
+int ruvnb_fast_init(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* U0);
+int ruvnb_fast_begin_outer(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total);
+int ruvnb_fast_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total_new, int bad[3]);
+int ruvnb_fast_halve_steps(ruvnb_ctx* ctx, const ruvnb_opts* o);
+int ruvnb_fast_accept(ruvnb_ctx* ctx);
 /* F5 (:632-716) W for ALL cells from the control genes.  The current state supplies alpha and gmean; wt_ctl: n_ctl
  * weights (best.wtctl); W_init: N x k (zeros with the Wsub rows filled in, :635-636); W_med/W_mad: colMedians/colMads of
  * Wsub (:653-654); max_sweeps = 8, tol = 1e-5 in the reference (:709-712).  W_out (N x k, may be NULL) and "W". */

@@ -73,3 +73,144 @@ def cap_psi(psi):
     lp = np.log(psi)
     cap = np.exp(rstats.r_median(lp) + 3.0 * rstats.r_mad(lp))                  # :766-768
     return np.where(psi > cap, cap, psi)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# F3 + F4: the subsample fit (R/fastruvIIInb.R:223-623), nbatch == 1, no pseudo-cells, ortho.W = FALSE.
+# Injection seams: U0 (irlba on RM_Z, :228), psi_idx (sample(), :218) and psi_fn (estimateDisp.par, :273-311,:569-575).
+# --------------------------------------------------------------------------------------------------------------
+def _row_avg(Z, grp, m):
+    return np.stack([Z[:, grp == j].mean(axis=1) for j in range(m)], axis=1)          # rowAvg (:857-865)
+
+
+def _row_wt_avg(Z, Wm, grp, m, lam):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.stack([(Z[:, grp == j] * Wm[:, grp == j]).sum(axis=1) / (Wm[:, grp == j].sum(axis=1) + lam) for j in range(m)], axis=1)
+
+
+def _clamp_cols(A):
+    A = A.copy()
+    med, mad = rstats.r_median(A, axis=0), rstats.r_mad(A, axis=0)
+    for i in range(A.shape[1]):
+        hi, lo = med[i] + 4 * mad[i], med[i] - 4 * mad[i]
+        A[A[:, i] > hi, i] = hi
+        A[A[:, i] < lo, i] = lo
+    return A
+
+
+def _seq_ridge_W(Zc, alpha_c, wt, lambda_a):
+    """:447-457 (and :247-254 with wt = 1): sequential ridge regressions of Z.c on alpha.c[, j]."""
+    k = alpha_c.shape[1]
+    W = np.zeros((Zc.shape[1], k))
+    Zc = Zc.copy()
+    for j in range(k):
+        if j > 0:
+            Zc = Zc - np.outer(alpha_c[:, j - 1], W[:, j - 1])
+        aw = alpha_c[:, j] * wt
+        W[:, j] = (Zc.T @ aw) / (lambda_a + aw @ alpha_c[:, j])
+    return W
+
+
+def _cell_loglik(Y, lmu, psi):
+    from . import nmath
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        t = nmath.dnbinom_mu_log(Y, (1.0 / psi)[:, None], np.exp(lmu))
+    t = np.where(np.isfinite(t), t, nmath.LOG_DBL_MIN)
+    return t.sum(axis=0)                                                                # per CELL (:334-346)
+
+
+def fast_fit_sub(Ysub, grp, ctl, k, U0, psi_fn, psi_idx, lambda_a=0.01, lambda_b=16.0, step_fac=0.5, inner_maxit=50,
+                 outer_maxit=25, trace=None):
+    """Returns dict(alpha, gmean, Mb, Wsub, psi, wt_ctl, logl)."""
+    Y = np.asarray(Ysub, dtype=np.float64)
+    G, ns = Y.shape
+    m = int(grp.max()) + 1
+    Z = np.log(Y + 1.0)                                                                 # :224
+    gmean = Z.mean(axis=1)
+    alpha = Z @ U0 @ np.linalg.inv(U0.T @ U0 + lambda_a * np.eye(k))                    # :230 (chol2inv)
+    alpha = _clamp_cols(alpha)                                                          # :233-238
+    Wsub = _clamp_cols(_seq_ridge_W(Z[ctl] - gmean[ctl, None], alpha[ctl], np.ones(ctl.sum()), lambda_a))   # :239-262
+    Mb = _row_avg(Z - alpha @ Wsub.T - gmean[:, None], grp, m)                          # :270 (lambda ignored: rowAvg)
+    Mb[ctl] = 0.0
+    offs = alpha @ Wsub.T + Mb[:, grp]
+    psi = psi_fn(Y[:, psi_idx], offs[:, psi_idx])                                       # :273-311
+    psi = np.where(np.isnan(psi), 0.0, psi)
+    conv, it_outer, logl_outer = False, 0, []
+    while not conv:
+        it_outer += 1
+        logl_beta = []
+        lmu = gmean[:, None] + Mb[:, grp] + alpha @ Wsub.T
+        with np.errstate(over="ignore", divide="ignore"):
+            sig_inv = 1.0 / (np.exp(-lmu) + psi[:, None])
+        wt_ctl = sig_inv[ctl].mean(axis=1)                                              # :331
+        loglik = _cell_loglik(Y, lmu, psi)
+        step = np.ones(ns)                                                              # :350
+        best = dict(W=Wsub, psi=psi, a=alpha, Mb=Mb, gmean=gmean, wtctl=wt_ctl)
+        it, halving, conv_beta = 1, 0, False
+        while not conv_beta:
+            lmu = gmean[:, None] + Mb[:, grp] + alpha @ Wsub.T
+            with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+                mu = np.exp(lmu)
+                sig_inv = 1.0 / (np.exp(-lmu) + psi[:, None])
+                Z = lmu + ((Y + 0.01) / (mu + 0.01) - 1.0) * step[None, :]              # :379
+            RM_Z = Z - _row_avg(Z, grp, m)[:, grp]                                      # :386-387
+            RM_W = Wsub - _row_avg(Wsub.T, grp, m).T[grp]
+            alpha_old = alpha
+            wt_cell = sig_inv.mean(axis=0)                                              # :405
+            p98 = rstats.r_quantile7(wt_cell, [0.98])[0]
+            wt_cell = np.where(wt_cell >= p98, p98, wt_cell)
+            b = (RM_Z * wt_cell[None, :]) @ RM_W
+            alpha = b @ np.linalg.inv((RM_W * wt_cell[:, None]).T @ RM_W + lambda_a * np.eye(k))   # :411
+            if not np.isfinite(alpha).all():
+                alpha = alpha_old
+            alpha = _clamp_cols(alpha)                                                  # :421-426
+            wt_ctl = sig_inv[ctl].mean(axis=1)                                          # :445
+            Wsub = _seq_ridge_W(Z[ctl] - gmean[ctl, None], alpha[ctl], wt_ctl, lambda_a)   # :443-457
+            Zres = Z - alpha @ Wsub.T - Mb[:, grp]
+            gmean = (Zres * sig_inv).sum(axis=1) / sig_inv.sum(axis=1)                  # :478-480
+            Zres = Z - alpha @ Wsub.T - gmean[:, None]
+            Mb_old = Mb
+            Mb = _row_wt_avg(Zres, sig_inv, grp, m, lambda_b)                           # :488
+            Mb[ctl] = 0.0
+            if np.isnan(Mb).any():
+                Mb = Mb_old.copy()
+            Mb = np.where(np.isfinite(Mb), Mb, 0.0)
+            Mb = _clamp_cols(Mb.T).T                                                    # :499-505
+            lmu = gmean[:, None] + Mb[:, grp] + alpha @ Wsub.T
+            loglik_tmp = _cell_loglik(Y, lmu, psi)
+            s_old, s_new = loglik.sum(), loglik_tmp.sum()
+            degener = bool(s_old > s_new) if np.isfinite(s_old) and np.isfinite(s_new) else True
+            rec = dict(outer=it_outer, iter=it, degener=degener, logl_new=s_new)
+            if degener:                                                                 # :535-545
+                step = np.where(loglik > loglik_tmp, step * step_fac, step)
+                Wsub, alpha, Mb, psi, gmean, wt_ctl = best["W"], best["a"], best["Mb"], best["psi"], best["gmean"], best["wtctl"]
+                halving += 1
+                if halving >= 3:
+                    loglik_tmp = loglik
+                    degener = False
+            if not degener:
+                loglik = loglik_tmp
+                logl_beta.append(loglik.sum())
+                best = dict(W=Wsub, psi=psi, a=alpha, Mb=Mb, gmean=gmean, wtctl=wt_ctl)
+                it += 1
+                halving = 0
+            rec["accepted"] = not degener
+            if trace is not None:
+                trace.append(rec)
+            conv_logl = it > 2 and (logl_beta[-1] - logl_beta[-2]) / abs(logl_beta[-2]) < 1e-4
+            conv_beta = it >= inner_maxit or conv_logl
+        updt = True
+        if it_outer > 1:
+            updt = abs(logl_outer[-1] - loglik.sum()) / abs(logl_outer[-1]) > 1e-8
+        offs = best["a"] @ best["W"].T + best["Mb"][:, grp]
+        if updt:
+            pn = psi_fn(Y[:, psi_idx], offs[:, psi_idx])
+            psi = np.where(np.isfinite(pn), pn, psi)
+        Wsub, alpha, Mb, gmean = best["W"], best["a"], best["Mb"], best["gmean"]
+        best["psi"] = psi
+        lmu = gmean[:, None] + Mb[:, grp] + alpha @ Wsub.T
+        logl_outer.append(_cell_loglik(Y, lmu, psi).sum())
+        if it_outer > 1:
+            conv = (logl_outer[-1] - logl_outer[-2]) / abs(logl_outer[-2]) < 1e-4 or it_outer >= outer_maxit
+    return dict(alpha=best["a"], gmean=best["gmean"], Mb=best["Mb"], Wsub=best["W"], psi=psi, wt_ctl=best["wtctl"],
+                logl=np.array(logl_outer))

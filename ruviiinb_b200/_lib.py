@@ -23,6 +23,7 @@ SYMBOLS = [
     "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_zinb_pi0", "ruvnb_snapshot_best",
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp", "ruvnb_estimate_disp_ex",
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
+    "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
 ]
 
 
@@ -105,6 +106,11 @@ def load():
     lib.ruvnb_fast_W_all.argtypes = [vp, C.c_int, C.c_double, vp, vp, vp, vp, C.c_int, C.c_double, vp, ip, dp]
     lib.ruvnb_fast_Mb_all.argtypes = [vp, C.c_double, vp, C.c_int64, vp]
     lib.ruvnb_fast_cap_psi.argtypes = [vp, C.c_int64]
+    lib.ruvnb_fast_init.argtypes = [vp, C.POINTER(Opts), vp]
+    lib.ruvnb_fast_begin_outer.argtypes = [vp, C.POINTER(Opts), dp]
+    lib.ruvnb_fast_iteration.argtypes = [vp, C.POINTER(Opts), dp, ip]
+    lib.ruvnb_fast_halve_steps.argtypes = [vp, C.POINTER(Opts)]
+    lib.ruvnb_fast_accept.argtypes = [vp]
     for s in SYMBOLS:
         f = getattr(lib, s)
         if f.restype is C.c_int and s not in ("ruvnb_abi_version",):
@@ -171,6 +177,7 @@ class Context:
         self._ck(self.lib.ruvnb_set_design(self.h, G, N, m, _ptr(grp), _ptr(ctl), _ptr(zi), g0, g1))
         self.G, self.N, self.m, self.g0, self.g1 = G, N, m, g0, g1
         self.Gl = g1 - g0
+        self.n_ctl = int(np.asarray(ctl).astype(bool).sum())
 
     def upload_counts(self, Y, Yctl=None, layout="gene_major"):
         """Y: local rows, int32.  layout 'gene_major' = C-order (Gl, N); 'cell_major' = R's column-major."""
@@ -204,7 +211,8 @@ class Context:
     # ---- state ------------------------------------------------------------------------------
     def _shape(self, name):
         return {"W": (self.N, self.k), "alpha": (self.Gl, self.k), "alpha_dev": (self.Gl, self.k),
-                "Mb": (self.Gl, self.m)}.get(name, (self.Gl,))
+                "Mb": (self.Gl, self.m), "cell_loglik": (self.N,), "cell_step": (self.N,),
+                "wt_ctl": (self.n_ctl,)}.get(name, (self.Gl,))
 
     def set_state(self, name, a, k=0):
         if name == "W":
@@ -297,6 +305,29 @@ class Context:
         mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
         self._ck(self.lib.ruvnb_get_res(self.h, int(kind), int(block_size), _ptr(mb), _ptr(out)))
         return out
+
+    # ---- fastruvIII.nb subsample fit (F3/F4) ------------------------------------------------------
+    def fast_init(self, opts, U0):
+        U0 = np.asfortranarray(U0, dtype=np.float64)
+        self.k = U0.shape[1]
+        self._ck(self.lib.ruvnb_fast_init(self.h, C.byref(opts), _ptr(U0)))
+
+    def fast_begin_outer(self, opts):
+        t = C.c_double()
+        self._ck(self.lib.ruvnb_fast_begin_outer(self.h, C.byref(opts), C.byref(t)))
+        return t.value
+
+    def fast_iteration(self, opts):
+        t = C.c_double()
+        bad = (C.c_int * 3)()
+        self._ck(self.lib.ruvnb_fast_iteration(self.h, C.byref(opts), C.byref(t), bad))
+        return t.value, list(bad)
+
+    def fast_halve_steps(self, opts):
+        self._ck(self.lib.ruvnb_fast_halve_steps(self.h, C.byref(opts)))
+
+    def fast_accept(self):
+        self._ck(self.lib.ruvnb_fast_accept(self.h))
 
     def fast_W_all(self, W_init, wt_ctl, W_med, W_mad, lambda_a=0.01, max_sweeps=8, tol=1e-5):
         """F5 (R/fastruvIIInb.R:632-716): returns (W, sweeps, crit)."""

@@ -150,6 +150,146 @@ def makeSCE(obj, cData=None, batch=None, assays=("pearson", "logPAC")):
     return sce
 
 
+def _estimate_disp_subset(Ysub, grp, ctl, alpha, W, Mb, cols, k, device):
+    """estimateDisp.par(Ysub[, cols], design = 1, offset = (alpha W' + Mb[, grp])[, cols]) (R/fastruvIIInb.R:273-311,569-575)
+    on a second context that holds only those columns."""
+    cols = np.asarray(cols)
+    g = grp[cols]
+    present, gc = np.unique(g, return_inverse=True)       # replicate groups that occur among the psi cells
+    opts = _lib.default_opts(k=int(k))
+    with _lib.Context(device) as c2:
+        c2.set_design(Ysub.shape[0], len(cols), gc.astype(np.int32), ctl)
+        c2.upload_counts(np.ascontiguousarray(Ysub[:, cols], dtype=np.int32))
+        c2.set_state("W", W[cols])
+        c2.set_state("alpha", alpha)
+        c2.set_state("Mb", Mb[:, present])
+        try:
+            c2.estimate_disp_ex(opts)
+        except _lib.RuvnbError:
+            return np.full(Ysub.shape[0], np.nan)         # tryCatch(..., error = function(e) rep(NA, ngene))
+        return c2.get_state("psi")
+
+
+def fastruvIII_nb_subfit(Ysub, Msub, ctl, k=2, lambda_a=0.01, lambda_b=16, step_fac=0.5, inner_maxit=50, outer_maxit=25,
+                         U0=None, psi_idx=None, psi=None, device=0, seed=0, trace=None):
+    """The subsample fit of `fastruvIII.nb` (R/fastruvIIInb.R:223-623) on the already-subsampled cells (every cell of
+    Msub annotated).  U0: the k right singular vectors of RM_Z (irlba, :228) -- computed by a dense SVD when None;
+    psi_idx: the <= 100 cells used for the dispersion (:215-221) -- drawn with NumPy when None; psi: injected dispersion
+    schedule (list of G-vectors) instead of estimateDisp.  Returns dict(alpha, gmean, Mb, Wsub, psi, wt_ctl, logl)."""
+    Ysub = np.ascontiguousarray(Ysub, dtype=np.int32)
+    G, ns = Ysub.shape
+    Msub = np.asarray(Msub).astype(bool)
+    if (Msub.sum(axis=1) != 1).any():
+        raise ValueError("every subsampled cell must belong to exactly one replicate group")
+    grp = np.argmax(Msub, axis=1).astype(np.int32)
+    ctl = np.asarray(ctl, bool)
+    rng = np.random.default_rng(seed)
+    if psi_idx is None:
+        psi_idx = np.sort(rng.choice(ns, size=min(100, int(round(0.5 * ns))), replace=False))    # :218
+    if U0 is None:
+        Z = np.log(Ysub + 1.0)
+        m = int(grp.max()) + 1
+        zbar = np.stack([Z[:, grp == j].mean(axis=1) for j in range(m)], axis=1)
+        _, _, vt = np.linalg.svd(Z - zbar[:, grp], full_matrices=False)
+        U0 = vt[:k].T.copy()
+    opts = _lib.default_opts(k=int(k), lambda_a=float(lambda_a), lambda_b=float(lambda_b), step_fac=float(step_fac),
+                             inner_maxit=int(inner_maxit), outer_maxit=int(outer_maxit))
+    calls = {"i": 0}
+
+    def new_psi(ctx):
+        if psi is not None:
+            i = min(calls["i"], len(psi) - 1)
+            calls["i"] += 1
+            return np.asarray(psi[i], dtype=np.float64)
+        return _estimate_disp_subset(Ysub, grp, ctl, ctx.get_state("alpha"), ctx.get_state("W"), ctx.get_state("Mb"), psi_idx, k, device)
+
+    with _lib.Context(device) as ctx:
+        ctx.set_design(G, ns, grp, ctl)
+        ctx.upload_counts(Ysub)
+        ctx.fast_init(opts, U0)                                                              # F3
+        p0 = new_psi(ctx)
+        ctx.set_state("psi", np.where(np.isnan(p0), 0.0, p0))                               # :311
+        conv, it_outer, logl_outer = False, 0, []
+        while not conv:                                                                      # :319
+            it_outer += 1
+            logl_beta = []
+            s_old = ctx.fast_begin_outer(opts)
+            ctx.snapshot_best()                                                              # :352
+            it, halving, conv_beta = 1, 0, False
+            while not conv_beta:
+                s_new, bad = ctx.fast_iteration(opts)
+                degener = (not (np.isfinite(s_old) and np.isfinite(s_new))) or s_old > s_new   # :533-534
+                rec = dict(outer=it_outer, iter=it, degener=degener, logl_new=s_new)
+                if degener:
+                    ctx.fast_halve_steps(opts)                                               # :538-539
+                    ctx.restore_best()
+                    halving += 1
+                    if halving >= 3:
+                        degener = False                                                      # loglik.tmp <- loglik
+                else:
+                    ctx.fast_accept()
+                    s_old = s_new
+                if not degener:
+                    logl_beta.append(s_old)
+                    ctx.snapshot_best()
+                    it += 1
+                    halving = 0
+                rec["accepted"] = not degener
+                if trace is not None:
+                    trace.append(rec)
+                conv_logl = it > 2 and (logl_beta[-1] - logl_beta[-2]) / abs(logl_beta[-2]) < 1e-4
+                conv_beta = it >= inner_maxit or conv_logl
+            updt = True
+            if it_outer > 1:
+                updt = abs(logl_outer[-1] - s_old) / abs(logl_outer[-1]) > 1e-8
+            ctx.restore_best()
+            if updt:
+                pn = new_psi(ctx)
+                cur = ctx.get_state("psi")
+                ctx.set_state("psi", np.where(np.isfinite(pn), pn, cur))                     # :577
+            logl_outer.append(ctx.fast_begin_outer(opts))                                    # :588-604
+            if it_outer > 1:
+                conv = (logl_outer[-1] - logl_outer[-2]) / abs(logl_outer[-2]) < 1e-4 or it_outer >= outer_maxit
+        ctx.snapshot_best()
+        return {"alpha": ctx.get_state("alpha"), "gmean": ctx.get_state("gmean"), "Mb": ctx.get_state("Mb"),
+                "Wsub": ctx.get_state("W"), "psi": ctx.get_state("psi"), "wt_ctl": ctx.get_state("wt_ctl"),
+                "logl": np.array(logl_outer), "psi_idx": psi_idx}
+
+
+def fastruvIII_nb(Y, M, ctl, k=2, lambda_a=0.01, lambda_b=16, step_fac=0.5, inner_maxit=50, outer_maxit=25, pCells_touse=0.2,
+                  block_size=5000, subsamples=None, U0=None, psi_idx=None, device=0, seed=0):
+    """`fastruvIII.nb` (R/fastruvIIInb.R:29-792), nbatch == 1, no pseudo-cells: stratified subsample of the annotated
+    cells (<= 3000, :118-137; NumPy RNG unless `subsamples` is given), the subsample fit, then W for all cells, Mb.all and
+    the psi cap.  Returns the reference's `out` list as a dict (the SCE packaging is makeSCE)."""
+    Y = np.ascontiguousarray(Y, dtype=np.int32)
+    M = np.asarray(M).astype(bool)
+    annotated = M.sum(axis=1) > 0
+    if annotated.mean() < 0.01:
+        raise ValueError("Less than 1% of cells have replicate annotation")
+    if (M.sum(axis=0) == 0).any():
+        raise ValueError("Each column of M matrix must have at least one non-zero entry")
+    rng = np.random.default_rng(seed)
+    if subsamples is None:
+        p = min(pCells_touse, 3000.0 / annotated.sum())                                      # :118-123
+        subsamples = np.sort(np.concatenate([rng.choice(np.where(M[:, j])[0], size=int(np.ceil(p * M[:, j].sum())), replace=False)
+                                             for j in range(M.shape[1])]))
+    subsamples = np.asarray(subsamples)
+    with _lib.Context(device) as ctx:                      # Winsorize on the full data (:81-95), then slice the subsample
+        ctx.set_design(Y.shape[0], Y.shape[1], np.where(annotated, np.argmax(M, axis=1), 0).astype(np.int32), np.asarray(ctl, bool))
+        ctx.upload_counts(Y)
+        ctx.winsorize()
+        Yw = ctx.get_counts()
+    keep = (Yw > 0).sum(axis=1) > 0
+    Yw, ctlk = Yw[keep], np.asarray(ctl, bool)[keep]
+    sub = fastruvIII_nb_subfit(Yw[:, subsamples], M[subsamples], ctlk, k=k, lambda_a=lambda_a, lambda_b=lambda_b, step_fac=step_fac,
+                               inner_maxit=inner_maxit, outer_maxit=outer_maxit, U0=U0, psi_idx=psi_idx, device=device, seed=seed)
+    out = fastruvIII_nb_finish(Yw, M, ctlk, sub["alpha"], sub["gmean"], sub["psi"], sub["Mb"], sub["Wsub"], subsamples, sub["wt_ctl"],
+                               lambda_a=lambda_a, lambda_b=lambda_b, block_size=block_size, device=device)
+    out["logl"] = sub["logl"]
+    out["zero_genes"] = ~keep
+    return out
+
+
 def fastruvIII_nb_finish(Y, M, ctl, alpha, gmean, psi, Mb_sub, Wsub, subsamples, wt_ctl, lambda_a=0.01, lambda_b=16,
                          block_size=5000, device=0):
     """The full-data tail of `fastruvIII.nb` (R/fastruvIIInb.R:625-792) given the subsample fit (alpha, gmean, psi,

@@ -17,6 +17,7 @@
 #include "res.cuh"
 #include "zinb.cuh"
 #include "fast.cuh"
+#include "fastfit.cuh"
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------
@@ -52,6 +53,7 @@ struct StateSet {  // one parameter set on device
   // Huber scale of THIS parameter set, written by the log-likelihood sweep (certificate) and completed by the
   // exact path: +Inf = every weight provably 1, 0 = not evaluated yet, else mad(signdev)/0.6745
   double* sigma = nullptr;
+  double* wtctl = nullptr;  // fastruvIII.nb subsample fit: wt.ctl = rowMeans(sig.inv[ctl,]) of this parameter set (best.wtctl)
   double* psi_w = nullptr;  // ZINB: the dispersion the last E-step (wt.zinb update) used -- R/ruvIIInb.R:262,465,502
   bool sig_valid = false;   // sigma was produced for the parameters currently held
   bool maybe_active = false; // some rows went through the exact path: their sigma may be finite (live Huber weights)
@@ -107,6 +109,12 @@ struct ruvnb_ctx {
   const double* ytab_psi = nullptr; long long ytab_ver = -1, psi_ver = 0;  // which psi the tables were built from
   int *w_fail = nullptr;         // [1 + Np] fast-W failures: count, then positions
   int *cert_diag = nullptr;      // [8] certificate failure reasons (ruvnb_cert_diag)
+  // fastruvIII.nb subsample fit (fastfit.cuh), allocated by ruvnb_fast_init
+  double *ff_Z = nullptr, *ff_SI = nullptr, *ff_ZS = nullptr, *ff_sirow = nullptr, *ff_wtcell = nullptr, *ff_step = nullptr,
+         *ff_cll = nullptr, *ff_cll_tmp = nullptr, *ff_b = nullptr, *ff_Ginv = nullptr, *ff_alpha_c = nullptr, *ff_A = nullptr, *ff_ones = nullptr;
+  uint8_t* ff_ctlmask = nullptr;
+  int* ff_ctl_rows_idx = nullptr;
+  bool ff_ready = false;
   // ZINB (zinb.cuh)
   bool zinb_on = false;          // opts.zinb && some cell is flagged zero-inflated
   uint8_t* d_zinf = nullptr;     // [Np] zero-inflated cells, permuted like the counts

@@ -1569,3 +1569,12 @@ __global__ void __launch_bounds__(256) k_count_big(const int32_t* Yp, int rows, 
   c = __reduce_add_sync(FULL, c);
   if (lane == 0) nbig[row] = c;
 }
+
+__global__ void k_scale_vec(double* x, long long n, double f) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= f;
+}
+__global__ void k_count_nan(const double* x, long long n, int* count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && x[i] != x[i]) atomicAdd(count, 1);
+}
