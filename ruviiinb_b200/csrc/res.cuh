@@ -189,7 +189,12 @@ __global__ void __launch_bounds__(256) k_sel_hist(const double* slab, long long 
       bool dup = false;  // targets sharing a prefix share a histogram (the first one's)
 #pragma unroll
       for (int u = 0; u < t; ++u) dup |= (pf[u] == pf[t]);
-      if (!dup && kp == pf[t]) atomicAdd(&sh[t * SEL_BINS + d], 1u);
+      if (dup) continue;   // block-uniform
+      // warp-aggregated update: the first levels put most of a warp into a handful of bins
+      const bool ok = kp == pf[t];
+      const unsigned act = __activemask();
+      const unsigned peers = __match_any_sync(act, ok ? d : 0xffffu + (threadIdx.x & 31));
+      if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[t * SEL_BINS + d], (unsigned)__popc(peers));
     }
   }
   __syncthreads();

@@ -95,3 +95,29 @@ def test_csr_upload_equals_dense():
         ctx.set_design(Y.shape[0], Y.shape[1], truth["grp"], ctl)
         ctx.upload_counts_csr(csr.indptr, csr.indices, csr.data)
         assert np.array_equal(ctx.get_counts(), Y)
+
+
+@pytest.mark.parametrize("G,N,k,m,n_ctl", [(40, 130, 8, 2, 9), (33, 257, 1, 5, 3), (24, 4100, 4, 33, 8)])
+def test_one_iteration_edge_shapes(G, N, k, m, n_ctl):
+    """k at its maximum (8), N just past a chunk boundary, very few control genes, more groups than a warp has lanes."""
+    from tests.parity import one_iteration_case
+    res = one_iteration_case(G=G, N=N, k=k, m=m, n_ctl=n_ctl, seed=300 + k, gmean_mu=0.5)
+    _check(res, tol=1e-8)
+
+
+def test_argument_errors_are_reported_not_crashed():
+    from ruviiinb_b200 import _lib, synth
+    Y, M, ctl, truth = synth.make_counts(20, 200, 2, 3, 5, seed=1)
+    with _lib.Context(0) as ctx:
+        with pytest.raises(_lib.RuvnbError, match="no counts|set_design|W not set|state"):
+            ctx.loglik(_lib.default_opts(k=2))
+        grp_bad = truth["grp"].copy(); grp_bad[grp_bad == 1] = 0      # replicate group 1 has no cell
+        with pytest.raises(_lib.RuvnbError, match="has no cell"):
+            ctx.set_design(20, 200, np.where(grp_bad == 2, 2, grp_bad), ctl)
+    with _lib.Context(0) as ctx:
+        ctx.set_design(20, 200, truth["grp"], ctl)
+        ctx.upload_counts(Y)
+        with pytest.raises(_lib.RuvnbError, match="outside 1..8"):
+            ctx.set_state("W", np.zeros((200, 9)))
+        with pytest.raises(_lib.RuvnbError, match="W not set"):
+            ctx.irls_iteration(_lib.default_opts(k=2))

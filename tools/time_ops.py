@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Wall-clock of the operators that are NOT on bench.py's line, at BASELINE.json config-2 scale (20k genes x 100k cells,
+k = 5): Winsorize, the dispersion step, get.res (Pearson / PAC, one 5000-cell block streamed at a time) and the
+fastruvIII.nb full-data passes.  Prints one JSON object; run on a B200 (`gpurun -- python tools/time_ops.py`)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+from ruviiinb_b200 import _lib  # noqa: E402
+
+
+def main():
+    import torch
+    G, N, k, m, n_ctl = bench.WORKLOADS["cfg2_nb_20kx100k"] if len(sys.argv) < 2 else bench.WORKLOADS[sys.argv[1]]
+    dev = torch.device("cuda", 0)
+    tp = bench.truth_params(G, N, k, m, n_ctl)
+    Yh = torch.empty((G, N), dtype=torch.int32, pin_memory=True).numpy()
+    bench.gen_rows_gpu(tp, np.arange(G), Yh, dev)
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    opts = _lib.default_opts(k=k)
+    out = {"workload": f"{G} x {N}, k={k}, m={m}, n_ctl={n_ctl}"}
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        out[name + "_s"] = round(time.perf_counter() - t0, 4)
+        return r
+
+    with _lib.Context(0) as ctx:
+        ctx.set_design(G, N, tp["grp"], tp["ctl"])
+        timed("upload_counts_8GB", lambda: ctx.upload_counts(Yh))
+        timed("winsorize", lambda: ctx.winsorize())
+        ctx.set_state("W", tp["W0"])
+        timed("init_coef", lambda: ctx.init_coef(opts))
+        ctx.set_state("psi", tp["psi"])
+        for _ in range(6):
+            ctx.irls_iteration(opts); ctx.accept()
+        d = timed("estimate_disp", lambda: ctx.estimate_disp_ex(opts))
+        out["estimate_disp_common"] = d["common"]; out["estimate_disp_prior_df"] = d["prior_df"]
+        timed("disp_newton", lambda: ctx.disp_newton(opts, maxit=30))
+        # get.res: time the first two 5000-cell blocks' worth by running on a 10000-cell problem slice is not possible
+        # on a resident context, so time the whole pass and report per-block figures
+        res = np.empty((G, N), dtype=np.float64, order="F")
+        import ctypes as C
+        for kind, nm in ((1, "get_res_pearson"), (2, "get_res_logcounts"), (3, "get_res_pac")):
+            timed(nm, lambda: ctx._ck(ctx.lib.ruvnb_get_res(ctx.h, kind, 5000, None, res.ctypes.data_as(C.c_void_p))))
+            out[nm + "_Melem_per_s"] = round(G * N / out[nm + "_s"] / 1e6, 1)
+        annot = np.where(np.arange(N) % 10 == 0, tp["grp"], -1).astype(np.int32)
+        timed("fast_Mb_all", lambda: ctx._ck(ctx.lib.ruvnb_fast_Mb_all(ctx.h, 16.0, annot.ctypes.data_as(C.c_void_p), 5000, res.ctypes.data_as(C.c_void_p))))
+        Wt = ctx.get_state("W")
+        sub = np.arange(0, N, 40)
+        W_init = np.zeros((N, k)); W_init[sub] = Wt[sub]
+        med = np.median(Wt[sub], axis=0); mad = 1.4826 * np.median(np.abs(Wt[sub] - med), axis=0)
+        W, sweeps, crit = timed("fast_W_all", lambda: ctx.fast_W_all(W_init, np.ones(n_ctl), med, mad))
+        out["fast_W_all_sweeps"] = sweeps
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
