@@ -937,12 +937,12 @@ __global__ void k_w_scale(double* W, long long Np, int K, const double* sumsq, c
 // (= forward substitution on the lower triangle of sum w a a').
 // ------------------------------------------------------------------------------------------------
 struct CtlPack {            // control-gene parameters, gathered (and, when sharded, all-reduced)
-  const double* gmean;      // [n_ctl]   old gmean
-  const double* psi;        // [n_ctl]
-  const double* step;       // [n_ctl]
-  const double* alpha_old;  // [n_ctl][K]
-  const double* alpha_new;  // [n_ctl][K]
-  const double* Mb;         // [n_ctl][m] old Mb
+  const double* __restrict__ gmean;      // [n_ctl]   old gmean
+  const double* __restrict__ psi;        // [n_ctl]
+  const double* __restrict__ step;       // [n_ctl]
+  const double* __restrict__ alpha_old;  // [n_ctl][K]
+  const double* __restrict__ alpha_new;  // [n_ctl][K]
+  const double* __restrict__ Mb;         // [n_ctl][m] old Mb
   const double* pi0;        // [n_ctl] ZINB only
   const double* psi_w;      // [n_ctl] ZINB only
   const uint8_t* zinf;      // [Np] or nullptr

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) k_sel_hist(const double* slab, long long 
       // warp-aggregated update: the first levels put most of a warp into a handful of bins
       const bool ok = kp == pf[t];
       const unsigned act = __activemask();
-      const unsigned peers = __match_any_sync(act, ok ? d : 0xffffu + (threadIdx.x & 31));
+      const unsigned peers = __match_any_sync(act, ok ? d : 0xffffu);   // one shared dummy: match cost grows with distinct values
       if (ok && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[t * SEL_BINS + d], (unsigned)__popc(peers));
     }
   }

@@ -62,7 +62,7 @@ __device__ unsigned long long group_select_kth(int len, long long kth, Get get, 
       int i = i0 + tid;
       unsigned long long key = 0;
       bool ok = (i < len) && get(i, key) && ((key & pmask) == prefix);
-      int b = ok ? (int)((key >> shift) & 255ull) : 256 + (tid & 31);  // distinct dummy per lane
+      int b = ok ? (int)((key >> shift) & 255ull) : 256;  // one shared dummy for the lanes that sit out (match cost grows with distinct values)
       // warp-aggregated histogram update: one atomic per distinct bucket in the warp
       unsigned peers = __match_any_sync(FULL, b);
       if (ok && (__ffs(peers) - 1) == (tid & 31)) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
@@ -169,7 +169,7 @@ __device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         bool ok = (i0 + q * RS_NT < len) && (kx[q] & pmask) == prefix;
-        int b = ok ? (int)((kx[q] >> shift) & (unsigned long long)(nb - 1)) : nb + lane;
+        int b = ok ? (int)((kx[q] >> shift) & (unsigned long long)(nb - 1)) : nb;   // one shared dummy for the lanes that sit out
         unsigned peers = __match_any_sync(FULL, b);
         if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
       }

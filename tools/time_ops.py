@@ -49,7 +49,7 @@ def main():
         timed("disp_newton", lambda: ctx.disp_newton(opts, maxit=30))
         # get.res: time the first two 5000-cell blocks' worth by running on a 10000-cell problem slice is not possible
         # on a resident context, so time the whole pass and report per-block figures
-        res = np.empty((G, N), dtype=np.float64, order="F")
+        res = np.zeros((G, N), dtype=np.float64, order="F")   # touched: the first write of fresh pages would be timed otherwise
         import ctypes as C
         for kind, nm in ((1, "get_res_pearson"), (2, "get_res_logcounts"), (3, "get_res_pac")):
             timed(nm, lambda: ctx._ck(ctx.lib.ruvnb_get_res(ctx.h, kind, 5000, None, res.ctypes.data_as(C.c_void_p))))
@@ -62,6 +62,36 @@ def main():
         med = np.median(Wt[sub], axis=0); mad = 1.4826 * np.median(np.abs(Wt[sub] - med), axis=0)
         W, sweeps, crit = timed("fast_W_all", lambda: ctx.fast_W_all(W_init, np.ones(n_ctl), med, mad))
         out["fast_W_all_sweeps"] = sweeps
+    # BASELINE.json config 3: ZINB, k = 3, 10k features x 50k samples, >= 90 % zeros, CSR upload, every cell zero-inflated
+    import scipy.sparse as sp
+    G3, N3, k3, m3, nc3 = 10000, 50000, 3, 20, 1000
+    rng = np.random.Generator(np.random.PCG64(bench.SEED + 1))
+    from ruviiinb_b200 import synth
+    tp3 = bench.truth_params(G3, N3, k3, m3, nc3, seed=bench.SEED + 1)
+    tp3["gmean"] = np.clip(-2.5 + rng.standard_normal(G3), -4.0, 5.0)
+    Y3 = np.empty((G3, N3), dtype=np.int32)
+    bench.gen_rows_gpu(tp3, np.arange(G3), Y3, dev)
+    pi0 = rng.beta(2.0, 5.0, size=G3)
+    Y3[rng.random(Y3.shape, dtype=np.float32) < pi0[:, None].astype(np.float32)] = 0
+    out["cfg3_zero_fraction"] = float((Y3 == 0).mean())
+    csr = sp.csr_matrix(Y3)
+    o3 = _lib.default_opts(k=k3, zinb=1)
+    with _lib.Context(0) as ctx:
+        ctx.set_design(G3, N3, tp3["grp"], tp3["ctl"], zeroinf=np.ones(N3, bool))
+        timed("cfg3_upload_csr", lambda: ctx.upload_counts_csr(csr.indptr, csr.indices, csr.data))
+        ctx.set_state("W", tp3["W0"])
+        ctx.init_coef(o3)
+        ctx.set_state("psi", tp3["psi"])
+        timed("cfg3_zinb_pi0_init", lambda: ctx.zinb_pi0(o3))
+        ctx.loglik(o3)
+        ctx.irls_iteration(o3); ctx.accept()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.irls_iteration(o3); ctx.accept()
+        torch.cuda.synchronize()
+        out["cfg3_zinb_iteration_s"] = round((time.perf_counter() - t0) / 3, 4)
+        out["cfg3_zinb_gene_fits_per_s"] = round(G3 / out["cfg3_zinb_iteration_s"], 1)
+        timed("cfg3_estimate_disp_weighted", lambda: ctx.estimate_disp_ex(o3))
     print(json.dumps(out))
 
 
