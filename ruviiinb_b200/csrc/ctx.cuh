@@ -62,6 +62,8 @@ struct StateSet {  // one parameter set on device
 struct ruvnb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // side stream: the few rows with live Huber weights run beside the certified bulk
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   long long launches = 0;
   std::vector<void*> allocs;

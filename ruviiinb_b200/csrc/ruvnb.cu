@@ -30,6 +30,8 @@ int ruvnb_create(ruvnb_ctx** out, int device) {
     return RUVNB_ECUDA;
   }
   for (int i = 0; i < RUVNB_NKERN; ++i) { cudaEventCreate(&ctx->kev[i][0]); cudaEventCreate(&ctx->kev[i][1]); }
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;
   return RUVNB_OK;
 }
@@ -43,6 +45,9 @@ void ruvnb_destroy(ruvnb_ctx* ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
   for (int i = 0; i < RUVNB_NKERN; ++i) { if (ctx->kev[i][0]) cudaEventDestroy(ctx->kev[i][0]); if (ctx->kev[i][1]) cudaEventDestroy(ctx->kev[i][1]); }
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -794,12 +799,19 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     if (ctx->zinb_on) {
       LAUNCH_ROWS_NW((k_pass1<KT, true, P1_NW>), P1_NW, 2, Gl, geom(ctx, Gl, nullptr), st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
     } else {
-      RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
-      LAUNCH_ROWS_NW((k_pass1<KT, false, P1_NW>), P1_NW, 2, Gl, gi, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      // the (few) rows with live Huber weights go FIRST, on the side stream: a row is one warp walking 100k cells, so a
+      // handful of them after the bulk would add a whole row-walk (2.5 ms at cfg 2) to every iteration
       if (hub) {
         RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        cudaStream_t main_ = ctx->stream; ctx->stream = ctx->stream2;
         LAUNCH_ROWS_NW((k_pass1<KT, true, P1_NW>), P1_NW, 2, Gl, gf, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+        ctx->stream = main_;
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
       }
+      RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
+      LAUNCH_ROWS_NW((k_pass1<KT, false, P1_NW>), P1_NW, 2, Gl, gi, st, ctx->RMW, c.sigma, kh, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS);
+      if (hub) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
     ctx->launch_parts = 1;
     if (P > 1) {
@@ -909,12 +921,17 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     if (ctx->zinb_on) {
       LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, geom(ctx, Gl, nullptr), st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
     } else {
-      RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
-      LAUNCH_ROWS((k_pass2<KT, false>), 2, Gl, gi, st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
       if (hub) {
         RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        cudaStream_t main_ = ctx->stream; ctx->stream = ctx->stream2;
         LAUNCH_ROWS((k_pass2<KT, true>), 2, Gl, gf, st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+        ctx->stream = main_;
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
       }
+      RowGeom gi = geom(ctx, Gl, ctx->list_inf); gi.nrows_dev = ctx->part_counts;
+      LAUNCH_ROWS((k_pass2<KT, false>), 2, Gl, gi, st, n.W, n.alpha, c.sigma, kh, ctx->S0, ctx->S1);
+      if (hub) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
     ctx->launch_parts = 1;
     if (P > 1) {
