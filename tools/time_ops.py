@@ -49,7 +49,8 @@ def main():
         timed("disp_newton", lambda: ctx.disp_newton(opts, maxit=30))
         # get.res: time the first two 5000-cell blocks' worth by running on a 10000-cell problem slice is not possible
         # on a resident context, so time the whole pass and report per-block figures
-        res = np.zeros((G, N), dtype=np.float64, order="F")   # touched: the first write of fresh pages would be timed otherwise
+        res = np.empty((G, N), dtype=np.float64, order="F")
+        res.fill(1.0)   # really touch the pages (np.zeros maps them lazily): first-touch faults would be timed otherwise
         import ctypes as C
         for kind, nm in ((1, "get_res_pearson"), (2, "get_res_logcounts"), (3, "get_res_pac")):
             timed(nm, lambda: ctx._ck(ctx.lib.ruvnb_get_res(ctx.h, kind, 5000, None, res.ctypes.data_as(C.c_void_p))))
