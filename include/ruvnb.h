@@ -97,8 +97,8 @@ void ruvnb_destroy(ruvnb_ctx* ctx);
 const char* ruvnb_last_error(const ruvnb_ctx* ctx);
 long long ruvnb_kernel_launches(const ruvnb_ctx* ctx);
 /* Device time of the Y-streaming sweep kernels, measured with CUDA events on the library's own stream
- * (bench.py's roofline line).  which: 0 devstats (Huber certificate sweep), 1 pass1 (Gram/score),
- * 2 w_update (per-cell), 3 pass2 (group sums), 4 loglik, 5 exact-MAD (signdev + select).
+ * (bench.py's roofline line).  which: 0 unused (the Huber certificate now rides in the log-likelihood sweep),
+ * 1 pass1 (Gram/score), 2 w_update (per-cell), 3 pass2 (group sums), 4 loglik + certificate, 5 exact-MAD (signdev + select).
  * Accumulated since ruvnb_kernel_time_reset. */
 #define RUVNB_NKERN 6
 int ruvnb_kernel_time(const ruvnb_ctx* ctx, int which, double* ms_total, long long* launches);

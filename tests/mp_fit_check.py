@@ -44,10 +44,23 @@ def main():
         ctx.upload_counts(Yl, Yctl=Yctl)
         logl, recs, stats = ctx.fit_nb(opts, W0=W0, psi_inject=sched[:, g0:g1])
         got = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
+        # the dispersion step and get.res on the sharded context: both need quantities of ALL genes (the trend / prior of
+        # estimateDisp, the block-wise Pearson clip limits), gathered over NCCL
+        from oracle import edger, getres
+        grp = truth["grp"]
+        disp = ctx.estimate_disp_ex(opts)
+        psi_dev = ctx.get_state("psi")
+        ref_disp = edger.estimate_disp(Yf, ref["a"] @ ref["W"].T + ref["Mb"][:, grp])
+        ctx.set_state("psi", ref["psi"][g0:g1])
+        pear = ctx.get_res(1, block_size=512)
+        ref_pear = getres.get_res(dict(counts=Y, a=ref["a"], W=ref["W"], gmean=ref["gmean"], Mb=ref["Mb"][:, grp], psi=ref["psi"]),
+                                  getres.PEARSON, block_size=512)
     dec = [(r["outer"], r["iter"], r["degener"], r["accepted"]) for r in recs]
     refdec = [(r["outer"], r["iter"], int(r["degener"]), int(r["accepted"])) for r in trace]
     err = dict(W=relerr(got["W"], ref["W"]), alpha=relerr(got["alpha"], ref["a"][g0:g1]), gmean=relerr(got["gmean"], ref["gmean"][g0:g1]),
-               Mb=relerr(got["Mb"], ref["Mb"][g0:g1], floor=1e-6), logl=relerr(logl, ref["logl"]))
+               Mb=relerr(got["Mb"], ref["Mb"][g0:g1], floor=1e-6), logl=relerr(logl, ref["logl"]),
+               disp_common=abs(disp["common"] / ref_disp["common"] - 1), disp_psi=relerr(psi_dev, ref_disp["tagwise"][g0:g1]),
+               pearson=relerr(pear, ref_pear[g0:g1]) / 10)   # the two fits differ at 1e-7; Pearson is allowed 1e-5
     ok = dec == refdec and all(v < 1e-6 for v in err.values())
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
