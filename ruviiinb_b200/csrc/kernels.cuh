@@ -1119,66 +1119,100 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
   const bool inb = pos < pos_end;
   const int chunk = inb ? (int)(pos >> 7) : 0;
   const bool valid = inb && (int)(pos & (CH - 1)) < chunk_valid[chunk];
-  const int j = chunk_grp[chunk];
+  // the 64 positions of a CTA lie in one 128-cell chunk, hence in ONE replicate group: Mb[g, j] is a per-gene scalar here
+  const int j = chunk_grp[(int)(min(pos_begin + (long long)blockIdx.x * 64, pos_end - 1) >> 7)];
   double wv[K];
 #pragma unroll
   for (int l = 0; l < K; ++l) wv[l] = valid ? W_old[(long long)l * Np + pos] : 0.0;
+  // control-gene parameters are staged GT genes at a time in shared memory (they were ~12 dependent global loads per
+  // element): [0] gmean + Mb[g, j], [1] psi, [2] 1/psi, [3] step, [4] gmean, [5..) alpha_old, then alpha_new
+  constexpr int GT = 128, PW = 5 + 2 * K;
+  __shared__ double gp[GT][PW];
+  __shared__ const int32_t* rowp[GT];
+  auto stage = [&](int g0) {
+    __syncthreads();
+    for (int idx = tid; idx < GT * PW; idx += 256) {
+      const int t = idx / PW, f = idx - t * PW, gi = g0 + t;
+      double v = 0.0;
+      if (gi < n_ctl) {
+        if (f == 0) v = cp.gmean[gi] + cp.Mb[(long long)gi * m + j];
+        else if (f == 1) v = cp.psi[gi];
+        else if (f == 2) v = 1.0 / cp.psi[gi];
+        else if (f == 3) v = cp.step[gi];
+        else if (f == 4) v = cp.gmean[gi];
+        else if (f < 5 + K) v = cp.alpha_old[(long long)gi * K + (f - 5)];
+        else v = cp.alpha_new[(long long)gi * K + (f - 5 - K)];
+      }
+      gp[t][f] = v;
+    }
+    for (int t = tid; t < GT; t += 256) rowp[t] = (g0 + t < n_ctl) ? ctl_rows[g0 + t] : nullptr;
+    __syncthreads();
+  };
   // sweep A: max half deviance
   double hmax = 0.0; int bad = 0;
-  if (valid) {
-    for (int gi = slice; gi < n_ctl; gi += 4) {
-      int y = ctl_rows[gi][pos];
-      double lmu = cp.gmean[gi] + cp.Mb[(long long)gi * m + j];
+  for (int g0 = 0; g0 < n_ctl; g0 += GT) {
+    stage(g0);
+    if (valid) {
+      const int nt = min(GT, n_ctl - g0);
+      int ynext = slice < nt ? rowp[slice][pos] : 0;     // counts are fetched one gene ahead
+      for (int t = slice; t < nt; t += 4) {
+        const int y = ynext;
+        if (t + 4 < nt) ynext = rowp[t + 4][pos];
+        double lmu = gp[t][0];
 #pragma unroll
-      for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
-      double mu = fexp(lmu, mt.ex);
-      double r = 1.0 / cp.psi[gi];
-      double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, &mt);
-      hmax = fmax(hmax, fmax(h, 0.0));
-      bad |= !(h == h);
+        for (int l = 0; l < K; ++l) lmu = fma(gp[t][5 + l], wv[l], lmu);
+        const double mu = fexp(lmu, mt.ex), r = gp[t][2];
+        const double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)(g0 + t) * YT, &mt);
+        hmax = fmax(hmax, fmax(h, 0.0));
+        bad |= !(h == h);
+      }
     }
   }
   hmax = fmax(hmax, __shfl_xor_sync(FULL, hmax, 8)); hmax = fmax(hmax, __shfl_xor_sync(FULL, hmax, 16));
   bad |= __shfl_xor_sync(FULL, bad, 8); bad |= __shfl_xor_sync(FULL, bad, 16);
   const double C = MAD_CONST / 0.6745;
   const double mx = sqrt(2.0 * hmax);
-  const double t = mx / (kh * C) * (1.0 + 1e-9);
+  const double t_ = mx / (kh * C) * (1.0 + 1e-9);
   const double binw = mx / 64.0;
-  const bool certp = valid && !bad && mx > 0.0 && mx < 1.79769313486231570e308 && (2.0 * t < 0.98 * binw) && n_ctl < 65536;
+  const bool certp = valid && !bad && mx > 0.0 && mx < 1.79769313486231570e308 && (2.0 * t_ < 0.98 * binw) && n_ctl < 65536;
   const double scale = certp ? 64.0 / mx : 0.0;
   // sweep B: histogram + Gram / score with weight sig.inv
   double acc[NACC];
 #pragma unroll
   for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-  if (valid) {
-    unsigned* myh = hist[warp][cell];
-    for (int gi = slice; gi < n_ctl; gi += 4) {
-      int y = ctl_rows[gi][pos];
-      double yd = (double)y;
-      double gm = cp.gmean[gi];
-      double lmu = gm + cp.Mb[(long long)gi * m + j];
+  unsigned* myh = hist[warp][cell];
+  for (int g0 = 0; g0 < n_ctl; g0 += GT) {
+    stage(g0);
+    if (valid) {
+      const int nt = min(GT, n_ctl - g0);
+      int ynext = slice < nt ? rowp[slice][pos] : 0;
+      for (int t = slice; t < nt; t += 4) {
+        const int y = ynext;
+        if (t + 4 < nt) ynext = rowp[t + 4][pos];
+        const double yd = (double)y;
+        double lmu = gp[t][0];
 #pragma unroll
-      for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
-      double mu = fexp(lmu, mt.ex);
-      double psi = cp.psi[gi];
-      if (certp) {
-        double r = 1.0 / psi;
-        double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)gi * YT, &mt);
-        double d = nb_signdev_from_half(h, yd, mu);
-        int b = (int)floor((d + mx) * scale);
-        b = b < 0 ? 0 : (b > 127 ? 127 : b);
-        atomicAdd(&myh[b >> 1], (b & 1) ? 65536u : 1u);
-      }
-      double s, q;
-      nb_siginv_ratio(yd, mu, psi, &s, &q);
-      double z = fma(cp.step[gi], q - 1.0, lmu) - gm;  // (Z - gmean)[ctl], :381
-      int idx = 0;
+        for (int l = 0; l < K; ++l) lmu = fma(gp[t][5 + l], wv[l], lmu);
+        const double mu = fexp(lmu, mt.ex);
+        if (certp) {
+          const double r = gp[t][2];
+          const double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)(g0 + t) * YT, &mt);
+          const double d = nb_signdev_from_half(h, yd, mu);
+          int b = (int)floor((d + mx) * scale);
+          b = b < 0 ? 0 : (b > 127 ? 127 : b);
+          atomicAdd(&myh[b >> 1], (b & 1) ? 65536u : 1u);
+        }
+        double sI, q;
+        nb_siginv_ratio(yd, mu, gp[t][1], &sI, &q);
+        const double z = fma(gp[t][3], q - 1.0, lmu) - gp[t][4];  // (Z - gmean)[ctl], :381
+        int idx = 0;
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        double wa = s * cp.alpha_new[(long long)gi * K + i];
-        acc[KK + i] = fma(wa, z, acc[KK + i]);
+        for (int i = 0; i < K; ++i) {
+          const double wa = sI * gp[t][5 + K + i];
+          acc[KK + i] = fma(wa, z, acc[KK + i]);
 #pragma unroll
-        for (int jx = 0; jx <= i; ++jx) { acc[idx] = fma(wa, cp.alpha_new[(long long)gi * K + jx], acc[idx]); ++idx; }
+          for (int jx = 0; jx <= i; ++jx) { acc[idx] = fma(wa, gp[t][5 + K + jx], acc[idx]); ++idx; }
+        }
       }
     }
   }
