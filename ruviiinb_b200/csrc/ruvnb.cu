@@ -611,6 +611,7 @@ static int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   RET(ensure_state(ctx, o->k));
   if (!ctx->have_W) return ctx->fail(RUVNB_ESTATE, "W not set: the initial W (irlba in the reference, R/ruvIIInb.R:167) is injected with ruvnb_set_state(\"W\")");
   ctx->zinb_on = o->zinb && ctx->any_zeroinf;   // ZINB only matters for cells flagged zeroinf (:237,254)
+  ctx->launch_parts = 1;                         // a failed call must not leave a sweep's part count behind
   CK(cudaSetDevice(ctx->device));
   return RUVNB_OK;
 }
