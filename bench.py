@@ -204,6 +204,9 @@ def main():
     ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--full-fit", action="store_true",
+                    help="also run the WHOLE ruvIII.nb fit (ruvnb_fit_nb: Winsorize, init, dispersion estimation, alternating IRLS to "
+                         "convergence) on the workload and report its wall time under \"full_fit\"")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,6 +346,28 @@ def main():
                "d2h_bytes_per_step": int(d2h * world / args.steps),
                "what": "on an existing context: upload_counts (pinned host int32 -> HBM, permuted) + W0/psi upload + init_coef + loglik + K irls_iteration (each returns its log-likelihood) + get_state(W, alpha, gmean, Mb); wall clock, max over ranks"}
 
+    # ---- optional: the whole fit, host buffers in, converged parameters out ---------------------------------------
+    full_fit = None
+    if args.full_fit:
+        ctx = make_ctx()
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload_counts(Yh, Yctl=Yctl)
+        ctx.winsorize()
+        logl_outer, recs, st = ctx.fit_nb(opts, W0=tp["W0"])
+        res = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
+        barrier()
+        dt = time.perf_counter() - t0
+        ctx.close()
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        full_fit = {"wall_seconds": float(tdt.item()), "outer_iterations": st["n_outer"], "inner_iterations": st["n_inner"],
+                    "inner_loop_seconds": st["inner_seconds"], "dispersion_seconds": st["disp_seconds"],
+                    "gene_fits_per_s_inner_loops": G * st["n_inner"] / st["inner_seconds"], "logl_outer": [float(x) for x in logl_outer],
+                    "corr_W_truth": [float(abs(np.corrcoef(res["W"][:, l], tp["W"][:, l])[0, 1])) for l in range(k)] if rank == 0 else None,
+                    "what": "upload (pinned host int32) + Winsorize + ruvnb_fit_nb with estimateDisp at every psi refresh (initial W = the bench start state) + read-back; wall clock, max over ranks"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,6 +409,8 @@ def main():
             "gpu_launches": int(launches), "exact_mad_rows_per_step": exact_rows_steps, "exact_mad_cells_per_step": exact_cells_steps, "cert_fail_reasons": cert_diag, "roofline": roofline, "logl_trace": logls, "datagen_seconds": t_gen}
     if e2e:
         line["e2e"] = e2e
+    if full_fit:
+        line["full_fit"] = full_fit
     if world == 1 and not args.no_cpu_baseline:
         v, desc, _ = cpu_sample_run(args.workload, 2, 1)
         line["cpu_baseline"] = dict(value=v, unit="gene-fits/s", **desc)

@@ -129,6 +129,7 @@ struct ruvnb_ctx {
          *dp_tabG = nullptr, *dp_tabRg = nullptr, *dp_lgr_grid = nullptr, *dp_zeros = nullptr, *dp_beta1 = nullptr, *dp_phi_row = nullptr,
          *dp_dev = nullptr, *dp_tabR2 = nullptr;
   int* dp_flag = nullptr;
+  int* dp_done = nullptr;
   bool dp_ready = false;
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare

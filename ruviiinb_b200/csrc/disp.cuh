@@ -34,6 +34,8 @@ struct DispArgs {
   int* notconv;             // set to 1 when some |step| >= tol
   double n;                 // number of cells
   const double* gm_real;    // [Gl] gmean of the parameter set: the ZINB weights wt.zinb need mu = exp(offset + gmean)
+  int* done;                // [Gl] rows whose ND intercepts have all converged: later sweeps skip them (edgeR stops each
+                            // fit at |step| < tol; rows converge after 4-8 steps, a few stragglers need 15-20)
 };
 
 // ---- start values ---------------------------------------------------------------------------------------------
@@ -102,6 +104,7 @@ struct OpDispNR {
       phi[d] = a.phi_row ? a.phi_row[row] : a.phi_grid[d];
       dl[d] = 0.0; info[d] = 0.0;
     }
+    if (a.done && a.done[row]) live = false;
     yadd = 0.0; escale = 1.0;
     if (a.emean) { double pcm = a.prior_count / a.emean[row]; yadd = pcm; escale = fma(2.0, pcm, 1.0); }
   }
@@ -115,7 +118,7 @@ struct OpDispNR {
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double mu = eb[d] * E;
-      double w = wzv / fma(mu, phi[d], 1.0);
+      double w = wzv * frcp(fma(mu, phi[d], 1.0));   // 1 + phi mu >= 1: inside frcp's range
       dl[d] = fma(yd - mu, w, dl[d]);
       info[d] = fma(mu, w, info[d]);
     }
@@ -141,7 +144,9 @@ struct OpDispNR {
         if (step == step) { *bp += step; nc |= !(fabs(step) < a.tol); }
       }
     }
-    if (nc) atomicExch(a.notconv, 1);
+    nc = __shfl_sync(FULL, nc, 0);
+    if (nc) { if ((threadIdx.x & 31) == 0) atomicExch(a.notconv, 1); }
+    else if (a.done && (threadIdx.x & 31) == 0) a.done[row] = 1;
   }
 };
 template <int K, int ND>
@@ -190,7 +195,7 @@ struct OpDispAPL {
       double t = -(yd + r[d]) * flog(mr, g.mt->rc, g.mt->lc);
       if (y > 0) t += (y < YT) ? tg[d][y] : nb_big_lgterm(yd, r[d], lgr_grid[d], g.mt);
       ll[d] = fma(wzv, t, ll[d]);
-      ww[d] = fma(wzv * mu * r[d], 1.0 / mr, ww[d]);   // w mu / (1 + phi mu)
+      ww[d] = fma(wzv * mu * r[d], frcp(mr), ww[d]);   // w mu / (1 + phi mu)
     }
   }
   template <bool FULLCHUNK>

@@ -1209,6 +1209,7 @@ static int disp_ensure(ruvnb_ctx* ctx) {
   RET(dev_alloc(ctx, &ctx->dp_tabG, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_tabRg, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_lgr_grid, DISP_NG));
   RET(dev_alloc(ctx, &ctx->dp_zeros, Gl)); RET(dev_alloc(ctx, &ctx->dp_beta1, Gl)); RET(dev_alloc(ctx, &ctx->dp_phi_row, Gl));
   RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 1));
+  RET(dev_alloc(ctx, &ctx->dp_done, Gl));
   CK(cudaMemsetAsync(ctx->dp_zeros, 0, (size_t)Gl * 8, ctx->stream));
   double grid[DISP_NG];
   for (int i = 0; i < DISP_NG; ++i) grid[i] = 0.1 * exp2(-10.0 + (double)i);  // spline.disp, R/estimateDisp.par.R:33-35
@@ -1228,6 +1229,8 @@ static GeneState<K> disp_state(ruvnb_ctx* ctx, const StateSet& s) {
 }
 // Newton-Raphson to convergence (edgeR glm_one_group: |step| < 1e-10, at most 50 iterations) for columns d0..d0+nd-1
 static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
+  a.done = ctx->dp_done;
+  CK(cudaMemsetAsync(ctx->dp_done, 0, (size_t)ctx->Gl * sizeof(int), ctx->stream));
   for (int it = 0; it < 50; ++it) {
     CK(cudaMemsetAsync(ctx->dp_flag, 0, sizeof(int), ctx->stream));
     DISPATCH_K(ctx->K, {
