@@ -156,6 +156,13 @@ int ruvnb_get_counts(ruvnb_ctx* ctx, int32_t* Y_out);
 int ruvnb_set_state(ruvnb_ctx* ctx, const char* name, const double* host, int k);
 int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host);
 
+/* H1  initial W (R/ruvIIInb.R:160-168): the k leading right singular vectors of log(Y[ctl,]/rowMeans(Y[ctl,]) + 1), by
+ *     subspace iteration on the resident control rows (the matrix is never formed) + one Rayleigh-Ritz rotation; each
+ *     vector signed so that its largest entry is positive.  The reference uses irlba (random start, tol 1e-5), so its own
+ *     W0 is defined only up to that: parity runs inject W0 instead.  Sets "W"; W_out (N x k), sv_out (k singular values)
+ *     and iters_out may be NULL.  max_iter <= 0 -> 200, tol <= 0 -> 1e-12 (relative change of the Ritz values). */
+int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, double* W_out, double* sv_out, int* iters_out);
+
 /* ---- step operators: one per reference helper seam ------------------------------------------ */
 /* H2  get.coef.wt (R/ruvIIInb.R:181-198,704-706): WLS of log(Y+1) on [1,W] with weights Y+1;
  *     sets gmean, alpha, alpha_dev, Mb = 0. */

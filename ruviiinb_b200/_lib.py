@@ -20,7 +20,7 @@ SYMBOLS = [
     "ruvnb_last_exact_cells", "ruvnb_selftest_math", "ruvnb_measure_fp64", "ruvnb_cert_diag",
     "ruvnb_comm_unique_id", "ruvnb_comm_init", "ruvnb_set_design",
     "ruvnb_upload_counts_dense", "ruvnb_upload_counts_csr", "ruvnb_winsorize", "ruvnb_get_counts", "ruvnb_set_state",
-    "ruvnb_get_state", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_zinb_pi0", "ruvnb_snapshot_best",
+    "ruvnb_get_state", "ruvnb_init_W", "ruvnb_init_coef", "ruvnb_loglik", "ruvnb_irls_iteration", "ruvnb_zinb_pi0", "ruvnb_snapshot_best",
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp", "ruvnb_estimate_disp_ex",
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
     "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
@@ -89,6 +89,7 @@ def load():
     lib.ruvnb_get_counts.argtypes = [vp, vp]
     lib.ruvnb_set_state.argtypes = [vp, cp, vp, C.c_int]
     lib.ruvnb_get_state.argtypes = [vp, cp, vp]
+    lib.ruvnb_init_W.argtypes = [vp, C.c_int, C.c_int, C.c_double, vp, vp, ip]
     lib.ruvnb_init_coef.argtypes = [vp, C.POINTER(Opts)]
     lib.ruvnb_loglik.argtypes = [vp, C.POINTER(Opts), dp]
     lib.ruvnb_irls_iteration.argtypes = [vp, C.POINTER(Opts), dp, ip]
@@ -227,6 +228,15 @@ class Context:
         return out
 
     # ---- operators ----------------------------------------------------------------------------
+    def init_W(self, k, max_iter=200, tol=1e-12):
+        """H1 (R/ruvIIInb.R:160-168) on the device; returns (W0 N x k, singular values, iterations) and sets "W"."""
+        self.k = int(k)
+        W = np.empty((self.N, self.k), dtype=np.float64, order="F")
+        sv = np.empty(self.k, dtype=np.float64)
+        it = C.c_int()
+        self._ck(self.lib.ruvnb_init_W(self.h, self.k, int(max_iter), float(tol), _ptr(W), _ptr(sv), C.byref(it)))
+        return W, sv, it.value
+
     def init_coef(self, opts):
         self._ck(self.lib.ruvnb_init_coef(self.h, C.byref(opts)))
 

@@ -35,9 +35,10 @@ def _as_logical_ctl(ctl, G, rownames=None):
 
 
 def init_W(Y, ctl, k):
-    """R/ruvIIInb.R:160-168: the k leading right singular vectors of log(Y[ctl,]/rowMeans(Y[ctl,]) + 1).  The reference
-    uses irlba (random start, arbitrary signs); here a dense eigen-decomposition of the n_ctl x n_ctl Gram with the sign of
-    each vector fixed so that its largest entry is positive."""
+    """Host check of `ruvnb_init_W` (R/ruvIIInb.R:160-168): the k leading right singular vectors of
+    log(Y[ctl,]/rowMeans(Y[ctl,]) + 1) by a dense eigen-decomposition of the n_ctl x n_ctl Gram, each vector signed so that
+    its largest entry is positive.  The fit itself uses the device routine (`Context.init_W`); this is kept for tests and
+    for callers that want to inject the same W0 on both sides of a comparison."""
     Yc = np.asarray(Y)[np.asarray(ctl, bool)].astype(np.float64)
     A = np.log(Yc / Yc.mean(axis=1, keepdims=True) + 1.0)
     w, U = np.linalg.eigh(A @ A.T)
@@ -91,7 +92,7 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
         ctx.winsorize()
         counts = ctx.get_counts()
         if W0 is None:
-            W0 = init_W(counts, ctlk, int(k))
+            W0, _, _ = ctx.init_W(int(k))        # H1 on the device (subspace iteration on the resident control rows)
         psi_inject = None if psi is None else np.atleast_2d(np.asarray(psi, dtype=np.float64))[:, keep]
         logl, recs, stats = ctx.fit_nb(opts, W0=np.asarray(W0, dtype=np.float64), psi_inject=psi_inject)
         out = {"counts": counts, "W": ctx.get_state("W"), "M": M, "ctl": ctlk, "logl": logl, "a": ctx.get_state("alpha"),

@@ -18,6 +18,7 @@
 #include "zinb.cuh"
 #include "fast.cuh"
 #include "fastfit.cuh"
+#include "svd.cuh"
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------

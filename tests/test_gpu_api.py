@@ -57,3 +57,22 @@ def test_api_argument_errors_mirror_stop():
         api.ruvIII_nb(Y, M, ctl, use_pseudosample=True)
     with pytest.raises(ValueError, match="unknown type"):
         api.get_res(dict(pi0=None, psi=np.ones(3)), type="foo")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 3])
+def test_init_W_device_matches_dense_svd(k):
+    """H1 (R/ruvIIInb.R:160-168): subspace iteration on the resident control rows against a dense LAPACK SVD."""
+    from ruviiinb_b200 import _lib, api, synth
+    Y, M, ctl, truth = synth.make_counts(300, 1700, 3, 4, 120, seed=97, gmean_mu=1.0)
+    ref = api.init_W(Y, ctl, k)
+    A = np.log(Y[ctl] / Y[ctl].mean(axis=1, keepdims=True) + 1.0)
+    sv_ref = np.linalg.svd(A, compute_uv=False)[:k]
+    with _lib.Context(0) as ctx:
+        ctx.set_design(Y.shape[0], Y.shape[1], truth["grp"], ctl)
+        ctx.upload_counts(Y)
+        W, sv, iters = ctx.init_W(k)
+        assert np.array_equal(ctx.get_state("W"), W)
+    assert np.allclose(sv, sv_ref, rtol=1e-9)
+    assert np.abs(W - ref).max() < 1e-6 * np.abs(ref).max(), (np.abs(W - ref).max(), iters)
+    assert np.allclose(W.T @ W, np.eye(k), atol=1e-10)
