@@ -160,7 +160,7 @@ int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host);
  *     subspace iteration on the resident control rows (the matrix is never formed) + one Rayleigh-Ritz rotation; each
  *     vector signed so that its largest entry is positive.  The reference uses irlba (random start, tol 1e-5), so its own
  *     W0 is defined only up to that: parity runs inject W0 instead.  Sets "W"; W_out (N x k), sv_out (k singular values)
- *     and iters_out may be NULL.  max_iter <= 0 -> 200, tol <= 0 -> 1e-12 (relative change of the Ritz values). */
+ *     and iters_out may be NULL.  max_iter <= 0 -> 100, tol <= 0 -> 1e-9 (relative change of the Ritz values, ~3e-5 on the vectors). */
 int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, double* W_out, double* sv_out, int* iters_out);
 
 /* ---- step operators: one per reference helper seam ------------------------------------------ */

@@ -228,7 +228,7 @@ class Context:
         return out
 
     # ---- operators ----------------------------------------------------------------------------
-    def init_W(self, k, max_iter=200, tol=1e-12):
+    def init_W(self, k, max_iter=0, tol=0.0):
         """H1 (R/ruvIIInb.R:160-168) on the device; returns (W0 N x k, singular values, iterations) and sets "W"."""
         self.k = int(k)
         W = np.empty((self.N, self.k), dtype=np.float64, order="F")

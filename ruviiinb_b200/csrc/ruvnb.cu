@@ -1904,8 +1904,8 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
   CK(cudaSetDevice(ctx->device));
   const int K = ctx->K, nc = ctx->n_ctl, KK = K * (K + 1) / 2; const long long Np = ctx->Np;
   if (nc < K) return ctx->fail(RUVNB_EARG, "init_W: %d control genes cannot carry %d factors", nc, K);
-  if (max_iter <= 0) max_iter = 200;
-  if (!(tol > 0)) tol = 1e-12;
+  if (max_iter <= 0) max_iter = 100;
+  if (!(tol > 0)) tol = 1e-9;   // on the Ritz values, i.e. ~3e-5 on the vectors: irlba's own tolerance is 1e-5
   double *rm = nullptr, *U = nullptr, *G = nullptr, *T = nullptr;
   CK(cudaMalloc((void**)&rm, (size_t)nc * 8)); CK(cudaMalloc((void**)&U, (size_t)nc * K * 8)); CK(cudaMalloc((void**)&G, KK * 8)); CK(cudaMalloc((void**)&T, K * K * 8));
   double* V = ctx->cur.W; double* V2 = ctx->nw.W;

@@ -71,7 +71,7 @@ def test_init_W_device_matches_dense_svd(k):
     with _lib.Context(0) as ctx:
         ctx.set_design(Y.shape[0], Y.shape[1], truth["grp"], ctl)
         ctx.upload_counts(Y)
-        W, sv, iters = ctx.init_W(k)
+        W, sv, iters = ctx.init_W(k, max_iter=400, tol=1e-13)
         assert np.array_equal(ctx.get_state("W"), W)
     assert np.allclose(sv, sv_ref, rtol=1e-9)
     assert np.abs(W - ref).max() < 1e-6 * np.abs(ref).max(), (np.abs(W - ref).max(), iters)
