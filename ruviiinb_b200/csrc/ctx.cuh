@@ -129,8 +129,14 @@ struct ruvnb_ctx {
   double *dp_beta = nullptr, *dp_beta0 = nullptr, *dp_rowsum = nullptr, *dp_emean = nullptr, *dp_l0 = nullptr, *dp_phi_grid = nullptr,
          *dp_tabG = nullptr, *dp_tabRg = nullptr, *dp_lgr_grid = nullptr, *dp_zeros = nullptr, *dp_beta1 = nullptr, *dp_phi_row = nullptr,
          *dp_dev = nullptr, *dp_tabR2 = nullptr;
-  int* dp_flag = nullptr;
+  double *dp_info = nullptr;                 // [Gl][21] Fisher information of the converged grid fits (Cox-Reid term)
+  double *dp_xs = nullptr, *dp_m0 = nullptr; // trend smoother scratch: [G] AveLogCPM sorted, [G][21] smoothed l0
+  int* dp_perm = nullptr;                    // [G]
+  int* dp_flag = nullptr;                    // [2]: some |step| >= tol; rows still iterating
   int* dp_done = nullptr;
+  int* dp_live = nullptr;                    // [Gl] list of the rows still iterating
+  int* dp_hist = nullptr;                    // [Gl][YT] count histogram of each row (valid while hist_ready)
+  bool hist_ready = false;
   bool dp_ready = false;
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare

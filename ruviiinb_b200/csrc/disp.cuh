@@ -27,13 +27,16 @@ struct DispArgs {
   const double* phi_grid;   // [ND] dispersions of this sweep, or nullptr
   const double* phi_row;    // [Gl] per-gene dispersion (ND == 1), or nullptr
   double* beta;             // [Gl][ldb] intercepts; this sweep uses columns d0 .. d0+ND-1
-  int ldb, d0;
+  int ldb, d0, ds;          // this sweep's columns are d0, d0 + ds, d0 + 2 ds, ... (ds = 3: every third grid point, so that
+                            // the next sweep's points start from a converged neighbour one grid step away)
   const double* emean;      // [Gl] mean_c exp(offset) (ave_log_cpm prior) or nullptr
   double prior_count;       // aveLogCPM: y + p_c, offset log(e^o + 2 p_c), p_c = prior_count e^o / mean e^o
   double tol;
   int* notconv;             // set to 1 when some |step| >= tol
   double n;                 // number of cells
   const double* gm_real;    // [Gl] gmean of the parameter set: the ZINB weights wt.zinb need mu = exp(offset + gmean)
+  double* info_out;         // [Gl][ldb] or nullptr: the sweep's Fisher information sum w mu / (1 + phi mu) per column -- at
+                            // convergence the Cox-Reid term of the APL (adjustedProfileLik: 0.5 log(X' W X), one column)
   int* done;                // [Gl] rows whose ND intercepts have all converged: later sweeps skip them (edgeR stops each
                             // fit at |step| < tol; rows converge after 4-8 steps, a few stragglers need 15-20)
 };
@@ -90,7 +93,9 @@ struct OpDispNR {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g; DispArgs a;
-  double eb[ND], phi[ND], dl[ND], info[ND];
+  // score = sum w (y - mu) / (1 + phi mu) = S1 - e^beta S2, information = e^beta S2, with S1 = sum w y / (1 + phi mu) and
+  // S2 = sum w E / (1 + phi mu), mu = e^beta E: per cell and dispersion one FMA for the denominator, the reciprocal, two FMAs
+  double eb[ND], ebphi[ND], dl[ND], info[ND];
   double yadd, escale, egm; bool live;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
@@ -98,10 +103,10 @@ struct OpDispNR {
     egm = g.zi ? exp(a.gm_real[row]) : 1.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-      double b = a.beta[(long long)row * a.ldb + a.d0 + d];
+      double b = a.beta[(long long)row * a.ldb + a.d0 + d * a.ds];
       eb[d] = exp(b);
       live |= (b > -1.79769313486231570e308) & (b < 1.79769313486231570e308);
-      phi[d] = a.phi_row ? a.phi_row[row] : a.phi_grid[d];
+      ebphi[d] = eb[d] * (a.phi_row ? a.phi_row[row] : a.phi_grid[d * a.ds]);
       dl[d] = 0.0; info[d] = 0.0;
     }
     if (a.done && a.done[row]) live = false;
@@ -115,12 +120,20 @@ struct OpDispNR {
     const double wzv = g.zi ? g.wz(y, E * egm, pos) : 1.0;
     double yd = fma(yadd, E, (double)y);
     E *= escale;
+    if (g.zi) {
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      double mu = eb[d] * E;
-      double w = wzv * frcp(fma(mu, phi[d], 1.0));   // 1 + phi mu >= 1: inside frcp's range
-      dl[d] = fma(yd - mu, w, dl[d]);
-      info[d] = fma(mu, w, info[d]);
+      for (int d = 0; d < ND; ++d) {
+        double w = wzv * frcp_nr(fma(E, ebphi[d], 1.0));
+        dl[d] = fma(yd, w, dl[d]);
+        info[d] = fma(E, w, info[d]);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        double w = frcp_nr(fma(E, ebphi[d], 1.0));   // 1 + phi mu >= 1: inside the seed's range
+        dl[d] = fma(yd, w, dl[d]);
+        info[d] = fma(E, w, info[d]);
+      }
     }
   }
   template <bool FULLCHUNK>
@@ -133,14 +146,19 @@ struct OpDispNR {
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
-    if (!live) return;
+    if (!live) {   // nothing to iterate on: out of the later sweeps' row lists
+      if (a.done && (threadIdx.x & 31) == 0) a.done[row] = 1;
+      return;
+    }
     bool nc = false;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double s1 = warp_sum(dl[d]), s2 = warp_sum(info[d]);
       if ((threadIdx.x & 31) == 0) {
-        double step = s1 / s2;
-        double* bp = a.beta + (long long)row * a.ldb + a.d0 + d;
+        s2 *= eb[d];
+        double step = (s1 - s2) / s2;
+        if (a.info_out) a.info_out[(long long)row * a.ldb + a.d0 + d * a.ds] = s2;
+        double* bp = a.beta + (long long)row * a.ldb + a.d0 + d * a.ds;
         if (step == step) { *bp += step; nc |= !(fabs(step) < a.tol); }
       }
     }
@@ -162,22 +180,29 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr(RowGeom geo, GeneSta
 // ---- adjusted profile likelihood for ND dispersions ---------------------------------------------------------------
 template <int K, int ND>
 struct OpDispAPL {
+  // log-lik of the row at dispersion 1/r and intercept beta:
+  //   sum_c w_c [ lgamma(y + r) - lgamma(r) - lgamma(y + 1) + y log mu + r log r - (y + r) log(mu + r) ]
+  // the lgamma term depends on the cell only through its count and w = 1 wherever y > 0 (wt.zinb only down-weights zeros),
+  // so for y < YT it is a dot product of the row's count histogram with the grid's table (row end); y log mu =
+  // y (beta + offset) is assembled at the row end too.  What is left per cell and dispersion is ONE logarithm.
+  // The Cox-Reid term 0.5 log(sum w mu / (1 + phi mu)) is the information the converged NR sweep left in a.info_out.
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g; DispArgs a;
   const double (*tg)[YT];   // shared: [ND][YT]
   const double* lgr_grid;   // [ND] lgamma(r_d)
-  double eb[ND], r[ND], ll[ND], ww[ND];
-  double syo, sy, sw, egm;  // sum w y offset, sum w y (y log mu = y (beta_d + offset) is assembled at the row end), sum w
+  const int* hist;          // [Gl][YT] cells of the row with count y (0 < y < YT)
+  double eb[ND], r[ND], ll[ND];
+  double syo, sy, sw, egm;  // sum w y offset, sum w y, sum w
   double* l0; int ld0;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
     egm = g.zi ? exp(a.gm_real[row]) : 1.0; sw = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-      eb[d] = exp(fmax(a.beta[(long long)row * a.ldb + a.d0 + d], -1e8));  // mglmOneWay: pmax(beta, -1e8)
-      r[d] = 1.0 / a.phi_grid[d];
-      ll[d] = 0.0; ww[d] = 0.0;
+      eb[d] = exp(fmax(a.beta[(long long)row * a.ldb + a.d0 + d * a.ds], -1e8));  // mglmOneWay: pmax(beta, -1e8)
+      r[d] = 1.0 / a.phi_grid[d * a.ds];
+      ll[d] = 0.0;
     }
     syo = 0.0; sy = 0.0;
   }
@@ -186,16 +211,19 @@ struct OpDispAPL {
     if (!m) return;
     double E = g.expm(off);
     double yd = (double)y;
-    const double wzv = g.zi ? g.wz(y, E * egm, pos) : 1.0;
-    syo = fma(yd * wzv, off, syo); sy = fma(yd, wzv, sy); sw += wzv;
+    syo = fma(yd, off, syo); sy += yd;
+    if (g.zi) {
+      const double wzv = g.wz(y, E * egm, pos);
+      sw += wzv;
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      double mu = eb[d] * E;
-      double mr = mu + r[d];
-      double t = -(yd + r[d]) * flog(mr, g.mt->rc, g.mt->lc);
-      if (y > 0) t += (y < YT) ? tg[d][y] : nb_big_lgterm(yd, r[d], lgr_grid[d], g.mt);
-      ll[d] = fma(wzv, t, ll[d]);
-      ww[d] = fma(wzv * mu * r[d], frcp(mr), ww[d]);   // w mu / (1 + phi mu)
+      for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]) * wzv, flog(fma(eb[d], E, r[d]), g.mt->rc, g.mt->lc), ll[d]);
+    } else {
+#pragma unroll
+      for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]), flog(fma(eb[d], E, r[d]), g.mt->rc, g.mt->lc), ll[d]);
+    }
+    if (y >= YT) {   // beyond the tables (rare): Stirling
+#pragma unroll
+      for (int d = 0; d < ND; ++d) ll[d] += nb_big_lgterm(yd, r[d], lgr_grid[d * a.ds], g.mt);
     }
   }
   template <bool FULLCHUNK>
@@ -207,30 +235,80 @@ struct OpDispAPL {
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
-    double tyo = warp_sum(syo), ty = warp_sum(sy), tw = warp_sum(sw);
+    double tyo = warp_sum(syo), ty = warp_sum(sy), tw = g.zi ? warp_sum(sw) : a.n;
+    const int lane = threadIdx.x & 31;
+    double hy[YT / 32];
+#pragma unroll
+    for (int q = 0; q < YT / 32; ++q) hy[q] = (double)hist[(long long)row * YT + q * 32 + lane];
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-      double s1 = warp_sum(ll[d]), s2 = warp_sum(ww[d]);
-      if ((threadIdx.x & 31) == 0) {
+      double t = ll[d];
+#pragma unroll
+      for (int q = 0; q < YT / 32; ++q) t = fma(hy[q], tg[d][q * 32 + lane], t);   // tg[d][0] = 0
+      double s1 = warp_sum(t);
+      if (lane == 0) {
         const double low = 1e-10;  // edgeR adj_coxreid low_value
+        double s2 = a.info_out[(long long)row * a.ldb + a.d0 + d * a.ds];
         double adj = 0.5 * log(s2 < low ? low : s2);
-        double beta = fmax(a.beta[(long long)row * a.ldb + a.d0 + d], -1e8);
+        double beta = fmax(a.beta[(long long)row * a.ldb + a.d0 + d * a.ds], -1e8);
         double ylogmu = ty > 0.0 ? fma(beta, ty, tyo) : 0.0;
-        l0[(long long)row * ld0 + a.d0 + d] = s1 + ylogmu + tw * r[d] * log(r[d]) - adj;   // tw = n when all weights are 1
+        l0[(long long)row * ld0 + a.d0 + d * a.ds] = s1 + ylogmu + tw * r[d] * log(r[d]) - adj;   // tw = n when all weights are 1
       }
     }
   }
 };
 template <int K, int ND>
 __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl(RowGeom geo, GeneState<K> st, DispArgs a, const double* tabG /* [ND][YT] */,
-                                                             const double* lgr_grid, double* l0, int ld0) {
+                                                             const double* lgr_grid, const int* hist, double* l0, int ld0) {
   extern __shared__ double smem[];
   __shared__ DispRowShared<K, ND> sh;
   if (threadIdx.x == 0) sh.base.wsets[0] = st.W;
-  for (int i = threadIdx.x; i < ND * YT; i += ROW_THREADS) (&sh.tg[0][0])[i] = tabG[i];
+  for (int i = threadIdx.x; i < ND * YT; i += ROW_THREADS) (&sh.tg[0][0])[i] = tabG[(long long)(i / YT) * a.ds * YT + (i % YT)];
   OpDispAPL<K, ND> op;
-  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.l0 = l0; op.ld0 = ld0;
+  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0;
   stream_rows<K, 1>(geo, &sh.base, op, smem);
+}
+
+// counts of each value 1 .. YT-1 in every row (pads hold -1): one CTA per row, shared-memory histogram.  Depends on the
+// counts only, so it is built once per upload / Winsorize.
+__global__ void __launch_bounds__(256) k_row_hist(const int32_t* __restrict__ Yp, long long Np, int* __restrict__ hist) {
+  __shared__ int h[YT];
+  const long long row = blockIdx.x;
+  for (int i = threadIdx.x; i < YT; i += 256) h[i] = 0;
+  __syncthreads();
+  const int4* p = reinterpret_cast<const int4*>(Yp + row * Np);   // Np is a multiple of CH = 128
+  for (long long i = threadIdx.x; i < Np / 4; i += 256) {
+    int4 v = p[i];
+    if ((unsigned)(v.x - 1) < (unsigned)(YT - 1)) atomicAdd(&h[v.x], 1);
+    if ((unsigned)(v.y - 1) < (unsigned)(YT - 1)) atomicAdd(&h[v.y], 1);
+    if ((unsigned)(v.z - 1) < (unsigned)(YT - 1)) atomicAdd(&h[v.z], 1);
+    if ((unsigned)(v.w - 1) < (unsigned)(YT - 1)) atomicAdd(&h[v.w], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < YT; i += 256) hist[row * YT + i] = h[i];
+}
+
+// rows with flag == 0 -> compact ascending list (one CTA, ordered scan): the NR sweeps after the bulk has converged
+__global__ void __launch_bounds__(1024) k_list_zero(int n, const int* flag, int* list, int* count) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int g0 = 0; g0 < n; g0 += 1024) {
+    int g = g0 + threadIdx.x;
+    bool f = g < n && flag[g] == 0;
+    unsigned bal = __ballot_sync(FULL, f);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int i = 0; i < w; ++i) off += wsum[i];
+    if (f) list[off + __popc(bal & ((1u << lane) - 1))] = g;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; base += t; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
 }
 
 // ---- NB deviance at a per-gene dispersion and intercept (prior d.f.) ------------------------------------------------

@@ -117,6 +117,19 @@ __host__ __device__ __forceinline__ double frcp(double x) {
 #endif
 }
 
+// 1/x to ~2^-58 (seed + the cubic step, no polish): for sums that only steer an iteration (Newton score / information)
+__host__ __device__ __forceinline__ double frcp_nr(double x) {
+#if defined(__CUDA_ARCH__)
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  double e = fma(-x, y0, 1.0);
+  double t = fma(e, e, e);
+  return fma(y0, t, y0);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // lgamma(x) for x >= 128 from its logarithm lx = log(x): Stirling series, truncation 1/(1680 x^7) < 2e-18
 __host__ __device__ __forceinline__ double lgamma_big(double x, double lx) {
   double ix = frcp(x), ix2 = ix * ix;

@@ -1,6 +1,7 @@
 // ruvnb.cu -- C ABI of libruvnb_b200 (include/ruvnb.h): context, data upload, the NB IRLS operators
 // and the whole-fit driver.  sm_100a only; no CPU fallback anywhere in this file.
 #include <stdlib.h>
+#include <chrono>
 #include "ctx.cuh"
 #include "winsor.cuh"
 
@@ -293,7 +294,7 @@ int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, cons
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false;
+  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false;
   return RUVNB_OK;
 }
 
@@ -339,7 +340,7 @@ int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false;
+  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false;
   return RUVNB_OK;
 }
 
@@ -362,7 +363,7 @@ int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out) {
   if (nonzero_out) CK(cudaMemcpyAsync(nonzero_out, d_nz, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(d_cap)); CK(cudaFree(d_nz));
-  ctx->cur.sig_valid = false; ctx->roworder_ready = false;
+  ctx->cur.sig_valid = false; ctx->roworder_ready = false; ctx->hist_ready = false;
   return RUVNB_OK;
 }
 
@@ -1195,6 +1196,34 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
 }  // extern "C"
 
 // ---- H3: dispersion (R/estimateDisp.par.R) ------------------------------------------------------------------------------
+// dst[r][d0 + i ds] = src[r * src_ld + src_col + i ds * (src_ld > 1)], i < nd: a start value per row (src_ld == 1) or the
+// converged neighbour column (src_ld == ld)
+__global__ void k_bcast_cols_strided(const double* src, int src_ld, int src_col, long long n, int ld, int d0, int ds, int nd, double* dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * nd) return;
+  long long r = i / nd; int d = (int)(i % nd);
+  double v = src_ld == 1 ? src[r] : src[r * src_ld + src_col + d * ds];
+  // an all-zero gene keeps -Inf; a neighbour that failed (NaN) falls back to nothing better: keep it
+  dst[r * ld + d0 + d * ds] = v;
+}
+// start value for a one-dispersion fit from the converged grid: the intercept is a smooth function of log(phi), so linear
+// interpolation between the two bracketing grid columns lands within ~1e-3 of the root (NR then needs 2-3 sweeps, not 8).
+// prior_count > 0: the aveLogCPM fit of y + p against log(e^o + 2p) -- shift the start as edgeR's own start is shifted.
+__global__ void k_beta_from_grid(const double* beta, const double* phi_grid, int ng, const double* phi_row, const double* emean,
+                                 double prior_count, int n, double* out) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double lp = log(phi_row[r]);
+  int d = 0;
+  while (d + 2 < ng && log(phi_grid[d + 1]) < lp) ++d;
+  const double l0 = log(phi_grid[d]), l1 = log(phi_grid[d + 1]);
+  double t = fmin(fmax((lp - l0) / (l1 - l0), 0.0), 1.0);
+  const double b0 = beta[(long long)r * ng + d], b1 = beta[(long long)r * ng + d + 1];
+  double b = (b0 == b1) ? b0 : fma(t, b1 - b0, b0);   // -Inf rows stay -Inf (no Inf - Inf)
+  if (!(b == b)) b = b0;
+  if (prior_count > 0.0) { double pcm = prior_count / emean[r]; b = log((exp(b) + pcm) / fma(2.0, pcm, 1.0)); }
+  out[r] = b;
+}
 __global__ void k_bcast_cols(const double* src, long long n, int ld, int d0, int nd, double* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * nd) return;
@@ -1208,8 +1237,10 @@ static int disp_ensure(ruvnb_ctx* ctx) {
   RET(dev_alloc(ctx, &ctx->dp_emean, Gl)); RET(dev_alloc(ctx, &ctx->dp_l0, Gl * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_phi_grid, DISP_NG));
   RET(dev_alloc(ctx, &ctx->dp_tabG, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_tabRg, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_lgr_grid, DISP_NG));
   RET(dev_alloc(ctx, &ctx->dp_zeros, Gl)); RET(dev_alloc(ctx, &ctx->dp_beta1, Gl)); RET(dev_alloc(ctx, &ctx->dp_phi_row, Gl));
-  RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 1));
-  RET(dev_alloc(ctx, &ctx->dp_done, Gl));
+  RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 2));
+  RET(dev_alloc(ctx, &ctx->dp_done, Gl)); RET(dev_alloc(ctx, &ctx->dp_live, Gl)); RET(dev_alloc(ctx, &ctx->dp_info, Gl * DISP_NG));
+  RET(dev_alloc(ctx, &ctx->dp_hist, Gl * YT));
+  RET(dev_alloc(ctx, &ctx->dp_xs, ctx->G)); RET(dev_alloc(ctx, &ctx->dp_m0, ctx->G * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_perm, ctx->G));
   CK(cudaMemsetAsync(ctx->dp_zeros, 0, (size_t)Gl * 8, ctx->stream));
   double grid[DISP_NG];
   for (int i = 0; i < DISP_NG; ++i) grid[i] = 0.1 * exp2(-10.0 + (double)i);  // spline.disp, R/estimateDisp.par.R:33-35
@@ -1231,39 +1262,73 @@ static GeneState<K> disp_state(ruvnb_ctx* ctx, const StateSet& s) {
 static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
   a.done = ctx->dp_done;
   CK(cudaMemsetAsync(ctx->dp_done, 0, (size_t)ctx->Gl * sizeof(int), ctx->stream));
+  const bool trace = getenv("RUVNB_TRACE_DISP") != nullptr;
+  // the bulk of the rows converges within 4-5 sweeps; from the third sweep on only the rows still iterating are launched
+  int nlive = ctx->Gl; const int* live = nullptr;
   for (int it = 0; it < 50; ++it) {
-    CK(cudaMemsetAsync(ctx->dp_flag, 0, sizeof(int), ctx->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    CK(cudaMemsetAsync(ctx->dp_flag, 0, 2 * sizeof(int), ctx->stream));
     DISPATCH_K(ctx->K, {
-      if (nd == DISP_ND) LAUNCH_ROWS((k_disp_nr<KT, DISP_ND>), 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), disp_state<KT>(ctx, s), a);
-      else LAUNCH_ROWS((k_disp_nr<KT, 1>), 1, ctx->Gl, geom(ctx, ctx->Gl, nullptr), disp_state<KT>(ctx, s), a);
+      if (nd == DISP_ND) LAUNCH_ROWS((k_disp_nr<KT, DISP_ND>), 1, nlive, geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
+      else LAUNCH_ROWS((k_disp_nr<KT, 1>), 1, nlive, geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
     });
     ctx->disp_nr_sweeps++;
-    CK(cudaMemcpyAsync(ctx->h_flags + 7, ctx->dp_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (it >= 2) { k_list_zero<<<1, 1024, 0, ctx->stream>>>(ctx->Gl, ctx->dp_done, ctx->dp_live, ctx->dp_flag + 1); CKL(); }
+    CK(cudaMemcpyAsync(ctx->h_flags + 6, ctx->dp_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_flags[7] == 0) break;
+    if (trace) {
+      std::vector<int> dn(ctx->Gl); long long nd_rows = 0;
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      CK(cudaMemcpy(dn.data(), ctx->dp_done, (size_t)ctx->Gl * sizeof(int), cudaMemcpyDeviceToHost));
+      for (int v : dn) nd_rows += v;
+      fprintf(stderr, "  disp NR (nd=%d) sweep %d: %.2f ms over %d rows, %lld of %d rows converged after it\n", nd, it, ms, nlive, nd_rows, ctx->Gl);
+    }
+    if (ctx->h_flags[6] == 0) break;
+    if (it >= 2) { nlive = ctx->h_flags[7]; live = ctx->dp_live; if (nlive <= 0) break; }
   }
+  return RUVNB_OK;
+}
+// count histogram of every row (the lgamma part of the grid log-likelihoods, disp.cuh OpDispAPL)
+static int ensure_hist(ruvnb_ctx* ctx) {
+  if (ctx->hist_ready) return RUVNB_OK;
+  k_row_hist<<<ctx->Gl, 256, 0, ctx->stream>>>(ctx->dY, ctx->Np, ctx->dp_hist); CKL();
+  ctx->hist_ready = true;
   return RUVNB_OK;
 }
 // l0 (device, [Gl][21] row-major), rowsum, emean, beta0 for the parameter set `s`
 static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
   RET(disp_ensure(ctx));
+  RET(ensure_hist(ctx));
   const int Gl = ctx->Gl;
   ctx->disp_nr_sweeps = 0;
+  CK(cudaMemsetAsync(ctx->dp_info, 0, (size_t)Gl * DISP_NG * 8, ctx->stream));   // all-zero genes are never iterated
   DISPATCH_K(ctx->K, {
     LAUNCH_ROWS(k_disp_init<KT>, 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), ctx->dp_beta0, ctx->dp_rowsum, ctx->dp_emean, (double)ctx->N,
                 s.gmean);
   });
-  for (int d0 = 0; d0 < DISP_NG; d0 += DISP_ND) {
-    k_bcast_cols<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta0, Gl, DISP_NG, d0, DISP_ND, ctx->dp_beta);
+  // three sweeps of seven interleaved grid points: {0,3,..,18}, {1,4,..,19}, {2,5,..,20}.  edgeR starts every fit from
+  // the same value (start = NULL, R/estimateDisp.par.R:107-110); the intercept is the unique root of a concave score, so
+  // starting the second and third sets from the converged neighbour one grid step below gives the same root (to the NR
+  // tolerance 1e-10) in about half the sweeps.
+  const int DS = DISP_NG / DISP_ND;   // 3
+  for (int c = 0; c < DS; ++c) {
+    if (c == 0) k_bcast_cols_strided<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta0, 1, 0, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
+    else k_bcast_cols_strided<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta, DISP_NG, c - 1, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
     CKL();
     DispArgs a;
-    a.phi_grid = ctx->dp_phi_grid + d0; a.phi_row = nullptr; a.beta = ctx->dp_beta; a.ldb = DISP_NG; a.d0 = d0;
+    a.phi_grid = ctx->dp_phi_grid + c; a.phi_row = nullptr; a.beta = ctx->dp_beta; a.ldb = DISP_NG; a.d0 = c; a.ds = DS;
     a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = (double)ctx->N; a.gm_real = s.gmean;
+    a.info_out = ctx->dp_info;
     RET(disp_nr(ctx, s, a, DISP_ND));
+    const auto t_apl = std::chrono::steady_clock::now();
     DISPATCH_K(ctx->K, {
-      LAUNCH_ROWS((k_disp_apl<KT, DISP_ND>), 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)d0 * YT,
-                  ctx->dp_lgr_grid + d0, ctx->dp_l0, DISP_NG);
+      LAUNCH_ROWS((k_disp_apl<KT, DISP_ND>), 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)c * YT,
+                  ctx->dp_lgr_grid + c, ctx->dp_hist, ctx->dp_l0, DISP_NG);
     });
+    if (getenv("RUVNB_TRACE_DISP")) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "  disp APL sweep %d: %.2f ms\n", c, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_apl).count());
+    }
   }
   return RUVNB_OK;
 }
@@ -1290,7 +1355,11 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
                            double* prior_df_out) {
   RET(check_ready(ctx, o));
   StateSet& s = ctx->cur;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
   RET(disp_grid(ctx, s));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double t_grid = now(); const int sweeps_grid = ctx->disp_nr_sweeps;
   const int Gl = ctx->Gl; const long long G = ctx->G, g0 = ctx->g0;
   const double N = (double)ctx->N;
   // gather l0 / rowsum of all genes on every rank (zero-padded sum over the ranks)
@@ -1319,19 +1388,16 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   for (int i : sel) for (int d = 0; d < DISP_NG; ++d) colsum[d] += l0[(size_t)i * DISP_NG + d];
   const double common = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, colsum));
   if (common_out) *common_out = common;
+  const double t_common = now();
   // AveLogCPM (:134): one-group fit of y + prior at the common dispersion
   {
     k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->dp_phi_row, Gl, common); CKL();
-    // start: log(sum (y + p)/(e^o + 2p) / n) = log((exp(beta0) + pcm) / (1 + 2 pcm)), pcm = prior.count / mean e^o
-    std::vector<double> b0(Gl), em(Gl);
-    CK(cudaMemcpyAsync(b0.data(), ctx->dp_beta0, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(em.data(), ctx->dp_emean, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int g = 0; g < Gl; ++g) { double pcm = 2.0 / em[g]; b0[g] = log((exp(b0[g]) + pcm) / (1.0 + 2.0 * pcm)); }
-    CK(cudaMemcpyAsync(ctx->dp_beta1, b0.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // edgeR's start is log(sum (y + p)/(e^o + 2p) / n) = log((exp(beta0) + pcm) / (1 + 2 pcm)), pcm = prior.count / mean e^o;
+    // the same shift of the grid's converged intercept at the common dispersion is closer to the (unique) root
+    k_beta_from_grid<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(ctx->dp_beta, ctx->dp_phi_grid, DISP_NG, ctx->dp_phi_row, ctx->dp_emean, 2.0, Gl, ctx->dp_beta1); CKL();
     DispArgs a;
-    a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0;
-    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean;
+    a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0; a.ds = 1;
+    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean; a.info_out = nullptr;
     RET(disp_nr(ctx, s, a, 1));
   }
   std::vector<double> alc(G, 0.0);
@@ -1347,6 +1413,7 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
       CK(cudaStreamSynchronize(ctx->stream));
     }
   }
+  const double t_alc = now(); const int sweeps_alc = ctx->disp_nr_sweeps;
   // trend: local-constant tricube smoother of l0 against AveLogCPM over the selected genes (:136-139, locfit stand-in)
   const double span = ns <= 50 ? 1.0 : 0.25 + 0.75 * sqrt(50.0 / (double)ns);  // edgeR::WLEB default
   const int q = std::min(ns, std::max(1, (int)ceil(span * (double)ns)));
@@ -1357,15 +1424,13 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   for (int i = 0; i < ns; ++i) { xs[i] = alc[sel[order[i]]]; perm[i] = sel[order[i]]; }
   std::vector<double> m0s((size_t)ns * DISP_NG);
   {
-    double *d_xs = nullptr, *d_m0 = nullptr, *d_l0g = nullptr; int* d_perm = nullptr;
-    CK(cudaMalloc((void**)&d_xs, (size_t)ns * 8)); CK(cudaMalloc((void**)&d_m0, (size_t)ns * DISP_NG * 8)); CK(cudaMalloc((void**)&d_perm, (size_t)ns * 4));
+    double *d_xs = ctx->dp_xs, *d_m0 = ctx->dp_m0, *d_l0g = nullptr; int* d_perm = ctx->dp_perm;   // ns <= G
     if (ctx->nranks > 1) d_l0g = tmpA; else d_l0g = ctx->dp_l0;
     CK(cudaMemcpyAsync(d_xs, xs.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_perm, perm.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, ctx->stream));
     k_tricube<<<ns, 128, 0, ctx->stream>>>(d_xs, d_perm, ns, q, d_l0g, DISP_NG, d_m0); CKL();
     CK(cudaMemcpyAsync(m0s.data(), d_m0, m0s.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaFree(d_xs)); CK(cudaFree(d_m0)); CK(cudaFree(d_perm));
   }
   // m0 back to gene order; trended dispersion (:140-145)
   std::vector<double> m0((size_t)G * DISP_NG, 0.0), trended(G, 0.0);
@@ -1377,14 +1442,15 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   for (int i = 1; i < ns; ++i) if (alc[sel[i]] < alc[sel[i_min]]) i_min = i;   // which.min(AveLogCPM[sel])
   { std::vector<char> issel(G, 0); for (int i : sel) issel[i] = 1; for (long long g = 0; g < G; ++g) if (!issel[g]) trended[g] = trended[sel[i_min]]; }
   if (trended_out) memcpy(trended_out, trended.data() + g0, (size_t)Gl * 8);
+  const double t_trend = now();
   // prior d.f. (:156-169): deviance at the trended dispersion -> limma fitFDist moments
   double prior_df = prior_df_in;
   if (!(prior_df >= 0.0)) {
     CK(cudaMemcpyAsync(ctx->dp_phi_row, trended.data() + g0, (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->dp_beta1, ctx->dp_beta0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_beta_from_grid<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(ctx->dp_beta, ctx->dp_phi_grid, DISP_NG, ctx->dp_phi_row, nullptr, 0.0, Gl, ctx->dp_beta1); CKL();
     DispArgs a;
-    a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0;
-    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean;
+    a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0; a.ds = 1;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean; a.info_out = nullptr;
     RET(disp_nr(ctx, s, a, 1));
     k_build_ytabs<<<Gl, YT, 0, ctx->stream>>>(ctx->dp_phi_row, Gl, nullptr, ctx->dp_tabR2, nullptr); CKL();
     DISPATCH_K(ctx->K, {
@@ -1406,6 +1472,7 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
     prior_df = fit_f_dist_df2(s2, N - 1.0);
   }
   if (prior_df_out) *prior_df_out = prior_df;
+  const double t_prior = now();
   const double prior_n = prior_df / (N - 1.0);  // :171 (ncoefs = 1)
   // tagwise (:172-190): per gene, maximise the spline through l0 + prior.n m0
   std::vector<double> tag(trended);
@@ -1426,6 +1493,11 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   ctx->psi_ver++; s.sig_valid = false;
   if (tmpA) CK(cudaFree(tmpA));
   if (tmpB) CK(cudaFree(tmpB));
+  if (o->verbose)
+    fprintf(stderr, "estimateDisp: grid APL %.3f s (%d NR sweeps + 3 APL sweeps), gather + common %.3f s, AveLogCPM %.3f s (%d sweeps), "
+                    "trend %.3f s, prior d.f. %.3f s (%d sweeps + deviance), tagwise %.3f s\n",
+            t_grid - t_start, sweeps_grid, t_common - t_grid, t_alc - t_common, sweeps_alc - sweeps_grid, t_trend - t_alc,
+            t_prior - t_trend, ctx->disp_nr_sweeps - sweeps_alc, now() - t_prior);
   return RUVNB_OK;
 }
 
