@@ -129,6 +129,7 @@ struct ruvnb_ctx {
   double *dp_beta = nullptr, *dp_beta0 = nullptr, *dp_rowsum = nullptr, *dp_emean = nullptr, *dp_l0 = nullptr, *dp_phi_grid = nullptr,
          *dp_tabG = nullptr, *dp_tabRg = nullptr, *dp_lgr_grid = nullptr, *dp_zeros = nullptr, *dp_beta1 = nullptr, *dp_phi_row = nullptr,
          *dp_dev = nullptr, *dp_tabR2 = nullptr;
+  double *dp_step = nullptr;                 // [Gl][21] previous NR step per column (stopping rule, disp.cuh DispArgs)
   double *dp_info = nullptr;                 // [Gl][21] Fisher information of the converged grid fits (Cox-Reid term)
   double *dp_xs = nullptr, *dp_m0 = nullptr; // trend smoother scratch: [G] AveLogCPM sorted, [G][21] smoothed l0
   int* dp_perm = nullptr;                    // [G]

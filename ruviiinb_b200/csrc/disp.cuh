@@ -37,6 +37,9 @@ struct DispArgs {
   const double* gm_real;    // [Gl] gmean of the parameter set: the ZINB weights wt.zinb need mu = exp(offset + gmean)
   double* info_out;         // [Gl][ldb] or nullptr: the sweep's Fisher information sum w mu / (1 + phi mu) per column -- at
                             // convergence the Cox-Reid term of the APL (adjustedProfileLik: 0.5 log(X' W X), one column)
+  double* step_prev;        // [Gl][ldb] last step of every column (0 before the first): Fisher scoring converges linearly, so
+                            // rho = |step / step_prev| predicts the next step; a column whose NEXT step would be below tol
+                            // stops now -- edgeR would spend one more sweep to apply a change < tol (1e-10) and stop
   int* done;                // [Gl] rows whose ND intercepts have all converged: later sweeps skip them (edgeR stops each
                             // fit at |step| < tol; rows converge after 4-8 steps, a few stragglers need 15-20)
 };
@@ -159,7 +162,17 @@ struct OpDispNR {
         double step = (s1 - s2) / s2;
         if (a.info_out) a.info_out[(long long)row * a.ldb + a.d0 + d * a.ds] = s2;
         double* bp = a.beta + (long long)row * a.ldb + a.d0 + d * a.ds;
-        if (step == step) { *bp += step; nc |= !(fabs(step) < a.tol); }
+        if (step == step) {
+          *bp += step;
+          bool conv = fabs(step) < a.tol;
+          if (a.step_prev) {
+            double* sp = a.step_prev + (long long)row * a.ldb + a.d0 + d * a.ds;
+            const double prev = *sp;
+            *sp = step;
+            if (!conv && prev != 0.0) { double rho = fabs(step / prev); conv = rho < 0.5 && rho * fabs(step) < a.tol; }
+          }
+          nc |= !conv;
+        }
       }
     }
     nc = __shfl_sync(FULL, nc, 0);

@@ -1238,7 +1238,7 @@ static int disp_ensure(ruvnb_ctx* ctx) {
   RET(dev_alloc(ctx, &ctx->dp_tabG, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_tabRg, DISP_NG * YT)); RET(dev_alloc(ctx, &ctx->dp_lgr_grid, DISP_NG));
   RET(dev_alloc(ctx, &ctx->dp_zeros, Gl)); RET(dev_alloc(ctx, &ctx->dp_beta1, Gl)); RET(dev_alloc(ctx, &ctx->dp_phi_row, Gl));
   RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 2));
-  RET(dev_alloc(ctx, &ctx->dp_done, Gl)); RET(dev_alloc(ctx, &ctx->dp_live, Gl)); RET(dev_alloc(ctx, &ctx->dp_info, Gl * DISP_NG));
+  RET(dev_alloc(ctx, &ctx->dp_done, Gl)); RET(dev_alloc(ctx, &ctx->dp_live, Gl)); RET(dev_alloc(ctx, &ctx->dp_info, Gl * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_step, Gl * DISP_NG));
   RET(dev_alloc(ctx, &ctx->dp_hist, Gl * YT));
   RET(dev_alloc(ctx, &ctx->dp_xs, ctx->G)); RET(dev_alloc(ctx, &ctx->dp_m0, ctx->G * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_perm, ctx->G));
   CK(cudaMemsetAsync(ctx->dp_zeros, 0, (size_t)Gl * 8, ctx->stream));
@@ -1260,8 +1260,9 @@ static GeneState<K> disp_state(ruvnb_ctx* ctx, const StateSet& s) {
 }
 // Newton-Raphson to convergence (edgeR glm_one_group: |step| < 1e-10, at most 50 iterations) for columns d0..d0+nd-1
 static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
-  a.done = ctx->dp_done;
+  a.done = ctx->dp_done; a.step_prev = ctx->dp_step;
   CK(cudaMemsetAsync(ctx->dp_done, 0, (size_t)ctx->Gl * sizeof(int), ctx->stream));
+  CK(cudaMemsetAsync(ctx->dp_step, 0, (size_t)ctx->Gl * DISP_NG * 8, ctx->stream));
   const bool trace = getenv("RUVNB_TRACE_DISP") != nullptr;
   // the bulk of the rows converges within 4-5 sweeps; from the third sweep on only the rows still iterating are launched
   int nlive = ctx->Gl; const int* live = nullptr;
