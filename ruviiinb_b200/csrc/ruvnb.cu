@@ -1979,10 +1979,28 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
   if (nc < K) return ctx->fail(RUVNB_EARG, "init_W: %d control genes cannot carry %d factors", nc, K);
   if (max_iter <= 0) max_iter = 100;
   if (!(tol > 0)) tol = 1e-9;   // on the Ritz values, i.e. ~3e-5 on the vectors: irlba's own tolerance is 1e-5
-  double *rm = nullptr, *U = nullptr, *G = nullptr, *T = nullptr;
+  double *rm = nullptr, *U = nullptr, *G = nullptr, *T = nullptr, *A = nullptr, *Upart = nullptr;
+  // cell parts of the A V product: enough CTAs for ~4 per SM, whole 128-cell chunks per part
+  const int row_blocks = (nc + 8 * SVD_RPW - 1) / (8 * SVD_RPW);
+  int n_sm = 148;
+  CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+  int parts = std::max(1, std::min((int)(Np / CH), (4 * n_sm + row_blocks - 1) / row_blocks));
+  const long long seg = ((Np / CH + parts - 1) / parts) * CH;
+  parts = (int)((Np + seg - 1) / seg);
   CK(cudaMalloc((void**)&rm, (size_t)nc * 8)); CK(cudaMalloc((void**)&U, (size_t)nc * K * 8)); CK(cudaMalloc((void**)&G, KK * 8)); CK(cudaMalloc((void**)&T, K * K * 8));
+  CK(cudaMalloc((void**)&Upart, (size_t)parts * nc * K * 8));
+  if (cudaMalloc((void**)&A, (size_t)nc * Np * 8) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(rm); cudaFree(U); cudaFree(G); cudaFree(T); cudaFree(Upart);
+    return ctx->fail(RUVNB_ECUDA, "init_W: no room for the %d x %lld FP64 slab of log-ratios (%.1f GB)", nc, Np, (double)nc * Np * 8 / 1e9);
+  }
   double* V = ctx->cur.W; double* V2 = ctx->nw.W;
   k_svd_rowmean<<<nblk(nc, 8), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, Np, (double)ctx->N, rm); CKL();
+  k_svd_build<<<nblk((long long)nc * Np, 256), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, Np, rm, A); CKL();
+  auto av = [&](const double* Vin) -> int {
+    DISPATCH_K(K, { k_svd_av<KT><<<dim3(row_blocks, parts), 256, 0, ctx->stream>>>(A, nc, Np, seg, Vin, Upart); CKL(); });
+    k_svd_sum_parts<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(Upart, (long long)nc * K, parts, U); CKL();
+    return RUVNB_OK;
+  };
   k_svd_start<<<nblk(Np * K, 256), 256, 0, ctx->stream>>>(V, Np, K, ctx->d_pos2cell); CKL();
   std::vector<double> Gh(KK), Th(K * K), prev(K, 0.0), diag(K, 0.0);
   // orthonormalise the K vectors in `X` in place: Gram -> Cholesky G = R'R on the host -> X <- X R^-1
@@ -2016,8 +2034,8 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
   RET(orth(V));
   int it = 0;
   for (; it < max_iter; ++it) {
-    k_svd_av<<<nblk(nc, 8), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, Np, K, rm, V, U); CKL();
-    DISPATCH_K(K, { k_svd_atu<KT><<<nblk(Np, 64), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, Np, ctx->d_chunk_valid, rm, U, V2); CKL(); });
+    RET(av(V));
+    DISPATCH_K(K, { k_svd_atu<KT><<<(unsigned)(Np / 32), 256, 0, ctx->stream>>>(A, nc, Np, U, V2); CKL(); });
     std::swap(V, V2);
     RET(orth(V));   // diag = squared norms of A'A v before normalisation ~ sigma^4 along converged directions
     double ch = 0.0;
@@ -2025,7 +2043,7 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
     if (it >= 2 && ch < tol) { ++it; break; }
   }
   // Rayleigh-Ritz: B = A V, eigen-decomposition of B'B -> singular values and the rotation of V
-  k_svd_av<<<nblk(nc, 8), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, Np, K, rm, V, U); CKL();
+  RET(av(V));
   std::vector<double> Uh((size_t)nc * K), BtB(K * K, 0.0), Q;
   CK(cudaMemcpyAsync(Uh.data(), U, Uh.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -2053,6 +2071,6 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
   if (W_out) memcpy(W_out, Wh.data(), Wh.size() * 8);
   if (sv_out) for (int l = 0; l < K; ++l) sv_out[l] = sqrt(std::max(BtB[l * K + l], 0.0));
   if (iters_out) *iters_out = it;
-  CK(cudaFree(rm)); CK(cudaFree(U)); CK(cudaFree(G)); CK(cudaFree(T));
+  CK(cudaFree(rm)); CK(cudaFree(U)); CK(cudaFree(G)); CK(cudaFree(T)); CK(cudaFree(A)); CK(cudaFree(Upart));
   return RUVNB_OK;
 }

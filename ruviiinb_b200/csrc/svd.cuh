@@ -1,7 +1,7 @@
 // svd.cuh -- H1: the initial W of ruvIII.nb (reference R/ruvIIInb.R:160-168),
 //   W0 = irlba(log(Y[ctl,]/rowMeans(Y[ctl,]) + 1), nv = k)$v  -- the k leading right singular vectors of the n_ctl x N matrix A.
-// Subspace iteration on A'A with the matrix never formed: V <- orth(A'(A V)), A[g,c] recomputed from the resident control
-// rows in both products; then one Rayleigh-Ritz rotation.  irlba's Lanczos start is random and its tolerance is 1e-5, so the
+// Subspace iteration on A'A: V <- orth(A'(A V)) with A held as a dense FP64 slab (n_ctl x N, 0.8 GB at 1000 x 100k) for the
+// duration of the call; then one Rayleigh-Ritz rotation.  irlba's Lanczos start is random and its tolerance is 1e-5, so the
 // reference's own W0 is only defined up to that (and up to sign); parity runs inject W0.
 // Sign convention: the entry of largest magnitude of every vector is positive.  Included by ruvnb.cu only.
 #pragma once
@@ -17,48 +17,85 @@ __global__ void __launch_bounds__(256) k_svd_rowmean(const int32_t* const* ctl_r
   s = warp_sum(s);
   if (lane == 0) rowmean[gi] = s / n;
 }
-// U[gi][l] = sum_c A[gi,c] V[l][c]; one warp per control row
-__global__ void __launch_bounds__(256) k_svd_av(const int32_t* const* ctl_rows, int n_ctl, long long Np, int K, const double* rowmean,
-                                               const double* V, double* U) {
-  const int gi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (gi >= n_ctl) return;
-  const int32_t* y = ctl_rows[gi];
-  const double irm = 1.0 / rowmean[gi];
-  double acc[RUVNB_MAX_K];
-  for (int l = 0; l < K; ++l) acc[l] = 0.0;
-  for (long long p = lane; p < Np; p += 32) {
-    int v = y[p];
-    if (v <= 0) continue;                       // log(0/rm + 1) = 0; pads skipped
-    double a = log1p((double)v * irm);
-    for (int l = 0; l < K; ++l) acc[l] = fma(a, V[(long long)l * Np + p], acc[l]);
-  }
-  for (int l = 0; l < K; ++l) { double s = warp_sum(acc[l]); if (lane == 0) U[(long long)gi * K + l] = s; }
+// A[gi][p] = log(Y[ctl_gi, p] / rowmean_gi + 1) as a dense FP64 slab [n_ctl][Np] (pads and zero counts 0), built once: the
+// iterations then stream 8 B per element instead of paying a logarithm per element in both products
+__global__ void __launch_bounds__(256) k_svd_build(const int32_t* const* ctl_rows, int n_ctl, long long Np, const double* rowmean, double* A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_ctl * Np) return;
+  const int gi = (int)(i / Np); const long long p = i - (long long)gi * Np;
+  const int v = ctl_rows[gi][p];
+  A[i] = v > 0 ? log1p((double)v / rowmean[gi]) : 0.0;
 }
-// Vout[l][p] = sum_gi A[gi,p] U[gi][l]; 8 cells x 4 gene slices per warp
+// Upart[part][gi][l] = sum over the part's cells of A[gi,c] V[l][c].  A CTA holds 32 rows (4 per warp) over ONE cell range,
+// so the V values its 8 warps load are the same lines (L1) and every V load feeds 4 rows; the parts fill the machine
+// (n_ctl / 32 row blocks alone would not) and are summed in a fixed order afterwards.
+#define SVD_RPW 4
 template <int K>
-__global__ void __launch_bounds__(256) k_svd_atu(const int32_t* const* ctl_rows, int n_ctl, long long Np, const int* chunk_valid,
-                                                const double* rowmean, const double* U, double* Vout) {
+__global__ void __launch_bounds__(256) k_svd_av(const double* __restrict__ A, int n_ctl, long long Np, long long seg,
+                                               const double* __restrict__ V, double* __restrict__ Upart) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cell = lane & 7, slice = lane >> 3;
-  const long long pos = ((long long)blockIdx.x * 8 + warp) * 8 + cell;
-  const bool valid = pos < Np && (int)(pos & (CH - 1)) < chunk_valid[pos >> 7];
-  double acc[K];
+  const int g0 = (blockIdx.x * 8 + warp) * SVD_RPW;
+  const long long p0 = (long long)blockIdx.y * seg, p1 = p0 + seg < Np ? p0 + seg : Np;
+  double acc[SVD_RPW][K];
 #pragma unroll
-  for (int l = 0; l < K; ++l) acc[l] = 0.0;
-  if (valid) {
-    for (int gi = slice; gi < n_ctl; gi += 4) {
-      int v = ctl_rows[gi][pos];
-      if (v <= 0) continue;
-      double a = log1p((double)v / rowmean[gi]);
+  for (int r = 0; r < SVD_RPW; ++r)
 #pragma unroll
-      for (int l = 0; l < K; ++l) acc[l] = fma(a, U[(long long)gi * K + l], acc[l]);
+    for (int l = 0; l < K; ++l) acc[r][l] = 0.0;
+  const double* a[SVD_RPW];
+#pragma unroll
+  for (int r = 0; r < SVD_RPW; ++r) a[r] = A + (long long)(g0 + r < n_ctl ? g0 + r : n_ctl - 1) * Np;
+  for (long long p = p0 + lane; p < p1; p += 32) {
+    double v[K];
+#pragma unroll
+    for (int l = 0; l < K; ++l) v[l] = V[(long long)l * Np + p];
+#pragma unroll
+    for (int r = 0; r < SVD_RPW; ++r) {
+      const double x = a[r][p];
+#pragma unroll
+      for (int l = 0; l < K; ++l) acc[r][l] = fma(x, v[l], acc[r][l]);
     }
   }
 #pragma unroll
-  for (int l = 0; l < K; ++l) { acc[l] += __shfl_xor_sync(FULL, acc[l], 8); acc[l] += __shfl_xor_sync(FULL, acc[l], 16); }
-  if (slice == 0 && pos < Np) {
+  for (int r = 0; r < SVD_RPW; ++r)
 #pragma unroll
-    for (int l = 0; l < K; ++l) Vout[(long long)l * Np + pos] = valid ? acc[l] : 0.0;
+    for (int l = 0; l < K; ++l) {
+      double t = warp_sum(acc[r][l]);
+      if (lane == 0 && g0 + r < n_ctl) Upart[((long long)blockIdx.y * n_ctl + g0 + r) * K + l] = t;
+    }
+}
+__global__ void k_svd_sum_parts(const double* Upart, long long n, int parts, double* U) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int q = 0; q < parts; ++q) s += Upart[(long long)q * n + i];
+  U[i] = s;
+}
+// Vout[l][p] = sum_gi A[gi,p] U[gi][l]: a CTA owns 32 cells, warp w the rows gi = w (mod 8); a row's 32 cells are one
+// 256-byte read; the 8 partial sums are combined through shared memory in warp order
+template <int K>
+__global__ void __launch_bounds__(256) k_svd_atu(const double* __restrict__ A, int n_ctl, long long Np, const double* __restrict__ U,
+                                                double* __restrict__ Vout) {
+  __shared__ double sm[8][K][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long pos = (long long)blockIdx.x * 32 + lane;   // Np is a multiple of 128
+  double acc[K];
+#pragma unroll
+  for (int l = 0; l < K; ++l) acc[l] = 0.0;
+#pragma unroll 4
+  for (int gi = warp; gi < n_ctl; gi += 8) {
+    const double x = A[(long long)gi * Np + pos];
+#pragma unroll
+    for (int l = 0; l < K; ++l) acc[l] = fma(x, U[(long long)gi * K + l], acc[l]);
+  }
+#pragma unroll
+  for (int l = 0; l < K; ++l) sm[warp][l][lane] = acc[l];
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * 32; i += 256) {
+    const int l = i >> 5, c = i & 31;
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][l][c];
+    Vout[(long long)l * Np + (long long)blockIdx.x * 32 + c] = t;   // pad cells: A = 0 there, so 0
   }
 }
 // Gram of the K vectors V[l][.] (lower triangle, KK entries), deterministic: one CTA per entry
