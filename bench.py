@@ -259,6 +259,7 @@ def main():
     t_gen = time.perf_counter() - t_gen
 
     opts = _lib.default_opts(k=k)
+    opts.verbose = int(os.environ.get("RUVNB_VERBOSE", "0")) if rank == 0 else 0   # stage timings on stderr
     from ruviiinb_b200 import shard
 
     def barrier():
@@ -353,7 +354,9 @@ def main():
         barrier()
         t0 = time.perf_counter()
         ctx.upload_counts(Yh, Yctl=Yctl)
+        t_up = time.perf_counter() - t0
         ctx.winsorize()
+        t_win = time.perf_counter() - t0 - t_up
         W0c, sv, svd_iters = ctx.init_W(k)                      # H1 on the device: a COLD start, as ruvIII.nb does it
         t_init = time.perf_counter() - t0
         logl_outer, recs, st = ctx.fit_nb(opts, W0=W0c)
@@ -366,7 +369,8 @@ def main():
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         full_fit = {"wall_seconds": float(tdt.item()), "outer_iterations": st["n_outer"], "inner_iterations": st["n_inner"],
                     "inner_loop_seconds": st["inner_seconds"], "dispersion_seconds": st["disp_seconds"],
-                    "upload_winsorize_initW_seconds": t_init, "initW_iterations": svd_iters,
+                    "upload_winsorize_initW_seconds": t_init, "upload_seconds": t_up, "winsorize_seconds": t_win,
+                    "initW_seconds": t_init - t_up - t_win, "initW_iterations": svd_iters,
                     "gene_fits_per_s_inner_loops": G * st["n_inner"] / st["inner_seconds"], "logl_outer": [float(x) for x in logl_outer],
                     "canonical_corr_W_truth": [float(x) for x in np.linalg.svd(np.linalg.qr(res["W"] - res["W"].mean(0))[0].T @ np.linalg.qr(tp["W"] - tp["W"].mean(0))[0], compute_uv=False)] if rank == 0 else None,
                     "what": "upload (pinned host int32) + Winsorize + ruvnb_init_W (truncated SVD of the control rows) + ruvnb_fit_nb with estimateDisp at every psi refresh + read-back; wall clock, max over ranks"}

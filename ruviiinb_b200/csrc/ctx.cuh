@@ -138,6 +138,7 @@ struct ruvnb_ctx {
   int* dp_live = nullptr;                    // [Gl] list of the rows still iterating
   int* dp_hist = nullptr;                    // [Gl][YT] count histogram of each row (valid while hist_ready)
   bool hist_ready = false;
+  bool dp_beta_warm = false;                 // dp_beta holds the converged grid intercepts of an earlier call on these counts
   bool dp_ready = false;
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare

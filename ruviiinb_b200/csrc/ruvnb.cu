@@ -294,7 +294,7 @@ int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, cons
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false;
+  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
 
@@ -340,7 +340,7 @@ int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false;
+  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
 
@@ -363,7 +363,7 @@ int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out) {
   if (nonzero_out) CK(cudaMemcpyAsync(nonzero_out, d_nz, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaFree(d_cap)); CK(cudaFree(d_nz));
-  ctx->cur.sig_valid = false; ctx->roworder_ready = false; ctx->hist_ready = false;
+  ctx->cur.sig_valid = false; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
 
@@ -1196,14 +1196,16 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
 }  // extern "C"
 
 // ---- H3: dispersion (R/estimateDisp.par.R) ------------------------------------------------------------------------------
-// dst[r][d0 + i ds] = src[r * src_ld + src_col + i ds * (src_ld > 1)], i < nd: a start value per row (src_ld == 1) or the
-// converged neighbour column (src_ld == ld)
-__global__ void k_bcast_cols_strided(const double* src, int src_ld, int src_col, long long n, int ld, int d0, int ds, int nd, double* dst) {
+// dst[r][d0 + i ds] = src[r][src_col + i ds] (a converged neighbour or earlier column) where that is finite and within
+// maxdiff of the one-group start value beta0[r], else beta0[r] (src == nullptr: always); i < nd.  From far above the root
+// Fisher scoring walks down by 1 per sweep, so an intercept left over from very different parameters (a gene whose
+// coefficients were reverted in between) must not be used.
+__global__ void k_start_cols(const double* src, int src_ld, int src_col, const double* beta0, double maxdiff, long long n, int ld, int d0, int ds, int nd, double* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * nd) return;
   long long r = i / nd; int d = (int)(i % nd);
-  double v = src_ld == 1 ? src[r] : src[r * src_ld + src_col + d * ds];
-  // an all-zero gene keeps -Inf; a neighbour that failed (NaN) falls back to nothing better: keep it
+  double v = beta0[r];
+  if (src) { double p = src[r * src_ld + src_col + d * ds]; if (fabs(p) <= 1.79769313486231570e308 && fabs(p - v) <= maxdiff) v = p; }
   dst[r * ld + d0 + d * ds] = v;
 }
 // start value for a one-dispersion fit from the converged grid: the intercept is a smooth function of log(phi), so linear
@@ -1286,6 +1288,17 @@ static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
     }
     if (ctx->h_flags[6] == 0) break;
     if (it >= 2) { nlive = ctx->h_flags[7]; live = ctx->dp_live; if (nlive <= 0) break; }
+    if (trace && it == 49) {
+      std::vector<int> lv(nlive); std::vector<double> bb((size_t)ctx->Gl * a.ldb), sp((size_t)ctx->Gl * DISP_NG);
+      CK(cudaMemcpy(lv.data(), ctx->dp_live, (size_t)nlive * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(bb.data(), a.beta, bb.size() * 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(sp.data(), ctx->dp_step, sp.size() * 8, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < std::min(nlive, 4); ++i) {
+        fprintf(stderr, "  not converged: row %d:", lv[i]);
+        for (int d = 0; d < nd; ++d) fprintf(stderr, " [beta %.17g step %.3g]", bb[(size_t)lv[i] * a.ldb + a.d0 + d * a.ds], sp[(size_t)lv[i] * a.ldb + a.d0 + d * a.ds]);
+        fprintf(stderr, "\n");
+      }
+    }
   }
   return RUVNB_OK;
 }
@@ -1313,8 +1326,11 @@ static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
   // tolerance 1e-10) in about half the sweeps.
   const int DS = DISP_NG / DISP_ND;   // 3
   for (int c = 0; c < DS; ++c) {
-    if (c == 0) k_bcast_cols_strided<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta0, 1, 0, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
-    else k_bcast_cols_strided<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta, DISP_NG, c - 1, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
+    // start values: a later call on the same counts (the next psi refresh of the fit) starts every column from its own
+    // converged intercept of the call before -- the parameters have moved less than one grid step does
+    if (ctx->dp_beta_warm) k_start_cols<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta, DISP_NG, c, ctx->dp_beta0, 2.0, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
+    else if (c == 0) k_start_cols<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(nullptr, 1, 0, ctx->dp_beta0, 0.0, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
+    else k_start_cols<<<nblk((long long)Gl * DISP_ND, 256), 256, 0, ctx->stream>>>(ctx->dp_beta, DISP_NG, c - 1, ctx->dp_beta0, 1e300, Gl, DISP_NG, c, DS, DISP_ND, ctx->dp_beta);
     CKL();
     DispArgs a;
     a.phi_grid = ctx->dp_phi_grid + c; a.phi_row = nullptr; a.beta = ctx->dp_beta; a.ldb = DISP_NG; a.d0 = c; a.ds = DS;
@@ -1331,6 +1347,7 @@ static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
       fprintf(stderr, "  disp APL sweep %d: %.2f ms\n", c, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_apl).count());
     }
   }
+  ctx->dp_beta_warm = true;
   return RUVNB_OK;
 }
 
