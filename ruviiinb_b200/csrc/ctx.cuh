@@ -138,6 +138,9 @@ struct ruvnb_ctx {
   int* dp_live = nullptr;                    // [Gl] list of the rows still iterating
   int* dp_hist = nullptr;                    // [Gl][YT] count histogram of each row (valid while hist_ready)
   bool hist_ready = false;
+  double* dp_E = nullptr;                    // [Gl][Np] exp(offset) cache of the dispersion step (disp.cuh DispArgs::Ecache), if it fits
+  bool dp_E_tried = false;
+  double* dp_syo = nullptr;                  // [Gl] sum y offset per row
   bool dp_beta_warm = false;                 // dp_beta holds the converged grid intercepts of an earlier call on these counts
   bool dp_ready = false;
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)

@@ -37,11 +37,41 @@ struct DispArgs {
   const double* gm_real;    // [Gl] gmean of the parameter set: the ZINB weights wt.zinb need mu = exp(offset + gmean)
   double* info_out;         // [Gl][ldb] or nullptr: the sweep's Fisher information sum w mu / (1 + phi mu) per column -- at
                             // convergence the Cox-Reid term of the APL (adjustedProfileLik: 0.5 log(X' W X), one column)
+  const double* Ecache;     // [Gl][Np] exp(offset) of every cell, written by k_disp_init, or nullptr (no room: recompute).  The
+  long long Np;             // offsets are fixed for the whole dispersion step, so its ~40 sweeps stream 8 B per element
+  int nchunks;              // instead of redoing k FMAs + one exp per element
+  const double* syo_row;    // [Gl] sum y offset and
+  const double* sy_row;     // [Gl] sum y of every row (k_disp_init): the APL needs no offset then
   double* step_prev;        // [Gl][ldb] last step of every column (0 before the first): Fisher scoring converges linearly, so
                             // rho = |step / step_prev| predicts the next step; a column whose NEXT step would be below tol
                             // stops now -- edgeR would spend one more sweep to apply a change < tol (1e-10) and stop
   int* done;                // [Gl] rows whose ND intercepts have all converged: later sweeps skip them (edgeR stops each
                             // fit at |step| < tol; rows converge after 4-8 steps, a few stragglers need 15-20)
+};
+
+// the row's slice of the exp(offset) cache, fetched one chunk ahead like the counts (stream_rows): a lane's two pairs of
+// chunk c sit at c CH + 2 lane and c CH + 64 + 2 lane
+struct ERow {
+  const double* base; double2 na, nb, hold; int pre_c, nchunks;
+  __device__ __forceinline__ void begin(const double* E, long long row, long long Np, int nch) {
+    base = E ? E + row * Np : nullptr; pre_c = -1; nchunks = nch;
+  }
+  __device__ __forceinline__ double2 get(int c, int ti) {
+    if (ti & 64) return hold;
+    const int lane2 = 2 * (threadIdx.x & 31);
+    double2 cur;
+    if (pre_c == c) { cur = na; hold = nb; }
+    else {
+      cur = __ldcs(reinterpret_cast<const double2*>(base + (long long)c * CH + lane2));
+      hold = __ldcs(reinterpret_cast<const double2*>(base + (long long)c * CH + 64 + lane2));
+    }
+    if (c + 1 < nchunks) {
+      na = __ldcs(reinterpret_cast<const double2*>(base + (long long)(c + 1) * CH + lane2));
+      nb = __ldcs(reinterpret_cast<const double2*>(base + (long long)(c + 1) * CH + 64 + lane2));
+      pre_c = c + 1;
+    }
+    return cur;
+  }
 };
 
 // ---- start values ---------------------------------------------------------------------------------------------
@@ -50,43 +80,52 @@ struct OpDispInit {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
   GeneState<K> st; GeneRegs<K> g;
-  double s_ye, s_y, s_e, s_w; int nz;
-  double *beta0, *rowsum, *emean; double n; const double* gm_real; double gmr;
-  __device__ __forceinline__ void row_begin(int row, int) { g.load(st, row); s_ye = s_y = s_e = s_w = 0.0; nz = 0; gmr = gm_real[row]; }
+  double s_ye, s_y, s_e, s_w, s_yo; int nz;
+  double *beta0, *rowsum, *emean, *syo_row; double n; const double* gm_real; double gmr;
+  double* Ecache; long long Np; double* erow;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); s_ye = s_y = s_e = s_w = s_yo = 0.0; nz = 0; gmr = gm_real[row];
+    erow = Ecache ? Ecache + (long long)row * Np : nullptr;
+  }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
-    if (!m) return;
+  __device__ __forceinline__ double one(int y, double off, bool m, long long pos) {
+    if (!m) return 0.0;
     double E = g.expm(off);
     double yd = (double)y;
     double w = g.zi ? g.wz(y, E * exp(gmr), pos) : 1.0;   // weights = wt.zinb (R/ruvIIInb.R:211)
-    s_e += E; s_y += yd; s_w += w;
+    s_e += E; s_y += yd; s_w += w; s_yo = fma(yd, off, s_yo);
     if (y > 0) { s_ye += yd / E * w; nz = 1; }
+    return E;
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     double o0, o1;
     g.lmu_pair(tile, ti, o0, o1);
     const long long pos = (long long)c * CH + (ti & (CH - 1));
-    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
+    double2 e;
+    e.x = one(y0, o0, m0, pos); e.y = one(y1, o1, m1, pos + 1);
+    if (erow) __stcs(reinterpret_cast<double2*>(erow + pos), e);
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
-    double a = warp_sum(s_ye), b = warp_sum(s_y), e = warp_sum(s_e), tw = warp_sum(s_w);
+    double a = warp_sum(s_ye), b = warp_sum(s_y), e = warp_sum(s_e), tw = warp_sum(s_w), yo = warp_sum(s_yo);
     int any = __any_sync(FULL, nz);
     if ((threadIdx.x & 31) == 0) {
       beta0[row] = any ? log(a / tw) : -__longlong_as_double(0x7ff0000000000000ll);   // glm_one_group start
-      rowsum[row] = b; emean[row] = e / n;
+      rowsum[row] = b; emean[row] = e / n; syo_row[row] = yo;
     }
   }
 };
 template <int K>
 __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_init(RowGeom geo, GeneState<K> st, double* beta0, double* rowsum,
-                                                              double* emean, double n, const double* gm_real) {
+                                                              double* emean, double n, const double* gm_real, double* syo_row,
+                                                              double* Ecache) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) sh.wsets[0] = st.W;
   OpDispInit<K> op;
   op.st = st; op.beta0 = beta0; op.rowsum = rowsum; op.emean = emean; op.n = n; op.gm_real = gm_real;
+  op.syo_row = syo_row; op.Ecache = Ecache; op.Np = geo.Np;
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
@@ -99,9 +138,10 @@ struct OpDispNR {
   // score = sum w (y - mu) / (1 + phi mu) = S1 - e^beta S2, information = e^beta S2, with S1 = sum w y / (1 + phi mu) and
   // S2 = sum w E / (1 + phi mu), mu = e^beta E: per cell and dispersion one FMA for the denominator, the reciprocal, two FMAs
   double eb[ND], ebphi[ND], dl[ND], info[ND];
-  double yadd, escale, egm; bool live;
+  double yadd, escale, egm; bool live; ERow er;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
+    er.begin(a.Ecache, row, a.Np, a.nchunks);
     live = false;
     egm = g.zi ? exp(a.gm_real[row]) : 1.0;
 #pragma unroll
@@ -117,9 +157,8 @@ struct OpDispNR {
     if (a.emean) { double pcm = a.prior_count / a.emean[row]; yadd = pcm; escale = fma(2.0, pcm, 1.0); }
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
+  __device__ __forceinline__ void one(int y, double E, bool m, long long pos) {
     if (!m) return;
-    double E = g.expm(off);
     const double wzv = g.zi ? g.wz(y, E * egm, pos) : 1.0;
     double yd = fma(yadd, E, (double)y);
     E *= escale;
@@ -142,10 +181,15 @@ struct OpDispNR {
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     if (!live) return;  // all-zero gene: beta = -Inf stays (edgeR returns R_NegInf)
-    double o0, o1;
-    g.lmu_pair(tile, ti, o0, o1);
     const long long pos = (long long)c * CH + (ti & (CH - 1));
-    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
+    if (er.base) {
+      const double2 e = er.get(c, ti);
+      one(y0, e.x, m0, pos); one(y1, e.y, m1, pos + 1);
+    } else {
+      double o0, o1;
+      g.lmu_pair(tile, ti, o0, o1);
+      one(y0, m0 ? g.expm(o0) : 0.0, m0, pos); one(y1, m1 ? g.expm(o1) : 0.0, m1, pos + 1);
+    }
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
@@ -207,9 +251,10 @@ struct OpDispAPL {
   const int* hist;          // [Gl][YT] cells of the row with count y (0 < y < YT)
   double eb[ND], r[ND], ll[ND];
   double syo, sy, sw, egm;  // sum w y offset, sum w y, sum w
-  double* l0; int ld0;
+  double* l0; int ld0; ERow er;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
+    er.begin(a.Ecache, row, a.Np, a.nchunks);
     egm = g.zi ? exp(a.gm_real[row]) : 1.0; sw = 0.0;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
@@ -220,11 +265,9 @@ struct OpDispAPL {
     syo = 0.0; sy = 0.0;
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
-  __device__ __forceinline__ void one(int y, double off, bool m, long long pos) {
+  __device__ __forceinline__ void one(int y, double E, bool m, long long pos) {
     if (!m) return;
-    double E = g.expm(off);
     double yd = (double)y;
-    syo = fma(yd, off, syo); sy += yd;
     if (g.zi) {
       const double wzv = g.wz(y, E * egm, pos);
       sw += wzv;
@@ -241,14 +284,21 @@ struct OpDispAPL {
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
-    double o0, o1;
-    g.lmu_pair(tile, ti, o0, o1);
     const long long pos = (long long)c * CH + (ti & (CH - 1));
-    one(y0, o0, m0, pos); one(y1, o1, m1, pos + 1);
+    if (er.base) {
+      const double2 e = er.get(c, ti);
+      one(y0, e.x, m0, pos); one(y1, e.y, m1, pos + 1);
+    } else {
+      double o0, o1;
+      g.lmu_pair(tile, ti, o0, o1);
+      if (m0) { syo = fma((double)y0, o0, syo); sy += (double)y0; }
+      if (m1) { syo = fma((double)y1, o1, syo); sy += (double)y1; }
+      one(y0, m0 ? g.expm(o0) : 0.0, m0, pos); one(y1, m1 ? g.expm(o1) : 0.0, m1, pos + 1);
+    }
   }
   __device__ __forceinline__ void group_end(int) {}
   __device__ __forceinline__ void row_end(int row) {
-    double tyo = warp_sum(syo), ty = warp_sum(sy), tw = g.zi ? warp_sum(sw) : a.n;
+    double tyo = er.base ? a.syo_row[row] : warp_sum(syo), ty = er.base ? a.sy_row[row] : warp_sum(sy), tw = g.zi ? warp_sum(sw) : a.n;
     const int lane = threadIdx.x & 31;
     double hy[YT / 32];
 #pragma unroll

@@ -1241,7 +1241,7 @@ static int disp_ensure(ruvnb_ctx* ctx) {
   RET(dev_alloc(ctx, &ctx->dp_zeros, Gl)); RET(dev_alloc(ctx, &ctx->dp_beta1, Gl)); RET(dev_alloc(ctx, &ctx->dp_phi_row, Gl));
   RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 2));
   RET(dev_alloc(ctx, &ctx->dp_done, Gl)); RET(dev_alloc(ctx, &ctx->dp_live, Gl)); RET(dev_alloc(ctx, &ctx->dp_info, Gl * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_step, Gl * DISP_NG));
-  RET(dev_alloc(ctx, &ctx->dp_hist, Gl * YT));
+  RET(dev_alloc(ctx, &ctx->dp_hist, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_syo, Gl));
   RET(dev_alloc(ctx, &ctx->dp_xs, ctx->G)); RET(dev_alloc(ctx, &ctx->dp_m0, ctx->G * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_perm, ctx->G));
   CK(cudaMemsetAsync(ctx->dp_zeros, 0, (size_t)Gl * 8, ctx->stream));
   double grid[DISP_NG];
@@ -1315,10 +1315,22 @@ static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
   RET(ensure_hist(ctx));
   const int Gl = ctx->Gl;
   ctx->disp_nr_sweeps = 0;
+  // exp(offset) of every cell, kept for the ~40 sweeps of the step when HBM has the room (16 GB at 20k x 100k) next to a
+  // reserve for everything allocated later (exact-MAD scratch, get.res slabs); otherwise every sweep recomputes it
+  if (!ctx->dp_E_tried) {
+    ctx->dp_E_tried = true;
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    const size_t need = (size_t)Gl * (size_t)ctx->Np * 8, reserve = std::max<size_t>((size_t)8 << 30, tot / 8);
+    if (!getenv("RUVNB_NO_ECACHE") && fr > need + reserve) {
+      void* q = nullptr;
+      if (cudaMalloc(&q, need) == cudaSuccess) { ctx->allocs.push_back(q); ctx->dp_E = (double*)q; } else cudaGetLastError();
+    }
+  }
   CK(cudaMemsetAsync(ctx->dp_info, 0, (size_t)Gl * DISP_NG * 8, ctx->stream));   // all-zero genes are never iterated
   DISPATCH_K(ctx->K, {
     LAUNCH_ROWS(k_disp_init<KT>, 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), ctx->dp_beta0, ctx->dp_rowsum, ctx->dp_emean, (double)ctx->N,
-                s.gmean);
+                s.gmean, ctx->dp_syo, ctx->dp_E);
   });
   // three sweeps of seven interleaved grid points: {0,3,..,18}, {1,4,..,19}, {2,5,..,20}.  edgeR starts every fit from
   // the same value (start = NULL, R/estimateDisp.par.R:107-110); the intercept is the unique root of a concave score, so
@@ -1334,7 +1346,7 @@ static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
     CKL();
     DispArgs a;
     a.phi_grid = ctx->dp_phi_grid + c; a.phi_row = nullptr; a.beta = ctx->dp_beta; a.ldb = DISP_NG; a.d0 = c; a.ds = DS;
-    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = (double)ctx->N; a.gm_real = s.gmean;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = (double)ctx->N; a.gm_real = s.gmean; a.Ecache = ctx->dp_E; a.Np = ctx->Np; a.nchunks = ctx->nchunks; a.syo_row = ctx->dp_syo; a.sy_row = ctx->dp_rowsum;
     a.info_out = ctx->dp_info;
     RET(disp_nr(ctx, s, a, DISP_ND));
     const auto t_apl = std::chrono::steady_clock::now();
@@ -1415,7 +1427,7 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
     k_beta_from_grid<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(ctx->dp_beta, ctx->dp_phi_grid, DISP_NG, ctx->dp_phi_row, ctx->dp_emean, 2.0, Gl, ctx->dp_beta1); CKL();
     DispArgs a;
     a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0; a.ds = 1;
-    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean; a.info_out = nullptr;
+    a.emean = ctx->dp_emean; a.prior_count = 2.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean; a.Ecache = ctx->dp_E; a.Np = ctx->Np; a.nchunks = ctx->nchunks; a.syo_row = ctx->dp_syo; a.sy_row = ctx->dp_rowsum; a.info_out = nullptr;
     RET(disp_nr(ctx, s, a, 1));
   }
   std::vector<double> alc(G, 0.0);
@@ -1468,7 +1480,7 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
     k_beta_from_grid<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(ctx->dp_beta, ctx->dp_phi_grid, DISP_NG, ctx->dp_phi_row, nullptr, 0.0, Gl, ctx->dp_beta1); CKL();
     DispArgs a;
     a.phi_grid = nullptr; a.phi_row = ctx->dp_phi_row; a.beta = ctx->dp_beta1; a.ldb = 1; a.d0 = 0; a.ds = 1;
-    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean; a.info_out = nullptr;
+    a.emean = nullptr; a.prior_count = 0.0; a.tol = 1e-10; a.notconv = ctx->dp_flag; a.n = N; a.gm_real = s.gmean; a.Ecache = ctx->dp_E; a.Np = ctx->Np; a.nchunks = ctx->nchunks; a.syo_row = ctx->dp_syo; a.sy_row = ctx->dp_rowsum; a.info_out = nullptr;
     RET(disp_nr(ctx, s, a, 1));
     k_build_ytabs<<<Gl, YT, 0, ctx->stream>>>(ctx->dp_phi_row, Gl, nullptr, ctx->dp_tabR2, nullptr); CKL();
     DISPATCH_K(ctx->K, {
