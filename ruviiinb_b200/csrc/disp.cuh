@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_init(RowGeom geo, GeneS
 }
 
 // ---- one Newton-Raphson step for ND dispersions ------------------------------------------------------------------
-template <int K, int ND>
+template <int K, int ND, bool CACHED = false>
 struct OpDispNR {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
@@ -182,7 +182,10 @@ struct OpDispNR {
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     if (!live) return;  // all-zero gene: beta = -Inf stays (edgeR returns R_NegInf)
     const long long pos = (long long)c * CH + (ti & (CH - 1));
-    if (er.base) {
+    if constexpr (CACHED) {
+      const double2 e = er.get(c, ti);
+      one(y0, e.x, m0, pos); one(y1, e.y, m1, pos + 1);
+    } else if (er.base) {
       const double2 e = er.get(c, ti);
       one(y0, e.x, m0, pos); one(y1, e.y, m1, pos + 1);
     } else {
@@ -234,8 +237,17 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr(RowGeom geo, GeneSta
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
-// ---- adjusted profile likelihood for ND dispersions ---------------------------------------------------------------
+// the same sweep on the exp(offset) cache (a.Ecache != nullptr): nothing is taken from the W tiles
 template <int K, int ND>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr_cached(RowGeom geo, GeneState<K> st, DispArgs a) {
+  __shared__ RowShared sh;
+  OpDispNR<K, ND, true> op;
+  op.st = st; op.a = a;
+  stream_rows_lean(geo, &sh, op);
+}
+
+// ---- adjusted profile likelihood for ND dispersions ---------------------------------------------------------------
+template <int K, int ND, bool CACHED = false>
 struct OpDispAPL {
   // log-lik of the row at dispersion 1/r and intercept beta:
   //   sum_c w_c [ lgamma(y + r) - lgamma(r) - lgamma(y + 1) + y log mu + r log r - (y + r) log(mu + r) ]
@@ -285,7 +297,10 @@ struct OpDispAPL {
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
     const long long pos = (long long)c * CH + (ti & (CH - 1));
-    if (er.base) {
+    if constexpr (CACHED) {
+      const double2 e = er.get(c, ti);
+      one(y0, e.x, m0, pos); one(y1, e.y, m1, pos + 1);
+    } else if (er.base) {
       const double2 e = er.get(c, ti);
       one(y0, e.x, m0, pos); one(y1, e.y, m1, pos + 1);
     } else {
@@ -330,6 +345,16 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl(RowGeom geo, GeneSt
   OpDispAPL<K, ND> op;
   op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0;
   stream_rows<K, 1>(geo, &sh.base, op, smem);
+}
+
+template <int K, int ND>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl_cached(RowGeom geo, GeneState<K> st, DispArgs a, const double* tabG, const double* lgr_grid,
+                                                                    const int* hist, double* l0, int ld0) {
+  __shared__ DispRowShared<K, ND> sh;
+  for (int i = threadIdx.x; i < ND * YT; i += ROW_THREADS) (&sh.tg[0][0])[i] = tabG[(long long)(i / YT) * a.ds * YT + (i % YT)];
+  OpDispAPL<K, ND, true> op;
+  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0;
+  stream_rows_lean(geo, &sh.base, op);
 }
 
 // counts of each value 1 .. YT-1 in every row (pads hold -1): one CTA per row, shared-memory histogram.  Depends on the

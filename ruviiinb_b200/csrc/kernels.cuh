@@ -230,6 +230,56 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   }
 }
 
+// The same walk for ops that take nothing from the W tiles (the dispersion sweeps on the exp(offset) cache): no tile
+// staging, no CTA barriers inside the row -- a warp only streams its row's counts one chunk ahead.  pair() gets
+// tile == nullptr.
+template <class Op, int NW = NWARP>
+__device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* sh, Op& op) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = blockIdx.x * NW + warp;
+  const int nrows = geo.nrows_dev ? min(geo.nrows, *geo.nrows_dev) : geo.nrows;
+  if (blockIdx.x * NW >= nrows) return;
+  const bool active = slot < nrows;
+  const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
+  {
+    const double* src = reinterpret_cast<const double*>(geo.mtabs);
+    double* dst = reinterpret_cast<double*>(&sh->mt);
+    for (int i = tid; i < (int)(sizeof(MathTabs) / 8); i += NW * 32) dst[i] = src[i];
+  }
+  op.g.tl = sh->tl[warp]; op.g.tr = sh->tr[warp]; op.g.mt = &sh->mt; op.g.as = sh->al[warp];
+  op.g.lgr = 0.0;
+  op.g.zinf = geo.zinf;
+  __syncthreads();
+  if (!active) return;
+  op.row_begin(row, slot);
+  const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
+  int curj = -1;
+  int2 ya = yrow2[lane], yb = yrow2[32 + lane];
+#pragma unroll 1
+  for (int c = 0; c < geo.nchunks; ++c) {
+    const int2 y01 = ya, y23 = yb;
+    if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; }
+    const int nv = geo.chunk_valid[c];
+    if (nv == 0) continue;
+    const int j = geo.chunk_grp[c];
+    if (j != curj) {
+      if (curj >= 0) op.group_end(curj);
+      curj = j;
+      op.group_begin(j);
+    }
+    const int ti = 2 * lane;
+    if (nv == CH) {
+      op.template pair<true>(y01.x, y01.y, c, ti, nullptr, true, true);
+      op.template pair<true>(y23.x, y23.y, c, ti + 64, nullptr, true, true);
+    } else {
+      op.template pair<false>(y01.x, y01.y, c, ti, nullptr, ti < nv, ti + 1 < nv);
+      op.template pair<false>(y23.x, y23.y, c, ti + 64, nullptr, ti + 64 < nv, ti + 65 < nv);
+    }
+  }
+  if (curj >= 0) op.group_end(curj);
+  op.row_end(row);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K_build_ytabs: per-gene count tables (rebuilt whenever psi changes -- once per outer iteration):
 //   tabL[y] = lgamma(y+r) - lgamma(r) - lgamma(y+1) = sum_{j<y} [log(r+j) - log(j+1)]   (no cancellation)

@@ -1272,7 +1272,11 @@ static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
     const auto t0 = std::chrono::steady_clock::now();
     CK(cudaMemsetAsync(ctx->dp_flag, 0, 2 * sizeof(int), ctx->stream));
     DISPATCH_K(ctx->K, {
-      if (nd == DISP_ND) LAUNCH_ROWS((k_disp_nr<KT, DISP_ND>), 1, nlive, geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
+      if (a.Ecache) {
+        if (nd == DISP_ND) k_disp_nr_cached<KT, DISP_ND><<<row_grid(nlive), ROW_THREADS, 0, ctx->stream>>>(geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
+        else k_disp_nr_cached<KT, 1><<<row_grid(nlive), ROW_THREADS, 0, ctx->stream>>>(geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
+        CKL();
+      } else if (nd == DISP_ND) LAUNCH_ROWS((k_disp_nr<KT, DISP_ND>), 1, nlive, geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
       else LAUNCH_ROWS((k_disp_nr<KT, 1>), 1, nlive, geom(ctx, nlive, live), disp_state<KT>(ctx, s), a);
     });
     ctx->disp_nr_sweeps++;
@@ -1351,8 +1355,14 @@ static int disp_grid(ruvnb_ctx* ctx, const StateSet& s) {
     RET(disp_nr(ctx, s, a, DISP_ND));
     const auto t_apl = std::chrono::steady_clock::now();
     DISPATCH_K(ctx->K, {
-      LAUNCH_ROWS((k_disp_apl<KT, DISP_ND>), 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)c * YT,
-                  ctx->dp_lgr_grid + c, ctx->dp_hist, ctx->dp_l0, DISP_NG);
+      if (a.Ecache) {
+        k_disp_apl_cached<KT, DISP_ND><<<row_grid(Gl), ROW_THREADS, 0, ctx->stream>>>(geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)c * YT,
+                                                                                    ctx->dp_lgr_grid + c, ctx->dp_hist, ctx->dp_l0, DISP_NG);
+        CKL();
+      } else {
+        LAUNCH_ROWS((k_disp_apl<KT, DISP_ND>), 1, Gl, geom(ctx, Gl, nullptr), disp_state<KT>(ctx, s), a, ctx->dp_tabG + (long long)c * YT,
+                    ctx->dp_lgr_grid + c, ctx->dp_hist, ctx->dp_l0, DISP_NG);
+      }
     });
     if (getenv("RUVNB_TRACE_DISP")) {
       CK(cudaStreamSynchronize(ctx->stream));
