@@ -27,8 +27,14 @@ def _ctx(Y, ctl, truth, W, alpha, Mb, k):
     return ctx, _lib.default_opts(k=k)
 
 
-def test_apl_grid_matches_oracle():
+@pytest.mark.parametrize("ecache", [True, False])
+def test_apl_grid_matches_oracle(ecache, monkeypatch):
+    """l0 of the 21-point grid against the oracle, on the exp(offset) cache and on the recompute path (what a shard too
+    large for the cache runs), then once more on the same context: the second call starts from the first call's
+    intercepts and must land on the same values."""
     from oracle import edger
+    if not ecache:
+        monkeypatch.setenv("RUVNB_NO_ECACHE", "1")
     Y, ctl, truth, W, alpha, Mb, offs = _case()
     Y[7] = 0            # all-zero gene: rowSums < 5 -> not selected
     Y[8, :] = 0
@@ -37,7 +43,10 @@ def test_apl_grid_matches_oracle():
     ctx, opts = _ctx(Y, ctl, truth, W, alpha, Mb, 2)
     with ctx:
         l0, rs = ctx.disp_apl_grid(opts)
+        l0b, _ = ctx.disp_apl_grid(opts)
     assert np.array_equal(rs, Y.sum(axis=1))
+    ok = np.isfinite(l0)
+    assert np.array_equal(ok, np.isfinite(l0b)) and np.abs(l0b[ok] / l0[ok] - 1).max() < 1e-9   # both within the NR tolerance of the same root
     sel = rs >= 5
     assert np.isnan(l0[~sel]).all() and not sel[7] and not sel[8]
     ref = edger.apl_grid(Y[sel].astype(float), offs[sel])
