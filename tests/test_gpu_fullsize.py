@@ -59,3 +59,46 @@ def test_cfg2_full_size_sampled_rows_match_oracle():
     ref_l0 = edger.apl_grid(Ys[sel], offs[sel])
     err = np.abs(l0[s][sel] - ref_l0) / np.abs(ref_l0)
     assert err.max() < 1e-9, err.max()
+
+
+def test_get_res_full_width_sampled_rows_match_oracle():
+    """get.res over all 100 000 cells in the reference's 5 000-cell blocks: logcounts and percentile-adjusted counts are
+    gene-local within a block (the caps are per gene), so sampled rows are compared with the oracle run on those rows;
+    the Pearson clip limits are quantiles over the whole block slab, so there the comparison is on the unclipped entries
+    and on the clipped fraction (1 % by construction)."""
+    import torch
+    import bench
+    from oracle import getres
+    from ruviiinb_b200 import _lib
+
+    G, N, k, m, n_ctl = 1500, 100000, 5, 50, 200
+    dev = torch.device("cuda", 0)
+    tp = bench.truth_params(G, N, k, m, n_ctl)
+    Yh = torch.empty((G, N), dtype=torch.int32, pin_memory=True).numpy()
+    bench.gen_rows_gpu(tp, np.arange(G), Yh, dev)
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    grp = np.asarray(tp["grp"])
+    with _lib.Context(0) as ctx:
+        ctx.set_design(G, N, grp, tp["ctl"])
+        ctx.upload_counts(Yh)
+        for name, key in (("W", "W"), ("alpha", "alpha"), ("gmean", "gmean"), ("Mb", "Mb"), ("psi", "psi")):
+            ctx.set_state(name, tp[key])
+        got = {kind: ctx.get_res(kind, block_size=5000) for kind in (1, 2, 3)}
+    s = np.unique(np.random.default_rng(8).choice(G, 5, replace=False))
+    out = dict(counts=Yh[s], a=tp["alpha"][s], W=tp["W"], gmean=tp["gmean"][s], Mb=tp["Mb"][s][:, grp], psi=tp["psi"][s])
+    ref2 = getres.get_res(out, 2, block_size=5000)
+    assert np.allclose(got[2][s], ref2, rtol=1e-12, atol=1e-14)
+    ref3 = getres.get_res(out, 3, block_size=5000)
+    mism = got[3][s] != ref3
+    assert mism.mean() <= 1e-5, (mism.sum(), got[3][s][mism][:5], ref3[mism][:5])     # quantile-boundary ties only
+    assert np.array_equal(got[3], np.round(got[3])) and got[3].min() >= 0             # counts
+    # Pearson: per block the two clip limits are attained by 0.5 % of the entries each; everything else is the raw residual
+    ref1 = getres.get_res(out, 1, block_size=5000)           # same per-gene caps; its clip limits are the sample's own
+    for b0 in range(0, N, 5000):
+        blk, rb = got[1][:, b0:b0 + 5000], ref1[:, b0:b0 + 5000]
+        lo, hi = blk.min(), blk.max()
+        frac = ((blk == lo) | (blk == hi)).mean()
+        assert 0.009 < frac < 0.0115, (b0, frac)
+        inside = (blk[s] > lo) & (blk[s] < hi) & (rb > rb.min()) & (rb < rb.max())
+        assert inside.mean() > 0.95
+        assert np.abs(blk[s][inside] - rb[inside]).max() <= 1e-10 * np.abs(rb).max()
