@@ -44,7 +44,8 @@ struct DispArgs {
   const double* sy_row;     // [Gl] sum y of every row (k_disp_init): the APL needs no offset then
   double* step_prev;        // [Gl][ldb] last step of every column (0 before the first): Fisher scoring converges linearly, so
                             // rho = |step / step_prev| predicts the next step; a column whose NEXT step would be below tol
-                            // stops now -- edgeR would spend one more sweep to apply a change < tol (1e-10) and stop
+                            // stops now -- edgeR would spend one more sweep to apply a change < tol (1e-10) and stop.
+                            // Only for |step| < 1e-8: info_out is the information BEFORE the step is applied
   int* done;                // [Gl] rows whose ND intercepts have all converged: later sweeps skip them (edgeR stops each
                             // fit at |step| < tol; rows converge after 4-8 steps, a few stragglers need 15-20)
 };
@@ -216,7 +217,7 @@ struct OpDispNR {
             double* sp = a.step_prev + (long long)row * a.ldb + a.d0 + d * a.ds;
             const double prev = *sp;
             *sp = step;
-            if (!conv && prev != 0.0) { double rho = fabs(step / prev); conv = rho < 0.5 && rho * fabs(step) < a.tol; }
+            if (!conv && prev != 0.0 && fabs(step) < 1e-8) { double rho = fabs(step / prev); conv = rho < 0.5 && rho * fabs(step) < a.tol; }
           }
           nc |= !conv;
         }
