@@ -193,7 +193,13 @@ int ruvnb_accept(ruvnb_ctx* ctx);
  *     ruvnb_disp_apl_grid: the Cox-Reid adjusted profile likelihood on the 21-point grid
  *     0.1*2^seq(-10,10) (:33-37,84-127) -> l0 (local rows x 21, column-major; rows with
  *     rowSums(y) < 5 are NaN), and AveLogCPM-ready intercepts.
- *     ruvnb_estimate_disp: grid + common + trend + prior + WLEB -> sets "psi" (tagwise). */
+ *     ruvnb_estimate_disp: grid + common + trend + prior + WLEB -> sets "psi" (tagwise).
+ *     The one-group fits stop at edgeR's tolerance (|step| < 1e-10, at most 50 sweeps) or one sweep earlier when the
+ *     next step is predicted below it; start values differ from edgeR's (neighbouring grid point, earlier call) but the
+ *     root of the concave score is the same.  Device memory: while free memory allows (need + max(8 GB, 1/8 of the
+ *     device)), the context keeps exp(offset) of every (local gene, cell) for the duration of the step (8 B per
+ *     element, allocated at the first call); the environment variable RUVNB_NO_ECACHE=1 turns that off.
+ *     RUVNB_TRACE_DISP=1 prints every sweep's time and converged rows on stderr. */
 int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double* rowsum);
 int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out);
 /* Same with the outputs of estimateDisp.par exposed: prior_df_in >= 0 injects prior.df (the reference derives it with

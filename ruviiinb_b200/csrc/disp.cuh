@@ -21,6 +21,7 @@ template <int K, int ND>
 struct DispRowShared {
   RowShared base;
   double tg[ND][YT];  // lgamma(y + r_d) - lgamma(r_d) - lgamma(y + 1)
+  FmRL rl[FM_NT];     // log tables interleaved (cached APL sweep)
 };
 
 struct DispArgs {
@@ -265,6 +266,7 @@ struct OpDispAPL {
   double eb[ND], r[ND], ll[ND];
   double syo, sy, sw, egm;  // sum w y offset, sum w y, sum w
   double* l0; int ld0; ERow er;
+  const FmRL* rl; bool rowok;   // cached sweep: every e^beta_d E + r_d of the row is a normal number while E < 1e280
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
     er.begin(a.Ecache, row, a.Np, a.nchunks);
@@ -275,6 +277,9 @@ struct OpDispAPL {
       r[d] = 1.0 / a.phi_grid[d * a.ds];
       ll[d] = 0.0;
     }
+    rowok = true;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) rowok &= (eb[d] < 1e20) & (r[d] > 1e-290) & (r[d] < 1e290);
     syo = 0.0; sy = 0.0;
   }
   __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; }
@@ -286,6 +291,9 @@ struct OpDispAPL {
       sw += wzv;
 #pragma unroll
       for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]) * wzv, flog(fma(eb[d], E, r[d]), g.mt->rc, g.mt->lc), ll[d]);
+    } else if (CACHED && rowok && E < 1e280) {   // no range checks inside, one table load per logarithm
+#pragma unroll
+      for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]), flog_nc2(fma(eb[d], E, r[d]), rl), ll[d]);
     } else {
 #pragma unroll
       for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]), flog(fma(eb[d], E, r[d]), g.mt->rc, g.mt->lc), ll[d]);
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl(RowGeom geo, GeneSt
   if (threadIdx.x == 0) sh.base.wsets[0] = st.W;
   for (int i = threadIdx.x; i < ND * YT; i += ROW_THREADS) (&sh.tg[0][0])[i] = tabG[(long long)(i / YT) * a.ds * YT + (i % YT)];
   OpDispAPL<K, ND> op;
-  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0;
+  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0; op.rl = sh.rl;
   stream_rows<K, 1>(geo, &sh.base, op, smem);
 }
 
@@ -353,8 +361,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl_cached(RowGeom geo,
                                                                     const int* hist, double* l0, int ld0) {
   __shared__ DispRowShared<K, ND> sh;
   for (int i = threadIdx.x; i < ND * YT; i += ROW_THREADS) (&sh.tg[0][0])[i] = tabG[(long long)(i / YT) * a.ds * YT + (i % YT)];
+  for (int i = threadIdx.x; i < FM_NT; i += ROW_THREADS) { sh.rl[i].rc = geo.mtabs->rc[i]; sh.rl[i].lc = geo.mtabs->lc[i]; }
   OpDispAPL<K, ND, true> op;
-  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0;
+  op.st = st; op.a = a; op.tg = sh.tg; op.lgr_grid = lgr_grid; op.hist = hist; op.l0 = l0; op.ld0 = ld0; op.rl = sh.rl;
   stream_rows_lean(geo, &sh.base, op);
 }
 

@@ -102,6 +102,23 @@ __host__ __device__ __forceinline__ double flog_nc(double v, const double* __res
   return fma(ed, 0.6931471805599453, fma(u, q, lc[j]));
 }
 
+// the same with the two table entries of an interval side by side ({rc[j], lc[j]}): one 16-byte load per logarithm
+struct FmRL { double rc, lc; };
+__host__ __device__ __forceinline__ double flog_nc2(double v, const FmRL* __restrict__ rl) {
+  int hi = FM_HI(v);
+  int e = (hi >> 20) - 1023;
+  const FmRL t = rl[(hi >> 13) & (FM_NT - 1)];
+  double m = FM_MK((hi & 0x000fffff) | 0x3ff00000, FM_LO(v));
+  double u = fma(m, t.rc, -1.0);
+  double q = fma(u, -1.0 / 6.0, 0.2);
+  q = fma(u, q, -0.25);
+  q = fma(u, q, 1.0 / 3.0);
+  q = fma(u, q, -0.5);
+  q = fma(u, q, 1.0);
+  double ed = FM_MK(0x43300000, (int)(0x80000000u ^ (unsigned)e)) - 4503601774854144.0;  // (double)e without I2F
+  return fma(ed, 0.6931471805599453, fma(u, q, t.lc));
+}
+
 // 1/x for normal positive x (callers guard the range)
 __host__ __device__ __forceinline__ double frcp(double x) {
 #if defined(__CUDA_ARCH__)
