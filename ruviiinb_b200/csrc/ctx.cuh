@@ -188,6 +188,19 @@ struct ruvnb_ctx {
   } while (0)
 #define RET(x) do { int r_ = (x); if (r_ != RUVNB_OK) return r_; } while (0)
 
+// call-scoped device buffers: released on every way out of the call (error returns included)
+struct ScopedDev {
+  std::vector<void*> ptrs;
+  ~ScopedDev() { for (void* q : ptrs) cudaFree(q); }
+  template <class T>
+  cudaError_t alloc(T** out, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+    if (e == cudaSuccess) { ptrs.push_back(q); *out = (T*)q; }
+    return e;
+  }
+};
+
 template <class T>
 static int dev_alloc(ruvnb_ctx* ctx, T** p, long long n) {
   void* q = nullptr;

@@ -289,8 +289,13 @@ struct OpDispAPL {
     if (g.zi) {
       const double wzv = g.wz(y, E * egm, pos);
       sw += wzv;
+      if (CACHED && rowok && E < 1e280) {
 #pragma unroll
-      for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]) * wzv, flog(fma(eb[d], E, r[d]), g.mt->rc, g.mt->lc), ll[d]);
+        for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]) * wzv, flog_nc2(fma(eb[d], E, r[d]), rl), ll[d]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]) * wzv, flog(fma(eb[d], E, r[d]), g.mt->rc, g.mt->lc), ll[d]);
+      }
     } else if (CACHED && rowok && E < 1e280) {   // no range checks inside, one table load per logarithm
 #pragma unroll
       for (int d = 0; d < ND; ++d) ll[d] = fma(-(yd + r[d]), flog_nc2(fma(eb[d], E, r[d]), rl), ll[d]);

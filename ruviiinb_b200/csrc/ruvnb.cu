@@ -1406,8 +1406,9 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   std::vector<double> l0((size_t)G * DISP_NG, 0.0), rowsum(G, 0.0);
   double* d_l0_full = ctx->dp_l0; double* d_rs_full = ctx->dp_rowsum;
   double *tmpA = nullptr, *tmpB = nullptr;
+  ScopedDev scratch;
   if (ctx->nranks > 1) {
-    CK(cudaMalloc((void**)&tmpA, (size_t)G * DISP_NG * 8)); CK(cudaMalloc((void**)&tmpB, (size_t)G * 8));
+    CK(scratch.alloc(&tmpA, (size_t)G * DISP_NG * 8)); CK(scratch.alloc(&tmpB, (size_t)G * 8));
     CK(cudaMemsetAsync(tmpA, 0, (size_t)G * DISP_NG * 8, ctx->stream)); CK(cudaMemsetAsync(tmpB, 0, (size_t)G * 8, ctx->stream));
     CK(cudaMemcpyAsync(tmpA + g0 * DISP_NG, ctx->dp_l0, (size_t)Gl * DISP_NG * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(tmpB + g0, ctx->dp_rowsum, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1531,8 +1532,6 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   CK(cudaMemcpyAsync(s.psi, old.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->psi_ver++; s.sig_valid = false;
-  if (tmpA) CK(cudaFree(tmpA));
-  if (tmpB) CK(cudaFree(tmpB));
   if (o->verbose)
     fprintf(stderr, "estimateDisp: grid APL %.3f s (%d NR sweeps + 3 APL sweeps), gather + common %.3f s, AveLogCPM %.3f s (%d sweeps), "
                     "trend %.3f s, prior d.f. %.3f s (%d sweeps + deviance), tagwise %.3f s\n",
@@ -2026,11 +2025,12 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
   int parts = std::max(1, std::min((int)(Np / CH), (4 * n_sm + row_blocks - 1) / row_blocks));
   const long long seg = ((Np / CH + parts - 1) / parts) * CH;
   parts = (int)((Np + seg - 1) / seg);
-  CK(cudaMalloc((void**)&rm, (size_t)nc * 8)); CK(cudaMalloc((void**)&U, (size_t)nc * K * 8)); CK(cudaMalloc((void**)&G, KK * 8)); CK(cudaMalloc((void**)&T, K * K * 8));
-  CK(cudaMalloc((void**)&Upart, (size_t)parts * nc * K * 8));
-  if (cudaMalloc((void**)&A, (size_t)nc * Np * 8) != cudaSuccess) {
-    cudaGetLastError(); cudaFree(rm); cudaFree(U); cudaFree(G); cudaFree(T); cudaFree(Upart);
-    return ctx->fail(RUVNB_ECUDA, "init_W: no room for the %d x %lld FP64 slab of log-ratios (%.1f GB)", nc, Np, (double)nc * Np * 8 / 1e9);
+  ScopedDev scratch;
+  CK(scratch.alloc(&rm, (size_t)nc * 8)); CK(scratch.alloc(&U, (size_t)nc * K * 8)); CK(scratch.alloc(&G, KK * 8)); CK(scratch.alloc(&T, K * K * 8));
+  CK(scratch.alloc(&Upart, (size_t)parts * nc * K * 8));
+  if (scratch.alloc(&A, (size_t)nc * Np * 8) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(RUVNB_ENOMEM, "init_W: no room for the %d x %lld FP64 slab of log-ratios (%.1f GB)", nc, Np, (double)nc * Np * 8 / 1e9);
   }
   double* V = ctx->cur.W; double* V2 = ctx->nw.W;
   k_svd_rowmean<<<nblk(nc, 8), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, Np, (double)ctx->N, rm); CKL();
@@ -2110,6 +2110,5 @@ extern "C" int ruvnb_init_W(ruvnb_ctx* ctx, int k, int max_iter, double tol, dou
   if (W_out) memcpy(W_out, Wh.data(), Wh.size() * 8);
   if (sv_out) for (int l = 0; l < K; ++l) sv_out[l] = sqrt(std::max(BtB[l * K + l], 0.0));
   if (iters_out) *iters_out = it;
-  CK(cudaFree(rm)); CK(cudaFree(U)); CK(cudaFree(G)); CK(cudaFree(T)); CK(cudaFree(A)); CK(cudaFree(Upart));
-  return RUVNB_OK;
+  return RUVNB_OK;   // scratch released by its scope
 }
