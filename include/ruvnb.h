@@ -116,8 +116,8 @@ int ruvnb_cert_diag(ruvnb_ctx* ctx, int out[8]);
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (2 flops per DFMA; a register-only DFMA-chain
  * kernel, best of 5): the denominator of the FP64 roofline bench.py reports beside the HBM one. */
 int ruvnb_measure_fp64(ruvnb_ctx* ctx, double* tflops);
-/* Host evaluation of the table-driven exp (which = 0) / log (which = 1) the kernels use (csrc/fastmath.cuh is
- * __host__ __device__): lets the CPU test-suite check the very source the GPU runs.  No device needed. */
+/* Host evaluation of the table-driven exp (which = 0) / log (which = 1) / unchecked log on the interleaved table
+ * (which = 2, normal positive arguments) the kernels use (csrc/fastmath.cuh is __host__ __device__): lets the CPU test-suite check the very source the GPU runs.  No device needed. */
 int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n);
 
 /* ---- multi-GPU wiring (gene sharding) -------------------------------- */

@@ -410,10 +410,11 @@ def fast_cap_psi(psi):
 
 
 def selftest_math(which, x):
-    """Host evaluation of the kernels' table-driven exp ('exp') / log ('log') -- csrc/fastmath.cuh."""
+    """Host evaluation of the kernels' table-driven exp ('exp') / log ('log') / unchecked log on the interleaved
+    table ('log_nc2', normal positive arguments) -- csrc/fastmath.cuh."""
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
-    rc = load().ruvnb_selftest_math({"exp": 0, "log": 1}[which], _ptr(x), _ptr(out), x.size)
+    rc = load().ruvnb_selftest_math({"exp": 0, "log": 1, "log_nc2": 2}[which], _ptr(x), _ptr(out), x.size)
     if rc != 0:
         raise RuvnbError(f"ruvnb_selftest_math failed with {rc}")
     return out

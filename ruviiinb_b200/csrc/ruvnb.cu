@@ -102,11 +102,13 @@ int ruvnb_cert_diag(ruvnb_ctx* ctx, int out[8]) {
 }
 int ruvnb_last_exact_cells(const ruvnb_ctx* ctx) { return ctx ? ctx->last_fail_cells : -1; }
 int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n) {
-  if (!x || !out || n < 0 || which < 0 || which > 1) return RUVNB_EARG;
+  if (!x || !out || n < 0 || which < 0 || which > 2) return RUVNB_EARG;
   static MathTabs mt;
+  static FmRL rl[FM_NT];
   static bool built = false;
-  if (!built) { build_math_tabs(&mt); built = true; }
-  for (int64_t i = 0; i < n; ++i) out[i] = which == 0 ? fexp(x[i], mt.ex) : flog(x[i], mt.rc, mt.lc);
+  if (!built) { build_math_tabs(&mt); for (int j = 0; j < FM_NT; ++j) { rl[j].rc = mt.rc[j]; rl[j].lc = mt.lc[j]; } built = true; }
+  // 2: the unchecked logarithm on the interleaved table (disp.cuh, cached APL sweep); normal positive arguments only
+  for (int64_t i = 0; i < n; ++i) out[i] = which == 0 ? fexp(x[i], mt.ex) : which == 1 ? flog(x[i], mt.rc, mt.lc) : flog_nc2(x[i], rl);
   return RUVNB_OK;
 }
 void* ruvnb_stream(const ruvnb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

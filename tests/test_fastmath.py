@@ -38,3 +38,12 @@ def test_flog_bulk_and_edges():
     assert np.abs(got - ref).max() < 1.5e-14
     sp = _lib.selftest_math("log", np.array([0.0, -1.0, np.inf, np.nan, 5e-324]))
     assert sp[0] == -np.inf and np.isnan(sp[1]) and sp[2] == np.inf and np.isnan(sp[3]) and np.isclose(sp[4], np.log(5e-324))
+
+
+def test_flog_nc2_is_flog_on_normal_arguments():
+    """The cached APL sweep's logarithm (one 16-byte table load, no range check) returns flog's bits wherever flog takes
+    its fast path."""
+    from ruviiinb_b200 import _lib
+    rng = np.random.default_rng(3)
+    v = np.concatenate([np.exp(rng.uniform(-600, 600, 200000)), 1.0 + rng.uniform(-1e-3, 1e-3, 50000), [1.0, 2.0, 1e-290, 1e290]])
+    assert np.array_equal(_lib.selftest_math("log_nc2", v), _lib.selftest_math("log", v))
