@@ -3,6 +3,7 @@
     ruvIII_nb(Y, M, ctl, k=2, ...)      R/ruvIIInb.R:27-629     -> dict with the reference's list elements
     get_res(out, type=..., ...)         R/get.res.R:12-129      -> G x N array
     makeSCE(obj, cData, batch, assays)  R/makeSCE.R:12-43       -> dict standing in for the SingleCellExperiment
+    estimateDisp_par(y, offset=...)     R/estimateDisp.par.R:3-202 -> dict with the reference's list elements
     fastruvIII_nb_finish(...)           R/fastruvIIInb.R:625-792 (the full-data passes after the subsample fit)
 
 Same argument names (dots become underscores), defaults and error behaviour: invalid input raises ValueError where the R
@@ -149,6 +150,90 @@ def makeSCE(obj, cData=None, batch=None, assays=("pearson", "logPAC")):
     if "logPAC" in want:
         sce["assays"]["logPAC"] = np.log(get_res(obj, type="quantile", batch=batch) + 1.0)   # R/makeSCE.R:36-38
     return sce
+
+
+def _factor_offset(offset, grp, m, tol=1e-9):
+    """offset (G x N) = Mb[:, grp] + alpha W' exactly, with k <= RUVNB_MAX_K: the form every offset of the reference has
+    (alpha W' + Mb[, grp], R/ruvIIInb.R:205-221,535-565) and the only one the device holds.  Group means go to Mb, the
+    rest must have numerical rank <= 8."""
+    O = np.asarray(offset, dtype=np.float64)
+    G, N = O.shape
+    cnt = np.bincount(grp, minlength=m).astype(np.float64)
+    Mb = np.zeros((G, m))
+    for j in range(m):
+        Mb[:, j] = O[:, grp == j].sum(axis=1) / cnt[j]
+    R = O - Mb[:, grp]
+    scale = max(1.0, float(np.abs(O).max()))
+    if np.abs(R).max() <= tol * scale:
+        return Mb, np.zeros((G, 1)), np.zeros((N, 1))
+    U, sv, Vt = np.linalg.svd(R, full_matrices=False)
+    for k in range(1, min(_lib.MAX_K, len(sv)) + 1):
+        alpha, W = U[:, :k] * sv[:k], Vt[:k].T
+        if np.abs(R - alpha @ W.T).max() <= tol * scale:
+            return Mb, alpha, W
+    raise ValueError(f"offset is not of the form alpha W' + Mb[, group] with at most {_lib.MAX_K} factors "
+                     "(the only offsets the reference passes, R/ruvIIInb.R:205-221); pass replicate_of_cell if the "
+                     "offset has a replicate-group part")
+
+
+def estimateDisp_par(y, design=None, group=None, lib_size=None, offset=None, prior_df=None, trend_method="locfit",
+                     tagwise=True, span=None, min_row_sum=5, grid_length=21, grid_range=(-10, 10), robust=False,
+                     winsor_tail_p=(0.05, 0.1), tol=1e-06, weights=None, BPPARAM=None, replicate_of_cell=None, device=0):
+    """estimateDisp.par (R/estimateDisp.par.R:3-202) as ruvIII.nb calls it: design = 1 (one coefficient), an offset matrix
+    of the form alpha W' + Mb[, grp], the 21-point grid 0.1 * 2^seq(-10, 10), trend.method = "locfit" (stood in for by the
+    local-constant tricube smoother), tagwise = TRUE.  Returns the reference's list elements
+    (common.dispersion, trended.dispersion, tagwise.dispersion, span, prior.df, prior.n).  Arguments the device path does
+    not implement raise ValueError instead of being ignored.  `replicate_of_cell` (0-based group of every cell) lets an
+    offset with a replicate-group part of any size be taken apart; `BPPARAM` is accepted and ignored."""
+    Y = np.asarray(y)
+    if Y.ndim != 2:
+        raise ValueError("y must be a matrix")
+    G, N = Y.shape
+    if G == 0:
+        return dict(span=span, **{"prior.df": prior_df, "prior.n": None})                       # :13-14
+    if design is not None:
+        d = np.asarray(design, dtype=np.float64)
+        if d.shape not in ((N,), (N, 1)) or not np.all(d == 1.0):
+            raise ValueError("only design = matrix(1, ncol(y)) (one intercept) is on the device path")
+    if group is not None and len(np.unique(np.asarray(group))) != 1:
+        raise ValueError("a grouping with more than one level needs a design with more than one coefficient: not on the device path")
+    if group is not None and len(np.asarray(group)) != N:
+        raise ValueError("Incorrect length of group.")                                              # :19-20
+    if weights is not None:
+        raise ValueError("observation weights are derived on the device from the ZINB state (opts.zinb); a weight matrix is not accepted")
+    if trend_method != "locfit" or not tagwise or robust or span is not None:
+        raise ValueError("only trend.method = 'locfit', tagwise = TRUE, robust = FALSE, span = NULL are on the device path")
+    if grid_length != 21 or tuple(grid_range) != (-10, 10) or min_row_sum != 5:
+        raise ValueError("the device grid is 0.1 * 2^seq(-10, 10, length = 21) with min.row.sum = 5")
+    if lib_size is not None and len(np.asarray(lib_size)) != N:
+        raise ValueError("Incorrect length of lib.size.")                                           # :24-25
+    if offset is None:                                                                              # .compressOffsets: log(lib.size)
+        ls = Y.sum(axis=0).astype(np.float64) if lib_size is None else np.asarray(lib_size, dtype=np.float64)
+        offset = np.broadcast_to(np.log(ls)[None, :], (G, N))
+    offset = np.asarray(offset, dtype=np.float64)
+    if offset.shape != (G, N):
+        raise ValueError("offset must be a matrix of the dimensions of y")
+    if not np.all(np.isfinite(offset)):
+        raise ValueError("offsets must be finite values")
+    grp = np.zeros(N, dtype=np.int32) if replicate_of_cell is None else np.asarray(replicate_of_cell, dtype=np.int32)
+    if grp.shape != (N,) or grp.min() < 0:
+        raise ValueError("replicate_of_cell must give a 0-based group for every column of y")
+    m = int(grp.max()) + 1
+    Mb, alpha, W = _factor_offset(offset, grp, m)
+    k = alpha.shape[1]
+    opts = _lib.default_opts(k=k)
+    ctl = np.zeros(G, dtype=bool)
+    ctl[0] = True                                   # the dispersion step does not read the control set
+    with _lib.Context(device) as ctx:
+        ctx.set_design(G, N, grp, ctl)
+        ctx.upload_counts(np.ascontiguousarray(Y, dtype=np.int32))
+        ctx.set_state("W", W); ctx.set_state("alpha", alpha); ctx.set_state("Mb", Mb)
+        out = ctx.estimate_disp_ex(opts, prior_df=prior_df)
+        tag = ctx.get_state("psi")
+    ns = int((Y.sum(axis=1) >= 5).sum())
+    return {"common.dispersion": out["common"], "trended.dispersion": out["trended"], "tagwise.dispersion": tag,
+            "span": 1.0 if ns <= 50 else 0.25 + 0.75 * np.sqrt(50.0 / ns),                          # edgeR::WLEB default
+            "prior.df": out["prior_df"], "prior.n": out["prior_df"] / (N - 1.0)}                   # :171, ncoefs = 1
 
 
 def _estimate_disp_subset(Ysub, grp, ctl, alpha, W, Mb, cols, k, device):

@@ -57,6 +57,52 @@ def test_api_argument_errors_mirror_stop():
         api.ruvIII_nb(Y, M, ctl, use_pseudosample=True)
     with pytest.raises(ValueError, match="unknown type"):
         api.get_res(dict(pi0=None, psi=np.ones(3)), type="foo")
+    # estimateDisp.par: the reference's own stop() conditions, then what the device path does not implement
+    with pytest.raises(ValueError, match="Incorrect length of group"):
+        api.estimateDisp_par(Y, group=np.ones(3))
+    with pytest.raises(ValueError, match="Incorrect length of lib.size"):
+        api.estimateDisp_par(Y, lib_size=np.ones(3))
+    with pytest.raises(ValueError, match="offsets must be finite"):
+        api.estimateDisp_par(Y, offset=np.full(Y.shape, np.inf))
+    with pytest.raises(ValueError, match="device path"):
+        api.estimateDisp_par(Y, trend_method="loess")
+    with pytest.raises(ValueError, match="weight matrix"):
+        api.estimateDisp_par(Y, weights=np.ones(Y.shape))
+    with pytest.raises(ValueError, match="not of the form"):
+        api.estimateDisp_par(Y, offset=np.random.default_rng(0).standard_normal(Y.shape))
+
+
+def test_offset_factorisation_is_exact():
+    """api._factor_offset: alpha W' + Mb[, grp] is recovered (as some exact factorisation) with and without the groups."""
+    from ruviiinb_b200 import api
+    rng = np.random.default_rng(4)
+    G, N, k, m = 40, 90, 3, 4
+    grp = rng.integers(0, m, N).astype(np.int32); grp[:m] = np.arange(m)
+    O = rng.standard_normal((G, k)) @ rng.standard_normal((N, k)).T + rng.standard_normal((G, m))[:, grp]
+    for g, mm in ((grp, m), (np.zeros(N, dtype=np.int32), 1)):
+        Mb, alpha, W = api._factor_offset(O, g, mm)
+        assert alpha.shape[1] <= 8 and np.abs(Mb[:, g] + alpha @ W.T - O).max() < 1e-9 * np.abs(O).max()
+    Mb, alpha, W = api._factor_offset(np.broadcast_to(rng.standard_normal(G)[:, None], (G, N)), np.zeros(N, dtype=np.int32), 1)
+    assert alpha.shape == (G, 1) and not alpha.any() and not W.any()      # a per-gene constant: nothing left after Mb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_groups", [True, False])
+def test_estimateDisp_par_matches_oracle(with_groups):
+    """estimateDisp.par called on its own, as the reference exports it: y and an offset matrix in, the list out."""
+    from oracle import edger
+    from ruviiinb_b200 import api, synth
+    Y, M, ctl, truth = synth.make_counts(160, 650, 2, 3, 40, seed=35, gmean_mu=0.5)
+    grp = truth["grp"]
+    Wn = truth["W"] / np.sqrt((truth["W"] ** 2).sum(axis=0))
+    offs = (truth["alpha"] * np.sqrt((truth["W"] ** 2).sum(axis=0))) @ Wn.T + truth["Mb"][:, grp]
+    ref = edger.estimate_disp(Y.astype(float), offs)
+    out = api.estimateDisp_par(Y, offset=offs, replicate_of_cell=grp if with_groups else None)
+    assert abs(out["common.dispersion"] / ref["common"] - 1) < 1e-8
+    assert np.abs(out["trended.dispersion"] / ref["trended"] - 1).max() < 1e-7
+    assert abs(out["prior.df"] / ref["prior_df"] - 1) < 1e-6
+    assert np.abs(out["tagwise.dispersion"] / ref["tagwise"] - 1).max() < 1e-6
+    assert out["prior.n"] == out["prior.df"] / (Y.shape[1] - 1)
 
 
 @pytest.mark.gpu
