@@ -56,7 +56,40 @@ def full_fit(G, N, k, m, n_ctl, seed):
                 gmean=ref["gmean"], Mb=ref["Mb"], psi=ref["psi"])
 
 
+def dispersion(G, N, k, m, n_ctl, seed):
+    """estimateDisp.par on a fitted-looking state: the APL grid, common / trended / tagwise dispersion, prior d.f."""
+    from oracle import edger
+    Y, M, ctl, truth = synth.make_counts(G, N, k, m, n_ctl, seed=seed, gmean_mu=0.5)
+    rng = np.random.default_rng(seed)
+    W = truth["W"] / np.sqrt((truth["W"] ** 2).sum(axis=0))
+    alpha = truth["alpha"] * np.sqrt((truth["W"] ** 2).sum(axis=0)) + 0.05 * rng.standard_normal((G, k))
+    Mb = truth["Mb"] + 0.05 * rng.standard_normal((G, m))
+    Y[3] = 0                      # an all-zero gene (rowSums < 5: not selected, takes the trend's value)
+    offs = alpha @ W.T + Mb[:, truth["grp"]]
+    Yf = Y.astype(np.float64)
+    sel = Yf.sum(axis=1) >= 5
+    l0 = np.full((G, 21), np.nan)
+    l0[sel] = edger.apl_grid(Yf[sel], offs[sel])
+    ref = edger.estimate_disp(Yf, offs)
+    return dict(Y=Y.astype(np.int32), grp=truth["grp"].astype(np.int32), ctl=ctl, W=W, alpha=alpha, Mb=Mb, l0=l0,
+                common=np.array(ref["common"]), trended=ref["trended"], tagwise=ref["tagwise"], prior_df=np.array(ref["prior_df"]))
+
+
+def residuals(G, N, k, m, n_ctl, seed, block_size):
+    """get.res of a fitted-looking state: Pearson, logcounts, percentile-adjusted counts, in blocks of `block_size` cells."""
+    from oracle import getres
+    Y, M, ctl, truth = synth.make_counts(G, N, k, m, n_ctl, seed=seed, gmean_mu=0.3)
+    W = truth["W"] / np.sqrt((truth["W"] ** 2).sum(axis=0))
+    a = truth["alpha"] * np.sqrt((truth["W"] ** 2).sum(axis=0))
+    out = dict(counts=Y, a=a, W=W, gmean=truth["gmean"], Mb=truth["Mb"][:, truth["grp"]], psi=truth["psi"])
+    return dict(Y=Y.astype(np.int32), grp=truth["grp"].astype(np.int32), ctl=ctl, W=W, alpha=a, gmean=truth["gmean"], Mb=truth["Mb"],
+                psi=truth["psi"], block_size=np.array(block_size), pearson=getres.get_res(out, 1, block_size),
+                logcounts=getres.get_res(out, 2, block_size), pac=getres.get_res(out, 3, block_size))
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "disp_k2_m3.npz"), **dispersion(90, 420, 2, 3, 20, 2029))
+    np.savez_compressed(os.path.join(HERE, "res_k2_m3.npz"), **residuals(40, 300, 2, 3, 12, 2030, 128))
     np.savez_compressed(os.path.join(HERE, "iter_k2_m3.npz"), **one_iteration(48, 300, 2, 3, 12, 2026, False))
     np.savez_compressed(os.path.join(HERE, "iter_k3_m4_robust.npz"), **one_iteration(40, 260, 3, 4, 12, 2027, True))
     np.savez_compressed(os.path.join(HERE, "fit_k2_m3.npz"), **full_fit(40, 260, 2, 3, 12, 2028))

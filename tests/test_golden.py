@@ -69,3 +69,57 @@ def test_cuda_matches_fit_golden():
         assert np.allclose(logl, g["logl_outer"], rtol=1e-6, atol=0)
         for n, key in (("W", "W"), ("alpha", "alpha"), ("gmean", "gmean"), ("Mb", "Mb"), ("psi", "psi")):
             assert _rel(ctx.get_state(n), g[key], 1e-6) < 1e-6, n
+
+
+def test_oracle_reproduces_dispersion_golden():
+    from oracle import edger
+    g = _load("disp_k2_m3.npz")
+    Y = g["Y"].astype(np.float64)
+    offs = g["alpha"] @ g["W"].T + g["Mb"][:, g["grp"]]
+    ref = edger.estimate_disp(Y, offs)
+    assert np.allclose(ref["tagwise"], g["tagwise"], rtol=1e-12) and np.allclose(ref["trended"], g["trended"], rtol=1e-12)
+    assert abs(ref["common"] / g["common"] - 1) < 1e-12 and abs(ref["prior_df"] / g["prior_df"] - 1) < 1e-10
+
+
+def test_oracle_reproduces_residual_golden():
+    from oracle import getres
+    g = _load("res_k2_m3.npz")
+    out = dict(counts=g["Y"], a=g["alpha"], W=g["W"], gmean=g["gmean"], Mb=g["Mb"][:, g["grp"]], psi=g["psi"])
+    bs = int(g["block_size"])
+    assert np.allclose(getres.get_res(out, 1, bs), g["pearson"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(getres.get_res(out, 2, bs), g["logcounts"], rtol=1e-12, atol=1e-14)
+    assert np.array_equal(getres.get_res(out, 3, bs), g["pac"])
+
+
+@pytest.mark.gpu
+def test_cuda_matches_dispersion_golden():
+    from ruviiinb_b200 import _lib
+    from tests.parity import make_ctx
+    g = _load("disp_k2_m3.npz")
+    opts = _lib.default_opts(k=g["W"].shape[1])
+    with make_ctx(g["Y"], g["grp"], g["ctl"]) as ctx:
+        ctx.set_state("W", g["W"]); ctx.set_state("alpha", g["alpha"]); ctx.set_state("Mb", g["Mb"])
+        l0, rs = ctx.disp_apl_grid(opts)
+        out = ctx.estimate_disp_ex(opts)
+        psi = ctx.get_state("psi")
+    sel = ~np.isnan(g["l0"][:, 0])
+    assert np.array_equal(sel, rs >= 5) and np.isnan(l0[~sel]).all()
+    assert (np.abs(l0[sel] - g["l0"][sel]) / np.abs(g["l0"][sel])).max() < 1e-9
+    assert abs(out["common"] / g["common"] - 1) < 1e-8
+    assert np.abs(out["trended"] / g["trended"] - 1).max() < 1e-7
+    assert abs(out["prior_df"] / g["prior_df"] - 1) < 1e-6
+    assert np.abs(psi / g["tagwise"] - 1).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_cuda_matches_residual_golden():
+    from tests.parity import make_ctx
+    g = _load("res_k2_m3.npz")
+    bs = int(g["block_size"])
+    with make_ctx(g["Y"], g["grp"], g["ctl"]) as ctx:
+        for n in ("W", "alpha", "gmean", "Mb", "psi"):
+            ctx.set_state(n, g[n])
+        pearson, logc, pac = (ctx.get_res(kind, block_size=bs) for kind in (1, 2, 3))
+    assert np.abs(pearson - g["pearson"]).max() <= 1e-10 * np.abs(g["pearson"]).max()
+    assert np.allclose(logc, g["logcounts"], rtol=1e-12, atol=1e-14)
+    assert (pac != g["pac"]).sum() <= 1              # a quantile-boundary tie at most (12 000 entries)
