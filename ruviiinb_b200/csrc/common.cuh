@@ -84,7 +84,7 @@ __device__ __forceinline__ void nb_big_logs(double yd, double r, const MathTabs*
   *lyr = flog(yd + r, mt->rc, mt->lc);
   *lyy = flog(yd, mt->rc, mt->lc);
 }
-__device__ __noinline__ double nb_slow_lgterm(double yd, double r, double lgr) { return lgamma(yd + r) - lgr - lgamma(yd + 1.0); }
+static __device__ __noinline__ double nb_slow_lgterm(double yd, double r, double lgr) { return lgamma(yd + r) - lgr - lgamma(yd + 1.0); }
 __device__ __forceinline__ double nb_big_lgterm(double yd, double r, double lgr, const MathTabs* mt) {
   if (!(r < 1e100 && yd < 1e15)) return nb_slow_lgterm(yd, r, lgr);
   double a = yd + r, b = yd + 1.0;
@@ -127,7 +127,7 @@ __device__ __forceinline__ double nb_logpmf_t(int y, double yd, double lmu, doub
 // (R/ruvIIInb.R:305,321) with ONE reciprocal: both share the denominator (1 + psi mu)(mu + .01).
 struct SQ { double mu, s, q; };
 // the reference's own formulas with libdevice: out-of-range arguments (rare), kept out of line
-__device__ __noinline__ SQ nb_sq_slow(double yd, double lmu, double psi) {
+static __device__ __noinline__ SQ nb_sq_slow(double yd, double lmu, double psi) {
   SQ o;
   o.mu = exp(lmu);
   o.s = 1.0 / (1.0 / o.mu + psi);

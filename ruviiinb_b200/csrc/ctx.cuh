@@ -1,4 +1,5 @@
-// ctx.cuh -- host-side context of libruvnb_b200: device buffers, launch helpers, NCCL wiring.
+// ctx.cuh -- host-side context of libruvnb_b200: device buffers, error macros, NCCL wiring, and the host functions the
+// translation units share (core.cu, irls.cu, sweep_*.cu, disp.cu, res.cu, fast.cu, svd.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -12,13 +13,9 @@
 #include <vector>
 
 #include "../../include/ruvnb.h"
-#include "kernels.cuh"
-#include "disp.cuh"
-#include "res.cuh"
-#include "zinb.cuh"
-#include "fast.cuh"
-#include "fastfit.cuh"
-#include "svd.cuh"
+#include "fastmath.cuh"
+
+struct NMState;   // zinb.cuh
 
 // ---- NCCL through dlopen: single-GPU use never needs libnccl, and a host that already loaded
 // torch's bundled libnccl.so.2 shares that copy (same soname) --------------------------------------
@@ -45,7 +42,7 @@ struct NcclApi {
     return true;
   }
 };
-static NcclApi g_nccl;
+inline NcclApi g_nccl;   // one copy for the whole library (C++17 inline variable)
 enum { NCCL_INT32 = 2, NCCL_INT64 = 4, NCCL_F64 = 8 };  // ncclDataType_t values (nccl.h)
 enum { NCCL_SUM = 0 };
 
@@ -251,3 +248,10 @@ static void kev_collect(ruvnb_ctx* ctx) {
     case 8: { constexpr int KT = 8; __VA_ARGS__; } break;            \
     default: return ctx->fail(RUVNB_EARG, "k = %d outside 1..%d", KVAL, RUVNB_MAX_K); \
   }
+
+// ---- host functions shared between the translation units ------------------------------------------------------------
+int ensure_state(ruvnb_ctx* ctx, int K);                              // core.cu
+int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o);                 // core.cu
+int ensure_roworder(ruvnb_ctx* ctx);                                  // core.cu
+int ensure_ytabs(ruvnb_ctx* ctx, const double* psi);                  // core.cu
+int make_rmw(ruvnb_ctx* ctx, const double* W);                        // irls.cu

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_apl_cached(RowGeom geo,
 
 // counts of each value 1 .. YT-1 in every row (pads hold -1): one CTA per row, shared-memory histogram.  Depends on the
 // counts only, so it is built once per upload / Winsorize.
-__global__ void __launch_bounds__(256) k_row_hist(const int32_t* __restrict__ Yp, long long Np, int* __restrict__ hist) {
+static __global__ void __launch_bounds__(256) k_row_hist(const int32_t* __restrict__ Yp, long long Np, int* __restrict__ hist) {
   __shared__ int h[YT];
   const long long row = blockIdx.x;
   for (int i = threadIdx.x; i < YT; i += 256) h[i] = 0;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) k_row_hist(const int32_t* __restrict__ Yp
 }
 
 // rows with flag == 0 -> compact ascending list (one CTA, ordered scan): the NR sweeps after the bulk has converged
-__global__ void __launch_bounds__(1024) k_list_zero(int n, const int* flag, int* list, int* count) {
+static __global__ void __launch_bounds__(1024) k_list_zero(int n, const int* flag, int* list, int* count) {
   __shared__ int wsum[32];
   __shared__ int base;
   if (threadIdx.x == 0) base = 0;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_dev(RowGeom geo, GeneSt
 // ---- local-constant tricube smoother (locfit deg = 0 stand-in) -------------------------------------------------------
 // xs: covariate sorted ascending (n), perm: row of l0 for each sorted position; one CTA per sorted position i.  The q
 // nearest neighbours of xs[i] are a contiguous window of the sorted order; bandwidth h = distance to the q-th nearest.
-__global__ void __launch_bounds__(128) k_tricube(const double* xs, const int* perm, int n, int q, const double* l0, int ld0,
+static __global__ void __launch_bounds__(128) k_tricube(const double* xs, const int* perm, int n, int q, const double* l0, int ld0,
                                                  double* m0 /* [n][DISP_NG] in sorted order */) {
   __shared__ double red[4][DISP_NG + 1];
   __shared__ int s_lo;
@@ -718,11 +718,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_psi_newton(RowGeom geo, Gene
   op.st = st; op.theta = theta; op.tol = tol; op.notconv = notconv;
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
-__global__ void k_log_vec(const double* x, long long n, double* y) {
+static __global__ void k_log_vec(const double* x, long long n, double* y) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = log(x[i]);
 }
-__global__ void k_exp_vec(const double* x, long long n, double* y) {
+static __global__ void k_exp_vec(const double* x, long long n, double* y) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = exp(x[i]);
 }

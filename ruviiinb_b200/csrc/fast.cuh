@@ -102,7 +102,7 @@ struct FastMbArgs {
   const double *rmed, *rmad;                    // [Gl] row median / mad of the annotated columns
   double lambda_b;
 };
-__global__ void __launch_bounds__(1024) k_fast_mb(FastMbArgs a, double* slab) {
+static __global__ void __launch_bounds__(1024) k_fast_mb(FastMbArgs a, double* slab) {
   __shared__ double tile[32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = blockIdx.x * 32 + warp, c = blockIdx.y * 32 + lane;

@@ -22,7 +22,7 @@ struct FFGeom {
 __device__ __forceinline__ bool ff_valid(const FFGeom& g, long long pos) { return (int)(pos & (CH - 1)) < g.chunk_valid[pos >> 7]; }
 
 // Z = log(y + 1) -> Zbuf; gmean = rowMeans(Z); ZS[g][j] = group sums.  One warp per gene.
-__global__ void __launch_bounds__(256) k_ff_init_z(FFGeom ge, double n, double* Zbuf, double* gmean, double* ZS) {
+static __global__ void __launch_bounds__(256) k_ff_init_z(FFGeom ge, double n, double* Zbuf, double* gmean, double* ZS) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (g >= ge.Gl) return;
   const int32_t* y = ge.Yp + (long long)g * ge.Np;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_ff_init_z(FFGeom ge, double n, double* 
 }
 
 // working quantities of the current parameters; one warp per gene
-__global__ void __launch_bounds__(256) k_ff_working(FFGeom ge, const double* gmean, const double* Mb, const double* alpha, const double* W,
+static __global__ void __launch_bounds__(256) k_ff_working(FFGeom ge, const double* gmean, const double* Mb, const double* alpha, const double* W,
                                                    const double* psi, const double* step_c, double* Zbuf, double* SIbuf, double* ZS,
                                                    double* si_rowsum) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -92,20 +92,20 @@ __global__ void __launch_bounds__(256) k_ff_working(FFGeom ge, const double* gme
 }
 
 // wt.cell[pos] = mean over genes of sig.inv; one thread per position (coalesced across positions)
-__global__ void k_ff_colmean(FFGeom ge, const double* SIbuf, double* wt_cell) {
+static __global__ void k_ff_colmean(FFGeom ge, const double* SIbuf, double* wt_cell) {
   long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= ge.Np) return;
   double s = 0.0;
   if (ff_valid(ge, pos)) { for (int g = 0; g < ge.Gl; ++g) s += SIbuf[(long long)g * ge.Np + pos]; s /= (double)ge.Gl; }
   wt_cell[pos] = s;
 }
-__global__ void k_ff_cap(double* x, long long n, double cap) {
+static __global__ void k_ff_cap(double* x, long long n, double cap) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && x[i] >= cap) x[i] = cap;
 }
 
 // b[g][l] = sum_c (Z - Zbar[g][grp c]) wt.cell[c] RM_W[c][l]; one warp per gene
-__global__ void __launch_bounds__(256) k_ff_b(FFGeom ge, const double* Zbuf, const double* ZS, const int* group_n, const double* wt_cell,
+static __global__ void __launch_bounds__(256) k_ff_b(FFGeom ge, const double* Zbuf, const double* ZS, const int* group_n, const double* wt_cell,
                                              const double* RMW, double* b) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (g >= ge.Gl) return;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_ff_b(FFGeom ge, const double* Zbuf, con
   for (int l = 0; l < ge.K; ++l) { double v = warp_sum(acc[l]); if (lane == 0) b[(long long)g * ge.K + l] = v; }
 }
 // alpha_g = b_g Ginv (Ginv symmetric k x k, row-major); counts non-finite entries
-__global__ void k_ff_alpha(int Gl, int K, const double* b, const double* Ginv, double* alpha, int* bad) {
+static __global__ void k_ff_alpha(int Gl, int K, const double* b, const double* Ginv, double* alpha, int* bad) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
   int nb = 0;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_ff_w(FFGeom ge, const int* ctl_local, i
 }
 
 // S0[g][j] = sum_{c in j} sig.inv, S1[g][j] = sum sig.inv (Z - alpha_new W_new); one warp per gene
-__global__ void __launch_bounds__(256) k_ff_gsums(FFGeom ge, const double* Zbuf, const double* SIbuf, const double* alpha_new,
+static __global__ void __launch_bounds__(256) k_ff_gsums(FFGeom ge, const double* Zbuf, const double* SIbuf, const double* alpha_new,
                                                  const double* W_new, double* S0, double* S1) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (g >= ge.Gl) return;
@@ -204,13 +204,13 @@ __global__ void __launch_bounds__(256) k_ff_gsums(FFGeom ge, const double* Zbuf,
   }
   if (curj >= 0) { double v0 = warp_sum(s0), v1 = warp_sum(s1); if (lane == 0) { S0[(long long)g * ge.m + curj] = v0; S1[(long long)g * ge.m + curj] = v1; } }
 }
-__global__ void k_ff_zero_ctl_rows(int Gl, int m, const uint8_t* ctl_local, double* Mb) {
+static __global__ void k_ff_zero_ctl_rows(int Gl, int m, const uint8_t* ctl_local, double* Mb) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Gl * m) return;
   if (ctl_local[i / m]) Mb[i] = 0.0;
 }
 // unweighted group means of the residual for the initial Mb (:270: projection(..., Wmat = NULL) ignores lambda)
-__global__ void __launch_bounds__(256) k_ff_init_mb(FFGeom ge, const double* Zbuf, const double* gmean, const double* alpha, const double* W,
+static __global__ void __launch_bounds__(256) k_ff_init_mb(FFGeom ge, const double* Zbuf, const double* gmean, const double* alpha, const double* W,
                                                    const int* group_n, const uint8_t* ctl_local, double* Mb) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (g >= ge.Gl) return;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) k_ff_init_mb(FFGeom ge, const double* Zbu
 }
 
 // per-CELL log-likelihood sum_g log dnbinom(y; mu, 1/psi_g), non-finite -> log(DBL_MIN); one thread per position
-__global__ void k_ff_cell_loglik(FFGeom ge, const double* gmean, const double* Mb, const double* alpha, const double* W, const double* psi,
+static __global__ void k_ff_cell_loglik(FFGeom ge, const double* gmean, const double* Mb, const double* alpha, const double* W, const double* psi,
                                  const double* tabL /* [Gl][YT] */, const double* lgr, double* out) {
   long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= ge.Np) return;
@@ -259,7 +259,7 @@ __global__ void k_ff_cell_loglik(FFGeom ge, const double* gmean, const double* M
   out[pos] = acc;
 }
 // step[c] *= fac where loglik_old[c] > loglik_new[c] (per cell, :538-539)
-__global__ void k_ff_halve(long long Np, const double* ll_old, const double* ll_new, double fac, double* step) {
+static __global__ void k_ff_halve(long long Np, const double* ll_old, const double* ll_new, double fac, double* step) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Np && ll_old[i] > ll_new[i]) step[i] *= fac;
 }

@@ -285,7 +285,7 @@ __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* 
 //   tabL[y] = lgamma(y+r) - lgamma(r) - lgamma(y+1) = sum_{j<y} [log(r+j) - log(j+1)]   (no cancellation)
 //   tabR[y] = log(y + r),  lgr = lgamma(r).   One CTA of YT threads per gene.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(YT) k_build_ytabs(const double* psi, int rows, double* tabL, double* tabR, double* lgr) {
+static __global__ void __launch_bounds__(YT) k_build_ytabs(const double* psi, int rows, double* tabL, double* tabR, double* lgr) {
   __shared__ double term[YT];
   const int row = blockIdx.x, y = threadIdx.x;
   if (row >= rows) return;
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_signdev(RowGeom geo, GeneSta
 // Exact sigma = mad(signdev)/0.6745 of one row from scratch D (one CTA of RS_NT threads per row), the
 // certificate hints for later sweeps, and -- with the fast path on -- promotion to "certified" (+Inf)
 // when k sigma >= max|d|, i.e. every Huber weight pmin(1, k sigma/|d|) is exactly 1.
-__global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long Np, long long n, const int* rowlist,
+static __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long Np, long long n, const int* rowlist,
                                                     const double* rowmax, const int* rownan, double kh, int fastpath,
                                                     double* sigma, double* sigma_exact, double* hint /* [Gl][3] lo, hi, tg */) {
   __shared__ RowSelScratch sc;
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long 
 
 // rows split by their Huber status: sigma = +Inf (every weight provably 1) -> list_inf, anything else (finite or NaN
 // sigma: live weights) -> list_fin; both in launch order `order` (or natural order); one CTA, ordered scan
-__global__ void __launch_bounds__(1024) k_partition_sigma(int Gl, const double* sigma, const int* order, int* list_inf, int* list_fin,
+static __global__ void __launch_bounds__(1024) k_partition_sigma(int Gl, const double* sigma, const int* order, int* list_inf, int* list_fin,
                                                          int* counts /* [2] */) {
   __shared__ int wsum[32];
   __shared__ int base_inf, base_fin;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(1024) k_partition_sigma(int Gl, const double* 
 }
 
 // rows whose certificate failed (sigma == 0 marker) -> compact list, ascending (one CTA, ordered scan)
-__global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigma, int* list, int* count, int* n_active) {
+static __global__ void __launch_bounds__(1024) k_list_failed(int Gl, const double* sigma, int* list, int* count, int* n_active) {
   __shared__ int wsum[32];
   __shared__ int base, act;
   if (threadIdx.x == 0) { base = 0; act = 0; }
@@ -576,7 +576,7 @@ struct OpLoglik {
 };
 // The certificate decision of a row from the counters of its parts (see the comment above OpLoglik): sigma = +Inf
 // (certified) or 0 (exact path), hint recentring, failure diagnostics.  One thread per row.
-__global__ void k_cert_finish(int Gl, int nparts, const int* certc /* [nparts][Gl][4] */, double* hint, double* sigma_out, double kh,
+static __global__ void k_cert_finish(int Gl, int nparts, const int* certc /* [nparts][Gl][4] */, double* hint, double* sigma_out, double kh,
                               int fastpath, long long n, int* diag) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= Gl) return;
@@ -626,7 +626,7 @@ __global__ void k_cert_finish(int Gl, int nparts, const int* certc /* [nparts][G
   if (diag && !cert) atomicAdd(diag + (fastpath ? 0 : 7), 1);   // 0: no usable hint (first visit or live Huber weights)
 }
 // dst[i] = sum over the parts of src[p * n + i], fixed order (deterministic); in place on part 0 when dst == src
-__global__ void k_sum_parts(double* dst, const double* src, long long n, int nparts) {
+static __global__ void k_sum_parts(double* dst, const double* src, long long n, int nparts) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = src[i];
@@ -796,7 +796,7 @@ __global__ void k_alpha_finish(int Gl, int m, double Nreal, const int* group_n, 
 }
 
 // deterministic column sums of X[n][ncol] (ncol <= 64): one CTA, fixed summation order
-__global__ void __launch_bounds__(1024) k_colsum(const double* X, long long n, int ncol, double* out) {
+static __global__ void __launch_bounds__(1024) k_colsum(const double* X, long long n, int ncol, double* out) {
   __shared__ double sm[1024];
   for (int cidx = 0; cidx < ncol; ++cidx) {
     double s = 0.0;
@@ -883,7 +883,7 @@ __global__ void k_adev(int Gl, const double* A, const double* cvec, const double
 }
 
 // if any alpha entry was non-finite, the reference reverts the WHOLE alpha (R/ruvIIInb.R:368)
-__global__ void k_revert_if(const int* flag, double* dst, const double* src, long long n) {
+static __global__ void k_revert_if(const int* flag, double* dst, const double* src, long long n) {
   if (*flag == 0) return;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
@@ -891,7 +891,7 @@ __global__ void k_revert_if(const int* flag, double* dst, const double* src, lon
 
 // median / mad of strided vectors (columns of alpha: R/ruvIIInb.R:371-372), one CTA of RS_NT threads per vector:
 // 12-bit radix descent with early gather (select.cuh: cta_two_middles); NaN anywhere -> NaN (R's median)
-__global__ void __launch_bounds__(RS_NT) k_strided_medmad(const double* base, long long vec_stride, long long elem_stride,
+static __global__ void __launch_bounds__(RS_NT) k_strided_medmad(const double* base, long long vec_stride, long long elem_stride,
                                                          int len, double* med, double* mad) {
   __shared__ RowSelScratch sc;
   __shared__ int s_nan;
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(RS_NT) k_strided_medmad(const double* base, lo
 }
 
 // clamp column l of X[n][K] to med[l] +- 4 mad[l]  (R/ruvIIInb.R:373-376; NaN bounds clamp nothing)
-__global__ void k_clamp_cols(double* X, long long n, int K, const double* med, const double* mad) {
+static __global__ void k_clamp_cols(double* X, long long n, int K, const double* med, const double* mad) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * K) return;
   int l = (int)(i % K);
@@ -934,7 +934,7 @@ __global__ void k_clamp_cols(double* X, long long n, int K, const double* med, c
 // W helpers: group means of W (projection of t(W), R/ruvIIInb.R:331-340), RM_W, norms
 // ------------------------------------------------------------------------------------------------
 // one warp per (factor l, group j): mean over the group's cells
-__global__ void k_wbar(const double* W, long long Np, int K, int m, const int* group_chunk0, const int* group_n,
+static __global__ void k_wbar(const double* W, long long Np, int K, int m, const int* group_chunk0, const int* group_n,
                        double* Wbar /* [m][K] */) {
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= K * m) return;
@@ -946,7 +946,7 @@ __global__ void k_wbar(const double* W, long long Np, int K, int m, const int* g
   s = warp_sum(s);
   if (lane == 0) Wbar[j * K + l] = s / (double)n;
 }
-__global__ void k_rmw(const double* W, long long Np, int K, const int* chunk_grp, const int* chunk_valid,
+static __global__ void k_rmw(const double* W, long long Np, int K, const int* chunk_grp, const int* chunk_valid,
                       const double* Wbar, double* RMW) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Np * K) return;
@@ -957,7 +957,7 @@ __global__ void k_rmw(const double* W, long long Np, int K, const int* chunk_grp
   RMW[i] = valid ? W[i] - Wbar[chunk_grp[c] * K + l] : 0.0;
 }
 // column sum of squares of W (one CTA per factor), deterministic
-__global__ void __launch_bounds__(1024) k_w_sumsq(const double* W, long long Np, double* out) {
+static __global__ void __launch_bounds__(1024) k_w_sumsq(const double* W, long long Np, double* out) {
   __shared__ double sm[1024];
   const double* w = W + (long long)blockIdx.x * Np;
   double s = 0.0;
@@ -968,7 +968,7 @@ __global__ void __launch_bounds__(1024) k_w_sumsq(const double* W, long long Np,
   if (threadIdx.x == 0) out[blockIdx.x] = sm[0];
 }
 // W[,l] /= sqrt(colNorm) (R/ruvIIInb.R:392-394); counts non-finite entries among real cells (:401)
-__global__ void k_w_scale(double* W, long long Np, int K, const double* sumsq, const int* chunk_valid, int* bad) {
+static __global__ void k_w_scale(double* W, long long Np, int K, const double* sumsq, const int* chunk_valid, int* bad) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Np * K) return;
   int l = (int)(i / Np);
@@ -1398,7 +1398,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState
 }
 
 // gmean (R/ruvIIInb.R:405-415) and Mb (:418-420, rowWtAvg :667-675) from the group sums.
-__global__ void k_gmean_mb(int Gl, int m, const double* S0, const double* S1, const double* Mb_old, double lambda_b,
+static __global__ void k_gmean_mb(int Gl, int m, const double* S0, const double* S1, const double* Mb_old, double lambda_b,
                            double* gmean_new, double* Mb_new, int* nan_flag, int* bad) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
@@ -1442,7 +1442,7 @@ __device__ __forceinline__ double warp_small_median(double x0, double x1, int m,
 }
 // any NA -> whole Mb reverts (:424); NA/Inf -> 0 (:425); each row clamped to median +- 4 mad (:428-433).
 // One warp per gene.
-__global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* nan_flag, const double* Mb_old,
+static __global__ void __launch_bounds__(256) k_mb_finalize(int Gl, int m, const int* nan_flag, const double* Mb_old,
                                                      double* Mb_new) {
   __shared__ SelScratch sc[8];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1546,7 +1546,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_init_coef(RowGeom geo, const
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 // alpha.dev = alpha - colMeans(alpha) from the RAW alpha (:187-188), then NaN/Inf alpha -> 0 (:195)
-__global__ void k_init_adev(long long n, int K, const double* colsum, double Gtot, double* alpha, double* adev) {
+static __global__ void k_init_adev(long long n, int K, const double* colsum, double Gtot, double* alpha, double* adev) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * K) return;
   int l = (int)(i % K);
@@ -1558,17 +1558,17 @@ __global__ void k_init_adev(long long n, int K, const double* colsum, double Gto
 // ------------------------------------------------------------------------------------------------
 // misc
 // ------------------------------------------------------------------------------------------------
-__global__ void k_fill(double* p, long long n, double v) {
+static __global__ void k_fill(double* p, long long n, double v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 // step[g] *= fac where loglik_old[g] > loglik_new[g]  (R/ruvIIInb.R:490-491)
-__global__ void k_halve(int Gl, const double* ll_old, const double* ll_new, double fac, double* step) {
+static __global__ void k_halve(int Gl, const double* ll_old, const double* ll_new, double fac, double* step) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g < Gl && ll_old[g] > ll_new[g]) step[g] *= fac;
 }
 // gather rows: dst[i][ncol] = src[idx[i]][ncol]  (idx < 0 -> zeros)
-__global__ void k_gather_rows(const double* src, const int* idx, int n, int ncol, double* dst) {
+static __global__ void k_gather_rows(const double* src, const int* idx, int n, int ncol, double* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * ncol) return;
   int r = (int)(i / ncol), cidx = (int)(i % ncol);
@@ -1576,7 +1576,7 @@ __global__ void k_gather_rows(const double* src, const int* idx, int n, int ncol
   dst[i] = s >= 0 ? src[(long long)s * ncol + cidx] : 0.0;
 }
 // permute + pad a slab of count rows: dst[r][pos] = pos2cell[pos] >= 0 ? src(r, cell) : -1
-__global__ void k_permute_rows(const int32_t* src, long long rows, long long N, long long src_row_stride,
+static __global__ void k_permute_rows(const int32_t* src, long long rows, long long N, long long src_row_stride,
                                long long src_cell_stride, const int* pos2cell, long long Np, int32_t* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * Np) return;
@@ -1584,14 +1584,14 @@ __global__ void k_permute_rows(const int32_t* src, long long rows, long long N, 
   int cidx = pos2cell[pos];
   dst[i] = cidx >= 0 ? src[r * src_row_stride + (long long)cidx * src_cell_stride] : -1;
 }
-__global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
+static __global__ void k_fill_i32(int32_t* p, long long n, int32_t v) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 // R-layout slab (cells [c0, c0+nc) x all Gh host rows, column-major) -> dst[r][cell2pos[c]].
 // 32 x 32 tile through shared memory: reads coalesced along genes, writes along positions of a row
 // (cells of one group are contiguous after the permutation, so mostly coalesced as well).
-__global__ void k_scatter_cellmajor(const int32_t* stage, long long Gh, const int* rowidx, long long row0, long long rows,
+static __global__ void k_scatter_cellmajor(const int32_t* stage, long long Gh, const int* rowidx, long long row0, long long rows,
                                     long long c0, long long nc, const int* cell2pos, long long Np, int32_t* dst) {
   __shared__ int32_t tile[32][33];
   const long long rb = (long long)blockIdx.x * 32, cb = (long long)blockIdx.y * 32;
@@ -1609,12 +1609,12 @@ __global__ void k_scatter_cellmajor(const int32_t* stage, long long Gh, const in
   }
 }
 // CSR expansion: zero the real cells / -1 the pads, then scatter the stored values (warp per row).
-__global__ void k_fill_pad(int32_t* dst, long long rows, long long Np, const int* pos2cell) {
+static __global__ void k_fill_pad(int32_t* dst, long long rows, long long Np, const int* pos2cell) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * Np) return;
   dst[i] = pos2cell[i % Np] >= 0 ? 0 : -1;
 }
-__global__ void k_csr_scatter(const long long* indptr, const int32_t* indices, const int32_t* values, long long rows,
+static __global__ void k_csr_scatter(const long long* indptr, const int32_t* indices, const int32_t* values, long long rows,
                               long long base, const int* cell2pos, long long Np, int32_t* dst) {
   long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -1626,7 +1626,7 @@ __global__ void k_csr_scatter(const long long* indptr, const int32_t* indices, c
 // FP64 FMA peak of this device (the governing roofline of the sweeps): 8 independent
 // DFMA chains per thread, 1024 x 8 x 2 flops per thread per call.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fp64_peak(double* out, double a, double b, int iters) {
+static __global__ void __launch_bounds__(256) k_fp64_peak(double* out, double a, double b, int iters) {
   double x[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] = a + (double)(threadIdx.x + i);
@@ -1644,7 +1644,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, double a, double
 
 // counts beyond the per-gene tables, per row: rows that hold many of them cost ~2.5x per element in the log-likelihood
 // sweep; the host launches those rows FIRST (RowGeom.rowlist) so that they do not form the tail of a sweep
-__global__ void __launch_bounds__(256) k_count_big(const int32_t* Yp, int rows, long long Np, int* nbig) {
+static __global__ void __launch_bounds__(256) k_count_big(const int32_t* Yp, int rows, long long Np, int* nbig) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int4* y4 = reinterpret_cast<const int4*>(Yp + (long long)row * Np);
@@ -1654,11 +1654,11 @@ __global__ void __launch_bounds__(256) k_count_big(const int32_t* Yp, int rows, 
   if (lane == 0) nbig[row] = c;
 }
 
-__global__ void k_scale_vec(double* x, long long n, double f) {
+static __global__ void k_scale_vec(double* x, long long n, double f) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= f;
 }
-__global__ void k_count_nan(const double* x, long long n, int* count) {
+static __global__ void k_count_nan(const double* x, long long n, int* count) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && x[i] != x[i]) atomicAdd(count, 1);
 }

@@ -33,7 +33,7 @@ __device__ __forceinline__ double res_mb(const ResArgs& a, int g, int c, long lo
   return a.mb_blk ? a.mb_blk[(long long)c * a.Gl + g] : a.Mb[(long long)g * a.m + a.chunk_grp[pos >> 7]];
 }
 
-__global__ void __launch_bounds__(256) k_res_caps(ResArgs a) {
+static __global__ void __launch_bounds__(256) k_res_caps(ResArgs a) {
   extern __shared__ double dyn[];   // wa[B], mb[B]
   __shared__ SelScratch sc;
   double* wa = dyn; double* mb = dyn + a.B;
@@ -67,7 +67,7 @@ __device__ __forceinline__ double res_log_p0(double r, double mu) {
   return r * (r < mu ? log(r / (r + mu)) : log1p(-mu / (r + mu)));
 }
 // percentile-adjusted count of one element
-__device__ double res_pac(int y, double mu_full, double mu_nouv, double r) {
+static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r) {
   const double BIG = 1e250, LBIG = 575.64627324851142;  // log(1e250)
   // mid-p under (mu_full, r)
   double ls = res_log_p0(r, mu_full);
@@ -155,7 +155,7 @@ struct SelTargets {
   double lims[2];
 };
 // ranks of the type-7 quantiles .005 / .995 of n values (stats::quantile): index = 1 + (n-1) p, lo = floor, hi = ceil
-__global__ void k_sel_init(SelTargets* T, long long n_total, const int* nan_count) {
+static __global__ void k_sel_init(SelTargets* T, long long n_total, const int* nan_count) {
   if (threadIdx.x || blockIdx.x) return;
   long long n = n_total - (long long)*nan_count;
   T->n = n; T->pmask = 0;
@@ -168,7 +168,7 @@ __global__ void k_sel_init(SelTargets* T, long long n_total, const int* nan_coun
     T->prefix[2 * q] = T->prefix[2 * q + 1] = 0;
   }
 }
-__global__ void __launch_bounds__(256) k_sel_hist(const double* slab, long long len, int shift, int bits, const SelTargets* T,
+static __global__ void __launch_bounds__(256) k_sel_hist(const double* slab, long long len, int shift, int bits, const SelTargets* T,
                                                  unsigned* hist /* [SEL_NT][SEL_BINS] global */) {
   extern __shared__ unsigned sh[];  // [SEL_NT][SEL_BINS]
   const int nb = 1 << bits;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) k_sel_hist(const double* slab, long long 
   __syncthreads();
   for (int i = threadIdx.x; i < SEL_NT * SEL_BINS; i += 256) if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
-__global__ void __launch_bounds__(SEL_NT * 32) k_sel_pick(SelTargets* T, unsigned* hist, int shift, int bits) {
+static __global__ void __launch_bounds__(SEL_NT * 32) k_sel_pick(SelTargets* T, unsigned* hist, int shift, int bits) {
   // one warp per target: locate the bucket holding its rank (serial scan by lane 0 over <= 4096 bins)
   const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = 1 << bits;
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(SEL_NT * 32) k_sel_pick(SelTargets* T, unsigne
   if (threadIdx.x == 0) T->pmask |= (unsigned long long)(nb - 1) << shift;
   for (int i = threadIdx.x; i < SEL_NT * SEL_BINS; i += SEL_NT * 32) hist[i] = 0;
 }
-__global__ void k_sel_finish(SelTargets* T) {
+static __global__ void k_sel_finish(SelTargets* T) {
   if (threadIdx.x || blockIdx.x) return;
   for (int q = 0; q < 2; ++q) {
     double lo = key_f64(T->prefix[2 * q]), hi = key_f64(T->prefix[2 * q + 1]);
@@ -231,7 +231,7 @@ __global__ void k_sel_finish(SelTargets* T) {
     T->lims[q] = v;
   }
 }
-__global__ void k_res_clip(double* slab, long long len, const SelTargets* T) {
+static __global__ void k_res_clip(double* slab, long long len, const SelTargets* T) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= len) return;
   double v = slab[i];
@@ -241,7 +241,7 @@ __global__ void k_res_clip(double* slab, long long len, const SelTargets* T) {
 }
 
 // colMeans(W) over the real cells (pads hold 0) and a %*% colMeans(W)
-__global__ void __launch_bounds__(1024) k_res_wmean(const double* W, long long Np, double n, double* wm) {
+static __global__ void __launch_bounds__(1024) k_res_wmean(const double* W, long long Np, double n, double* wm) {
   __shared__ double sm[1024];
   const double* w = W + (long long)blockIdx.x * Np;
   double s = 0.0;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(1024) k_res_wmean(const double* W, long long N
   for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
   if (threadIdx.x == 0) wm[blockIdx.x] = sm[0] / n;
 }
-__global__ void k_res_wamean(int Gl, int K, const double* alpha, const double* wm, double* out) {
+static __global__ void k_res_wamean(int Gl, int K, const double* alpha, const double* wm, double* out) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
   double s = 0.0;

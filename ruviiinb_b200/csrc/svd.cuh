@@ -8,7 +8,7 @@
 #include "kernels.cuh"
 
 // rowMeans(Y[ctl,]) over the real cells: one warp per control row
-__global__ void __launch_bounds__(256) k_svd_rowmean(const int32_t* const* ctl_rows, int n_ctl, long long Np, double n, double* rowmean) {
+static __global__ void __launch_bounds__(256) k_svd_rowmean(const int32_t* const* ctl_rows, int n_ctl, long long Np, double n, double* rowmean) {
   const int gi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (gi >= n_ctl) return;
   const int32_t* y = ctl_rows[gi];
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) k_svd_rowmean(const int32_t* const* ctl_r
 }
 // A[gi][p] = log(Y[ctl_gi, p] / rowmean_gi + 1) as a dense FP64 slab [n_ctl][Np] (pads and zero counts 0), built once: the
 // iterations then stream 8 B per element instead of paying a logarithm per element in both products
-__global__ void __launch_bounds__(256) k_svd_build(const int32_t* const* ctl_rows, int n_ctl, long long Np, const double* rowmean, double* A) {
+static __global__ void __launch_bounds__(256) k_svd_build(const int32_t* const* ctl_rows, int n_ctl, long long Np, const double* rowmean, double* A) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_ctl * Np) return;
   const int gi = (int)(i / Np); const long long p = i - (long long)gi * Np;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_svd_av(const double* __restrict__ A, in
       if (lane == 0 && g0 + r < n_ctl) Upart[((long long)blockIdx.y * n_ctl + g0 + r) * K + l] = t;
     }
 }
-__global__ void k_svd_sum_parts(const double* Upart, long long n, int parts, double* U) {
+static __global__ void k_svd_sum_parts(const double* Upart, long long n, int parts, double* U) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_svd_atu(const double* __restrict__ A, i
   }
 }
 // Gram of the K vectors V[l][.] (lower triangle, KK entries), deterministic: one CTA per entry
-__global__ void __launch_bounds__(1024) k_svd_gram(const double* V, long long Np, int K, double* G) {
+static __global__ void __launch_bounds__(1024) k_svd_gram(const double* V, long long Np, int K, double* G) {
   __shared__ double sm[1024];
   int e = blockIdx.x, i = 0;
   while ((i + 1) * (i + 2) / 2 <= e) ++i;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(1024) k_svd_gram(const double* V, long long Np
   if (threadIdx.x == 0) G[e] = sm[0];
 }
 // V[.][p] <- V[.][p] T  (T: K x K row-major, applied from the right to the row vector of the K factors of a cell)
-__global__ void k_svd_apply(double* V, long long Np, int K, const double* T) {
+static __global__ void k_svd_apply(double* V, long long Np, int K, const double* T) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= Np) return;
   double v[RUVNB_MAX_K], o[RUVNB_MAX_K];
@@ -122,7 +122,7 @@ __global__ void k_svd_apply(double* V, long long Np, int K, const double* T) {
   for (int l = 0; l < K; ++l) V[(long long)l * Np + p] = o[l];
 }
 // deterministic start: a hash of (cell, factor) mapped to (-1, 1); pads 0
-__global__ void k_svd_start(double* V, long long Np, int K, const int* pos2cell) {
+static __global__ void k_svd_start(double* V, long long Np, int K, const int* pos2cell) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Np * K) return;
   const int l = (int)(i / Np); const long long p = i - (long long)l * Np;

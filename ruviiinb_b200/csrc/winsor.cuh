@@ -11,7 +11,7 @@
 #define WZ_BINS 4096
 
 // kth (0-based) smallest non-negative value of the row by radix descent (pads are negative and skipped)
-__device__ unsigned wz_select(const int32_t* y, long long Np, long long kth, unsigned* hist, unsigned* s_pick) {
+static __device__ unsigned wz_select(const int32_t* y, long long Np, long long kth, unsigned* hist, unsigned* s_pick) {
   const int tid = threadIdx.x;
   unsigned prefix = 0, pmask = 0;
   const int shifts[3] = {20, 8, 0}, bits[3] = {12, 12, 8};
@@ -36,7 +36,7 @@ __device__ unsigned wz_select(const int32_t* y, long long Np, long long kth, uns
   return prefix;
 }
 
-__global__ void __launch_bounds__(WZ_NT) k_winsorize(int32_t* Yp, long long Np, long long n, double prob, double* cap_out,
+static __global__ void __launch_bounds__(WZ_NT) k_winsorize(int32_t* Yp, long long Np, long long n, double prob, double* cap_out,
                                                     long long* nz_out) {
   __shared__ unsigned hist[WZ_BINS];
   __shared__ unsigned s_pick[4];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(WZ_NT) k_winsorize(int32_t* Yp, long long Np, 
 }
 
 // inverse of the upload permutation: dst[r][cell] = Yp[r][cell2pos[cell]] (gene-major host layout)
-__global__ void k_unpermute_rows(const int32_t* Yp, long long rows, long long N, long long Np, const int* cell2pos, int32_t* dst) {
+static __global__ void k_unpermute_rows(const int32_t* Yp, long long rows, long long N, long long Np, const int* cell2pos, int32_t* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * N) return;
   long long r = i / N, c = i - r * N;

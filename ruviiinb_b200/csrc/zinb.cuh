@@ -75,7 +75,7 @@ struct NMState {
 #define NM_RELTOL 1.4901161193847656e-08   // sqrt(.Machine$double.eps)
 #define NM_MAXIT 500
 
-__global__ void k_nm_init(int Gl, NMState* S, double* xeval) {
+static __global__ void k_nm_init(int Gl, NMState* S, double* xeval) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
   NMState s;
@@ -86,7 +86,7 @@ __global__ void k_nm_init(int Gl, NMState* S, double* xeval) {
 }
 
 // f(x) of every gene still running: one warp per gene over its q row
-__global__ void __launch_bounds__(256) k_nm_eval(int Gl, long long Np, const double* Q, const double* S_pos, const int* n_pos,
+static __global__ void __launch_bounds__(256) k_nm_eval(int Gl, long long Np, const double* Q, const double* S_pos, const int* n_pos,
                                                 const NMState* S, const double* xeval, const MathTabs* gt, double* feval) {
   __shared__ MathTabs mt;
   {
@@ -130,7 +130,7 @@ __device__ __forceinline__ void nm_while_check(NMState& s, bool calcvert) {
   if (calcvert) { s.B = s.P[1 - s.L]; s.phase = NM_CALCVERT; return; }
   nm_loop_top(s);
 }
-__global__ void k_nm_step(int Gl, NMState* S, const double* feval, double* xeval, int* n_active) {
+static __global__ void k_nm_step(int Gl, NMState* S, const double* feval, double* xeval, int* n_active) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
   NMState s = S[g];
@@ -199,7 +199,7 @@ __global__ void k_nm_step(int Gl, NMState* S, const double* feval, double* xeval
   S[g] = s;
 }
 // pi0 <- logistic(par) where optim succeeded, else the previous value (:251,451); counts non-finite entries (:453)
-__global__ void k_nm_finish(int Gl, const NMState* S, const double* pi0_old, double* pi0_new, int* bad) {
+static __global__ void k_nm_finish(int Gl, const NMState* S, const double* pi0_old, double* pi0_new, int* bad) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
   const NMState& s = S[g];
