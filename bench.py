@@ -37,8 +37,25 @@ WORKLOADS = {
     "tiny_256x2k": (256, 2048, 2, 3, 64),
 }
 SEED = 20261019 + 2
-# FP64-pipe instructions per element of each sweep at k = 5 (ncu smsp__inst_executed_pipe_fp64 / elements, profiles/)
-FP64_INSTR = {"pass1": 67.8, "pass2": 41.5, "loglik": 40.8}
+
+
+def fp64_instr_table():
+    """FP64-pipe instructions per element of each sweep (ncu smsp__inst_executed_pipe_fp64 / elements of the captured launch);
+    measured under ncu and committed as profiles/fp64_instr.json with the capture it came from -- nothing hard-coded here."""
+    p = os.path.join(ROOT, "profiles", "fp64_instr.json")
+    if not os.path.exists(p):
+        return {}, None
+    d = json.load(open(p))
+    return d.get("instr_per_element", {}), d.get("source")
+
+
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed on (torchrun exports OMP_NUM_THREADS=1 for N > 1, which
+    must not decide it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -105,37 +122,59 @@ def gen_rows_cpu(tp, rows, seed=SEED, chunk=500):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 20 ms in the background; only the samples taken between begin() and end() count.  start() returns
+    once the first sample has arrived (nvidia-smi needs ~0.5 s to come up), so that even a sub-second region is sampled."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.samples = []      # (perf_counter, line)
         self.proc = None
+        self.t0 = self.t1 = None
 
-    def start(self):
+    def start(self, wait=5.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t = time.perf_counter()
+            while not self.samples and time.perf_counter() - t < wait:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is None:
+            self.end()
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else -1e300
+        inside = [l for (t, l) in self.samples if t0 <= t <= self.t1 + 0.03]
+        note = None
+        if not inside and self.samples:   # region shorter than one polling period: the sample nearest to it
+            mid = 0.5 * (t0 + self.t1)
+            inside = [min(self.samples, key=lambda x: abs(x[0] - mid))[1]]
+            note = "region shorter than the polling period: nearest sample"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in inside:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -146,8 +185,11 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,7 +201,7 @@ def cpu_sample_run(workload, steps, warmup, target_seconds=20.0):
     G, N, k, m, n_ctl = WORKLOADS[workload]
     from oracle import cport
     tp = truth_params(G, N, k, m, n_ctl)
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     have_c = cport.available()
     Gs = min(G, 2048, 64 * cores if have_c else 96)
     ncs = min(n_ctl, max(8, Gs // 4))
@@ -173,7 +215,7 @@ def cpu_sample_run(workload, steps, warmup, target_seconds=20.0):
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        state, ll = cport.inner_iteration(Y, state, tp["grp"], ctl, k_huber=100.0, lambda_a=0.01, lambda_b=16.0)
+        state, ll = cport.inner_iteration(Y, state, tp["grp"], ctl, k_huber=100.0, lambda_a=0.01, lambda_b=16.0, nthreads=cores)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -181,7 +223,8 @@ def cpu_sample_run(workload, steps, warmup, target_seconds=20.0):
     kind = "port"
     sample = (f"{Gs} genes ({ncs} controls) x all {N} cells of {workload}, {steps} inner iterations, "
               f"{'C/OpenMP' if have_c else 'NumPy'} restatement of R/ruvIIInb.R:303-484")
-    return Gs * steps / tot, dict(kind=kind, cores=cores if have_c else 1, sample=sample), 1e3 * tot / steps
+    used = cport.threads() if have_c else 1    # omp_get_max_threads() after the call: what the C side really ran with
+    return Gs * steps / tot, dict(kind=kind, cores=used, sample=sample), 1e3 * tot / steps
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,9 +247,10 @@ def main():
     ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--full-fit", action="store_true",
-                    help="also run the WHOLE ruvIII.nb fit (ruvnb_fit_nb: Winsorize, init, dispersion estimation, alternating IRLS to "
-                         "convergence) on the workload and report its wall time under \"full_fit\"")
+    ap.add_argument("--no-full-fit", action="store_true",
+                    help="skip the WHOLE ruvIII.nb fit (ruvnb_fit_nb: Winsorize, init, dispersion estimation, alternating IRLS to "
+                         "convergence) whose wall time is the second half of BASELINE.json's metric (\"full_fit\" in the line)")
+    ap.add_argument("--full-fit", action="store_true", help="(default; kept for older command lines)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,9 +337,10 @@ def main():
     ctx.kernel_time_reset()
     l0 = ctx.kernel_launches
     clocks = ClockSampler(local)
-    barrier()
     if rank == 0:
         clocks.start()
+    barrier()
+    clocks.begin()
     e0.record(stream)
     logls, exact_rows_steps, exact_cells_steps = [], [], []
     ctx.cert_diag()
@@ -307,6 +352,7 @@ def main():
         exact_cells_steps.append(ctx.last_exact_cells)
     e1.record(stream)
     barrier()
+    clocks.end()
     clk = clocks.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches - l0
@@ -349,9 +395,13 @@ def main():
 
     # ---- optional: the whole fit, host buffers in, converged parameters out ---------------------------------------
     full_fit = None
-    if args.full_fit:
+    if not args.no_full_fit:
         ctx = make_ctx()
+        fclocks = ClockSampler(local)
+        if rank == 0:
+            fclocks.start()
         barrier()
+        fclocks.begin()
         t0 = time.perf_counter()
         ctx.upload_counts(Yh, Yctl=Yctl)
         t_up = time.perf_counter() - t0
@@ -363,11 +413,13 @@ def main():
         res = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
         barrier()
         dt = time.perf_counter() - t0
+        fclocks.end()
+        fclk = fclocks.stop() if rank == 0 else None
         ctx.close()
         tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-        full_fit = {"wall_seconds": float(tdt.item()), "outer_iterations": st["n_outer"], "inner_iterations": st["n_inner"],
+        full_fit = {"wall_seconds": float(tdt.item()), "clocks": fclk, "outer_iterations": st["n_outer"], "inner_iterations": st["n_inner"],
                     "inner_loop_seconds": st["inner_seconds"], "dispersion_seconds": st["disp_seconds"],
                     "upload_winsorize_initW_seconds": t_init, "upload_seconds": t_up, "winsorize_seconds": t_win,
                     "initW_seconds": t_init - t_up - t_win, "initW_iterations": svd_iters,
@@ -395,20 +447,30 @@ def main():
             kern[name] = {"ms": tot / cnt, "launches_per_step": cnt / args.steps,
                           "GBps": sweep_bytes[name] / (tot / cnt * 1e-3) / 1e9 if sweep_bytes[name] else None}
     dom = max((n for n in kern if sweep_bytes[n] > 0), key=lambda n: kern[n]["ms"] * kern[n]["launches_per_step"])
-    traffic = None
+    fused = not os.environ.get("RUVNB_NO_FUSE")
+    label = {"loglik": "ll_pass1 (log-likelihood + certificate fused with the next iteration's Gram/score sweep)" if fused else "loglik"}
+    # measured DRAM traffic of the dominant kernel (ncu --set full, profiles/traffic.json: bytes per launch over ALL G rows of the
+    # workload), scaled to the rows this rank's launch walks
+    traffic, traffic_src = None, None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    key = ("ll_pass1" if fused else "loglik") if dom == "loglik" else dom
     if os.path.exists(tr_path):
         tr = json.load(open(tr_path))
-        traffic = tr.get(args.workload, {}).get(dom)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "peak_source": peak_src,
+        full = tr.get(args.workload, {}).get(key)
+        if full is not None:
+            traffic = full * Gl / G
+            traffic_src = tr.get("source")
+    instr, instr_src = fp64_instr_table()
+    ipe = instr.get(key)
+    roofline = {"bound": "hbm", "kernel": label.get(dom, dom), "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": sweep_bytes[dom],
                 "note": "FP64-pipe-bound sweep (DESIGN.md section 5): the HBM budget is ~11 FP64 instructions per element",
-                "fp64": {"peak_tflops_measured": fp64_peak, "instr_per_element": FP64_INSTR.get(dom),
-                         "achieved_tflops": (2.0 * FP64_INSTR[dom] * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12) if dom in FP64_INSTR else None,
-                         "frac": (2.0 * FP64_INSTR[dom] * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12 / fp64_peak) if dom in FP64_INSTR and fp64_peak else None,
-                         "what": "FP64-pipe instructions per element counted from ncu (profiles/), 2 flops each, against the DFMA-chain peak measured in this run"},
-                "kernels": kern}
+                "fp64": {"peak_tflops_measured": fp64_peak, "instr_per_element": ipe, "instr_source": instr_src,
+                         "achieved_tflops": (2.0 * ipe * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12) if ipe else None,
+                         "frac": (2.0 * ipe * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12 / fp64_peak) if ipe and fp64_peak else None,
+                         "what": "FP64-pipe instructions per element counted from ncu (profiles/fp64_instr.json), 2 flops each, against the DFMA-chain peak measured in this run"},
+                "kernels": {label.get(n, n): v for n, v in kern.items()}}
 
     line = {"metric": "NB IRLS gene-fits/sec", "value": value, "unit": "gene-fits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -418,7 +480,7 @@ def main():
         line["e2e"] = e2e
     if full_fit:
         line["full_fit"] = full_fit
-    if world == 1 and not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:   # rank 0, every N (the other ranks have left)
         v, desc, _ = cpu_sample_run(args.workload, 2, 1)
         line["cpu_baseline"] = dict(value=v, unit="gene-fits/s", **desc)
     print(json.dumps(line), file=json_out, flush=True)

@@ -78,20 +78,32 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
     if batch_disp and len(np.unique(batch)) > 1:
         raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
     zi = np.zeros(N, dtype=bool) if zeroinf is None else np.asarray(zeroinf).astype(bool)   # :39-40
-    # :53-62 Winsorize + ceiling happen on the device; all-zero genes are dropped before the upload (a gene is all zero
-    # after the cap iff it was before)
-    keep = (Y > 0).sum(axis=1) > 0
-    Yk = np.ascontiguousarray(np.ceil(Y[keep]), dtype=np.int32)
-    ctlk = ctl[keep]
+    # :53-62: Winsorize + ceiling on the device, THEN drop the genes that are all zero (a gene expressed in fewer than 0.5 % of
+    # the cells has a 99.5 % quantile of 0: the cap zeroes the whole row, and the reference removes it only after the cap).
+    # Genes that are all zero in the raw data are certainly all zero after it: they never travel.
     grp = np.argmax(M, axis=1).astype(np.int32)                      # apply(M, 1, which), :50
     opts = _lib.default_opts(k=int(k), robust=int(bool(robust)), lambda_a=float(lambda_a), lambda_b=float(lambda_b),
                              step_fac=float(step_fac), inner_maxit=int(inner_maxit), outer_maxit=int(outer_maxit),
                              zinb=int(zi.any()))
-    with _lib.Context(device) as ctx:
-        ctx.set_design(Yk.shape[0], N, grp, ctlk, zeroinf=zi if zi.any() else None)
+    keep = (Y > 0).sum(axis=1) > 0
+    Yk = np.ascontiguousarray(np.ceil(Y[keep]), dtype=np.int32)
+    ctx = _lib.Context(device)
+    try:
+        ctx.set_design(Yk.shape[0], N, grp, ctl[keep], zeroinf=zi if zi.any() else None)
         ctx.upload_counts(Yk)
-        ctx.winsorize()
+        _, nz = ctx.winsorize()
         counts = ctx.get_counts()
+        if (nz == 0).any():            # rows emptied by the cap: the fit context holds the surviving rows only (:57-62)
+            ctx.close()
+            alive = nz > 0
+            keep[np.where(keep)[0][~alive]] = False
+            counts = np.ascontiguousarray(counts[alive])
+            ctx = _lib.Context(device)
+            ctx.set_design(counts.shape[0], N, grp, ctl[keep], zeroinf=zi if zi.any() else None)
+            ctx.upload_counts(counts)   # already capped (the cap of a capped row is the same cap)
+        ctlk = ctl[keep]
+        if ctlk.sum() == 0:
+            raise ValueError("no control gene is left after removing all-zero genes")
         if W0 is None:
             W0, _, _ = ctx.init_W(int(k))        # H1 on the device (subspace iteration on the resident control rows)
         psi_inject = None if psi is None else np.atleast_2d(np.asarray(psi, dtype=np.float64))[:, keep]
@@ -100,6 +112,8 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
                "Mb": ctx.get_state("Mb"), "gmean": ctx.get_state("gmean"), "psi": ctx.get_state("psi"),
                "L.a": lambda_a, "L.b": lambda_b, "batch": batch}
         pi0 = ctx.get_state("pi0")
+    finally:
+        ctx.close()
     out["pi0"] = np.outer(pi0, zi.astype(np.float64)) if zi.any() else None   # :611-626
     out["zero_genes"] = ~keep
     if return_trace:
@@ -380,7 +394,7 @@ def fastruvIII_nb_finish(Y, M, ctl, alpha, gmean, psi, Mb_sub, Wsub, subsamples,
                          block_size=5000, device=0):
     """The full-data tail of `fastruvIII.nb` (R/fastruvIIInb.R:625-792) given the subsample fit (alpha, gmean, psi,
     Mb_sub G x m, Wsub rows for the cells `subsamples`, wt_ctl = best.wtctl): W for all cells, Mb.all, the psi cap.
-    The subsample fit itself (:118-623) is not built yet."""
+    The subsample fit (:118-623) is `fastruvIII_nb_subfit`."""
     from . import _lib as L
     Y = np.ascontiguousarray(Y, dtype=np.int32)
     G, N = Y.shape

@@ -32,6 +32,9 @@ int ruvnb_create(ruvnb_ctx** out, int device) {
   }
   for (int i = 0; i < RUVNB_NKERN; ++i) { cudaEventCreate(&ctx->kev[i][0]); cudaEventCreate(&ctx->kev[i][1]); }
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_ctl, cudaEventDisableTiming);
+  { const char* e = getenv("RUVNB_NO_FUSE"); ctx->opt_no_fuse = e && *e && *e != '0'; }
+  { const char* e = getenv("RUVNB_LLP1_NW"); ctx->opt_llp1_nw = e ? atoi(e) : 0; }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;
   return RUVNB_OK;
@@ -49,6 +52,7 @@ void ruvnb_destroy(ruvnb_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_ctl) cudaEventDestroy(ctx->ev_ctl);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -207,9 +211,16 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   RET(dev_upload(ctx, &ctx->d_cell2pos, ctx->cell2pos));
   RET(dev_upload(ctx, &ctx->d_chunk_grp, ctx->chunk_grp));
   RET(dev_upload(ctx, &ctx->d_chunk_valid, ctx->chunk_valid));
+  {
+    if (m > (1 << 22)) return ctx->fail(RUVNB_EARG, "set_design: more than 2^22 replicate groups");
+    std::vector<int> meta(nch);
+    for (int q = 0; q < nch; ++q) meta[q] = (ctx->chunk_grp[q] << 8) | ctx->chunk_valid[q];
+    RET(dev_upload(ctx, &ctx->d_chunk_meta, meta));
+  }
   RET(dev_upload(ctx, &ctx->d_group_chunk0, ctx->group_chunk0));
   RET(dev_upload(ctx, &ctx->d_group_n, ctx->group_n));
   RET(dev_upload(ctx, &ctx->d_ctl_local, ctl_local));
+  RET(dev_upload(ctx, &ctx->d_ctl_global, ctx->ctl_gene));
   if (ctx->any_zeroinf) {
     std::vector<uint8_t> zp(ctx->Np, 0);
     for (long long c = 0; c < N; ++c) zp[ctx->cell2pos[c]] = ctx->zeroinf[c] ? 1 : 0;
@@ -444,9 +455,20 @@ int ensure_state(ruvnb_ctx* ctx, int K) {
   // row parts: enough CTAs for >= 6 waves of 296 (2 CTAs x 148 SMs) so that a small gene shard does not leave most
   // of a wave empty (20000 rows on one GPU: 1 part; 2500 rows per GPU on eight: 8 parts)
   {
+    // cost model of a sweep: waves of 296 resident CTAs x tiles per part; the smallest product wins (at most 24 parts:
+    // the part-major partial sums grow with P).  20000 rows: 1 part (8.4 waves); 2500 rows: 17 parts (18.0 waves of 12 tiles)
     const long long ctas = (Gl + NWARP - 1) / NWARP;
+    const long long ntiles = ctx->nchunks / TileCfg_SC(K);
     int P = 1;
-    while (P < 8 && ctas * P < 6 * 296) P *= 2;
+    if (ctas < 6 * 296) {
+      long long best = -1;
+      for (int p = 1; p <= 24 && p <= ntiles; ++p) {
+        const long long waves = (ctas * p + 295) / 296, tpp = (ntiles + p - 1) / p;
+        const long long cost = waves * tpp * 16 + p;   // ties -> fewer parts
+        if (best < 0 || cost < best) { best = cost; P = p; }
+      }
+    }
+    if (const char* e = getenv("RUVNB_NPARTS")) { int v = atoi(e); if (v >= 1 && v <= 24) P = v; }
     ctx->nparts = P;
   }
   const long long P = ctx->nparts;
@@ -489,7 +511,11 @@ int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->mad, K));
   RET(dev_alloc(ctx, &ctx->ctlpack, (long long)ctx->n_ctl * (5 + 2 * K + m)));
   RET(dev_alloc(ctx, &ctx->scal, 16));
-  if (ctx->nranks > 1) RET(dev_alloc(ctx, &ctx->alpha_full, ctx->G * K));
+  if (ctx->nranks > 1) {
+    RET(dev_alloc(ctx, &ctx->alpha_full, ctx->G * K + 1));
+    const long long per = (ctx->G + ctx->nranks - 1) / ctx->nranks;
+    RET(dev_alloc(ctx, &ctx->agather, (long long)ctx->nranks * (2 * per * K + 1)));
+  }
   return RUVNB_OK;
 }
 

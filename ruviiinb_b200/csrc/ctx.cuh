@@ -27,6 +27,8 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool load(std::string* err) {
     if (h) return true;
@@ -37,8 +39,10 @@ struct NcclApi {
     CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId_t, int))dlsym(h, "ncclCommInitRank");
     CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
     AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
     GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { *err = "libnccl lacks a required symbol"; return false; }
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !AllGather || !Broadcast) { *err = "libnccl lacks a required symbol"; return false; }
     return true;
   }
 };
@@ -54,6 +58,9 @@ struct StateSet {  // one parameter set on device
   double* wtctl = nullptr;  // fastruvIII.nb subsample fit: wt.ctl = rowMeans(sig.inv[ctl,]) of this parameter set (best.wtctl)
   double* psi_w = nullptr;  // ZINB: the dispersion the last E-step (wt.zinb update) used -- R/ruvIIInb.R:262,465,502
   bool sig_valid = false;   // sigma was produced for the parameters currently held
+  bool p1_valid = false;    // ctx->A, u, sw, ZS, VS hold the (unit-Huber-weight) Gram / score sums of THIS parameter set with the
+                            // current steps: left by the fused log-likelihood sweep that scored it (kernels.cuh k_ll_pass1)
+  int nfail = -1;           // rows of `sigma` still marked 0 (exact MAD to be computed), as read back by the host; -1 = not read
   bool maybe_active = false; // some rows went through the exact path: their sigma may be finite (live Huber weights)
 };
 
@@ -79,10 +86,12 @@ struct ruvnb_ctx {
   std::vector<int> pos2cell, cell2pos, chunk_grp, chunk_valid, group_chunk0, group_n;
   int *d_pos2cell = nullptr, *d_cell2pos = nullptr, *d_chunk_grp = nullptr, *d_chunk_valid = nullptr,
       *d_group_chunk0 = nullptr, *d_group_n = nullptr;
+  int* d_chunk_meta = nullptr;     // [nchunks] (group << 8) | valid cells: one load per chunk in the row walk
   // control genes
   int n_ctl = 0;
   std::vector<int> ctl_gene;       // global gene index of each control
   int* d_ctl_local = nullptr;      // local row of each control gene, or -1
+  int* d_ctl_global = nullptr;     // global row of each control gene
   const int32_t** d_ctl_rows = nullptr;
   // counts
   int* d_roworder = nullptr; // [Gl] launch order of the gene rows: heavy rows (many counts >= YT) first
@@ -143,6 +152,7 @@ struct ruvnb_ctx {
   int disp_nr_sweeps = 0;        // Newton-Raphson sweeps of the last dispersion call (diagnostics)
   int *flags = nullptr;      // [8] device ints: 0 bad_alpha 1 bad_W 2 bad_Mb 3 nan_Mb 4 n_fail 5..7 spare
   int *faillist = nullptr;
+  const double* faillist_for = nullptr;  // the sigma buffer whose unevaluated rows faillist currently lists
   int nparts = 1;            // row parts of the IRLS sweeps (kernels.cuh RowGeom::nparts), chosen from the shard size
   int launch_parts = 1;      // parts of the launch being issued (geom() and LAUNCH_ROWS read it)
   double* llparts = nullptr; // [nparts][Gl] partial log-likelihoods
@@ -153,6 +163,12 @@ struct ruvnb_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  bool even_shards = false;  // rank r holds rows [r per, min(G, (r+1) per)), per = ceil(G / nranks): slices can be all-gathered
+  double* agather = nullptr; // [nranks][per K + 1] alpha slices + the rank's non-finite count (all-gather buffer)
+  cudaEvent_t ev_ctl = nullptr;  // the control-gene parameter exchange on the side stream has finished
+  // switches read once from the environment (tuning / A-B measurements)
+  bool opt_no_fuse = false;  // RUVNB_NO_FUSE=1: separate log-likelihood and Gram sweeps (three Y sweeps per iteration)
+  int opt_llp1_nw = 0;       // RUVNB_LLP1_NW=6|8: rows per CTA of the fused sweep
   // stats of the last iteration
   int last_fail_rows = 0, last_active_rows = 0, last_fail_cells = 0;
   // per-kernel device timing of the sweep kernels (CUDA events on ctx->stream, read at the

@@ -3,45 +3,82 @@
 #include "sweeps.cuh"
 #include "zinb.cuh"
 
+// the fused log-likelihood + Gram sweep applies to plain NB fits with the default Huber constant (robust = TRUE makes
+// every Huber weight live, ZINB needs the general instantiation): see kernels.cuh k_ll_pass1
+static bool fuse_ok(const ruvnb_ctx* ctx, const ruvnb_opts* o) {
+  return o->huber_fastpath && !o->robust && !ctx->zinb_on && !ctx->opt_no_fuse;
+}
+// [Sum l | bad_Mb | nan_Mb] of this rank into scal[0..2] (one all-reduce carries the three)
+static __global__ void k_pack_fin(double* scal, const int* flags) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { scal[1] = (double)flags[2]; scal[2] = (double)flags[3]; }
+}
+
 // per-gene log-likelihood of parameter set `s` into `out` (R/ruvIIInb.R:276-291) and, in the same sweep, the
-// Huber certificate of `s` (s.sigma: +Inf certified / 0 to be evaluated exactly); total (all ranks) into
-// *total if non-null
-static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* out, double* total) {
+// Huber certificate of `s` (s.sigma: +Inf certified / 0 to be evaluated exactly; the rows left at 0 are listed in
+// ctx->faillist).  with_p1: the sweep also leaves the Gram / score sums of `s` for the next inner iteration (k_ll_pass1).
+// total != nullptr: the sum over all genes of all ranks is brought to the host (ONE stream synchronisation, which also
+// brings the number of listed rows and, in fin[0..1], the global counts of problematic / NaN Mb entries).
+static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* out, double* total, bool with_p1 = false, double* fin = nullptr) {
   const double kh = o->robust ? 1.345 : 100.0;  // :155
+  const int Gl = ctx->Gl, P = ctx->nparts;
   RET(ensure_ytabs(ctx, s.psi));
-  const int P = ctx->nparts;
+  if (with_p1) RET(make_rmw(ctx, s.W));
   KEV_BEGIN(4);
   ctx->launch_parts = P;
-  RET(launch_loglik(ctx, geom(ctx, ctx->Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath));
+  int r;
+  if (with_p1) {
+    if (P > 1) {  // groups that a part never meets must read as zero
+      CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * ctx->m * ctx->K * 8, ctx->stream));
+    }
+    r = launch_ll_pass1(ctx, geom(ctx, Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath);
+  } else {
+    r = launch_loglik(ctx, geom(ctx, Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath);
+  }
   ctx->launch_parts = 1;
-  if (P > 1) { k_sum_parts<<<nblk(ctx->Gl, 256), 256, 0, ctx->stream>>>(out, ctx->llparts, ctx->Gl, P); CKL(); }
-  k_cert_finish<<<nblk(ctx->Gl, 128), 128, 0, ctx->stream>>>(ctx->Gl, P, ctx->certc, ctx->hint, s.sigma, kh, o->huber_fastpath, (long long)ctx->N, ctx->cert_diag);
+  RET(r);
+  if (P > 1) { k_sum_parts<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(out, ctx->llparts, Gl, P); CKL(); }
+  k_cert_finish<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, P, ctx->certc, ctx->hint, s.sigma, kh, o->huber_fastpath, (long long)ctx->N, ctx->cert_diag);
   CKL();
   KEV_END(4);
-  s.sig_valid = true; s.maybe_active = false;
+  s.sig_valid = true; s.maybe_active = false; s.p1_valid = with_p1; s.nfail = -1;
+  if (with_p1) { ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false; s.p1_valid = true; }   // one set of sums
+  k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, s.sigma, ctx->faillist, ctx->flags + 4, nullptr);
+  CKL();
+  ctx->faillist_for = s.sigma;
   if (total) {
-    k_colsum<<<1, 1024, 0, ctx->stream>>>(out, ctx->Gl, 1, ctx->scal);
+    k_colsum<<<1, 1024, 0, ctx->stream>>>(out, Gl, 1, ctx->scal);
     CKL();
-    RET(allreduce(ctx, ctx->scal, 1, NCCL_F64));
-    CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    k_pack_fin<<<1, 32, 0, ctx->stream>>>(ctx->scal, ctx->flags); CKL();
+    RET(allreduce(ctx, ctx->scal, 3, NCCL_F64));
+    CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_flags + 6, ctx->w_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     kev_collect(ctx);
     *total = ctx->h_scal[0];
+    s.nfail = ctx->h_flags[4];
+    if (fin) { fin[0] = ctx->h_scal[1]; fin[1] = ctx->h_scal[2]; }
   }
   return RUVNB_OK;
 }
 
 // complete s.sigma: rows the certificate sweep left at 0 get the exact mad/0.6745 (R/ruvIIInb.R:713) -- or +Inf
 // when that exact value proves every weight is 1.  *nfail = rows evaluated exactly, *nactive = rows whose
-// Huber weights are live (finite sigma) afterwards.
+// Huber weights are live (finite sigma) afterwards.  No host synchronisation when the row count came back with the
+// log-likelihood total of the sweep that wrote s.sigma.
 static int complete_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double kh, int* nfail, int* nactive) {
   const int Gl = ctx->Gl;
-  k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, s.sigma, ctx->faillist, ctx->flags + 4, nullptr);
-  CKL();
-  CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  kev_collect(ctx);
-  const int nf = ctx->h_flags[4];
+  if (s.nfail < 0 || (s.nfail > 0 && ctx->faillist_for != s.sigma)) {
+    k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, s.sigma, ctx->faillist, ctx->flags + 4, nullptr);
+    CKL();
+    ctx->faillist_for = s.sigma;
+    CK(cudaMemcpyAsync(ctx->h_flags + 4, ctx->flags + 4, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    kev_collect(ctx);
+    s.nfail = ctx->h_flags[4];
+  }
+  const int nf = s.nfail;
   *nfail = nf;
   if (nf > 0) {
     // exact path in batches of rows through the deviance scratch (<= 2 GB)
@@ -64,15 +101,17 @@ static int complete_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, doub
         while (Ps < 8 && (long long)((nr + NWARP - 1) / NWARP) * Ps < 2 * 296) Ps *= 2;   // few failing rows: cut them into parts
         ctx->launch_parts = Ps;
       }
-      RET(launch_signdev(ctx, geom(ctx, nr, ctx->faillist + r0), s));
+      int r = launch_signdev(ctx, geom(ctx, nr, ctx->faillist + r0), s);
       ctx->launch_parts = 1;
+      RET(r);
       k_row_sigma<<<nr, RS_NT, 0, ctx->stream>>>(ctx->D, ctx->Np, (long long)ctx->N, ctx->faillist + r0, ctx->rowmax, ctx->rownan, kh,
                                                  o->huber_fastpath, s.sigma, ctx->sigma_exact, ctx->hint);
       CKL();
     }
     KEV_END(5);
+    s.maybe_active = true;  // finite sigmas can only come from the exact path
+    s.nfail = 0;            // sigma is complete now
   }
-  if (nf > 0) s.maybe_active = true;  // finite sigmas can only come from the exact path
   *nactive = s.maybe_active ? 1 : 0;
   return RUVNB_OK;
 }
@@ -144,14 +183,84 @@ static int split_rows(ruvnb_ctx* ctx, bool hub, Fn fn) {
   return RUVNB_OK;
 }
 
+// control-gene parameters of the CURRENT state gathered into ctx->ctlpack: [gmean | psi | step | alpha_old (K) | alpha_new (K,
+// filled later) | Mb (m) | pi0 | psi_w] x n_ctl; genes of other ranks read 0 (the pack is then summed over the ranks)
+static __global__ void k_gather_ctlpack(int nc, int K, int m, const int* ctl_local, const double* gmean, const double* psi, const double* step,
+                                        const double* alpha, const double* Mb, const double* pi0, const double* psi_w, double* pk) {
+  const int per = 5 + 2 * K + m;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nc * per) return;
+  // field-major layout (as CtlPack expects): locate the field of element i
+  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
+  double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
+  double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
+  double* dst = pk + i;
+  double v = 0.0;
+  if (dst < p_psi) { int g = ctl_local[i]; if (g >= 0) v = gmean[g]; }
+  else if (dst < p_step) { int g = ctl_local[i - nc]; if (g >= 0) v = psi[g]; }
+  else if (dst < p_aold) { int g = ctl_local[i - 2 * nc]; if (g >= 0) v = step[g]; }
+  else if (dst < p_anew) { long long q = dst - p_aold; int g = ctl_local[q / K]; if (g >= 0) v = alpha[(long long)g * K + q % K]; }
+  else if (dst < p_mb) { v = 0.0; }
+  else if (dst < p_pi0) { long long q = dst - p_mb; int g = ctl_local[q / m]; if (g >= 0) v = Mb[(long long)g * m + q % m]; }
+  else if (dst < p_psiw) { int g = ctl_local[dst - p_pi0]; if (g >= 0) v = pi0[g]; }
+  else { int g = ctl_local[dst - p_psiw]; if (g >= 0) v = psi_w[g]; }
+  *dst = v;
+}
+// this rank's slice of the all-gather buffer: [new alpha rows | current alpha rows] (each zero-padded to `per` rows), then
+// its non-finite count.  The current rows ride along because a NaN on ANY rank reverts the whole matrix (:368).
+static __global__ void k_pack_alpha(const double* a_new, const double* a_cur, long long nloc, long long per_k, const int* bad, double* slice) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 2 * per_k) return;
+  if (i == 2 * per_k) { slice[i] = (double)*bad; return; }
+  const long long q = i < per_k ? i : i - per_k;
+  slice[i] = q < nloc ? (i < per_k ? a_new[q] : a_cur[q]) : 0.0;
+}
+// gathered slices -> alpha_full [G][K] (the new matrix, or the current one when any rank counted a non-finite entry);
+// *bad = sum of the ranks' counts
+static __global__ void k_unpack_alpha(const double* gath, int nranks, long long per_k, long long GK, double* alpha_full, int* bad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long sl = 2 * per_k + 1;
+  double t = 0.0;
+  for (int r = 0; r < nranks; ++r) t += gath[(long long)r * sl + 2 * per_k];
+  if (i < GK) alpha_full[i] = gath[(i / per_k) * sl + (t > 0.0 ? per_k : 0) + i % per_k];
+  if (i == 0) *bad = (int)t;
+}
+// the zero-padded sum path (uneven shards): buf = [new G K | current G K | count]
+static __global__ void k_sumpath_pack(double* buf, long long GK, long long off, long long nloc, const double* a_new, const double* a_cur, const int* bad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nloc) { buf[off + i] = a_new[i]; buf[GK + off + i] = a_cur[i]; }
+  if (i == 0) buf[2 * GK] = (double)*bad;
+}
+static __global__ void k_sumpath_unpack(const double* buf, long long GK, double* alpha_full, int* bad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const double t = buf[2 * GK];
+  if (i < GK) alpha_full[i] = buf[(t > 0.0 ? GK : 0) + i];
+  if (i == 0) *bad = (int)t;
+}
+// all parts of the five pass-1 buffers summed in one launch (k_sum_parts five times)
+static __global__ void k_sum_parts5(double* A, long long nA, double* u, long long nu, double* sw, long long nsw, double* ZS, long long nZS, double* VS, long long nVS, int P) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double* p; long long n;
+  if (i < nA) { p = A; n = nA; }
+  else if ((i -= nA) < nu) { p = u; n = nu; }
+  else if ((i -= nu) < nsw) { p = sw; n = nsw; }
+  else if ((i -= nsw) < nZS) { p = ZS; n = nZS; }
+  else if ((i -= nZS) < nVS) { p = VS; n = nVS; }
+  else return;
+  double s = p[i];
+  for (int q = 1; q < P; ++q) s += p[(long long)q * n + i];
+  p[i] = s;
+}
+
 static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
   const int Gl = ctx->Gl, K = ctx->K, m = ctx->m, KK = K * (K + 1) / 2;
   const double kh = o->robust ? 1.345 : 100.0;  // :155
   StateSet& c = ctx->cur; StateSet& n = ctx->nw;
+  const bool fuse = fuse_ok(ctx, o);
   CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
   RET(ensure_ytabs(ctx, c.psi));
   // Huber scale of the current state (:713,723,409): normally left by the log-likelihood sweep that scored it
-  if (!c.sig_valid) RET(loglik_of(ctx, o, c, ctx->loglik, nullptr));
+  if (!c.sig_valid) RET(loglik_of(ctx, o, c, ctx->loglik, nullptr, fuse));
   int nfail = 0, nactive = 0;
   RET(complete_sigma(ctx, o, c, kh, &nfail, &nactive));
   ctx->last_fail_rows = nfail; ctx->last_active_rows = nactive;
@@ -159,26 +268,49 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   k_partition_sigma<<<1, 1024, 0, ctx->stream>>>(Gl, c.sigma, ctx->roworder_ready ? ctx->d_roworder : nullptr, ctx->list_inf, ctx->list_fin, ctx->part_counts);
   CKL();
   const int P = ctx->nparts;
+  // control-gene parameters of the current state for the W step: gathered (and, when sharded, summed over the ranks) on the
+  // side stream while pass 1 runs -- nothing of it depends on this iteration's work except alpha_new, filled in later
+  const int nc = ctx->n_ctl;
+  double* pk = ctx->ctlpack;
+  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
+  double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
+  double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
+  {
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    k_gather_ctlpack<<<nblk((long long)nc * (5 + 2 * K + m), 256), 256, 0, ctx->stream2>>>(nc, K, m, ctx->d_ctl_local, c.gmean, c.psi, ctx->step, c.alpha, c.Mb, c.pi0, c.psi_w, pk);
+    CKL();
+    if (ctx->nranks > 1) {
+      int r = g_nccl.AllReduce(pk, pk, (size_t)nc * (5 + 2 * K + m), NCCL_F64, NCCL_SUM, ctx->comm, ctx->stream2);
+      if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclAllReduce (control-gene pack): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    }
+    CK(cudaEventRecord(ctx->ev_ctl, ctx->stream2));
+  }
   // alpha ------------------------------------------------------------------------------------------
-  RET(make_rmw(ctx, c.W));
   {
     KEV_BEGIN(1);
     ctx->launch_parts = P;
-    if (P > 1) {  // groups that a part never meets must read as zero
-      CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * m * 8, ctx->stream));
-      CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
+    int r = RUVNB_OK;
+    if (!c.p1_valid) {
+      RET(make_rmw(ctx, c.W));
+      if (P > 1) {  // groups that a part never meets must read as zero
+        CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * m * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
+      }
+      // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
+      // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
+      r = split_rows(ctx, hub, [&](const RowGeom& g, bool huber) { return launch_pass1(ctx, huber, g, c, kh); });
+    } else if (hub) {
+      // the sums came with the sweep that scored this state (k_ll_pass1, unit Huber weights; ctx->RMW is that of c.W);
+      // only the rows whose weights turned out to be live are redone
+      RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
+      r = launch_pass1(ctx, true, gf, c, kh);
     }
-    // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
-    // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
-    int r = split_rows(ctx, hub, [&](const RowGeom& g, bool huber) { return launch_pass1(ctx, huber, g, c, kh); });
     ctx->launch_parts = 1;
     RET(r);
+    c.p1_valid = false;   // consumed: the sums are normalised in place below
     if (P > 1) {
-      k_sum_parts<<<nblk((long long)Gl * KK, 256), 256, 0, ctx->stream>>>(ctx->A, ctx->A, (long long)Gl * KK, P); CKL();
-      k_sum_parts<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(ctx->u, ctx->u, (long long)Gl * K, P); CKL();
-      k_sum_parts<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->sw, ctx->sw, Gl, P); CKL();
-      k_sum_parts<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(ctx->ZS, ctx->ZS, (long long)Gl * m, P); CKL();
-      k_sum_parts<<<nblk((long long)Gl * m * K, 256), 256, 0, ctx->stream>>>(ctx->VS, ctx->VS, (long long)Gl * m * K, P); CKL();
+      const long long nA = (long long)Gl * KK, nu = (long long)Gl * K, nZ = (long long)Gl * m, nV = (long long)Gl * m * K;
+      k_sum_parts5<<<nblk(nA + nu + Gl + nZ + nV, 256), 256, 0, ctx->stream>>>(ctx->A, nA, ctx->u, nu, ctx->sw, Gl, ctx->ZS, nZ, ctx->VS, nV, P); CKL();
     }
     KEV_END(1);
   }
@@ -193,38 +325,42 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     k_adev<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, ctx->A, ctx->cvec, ctx->amean, o->lambda_a, n.alpha, n.adev, ctx->flags + 0);
     CKL();
   });
-  RET(allreduce(ctx, ctx->flags, 1, NCCL_INT32));
-  k_revert_if<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(ctx->flags + 0, n.alpha, c.alpha, (long long)Gl * K);  // :368
-  CKL();
-  // clamp each column to median +- 4 mad over ALL genes (:371-376)
+  // NaN anywhere (any rank) -> the whole alpha reverts (:368); then each column is clamped to median +- 4 mad over ALL genes
+  // (:371-376).  Sharded: the slices (and each rank's non-finite count) are all-gathered, so every rank holds the full
+  // matrix -- the control-gene rows of it feed the W step
   if (ctx->nranks > 1) {
-    CK(cudaMemsetAsync(ctx->alpha_full, 0, (size_t)ctx->G * K * 8, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->alpha_full + ctx->g0 * K, n.alpha, (size_t)Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    RET(allreduce(ctx, ctx->alpha_full, (size_t)ctx->G * K, NCCL_F64));
-    k_strided_medmad<<<K, RS_NT, 0, ctx->stream>>>(ctx->alpha_full, 1, K, (int)ctx->G, ctx->med, ctx->mad);
+    const long long per = (ctx->G + ctx->nranks - 1) / ctx->nranks, per_k = per * K, GK = ctx->G * K;
+    const bool even = ctx->g0 == std::min<long long>(ctx->G, per * ctx->rank) && ctx->g1 == std::min<long long>(ctx->G, per * (ctx->rank + 1));
+    // every rank must take the same branch: uneven shards are a property of the caller's set_design ranges on ALL ranks
+    if (even) {
+      const long long sl = 2 * per_k + 1;
+      double* mine = ctx->agather + (long long)ctx->rank * sl;
+      k_pack_alpha<<<nblk(sl, 256), 256, 0, ctx->stream>>>(n.alpha, c.alpha, (long long)Gl * K, per_k, ctx->flags + 0, mine); CKL();
+      int r = g_nccl.AllGather(mine, ctx->agather, (size_t)sl, NCCL_F64, ctx->comm, ctx->stream);
+      if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclAllGather (alpha): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+      k_unpack_alpha<<<nblk(GK, 256), 256, 0, ctx->stream>>>(ctx->agather, ctx->nranks, per_k, GK, ctx->alpha_full, ctx->flags + 0); CKL();
+    } else {
+      CK(cudaMemsetAsync(ctx->agather, 0, (size_t)(2 * GK + 1) * 8, ctx->stream));
+      k_sumpath_pack<<<nblk(std::max<long long>(1, (long long)Gl * K), 256), 256, 0, ctx->stream>>>(ctx->agather, GK, ctx->g0 * K, (long long)Gl * K, n.alpha, c.alpha, ctx->flags + 0); CKL();
+      RET(allreduce(ctx, ctx->agather, (size_t)(2 * GK + 1), NCCL_F64));
+      k_sumpath_unpack<<<nblk(GK, 256), 256, 0, ctx->stream>>>(ctx->agather, GK, ctx->alpha_full, ctx->flags + 0); CKL();
+    }
+    k_revert_if<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(ctx->flags + 0, n.alpha, c.alpha, (long long)Gl * K); CKL();  // :368
+    k_strided_medmad<<<K, RS_NT, 0, ctx->stream>>>(ctx->alpha_full, 1, K, (int)ctx->G, ctx->med, ctx->mad); CKL();
+    k_clamp_cols<<<nblk((long long)ctx->G * K, 256), 256, 0, ctx->stream>>>(ctx->alpha_full, ctx->G, K, ctx->med, ctx->mad); CKL();
+    k_clamp_cols<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(n.alpha, Gl, K, ctx->med, ctx->mad); CKL();
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ctl, 0));   // the control-gene pack (side stream) is complete
+    k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(ctx->alpha_full, ctx->d_ctl_global, nc, K, p_anew); CKL();
   } else {
-    k_strided_medmad<<<K, RS_NT, 0, ctx->stream>>>(n.alpha, 1, K, Gl, ctx->med, ctx->mad);
+    k_revert_if<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(ctx->flags + 0, n.alpha, c.alpha, (long long)Gl * K); CKL();  // :368
+    k_strided_medmad<<<K, RS_NT, 0, ctx->stream>>>(n.alpha, 1, K, Gl, ctx->med, ctx->mad); CKL();
+    k_clamp_cols<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(n.alpha, Gl, K, ctx->med, ctx->mad); CKL();
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ctl, 0));   // the control-gene pack (side stream) is complete
+    k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(n.alpha, ctx->d_ctl_local, nc, K, p_anew); CKL();
   }
-  CKL();
-  k_clamp_cols<<<nblk((long long)Gl * K, 256), 256, 0, ctx->stream>>>(n.alpha, Gl, K, ctx->med, ctx->mad);
-  CKL();
   // W ------------------------------------------------------------------------------------------------
   {
-    const int nc = ctx->n_ctl;
-    double* pk = ctx->ctlpack;
     CtlPack cp;
-    double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
-    double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
-    double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
-    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.gmean, ctx->d_ctl_local, nc, 1, p_gmean); CKL();
-    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.psi, ctx->d_ctl_local, nc, 1, p_psi); CKL();
-    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(ctx->step, ctx->d_ctl_local, nc, 1, p_step); CKL();
-    k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(c.alpha, ctx->d_ctl_local, nc, K, p_aold); CKL();
-    k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(n.alpha, ctx->d_ctl_local, nc, K, p_anew); CKL();
-    k_gather_rows<<<nblk((long long)nc * m, 256), 256, 0, ctx->stream>>>(c.Mb, ctx->d_ctl_local, nc, m, p_mb); CKL();
-    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.pi0, ctx->d_ctl_local, nc, 1, p_pi0); CKL();
-    k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(c.psi_w, ctx->d_ctl_local, nc, 1, p_psiw); CKL();
-    RET(allreduce(ctx, pk, (size_t)nc * (5 + 2 * K + m), NCCL_F64));
     cp.gmean = p_gmean; cp.psi = p_psi; cp.step = p_step; cp.alpha_old = p_aold; cp.alpha_new = p_anew; cp.Mb = p_mb;
     cp.pi0 = p_pi0; cp.psi_w = p_psiw; cp.zinf = ctx->d_zinf; cp.zinb = ctx->zinb_on ? 1 : 0;
     // cells are sharded over the ranks in whole chunks; the slices are summed (disjoint) afterwards
@@ -253,16 +389,20 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     ctx->launch_parts = 1;
     RET(r);
     if (P > 1) {
-      k_sum_parts<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(ctx->S0, ctx->S0, (long long)Gl * m, P); CKL();
-      k_sum_parts<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(ctx->S1, ctx->S1, (long long)Gl * m, P); CKL();
+      const long long nZ = (long long)Gl * m;
+      k_sum_parts5<<<nblk(2 * nZ, 256), 256, 0, ctx->stream>>>(ctx->S0, nZ, ctx->S1, nZ, nullptr, 0, nullptr, 0, nullptr, 0, P); CKL();
     }
     KEV_END(3);
   }
   k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
-  RET(allreduce(ctx, ctx->flags + 2, 2, NCCL_INT32));
+  // "any NA -> the whole Mb reverts" (:424) needs the NaN count of ALL ranks.  NB: it is taken speculatively as this rank's
+  // own count; the global count travels with the log-likelihood total, and the tail is redone in the (rare) case they
+  // disagree.  ZINB (whose tail holds the Nelder-Mead rounds) settles the count first.
+  if (ctx->zinb_on) RET(allreduce(ctx, ctx->flags + 2, 2, NCCL_INT32));
   k_mb_finalize<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, m, ctx->flags + 3, c.Mb, n.Mb); CKL();
   // psi is fixed inside the inner loop
   CK(cudaMemcpyAsync(n.psi, c.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  double fin[2] = {0.0, 0.0};
   if (ctx->zinb_on) {
     // step 4a (:435-467): pi0 at the NEW parameters, then the E-step weights -- recomputed on the fly from (pi0, psi_w)
     CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -271,16 +411,26 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     RET(zinb_update_pi0(ctx, n, c.pi0, n.pi0, &nbad_pi0));
     if (nbad_pi0) CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :454
     CK(cudaMemcpyAsync(n.psi_w, n.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));             // :457-467
+    RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new, false, nullptr));
+    fin[0] = ctx->h_flags[2]; fin[1] = ctx->h_flags[3];   // already global
   } else {
     CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(n.psi_w, c.psi_w, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    // candidate log-likelihood (:469-484) + its Huber certificate (+ its Gram / score sums) for the next iteration
+    RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new, fuse, fin));
+    if (ctx->nranks > 1 && fin[1] > 0.0 && ctx->h_flags[3] == 0) {
+      // another rank produced NaN in Mb and this one did not revert: revert now and score the candidate again
+      const int one = 1;
+      CK(cudaMemcpyAsync(ctx->flags + 3, &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      k_mb_finalize<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, m, ctx->flags + 3, c.Mb, n.Mb); CKL();
+    }
+    if (ctx->nranks > 1 && fin[1] > 0.0) {   // every rank scores again (same branch everywhere: fin is a global count)
+      double f2[2];
+      RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new, fuse, f2));
+    }
   }
-  // candidate log-likelihood (:469-484) + its Huber certificate for the next iteration
-  RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new));
-  CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_flags + 6, ctx->w_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (bad) { bad[0] = ctx->h_flags[0]; bad[1] = ctx->h_flags[1]; bad[2] = ctx->h_flags[2]; }
+  // h_flags[0..4] and [6] came back with the log-likelihood total (loglik_of)
+  if (bad) { bad[0] = ctx->h_flags[0]; bad[1] = ctx->h_flags[1]; bad[2] = (ctx->nranks > 1 && !ctx->zinb_on) ? (int)fin[0] : ctx->h_flags[2]; }
   ctx->last_fail_cells = ctx->h_flags[6];
   std::swap(ctx->cur, ctx->nw);
   return RUVNB_OK;
@@ -298,7 +448,8 @@ static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
   CK(cudaMemcpyAsync(dst.sigma, src.sigma, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.psi_w, src.psi_w, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.wtctl, src.wtctl, (size_t)ctx->n_ctl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active;
+  dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active; dst.nfail = src.nfail;
+  dst.p1_valid = false;   // the Gram / score sums in ctx->A.. belong to one parameter set (and one step vector) only
   return RUVNB_OK;
 }
 
@@ -324,7 +475,7 @@ int ruvnb_init_coef(ruvnb_ctx* ctx, const ruvnb_opts* o) {
 
 int ruvnb_loglik(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total) {
   RET(check_ready(ctx, o));
-  return loglik_of(ctx, o, ctx->cur, ctx->loglik, total);
+  return loglik_of(ctx, o, ctx->cur, ctx->loglik, total, fuse_ok(ctx, o));   // the next ruvnb_irls_iteration starts from its sums
 }
 
 int ruvnb_irls_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
@@ -367,6 +518,7 @@ int ruvnb_halve_steps(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   if (!ctx || !o || ctx->K == 0) return RUVNB_EARG;
   CK(cudaSetDevice(ctx->device));
   k_halve<<<nblk(ctx->Gl, 256), 256, 0, ctx->stream>>>(ctx->Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();
+  ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false;   // the Gram / score sums were taken with the old steps
   return RUVNB_OK;
 }
 // accept the candidate: loglik <- loglik.tmp (:512)
@@ -431,12 +583,16 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
   bool conv = false;
   int iter_outer = 0;
   std::vector<double> lo;
+  double s_carry = 0.0; bool have_carry = false;
+  long long exact_cells = 0;
   while (!conv) {
     iter_outer++;
     std::vector<double> logl_beta;
-    double s_old = 0.0;
-    RET(loglik_of(ctx, o, ctx->cur, ctx->loglik, &s_old));  // :276-291
-    k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :293
+    double s_old = s_carry;
+    if (!have_carry) {
+      k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :293 (before the sweep: its Gram sums use the steps)
+      RET(loglik_of(ctx, o, ctx->cur, ctx->loglik, &s_old, fuse_ok(ctx, o)));  // :276-291
+    }   // else: the sweep that closed the previous outer iteration (:577-593) scored this very state with these psi and steps
     RET(copy_set(ctx, ctx->best, ctx->cur));                                    // :296
     int iter = 1, halving = 0;
     bool conv_beta = false;
@@ -447,12 +603,14 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
       RET(irls_body(ctx, o, &s_new, bad));
       n_inner++;
       exact_rows += ctx->last_fail_rows;
+      exact_cells += ctx->last_fail_cells;
       bool degener = !(std::isfinite(s_old) && std::isfinite(s_new)) || (s_old > s_new);  // :487-488
       ruvnb_trace_rec rec;
       rec.outer = iter_outer; rec.iter = iter; rec.halving = halving; rec.degener = degener ? 1 : 0;
       rec.logl_old = s_old; rec.logl_new = s_new; rec.bad_alpha = bad[0]; rec.bad_W = bad[1]; rec.bad_Mb = bad[2];
       if (degener) {
         k_halve<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();  // :490-491
+        ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false;
         RET(copy_set(ctx, ctx->cur, ctx->best));  // :492
         if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :494-504
         halving++;
@@ -487,7 +645,9 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
     RET(copy_set(ctx, ctx->cur, ctx->best));  // :568-573
     if (updt) RET(refresh_psi(ctx->cur));
     double s = 0.0;
-    RET(loglik_of(ctx, o, ctx->cur, ctx->loglik, &s));  // :577-593
+    k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // the next outer iteration's :293, before the sweep
+    RET(loglik_of(ctx, o, ctx->cur, ctx->loglik, &s, fuse_ok(ctx, o)));  // :577-593; also the next outer iteration's :276-291
+    s_carry = s; have_carry = true;
     lo.push_back(s);
     if (logl_outer && iter_outer <= o->outer_maxit) logl_outer[iter_outer - 1] = s;
     if (o->verbose) fprintf(stderr, "Outer Iter %d logl-likelihood:%.10g\n", iter_outer, s);
@@ -503,7 +663,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
     stats->n_outer = iter_outer; stats->n_inner = n_inner; stats->n_trace = n_trace;
     stats->inner_seconds = inner_ms * 1e-3; stats->disp_seconds = disp_ms * 1e-3; stats->total_seconds = ms * 1e-3;
     stats->kernel_launches = ctx->launches - launches0;
-    stats->n_exact_mad_rows = exact_rows; stats->n_exact_mad_cells = (int)std::min<long long>(ctx->N * (long long)n_inner, 2147483647ll);
+    stats->n_exact_mad_rows = exact_rows; stats->n_exact_mad_cells = (int)std::min<long long>(exact_cells, 2147483647ll);
   }
   CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1)); CK(cudaEventDestroy(t0)); CK(cudaEventDestroy(t1));
   return RUVNB_OK;

@@ -18,6 +18,7 @@ struct RowGeom {
   int nchunks;          // multiple of CHPAD; trailing chunks may be empty (chunk_valid == 0)
   const int* chunk_grp;
   const int* chunk_valid;
+  const int* chunk_meta; // [nchunks] (group << 8) | valid: what the row walk reads (one load per chunk, fetched a chunk ahead)
   int nrows;            // rows this launch walks (upper bound when nrows_dev is set)
   const int* rowlist;   // nullptr -> slot == row; else row = rowlist[slot] (exact-MAD batches, partitions)
   const int* nrows_dev; // optional device-side row count: slots >= *nrows_dev idle (lists built on the device)
@@ -48,6 +49,7 @@ struct GeneState {  // pointers to one parameter set (current, candidate or best
 
 // chunks per shared-memory stage: 512 cells for k <= 5, 256 above (tile bytes = 2 x NSETS x K x 8 x cells)
 template <int K> struct TileCfg { static constexpr int SC = (K <= 5) ? 4 : 2; static constexpr int CELLS = SC * CH; };
+static inline int TileCfg_SC(int K) { return K <= 5 ? 4 : 2; }   // host mirror
 
 // per-CTA shared tables of the row-streaming kernels
 struct RowShared {
@@ -182,7 +184,8 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   int curj = -1;
   // the counts of the next chunk are fetched one chunk ahead (HBM latency hides behind ~4 elements of math)
   int2 ya = make_int2(0, 0), yb = ya;
-  if (active && t0 < ntiles) { ya = yrow2[t0 * SC * (CH / 2) + lane]; yb = yrow2[t0 * SC * (CH / 2) + 32 + lane]; }
+  int meta = 0;   // (group << 8) | valid cells of the next chunk, fetched with its counts
+  if (active && t0 < ntiles) { ya = yrow2[t0 * SC * (CH / 2) + lane]; yb = yrow2[t0 * SC * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[t0 * SC]; }
   if (t0 < ntiles) stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, t0, tid);
   for (int t = t0; t < ntiles; ++t) {
     if (t + 1 < ntiles) {
@@ -198,10 +201,11 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
       for (int sc = 0; sc < SC; ++sc) {
         const int c = t * SC + sc;
         const int2 y01 = ya, y23 = yb;
-        if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; }
-        const int nv = geo.chunk_valid[c];
+        const int mcur = meta;
+        if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c + 1]; }
+        const int nv = mcur & 0xff;
         if (nv == 0 && !Op::PADS) continue;
-        const int j = geo.chunk_grp[c];
+        const int j = mcur >> 8;
         if (j != curj && nv > 0) {
           if (curj >= 0) op.group_end(curj);
           curj = j;
@@ -255,13 +259,15 @@ __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* 
   const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
   int curj = -1;
   int2 ya = yrow2[lane], yb = yrow2[32 + lane];
+  int meta = geo.chunk_meta[0];
 #pragma unroll 1
   for (int c = 0; c < geo.nchunks; ++c) {
     const int2 y01 = ya, y23 = yb;
-    if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; }
-    const int nv = geo.chunk_valid[c];
+    const int mcur = meta;
+    if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c + 1]; }
+    const int nv = mcur & 0xff;
     if (nv == 0) continue;
-    const int j = geo.chunk_grp[c];
+    const int j = mcur >> 8;
     if (j != curj) {
       if (curj >= 0) op.group_end(curj);
       curj = j;
@@ -752,6 +758,157 @@ __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> 
   op.st = st; op.sigma = sigma; op.kh = kh;
   op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
   stream_rows<K, 2, OpPass1<K, HUBER>, NW>(geo, &sh, op, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_ll_pass1: the candidate's log-likelihood sweep (k_loglik, with the Huber certificate counters) FUSED with the Gram /
+// score sweep (k_pass1<HUBER = false>) of the NEXT inner iteration.  Both walk the same row with the same parameter set:
+// when the candidate is accepted (R/ruvIIInb.R:486-516) it becomes the current state, and its lmu, exp(lmu) and
+// sig.inv are exactly what get.coef2 needs one iteration later (:303-354) -- one read of Y, one dot product and one exp
+// per element instead of two.  The pass-1 half is speculative: it assumes (i) the step is accepted -- a rejected
+// candidate is thrown away with its sums -- and (ii) every Huber weight is 1; rows whose certificate fails in this very
+// sweep are redone by k_pass1<HUBER = true> once their exact sigma is known.  Per-element arithmetic and summation order
+// are those of OpLoglik and OpPass1, so the fused and the separate sweeps return the same bits.  NB only (no ZINB).
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct OpLLPass1 {
+  static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
+  static constexpr int KK = K * (K + 1) / 2;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
+  GeneState<K> st;
+  GeneRegs<K> g;
+  // log-likelihood + certificate (OpLoglik)
+  double acc, rlogr;
+  double* ll_out; const double* hint; int* certc; int fastpath;
+  int k_lo, k_hi, k_wl, k_wh, hmaxk, c1, c2, c3; bool cert;
+  // Gram / score / group sums (OpPass1)
+  double A[KK], u[K], sw, gz, V[K];
+  double *A_out, *u_out, *sw_out, *ZS, *VS;
+  int row_, lane;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    g.load(st, row); row_ = row; lane = threadIdx.x & 31;
+    acc = 0.0; rlogr = g.r * log(g.r);
+    cert = false; c1 = c2 = c3 = 0; hmaxk = 0; k_lo = k_hi = k_wl = k_wh = 0;
+    if (fastpath && certc) {
+      double lo = hint[(long long)row * 3 + 0], hi = hint[(long long)row * 3 + 1], tg = hint[(long long)row * 3 + 2];
+      cert = tg > 0.0 && lo <= hi;
+      if (cert) {
+        k_lo = OpLoglik<K>::okey(u_of_d(lo)); k_hi = OpLoglik<K>::okey(u_of_d(hi));
+        k_wl = OpLoglik<K>::okey(u_of_d(lo - tg)); k_wh = OpLoglik<K>::okey(u_of_d(hi + tg));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KK; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) u[i] = 0.0;
+    sw = 0.0;
+  }
+  __device__ __forceinline__ void group_begin(int j) {
+    g.mbj = g.mb[j]; gz = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) V[i] = 0.0;
+  }
+  __device__ __forceinline__ void count(double h, double yd, double mu, bool m) {   // OpLoglik::count
+    const int hi = __double2hiint(h);
+    const int kraw = m ? (hi & 0x7fffffff) : 0;
+    hmaxk = max(hmaxk, kraw);
+    const int kpos = max(hi, 0);
+    const int ks = (yd > mu) ? kpos : ~kpos;
+    c1 += m & (ks <= k_lo); c2 += m & (ks >= k_hi); c3 += m & (ks >= k_wl) & (ks <= k_wh);
+  }
+  // OpLoglik::one_fast given mu = fexp_nc(lmu)
+  __device__ __forceinline__ void ll_fast(int y, double yd, double lmu, double mu) {
+    const double L = flog_nc(mu + g.r, g.mt->rc, g.mt->lc);
+    acc += fma(-g.r, L, rlogr) + fma(yd, lmu - L, g.tl[y]);
+    if (cert) count(fma(yd, g.mt->ly[y] - lmu, -(yd + g.r) * (g.tr[y] - L)), yd, mu, true);
+  }
+  // OpLoglik::one (plain NB): any count, any argument range
+  __device__ __forceinline__ void ll_gen(int y, double yd, double lmu) {
+    const double mu = g.expm(lmu);
+    const double L = g.logL(mu);
+    acc += nb_logpmf_t(y, yd, lmu, L, g.r, g.lgr, rlogr, g.tl, g.mt);
+    if (cert) count(nb_devhalf_t(y, yd, lmu, L, g.r, g.tr, g.mt), yd, mu, true);
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
+    const double* w = tile; const double* rw = tile + K * CELLS;
+    double l0, l1;
+    g.lmu_pair(w, ti, l0, l1);
+    const double yd0 = (double)y0, yd1 = (double)y1;
+    double mu0, s0, q0, mu1, s1, q1;
+    const bool fr = g.fast_range(l0, l1);
+    if (fr) {
+      nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &s0, &q0);
+      nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &s1, &q1);
+    } else {
+      SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
+      mu0 = a.mu; s0 = a.s; q0 = a.q; mu1 = b.mu; s1 = b.s; q1 = b.q;
+    }
+    if (FULLCHUNK && fr && (unsigned)(y0 | y1) < (unsigned)YT) {
+      ll_fast(y0, yd0, l0, mu0);
+      ll_fast(y1, yd1, l1, mu1);
+    } else {
+      if (m0) ll_gen(y0, yd0, l0);
+      if (m1) ll_gen(y1, yd1, l1);
+    }
+    double Z0 = fma(g.step, q0 - 1.0, l0), Z1 = fma(g.step, q1 - 1.0, l1);
+    double wt0 = s0, wt1 = s1;
+    if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
+    sw += wt0 + wt1; gz += Z0 + Z1;
+    double2 r[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double wi0 = wt0 * r[i].x, wi1 = wt1 * r[i].y;
+      V[i] += wi0 + wi1;
+      u[i] = fma(wi1, Z1, fma(wi0, Z0, u[i]));
+#pragma unroll
+      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi1, r[jx].y, fma(wi0, r[jx].x, A[idx])); ++idx; }
+    }
+  }
+  __device__ __forceinline__ void group_end(int j) {
+    double z = warp_sum(gz);
+    if (lane == 0) ZS[(long long)row_ * st.m + j] = z;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      double v = warp_sum(V[i]);
+      if (lane == 0) VS[((long long)row_ * st.m + j) * K + i] = v;
+    }
+  }
+  __device__ __forceinline__ void row_end(int row) {
+    {
+      double v = warp_sum(acc);
+      if (lane == 0) ll_out[row] = v;
+      if (certc) {
+        int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
+        const int hk = __reduce_max_sync(FULL, hmaxk);
+        if (lane == 0) { int4 o = make_int4(a1, a2, a3, hk); reinterpret_cast<int4*>(certc)[row] = o; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < KK; ++i) { double v = warp_sum(A[i]); if (lane == 0) A_out[(long long)row * KK + i] = v; }
+#pragma unroll
+    for (int i = 0; i < K; ++i) { double v = warp_sum(u[i]); if (lane == 0) u_out[(long long)row * K + i] = v; }
+    double v = warp_sum(sw);
+    if (lane == 0) sw_out[row] = v;
+  }
+};
+template <int K, int NW>
+__global__ void __launch_bounds__(NW * 32, 2) k_ll_pass1(RowGeom geo, GeneState<K> st, const double* RMW, double* ll_out /* [nparts][Gl] */,
+                                                         const double* hint, int* certc /* [nparts][Gl][4] or nullptr */, int fastpath,
+                                                         double* A_out, double* u_out, double* sw_out, double* ZS, double* VS) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
+  constexpr int KK = K * (K + 1) / 2;
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;   // part-major partial sums
+  OpLLPass1<K> op;
+  op.st = st; op.ll_out = ll_out + poff; op.hint = hint; op.certc = certc ? certc + poff * 4 : nullptr; op.fastpath = fastpath;
+  op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
+  stream_rows<K, 2, OpLLPass1<K>, NW>(geo, &sh, op, smem);
 }
 
 // finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its

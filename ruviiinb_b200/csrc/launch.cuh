@@ -5,7 +5,7 @@
 // ---- launch helpers ---------------------------------------------------------------------------------
 static RowGeom geom(ruvnb_ctx* ctx, int nrows, const int* rowlist) {
   RowGeom g;
-  g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid;
+  g.Yp = ctx->dY; g.Np = ctx->Np; g.nchunks = ctx->nchunks; g.chunk_grp = ctx->d_chunk_grp; g.chunk_valid = ctx->d_chunk_valid; g.chunk_meta = ctx->d_chunk_meta;
   g.nrows = nrows; g.rowlist = rowlist; g.nrows_dev = nullptr; g.nparts = ctx->launch_parts; g.Gl = ctx->Gl;
   if (!rowlist && nrows == ctx->Gl && ctx->roworder_ready) g.rowlist = ctx->d_roworder;   // full sweeps: heavy rows first
   g.mtabs = ctx->d_mtabs; g.tabL = ctx->tabL; g.tabR = ctx->tabR; g.lgr = ctx->lgr;

@@ -6,6 +6,8 @@
 
 // k_loglik: per-gene log-likelihood of `s` (+ certificate counters) into out[part][Gl]      (sweep_loglik.cu)
 int launch_loglik(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s, double* out, int fastpath);
+// k_ll_pass1: the same fused with the next iteration's Gram / score sums (ctx->RMW must hold RM_W of s.W)  (sweep_llp1.cu)
+int launch_ll_pass1(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s, double* out, int fastpath);
 // k_signdev: signed deviances of the listed rows into ctx->D (exact-MAD path)                (sweep_loglik.cu)
 int launch_signdev(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s);
 // k_pass1<HUBER>: Gram / score / group sums of `c` into ctx->A, u, sw, ZS, VS                (sweep_pass1.cu)

@@ -9,7 +9,8 @@ def _data(G=90, N=700, k=2, m=3, n_ctl=24, seed=91):
     Y, M, ctl, truth = synth.make_counts(G, N, k, m, n_ctl, seed=seed, gmean_mu=0.8, gmean_sd=0.9)
     Y[7] = 0                      # an all-zero gene is dropped (R/ruvIIInb.R:57-62)
     Y[11, 5] = 4000               # an outlier count is winsorised (:53)
-    return Y, M, ctl, truth
+    Y[13] = 0; Y[13, [3, N // 2]] = [2, 5]   # expressed in < 0.5 % of the cells: the cap (99.5 % quantile = 0) empties the row, which is
+    return Y, M, ctl, truth              # dropped AFTER the cap like an all-zero gene (:53-62)
 
 
 @pytest.mark.gpu
@@ -29,7 +30,7 @@ def test_ruvIII_nb_end_to_end_matches_oracle():
     trace = []
     ref = orc.ruvIII_nb(Y.astype(np.float64), M, ctl, k=2, outer_maxit=3, W0=W0, psi_fn=psi_fn, trace=trace)
     out = api.ruvIII_nb(Y, M, ctl, k=2, outer_maxit=3, W0=W0, return_trace=True)
-    assert out["zero_genes"][7] and out["counts"].shape[0] == Y.shape[0] - 1
+    assert out["zero_genes"][7] and out["zero_genes"][13] and out["counts"].shape[0] == Y.shape[0] - 2 == ref["counts"].shape[0]
     assert np.array_equal(out["counts"], ref["counts"].astype(np.int32))
     dec = [(r["outer"], r["iter"], r["degener"], r["accepted"]) for r in out["trace"]]
     assert dec == [(r["outer"], r["iter"], int(r["degener"]), int(r["accepted"])) for r in trace]
