@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RUVNB_ABI_VERSION 2
+#define RUVNB_ABI_VERSION 3
 
 #define RUVNB_OK 0
 #define RUVNB_EARG (-1)    /* invalid argument */
@@ -248,6 +248,32 @@ int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp,
 /* F7 (:765-770) psi capped at exp(median(log psi) + 3 mad(log psi)), in place (host vector; no device needed). */
 int ruvnb_fast_cap_psi(double* psi, int64_t G);
 
+/* ---- cell shards: the full-data passes of fastruvIII.nb and get.res at 10^6 cells ----------------
+ * Blocks of `block.size` cells are independent in get.res (R/get.res.R:27-126) and in the W / Mb passes of fastruvIII.nb
+ * (R/fastruvIIInb.R:639-689,727-738), so a problem too large for one GPU is cut by CELL: every rank (one context per GPU)
+ * holds ALL genes of the cells [c0, c0 + N) of N_total, N being the N of ruvnb_set_design and c0 a multiple of the block size
+ * used later.  The three quantities that cross blocks are summed over the communicator of ruvnb_comm_init (call it BEFORE
+ * ruvnb_set_design): the per-gene count histograms of the Winsorize quantile (R/fastruvIIInb.R:81-95), colSums(W) for
+ * colMeans(W) (R/get.res.R:36) and the convergence criterion of the W sweeps (R/fastruvIIInb.R:709).  A cell-sharded context
+ * refuses the gene-sharded operators (ruvnb_irls_iteration, ruvnb_fit_nb, ...). */
+int ruvnb_set_cell_shard(ruvnb_ctx* ctx, int64_t N_total, int64_t c0);
+/* Rows (genes) that get.res / the fused Mb + PAC pass report: alive[g] = 0 drops local row g from every output (the reference
+ * removes the genes the Winsorize cap emptied, R/fastruvIIInb.R:97-101, before anything else sees them; here they stay resident
+ * and are skipped).  Outputs then have sum(alive) rows.  NULL restores all rows. */
+int ruvnb_set_row_mask(ruvnb_ctx* ctx, const uint8_t* alive);
+/* Counts already in device memory (a slab of nrows gene rows x N cells, gene-major, row0 = first local row): the upload
+ * permutes them into the resident layout without touching the host.  on_device = 0 takes a host slab the same way (a matrix
+ * larger than host memory arrives in pieces).  Call ruvnb_upload_counts_done after the last slab. */
+int ruvnb_upload_counts_rows(ruvnb_ctx* ctx, const int32_t* Y_rows, int on_device, int64_t row0, int64_t nrows);
+int ruvnb_upload_counts_done(ruvnb_ctx* ctx);
+/* The resident (winsorized) counts of `n` local cells (0-based, any order), all local rows: out is G x n column-major int32 --
+ * how the subsample of fastruvIII.nb (R/fastruvIIInb.R:118-137) leaves the device without the whole matrix travelling. */
+int ruvnb_get_cells(ruvnb_ctx* ctx, const int64_t* cells, int64_t n, int32_t* out);
+/* Page-locked host memory for the large result matrices (a pageable destination runs the device->host stream at a fifth of
+ * the PCIe rate). */
+void* ruvnb_host_alloc(size_t bytes);
+void ruvnb_host_free(void* p);
+
 /* ---- get.res (R/get.res.R:12-129) -------------------------------------------------------------- */
 #define RUVNB_RES_PEARSON 1
 #define RUVNB_RES_LOGCOUNTS 2
@@ -255,6 +281,30 @@ int ruvnb_fast_cap_psi(double* psi, int64_t G);
 /* Mb_cells: G x N per-cell Mb (fastruvIII.nb's Mb.all) or NULL to expand the resident G x m Mb by
  * group.  out: G x N column-major doubles (what write_block receives, :125). */
 int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out);
+/* The same with the sink chosen by the caller.  out_kind: */
+#define RUVNB_OUT_F64 0    /* doubles, G x N column-major (what ruvnb_get_res writes)                                     */
+#define RUVNB_OUT_I32 1    /* int32 (type RUVNB_RES_QUANTILE only: PAC are integers; half the bytes of the stream)        */
+#define RUVNB_OUT_LOG1P 2  /* log(PAC + 1) as doubles: makeSCE's logPAC assay (R/makeSCE.R:36-38)                         */
+#define RUVNB_OUT_NONE 3   /* nothing leaves the device: only `checksum` (sum of all values written) -- full-size runs    */
+typedef struct ruvnb_res_stats {
+  double checksum;          /* sum over all reported elements of the values written (clipped Pearson, PAC, ...)            */
+  double device_seconds;    /* first kernel to last kernel of the call, CUDA events on the library's stream                */
+  double caps_ms, elem_ms, select_ms, mb_ms;  /* device time in k_res_caps / k_res_elem / the Pearson quantile select +    */
+                            /* clip / the Mb.all block (k_fast_mb or transpose), summed over the blocks                    */
+  long long elements;       /* reported rows x cells                                                                       */
+  long long launches;       /* kernels launched by the call                                                                */
+  long long clipped_lo, clipped_hi;  /* reserved                                                                           */
+} ruvnb_res_stats;
+/* cells [cell_begin, cell_end) only (cell_begin a multiple of block_size, cell_end = -1: all): `out` then starts at cell_begin.
+ * stats may be NULL. */
+int ruvnb_get_res_ex(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, int out_kind, void* out,
+                     int64_t cell_begin, int64_t cell_end, ruvnb_res_stats* stats);
+/* fastruvIII.nb's tail as ONE pass per block (R/fastruvIIInb.R:719-748 + makeSCE(assays = 'logPAC') -> get.res(type = 'quantile'),
+ * R/fastruvIIInb.R:790, R/makeSCE.R:36-38): the block of Mb.all is computed on the device (as ruvnb_fast_Mb_all does), feeds the
+ * caps and the PAC of the same block and is dropped -- the 8 bytes per element of Mb.all never cross PCIe (240 GB at 30k x 1M).
+ * Mb_all_out (G x N doubles, column-major) may be NULL; type as ruvnb_get_res (normally RUVNB_RES_QUANTILE). */
+int ruvnb_fast_res(ruvnb_ctx* ctx, int type, double lambda_b, const int32_t* annot_grp, int64_t block_size, int out_kind, void* out,
+                   double* Mb_all_out, int64_t cell_begin, int64_t cell_end, ruvnb_res_stats* stats);
 
 #ifdef __cplusplus
 }

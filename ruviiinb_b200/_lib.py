@@ -24,6 +24,8 @@ SYMBOLS = [
     "ruvnb_restore_best", "ruvnb_halve_steps", "ruvnb_accept", "ruvnb_disp_apl_grid", "ruvnb_estimate_disp", "ruvnb_estimate_disp_ex",
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
     "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
+    "ruvnb_set_cell_shard", "ruvnb_set_row_mask", "ruvnb_upload_counts_rows", "ruvnb_upload_counts_done", "ruvnb_get_cells",
+    "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res",
 ]
 
 
@@ -46,6 +48,18 @@ class FitStats(C.Structure):
                 ("disp_seconds", C.c_double), ("total_seconds", C.c_double), ("kernel_launches", C.c_longlong),
                 ("n_exact_mad_rows", C.c_int), ("n_exact_mad_cells", C.c_int)]
 
+
+class ResStats(C.Structure):
+    _fields_ = [("checksum", C.c_double), ("device_seconds", C.c_double), ("caps_ms", C.c_double), ("elem_ms", C.c_double),
+                ("select_ms", C.c_double), ("mb_ms", C.c_double), ("elements", C.c_longlong), ("launches", C.c_longlong),
+                ("clipped_lo", C.c_longlong), ("clipped_hi", C.c_longlong)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if not n.startswith("clipped")}
+
+
+OUT_F64, OUT_I32, OUT_LOG1P, OUT_NONE = 0, 1, 2, 3
+RES_KINDS = {"pearson": 1, "logcounts": 2, "quantile": 3}
 
 _lib = None
 
@@ -112,6 +126,17 @@ def load():
     lib.ruvnb_fast_iteration.argtypes = [vp, C.POINTER(Opts), dp, ip]
     lib.ruvnb_fast_halve_steps.argtypes = [vp, C.POINTER(Opts)]
     lib.ruvnb_fast_accept.argtypes = [vp]
+    lib.ruvnb_set_cell_shard.argtypes = [vp, C.c_int64, C.c_int64]
+    lib.ruvnb_set_row_mask.argtypes = [vp, vp]
+    lib.ruvnb_upload_counts_rows.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64]
+    lib.ruvnb_upload_counts_done.argtypes = [vp]
+    lib.ruvnb_get_cells.argtypes = [vp, vp, C.c_int64, vp]
+    lib.ruvnb_host_alloc.argtypes = [C.c_size_t]
+    lib.ruvnb_host_alloc.restype = vp
+    lib.ruvnb_host_free.argtypes = [vp]
+    lib.ruvnb_host_free.restype = None
+    lib.ruvnb_get_res_ex.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(ResStats)]
+    lib.ruvnb_fast_res.argtypes = [vp, C.c_int, C.c_double, vp, C.c_int64, C.c_int, vp, vp, C.c_int64, C.c_int64, C.POINTER(ResStats)]
     for s in SYMBOLS:
         f = getattr(lib, s)
         if f.restype is C.c_int and s not in ("ruvnb_abi_version",):
@@ -169,11 +194,12 @@ class Context:
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(uid))
         self._ck(self.lib.ruvnb_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
 
-    def set_design(self, G, N, grp, ctl, zeroinf=None, rows=None):
+    def set_design(self, G, N, grp, ctl, zeroinf=None, rows=None, m=None):
         grp = np.ascontiguousarray(grp, dtype=np.int32)
         ctl = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
         zi = None if zeroinf is None else np.ascontiguousarray(np.asarray(zeroinf).astype(np.uint8))
-        m = int(grp.max()) + 1 if grp.size else 0
+        if m is None:   # (a cell shard passes the group count of the whole problem)
+            m = int(grp.max()) + 1 if grp.size else 0
         g0, g1 = (0, G) if rows is None else rows
         self._ck(self.lib.ruvnb_set_design(self.h, G, N, m, _ptr(grp), _ptr(ctl), _ptr(zi), g0, g1))
         self.G, self.N, self.m, self.g0, self.g1 = G, N, m, g0, g1
@@ -315,6 +341,64 @@ class Context:
         mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
         self._ck(self.lib.ruvnb_get_res(self.h, int(kind), int(block_size), _ptr(mb), _ptr(out)))
         return out
+
+    # ---- cell shards, row mask, slab upload, sinks (include/ruvnb.h) -----------------------------------------------
+    def set_cell_shard(self, N_total, c0):
+        self._ck(self.lib.ruvnb_set_cell_shard(self.h, int(N_total), int(c0)))
+
+    def set_row_mask(self, alive):
+        """Rows reported by get_res_ex / fast_res; None restores all rows."""
+        a = None if alive is None else np.ascontiguousarray(np.asarray(alive).astype(np.uint8))
+        self._ck(self.lib.ruvnb_set_row_mask(self.h, _ptr(a)))
+        self.Gout = self.Gl if a is None else int(a.sum())
+
+    def upload_counts_rows(self, Y_rows, row0, device_ptr=None, nrows=None):
+        """One gene-major slab of rows [row0, row0 + nrows): a host int32 array, or a device pointer (`device_ptr`, `nrows`)."""
+        if device_ptr is not None:
+            self._ck(self.lib.ruvnb_upload_counts_rows(self.h, C.c_void_p(int(device_ptr)), 1, int(row0), int(nrows)))
+        else:
+            Y = np.ascontiguousarray(Y_rows, dtype=np.int32)
+            self._ck(self.lib.ruvnb_upload_counts_rows(self.h, _ptr(Y), 0, int(row0), Y.shape[0]))
+
+    def upload_counts_done(self):
+        self._ck(self.lib.ruvnb_upload_counts_done(self.h))
+
+    def get_cells(self, cells):
+        """Resident (winsorized) counts of the listed local cells: (Gl, n) int32."""
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        out = np.empty((self.Gl, cells.size), dtype=np.int32, order="F")
+        self._ck(self.lib.ruvnb_get_cells(self.h, _ptr(cells), cells.size, _ptr(out)))
+        return out
+
+    def _res_out(self, out_kind, ncells, out):
+        rows = getattr(self, "Gout", None) or self.Gl
+        if out_kind == OUT_NONE:
+            return None, rows
+        dt = np.int32 if out_kind == OUT_I32 else np.float64
+        if out is None:
+            out = np.empty((rows, ncells), dtype=dt, order="F")
+        assert out.dtype == dt and out.shape == (rows, ncells) and out.flags.f_contiguous
+        return out, rows
+
+    def get_res_ex(self, kind, block_size=5000, Mb_cells=None, out_kind=OUT_F64, cells=None, out=None):
+        """`ruvnb_get_res_ex`: returns (out or None, stats dict).  cells = (begin, end) restricts the pass to whole blocks."""
+        cb, ce = (0, self.N) if cells is None else cells
+        out, _ = self._res_out(out_kind, ce - cb, out)
+        mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
+        st = ResStats()
+        self._ck(self.lib.ruvnb_get_res_ex(self.h, int(kind), int(block_size), _ptr(mb), int(out_kind), _ptr(out), int(cb), int(ce), C.byref(st)))
+        return out, st.as_dict()
+
+    def fast_res(self, kind, annot_grp, lambda_b=16.0, block_size=5000, out_kind=OUT_F64, cells=None, out=None, want_Mb_all=False):
+        """`ruvnb_fast_res`: Mb.all block -> caps -> residual of the same block on the device.  Returns (out, Mb_all or None, stats)."""
+        cb, ce = (0, self.N) if cells is None else cells
+        out, _ = self._res_out(out_kind, ce - cb, out)
+        ag = np.ascontiguousarray(annot_grp, dtype=np.int32)
+        mball = np.empty((self.Gl, ce - cb), dtype=np.float64, order="F") if want_Mb_all else None
+        st = ResStats()
+        self._ck(self.lib.ruvnb_fast_res(self.h, int(kind), float(lambda_b), _ptr(ag), int(block_size), int(out_kind), _ptr(out), _ptr(mball),
+                                         int(cb), int(ce), C.byref(st)))
+        return out, mball, st.as_dict()
 
     # ---- fastruvIII.nb subsample fit (F3/F4) ------------------------------------------------------
     def fast_init(self, opts, U0):

@@ -121,11 +121,16 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
     return out
 
 
-def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_size=5000, device=0):
+def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_size=5000, device=0, ranks=None, N_total=None, c0=0,
+            sink="f64", return_stats=False):
     """`get.res` (R/get.res.R:12-129).  `type`: like the reference, every requested kind is evaluated in the order
     pearson, logcounts, quantile and the LAST one is returned (:49,68,75), so the default returns the percentile-adjusted
     counts.  out["Mb"] may be G x N (fastruvIII.nb's Mb.all) or G x m (a ruvIII.nb fit: expanded by replicate group --
-    the reference indexes Mb by cell, :35, and would need the caller to expand it)."""
+    the reference indexes Mb by cell, :35, and would need the caller to expand it).
+
+    Cell shards (`ranks`, `N_total`, `c0` as in `fastruvIII_nb`): blocks are independent (:27-126) except for colMeans(W)
+    (:36), which the library sums over the ranks; `out` then holds this rank's cells.  sink: "f64" (the reference's doubles),
+    "i32" (PAC as int32), "log1p" (log(PAC + 1)), "none" (checksum only; with return_stats)."""
     kinds = [type] if isinstance(type, str) else list(type)
     for t in kinds:
         if t not in ("pearson", "logcounts", "quantile"):
@@ -135,23 +140,33 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
         raise NotImplementedError("get.res for zero-inflated fits (ZIM::pzinb / qzinb branch, R/get.res.R:84-105)")
     if np.ndim(out["psi"]) != 1:
         raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
+    ranks = ranks or Ranks()
     Y = np.ascontiguousarray(out["counts"], dtype=np.int32)
     G, N = Y.shape
+    N_total = N if N_total is None else int(N_total)
     M = np.asarray(out["M"]).astype(bool)
     Mb = np.asarray(out["Mb"], dtype=np.float64)
     per_cell = Mb.shape[1] == N and Mb.shape[1] != M.shape[1]
     grp = np.argmax(M, axis=1).astype(np.int32) if (M.sum(axis=1) == 1).all() else np.zeros(N, dtype=np.int32)
-    m = int(grp.max()) + 1
+    m = max(int(g.max()) for g in ranks.allgather(grp)) + 1
+    kind = {"f64": _lib.OUT_F64, "i32": _lib.OUT_I32, "log1p": _lib.OUT_LOG1P, "none": _lib.OUT_NONE}[sink]
     with _lib.Context(device) as ctx:
-        ctx.set_design(G, N, grp, np.asarray(out["ctl"], bool))
+        if ranks.world > 1:
+            ctx.comm_init(ranks.unique_id(), ranks.rank, ranks.world)
+        ctx.set_design(G, N, grp, np.asarray(out["ctl"], bool), m=m)
+        if ranks.world > 1 or N_total != N:
+            ctx.set_cell_shard(N_total, c0)
         ctx.upload_counts(Y)
         ctx.set_state("W", out["W"])
         ctx.set_state("alpha", out["a"])
         ctx.set_state("gmean", out["gmean"])
         ctx.set_state("psi", out["psi"])
-        ctx.set_state("Mb", np.zeros((G, m)) if per_cell else Mb)
-        return ctx.get_res({"pearson": 1, "logcounts": 2, "quantile": 3}[last], block_size=block_size,
-                           Mb_cells=Mb if per_cell else None)
+        Mbg = np.zeros((G, m))
+        if not per_cell:
+            Mbg[:, :Mb.shape[1]] = Mb
+        ctx.set_state("Mb", Mbg)
+        res, st = ctx.get_res_ex(_lib.RES_KINDS[last], block_size=block_size, Mb_cells=Mb if per_cell else None, out_kind=kind)
+    return (res, st) if return_stats else res
 
 
 def makeSCE(obj, cData=None, batch=None, assays=("pearson", "logPAC")):
@@ -356,37 +371,125 @@ def fastruvIII_nb_subfit(Ysub, Msub, ctl, k=2, lambda_a=0.01, lambda_b=16, step_
                 "logl": np.array(logl_outer), "psi_idx": psi_idx}
 
 
+class Ranks:
+    """How the ranks of a cell-sharded run talk on the host side (small objects only: labels, the <= 3000 subsampled columns).
+    `dist` is torch.distributed (any backend) or None for a single process; the bulk collectives (histograms, W column sums,
+    the W-sweep criterion) run inside the library over NCCL (`ruvnb_set_cell_shard`)."""
+
+    def __init__(self, dist=None, device=None):
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.device = device
+
+    def allgather(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def unique_id(self):
+        from . import shard
+        return shard.broadcast_unique_id(self.dist, _lib.load(), device=self.device)
+
+
+def cell_shard_range(N_total, world, rank, block_size):
+    """Cells [c0, c1) of rank `rank`: whole blocks of `block_size` cells (blocks are the unit of independence of get.res and of
+    the fastruvIII.nb passes, R/get.res.R:27-126, R/fastruvIIInb.R:639-689,727-738), as evenly as the block count allows."""
+    nb = -(-N_total // block_size)
+    per = -(-nb // world)
+    return min(N_total, rank * per * block_size), min(N_total, (rank + 1) * per * block_size)
+
+
 def fastruvIII_nb(Y, M, ctl, k=2, lambda_a=0.01, lambda_b=16, step_fac=0.5, inner_maxit=50, outer_maxit=25, pCells_touse=0.2,
-                  block_size=5000, subsamples=None, U0=None, psi_idx=None, device=0, seed=0):
-    """`fastruvIII.nb` (R/fastruvIIInb.R:29-792), nbatch == 1, no pseudo-cells: stratified subsample of the annotated
-    cells (<= 3000, :118-137; NumPy RNG unless `subsamples` is given), the subsample fit, then W for all cells, Mb.all and
-    the psi cap.  Returns the reference's `out` list as a dict (the SCE packaging is makeSCE)."""
-    Y = np.ascontiguousarray(Y, dtype=np.int32)
+                  block_size=5000, subsamples=None, U0=None, psi_idx=None, device=0, seed=0, ranks=None, N_total=None, c0=0,
+                  assay="logPAC", return_Mb_all=True, pinned_out=None):
+    """`fastruvIII.nb` (R/fastruvIIInb.R:29-792), nbatch == 1, no pseudo-cells: Winsorize (:81-95), stratified subsample of the
+    annotated cells (<= 3000, :118-137; NumPy RNG unless `subsamples` is given), the subsample fit (:223-623), W for all cells
+    (:632-716), Mb.all + the percentile-adjusted counts of `makeSCE(assays = 'logPAC')` in one pass per block (:719-748,790),
+    the psi cap (:765-770).  The count matrix is uploaded ONCE and never comes back: the subsample's columns are gathered on
+    the device.
+
+    Cell shards: with `ranks` (a `Ranks` over torch.distributed), Y / M are THIS rank's cells [c0, c0 + N) of N_total (c0 on
+    a block boundary: `cell_shard_range`); `subsamples` are global cell indices.  Per-cell outputs (W, Mb, the assay) are the
+    rank's own cells; per-gene outputs are identical on every rank.
+    Returns the reference's `out` list as a dict plus the assay ("logPAC": log(PAC + 1) doubles, "PAC": int32, None)."""
+    ranks = ranks or Ranks()
+    Y = np.asarray(Y)
     M = np.asarray(M).astype(bool)
+    G, N = Y.shape
+    N_total = N if N_total is None else int(N_total)
+    ctl = np.asarray(ctl, bool)
     annotated = M.sum(axis=1) > 0
-    if annotated.mean() < 0.01:
-        raise ValueError("Less than 1% of cells have replicate annotation")
-    if (M.sum(axis=0) == 0).any():
-        raise ValueError("Each column of M matrix must have at least one non-zero entry")
+    grp_local = np.where(annotated, np.argmax(M, axis=1), -1).astype(np.int32)
+    annot_all = np.concatenate(ranks.allgather(grp_local))             # replicate group of every cell of the problem, -1 = none
+    if annot_all.size != N_total:
+        raise ValueError("the ranks' cells do not add up to N_total")
+    if (annot_all >= 0).mean() < 0.01:
+        raise ValueError("Less than 1% of cells have replicate annotation")                 # :53
+    m = M.shape[1]
+    if (np.bincount(annot_all[annot_all >= 0], minlength=m) == 0).any():
+        raise ValueError("Each column of M matrix must have at least one non-zero entry")   # :60
     rng = np.random.default_rng(seed)
-    if subsamples is None:
-        p = min(pCells_touse, 3000.0 / annotated.sum())                                      # :118-123
-        subsamples = np.sort(np.concatenate([rng.choice(np.where(M[:, j])[0], size=int(np.ceil(p * M[:, j].sum())), replace=False)
-                                             for j in range(M.shape[1])]))
-    subsamples = np.asarray(subsamples)
-    with _lib.Context(device) as ctx:                      # Winsorize on the full data (:81-95), then slice the subsample
-        ctx.set_design(Y.shape[0], Y.shape[1], np.where(annotated, np.argmax(M, axis=1), 0).astype(np.int32), np.asarray(ctl, bool))
-        ctx.upload_counts(Y)
-        ctx.winsorize()
-        Yw = ctx.get_counts()
-    keep = (Yw > 0).sum(axis=1) > 0
-    Yw, ctlk = Yw[keep], np.asarray(ctl, bool)[keep]
-    sub = fastruvIII_nb_subfit(Yw[:, subsamples], M[subsamples], ctlk, k=k, lambda_a=lambda_a, lambda_b=lambda_b, step_fac=step_fac,
-                               inner_maxit=inner_maxit, outer_maxit=outer_maxit, U0=U0, psi_idx=psi_idx, device=device, seed=seed)
-    out = fastruvIII_nb_finish(Yw, M, ctlk, sub["alpha"], sub["gmean"], sub["psi"], sub["Mb"], sub["Wsub"], subsamples, sub["wt_ctl"],
-                               lambda_a=lambda_a, lambda_b=lambda_b, block_size=block_size, device=device)
-    out["logl"] = sub["logl"]
-    out["zero_genes"] = ~keep
+    if subsamples is None:                                                                   # :118-137 (same draw on every rank)
+        p = min(pCells_touse, 3000.0 / (annot_all >= 0).sum())
+        subsamples = np.sort(np.concatenate([rng.choice(np.where(annot_all == j)[0], size=int(np.ceil(p * (annot_all == j).sum())), replace=False)
+                                             for j in range(m)]))
+    subsamples = np.asarray(subsamples, dtype=np.int64)
+    with _lib.Context(device) as ctx:
+        if ranks.world > 1:
+            ctx.comm_init(ranks.unique_id(), ranks.rank, ranks.world)
+        ctx.set_design(G, N, np.where(annotated, grp_local, 0).astype(np.int32), ctl, m=m)
+        if ranks.world > 1 or N_total != N:
+            ctx.set_cell_shard(N_total, c0)
+        ctx.upload_counts(np.ascontiguousarray(Y, dtype=np.int32))
+        _, nz = ctx.winsorize()                                                              # :81-95, quantile over ALL cells
+        keep = nz > 0                                                                        # :97-101
+        if not keep.all():
+            ctx.set_row_mask(keep)
+        ctlk = ctl[keep]
+        # the subsample's columns leave the device (G x <= 3000 int32), every rank its own, and are put in subsample order
+        mine = (subsamples >= c0) & (subsamples < c0 + N)
+        cols = ctx.get_cells(subsamples[mine] - c0)
+        parts = ranks.allgather((np.where(mine)[0], cols))
+        Ysub = np.empty((G, subsamples.size), dtype=np.int32)
+        for idx, cc in parts:
+            Ysub[:, idx] = cc
+        Msub = np.zeros((subsamples.size, m), dtype=bool)
+        Msub[np.arange(subsamples.size), annot_all[subsamples]] = True
+        # the subsample fit is small (<= 3000 cells): every rank runs it on a second context and gets the same result
+        sub = fastruvIII_nb_subfit(Ysub[keep], Msub, ctlk, k=k, lambda_a=lambda_a, lambda_b=lambda_b, step_fac=step_fac,
+                                   inner_maxit=inner_maxit, outer_maxit=outer_maxit, U0=U0, psi_idx=psi_idx, device=device, seed=seed)
+        # full-data passes on the resident counts: rows the cap emptied stay resident with neutral parameters and are not reported
+        def full(x, fill=0.0):
+            out = np.full((G,) + x.shape[1:], fill)
+            out[keep] = x
+            return out
+        W_init = np.zeros((N, k))
+        W_init[subsamples[mine] - c0] = sub["Wsub"][mine]                                     # :635-636
+        med = np.median(sub["Wsub"], axis=0)
+        mad = 1.4826 * np.median(np.abs(sub["Wsub"] - med[None, :]), axis=0)                 # :653-654
+        wt_full = np.zeros(int(ctl.sum()))
+        wt_full[keep[ctl]] = sub["wt_ctl"]
+        ctx.set_state("W", W_init)
+        ctx.set_state("alpha", full(sub["alpha"]))
+        ctx.set_state("gmean", full(sub["gmean"]))
+        ctx.set_state("psi", full(sub["psi"], 1.0))
+        ctx.set_state("Mb", full(sub["Mb"]))
+        W, sweeps, crit = ctx.fast_W_all(W_init, wt_full, med, mad, lambda_a=lambda_a)       # :632-716
+        res = None
+        Mb_all = None
+        if assay is not None or return_Mb_all:
+            kind = {"logPAC": _lib.OUT_LOG1P, "PAC": _lib.OUT_I32, None: _lib.OUT_NONE}[assay]
+            res, Mb_all, st = ctx.fast_res(_lib.RES_KINDS["quantile"], grp_local, lambda_b=lambda_b, block_size=block_size,
+                                           out_kind=kind, out=pinned_out, want_Mb_all=return_Mb_all)   # :719-748 + makeSCE
+            if Mb_all is not None:
+                Mb_all = Mb_all[keep]
+        counts = ctx.get_counts()[keep] if return_Mb_all else None   # the `counts` element (small problems / tests only)
+    out = {"counts": counts, "W": W, "M": M, "ctl": ctlk, "logl": sub["logl"], "a": sub["alpha"], "Mb": Mb_all, "gmean": sub["gmean"],
+           "psi": _lib.fast_cap_psi(sub["psi"]), "L.a": lambda_a, "L.b": lambda_b, "subsamples": subsamples, "Wsub": sub["Wsub"],
+           "Mb.sub": sub["Mb"], "W_sweeps": sweeps, "zero_genes": ~keep, assay or "assay": res}
     return out
 
 

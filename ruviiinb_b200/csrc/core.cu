@@ -174,8 +174,9 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   }
   // every column of M must be non-empty (R/fastruvIIInb.R:60 stop(); ruvIII.nb's projection would
   // divide by zero, R/ruvIIInb.R:657-665)
-  for (int j = 0; j < m; ++j)
-    if (ctx->group_n[j] == 0) return ctx->fail(RUVNB_EARG, "set_design: replicate group %d has no cell", j);
+  // (a cell shard may hold no cell of some group: only the IRLS operators need every group, and check_ready refuses them)
+  ctx->empty_group = -1;
+  for (int j = 0; j < m; ++j) if (ctx->group_n[j] == 0 && ctx->empty_group < 0) ctx->empty_group = j;
   ctx->group_chunk0.assign(m, 0);
   int nch = 0;
   for (int j = 0; j < m; ++j) { ctx->group_chunk0[j] = nch; nch += (ctx->group_n[j] + CH - 1) / CH; }
@@ -363,19 +364,54 @@ int ruvnb_winsorize(ruvnb_ctx* ctx, double* cap_out, int64_t* nonzero_out) {
   if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "winsorize: no counts uploaded");
   CK(cudaSetDevice(ctx->device));
   const int Gl = ctx->Gl;
+  ScopedDev own;
   double* d_cap = nullptr; long long* d_nz = nullptr;
-  CK(cudaMalloc((void**)&d_cap, (size_t)Gl * 8));
-  CK(cudaMalloc((void**)&d_nz, (size_t)Gl * 8));
-  k_winsorize<<<Gl, WZ_NT, 0, ctx->stream>>>(ctx->dY, ctx->Np, ctx->N, 0.995, d_cap, d_nz);
-  CKL();
-  if (ctx->dYctl) {  // the replicated control-gene rows get the same treatment (same rows, same caps)
-    k_winsorize<<<ctx->n_ctl, WZ_NT, 0, ctx->stream>>>(ctx->dYctl, ctx->Np, ctx->N, 0.995, nullptr, nullptr);
+  CK(own.alloc(&d_cap, (size_t)Gl * 8));
+  CK(own.alloc(&d_nz, (size_t)Gl * 8));
+  if (ctx->cell_shard && (ctx->nranks > 1 || getenv("RUVNB_WZ_HIST"))) {   // (the variable: the same path on one rank, for tests)
+    // cells over the ranks: the quantile of a gene needs the counts of ALL its cells.  Per-gene histograms of the values
+    // 0..4094 (+ one overflow bin) are summed over the ranks; genes whose quantile falls into the overflow bin (counts in
+    // the thousands for > 0.5 % of the cells) repeat the step on the value's upper bits, then on the lower 12 of that bucket
+    unsigned* hist = nullptr; int* d_need = nullptr; unsigned *d_v[2] = {nullptr, nullptr}; long long* d_rank = nullptr;
+    CK(own.alloc(&hist, (size_t)Gl * WZ_BINS * 4)); CK(own.alloc(&d_need, 4)); CK(own.alloc(&d_v[0], (size_t)Gl * 4)); CK(own.alloc(&d_v[1], (size_t)Gl * 4));
+    CK(own.alloc(&d_rank, (size_t)Gl * 8));
+    const long long n = ctx->N_total;
+    CK(cudaMemsetAsync(hist, 0, (size_t)Gl * WZ_BINS * 4, ctx->stream));
+    k_wz_hist<<<Gl, WZ_NT, 0, ctx->stream>>>(ctx->dY, ctx->Np, 0, WZ_BINS, 0u, nullptr, d_cap, 1, hist); CKL();
+    RET(allreduce(ctx, hist, (size_t)Gl * WZ_BINS, NCCL_INT32));
+    CK(cudaMemsetAsync(d_need, 0, 4, ctx->stream));
+    k_wz_pick_direct<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, n, 0.995, hist, d_cap, d_need); CKL();
+    CK(cudaMemcpyAsync(ctx->h_flags + 7, d_need, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_flags[7] > 0) {   // the same on every rank: the histograms are global
+      const int shifts[3] = {20, 8, 0}, bits[3] = {12, 12, 8};
+      for (int which = 0; which < 2; ++which) {
+        k_wz_desc_init<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, n, 0.995, which, d_cap, d_v[which], d_rank); CKL();
+        unsigned pmask = 0;
+        for (int lv = 0; lv < 3; ++lv) {
+          const int nb = 1 << bits[lv];
+          CK(cudaMemsetAsync(hist, 0, (size_t)Gl * WZ_BINS * 4, ctx->stream));
+          k_wz_hist<<<Gl, WZ_NT, 0, ctx->stream>>>(ctx->dY, ctx->Np, shifts[lv], nb, pmask, d_v[which], d_cap, 0, hist); CKL();
+          RET(allreduce(ctx, hist, (size_t)Gl * WZ_BINS, NCCL_INT32));
+          k_wz_desc_pick<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, hist, shifts[lv], nb, d_cap, d_v[which], d_rank); CKL();
+          pmask |= (unsigned)(nb - 1) << shifts[lv];
+        }
+      }
+      k_wz_desc_finish<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, n, 0.995, d_v[0], d_v[1], d_cap); CKL();
+    }
+    k_wz_apply<<<Gl, WZ_NT, 0, ctx->stream>>>(ctx->dY, ctx->Np, d_cap, d_nz); CKL();
+    RET(allreduce(ctx, d_nz, Gl, NCCL_INT64));
+  } else {
+    k_winsorize<<<Gl, WZ_NT, 0, ctx->stream>>>(ctx->dY, ctx->Np, ctx->N, 0.995, d_cap, d_nz);
     CKL();
+    if (ctx->dYctl) {  // the replicated control-gene rows get the same treatment (same rows, same caps)
+      k_winsorize<<<ctx->n_ctl, WZ_NT, 0, ctx->stream>>>(ctx->dYctl, ctx->Np, ctx->N, 0.995, nullptr, nullptr);
+      CKL();
+    }
   }
   if (cap_out) CK(cudaMemcpyAsync(cap_out, d_cap, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (nonzero_out) CK(cudaMemcpyAsync(nonzero_out, d_nz, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaFree(d_cap)); CK(cudaFree(d_nz));
   ctx->cur.sig_valid = false; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
@@ -401,6 +437,88 @@ int ruvnb_get_counts(ruvnb_ctx* ctx, int32_t* Y_out) {
   CK(cudaFree(stage));
   return RUVNB_OK;
 }
+
+// ---- cell shards, row mask, slab upload, cell gather (include/ruvnb.h) ---------------------------------------------------
+int ruvnb_set_cell_shard(ruvnb_ctx* ctx, int64_t N_total, int64_t c0) {
+  if (!ctx) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "set_cell_shard: call ruvnb_set_design first");
+  if (ctx->Gl != ctx->G) return ctx->fail(RUVNB_EARG, "set_cell_shard: a cell shard holds ALL genes (set_design rows [0, G))");
+  if (N_total < ctx->N || c0 < 0 || c0 + ctx->N > N_total) return ctx->fail(RUVNB_EARG, "set_cell_shard: cells [%lld, %lld) outside 0..%lld", (long long)c0, (long long)(c0 + ctx->N), (long long)N_total);
+  ctx->cell_shard = true; ctx->N_total = N_total; ctx->cell0 = c0;
+  return RUVNB_OK;
+}
+
+int ruvnb_set_row_mask(ruvnb_ctx* ctx, const uint8_t* alive) {
+  if (!ctx) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "set_row_mask: call ruvnb_set_design first");
+  CK(cudaSetDevice(ctx->device));
+  if (!alive) { ctx->d_orow = nullptr; ctx->Gout = ctx->Gl; return RUVNB_OK; }   // the buffer stays in ctx->allocs
+  std::vector<int> orow(ctx->Gl);
+  int n = 0;
+  for (int g = 0; g < ctx->Gl; ++g) orow[g] = alive[g] ? n++ : -1;
+  if (n == 0) return ctx->fail(RUVNB_EARG, "set_row_mask: no row left");
+  int* d = nullptr;
+  RET(dev_upload(ctx, &d, orow));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->d_orow = d; ctx->Gout = n;
+  return RUVNB_OK;
+}
+
+int ruvnb_upload_counts_rows(ruvnb_ctx* ctx, const int32_t* Y_rows, int on_device, int64_t row0, int64_t nrows) {
+  if (!ctx || !Y_rows) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "upload_counts_rows: call ruvnb_set_design first");
+  if (row0 < 0 || nrows <= 0 || row0 + nrows > ctx->Gl) return ctx->fail(RUVNB_EARG, "upload_counts_rows: rows [%lld, %lld) outside the %d local rows", (long long)row0, (long long)(row0 + nrows), ctx->Gl);
+  if (ctx->Gl != ctx->G) return ctx->fail(RUVNB_EARG, "upload_counts_rows: gene shards take their control rows through ruvnb_upload_counts_dense");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->dY) RET(dev_alloc(ctx, &ctx->dY, (long long)ctx->Gl * ctx->Np));
+  if (on_device) {
+    k_permute_rows<<<nblk(nrows * ctx->Np, 256), 256, 0, ctx->stream>>>(Y_rows, nrows, ctx->N, ctx->N, 1, ctx->d_pos2cell, ctx->Np, ctx->dY + row0 * ctx->Np);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->stream));   // the caller may reuse its slab
+  } else {
+    RET(upload_rows(ctx, Y_rows, RUVNB_LAYOUT_GENE_MAJOR, nrows, nullptr, 0, nrows, ctx->dY + row0 * ctx->Np));
+  }
+  return RUVNB_OK;
+}
+int ruvnb_upload_counts_done(ruvnb_ctx* ctx) {
+  if (!ctx) return RUVNB_EARG;
+  if (!ctx->dY) return ctx->fail(RUVNB_ESTATE, "upload_counts_done: no slab uploaded");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<const int32_t*> rows(ctx->n_ctl);
+  for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dY + (long long)ctx->ctl_gene[i] * ctx->Np;
+  if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
+  CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
+  return RUVNB_OK;
+}
+
+int ruvnb_get_cells(ruvnb_ctx* ctx, const int64_t* cells, int64_t n, int32_t* out) {
+  if (!ctx || !cells || !out || n < 0) return RUVNB_EARG;
+  if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "get_cells: no counts uploaded");
+  if (n == 0) return RUVNB_OK;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<int> pos(n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (cells[i] < 0 || cells[i] >= ctx->N) return ctx->fail(RUVNB_EARG, "get_cells: cell %lld outside 0..%lld", (long long)cells[i], (long long)ctx->N - 1);
+    pos[i] = ctx->cell2pos[cells[i]];
+  }
+  ScopedDev own;
+  int* d_pos = nullptr; int32_t* d_out = nullptr;
+  CK(own.alloc(&d_pos, (size_t)n * 4)); CK(own.alloc(&d_out, (size_t)n * ctx->Gl * 4));
+  CK(cudaMemcpyAsync(d_pos, pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_gather_cells<<<dim3(nblk(ctx->Gl, 32), nblk(n, 32)), dim3(32, 8), 0, ctx->stream>>>(ctx->dY, ctx->Gl, ctx->Np, d_pos, n, d_out); CKL();
+  CK(cudaMemcpyAsync(out, d_out, (size_t)n * ctx->Gl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
+
+void* ruvnb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void ruvnb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"
 
@@ -601,6 +719,8 @@ int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "no counts uploaded");
   RET(ensure_state(ctx, o->k));
   if (!ctx->have_W) return ctx->fail(RUVNB_ESTATE, "W not set: the initial W (irlba in the reference, R/ruvIIInb.R:167) is injected with ruvnb_set_state(\"W\")");
+  if (ctx->empty_group >= 0) return ctx->fail(RUVNB_EARG, "set_design: replicate group %d has no cell", ctx->empty_group);
+  if (ctx->cell_shard && ctx->nranks > 1) return ctx->fail(RUVNB_ESTATE, "this context holds a CELL shard: the IRLS / dispersion operators shard by gene (ruvnb_set_design rows)");
   ctx->zinb_on = o->zinb && ctx->any_zeroinf;   // ZINB only matters for cells flagged zeroinf (:237,254)
   ctx->launch_parts = 1;                         // a failed call must not leave a sweep's part count behind
   CK(cudaSetDevice(ctx->device));

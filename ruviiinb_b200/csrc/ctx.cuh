@@ -77,6 +77,7 @@ struct ruvnb_ctx {
   long long G = 0, N = 0, g0 = 0, g1 = 0;
   int Gl = 0, m = 0, K = 0;
   bool have_design = false, have_counts = false;
+  int empty_group = -1;            // first replicate group without a cell (legal on a cell shard only), or -1
   std::vector<int> grp;
   std::vector<uint8_t> ctl, zeroinf;
   bool any_zeroinf = false;
@@ -163,6 +164,11 @@ struct ruvnb_ctx {
   // multi-GPU
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // cell shard (fastruvIII.nb full-data passes, get.res at 10^6 cells): this context holds cells [cell0, cell0 + N) of
+  // N_total and ALL genes; what crosses ranks is summed over the communicator (ruvnb_set_cell_shard)
+  bool cell_shard = false;
+  long long N_total = 0, cell0 = 0;
+  uint8_t* d_row_alive = nullptr; int* d_orow = nullptr; int Gout = 0;   // rows reported by get.res / F6 (ruvnb_set_row_mask)
   bool even_shards = false;  // rank r holds rows [r per, min(G, (r+1) per)), per = ceil(G / nranks): slices can be all-gathered
   double* agather = nullptr; // [nranks][per K + 1] alpha slices + the rank's non-finite count (all-gather buffer)
   cudaEvent_t ev_ctl = nullptr;  // the control-gene parameter exchange on the side stream has finished
@@ -271,3 +277,5 @@ int check_ready(ruvnb_ctx* ctx, const ruvnb_opts* o);                 // core.cu
 int ensure_roworder(ruvnb_ctx* ctx);                                  // core.cu
 int ensure_ytabs(ruvnb_ctx* ctx, const double* psi);                  // core.cu
 int make_rmw(ruvnb_ctx* ctx, const double* W);                        // irls.cu
+struct FastMbPrep { double *d_rmed = nullptr, *d_rmad = nullptr; int* d_annot = nullptr; uint8_t* d_ctl = nullptr; };
+int fast_mb_prepare(ruvnb_ctx* ctx, const int32_t* annot_grp, ScopedDev* own, FastMbPrep* p);   // fast.cu

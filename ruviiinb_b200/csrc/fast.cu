@@ -24,7 +24,7 @@ int ruvnb_fast_W_all(ruvnb_ctx* ctx, int k, double lambda_a, const double* wt_ct
                      const double* W_mad, int max_sweeps, double tol, double* W_out, int* n_sweeps, double* crit_out) {
   if (!ctx || !wt_ctl || !W_init || !W_med || !W_mad) return RUVNB_EARG;
   if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "fast_W_all: no counts uploaded");
-  if (ctx->nranks > 1) return ctx->fail(RUVNB_ESTATE, "fast_W_all: single-GPU only in this build (cells are independent: shard N across contexts)");
+  if (ctx->nranks > 1 && !ctx->cell_shard) return ctx->fail(RUVNB_ESTATE, "fast_W_all: cells are independent -- shard them (ruvnb_set_cell_shard), not the genes");
   RET(ensure_state(ctx, k));
   CK(cudaSetDevice(ctx->device));
   RET(ruvnb_set_state(ctx, "W", W_init, k));
@@ -32,8 +32,9 @@ int ruvnb_fast_W_all(ruvnb_ctx* ctx, int k, double lambda_a, const double* wt_ct
   StateSet& s = ctx->cur;
   double *d_gm = nullptr, *d_al = nullptr, *d_wt = nullptr, *d_A = nullptr, *d_med = nullptr, *d_mad = nullptr, *d_crit = nullptr;
   const unsigned grid = nblk(ctx->Np, 64);
-  CK(cudaMalloc((void**)&d_gm, (size_t)nc * 8)); CK(cudaMalloc((void**)&d_al, (size_t)nc * K * 8)); CK(cudaMalloc((void**)&d_wt, (size_t)nc * 8));
-  CK(cudaMalloc((void**)&d_A, KK * 8)); CK(cudaMalloc((void**)&d_med, K * 8)); CK(cudaMalloc((void**)&d_mad, K * 8)); CK(cudaMalloc((void**)&d_crit, (size_t)grid * 8));
+  ScopedDev own;   // released on every way out
+  CK(own.alloc(&d_gm, (size_t)nc * 8)); CK(own.alloc(&d_al, (size_t)nc * K * 8)); CK(own.alloc(&d_wt, (size_t)nc * 8));
+  CK(own.alloc(&d_A, KK * 8)); CK(own.alloc(&d_med, K * 8)); CK(own.alloc(&d_mad, K * 8)); CK(own.alloc(&d_crit, (size_t)grid * 8));
   k_gather_rows<<<nblk(nc, 256), 256, 0, ctx->stream>>>(s.gmean, ctx->d_ctl_local, nc, 1, d_gm); CKL();
   k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(s.alpha, ctx->d_ctl_local, nc, K, d_al); CKL();
   CK(cudaMemcpyAsync(d_wt, wt_ctl, (size_t)nc * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -55,28 +56,42 @@ int ruvnb_fast_W_all(ruvnb_ctx* ctx, int k, double lambda_a, const double* wt_ct
     CK(cudaStreamSynchronize(ctx->stream));
     double t = 0.0;
     for (double v : part) t += v;
-    crit = t / ((double)ctx->N * K);                       // mean over all N x k entries (:709)
+    double n_all = (double)ctx->N;
+    if (ctx->cell_shard && ctx->nranks > 1) {              // the criterion is a mean over the cells of ALL ranks
+      CK(cudaMemcpyAsync(ctx->scal, &t, 8, cudaMemcpyHostToDevice, ctx->stream));
+      RET(allreduce(ctx, ctx->scal, 1, NCCL_F64));
+      CK(cudaMemcpyAsync(&t, ctx->scal, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      n_all = (double)ctx->N_total;
+    }
+    crit = t / (n_all * K);                                // mean over all N x k entries (:709)
     if (it >= 1 && crit < tol) break;                      // the initial pass has no convergence test
   }
   s.sig_valid = false;
   if (n_sweeps) *n_sweeps = sweeps;
   if (crit_out) *crit_out = crit;
-  CK(cudaFree(d_gm)); CK(cudaFree(d_al)); CK(cudaFree(d_wt)); CK(cudaFree(d_A)); CK(cudaFree(d_med)); CK(cudaFree(d_mad)); CK(cudaFree(d_crit));
   if (W_out) RET(ruvnb_get_state(ctx, "W", W_out));
   return RUVNB_OK;
 }
 
-// F6: Mb.all (G x N, column-major, streamed to the host in blocks of block_size cells).  annot_grp[c] = replicate group
-// of cell c or -1; the current state supplies alpha, gmean, psi, W and the subsample fit's Mb (G x m).
-int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp, int64_t block_size, double* Mb_all_out) {
-  if (!ctx || !annot_grp || !Mb_all_out) return RUVNB_EARG;
-  if (!ctx->have_counts || ctx->K == 0 || !ctx->have_W) return ctx->fail(RUVNB_ESTATE, "fast_Mb_all: needs counts and a state (W, alpha, gmean, Mb, psi)");
-  CK(cudaSetDevice(ctx->device));
+}  // extern "C"
+
+// what F6 needs besides the state: annotation of every local cell, control flags, and the per-gene clamp limits
+// median +- 4 mad of Mb.all over the ANNOTATED columns (R/fastruvIIInb.R:744-745) = of the values Mb[g, j] with multiplicity
+// #annotated cells of group j (summed over the ranks of a cell-sharded problem).  Buffers land in `own` (freed by its scope).
+int fast_mb_prepare(ruvnb_ctx* ctx, const int32_t* annot_grp, ScopedDev* own, FastMbPrep* p) {
   const int Gl = ctx->Gl, m = ctx->m; const long long N = ctx->N;
   StateSet& s = ctx->cur;
-  // row median / mad over the annotated columns (:744-745): values Mb[g, j] with multiplicity = annotated cells of group j
   std::vector<long long> cnt(m, 0);
-  for (long long c = 0; c < N; ++c) { int j = annot_grp[c]; if (j >= m) return ctx->fail(RUVNB_EARG, "fast_Mb_all: group %d outside 0..%d", j, m - 1); if (j >= 0) cnt[j]++; }
+  for (long long c = 0; c < N; ++c) { int j = annot_grp[c]; if (j >= m) return ctx->fail(RUVNB_EARG, "fast Mb: group %d outside 0..%d", j, m - 1); if (j >= 0) cnt[j]++; }
+  if (ctx->cell_shard && ctx->nranks > 1) {
+    long long* d_cnt = nullptr;
+    CK(own->alloc(&d_cnt, (size_t)m * 8));
+    CK(cudaMemcpyAsync(d_cnt, cnt.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RET(allreduce(ctx, d_cnt, m, NCCL_INT64));
+    CK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
   std::vector<double> Mbh((size_t)Gl * m), rmed(Gl), rmad(Gl);
   CK(cudaMemcpyAsync(Mbh.data(), s.Mb, Mbh.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -89,24 +104,39 @@ int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp,
     for (int j = 0; j < m; ++j) vc[j].first = fabs(vc[j].first - med);
     rmed[g] = med; rmad[g] = 1.4826 * weighted_median_h(vc);
   }
+  CK(own->alloc(&p->d_rmed, (size_t)Gl * 8)); CK(own->alloc(&p->d_rmad, (size_t)Gl * 8)); CK(own->alloc(&p->d_annot, (size_t)N * 4)); CK(own->alloc(&p->d_ctl, (size_t)Gl));
+  CK(cudaMemcpyAsync(p->d_rmed, rmed.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->d_rmad, rmad.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->d_annot, annot_grp, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(p->d_ctl, ctl_local.data(), Gl, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // the host vectors go out of scope
+  return RUVNB_OK;
+}
+
+extern "C" {
+
+// F6: Mb.all (G x N, column-major, streamed to the host in blocks of block_size cells).  annot_grp[c] = replicate group
+// of cell c or -1; the current state supplies alpha, gmean, psi, W and the subsample fit's Mb (G x m).
+int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp, int64_t block_size, double* Mb_all_out) {
+  if (!ctx || !annot_grp || !Mb_all_out) return RUVNB_EARG;
+  if (!ctx->have_counts || ctx->K == 0 || !ctx->have_W) return ctx->fail(RUVNB_ESTATE, "fast_Mb_all: needs counts and a state (W, alpha, gmean, Mb, psi)");
+  CK(cudaSetDevice(ctx->device));
+  const int Gl = ctx->Gl, m = ctx->m; const long long N = ctx->N;
+  StateSet& s = ctx->cur;
+  ScopedDev own; FastMbPrep pr;
+  RET(fast_mb_prepare(ctx, annot_grp, &own, &pr));
   long long bs = std::min<long long>(block_size > 0 ? block_size : 5000, N);
-  double *d_rmed = nullptr, *d_rmad = nullptr, *slab[2] = {nullptr, nullptr}; int* d_annot = nullptr; uint8_t* d_ctl = nullptr;
+  double* slab[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr; cudaEvent_t done[2], copied[2];
-  CK(cudaMalloc((void**)&d_rmed, (size_t)Gl * 8)); CK(cudaMalloc((void**)&d_rmad, (size_t)Gl * 8)); CK(cudaMalloc((void**)&d_annot, (size_t)N * 4));
-  CK(cudaMalloc((void**)&d_ctl, Gl));
-  for (int i = 0; i < 2; ++i) { CK(cudaMalloc((void**)&slab[i], (size_t)Gl * bs * 8)); CK(cudaEventCreate(&done[i])); CK(cudaEventCreate(&copied[i])); }
+  for (int i = 0; i < 2; ++i) { CK(own.alloc(&slab[i], (size_t)Gl * bs * 8)); CK(cudaEventCreate(&done[i])); CK(cudaEventCreate(&copied[i])); }
   CK(cudaStreamCreate(&copy_stream));
-  CK(cudaMemcpyAsync(d_rmed, rmed.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_rmad, rmad.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_annot, annot_grp, (size_t)N * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ctl, ctl_local.data(), Gl, cudaMemcpyHostToDevice, ctx->stream));
   int blk = 0;
   for (long long c0 = 0; c0 < N; c0 += bs, ++blk) {
     const int B = (int)std::min<long long>(bs, N - c0), sl = blk & 1;
     if (blk >= 2) CK(cudaStreamWaitEvent(ctx->stream, copied[sl], 0));
     FastMbArgs a;
     a.Gl = Gl; a.K = ctx->K; a.m = m; a.B = B; a.Np = ctx->Np; a.c0 = c0; a.Yp = ctx->dY; a.alpha = s.alpha; a.gmean = s.gmean; a.psi = s.psi;
-    a.W = s.W; a.Mb = s.Mb; a.cell2pos = ctx->d_cell2pos; a.annot = d_annot; a.ctl_local = d_ctl; a.rmed = d_rmed; a.rmad = d_rmad; a.lambda_b = lambda_b;
+    a.W = s.W; a.Mb = s.Mb; a.cell2pos = ctx->d_cell2pos; a.annot = pr.d_annot; a.ctl_local = pr.d_ctl; a.rmed = pr.d_rmed; a.rmad = pr.d_rmad; a.lambda_b = lambda_b; a.gene_major = 0; a.ldB = 0;
     k_fast_mb<<<dim3(nblk(Gl, 32), nblk(B, 32)), 1024, 0, ctx->stream>>>(a, slab[sl]); CKL();
     CK(cudaEventRecord(done[sl], ctx->stream));
     CK(cudaStreamWaitEvent(copy_stream, done[sl], 0));
@@ -115,8 +145,7 @@ int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp,
   }
   CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(copy_stream));
   CK(cudaStreamDestroy(copy_stream));
-  for (int i = 0; i < 2; ++i) { CK(cudaFree(slab[i])); CK(cudaEventDestroy(done[i])); CK(cudaEventDestroy(copied[i])); }
-  CK(cudaFree(d_rmed)); CK(cudaFree(d_rmad)); CK(cudaFree(d_annot)); CK(cudaFree(d_ctl));
+  for (int i = 0; i < 2; ++i) { CK(cudaEventDestroy(done[i])); CK(cudaEventDestroy(copied[i])); }
   return RUVNB_OK;
 }
 

@@ -101,6 +101,7 @@ struct FastMbArgs {
   const uint8_t* ctl_local;                     // [Gl]
   const double *rmed, *rmad;                    // [Gl] row median / mad of the annotated columns
   double lambda_b;
+  int gene_major, ldB;                          // output [Gl][ldB] instead of the R-layout slab [B][Gl]
 };
 static __global__ void __launch_bounds__(1024) k_fast_mb(FastMbArgs a, double* slab) {
   __shared__ double tile[32][33];
@@ -129,6 +130,10 @@ static __global__ void __launch_bounds__(1024) k_fast_mb(FastMbArgs a, double* s
     const double hi = a.rmed[g] + 4.0 * a.rmad[g], lo = a.rmed[g] - 4.0 * a.rmad[g];   // clamp every row (:744-748)
     if (v > hi) v = hi;
     if (v < lo) v = lo;
+  }
+  if (a.gene_major) {   // the block stays on the device for get.res: [Gl][ldB], coalesced along the cells
+    if (g < a.Gl && c < a.B) slab[(long long)g * a.ldB + c] = v;
+    return;
   }
   tile[warp][lane] = v;
   __syncthreads();

@@ -449,6 +449,7 @@ static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
   CK(cudaMemcpyAsync(dst.psi_w, src.psi_w, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.wtctl, src.wtctl, (size_t)ctx->n_ctl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active; dst.nfail = src.nfail;
+  if (ctx->faillist_for == dst.sigma) ctx->faillist_for = nullptr;   // the list was made from what this buffer held before
   dst.p1_valid = false;   // the Gram / score sums in ctx->A.. belong to one parameter set (and one step vector) only
   return RUVNB_OK;
 }

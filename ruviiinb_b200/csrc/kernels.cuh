@@ -57,6 +57,8 @@ struct RowShared {
   double tl[NWARP][YT];     // this warp's row: lgamma table
   double tr[NWARP][YT];     // this warp's row: log(y + r)
   double al[NWARP][8];      // this warp's row: alpha_g (kept out of the register file)
+  int ybuf[NWARP][2][CH];   // this warp's row: the counts of the current and the next chunk (cp.async ring, 512 B per slot)
+  int meta[2][4];           // (group << 8) | valid cells of the chunks of the current / next tile
   const double* wsets[2];
 };
 
@@ -64,8 +66,10 @@ struct RowShared {
 // row-streaming skeleton
 // ------------------------------------------------------------------------------------------------
 template <int K, int NSETS, int NW = NWARP>
-__device__ __forceinline__ void stage_tile(double* dst, const double* const* wsets, long long Np, int tile, int tid) {
+__device__ __forceinline__ void stage_tile(double* dst, const double* const* wsets, long long Np, int tile, int tid, int* meta_dst,
+                                           const int* chunk_meta) {
   constexpr int CELLS = TileCfg<K>::CELLS;
+  if (tid == 0) __pipeline_memcpy_async(meta_dst, chunk_meta + tile * TileCfg<K>::SC, TileCfg<K>::SC * 4);
   constexpr int UNITS_PER_ROW = CELLS / 2;  // 16-byte units
   constexpr int UNITS = NSETS * K * UNITS_PER_ROW;
   for (int u = tid; u < UNITS; u += NW * 32) {
@@ -177,32 +181,35 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   op.g.zinf = geo.zinf;
   __syncthreads();
   if (active) op.row_begin(row, slot);
-  const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
   const int ntiles_all = geo.nchunks / SC;
   const int tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;           // tiles per part
   const int t0 = min(ntiles_all, part * tpp), ntiles = min(ntiles_all, t0 + tpp);
   int curj = -1;
-  // the counts of the next chunk are fetched one chunk ahead (HBM latency hides behind ~4 elements of math)
-  int2 ya = make_int2(0, 0), yb = ya;
-  int meta = 0;   // (group << 8) | valid cells of the next chunk, fetched with its counts
-  if (active && t0 < ntiles) { ya = yrow2[t0 * SC * (CH / 2) + lane]; yb = yrow2[t0 * SC * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[t0 * SC]; }
-  if (t0 < ntiles) stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, t0, tid);
+  // The counts travel HBM -> shared memory with cp.async, one 128-cell chunk (16 B per lane) ahead of the arithmetic: no
+  // register holds a load in flight (with ~128 live registers ptxas spilled the prefetched values, i.e. waited for them at
+  // once).  A lane reads its four cells {2l, 2l+1, 64+2l, 65+2l} back with two conflict-free 8-byte loads.
+  const int* yrow = geo.Yp + (long long)row * geo.Np;
+  int* yring = &sh->ybuf[warp][0][0];
+  const int c_end = ntiles * SC;
+  if (t0 < ntiles) {
+    if (active) __pipeline_memcpy_async(yring + ((t0 * SC) & 1) * CH + 4 * lane, yrow + (long long)t0 * SC * CH + 4 * lane, 16);
+    stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, t0, tid, sh->meta[0], geo.chunk_meta);
+  }
   for (int t = t0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) {
-      stage_tile<K, NSETS, NW>(smem + ((t + 1 - t0) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid);
-      __pipeline_wait_prior(1);
-    } else {
-      __pipeline_wait_prior(0);
-    }
-    __syncthreads();
+    __pipeline_wait_prior(0);
+    __syncthreads();           // tile t, its chunk meta and the counts of its first chunk are in shared memory
+    if (t + 1 < ntiles) stage_tile<K, NSETS, NW>(smem + ((t + 1 - t0) & 1) * TILE, sh->wsets, geo.Np, t + 1, tid, sh->meta[(t + 1 - t0) & 1], geo.chunk_meta);
     if (active) {
       const double* tile = smem + ((t - t0) & 1) * TILE;
+      const int* mt_ = sh->meta[(t - t0) & 1];
 #pragma unroll 1
       for (int sc = 0; sc < SC; ++sc) {
         const int c = t * SC + sc;
-        const int2 y01 = ya, y23 = yb;
-        const int mcur = meta;
-        if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c + 1]; }
+        if (sc > 0) { __pipeline_wait_prior(0); __syncwarp(); }   // the counts of chunk c have landed (all lanes' pieces)
+        const int* yb = yring + (c & 1) * CH;
+        const int2 y01 = *reinterpret_cast<const int2*>(yb + 2 * lane), y23 = *reinterpret_cast<const int2*>(yb + 64 + 2 * lane);
+        if (c + 1 < c_end) { __pipeline_memcpy_async(yring + ((c + 1) & 1) * CH + 4 * lane, yrow + (long long)(c + 1) * CH + 4 * lane, 16); __pipeline_commit(); }
+        const int mcur = mt_[sc];
         const int nv = mcur & 0xff;
         if (nv == 0 && !Op::PADS) continue;
         const int j = mcur >> 8;
@@ -767,8 +774,8 @@ __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> 
 // sig.inv are exactly what get.coef2 needs one iteration later (:303-354) -- one read of Y, one dot product and one exp
 // per element instead of two.  The pass-1 half is speculative: it assumes (i) the step is accepted -- a rejected
 // candidate is thrown away with its sums -- and (ii) every Huber weight is 1; rows whose certificate fails in this very
-// sweep are redone by k_pass1<HUBER = true> once their exact sigma is known.  Per-element arithmetic and summation order
-// are those of OpLoglik and OpPass1, so the fused and the separate sweeps return the same bits.  NB only (no ZINB).
+// sweep are redone by k_pass1<HUBER = true> once their exact sigma is known.  The log-likelihood half keeps the arithmetic
+// and the summation order of OpLoglik (same bits as the separate sweep).  NB only (no ZINB).
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct OpLLPass1 {
@@ -832,41 +839,43 @@ struct OpLLPass1 {
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int y0, int y1, int c, int ti, const double* tile, bool m0, bool m1) {
-    const double* w = tile; const double* rw = tile + K * CELLS;
     double l0, l1;
-    g.lmu_pair(w, ti, l0, l1);
-    const double yd0 = (double)y0, yd1 = (double)y1;
-    double mu0, s0, q0, mu1, s1, q1;
+    g.lmu_pair(tile, ti, l0, l1);
     const bool fr = g.fast_range(l0, l1);
-    if (fr) {
-      nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &s0, &q0);
-      nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &s1, &q1);
-    } else {
-      SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
-      mu0 = a.mu; s0 = a.s; q0 = a.q; mu1 = b.mu; s1 = b.s; q1 = b.q;
-    }
-    if (FULLCHUNK && fr && (unsigned)(y0 | y1) < (unsigned)YT) {
-      ll_fast(y0, yd0, l0, mu0);
-      ll_fast(y1, yd1, l1, mu1);
-    } else {
-      if (m0) ll_gen(y0, yd0, l0);
-      if (m1) ll_gen(y1, yd1, l1);
-    }
-    double Z0 = fma(g.step, q0 - 1.0, l0), Z1 = fma(g.step, q1 - 1.0, l1);
-    double wt0 = s0, wt1 = s1;
-    if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
-    sw += wt0 + wt1; gz += Z0 + Z1;
-    double2 r[K];
+    {   // both cells interleaved (as OpPass1::pair; measured: one cell after the other costs 45 % more, 32.7 vs 22.3 ms at cfg 2)
+      const double* rw = tile + K * CELLS;
+      const double yd0 = (double)y0, yd1 = (double)y1;
+      double mu0, s0, q0, mu1, s1, q1;
+      if (fr) {
+        nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &s0, &q0);
+        nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &s1, &q1);
+      } else {
+        SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
+        mu0 = a.mu; s0 = a.s; q0 = a.q; mu1 = b.mu; s1 = b.s; q1 = b.q;
+      }
+      if (FULLCHUNK && fr && (unsigned)(y0 | y1) < (unsigned)YT) {
+        ll_fast(y0, yd0, l0, mu0);
+        ll_fast(y1, yd1, l1, mu1);
+      } else {
+        if (m0) ll_gen(y0, yd0, l0);
+        if (m1) ll_gen(y1, yd1, l1);
+      }
+      double Z0 = fma(g.step, q0 - 1.0, l0), Z1 = fma(g.step, q1 - 1.0, l1);
+      double wt0 = s0, wt1 = s1;
+      if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
+      sw += wt0 + wt1; gz += Z0 + Z1;
+      double2 r[K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
-    int idx = 0;
+      for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
+      int idx = 0;
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-      double wi0 = wt0 * r[i].x, wi1 = wt1 * r[i].y;
-      V[i] += wi0 + wi1;
-      u[i] = fma(wi1, Z1, fma(wi0, Z0, u[i]));
+      for (int i = 0; i < K; ++i) {
+        double wi0 = wt0 * r[i].x, wi1 = wt1 * r[i].y;
+        V[i] += wi0 + wi1;
+        u[i] = fma(wi1, Z1, fma(wi0, Z0, u[i]));
 #pragma unroll
-      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi1, r[jx].y, fma(wi0, r[jx].x, A[idx])); ++idx; }
+        for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi1, r[jx].y, fma(wi0, r[jx].x, A[idx])); ++idx; }
+      }
     }
   }
   __device__ __forceinline__ void group_end(int j) {

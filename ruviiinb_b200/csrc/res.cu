@@ -1,77 +1,224 @@
-// res.cu -- get.res (R/get.res.R:12-129)
+// res.cu -- get.res (R/get.res.R:12-129) and the fused tail of fastruvIII.nb (Mb.all block -> caps -> PAC, R/fastruvIIInb.R:719-748
+// + R/makeSCE.R:36-38), block by block of `block.size` cells as the reference streams them.  Sinks: doubles / int32 / log1p to
+// host memory (double-buffered device slabs, copies on a second stream) or nothing but a checksum.
 #include "ctx.cuh"
 #include "launch.cuh"
 #include "res.cuh"
+#include "fast.cuh"
 
-// ---- get.res (R/get.res.R:12-129) ----------------------------------------------------------------------------------------
-extern "C" int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out) {
-  if (!ctx || !out) return RUVNB_EARG;
+namespace {
+
+struct EvPair { cudaEvent_t a = nullptr, b = nullptr; int which = 0; };
+
+// where the per-cell Mb of a block comes from
+enum MbSource { MB_GROUP, MB_HOST_CELLS, MB_FAST };
+
+struct ResRun {
+  int type, out_kind;
+  long long bs, cell_begin, cell_end;
+  MbSource src;
+  const double* Mb_cells;       // MB_HOST_CELLS: host G x N doubles, column-major
+  double lambda_b;              // MB_FAST
+  const int32_t* annot_grp;     // MB_FAST
+  double* Mb_all_out;           // MB_FAST: optional host copy of Mb.all (G x N doubles, column-major)
+  void* out;
+  ruvnb_res_stats* stats;
+};
+
+template <int TYPE>
+int launch_elem(ruvnb_ctx* ctx, const ResArgs& a, int out_kind, void* slab, int* nanc, double* sum) {
+  dim3 grid(nblk(a.Gl, 32), nblk(a.B, 32));
+  if (out_kind == RUVNB_OUT_I32) k_res_elem<TYPE, 1><<<grid, 1024, 0, ctx->stream>>>(a, slab, nanc, sum);
+  else if (out_kind == RUVNB_OUT_LOG1P) k_res_elem<TYPE, 2><<<grid, 1024, 0, ctx->stream>>>(a, slab, nanc, sum);
+  else k_res_elem<TYPE, 0><<<grid, 1024, 0, ctx->stream>>>(a, slab, nanc, sum);
+  CKL();
+  return RUVNB_OK;
+}
+
+int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
+  const int type = rr.type;
   if (type < RES_PEARSON || type > RES_QUANTILE) return ctx->fail(RUVNB_EARG, "get_res: type %d is not 1 (pearson), 2 (logcounts) or 3 (quantile)", type);
   if (!ctx->have_counts || ctx->K == 0 || !ctx->have_W) return ctx->fail(RUVNB_ESTATE, "get_res: needs counts and a fitted state (W, alpha, gmean, Mb, psi)");
+  if (rr.out_kind < RUVNB_OUT_F64 || rr.out_kind > RUVNB_OUT_NONE) return ctx->fail(RUVNB_EARG, "get_res: unknown sink %d", rr.out_kind);
+  if ((rr.out_kind == RUVNB_OUT_I32 || rr.out_kind == RUVNB_OUT_LOG1P) && type != RES_QUANTILE)
+    return ctx->fail(RUVNB_EARG, "get_res: the int32 / log1p sinks hold percentile-adjusted counts (type 3) only");
+  if (rr.out_kind != RUVNB_OUT_NONE && !rr.out) return ctx->fail(RUVNB_EARG, "get_res: no output buffer");
   CK(cudaSetDevice(ctx->device));
   const int Gl = ctx->Gl, K = ctx->K;
   const long long N = ctx->N;
-  long long bs = std::min<long long>(block_size > 0 ? block_size : 5000, N);   // :18
-  if (bs > 12000) return ctx->fail(RUVNB_EARG, "get_res: block.size %lld exceeds the 12000 cells a per-gene shared-memory tile holds", bs);
+  const bool gene_sharded = ctx->Gl != ctx->G && ctx->nranks > 1;   // rows over the ranks: the Pearson clip needs all of them
+  const long long bs = std::min<long long>(rr.bs > 0 ? rr.bs : 5000, std::max<long long>(N, 1));   // :18
+  if (bs > 12288) return ctx->fail(RUVNB_EARG, "get_res: block.size %lld exceeds the 12288 cells a per-gene shared-memory tile holds", bs);
+  const long long cb = rr.cell_begin, ce = rr.cell_end < 0 ? N : rr.cell_end;
+  if (cb < 0 || ce > N || cb > ce || cb % bs != 0) return ctx->fail(RUVNB_EARG, "get_res: cells [%lld, %lld) must start on a block boundary inside 0..%lld", cb, ce, N);
+  if (ctx->cell_shard && ctx->cell0 % bs != 0) return ctx->fail(RUVNB_EARG, "get_res: the cell shard starts at %lld, not on a block of %lld cells", ctx->cell0, bs);
+  const int Gout = ctx->d_orow ? ctx->Gout : Gl;
   StateSet& s = ctx->cur;
-  double *wm = nullptr, *wam = nullptr, *logcap = nullptr, *slab[2] = {nullptr, nullptr}, *mbblk = nullptr;
+  const size_t esz = rr.out_kind == RUVNB_OUT_I32 ? 4 : 8;
+  ScopedDev own;
+  double *wm = nullptr, *wam = nullptr, *caps = nullptr, *mbstage = nullptr, *mbG = nullptr, *mbslab[2] = {nullptr, nullptr}, *sum = nullptr;
+  void* slab[2] = {nullptr, nullptr};
   unsigned* hist = nullptr; SelTargets* T = nullptr; int* nanc = nullptr;
-  cudaStream_t copy_stream = nullptr; cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
-  CK(cudaMalloc((void**)&wm, K * 8)); CK(cudaMalloc((void**)&wam, (size_t)Gl * 8)); CK(cudaMalloc((void**)&logcap, (size_t)Gl * 3 * 8));
-  for (int i = 0; i < 2; ++i) { CK(cudaMalloc((void**)&slab[i], (size_t)Gl * bs * 8)); CK(cudaEventCreate(&done[i])); CK(cudaEventCreate(&copied[i])); }
-  if (Mb_cells) CK(cudaMalloc((void**)&mbblk, (size_t)Gl * bs * 8));
-  CK(cudaMalloc((void**)&hist, SEL_NT * SEL_BINS * 4)); CK(cudaMalloc((void**)&T, sizeof(SelTargets))); CK(cudaMalloc((void**)&nanc, 4));
+  const int ldB = (int)((bs + 31) / 32 * 32);
+  CK(own.alloc(&wm, K * 8)); CK(own.alloc(&wam, (size_t)Gl * 8)); CK(own.alloc(&caps, (size_t)Gl * 3 * 8)); CK(own.alloc(&sum, 8));
+  for (int i = 0; i < 2; ++i) CK(own.alloc((char**)&slab[i], (size_t)Gout * bs * 8));
+  if (rr.src != MB_GROUP) CK(own.alloc(&mbG, (size_t)Gl * ldB * 8));
+  if (rr.src == MB_HOST_CELLS) CK(own.alloc(&mbstage, (size_t)Gl * bs * 8));
+  if (rr.src == MB_FAST && rr.Mb_all_out) for (int i = 0; i < 2; ++i) CK(own.alloc(&mbslab[i], (size_t)Gl * bs * 8));
+  CK(own.alloc(&hist, SEL_NT * SEL_BINS * 4)); CK(own.alloc(&T, sizeof(SelTargets))); CK(own.alloc(&nanc, 4));
   CK(cudaMemsetAsync(hist, 0, SEL_NT * SEL_BINS * 4, ctx->stream));
+  CK(cudaMemsetAsync(sum, 0, 8, ctx->stream));
+  FastMbPrep pr;
+  if (rr.src == MB_FAST) RET(fast_mb_prepare(ctx, rr.annot_grp, &own, &pr));
+  cudaStream_t copy_stream = nullptr; cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, t_begin = nullptr, t_end = nullptr;
   CK(cudaStreamCreate(&copy_stream));
-  k_res_wmean<<<K, 1024, 0, ctx->stream>>>(s.W, ctx->Np, (double)N, wm); CKL();
-  k_res_wamean<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(Gl, K, s.alpha, wm, wam); CKL();
-  CK(cudaFuncSetAttribute(k_res_caps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * bs * 8)));
+  for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&done[i])); CK(cudaEventCreate(&copied[i])); }
+  CK(cudaEventCreate(&t_begin)); CK(cudaEventCreate(&t_end));
+  std::vector<EvPair> evs;
+  const bool timing = rr.stats != nullptr;
+  auto ev_begin = [&](int which) -> int {
+    if (!timing) return RUVNB_OK;
+    EvPair p; p.which = which;
+    CK(cudaEventCreate(&p.a)); CK(cudaEventCreate(&p.b));
+    CK(cudaEventRecord(p.a, ctx->stream));
+    evs.push_back(p);
+    return RUVNB_OK;
+  };
+  auto ev_end = [&]() -> int { if (timing) CK(cudaEventRecord(evs.back().b, ctx->stream)); return RUVNB_OK; };
+  const long long launches0 = ctx->launches;
+  // colMeans(W) over ALL cells (:36): column sums of the local cells (pads hold 0), summed over the ranks of a cell shard
+  k_res_wmean<<<K, 1024, 0, ctx->stream>>>(s.W, ctx->Np, 1.0, wm); CKL();
+  const double n_all = ctx->cell_shard ? (double)ctx->N_total : (double)N;
+  if (ctx->cell_shard) RET(allreduce(ctx, wm, K, NCCL_F64));
+  k_res_wamean<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(Gl, K, s.alpha, wm, 1.0 / n_all, wam); CKL();
+  const int Bp_max = (int)((bs + RS_NT - 1) / RS_NT * RS_NT);
+  CK(cudaFuncSetAttribute(k_res_caps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * Bp_max * 8)));
   CK(cudaFuncSetAttribute(k_sel_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_NT * SEL_BINS * 4));
+  CK(cudaEventRecord(t_begin, ctx->stream));
   int blk = 0;
-  for (long long c0 = 0; c0 < N; c0 += bs, ++blk) {
-    const int B = (int)std::min<long long>(bs, N - c0);
+  for (long long c0 = cb; c0 < ce; c0 += bs, ++blk) {
+    const int B = (int)std::min<long long>(bs, ce - c0);
     const int sl = blk & 1;
     if (blk >= 2) CK(cudaStreamWaitEvent(ctx->stream, copied[sl], 0));   // the slab's previous contents reached the host
     ResArgs a;
-    a.Gl = Gl; a.K = K; a.m = ctx->m; a.B = B; a.N = N; a.Np = ctx->Np; a.c0 = c0; a.Yp = ctx->dY;
-    a.alpha = s.alpha; a.gmean = s.gmean; a.psi = s.psi; a.W = s.W; a.Mb = s.Mb; a.mb_blk = nullptr;
-    a.cell2pos = ctx->d_cell2pos; a.chunk_grp = ctx->d_chunk_grp; a.wa_mean = wam; a.logcap = logcap;
-    if (Mb_cells) {  // host G x N column-major: the block is one contiguous Gl x B piece == device [B][Gl]
-      CK(cudaMemcpyAsync(mbblk, Mb_cells + (size_t)c0 * Gl, (size_t)Gl * B * 8, cudaMemcpyHostToDevice, ctx->stream));
-      a.mb_blk = mbblk;
+    a.Gl = Gl; a.K = K; a.m = ctx->m; a.B = B; a.ldB = ldB; a.Gout = Gout; a.N = N; a.Np = ctx->Np; a.c0 = c0; a.Yp = ctx->dY;
+    a.alpha = s.alpha; a.gmean = s.gmean; a.psi = s.psi; a.W = s.W; a.Mb = s.Mb; a.mbG = nullptr;
+    a.cell2pos = ctx->d_cell2pos; a.chunk_grp = ctx->d_chunk_grp; a.orow = ctx->d_orow; a.wa_mean = wam; a.caps = caps; a.mtabs = ctx->d_mtabs;
+    if (rr.src == MB_HOST_CELLS) {  // host G x N column-major: the block is one contiguous Gl x B piece == device [B][Gl]
+      RET(ev_begin(3));
+      CK(cudaMemcpyAsync(mbstage, rr.Mb_cells + (size_t)c0 * Gl, (size_t)Gl * B * 8, cudaMemcpyHostToDevice, ctx->stream));
+      k_res_transpose<<<dim3(nblk(Gl, 32), nblk(B, 32)), dim3(32, 8), 0, ctx->stream>>>(mbstage, Gl, B, ldB, mbG); CKL();
+      RET(ev_end());
+      a.mbG = mbG;
+    } else if (rr.src == MB_FAST) {  // F6 for this block, kept on the device in gene-major order
+      RET(ev_begin(3));
+      FastMbArgs f;
+      f.Gl = Gl; f.K = K; f.m = ctx->m; f.B = B; f.Np = ctx->Np; f.c0 = c0; f.Yp = ctx->dY; f.alpha = s.alpha; f.gmean = s.gmean; f.psi = s.psi;
+      f.W = s.W; f.Mb = s.Mb; f.cell2pos = ctx->d_cell2pos; f.annot = pr.d_annot; f.ctl_local = pr.d_ctl; f.rmed = pr.d_rmed; f.rmad = pr.d_rmad;
+      f.lambda_b = rr.lambda_b; f.gene_major = 1; f.ldB = ldB;
+      k_fast_mb<<<dim3(nblk(Gl, 32), nblk(B, 32)), 1024, 0, ctx->stream>>>(f, mbG); CKL();
+      if (rr.Mb_all_out) {   // the caller also wants Mb.all itself: a second launch writes the R-layout slab
+        f.gene_major = 0;
+        k_fast_mb<<<dim3(nblk(Gl, 32), nblk(B, 32)), 1024, 0, ctx->stream>>>(f, mbslab[sl]); CKL();
+      }
+      RET(ev_end());
+      a.mbG = mbG;
     }
-    if (type != RES_LOGCOUNTS) { k_res_caps<<<Gl, 256, (size_t)2 * B * 8, ctx->stream>>>(a); CKL(); }
-    dim3 grid(nblk(Gl, 32), nblk(B, 32));
+    if (type != RES_LOGCOUNTS) {
+      RET(ev_begin(0));
+      k_res_caps<<<Gl, RS_NT, (size_t)2 * ((B + RS_NT - 1) / RS_NT * RS_NT) * 8, ctx->stream>>>(a, type == RES_PEARSON ? 3 : 6); CKL();
+      RET(ev_end());
+    }
+    double* sumptr = rr.out_kind == RUVNB_OUT_NONE || timing ? sum : nullptr;
+    RET(ev_begin(1));
     if (type == RES_PEARSON) {
       CK(cudaMemsetAsync(nanc, 0, 4, ctx->stream));
-      k_res_elem<RES_PEARSON><<<grid, 1024, 0, ctx->stream>>>(a, slab[sl], nanc); CKL();
+      RET(launch_elem<RES_PEARSON>(ctx, a, rr.out_kind, slab[sl], nanc, nullptr));
+      RET(ev_end());
+      RET(ev_begin(2));
       // clip at the type-7 0.5 % / 99.5 % quantiles of ALL genes x this block's cells (:63-66)
-      long long len = (long long)Gl * B, ntot = len;
-      if (ctx->nranks > 1) { ntot = (long long)ctx->G * B; RET(allreduce(ctx, nanc, 1, NCCL_INT32)); }
+      long long len = (long long)Gout * B, ntot = len;
+      if (gene_sharded) { ntot = (long long)ctx->G * B; RET(allreduce(ctx, nanc, 1, NCCL_INT32)); }
       k_sel_init<<<1, 1, 0, ctx->stream>>>(T, ntot, nanc); CKL();
       const int shifts[6] = {52, 40, 28, 16, 4, 0}, bits[6] = {12, 12, 12, 12, 12, 4};
       for (int lv = 0; lv < 6; ++lv) {
-        k_sel_hist<<<296, 256, SEL_NT * SEL_BINS * 4, ctx->stream>>>(slab[sl], len, shifts[lv], bits[lv], T, hist); CKL();
-        RET(allreduce(ctx, hist, SEL_NT * SEL_BINS, NCCL_INT32));
+        k_sel_hist<<<296, 256, SEL_NT * SEL_BINS * 4, ctx->stream>>>((const double*)slab[sl], len, shifts[lv], bits[lv], T, hist); CKL();
+        if (gene_sharded) RET(allreduce(ctx, hist, SEL_NT * SEL_BINS, NCCL_INT32));
         k_sel_pick<<<1, SEL_NT * 32, 0, ctx->stream>>>(T, hist, shifts[lv], bits[lv]); CKL();
       }
       k_sel_finish<<<1, 1, 0, ctx->stream>>>(T); CKL();
-      k_res_clip<<<nblk(len, 256), 256, 0, ctx->stream>>>(slab[sl], len, T); CKL();
+      k_res_clip<<<nblk(len, 256), 256, 0, ctx->stream>>>((double*)slab[sl], len, T, sumptr); CKL();
+      RET(ev_end());
     } else if (type == RES_LOGCOUNTS) {
-      k_res_elem<RES_LOGCOUNTS><<<grid, 1024, 0, ctx->stream>>>(a, slab[sl], nanc); CKL();
+      RET(launch_elem<RES_LOGCOUNTS>(ctx, a, rr.out_kind, slab[sl], nanc, sumptr));
+      RET(ev_end());
     } else {
-      k_res_elem<RES_QUANTILE><<<grid, 1024, 0, ctx->stream>>>(a, slab[sl], nanc); CKL();
+      RET(launch_elem<RES_QUANTILE>(ctx, a, rr.out_kind, slab[sl], nanc, sumptr));
+      RET(ev_end());
     }
     CK(cudaEventRecord(done[sl], ctx->stream));
-    CK(cudaStreamWaitEvent(copy_stream, done[sl], 0));
-    CK(cudaMemcpyAsync(out + (size_t)c0 * Gl, slab[sl], (size_t)Gl * B * 8, cudaMemcpyDeviceToHost, copy_stream));  // write_block, :125
-    CK(cudaEventRecord(copied[sl], copy_stream));
+    if (rr.out_kind != RUVNB_OUT_NONE || (rr.src == MB_FAST && rr.Mb_all_out)) {
+      CK(cudaStreamWaitEvent(copy_stream, done[sl], 0));
+      if (rr.out_kind != RUVNB_OUT_NONE)
+        CK(cudaMemcpyAsync((char*)rr.out + (size_t)(c0 - cb) * Gout * esz, slab[sl], (size_t)Gout * B * esz, cudaMemcpyDeviceToHost, copy_stream));  // write_block, :125
+      if (rr.src == MB_FAST && rr.Mb_all_out)
+        CK(cudaMemcpyAsync(rr.Mb_all_out + (size_t)(c0 - cb) * Gl, mbslab[sl], (size_t)Gl * B * 8, cudaMemcpyDeviceToHost, copy_stream));
+      CK(cudaEventRecord(copied[sl], copy_stream));
+    } else {
+      CK(cudaEventRecord(copied[sl], ctx->stream));
+    }
   }
+  CK(cudaEventRecord(t_end, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(copy_stream));
+  if (rr.stats) {
+    ruvnb_res_stats* st = rr.stats;
+    memset(st, 0, sizeof *st);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t_begin, t_end));
+    st->device_seconds = ms * 1e-3;
+    for (auto& p : evs) {
+      float t = 0; CK(cudaEventElapsedTime(&t, p.a, p.b));
+      (p.which == 0 ? st->caps_ms : p.which == 1 ? st->elem_ms : p.which == 2 ? st->select_ms : st->mb_ms) += t;
+    }
+    CK(cudaMemcpy(&st->checksum, sum, 8, cudaMemcpyDeviceToHost));
+    st->elements = (long long)Gout * (ce - cb);
+    st->launches = ctx->launches - launches0;
+  }
+  for (auto& p : evs) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   CK(cudaStreamDestroy(copy_stream));
-  for (int i = 0; i < 2; ++i) { CK(cudaFree(slab[i])); CK(cudaEventDestroy(done[i])); CK(cudaEventDestroy(copied[i])); }
-  CK(cudaFree(wm)); CK(cudaFree(wam)); CK(cudaFree(logcap)); CK(cudaFree(hist)); CK(cudaFree(T)); CK(cudaFree(nanc));
-  if (mbblk) CK(cudaFree(mbblk));
+  for (int i = 0; i < 2; ++i) { CK(cudaEventDestroy(done[i])); CK(cudaEventDestroy(copied[i])); }
+  CK(cudaEventDestroy(t_begin)); CK(cudaEventDestroy(t_end));
   return RUVNB_OK;
 }
+
+}  // namespace
+
+extern "C" {
+
+int ruvnb_get_res_ex(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, int out_kind, void* out,
+                     int64_t cell_begin, int64_t cell_end, ruvnb_res_stats* stats) {
+  if (!ctx) return RUVNB_EARG;
+  ResRun rr;
+  rr.type = type; rr.out_kind = out_kind; rr.bs = block_size; rr.cell_begin = cell_begin; rr.cell_end = cell_end;
+  rr.src = Mb_cells ? MB_HOST_CELLS : MB_GROUP; rr.Mb_cells = Mb_cells; rr.lambda_b = 0.0; rr.annot_grp = nullptr; rr.Mb_all_out = nullptr;
+  rr.out = out; rr.stats = stats;
+  return res_run(ctx, rr);
+}
+
+int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out) {
+  if (!ctx || !out) return RUVNB_EARG;
+  return ruvnb_get_res_ex(ctx, type, block_size, Mb_cells, RUVNB_OUT_F64, out, 0, -1, nullptr);
+}
+
+int ruvnb_fast_res(ruvnb_ctx* ctx, int type, double lambda_b, const int32_t* annot_grp, int64_t block_size, int out_kind, void* out,
+                   double* Mb_all_out, int64_t cell_begin, int64_t cell_end, ruvnb_res_stats* stats) {
+  if (!ctx || !annot_grp) return RUVNB_EARG;
+  ResRun rr;
+  rr.type = type; rr.out_kind = out_kind; rr.bs = block_size; rr.cell_begin = cell_begin; rr.cell_end = cell_end;
+  rr.src = MB_FAST; rr.Mb_cells = nullptr; rr.lambda_b = lambda_b; rr.annot_grp = annot_grp; rr.Mb_all_out = Mb_all_out;
+  rr.out = out; rr.stats = stats;
+  return res_run(ctx, rr);
+}
+
+}  // extern "C"

@@ -20,46 +20,65 @@
 
 struct ResArgs {
   int Gl, K, m, B;
+  int ldB;                                      // leading dimension (cells) of mbG
+  int Gout;                                     // rows of the output slab: live rows only (orow)
   long long N, Np, c0;
   const int32_t* Yp;
   const double *alpha, *gmean, *psi, *W, *Mb;   // current parameter set (Mb: [Gl][m])
-  const double* mb_blk;                         // [B][Gl] per-cell Mb of this block (fastruvIII.nb's Mb.all) or nullptr
+  const double* mbG;                            // [Gl][ldB] per-cell Mb of this block, gene-major (fastruvIII.nb's Mb.all), or nullptr
   const int *cell2pos, *chunk_grp;
+  const int* orow;                              // [Gl] output row of every resident row, -1 = row not reported (all-zero gene), or nullptr
   const double* wa_mean;                        // [Gl] a %*% colMeans(W)
-  double* logcap;                               // [Gl][3]
+  double* caps;                                 // [Gl][3] exp(median + 4 mad) of log mu, log mu.full, log mu.noUV over the block
+  const MathTabs* mtabs;
 };
 
 __device__ __forceinline__ double res_mb(const ResArgs& a, int g, int c, long long pos) {
-  return a.mb_blk ? a.mb_blk[(long long)c * a.Gl + g] : a.Mb[(long long)g * a.m + a.chunk_grp[pos >> 7]];
+  return a.mbG ? a.mbG[(long long)g * a.ldB + c] : a.Mb[(long long)g * a.m + a.chunk_grp[pos >> 7]];
 }
 
-static __global__ void __launch_bounds__(256) k_res_caps(ResArgs a) {
-  extern __shared__ double dyn[];   // wa[B], mb[B]
-  __shared__ SelScratch sc;
-  double* wa = dyn; double* mb = dyn + a.B;
+// R1: per (gene, block) caps exp(rowMedians(log mu) + 4 rowMads(log mu)) (R/get.res.R:38-45,77-80).  One CTA of RS_NT
+// threads per gene; a W' and Mb of the block's cells sit in shared memory; both middle order statistics of a vector come
+// out of ONE 12-bit radix descent (select.cuh cta_two_middles: 2-3 passes over the <= 12288 values instead of the 18 of
+// an 8-bit select with a separate lower-middle pass).  which: bit 0 mu, bit 1 mu.full, bit 2 mu.noUV.
+static __global__ void __launch_bounds__(RS_NT) k_res_caps(ResArgs a, int which) {
+  extern __shared__ double dyn[];   // wa[Bp], mb[Bp]
+  __shared__ RowSelScratch sc;
   const int g = blockIdx.x, tid = threadIdx.x;
+  if (a.orow && a.orow[g] < 0) return;
+  const int Bp = (a.B + RS_NT - 1) / RS_NT * RS_NT;
+  double* wa = dyn; double* mb = dyn + Bp;
   const double gm = a.gmean[g], wam = a.wa_mean[g];
-  for (int c = tid; c < a.B; c += 256) {
-    long long pos = a.cell2pos[a.c0 + c];
-    double s = 0.0;
-    for (int l = 0; l < a.K; ++l) s = fma(a.alpha[(long long)g * a.K + l], a.W[(long long)l * a.Np + pos], s);
-    wa[c] = s;
-    mb[c] = res_mb(a, g, c, pos);
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  int nnan = 0;
+  for (int c = tid; c < Bp; c += RS_NT) {
+    double s = inf, b = 0.0;   // pads sort last in every vector
+    if (c < a.B) {
+      const long long pos = a.cell2pos[a.c0 + c];
+      s = 0.0;
+      for (int l = 0; l < a.K; ++l) s = fma(a.alpha[(long long)g * a.K + l], a.W[(long long)l * a.Np + pos], s);
+      b = res_mb(a, g, c, pos);
+      nnan |= (s != s) | (b != b);
+    }
+    wa[c] = s; mb[c] = b;
   }
-  __syncthreads();
-  auto vld = [&](int) { return true; };
-  double med, mad;
-  auto v0 = [&](int i) { return wa[i] + gm; };
-  group_median_mad<256>(a.B, v0, vld, &sc, tid, &med, &mad);
-  if (tid == 0) a.logcap[(long long)g * 3 + 0] = med + 4.0 * mad;
-  __syncthreads();
-  auto v1 = [&](int i) { return wa[i] + gm + mb[i]; };
-  group_median_mad<256>(a.B, v1, vld, &sc, tid, &med, &mad);
-  if (tid == 0) a.logcap[(long long)g * 3 + 1] = med + 4.0 * mad;
-  __syncthreads();
-  auto v2 = [&](int i) { return mb[i] + gm + wam; };
-  group_median_mad<256>(a.B, v2, vld, &sc, tid, &med, &mad);
-  if (tid == 0) a.logcap[(long long)g * 3 + 2] = med + 4.0 * mad;
+  nnan = __syncthreads_or(nnan);
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+  const long long n = a.B;
+  auto med_mad = [&](auto val) -> double {   // median + 4 mad of val(i), i < B (R: NA if any NaN)
+    if (nnan || gm != gm) return qnan;
+    unsigned long long klo, khi;
+    auto k1 = [&](int i) { return f64_key(val(i)); };
+    cta_two_middles(Bp, n, k1, &sc, &klo, &khi);
+    const double med = (n & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0;
+    auto k2 = [&](int i) { return i < a.B ? f64_key(fabs(val(i) - med)) : f64_key(inf); };
+    cta_two_middles(Bp, n, k2, &sc, &klo, &khi);
+    const double mad = MAD_CONST * ((n & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0);
+    return med + 4.0 * mad;
+  };
+  if (which & 1) { double v = med_mad([&](int i) { return wa[i] + gm; }); if (tid == 0) a.caps[(long long)g * 3 + 0] = exp(v); }
+  if (which & 2) { double v = med_mad([&](int i) { return wa[i] + gm + mb[i]; }); if (tid == 0) a.caps[(long long)g * 3 + 1] = exp(v); }
+  if (which & 4) { double v = med_mad([&](int i) { return i < a.B ? mb[i] + gm + wam : inf; }); if (tid == 0) a.caps[(long long)g * 3 + 2] = exp(v); }
 }
 
 // log((r)/(r + mu)) the way R's dnbinom_mu takes it at x = 0
@@ -67,7 +86,7 @@ __device__ __forceinline__ double res_log_p0(double r, double mu) {
   return r * (r < mu ? log(r / (r + mu)) : log1p(-mu / (r + mu)));
 }
 // percentile-adjusted count of one element
-static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r) {
+static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r, const MathTabs* mt) {
   const double BIG = 1e250, LBIG = 575.64627324851142;  // log(1e250)
   // mid-p under (mu_full, r)
   double ls = res_log_p0(r, mu_full);
@@ -78,7 +97,7 @@ static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r
     t *= ((double)j + r) * frcp((double)j + 1.0) * ratio;
     if (t > BIG) { t *= 1e-250; s *= 1e-250; ls += LBIG; }
   }
-  double sc = exp(ls);
+  double sc = fexp(ls, mt->ex);
   double lo = s * sc, hi = lo + t * sc;      // pnbinom(y - 1), + dnbinom(y)
   double p = (lo + hi) / 2.0;
   if (p > 0.995) p = 0.995;
@@ -89,7 +108,7 @@ static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r
   const double target = p * (1.0 - 64.0 * 2.220446049250313e-16);
   ls = res_log_p0(r, mu_nouv);
   const double ratio2 = mu_nouv / (mu_nouv + r);
-  sc = exp(ls);
+  sc = fexp(ls, mt->ex);
   t = 1.0;
   double cum = 1.0;
   long long q = 0;
@@ -97,51 +116,86 @@ static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r
     t *= ((double)q + r) * frcp((double)q + 1.0) * ratio2;
     ++q;
     cum += t;
-    if (t > BIG) { t *= 1e-250; cum *= 1e-250; ls += LBIG; sc = exp(ls); }
+    if (t > BIG) { t *= 1e-250; cum *= 1e-250; ls += LBIG; sc = fexp(ls, mt->ex); }
     if (!(t == t)) return t;
   }
   return (double)q;
 }
 
-// one CTA = 32 genes x 32 cells; warp w handles gene g0 + w, lane l cell cb + l; output slab[c * Gl + g]
-template <int TYPE>
-__global__ void __launch_bounds__(1024) k_res_elem(ResArgs a, double* slab, int* nan_count) {
+// one CTA = 32 genes x 32 cells; warp w handles gene g0 + w, lane l cell cb + l; output slab[c * Gout + orow[g]] (R's
+// column-major G x B).  OUT: 0 doubles, 1 int32 (PAC), 2 log(PAC + 1) as doubles (makeSCE's logPAC, R/makeSCE.R:36-38).
+// sum (nullable): every CTA adds the sum of what it wrote (the checksum of the sink that keeps nothing).
+template <int TYPE, int OUT>
+static __global__ void __launch_bounds__(1024) k_res_elem(ResArgs a, void* slab_, int* nan_count, double* sum) {
   __shared__ double tile[32][33];
+  __shared__ MathTabs mt;
+  __shared__ double s_part[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const double* src = reinterpret_cast<const double*>(a.mtabs);
+    double* dst = reinterpret_cast<double*>(&mt);
+    for (int i = threadIdx.x; i < (int)(sizeof(MathTabs) / 8); i += 1024) dst[i] = src[i];
+  }
+  __syncthreads();
   const int g = blockIdx.x * 32 + warp, c = blockIdx.y * 32 + lane;
   double v = 0.0;
-  if (g < a.Gl && c < a.B) {
+  if (g < a.Gl && c < a.B && (!a.orow || a.orow[g] >= 0)) {
     const long long pos = a.cell2pos[a.c0 + c];
     const int y = a.Yp[(long long)g * a.Np + pos];
     double wa = 0.0;
     for (int l = 0; l < a.K; ++l) wa = fma(a.alpha[(long long)g * a.K + l], a.W[(long long)l * a.Np + pos], wa);
     const double gm = a.gmean[g];
     if (TYPE == RES_LOGCOUNTS) {
-      v = log((double)y / exp(wa) + 1.0);                                   // :68-74
+      v = log((double)y / fexp(wa, mt.ex) + 1.0);                             // :68-74
     } else {
       const double mb = res_mb(a, g, c, pos);
       const double psi = a.psi[g];
-      double mf = exp(wa + gm + mb);
-      const double cap1 = exp(a.logcap[(long long)g * 3 + 1]);
+      double mf = fexp(wa + gm + mb, mt.ex);
+      const double cap1 = a.caps[(long long)g * 3 + 1];
       if (mf > cap1) mf = cap1;                                               // :42-44
       if (TYPE == RES_PEARSON) {
-        double mu = exp(wa + gm);
-        const double cap0 = exp(a.logcap[(long long)g * 3 + 0]);
+        double mu = fexp(wa + gm, mt.ex);
+        const double cap0 = a.caps[(long long)g * 3 + 0];
         if (mu > cap0) mu = cap0;                                             // :38-40
         v = ((double)y - mu) / sqrt(mf * (1.0 + mf * psi));                   // :57
         if (v != v) atomicAdd(nan_count, 1);
       } else {
-        double mn = exp(mb + gm + a.wa_mean[g]);
-        const double cap2 = exp(a.logcap[(long long)g * 3 + 2]);
+        double mn = fexp(mb + gm + a.wa_mean[g], mt.ex);
+        const double cap2 = a.caps[(long long)g * 3 + 2];
         if (mn > cap2) mn = cap2;                                             // :77-80
-        v = res_pac(y, mf, mn, 1.0 / psi);                                    // :88-99
+        v = res_pac(y, mf, mn, 1.0 / psi, &mt);                               // :88-99
+        if (OUT == 2) v = log(v + 1.0);
       }
     }
   }
   tile[warp][lane] = v;
   __syncthreads();
   const int g2 = blockIdx.x * 32 + lane, c2 = blockIdx.y * 32 + warp;
-  if (g2 < a.Gl && c2 < a.B) slab[(long long)c2 * a.Gl + g2] = tile[lane][warp];
+  double w = 0.0;
+  if (g2 < a.Gl && c2 < a.B) {
+    const int o = a.orow ? a.orow[g2] : g2;
+    if (o >= 0) {
+      w = tile[lane][warp];
+      if (OUT == 1) reinterpret_cast<int32_t*>(slab_)[(long long)c2 * a.Gout + o] = (w >= 2147483647.0) ? 2147483647 : (int32_t)w;
+      else reinterpret_cast<double*>(slab_)[(long long)c2 * a.Gout + o] = w;
+    }
+  }
+  if (sum && TYPE != RES_PEARSON) {   // Pearson: summed after the clip (k_res_clip)
+    w = (w == w) ? w : 0.0;
+    w = warp_sum(w);
+    if (lane == 0) s_part[warp] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 32; ++i) t += s_part[i]; atomicAdd(sum, t); }
+  }
+}
+
+// [B][Gl] (a block of R's column-major G x N matrix) -> gene-major [Gl][ldB]
+static __global__ void k_res_transpose(const double* src, int Gl, int B, int ldB, double* dst) {
+  __shared__ double tile[32][33];
+  const int gb = blockIdx.x * 32, cb = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) { int c = cb + i, g = gb + threadIdx.x; if (c < B && g < Gl) tile[i][threadIdx.x] = src[(long long)c * Gl + g]; }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) { int g = gb + i, c = cb + threadIdx.x; if (c < B && g < Gl) dst[(long long)g * ldB + c] = tile[threadIdx.x][i]; }
 }
 
 // ---- exact quantiles of a slab: four order statistics by 12-bit radix descent ---------------------------------------
@@ -231,13 +285,23 @@ static __global__ void k_sel_finish(SelTargets* T) {
     T->lims[q] = v;
   }
 }
-static __global__ void k_res_clip(double* slab, long long len, const SelTargets* T) {
+static __global__ void __launch_bounds__(256) k_res_clip(double* slab, long long len, const SelTargets* T, double* sum) {
+  __shared__ double s_part[8];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= len) return;
-  double v = slab[i];
-  if (v < T->lims[0]) v = T->lims[0];
-  if (v > T->lims[1]) v = T->lims[1];
-  slab[i] = v;
+  double v = 0.0;
+  if (i < len) {
+    v = slab[i];
+    if (v < T->lims[0]) v = T->lims[0];
+    if (v > T->lims[1]) v = T->lims[1];
+    slab[i] = v;
+  }
+  if (sum) {
+    v = (v == v) ? v : 0.0;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0.0; for (int q = 0; q < 8; ++q) t += s_part[q]; atomicAdd(sum, t); }
+  }
 }
 
 // colMeans(W) over the real cells (pads hold 0) and a %*% colMeans(W)
@@ -251,10 +315,10 @@ static __global__ void __launch_bounds__(1024) k_res_wmean(const double* W, long
   for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
   if (threadIdx.x == 0) wm[blockIdx.x] = sm[0] / n;
 }
-static __global__ void k_res_wamean(int Gl, int K, const double* alpha, const double* wm, double* out) {
+static __global__ void k_res_wamean(int Gl, int K, const double* alpha, const double* wsum, double inv_n, double* out) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Gl) return;
   double s = 0.0;
-  for (int l = 0; l < K; ++l) s = fma(alpha[(long long)g * K + l], wm[l], s);
+  for (int l = 0; l < K; ++l) s = fma(alpha[(long long)g * K + l], wsum[l] * inv_n, s);   // colMeans(W) = colSums / N (all ranks)
   out[g] = s;
 }

@@ -101,6 +101,105 @@ static __global__ void __launch_bounds__(WZ_NT) k_winsorize(int32_t* Yp, long lo
   }
 }
 
+// ---- the same over cell shards: histograms summed over the ranks (core.cu ruvnb_winsorize) ------------------------------------
+// Pass A: hist[g][min(v, 4095)] -- resolves every gene whose two order statistics lie below the overflow bin (all but genes with
+// counts in the thousands in > 0.5 % of the cells).  Pass B, unresolved genes only (cap[g] < 0), once per order statistic: the
+// 12/12/8-bit radix descent of wz_select with every level's histogram summed over the ranks.
+static __global__ void __launch_bounds__(WZ_NT) k_wz_hist(const int32_t* Yp, long long Np, int shift, int nb, unsigned pmask, const unsigned* prefix,
+                                                         const double* cap, int direct, unsigned* hist) {
+  __shared__ unsigned h[WZ_BINS];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  if (!direct && !(cap[g] < 0.0)) return;
+  for (int i = tid; i < WZ_BINS; i += WZ_NT) h[i] = 0;
+  __syncthreads();
+  const int32_t* y = Yp + (long long)g * Np;
+  const unsigned pf = direct ? 0u : prefix[g];
+  for (long long i = tid; i < Np; i += WZ_NT) {
+    const int v = y[i];
+    if (v < 0) continue;   // pad
+    if (direct) atomicAdd(&h[v < WZ_BINS - 1 ? v : WZ_BINS - 1], 1u);
+    else if (((unsigned)v & pmask) == pf) atomicAdd(&h[((unsigned)v >> shift) & (unsigned)(nb - 1)], 1u);
+  }
+  __syncthreads();
+  for (int i = tid; i < WZ_BINS; i += WZ_NT) if (h[i]) hist[(long long)g * WZ_BINS + i] = h[i];
+}
+// type-7 positions (stats::quantile): index = 1 + (n-1) p; the two 0-based ranks and the interpolation weight
+__device__ __forceinline__ void wz_ranks(long long n, double prob, long long* klo, long long* khi, double* frac) {
+  const double index = 1.0 + (double)(n > 0 ? n - 1 : 0) * prob;
+  const double lo = floor(index), hi = ceil(index);
+  *klo = (long long)lo - 1; *khi = (long long)hi - 1; *frac = index - lo;
+}
+__device__ __forceinline__ double wz_cap_from(double a, double b, double frac) {
+  double q = a;
+  if (frac > 0.0 && b != a) q = (1.0 - frac) * a + frac * b;
+  return ceil(q);
+}
+// pass A: one thread per gene
+static __global__ void k_wz_pick_direct(int Gl, long long n, double prob, const unsigned* hist, double* cap, int* need) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl) return;
+  long long klo, khi; double frac;
+  wz_ranks(n, prob, &klo, &khi, &frac);
+  const unsigned* h = hist + (long long)g * WZ_BINS;
+  long long acc = 0; int a = -1, b = -1;
+  for (int v = 0; v < WZ_BINS; ++v) {
+    acc += h[v];
+    if (a < 0 && acc > klo) a = v;
+    if (acc > khi) { b = v; break; }
+  }
+  if (a >= 0 && b >= 0 && b < WZ_BINS - 1) cap[g] = wz_cap_from((double)a, (double)b, frac);
+  else { cap[g] = -1.0; atomicAdd(need, 1); }
+}
+// pass B: start of a descent for order statistic `which` (0 lower, 1 upper)
+static __global__ void k_wz_desc_init(int Gl, long long n, double prob, int which, const double* cap, unsigned* prefix, long long* rank) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl || !(cap[g] < 0.0)) return;
+  long long klo, khi; double frac;
+  wz_ranks(n, prob, &klo, &khi, &frac);
+  prefix[g] = 0u; rank[g] = which ? khi : klo;
+}
+static __global__ void k_wz_desc_pick(int Gl, const unsigned* hist, int shift, int nb, const double* cap, unsigned* prefix, long long* rank) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl || !(cap[g] < 0.0)) return;
+  const unsigned* h = hist + (long long)g * WZ_BINS;
+  long long acc = 0, rk = rank[g]; int b = 0;
+  for (; b < nb - 1; ++b) { if (acc + (long long)h[b] > rk) break; acc += h[b]; }
+  prefix[g] |= (unsigned)b << shift; rank[g] = rk - acc;
+}
+static __global__ void k_wz_desc_finish(int Gl, long long n, double prob, const unsigned* vlo, const unsigned* vhi, double* cap) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Gl || !(cap[g] < 0.0)) return;
+  long long klo, khi; double frac;
+  wz_ranks(n, prob, &klo, &khi, &frac);
+  cap[g] = wz_cap_from((double)vlo[g], (double)vhi[g], frac);
+}
+static __global__ void __launch_bounds__(WZ_NT) k_wz_apply(int32_t* Yp, long long Np, const double* capd, long long* nz_out) {
+  __shared__ long long s_nz[WZ_NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int32_t* y = Yp + (long long)blockIdx.x * Np;
+  const double cd = capd[blockIdx.x];
+  const int cap = cd >= 2147483647.0 ? 2147483647 : (int)cd;
+  long long nz = 0;
+  for (long long i = tid; i < Np; i += WZ_NT) {
+    int v = y[i];
+    if (v > cap) { v = cap; y[i] = v; }
+    nz += v > 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(FULL, nz, o);
+  if (lane == 0) s_nz[warp] = nz;
+  __syncthreads();
+  if (tid == 0) { long long t = 0; for (int w = 0; w < WZ_NT / 32; ++w) t += s_nz[w]; nz_out[blockIdx.x] = t; }
+}
+// out[c][g] = Yp[g][pos[c]]: n cells gathered into R's column-major G x n (32 x 32 tiles through shared memory)
+static __global__ void k_gather_cells(const int32_t* Yp, int Gl, long long Np, const int* pos, long long n, int32_t* out) {
+  __shared__ int32_t tile[32][33];
+  const long long gb = (long long)blockIdx.x * 32, cb = (long long)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) { long long g = gb + i, c = cb + threadIdx.x; if (g < Gl && c < n) tile[i][threadIdx.x] = Yp[g * Np + pos[c]]; }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) { long long c = cb + i, g = gb + threadIdx.x; if (g < Gl && c < n) out[c * Gl + g] = tile[threadIdx.x][i]; }
+}
+
 // inverse of the upload permutation: dst[r][cell] = Yp[r][cell2pos[cell]] (gene-major host layout)
 static __global__ void k_unpermute_rows(const int32_t* Yp, long long rows, long long N, long long Np, const int* cell2pos, int32_t* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

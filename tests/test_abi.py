@@ -23,7 +23,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_defaults(lib):
     from ruviiinb_b200 import _lib
-    assert lib.ruvnb_abi_version() == 2
+    assert lib.ruvnb_abi_version() == 3
     o = _lib.default_opts()
     # defaults of ruvIII.nb (R/ruvIIInb.R:27-28)
     assert (o.k, o.robust, o.lambda_a, o.lambda_b, o.step_fac, o.inner_maxit, o.outer_maxit) == (2, 0, 0.01, 16.0, 0.5, 50, 25)

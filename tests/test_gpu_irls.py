@@ -111,9 +111,13 @@ def test_argument_errors_are_reported_not_crashed():
     with _lib.Context(0) as ctx:
         with pytest.raises(_lib.RuvnbError, match="no counts|set_design|W not set|state"):
             ctx.loglik(_lib.default_opts(k=2))
-        grp_bad = truth["grp"].copy(); grp_bad[grp_bad == 1] = 0      # replicate group 1 has no cell
+    with _lib.Context(0) as ctx:
+        grp_bad = truth["grp"].copy(); grp_bad[grp_bad == 1] = 0      # replicate group 1 has no cell: legal for a cell shard
+        ctx.set_design(20, 200, np.where(grp_bad == 2, 2, grp_bad), ctl)   # (get.res / fastruvIII.nb passes), refused by the fit
+        ctx.upload_counts(Y)
+        ctx.set_state("W", np.zeros((200, 2)))
         with pytest.raises(_lib.RuvnbError, match="has no cell"):
-            ctx.set_design(20, 200, np.where(grp_bad == 2, 2, grp_bad), ctl)
+            ctx.loglik(_lib.default_opts(k=2))
     with _lib.Context(0) as ctx:
         ctx.set_design(20, 200, truth["grp"], ctl)
         ctx.upload_counts(Y)

@@ -80,3 +80,88 @@ def test_shard_ranges_cover_and_handle_more_ranks_than_rows():
         assert r[0][0] == 0 and r[-1][1] == G
         assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert sum(b - a for a, b in r) == G
+
+
+def _cells_worker(rank, world, port, ret):
+    """Host side of a cell-sharded run: block-aligned cell ranges, the gathered annotation, the subsample's
+    columns assembled from every rank's piece, the padded all-gather of the alpha slices, and the Winsorize quantile from
+    per-shard histograms summed over the ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ruviiinb_b200 import api
+        from oracle import rstats
+        rng = np.random.default_rng(0)
+        G, N, bs, k = 23, 1337, 100, 3
+        Y = rng.poisson(3.0, (G, N)).astype(np.int32)
+        Y[2] = rng.poisson(6000.0, N)                      # quantile beyond the 4096 direct bins
+        ranks = api.Ranks(dist)
+        c0, c1 = api.cell_shard_range(N, world, rank, bs)
+        ok = c0 % bs == 0 and (c1 == N or c1 % bs == 0)
+        spans = ranks.allgather((c0, c1))
+        ok = ok and spans[0][0] == 0 and spans[-1][1] == N and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        # the subsample's columns: every rank contributes its own, the union is in subsample order
+        sub = np.sort(rng.choice(N, 60, replace=False))
+        mine = (sub >= c0) & (sub < c1)
+        parts = ranks.allgather((np.where(mine)[0], Y[:, sub[mine]]))
+        Ysub = np.empty((G, sub.size), dtype=np.int32)
+        for idx, cc in parts:
+            Ysub[:, idx] = cc
+        ok = ok and np.array_equal(Ysub, Y[:, sub])
+        # alpha slices of ceil(G / world) rows, zero-padded, with the non-finite count in the last slot (irls.cu k_pack_alpha)
+        alpha = rng.standard_normal((G, k))
+        g0, g1 = shard.gene_range(G, world, rank)
+        per = -(-G // world)
+        sl = np.zeros(per * k + 1); sl[:(g1 - g0) * k] = alpha[g0:g1].ravel(); sl[-1] = float(rank == 1)
+        got = [torch.zeros(per * k + 1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(got, torch.tensor(sl))
+        full = np.concatenate([g.numpy()[:-1] for g in got])[:G * k].reshape(G, k)
+        ok = ok and np.array_equal(full, alpha) and sum(float(g[-1]) for g in got) == 1.0
+        # Winsorize cap = ceil(type-7 quantile at 0.995) from summed histograms (winsor.cuh k_wz_hist / k_wz_pick_direct + descent)
+        hist = np.stack([np.bincount(np.minimum(Y[g, c0:c1], 4095), minlength=4096) for g in range(G)])
+        t = torch.tensor(hist); dist.all_reduce(t); hist = t.numpy()
+        index = 1.0 + (N - 1) * 0.995
+        klo, khi, frac = int(np.floor(index)) - 1, int(np.ceil(index)) - 1, index - np.floor(index)
+        caps = np.empty(G)
+        for g in range(G):
+            cum = np.cumsum(hist[g])
+            a, b = int(np.searchsorted(cum, klo + 1)), int(np.searchsorted(cum, khi + 1))
+            if b < 4095:
+                caps[g] = np.ceil(a if (frac == 0 or a == b) else (1 - frac) * a + frac * b)
+            else:   # radix descent on the full value, one level's histogram summed per step
+                vals = []
+                for rk in (klo, khi):
+                    prefix, pmask = 0, 0
+                    for shift, bits in ((20, 12), (8, 12), (0, 8)):
+                        v = Y[g, c0:c1].astype(np.int64)
+                        sel = (v & pmask) == prefix
+                        h = torch.tensor(np.bincount((v[sel] >> shift) & ((1 << bits) - 1), minlength=1 << bits)); dist.all_reduce(h)
+                        cum = np.cumsum(h.numpy()); bsel = int(np.searchsorted(cum, rk + 1))
+                        rk -= int(cum[bsel - 1]) if bsel > 0 else 0
+                        prefix |= bsel << shift; pmask |= ((1 << bits) - 1) << shift
+                    vals.append(prefix)
+                a, b = vals
+                caps[g] = np.ceil(a if (frac == 0 or a == b) else (1 - frac) * a + frac * b)
+        ref = np.ceil(np.array([rstats.r_quantile7(Y[g].astype(np.float64), [0.995])[0] for g in range(G)]))
+        ok = ok and np.array_equal(caps, ref) and caps[2] > 4095
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_cell_shard_host_logic():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = _free_port()
+    mp.spawn(_cells_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_cell_shard_ranges_are_block_aligned():
+    from ruviiinb_b200 import api
+    for N, world, bs in [(1000000, 8, 5000), (1337, 2, 100), (300, 4, 256), (5000, 3, 5000)]:
+        r = [api.cell_shard_range(N, world, k, bs) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == N and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(a % bs == 0 or a == N for a, _ in r)   # (ranks beyond the last block hold no cell)
