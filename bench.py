@@ -244,7 +244,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS))
+    import bench_workloads as bw
+    ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS) + sorted(bw.CELL_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-fit", action="store_true",
@@ -255,6 +256,27 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in bw.CELL_WORKLOADS:    # BASELINE configs 4 and 5: the 10^6-cell passes, cells sharded over the ranks
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps(bw.run_reference(args)), file=json_out, flush=True)
+            return
+        import torch
+        import torch.distributed as dist
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+        torch.cuda.set_device(local)
+        if world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        fn = bw.run_fast if "fast" in args.workload or "cells_small" in args.workload and os.environ.get("BENCH_FAST") else bw.run_getres
+        line = fn(args, rank, world, local, dist if world > 1 else None, json_out, ClockSampler)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if line is not None:
+            print(json.dumps(line), file=json_out, flush=True)
+        return
     G, N, k, m, n_ctl = WORKLOADS[args.workload]
     config = {"workload": f"ruvIII.nb NB inner IRLS iteration, k={k}, {G} genes x {N} cells, {m} replicate groups, "
                           f"{n_ctl} control genes ({args.workload})",
