@@ -119,6 +119,11 @@ int ruvnb_measure_fp64(ruvnb_ctx* ctx, double* tflops);
 /* Host evaluation of the table-driven exp (which = 0) / log (which = 1) / unchecked log on the interleaved table
  * (which = 2, normal positive arguments) the kernels use (csrc/fastmath.cuh is __host__ __device__): lets the CPU test-suite check the very source the GPU runs.  No device needed. */
 int ruvnb_selftest_math(int which, const double* x, double* out, int64_t n);
+/* Host evaluation of the prior-d.f. step of the dispersion estimator (csrc/limma_host.h: limma::squeezeVar(s2, df = df1,
+ * covariate, robust, winsor.tail.p = c(0.05, 0.1))$df.prior as R/estimateDisp.par.R:166-168 calls it): df_prior_out receives n
+ * values (all equal when robust = 0).  covariate may be NULL.  No device needed: the CPU test-suite checks it against the
+ * SciPy-based restatement. */
+int ruvnb_selftest_squeeze_var(const double* s2, int64_t n, double df1, const double* covariate, int robust, double* df_prior_out);
 
 /* ---- multi-GPU wiring (gene sharding) -------------------------------- */
 /* id: 128 bytes from ruvnb_comm_unique_id on rank 0, distributed by the host (torch.distributed
@@ -203,10 +208,17 @@ int ruvnb_accept(ruvnb_ctx* ctx);
 int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double* rowsum);
 int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out);
 /* Same with the outputs of estimateDisp.par exposed: prior_df_in >= 0 injects prior.df (the reference derives it with
- * limma::squeezeVar(robust = TRUE, covariate), third-party arithmetic that is only approximated here by limma's plain
- * fitFDist moments); < 0 estimates it.  trended_out: local rows; prior_df_out: the prior d.f. used. */
+ * limma::squeezeVar; this entry point uses its NON-robust form, fitFDist with the AveLogCPM spline trend); < 0 estimates it.  trended_out: local rows; prior_df_out: the prior d.f. used. */
 int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_in, double* common_out, double* trended_out,
                            double* prior_df_out);
+/* estimateDisp.par's `robust` argument (R/estimateDisp.par.R:7,166-168,186-198): robust = 1 is what every call site of the reference
+ * passes (R/ruvIIInb.R:210,540; R/fastruvIIInb.R:282,569) and what ruvnb_estimate_disp / ruvnb_fit_nb use -- limma's
+ * squeezeVar(robust = TRUE, covariate = AveLogCPM, winsor.tail.p = c(0.05, 0.1)): lowess trend of log s2, Winsorized moments,
+ * ONE PRIOR D.F. PER GENE (outlier genes are shrunk less), tagwise values only where prior.n <= 1e6.  robust = 0: limma's fitFDist
+ * with the natural-spline trend in AveLogCPM (one prior d.f.).  prior_df_vec_out: local rows (Inf outside the selected genes when
+ * robust).  limma's arithmetic is restated in csrc/limma_host.h (third-party, parity unpinned). */
+int ruvnb_estimate_disp_r(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, double prior_df_in, double* common_out, double* trended_out,
+                          double* prior_df_vec_out);
 /* The north_star variant: per-gene Newton on log(psi) of the NB log-likelihood at the CURRENT fitted means, with the
  * digamma / trigamma differences psi0(y + r) - psi0(r), psi1(y + r) - psi1(r) tabulated per gene and iteration (one
  * sweep per Newton iteration, FP64 pipe).  NOT what the reference computes (it interpolates the 21-point APL grid and

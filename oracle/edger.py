@@ -240,9 +240,12 @@ def nb_deviance_one_group(y, mu, phi):
     return 2.0 * t.sum(axis=1)
 
 
-def estimate_disp(y, offset, weights=None, prior_df=None, min_row_sum=5.0):
-    """Control flow of R/estimateDisp.par.R:27-201 for design = 1, trend.method = "locfit", tagwise = TRUE.
+def estimate_disp(y, offset, weights=None, prior_df=None, min_row_sum=5.0, robust=True):
+    """Control flow of R/estimateDisp.par.R:27-201 for design = 1, trend.method = "locfit", tagwise = TRUE; robust = TRUE is what
+    every call site of the reference passes (R/ruvIIInb.R:210,540).  The prior d.f. come from limma::squeezeVar(s2, df = N - 1,
+    covariate = AveLogCPM[sel], robust) restated in oracle/limma.py: one value, or one per selected gene when robust.
     Returns dict(common, trended, tagwise, span, prior_df, prior_n, l0, sel, ave_log_cpm)."""
+    from . import limma
     y = np.asarray(y, dtype=np.float64)
     G, N = y.shape
     sel = y.sum(axis=1) >= min_row_sum                                   # :29
@@ -256,16 +259,28 @@ def estimate_disp(y, offset, weights=None, prior_df=None, min_row_sum=5.0):
     disp_trend = 0.1 * 2.0 ** trend                                       # :142
     trended = np.full(G, disp_trend[np.argmin(alc[sel])])                 # :143-145
     trended[sel] = disp_trend
-    if prior_df is None:                                                  # :156-169 (squeezeVar stand-in)
+    ns = int(sel.sum())
+    if prior_df is None:                                                  # :156-169
         beta = glm_one_group(y[sel], offset[sel], disp_trend, None if weights is None else weights[sel])
         mu = np.exp(beta[:, None] + offset[sel])
         dev = nb_deviance_one_group(y[sel], mu, disp_trend[:, None])
-        s2 = np.maximum(dev / (N - 1.0), 0.0)
-        _, prior_df = fit_f_dist(s2, N - 1.0)
-    prior_n = prior_df / (N - 1.0)                                        # :171
+        s2 = np.maximum(dev / (N - 1.0), 0.0)                             # df.residual = N - 1 (no zerofit partition)
+        prior_df_sel = np.broadcast_to(limma.squeeze_var_df_prior(s2, N - 1.0, alc[sel], robust), (ns,)).astype(np.float64)
+    else:
+        prior_df_sel = np.full(ns, float(prior_df))
+    prior_n = prior_df_sel / (N - 1.0)                                    # :171
     tagwise = trended.copy()
-    if not prior_n > 1e6:
-        l0a = l0 + prior_n * m0                                           # WLEB individual
-        tagwise[sel] = 0.1 * 2.0 ** maximize_interpolant(GRID_PTS, l0a)   # :181-190
-    return dict(common=common, trended=trended, tagwise=tagwise, span=span, prior_df=prior_df, prior_n=prior_n, l0=l0,
+    too_large = prior_n > 1e6                                             # :176
+    if not too_large.all():
+        temp_n = np.where(too_large, 1e6, prior_n)
+        ind = 0.1 * 2.0 ** maximize_interpolant(GRID_PTS, l0 + temp_n[:, None] * m0)   # WLEB individual, :181-184
+        tw = tagwise[sel]
+        if robust:
+            tw[~too_large] = ind[~too_large]                              # :189
+        else:
+            tw = ind                                                      # :186
+        tagwise[sel] = tw
+    prior_full = np.full(G, np.inf if robust else prior_df_sel[0])        # :192-198
+    prior_full[sel] = prior_df_sel
+    return dict(common=common, trended=trended, tagwise=tagwise, span=span, prior_df=prior_full, prior_n=prior_full / (N - 1.0), l0=l0,
                 sel=sel, ave_log_cpm=alc, m0=m0)

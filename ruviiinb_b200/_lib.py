@@ -25,7 +25,7 @@ SYMBOLS = [
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
     "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
     "ruvnb_set_cell_shard", "ruvnb_set_row_mask", "ruvnb_upload_counts_rows", "ruvnb_upload_counts_done", "ruvnb_get_cells",
-    "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res",
+    "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res", "ruvnb_selftest_squeeze_var", "ruvnb_estimate_disp_r",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
     lib.ruvnb_measure_fp64.argtypes = [vp, dp]
     lib.ruvnb_cert_diag.argtypes = [vp, ip]
     lib.ruvnb_selftest_math.argtypes = [C.c_int, vp, vp, C.c_int64]
+    lib.ruvnb_selftest_squeeze_var.argtypes = [vp, C.c_int64, C.c_double, vp, C.c_int, vp]
     lib.ruvnb_comm_unique_id.argtypes = [vp]
     lib.ruvnb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.ruvnb_set_design.argtypes = [vp, C.c_int64, C.c_int64, C.c_int, vp, vp, vp, C.c_int64, C.c_int64]
@@ -115,6 +116,7 @@ def load():
     lib.ruvnb_disp_apl_grid.argtypes = [vp, C.POINTER(Opts), vp, vp]
     lib.ruvnb_estimate_disp.argtypes = [vp, C.POINTER(Opts), dp]
     lib.ruvnb_estimate_disp_ex.argtypes = [vp, C.POINTER(Opts), C.c_double, dp, vp, dp]
+    lib.ruvnb_estimate_disp_r.argtypes = [vp, C.POINTER(Opts), C.c_int, C.c_double, dp, vp, vp]
     lib.ruvnb_disp_newton.argtypes = [vp, C.POINTER(Opts), vp, C.c_int]
     lib.ruvnb_fit_nb.argtypes = [vp, C.POINTER(Opts), vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(FitStats)]
     lib.ruvnb_get_res.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
@@ -313,6 +315,15 @@ class Context:
                                                  C.byref(pdf)))
         return dict(common=c.value, trended=tr, prior_df=pdf.value)
 
+    def estimate_disp_r(self, opts, robust=True, prior_df=None):
+        """estimateDisp.par(..., robust = robust) on the current parameters -> dict(common, trended, prior_df (per local gene)); sets "psi"."""
+        c = C.c_double()
+        tr = np.empty(self.Gl, dtype=np.float64)
+        pv = np.empty(self.Gl, dtype=np.float64)
+        self._ck(self.lib.ruvnb_estimate_disp_r(self.h, C.byref(opts), int(bool(robust)), -1.0 if prior_df is None else float(prior_df),
+                                                C.byref(c), _ptr(tr), _ptr(pv)))
+        return dict(common=c.value, trended=tr, prior_df=pv)
+
     def disp_newton(self, opts, maxit=30):
         out = np.empty(self.Gl, dtype=np.float64)
         self._ck(self.lib.ruvnb_disp_newton(self.h, C.byref(opts), _ptr(out), maxit))
@@ -491,6 +502,17 @@ def fast_cap_psi(psi):
     if rc != 0:
         raise RuvnbError(f"ruvnb_fast_cap_psi failed with {rc}")
     return p
+
+
+def squeeze_var_df_prior(s2, df1, covariate=None, robust=False):
+    """csrc/limma_host.h on the host: df.prior of limma::squeezeVar as estimateDisp.par calls it (one value per gene)."""
+    s2 = np.ascontiguousarray(s2, dtype=np.float64)
+    cov = None if covariate is None else np.ascontiguousarray(covariate, dtype=np.float64)
+    out = np.empty_like(s2)
+    rc = load().ruvnb_selftest_squeeze_var(_ptr(s2), s2.size, float(df1), _ptr(cov), int(bool(robust)), _ptr(out))
+    if rc != 0:
+        raise RuvnbError(f"ruvnb_selftest_squeeze_var failed with {rc}")
+    return out
 
 
 def selftest_math(which, x):

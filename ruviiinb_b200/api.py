@@ -210,7 +210,8 @@ def estimateDisp_par(y, design=None, group=None, lib_size=None, offset=None, pri
                      winsor_tail_p=(0.05, 0.1), tol=1e-06, weights=None, BPPARAM=None, replicate_of_cell=None, device=0):
     """estimateDisp.par (R/estimateDisp.par.R:3-202) as ruvIII.nb calls it: design = 1 (one coefficient), an offset matrix
     of the form alpha W' + Mb[, grp], the 21-point grid 0.1 * 2^seq(-10, 10), trend.method = "locfit" (stood in for by the
-    local-constant tricube smoother), tagwise = TRUE.  Returns the reference's list elements
+    local-constant tricube smoother), tagwise = TRUE, robust = FALSE (the function's own default) or TRUE
+    (what ruvIII.nb passes: per-gene prior.df from limma's robust squeezeVar).  Returns the reference's list elements
     (common.dispersion, trended.dispersion, tagwise.dispersion, span, prior.df, prior.n).  Arguments the device path does
     not implement raise ValueError instead of being ignored.  `replicate_of_cell` (0-based group of every cell) lets an
     offset with a replicate-group part of any size be taken apart; `BPPARAM` is accepted and ignored."""
@@ -230,8 +231,10 @@ def estimateDisp_par(y, design=None, group=None, lib_size=None, offset=None, pri
         raise ValueError("Incorrect length of group.")                                              # :19-20
     if weights is not None:
         raise ValueError("observation weights are derived on the device from the ZINB state (opts.zinb); a weight matrix is not accepted")
-    if trend_method != "locfit" or not tagwise or robust or span is not None:
-        raise ValueError("only trend.method = 'locfit', tagwise = TRUE, robust = FALSE, span = NULL are on the device path")
+    if trend_method != "locfit" or not tagwise or span is not None:
+        raise ValueError("only trend.method = 'locfit', tagwise = TRUE, span = NULL are on the device path")
+    if tuple(winsor_tail_p) != (0.05, 0.1):
+        raise ValueError("winsor.tail.p = c(0.05, 0.1) (the default every call site of the reference uses) is the one on the device path")
     if grid_length != 21 or tuple(grid_range) != (-10, 10) or min_row_sum != 5:
         raise ValueError("the device grid is 0.1 * 2^seq(-10, 10, length = 21) with min.row.sum = 5")
     if lib_size is not None and len(np.asarray(lib_size)) != N:
@@ -257,12 +260,13 @@ def estimateDisp_par(y, design=None, group=None, lib_size=None, offset=None, pri
         ctx.set_design(G, N, grp, ctl)
         ctx.upload_counts(np.ascontiguousarray(Y, dtype=np.int32))
         ctx.set_state("W", W); ctx.set_state("alpha", alpha); ctx.set_state("Mb", Mb)
-        out = ctx.estimate_disp_ex(opts, prior_df=prior_df)
+        out = ctx.estimate_disp_r(opts, robust=bool(robust), prior_df=prior_df)
         tag = ctx.get_state("psi")
     ns = int((Y.sum(axis=1) >= 5).sum())
+    pdf = out["prior_df"] if robust else float(out["prior_df"][Y.sum(axis=1) >= 5][0])        # :192-198: per gene when robust
     return {"common.dispersion": out["common"], "trended.dispersion": out["trended"], "tagwise.dispersion": tag,
             "span": 1.0 if ns <= 50 else 0.25 + 0.75 * np.sqrt(50.0 / ns),                          # edgeR::WLEB default
-            "prior.df": out["prior_df"], "prior.n": out["prior_df"] / (N - 1.0)}                   # :171, ncoefs = 1
+            "prior.df": pdf, "prior.n": pdf / (N - 1.0)}                                           # :171, ncoefs = 1
 
 
 def _estimate_disp_subset(Ysub, grp, ctl, alpha, W, Mb, cols, k, device):
@@ -279,7 +283,7 @@ def _estimate_disp_subset(Ysub, grp, ctl, alpha, W, Mb, cols, k, device):
         c2.set_state("alpha", alpha)
         c2.set_state("Mb", Mb[:, present])
         try:
-            c2.estimate_disp_ex(opts)
+            c2.estimate_disp_r(opts, robust=True)           # robust = TRUE, R/fastruvIIInb.R:282,569
         except _lib.RuvnbError:
             return np.full(Ysub.shape[0], np.nan)         # tryCatch(..., error = function(e) rep(NA, ngene))
         return c2.get_state("psi")

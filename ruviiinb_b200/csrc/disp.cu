@@ -2,6 +2,7 @@
 #include <stdlib.h>
 #include <chrono>
 #include "disp_launch.cuh"
+#include "limma_host.h"
 
 // ---- H3: dispersion (R/estimateDisp.par.R) ------------------------------------------------------------------------------
 // dst[r][d0 + i ds] = src[r][src_col + i ds] (a converged neighbour or earlier column) where that is finite and within
@@ -176,8 +177,11 @@ int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double*
 // The whole of estimateDisp.par for design = 1 (R/estimateDisp.par.R:27-201): sets "psi" of the current parameter set to
 // the tagwise dispersion.  prior_df < 0: estimate it (limma fitFDist moments; the reference's robust squeezeVar with a
 // covariate trend is not restated); prior_df >= 0: use it (injection seam).
-int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_in, double* common_out, double* trended_out,
-                           double* prior_df_out) {
+// robust: limma's squeezeVar(robust = TRUE) prior (one prior d.f. per gene, outlier genes shrink less) as every call site of the
+// reference asks (R/ruvIIInb.R:210,540, R/fastruvIIInb.R:282,569); 0: the plain fitFDist prior with the AveLogCPM trend.
+// prior_df_in >= 0 injects one prior d.f. for all genes.  prior_df_vec_out: local rows (Inf outside the selected genes when robust).
+static int estimate_disp_impl(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, double prior_df_in, double* common_out, double* trended_out,
+                              double* prior_df_out, double* prior_df_vec_out) {
   RET(check_ready(ctx, o));
   StateSet& s = ctx->cur;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -269,9 +273,9 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   { std::vector<char> issel(G, 0); for (int i : sel) issel[i] = 1; for (long long g = 0; g < G; ++g) if (!issel[g]) trended[g] = trended[sel[i_min]]; }
   if (trended_out) memcpy(trended_out, trended.data() + g0, (size_t)Gl * 8);
   const double t_trend = now();
-  // prior d.f. (:156-169): deviance at the trended dispersion -> limma fitFDist moments
-  double prior_df = prior_df_in;
-  if (!(prior_df >= 0.0)) {
+  // prior d.f. (:156-169): deviance at the trended dispersion -> limma::squeezeVar(s2, df = N - 1, covariate = AveLogCPM[sel], robust)
+  std::vector<double> prior_df_sel(ns, prior_df_in);   // one value per selected gene
+  if (!(prior_df_in >= 0.0)) {
     CK(cudaMemcpyAsync(ctx->dp_phi_row, trended.data() + g0, (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
     k_beta_from_grid<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(ctx->dp_beta, ctx->dp_phi_grid, DISP_NG, ctx->dp_phi_row, nullptr, 0.0, Gl, ctx->dp_beta1); CKL();
     DispArgs a;
@@ -293,21 +297,34 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
       CK(cudaMemcpyAsync(dev.data(), tmpB, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
     }
-    std::vector<double> s2(ns);
-    for (int i = 0; i < ns; ++i) s2[i] = std::max(dev[sel[i]] / (N - 1.0), 0.0);
-    prior_df = fit_f_dist_df2(s2, N - 1.0);
+    std::vector<double> s2(ns), cov(ns);
+    for (int i = 0; i < ns; ++i) { s2[i] = std::max(dev[sel[i]] / (N - 1.0), 0.0); cov[i] = alc[sel[i]]; }   // :163-165 (df.residual = N - 1)
+    prior_df_sel = limma_host::squeeze_var_df_prior(s2, N - 1.0, &cov, robust != 0);                          // :166-168
   }
-  if (prior_df_out) *prior_df_out = prior_df;
+  if (prior_df_out) *prior_df_out = prior_df_sel.empty() ? NAN : prior_df_sel[0];
   const double t_prior = now();
-  const double prior_n = prior_df / (N - 1.0);  // :171 (ncoefs = 1)
-  // tagwise (:172-190): per gene, maximise the spline through l0 + prior.n m0
+  // tagwise (:170-190): per gene, maximise the spline through l0 + prior.n m0 with prior.n = prior.df / (N - 1) (ncoefs = 1), prior.n
+  // capped at 1e6; robust: genes whose prior.n exceeds 1e6 keep the trended value (:186-189)
   std::vector<double> tag(trended);
-  if (!(prior_n > 1e6)) {
-    double l0a[DISP_NG];
-    for (int i : sel) {
-      for (int d = 0; d < DISP_NG; ++d) l0a[d] = l0[(size_t)i * DISP_NG + d] + prior_n * m0[(size_t)i * DISP_NG + d];
-      tag[i] = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, l0a));
+  {
+    bool all_large = true;
+    for (int i = 0; i < ns; ++i) all_large &= (prior_df_sel[i] / (N - 1.0) > 1e6);
+    if (!all_large) {
+      double l0a[DISP_NG];
+      for (int q = 0; q < ns; ++q) {
+        const int i = sel[q];
+        double pn = prior_df_sel[q] / (N - 1.0);
+        const bool large = pn > 1e6;
+        if (large) { if (robust) continue; pn = 1e6; }
+        for (int dd = 0; dd < DISP_NG; ++dd) l0a[dd] = l0[(size_t)i * DISP_NG + dd] + pn * m0[(size_t)i * DISP_NG + dd];
+        tag[i] = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, l0a));
+      }
     }
+  }
+  if (prior_df_vec_out) {   // :192-198: Inf outside the selected genes when robust, else the one value
+    std::vector<double> full(G, robust ? INFINITY : (prior_df_sel.empty() ? NAN : prior_df_sel[0]));
+    for (int q = 0; q < ns; ++q) full[sel[q]] = prior_df_sel[q];
+    memcpy(prior_df_vec_out, full.data() + g0, (size_t)Gl * 8);
   }
   // psi <- tagwise where finite (R/ruvIIInb.R:564)
   std::vector<double> old(Gl);
@@ -325,8 +342,17 @@ int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_
   return RUVNB_OK;
 }
 
+int ruvnb_estimate_disp_ex(ruvnb_ctx* ctx, const ruvnb_opts* o, double prior_df_in, double* common_out, double* trended_out,
+                           double* prior_df_out) {
+  return estimate_disp_impl(ctx, o, 0, prior_df_in, common_out, trended_out, prior_df_out, nullptr);
+}
+int ruvnb_estimate_disp_r(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, double prior_df_in, double* common_out, double* trended_out,
+                          double* prior_df_vec_out) {
+  return estimate_disp_impl(ctx, o, robust, prior_df_in, common_out, trended_out, nullptr, prior_df_vec_out);
+}
+// what the fit calls at every psi refresh: robust = TRUE, as R/ruvIIInb.R:210,540 pass it
 int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out) {
-  return ruvnb_estimate_disp_ex(ctx, o, -1.0, common_out, nullptr, nullptr);
+  return estimate_disp_impl(ctx, o, 1, -1.0, common_out, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"
@@ -356,5 +382,15 @@ extern "C" int ruvnb_disp_newton(ruvnb_ctx* ctx, const ruvnb_opts* o, double* ps
   k_exp_vec<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(theta, Gl, ctx->dp_phi_row); CKL();
   CK(cudaMemcpyAsync(psi_out, ctx->dp_phi_row, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return RUVNB_OK;
+}
+
+// host-only: the prior-d.f. step (limma_host.h) for the CPU test-suite
+extern "C" int ruvnb_selftest_squeeze_var(const double* s2, int64_t n, double df1, const double* covariate, int robust, double* df_prior_out) {
+  if (!s2 || !df_prior_out || n < 0 || !(df1 > 0.0)) return RUVNB_EARG;
+  std::vector<double> x(s2, s2 + n), cov;
+  if (covariate) cov.assign(covariate, covariate + n);
+  const std::vector<double> r = limma_host::squeeze_var_df_prior(x, df1, covariate ? &cov : nullptr, robust != 0);
+  for (int64_t i = 0; i < n; ++i) df_prior_out[i] = r[i];
   return RUVNB_OK;
 }

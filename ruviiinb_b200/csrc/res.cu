@@ -26,11 +26,12 @@ struct ResRun {
 };
 
 template <int TYPE>
-int launch_elem(ruvnb_ctx* ctx, const ResArgs& a, int out_kind, void* slab, int* nanc, double* sum) {
+int launch_elem(ruvnb_ctx* ctx, const ResArgs& a, int out_kind, double* tmp, void* slab, int* nanc, double* sum) {
+  k_res_elem<TYPE><<<dim3(nblk(a.Gl, 8), nblk(a.B, 32)), 256, 0, ctx->stream>>>(a, tmp, nanc); CKL();
   dim3 grid(nblk(a.Gl, 32), nblk(a.B, 32));
-  if (out_kind == RUVNB_OUT_I32) k_res_elem<TYPE, 1><<<grid, 1024, 0, ctx->stream>>>(a, slab, nanc, sum);
-  else if (out_kind == RUVNB_OUT_LOG1P) k_res_elem<TYPE, 2><<<grid, 1024, 0, ctx->stream>>>(a, slab, nanc, sum);
-  else k_res_elem<TYPE, 0><<<grid, 1024, 0, ctx->stream>>>(a, slab, nanc, sum);
+  if (out_kind == RUVNB_OUT_I32) k_res_out<1><<<grid, 256, 0, ctx->stream>>>(a, tmp, slab, sum);
+  else if (out_kind == RUVNB_OUT_LOG1P) k_res_out<2><<<grid, 256, 0, ctx->stream>>>(a, tmp, slab, sum);
+  else k_res_out<0><<<grid, 256, 0, ctx->stream>>>(a, tmp, slab, sum);
   CKL();
   return RUVNB_OK;
 }
@@ -56,12 +57,13 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
   StateSet& s = ctx->cur;
   const size_t esz = rr.out_kind == RUVNB_OUT_I32 ? 4 : 8;
   ScopedDev own;
-  double *wm = nullptr, *wam = nullptr, *caps = nullptr, *mbstage = nullptr, *mbG = nullptr, *mbslab[2] = {nullptr, nullptr}, *sum = nullptr;
+  double *wm = nullptr, *wam = nullptr, *caps = nullptr, *mbstage = nullptr, *mbG = nullptr, *mbslab[2] = {nullptr, nullptr}, *sum = nullptr, *tmp = nullptr;
   void* slab[2] = {nullptr, nullptr};
   unsigned* hist = nullptr; SelTargets* T = nullptr; int* nanc = nullptr;
   const int ldB = (int)((bs + 31) / 32 * 32);
   CK(own.alloc(&wm, K * 8)); CK(own.alloc(&wam, (size_t)Gl * 8)); CK(own.alloc(&caps, (size_t)Gl * 3 * 8)); CK(own.alloc(&sum, 8));
   for (int i = 0; i < 2; ++i) CK(own.alloc((char**)&slab[i], (size_t)Gout * bs * 8));
+  CK(own.alloc(&tmp, (size_t)Gl * ldB * 8));   // gene-major results of the block before the transpose into the slab
   if (rr.src != MB_GROUP) CK(own.alloc(&mbG, (size_t)Gl * ldB * 8));
   if (rr.src == MB_HOST_CELLS) CK(own.alloc(&mbstage, (size_t)Gl * bs * 8));
   if (rr.src == MB_FAST && rr.Mb_all_out) for (int i = 0; i < 2; ++i) CK(own.alloc(&mbslab[i], (size_t)Gl * bs * 8));
@@ -133,7 +135,7 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
     RET(ev_begin(1));
     if (type == RES_PEARSON) {
       CK(cudaMemsetAsync(nanc, 0, 4, ctx->stream));
-      RET(launch_elem<RES_PEARSON>(ctx, a, rr.out_kind, slab[sl], nanc, nullptr));
+      RET(launch_elem<RES_PEARSON>(ctx, a, rr.out_kind, tmp, slab[sl], nanc, nullptr));
       RET(ev_end());
       RET(ev_begin(2));
       // clip at the type-7 0.5 % / 99.5 % quantiles of ALL genes x this block's cells (:63-66)
@@ -150,10 +152,10 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
       k_res_clip<<<nblk(len, 256), 256, 0, ctx->stream>>>((double*)slab[sl], len, T, sumptr); CKL();
       RET(ev_end());
     } else if (type == RES_LOGCOUNTS) {
-      RET(launch_elem<RES_LOGCOUNTS>(ctx, a, rr.out_kind, slab[sl], nanc, sumptr));
+      RET(launch_elem<RES_LOGCOUNTS>(ctx, a, rr.out_kind, tmp, slab[sl], nanc, sumptr));
       RET(ev_end());
     } else {
-      RET(launch_elem<RES_QUANTILE>(ctx, a, rr.out_kind, slab[sl], nanc, sumptr));
+      RET(launch_elem<RES_QUANTILE>(ctx, a, rr.out_kind, tmp, slab[sl], nanc, sumptr));
       RET(ev_end());
     }
     CK(cudaEventRecord(done[sl], ctx->stream));

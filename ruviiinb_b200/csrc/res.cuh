@@ -69,10 +69,10 @@ static __global__ void __launch_bounds__(RS_NT) k_res_caps(ResArgs a, int which)
     if (nnan || gm != gm) return qnan;
     unsigned long long klo, khi;
     auto k1 = [&](int i) { return f64_key(val(i)); };
-    cta_two_middles(Bp, n, k1, &sc, &klo, &khi);
+    cta_two_middles<48>(Bp, n, k1, &sc, &klo, &khi);
     const double med = (n & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0;
     auto k2 = [&](int i) { return i < a.B ? f64_key(fabs(val(i) - med)) : f64_key(inf); };
-    cta_two_middles(Bp, n, k2, &sc, &klo, &khi);
+    cta_two_middles<48>(Bp, n, k2, &sc, &klo, &khi);
     const double mad = MAD_CONST * ((n & 1) ? key_f64(khi) : (key_f64(klo) + key_f64(khi)) / 2.0);
     return med + 4.0 * mad;
   };
@@ -122,70 +122,84 @@ static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r
   return (double)q;
 }
 
-// one CTA = 32 genes x 32 cells; warp w handles gene g0 + w, lane l cell cb + l; output slab[c * Gout + orow[g]] (R's
-// column-major G x B).  OUT: 0 doubles, 1 int32 (PAC), 2 log(PAC + 1) as doubles (makeSCE's logPAC, R/makeSCE.R:36-38).
-// sum (nullable): every CTA adds the sum of what it wrote (the checksum of the sink that keeps nothing).
-template <int TYPE, int OUT>
-static __global__ void __launch_bounds__(1024) k_res_elem(ResArgs a, void* slab_, int* nan_count, double* sum) {
-  __shared__ double tile[32][33];
+// Element kernel: warp = one gene x 32 consecutive cells, every warp on its own -- the pmf recurrences of the PAC run as long as
+// the gene's counts are large, so warps of one CTA finish far apart and a CTA-wide barrier (the shared-memory transpose this
+// kernel used to end with) left 2/3 of the issue slots waiting (ncu: stall_barrier 66 %).  Results go to a gene-major scratch
+// tmp[g][ldB] (coalesced); k_res_out transposes it into the R-layout slab.
+template <int TYPE>
+static __global__ void __launch_bounds__(256) k_res_elem(ResArgs a, double* tmp, int* nan_count) {
   __shared__ MathTabs mt;
-  __shared__ double s_part[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
     const double* src = reinterpret_cast<const double*>(a.mtabs);
     double* dst = reinterpret_cast<double*>(&mt);
-    for (int i = threadIdx.x; i < (int)(sizeof(MathTabs) / 8); i += 1024) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(MathTabs) / 8); i += 256) dst[i] = src[i];
   }
   __syncthreads();
-  const int g = blockIdx.x * 32 + warp, c = blockIdx.y * 32 + lane;
-  double v = 0.0;
-  if (g < a.Gl && c < a.B && (!a.orow || a.orow[g] >= 0)) {
-    const long long pos = a.cell2pos[a.c0 + c];
-    const int y = a.Yp[(long long)g * a.Np + pos];
-    double wa = 0.0;
-    for (int l = 0; l < a.K; ++l) wa = fma(a.alpha[(long long)g * a.K + l], a.W[(long long)l * a.Np + pos], wa);
-    const double gm = a.gmean[g];
-    if (TYPE == RES_LOGCOUNTS) {
-      v = log((double)y / fexp(wa, mt.ex) + 1.0);                             // :68-74
+  const int g = blockIdx.x * 8 + warp, c = blockIdx.y * 32 + lane;
+  if (g >= a.Gl || c >= a.B || (a.orow && a.orow[g] < 0)) return;
+  double v;
+  const long long pos = a.cell2pos[a.c0 + c];
+  const int y = a.Yp[(long long)g * a.Np + pos];
+  double wa = 0.0;
+  for (int l = 0; l < a.K; ++l) wa = fma(a.alpha[(long long)g * a.K + l], a.W[(long long)l * a.Np + pos], wa);
+  const double gm = a.gmean[g];
+  if (TYPE == RES_LOGCOUNTS) {
+    v = log((double)y / fexp(wa, mt.ex) + 1.0);                             // :68-74
+  } else {
+    const double mb = res_mb(a, g, c, pos);
+    const double psi = a.psi[g];
+    double mf = fexp(wa + gm + mb, mt.ex);
+    const double cap1 = a.caps[(long long)g * 3 + 1];
+    if (mf > cap1) mf = cap1;                                               // :42-44
+    if (TYPE == RES_PEARSON) {
+      double mu = fexp(wa + gm, mt.ex);
+      const double cap0 = a.caps[(long long)g * 3 + 0];
+      if (mu > cap0) mu = cap0;                                             // :38-40
+      v = ((double)y - mu) / sqrt(mf * (1.0 + mf * psi));                   // :57
+      if (v != v) atomicAdd(nan_count, 1);
     } else {
-      const double mb = res_mb(a, g, c, pos);
-      const double psi = a.psi[g];
-      double mf = fexp(wa + gm + mb, mt.ex);
-      const double cap1 = a.caps[(long long)g * 3 + 1];
-      if (mf > cap1) mf = cap1;                                               // :42-44
-      if (TYPE == RES_PEARSON) {
-        double mu = fexp(wa + gm, mt.ex);
-        const double cap0 = a.caps[(long long)g * 3 + 0];
-        if (mu > cap0) mu = cap0;                                             // :38-40
-        v = ((double)y - mu) / sqrt(mf * (1.0 + mf * psi));                   // :57
-        if (v != v) atomicAdd(nan_count, 1);
-      } else {
-        double mn = fexp(mb + gm + a.wa_mean[g], mt.ex);
-        const double cap2 = a.caps[(long long)g * 3 + 2];
-        if (mn > cap2) mn = cap2;                                             // :77-80
-        v = res_pac(y, mf, mn, 1.0 / psi, &mt);                               // :88-99
+      double mn = fexp(mb + gm + a.wa_mean[g], mt.ex);
+      const double cap2 = a.caps[(long long)g * 3 + 2];
+      if (mn > cap2) mn = cap2;                                             // :77-80
+      v = res_pac(y, mf, mn, 1.0 / psi, &mt);                               // :88-99
+    }
+  }
+  tmp[(long long)g * a.ldB + c] = v;
+}
+// tmp[g][ldB] -> slab[c * Gout + orow[g]] (R's column-major G x B; rows without an output row are skipped).  OUT: 0 doubles,
+// 1 int32 (PAC), 2 log(PAC + 1) as doubles (makeSCE's logPAC, R/makeSCE.R:36-38).  sum (nullable): every CTA adds the sum of
+// what it wrote (the checksum of the sink that keeps nothing).  32 x 32 tiles, 256 threads.
+template <int OUT>
+static __global__ void __launch_bounds__(256) k_res_out(ResArgs a, const double* tmp, void* slab_, double* sum) {
+  __shared__ double tile[32][33];
+  __shared__ double s_part[8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int gb = blockIdx.x * 32, cb = blockIdx.y * 32;
+  for (int i = ty; i < 32; i += 8) {
+    const int g = gb + i, c = cb + tx;
+    tile[i][tx] = (g < a.Gl && c < a.B && (!a.orow || a.orow[g] >= 0)) ? tmp[(long long)g * a.ldB + c] : 0.0;
+  }
+  __syncthreads();
+  double w = 0.0;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = cb + i, g = gb + tx;
+    if (g < a.Gl && c < a.B) {
+      const int o = a.orow ? a.orow[g] : g;
+      if (o >= 0) {
+        double v = tile[tx][i];
         if (OUT == 2) v = log(v + 1.0);
+        if (OUT == 1) reinterpret_cast<int32_t*>(slab_)[(long long)c * a.Gout + o] = (v >= 2147483647.0) ? 2147483647 : (int32_t)v;
+        else reinterpret_cast<double*>(slab_)[(long long)c * a.Gout + o] = v;
+        w += (v == v) ? v : 0.0;
       }
     }
   }
-  tile[warp][lane] = v;
-  __syncthreads();
-  const int g2 = blockIdx.x * 32 + lane, c2 = blockIdx.y * 32 + warp;
-  double w = 0.0;
-  if (g2 < a.Gl && c2 < a.B) {
-    const int o = a.orow ? a.orow[g2] : g2;
-    if (o >= 0) {
-      w = tile[lane][warp];
-      if (OUT == 1) reinterpret_cast<int32_t*>(slab_)[(long long)c2 * a.Gout + o] = (w >= 2147483647.0) ? 2147483647 : (int32_t)w;
-      else reinterpret_cast<double*>(slab_)[(long long)c2 * a.Gout + o] = w;
-    }
-  }
-  if (sum && TYPE != RES_PEARSON) {   // Pearson: summed after the clip (k_res_clip)
-    w = (w == w) ? w : 0.0;
+  if (sum) {
     w = warp_sum(w);
-    if (lane == 0) s_part[warp] = w;
+    if (tx == 0) s_part[ty] = w;
     __syncthreads();
-    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 32; ++i) t += s_part[i]; atomicAdd(sum, t); }
+    if (threadIdx.x == 0) { double t = 0.0; for (int i = 0; i < 8; ++i) t += s_part[i]; atomicAdd(sum, t); }
   }
 }
 

@@ -147,7 +147,11 @@ struct RowSelScratch {
 
 // key(i) for i in [0, len), len a multiple of RS_NT; n = number of real items (the rest are +Inf pads
 // that sort last); ranks are 0-based.  All RS_NT threads call with identical arguments.
-template <class KeyFn>
+// CAP: bucket size at which the descent stops and the bucket is ranked in shared memory (cost ~ CAP^2 / RS_NT compare steps).
+// Rows streamed from HBM (a pass costs a sweep over the row) stop early, at RS_CAP; vectors that already sit in shared memory
+// (get.res caps: a pass is ~10 iterations per thread) keep descending to a few dozen keys.  AGG: warp-aggregated histogram
+// updates (one atomic per distinct bin and warp) -- pays at the first level, where most keys share a few exponent bins.
+template <int CAP = RS_CAP, class KeyFn>
 __device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* sc, unsigned long long* klo_out,
                                 unsigned long long* khi_out) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -170,8 +174,12 @@ __device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* 
       for (int q = 0; q < 4; ++q) {
         bool ok = (i0 + q * RS_NT < len) && (kx[q] & pmask) == prefix;
         int b = ok ? (int)((kx[q] >> shift) & (unsigned long long)(nb - 1)) : nb;   // one shared dummy for the lanes that sit out
-        unsigned peers = __match_any_sync(FULL, b);
-        if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
+        if (level == 0) {
+          unsigned peers = __match_any_sync(FULL, b);
+          if (ok && (__ffs(peers) - 1) == lane) atomicAdd(&sc->hist[b], (unsigned)__popc(peers));
+        } else if (ok) {
+          atomicAdd(&sc->hist[b], 1u);   // deeper levels spread the surviving keys over the bins: no contention to aggregate
+        }
       }
     }
     __syncthreads();
@@ -202,13 +210,13 @@ __device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* 
     rank -= (long long)sc->below;
     cnt = sc->cnt;
     __syncthreads();
-    if (cnt <= RS_CAP) break;
+    if (cnt <= CAP) break;
   }
   // gather the bucket; largest key below it
   if (tid == 0) sc->nbuf = 0;
   __syncthreads();
   unsigned long long bmax = 0;
-  const bool fits = cnt <= RS_CAP;
+  const bool fits = cnt <= CAP;
   for (int i0 = 0; i0 < len; i0 += RS_NT) {
     unsigned long long kx = key(i0 + tid);
     unsigned long long mk = kx & pmask;
@@ -225,7 +233,7 @@ __device__ void cta_two_middles(int len, long long n, KeyFn key, RowSelScratch* 
   bmax = 0;
   for (int w = 0; w < RS_NT / 32; ++w) bmax = sc->red[w] > bmax ? sc->red[w] : bmax;
   if (!fits) {
-    // > RS_CAP identical keys: all 64 bits are resolved and the bucket is one value
+    // > CAP identical keys: all 64 bits are resolved and the bucket is one value
     *khi_out = prefix;
     *klo_out = rank >= 1 ? prefix : bmax;
     __syncthreads();

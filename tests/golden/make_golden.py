@@ -72,7 +72,7 @@ def dispersion(G, N, k, m, n_ctl, seed):
     l0[sel] = edger.apl_grid(Yf[sel], offs[sel])
     ref = edger.estimate_disp(Yf, offs)
     return dict(Y=Y.astype(np.int32), grp=truth["grp"].astype(np.int32), ctl=ctl, W=W, alpha=alpha, Mb=Mb, l0=l0,
-                common=np.array(ref["common"]), trended=ref["trended"], tagwise=ref["tagwise"], prior_df=np.array(ref["prior_df"]))
+                common=np.array(ref["common"]), trended=ref["trended"], tagwise=ref["tagwise"], prior_df=np.asarray(ref["prior_df"]))
 
 
 def residuals(G, N, k, m, n_ctl, seed, block_size):

@@ -48,7 +48,7 @@ def main():
         # estimateDisp, the block-wise Pearson clip limits), gathered over NCCL
         from oracle import edger, getres
         grp = truth["grp"]
-        disp = ctx.estimate_disp_ex(opts)
+        disp = ctx.estimate_disp_r(opts, robust=True)
         psi_dev = ctx.get_state("psi")
         ref_disp = edger.estimate_disp(Yf, ref["a"] @ ref["W"].T + ref["Mb"][:, grp])
         ctx.set_state("psi", ref["psi"][g0:g1])

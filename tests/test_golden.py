@@ -78,7 +78,9 @@ def test_oracle_reproduces_dispersion_golden():
     offs = g["alpha"] @ g["W"].T + g["Mb"][:, g["grp"]]
     ref = edger.estimate_disp(Y, offs)
     assert np.allclose(ref["tagwise"], g["tagwise"], rtol=1e-12) and np.allclose(ref["trended"], g["trended"], rtol=1e-12)
-    assert abs(ref["common"] / g["common"] - 1) < 1e-12 and abs(ref["prior_df"] / g["prior_df"] - 1) < 1e-10
+    fin = np.isfinite(g["prior_df"])
+    assert abs(ref["common"] / g["common"] - 1) < 1e-12 and np.array_equal(np.isfinite(ref["prior_df"]), fin)
+    assert np.abs(ref["prior_df"][fin] / g["prior_df"][fin] - 1).max() < 1e-7     # the Brent root behind df2 stops at 1e-8
 
 
 def test_oracle_reproduces_residual_golden():
@@ -100,14 +102,15 @@ def test_cuda_matches_dispersion_golden():
     with make_ctx(g["Y"], g["grp"], g["ctl"]) as ctx:
         ctx.set_state("W", g["W"]); ctx.set_state("alpha", g["alpha"]); ctx.set_state("Mb", g["Mb"])
         l0, rs = ctx.disp_apl_grid(opts)
-        out = ctx.estimate_disp_ex(opts)
+        out = ctx.estimate_disp_r(opts, robust=True)     # what the fit calls: estimateDisp.par(..., robust = TRUE)
         psi = ctx.get_state("psi")
     sel = ~np.isnan(g["l0"][:, 0])
     assert np.array_equal(sel, rs >= 5) and np.isnan(l0[~sel]).all()
     assert (np.abs(l0[sel] - g["l0"][sel]) / np.abs(g["l0"][sel])).max() < 1e-9
     assert abs(out["common"] / g["common"] - 1) < 1e-8
     assert np.abs(out["trended"] / g["trended"] - 1).max() < 1e-7
-    assert abs(out["prior_df"] / g["prior_df"] - 1) < 1e-6
+    fin = np.isfinite(g["prior_df"])
+    assert np.array_equal(np.isfinite(out["prior_df"]), fin) and np.abs(out["prior_df"][fin] / g["prior_df"][fin] - 1).max() < 1e-6
     assert np.abs(psi / g["tagwise"] - 1).max() < 1e-6
 
 

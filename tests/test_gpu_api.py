@@ -90,20 +90,23 @@ def test_offset_factorisation_is_exact():
 @pytest.mark.gpu
 @pytest.mark.parametrize("with_groups", [True, False])
 def test_estimateDisp_par_matches_oracle(with_groups):
-    """estimateDisp.par called on its own, as the reference exports it: y and an offset matrix in, the list out."""
+    """estimateDisp.par called on its own, as the reference exports it: y and an offset matrix in, the list out; robust = FALSE
+    (its default) and robust = TRUE (how ruvIII.nb calls it)."""
     from oracle import edger
     from ruviiinb_b200 import api, synth
     Y, M, ctl, truth = synth.make_counts(160, 650, 2, 3, 40, seed=35, gmean_mu=0.5)
     grp = truth["grp"]
     Wn = truth["W"] / np.sqrt((truth["W"] ** 2).sum(axis=0))
     offs = (truth["alpha"] * np.sqrt((truth["W"] ** 2).sum(axis=0))) @ Wn.T + truth["Mb"][:, grp]
-    ref = edger.estimate_disp(Y.astype(float), offs)
-    out = api.estimateDisp_par(Y, offset=offs, replicate_of_cell=grp if with_groups else None)
-    assert abs(out["common.dispersion"] / ref["common"] - 1) < 1e-8
-    assert np.abs(out["trended.dispersion"] / ref["trended"] - 1).max() < 1e-7
-    assert abs(out["prior.df"] / ref["prior_df"] - 1) < 1e-6
-    assert np.abs(out["tagwise.dispersion"] / ref["tagwise"] - 1).max() < 1e-6
-    assert out["prior.n"] == out["prior.df"] / (Y.shape[1] - 1)
+    for robust in (False, True):
+        ref = edger.estimate_disp(Y.astype(float), offs, robust=robust)
+        out = api.estimateDisp_par(Y, offset=offs, replicate_of_cell=grp if with_groups else None, robust=robust)
+        assert abs(out["common.dispersion"] / ref["common"] - 1) < 1e-8
+        assert np.abs(out["trended.dispersion"] / ref["trended"] - 1).max() < 1e-7
+        fin = np.isfinite(ref["prior_df"])
+        assert np.abs(np.broadcast_to(out["prior.df"], fin.shape)[fin] / ref["prior_df"][fin] - 1).max() < 1e-6
+        assert np.abs(out["tagwise.dispersion"] / ref["tagwise"] - 1).max() < 1e-6
+        assert np.all(np.asarray(out["prior.n"]) == np.asarray(out["prior.df"]) / (Y.shape[1] - 1))
 
 
 @pytest.mark.gpu

@@ -54,19 +54,30 @@ def test_apl_grid_matches_oracle(ecache, monkeypatch):
     assert err.max() < 1e-9, err.max()
 
 
+@pytest.mark.parametrize("robust", [True, False])
 @pytest.mark.parametrize("prior_df", [None, 0.0, 7.5])
-def test_estimate_disp_matches_oracle(prior_df):
+def test_estimate_disp_matches_oracle(prior_df, robust):
+    """The whole of estimateDisp.par: robust = TRUE (per-gene prior d.f. from limma's robust squeezeVar with the AveLogCPM trend)
+    is what the reference always passes; robust = FALSE is fitFDist with the same trend; an injected prior d.f. skips both."""
     from oracle import edger
     Y, ctl, truth, W, alpha, Mb, offs = _case(G=180, N=700, seed=33)
-    ref = edger.estimate_disp(Y.astype(float), offs, prior_df=prior_df)
+    Y[11] *= 6; Y[12] = np.random.default_rng(1).poisson(3.0, Y.shape[1]) * np.random.default_rng(2).integers(0, 30, Y.shape[1])   # outlier genes
+    ref = edger.estimate_disp(Y.astype(float), offs, prior_df=prior_df, robust=robust)
     ctx, opts = _ctx(Y, ctl, truth, W, alpha, Mb, 2)
     with ctx:
-        out = ctx.estimate_disp_ex(opts, prior_df=prior_df)
+        out = ctx.estimate_disp_r(opts, robust=robust, prior_df=prior_df)
         psi = ctx.get_state("psi")
+        if not robust:   # the older entry point is the non-robust form
+            ctx.set_state("psi", np.ones(Y.shape[0]))
+            ex = ctx.estimate_disp_ex(opts, prior_df=prior_df)
+            assert np.array_equal(ctx.get_state("psi"), psi) and ex["prior_df"] == out["prior_df"][ref["sel"]][0]
     assert abs(out["common"] / ref["common"] - 1) < 1e-8
     assert np.abs(out["trended"] / ref["trended"] - 1).max() < 1e-7
-    if prior_df is None:
-        assert abs(out["prior_df"] / ref["prior_df"] - 1) < 1e-6
+    fin = np.isfinite(ref["prior_df"])
+    assert np.array_equal(np.isfinite(out["prior_df"]), fin)
+    assert np.abs(out["prior_df"][fin] / ref["prior_df"][fin] - 1).max() < 1e-6
+    if robust and prior_df is None:
+        assert len(np.unique(out["prior_df"][ref["sel"]])) > 1      # outlier genes carry a smaller prior d.f.
     assert np.abs(psi / ref["tagwise"] - 1).max() < 1e-6   # north_star tolerance on psi
 
 
