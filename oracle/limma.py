@@ -204,6 +204,8 @@ _GL_NODES, _GL_WEIGHTS = (_GL[0] + 1.0) / 2.0, _GL[1] / 2.0      # statmod::gaus
 
 
 def _winsorized_moments(df1, df2, tail):
+    if df2 > 1e6:      # beyond this the F quantiles / density are the chi-square ones to 1e-6 (the product makes the same cut)
+        df2 = np.inf
     if np.isinf(df2):
         fq = stats.chi2.ppf([tail[0], 1.0 - tail[1]], df1) / df1
         dens = lambda f: stats.chi2.pdf(f * df1, df1) * df1
@@ -273,10 +275,13 @@ def fit_f_dist_robustly(x, df1, covariate=None, winsor_tail_p=(0.05, 0.1)):
     if f_low >= 0:
         df2 = nr_df2
     else:
-        u = optimize.brentq(fun, rbx, 1.0 - 1e-15, xtol=1e-8, rtol=8.9e-16)
-        df2 = u / (1.0 - u)
+        # uniroot(fun, interval = c(rbx, 1), f.lower = funvalLow, f.upper = funvalInf): the upper end is never evaluated by fun
+        u = optimize.brentq(lambda t: funval_inf if t >= 1.0 else fun(t), rbx, 1.0, xtol=1e-8, rtol=8.9e-16)
+        df2 = u / (1.0 - u) if u < 1.0 else np.inf
     mom_mean, mom_var = _winsorized_moments(df1, df2, tail)
     ztc = ztrend + zwmean - mom_mean
+    if np.isinf(df2):
+        return dict(scale=np.exp(ztc), df2=np.inf, df2_shrunk=np.full(n, np.inf))
     fstat = np.exp(z - ztc)
     log_tailp = stats.f.logsf(fstat, df1, df2)
     tailp = np.exp(log_tailp)

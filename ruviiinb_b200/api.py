@@ -269,6 +269,27 @@ def estimateDisp_par(y, design=None, group=None, lib_size=None, offset=None, pri
             "prior.df": pdf, "prior.n": pdf / (N - 1.0)}                                           # :171, ncoefs = 1
 
 
+def _top_right_singular_vectors(Ysub, grp, k, device):
+    """U0 = irlba(RM_Z, nv = k)$v (R/fastruvIIInb.R:223-228), RM_Z = log(Ysub + 1) minus its replicate-group means: the k leading
+    eigenvectors of the nsub x nsub Gram RM_Z' RM_Z.  irlba starts from a random vector, so the reference's own U0 is defined up to
+    its tolerance and sign only (parity runs inject U0); this is set-up plumbing, not the hot path: the Gram and its symmetric
+    eigen-decomposition run through torch on the context's GPU (a 30 000 x 3 000 dense SVD takes half a minute on one host thread)."""
+    import torch
+    dev = torch.device("cuda", int(device))
+    Z = torch.log(torch.as_tensor(np.ascontiguousarray(Ysub), device=dev).to(torch.float64) + 1.0)
+    g = torch.as_tensor(np.asarray(grp, dtype=np.int64), device=dev)
+    m = int(g.max().item()) + 1
+    for j in range(m):
+        sel = g == j
+        Z[:, sel] -= Z[:, sel].mean(dim=1, keepdim=True)
+    w, V = torch.linalg.eigh(Z.T @ Z)
+    U0 = V[:, torch.argsort(w, descending=True)[:k]].cpu().numpy()
+    for j in range(k):                                   # a fixed sign: largest entry positive
+        if U0[np.argmax(np.abs(U0[:, j])), j] < 0:
+            U0[:, j] = -U0[:, j]
+    return np.ascontiguousarray(U0)
+
+
 def _estimate_disp_subset(Ysub, grp, ctl, alpha, W, Mb, cols, k, device):
     """estimateDisp.par(Ysub[, cols], design = 1, offset = (alpha W' + Mb[, grp])[, cols]) (R/fastruvIIInb.R:273-311,569-575)
     on a second context that holds only those columns."""
@@ -306,11 +327,7 @@ def fastruvIII_nb_subfit(Ysub, Msub, ctl, k=2, lambda_a=0.01, lambda_b=16, step_
     if psi_idx is None:
         psi_idx = np.sort(rng.choice(ns, size=min(100, int(round(0.5 * ns))), replace=False))    # :218
     if U0 is None:
-        Z = np.log(Ysub + 1.0)
-        m = int(grp.max()) + 1
-        zbar = np.stack([Z[:, grp == j].mean(axis=1) for j in range(m)], axis=1)
-        _, _, vt = np.linalg.svd(Z - zbar[:, grp], full_matrices=False)
-        U0 = vt[:k].T.copy()
+        U0 = _top_right_singular_vectors(Ysub, grp, k, device)
     opts = _lib.default_opts(k=int(k), lambda_a=float(lambda_a), lambda_b=float(lambda_b), step_fac=float(step_fac),
                              inner_maxit=int(inner_maxit), outer_maxit=int(outer_maxit))
     calls = {"i": 0}

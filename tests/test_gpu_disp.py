@@ -70,12 +70,13 @@ def test_estimate_disp_matches_oracle(prior_df, robust):
         if not robust:   # the older entry point is the non-robust form
             ctx.set_state("psi", np.ones(Y.shape[0]))
             ex = ctx.estimate_disp_ex(opts, prior_df=prior_df)
-            assert np.array_equal(ctx.get_state("psi"), psi) and ex["prior_df"] == out["prior_df"][ref["sel"]][0]
+            # (a second call starts its grid fits from the first call's intercepts: equal to the Newton tolerance, not to the bit)
+            assert np.allclose(ctx.get_state("psi"), psi, rtol=1e-8) and abs(ex["prior_df"] - out["prior_df"][ref["sel"]][0]) <= 1e-8 * max(1.0, ex["prior_df"])
     assert abs(out["common"] / ref["common"] - 1) < 1e-8
     assert np.abs(out["trended"] / ref["trended"] - 1).max() < 1e-7
     fin = np.isfinite(ref["prior_df"])
     assert np.array_equal(np.isfinite(out["prior_df"]), fin)
-    assert np.abs(out["prior_df"][fin] / ref["prior_df"][fin] - 1).max() < 1e-6
+    assert np.all(np.abs(out["prior_df"][fin] - ref["prior_df"][fin]) <= 1e-6 * np.abs(ref["prior_df"][fin]))
     if robust and prior_df is None:
         assert len(np.unique(out["prior_df"][ref["sel"]])) > 1      # outlier genes carry a smaller prior d.f.
     assert np.abs(psi / ref["tagwise"] - 1).max() < 1e-6   # north_star tolerance on psi
