@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     import bench_workloads as bw
-    ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS) + sorted(bw.CELL_WORKLOADS))
+    ap.add_argument("--workload", default="cfg2_nb_20kx100k", choices=sorted(WORKLOADS) + sorted(bw.CELL_WORKLOADS) + sorted(bw.FIT_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-fit", action="store_true",
@@ -256,6 +256,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload in bw.FIT_WORKLOADS:     # BASELINE configs 3 and 1 on one GPU
+        if args.impl == "reference":
+            args.workload = "cfg2_nb_20kx100k"     # the CPU arm has the NB inner iteration only
+        else:
+            import torch
+            torch.cuda.set_device(local)
+            line = bw.run_fit(args, rank, world, local, None, json_out, ClockSampler)
+            print(json.dumps(line), file=json_out, flush=True)
+            return
     if args.workload in bw.CELL_WORKLOADS:    # BASELINE configs 4 and 5: the 10^6-cell passes, cells sharded over the ranks
         if args.impl == "reference":
             if rank == 0:

@@ -336,6 +336,103 @@ def run_fast(args, rank, world, local, dist, json_out, ClockSampler):
     return line
 
 
+# ------------------------------------------------------------------------------------------------------------------------
+FIT_WORKLOADS = {
+    # name: G, N, k, m, n_ctl, zinb
+    "cfg3_zinb_10kx50k": (10000, 50000, 3, 20, 1000, True),
+    "cfg1_standin_12kx9k": (12000, 9027, 2, 2, 1085, False),
+}
+
+
+def run_fit(args, rank, world, local, dist, json_out, ClockSampler):
+    """BASELINE configs 3 (ZINB, CSR upload) and 1 (the stand-in for the bundled cellline data): K inner IRLS iterations timed on the
+    device as on the headline line, plus the whole ruvIII.nb fit through the public mirror (wall clock).  One GPU."""
+    import torch
+    import bench
+    from ruviiinb_b200 import _lib, api
+    if world > 1:
+        raise SystemExit("these workloads are single-GPU lines (the headline workload carries the gene-sharded scaling)")
+    G, N, k, m, n_ctl, zinb = FIT_WORKLOADS[args.workload]
+    dev = torch.device("cuda", local)
+    seed = bench.SEED + (1 if zinb else -1)
+    tp = bench.truth_params(G, N, k, m, n_ctl, seed=seed)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if zinb:
+        tp["gmean"] = np.clip(-2.5 + rng.standard_normal(G), -4.0, 5.0)
+    if m == 2:     # the cellline stand-in: group sizes 4330 / 4697
+        grp = np.zeros(N, dtype=np.int32); grp[rng.permutation(N)[:4697]] = 1
+        tp["grp"] = grp
+    Y = np.empty((G, N), dtype=np.int32)
+    bench.gen_rows_gpu(tp, np.arange(G), Y, dev)
+    zi = None
+    if zinb:
+        pi0 = rng.beta(2.0, 5.0, size=G)
+        Y[rng.random(Y.shape, dtype=np.float32) < pi0[:, None].astype(np.float32)] = 0
+        zi = np.ones(N, bool)
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    opts = _lib.default_opts(k=k, zinb=int(zinb))
+    config = {"workload": f"ruvIII.nb {'ZINB' if zinb else 'NB'} inner IRLS iteration, k={k}, {G} genes x {N} cells, {m} replicate groups, {n_ctl} control genes "
+                          f"({args.workload}{', %.0f %% zeros, CSR upload' % (100 * (Y == 0).mean()) if zinb else ''})",
+              "l2": "inputs larger than L2 (int32 counts %.1f GB per pass)" % (4.0 * G * N / 1e9), "sharding": "none"}
+    ctx = _lib.Context(local)
+    ctx.set_design(G, N, tp["grp"], tp["ctl"], zeroinf=zi)
+    if zinb:
+        import scipy.sparse as sp
+        csr = sp.csr_matrix(Y)
+        t0 = time.perf_counter(); ctx.upload_counts_csr(csr.indptr, csr.indices, csr.data); t_up = time.perf_counter() - t0
+    else:
+        t0 = time.perf_counter(); ctx.upload_counts(Y); t_up = time.perf_counter() - t0
+    ctx.set_state("W", tp["W0"]); ctx.init_coef(opts); ctx.set_state("psi", tp["psi"])
+    if zinb:
+        ctx.zinb_pi0(opts)
+    ctx.loglik(opts)
+    for _ in range(args.warmup):
+        ctx.irls_iteration(opts); ctx.accept()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.kernel_time_reset()
+    l0 = ctx.kernel_launches
+    clocks = ClockSampler(local); clocks.start()
+    torch.cuda.synchronize(); clocks.begin()
+    e0.record(stream)
+    logls = []
+    for _ in range(args.steps):
+        ll, bad = ctx.irls_iteration(opts); ctx.accept(); logls.append(ll)
+    e1.record(stream)
+    torch.cuda.synchronize(); clocks.end()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - l0
+    kt = ctx.kernel_times()
+    ctx.close()
+    # the whole fit through the public mirror: Winsorize, device SVD start, robust estimateDisp at every psi refresh, alternating IRLS
+    M = np.zeros((N, m), bool); M[np.arange(N), tp["grp"]] = True
+    t0 = time.perf_counter()
+    fit = api.ruvIII_nb(Y, M, tp["ctl"], k=k, zeroinf=zi, device=local, return_trace=True)
+    wall = time.perf_counter() - t0
+    peak, peak_src = _peaks()
+    kern = {n: {"ms": tot / cnt, "launches_per_step": cnt / args.steps} for n, (tot, cnt) in kt.items() if cnt}
+    dom = max(kern, key=lambda n: kern[n]["ms"] * kern[n]["launches_per_step"])
+    ach = 4.0 * G * N / (kern[dom]["ms"] * 1e-3) / 1e9
+    line = {"metric": "NB IRLS gene-fits/sec", "value": G * args.steps / (ms * 1e-3), "unit": "gene-fits/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clk, "gpu_launches": int(launches), "logl_trace": logls,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 4.0 * G * N, "note": "FP64-pipe-bound sweep (DESIGN.md section 5)", "kernels": kern},
+            "e2e": {"value": G * fit["stats"]["n_inner"] / wall, "unit": "gene-fits/s", "h2d_bytes_per_step": int(Y.nbytes / max(1, fit["stats"]["n_inner"])),
+                    "d2h_bytes_per_step": int((fit["W"].nbytes + fit["a"].nbytes + fit["Mb"].nbytes + Y.nbytes) / max(1, fit["stats"]["n_inner"])),
+                    "what": "the whole ruvIII.nb through api.ruvIII_nb with host buffers: upload, Winsorize, zero-gene filter, device SVD start, estimateDisp "
+                            "(robust) at every psi refresh, all inner iterations, read-back of counts and parameters; gene-fits = G x inner iterations / wall"},
+            "full_fit": {"wall_seconds": wall, "outer_iterations": fit["stats"]["n_outer"], "inner_iterations": fit["stats"]["n_inner"],
+                         "inner_loop_seconds": fit["stats"]["inner_seconds"], "dispersion_seconds": fit["stats"]["disp_seconds"], "upload_seconds_bench_ctx": t_up,
+                         "logl_outer": [float(x) for x in fit["logl"]], "dropped_genes": int(fit["zero_genes"].sum())}}
+    if not args.no_cpu_baseline:
+        v, desc, _ = bench.cpu_sample_run("cfg2_nb_20kx100k", 2, 1)
+        desc["sample"] += " (the NB inner iteration of the headline workload; the C restatement has no ZINB branch)" if zinb else ""
+        line["cpu_baseline"] = dict(value=v, unit="gene-fits/s", **desc)
+    return line
+
+
 def run_reference(args):
     v, desc = cpu_getres_sample(args.workload)
     G, N, k, m, n_ctl, frac = CELL_WORKLOADS[args.workload]

@@ -293,6 +293,12 @@ void ruvnb_host_free(void* p);
 /* Mb_cells: G x N per-cell Mb (fastruvIII.nb's Mb.all) or NULL to expand the resident G x m Mb by
  * group.  out: G x N column-major doubles (what write_block receives, :125). */
 int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out);
+/* get.res of a ZERO-INFLATED fit (R/get.res.R:52-57,69-70,84-85,95-96,104-105; ZIM::dzinb / pzinb / qzinb restated): the state's "pi0"
+ * enters as omega_gc = pi0_g where zflag_of_cell[c] != 0, else 0.  The reference reads out$pi0[, curr.batch] -- column batch[c] of
+ * the G x N matrix outer(pi0, zeroinf) -- so the flag of cell c is zeroinf[batch[c]] (with one batch: zeroinf[1] for every cell); the
+ * host passes exactly that vector.  mean_zeroinf: rowMeans(out$pi0) = pi0_g * mean(zeroinf), the omega of the qzinb call.  NULL
+ * switches back to the NB formulas. */
+int ruvnb_set_res_zinb(ruvnb_ctx* ctx, const uint8_t* zflag_of_cell, double mean_zeroinf);
 /* The same with the sink chosen by the caller.  out_kind: */
 #define RUVNB_OUT_F64 0    /* doubles, G x N column-major (what ruvnb_get_res writes)                                     */
 #define RUVNB_OUT_I32 1    /* int32 (type RUVNB_RES_QUANTILE only: PAC are integers; half the bytes of the stream)        */

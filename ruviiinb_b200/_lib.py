@@ -25,7 +25,7 @@ SYMBOLS = [
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
     "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
     "ruvnb_set_cell_shard", "ruvnb_set_row_mask", "ruvnb_upload_counts_rows", "ruvnb_upload_counts_done", "ruvnb_get_cells",
-    "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res", "ruvnb_selftest_squeeze_var", "ruvnb_estimate_disp_r",
+    "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res", "ruvnb_selftest_squeeze_var", "ruvnb_estimate_disp_r", "ruvnb_set_res_zinb",
 ]
 
 
@@ -128,6 +128,7 @@ def load():
     lib.ruvnb_fast_iteration.argtypes = [vp, C.POINTER(Opts), dp, ip]
     lib.ruvnb_fast_halve_steps.argtypes = [vp, C.POINTER(Opts)]
     lib.ruvnb_fast_accept.argtypes = [vp]
+    lib.ruvnb_set_res_zinb.argtypes = [vp, vp, C.c_double]
     lib.ruvnb_set_cell_shard.argtypes = [vp, C.c_int64, C.c_int64]
     lib.ruvnb_set_row_mask.argtypes = [vp, vp]
     lib.ruvnb_upload_counts_rows.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int64]
@@ -352,6 +353,10 @@ class Context:
         mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
         self._ck(self.lib.ruvnb_get_res(self.h, int(kind), int(block_size), _ptr(mb), _ptr(out)))
         return out
+
+    def set_res_zinb(self, zflag_of_cell, mean_zeroinf):
+        z = None if zflag_of_cell is None else np.ascontiguousarray(np.asarray(zflag_of_cell).astype(np.uint8))
+        self._ck(self.lib.ruvnb_set_res_zinb(self.h, _ptr(z), float(mean_zeroinf)))
 
     # ---- cell shards, row mask, slab upload, sinks (include/ruvnb.h) -----------------------------------------------
     def set_cell_shard(self, N_total, c0):

@@ -130,14 +130,13 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
 
     Cell shards (`ranks`, `N_total`, `c0` as in `fastruvIII_nb`): blocks are independent (:27-126) except for colMeans(W)
     (:36), which the library sums over the ranks; `out` then holds this rank's cells.  sink: "f64" (the reference's doubles),
-    "i32" (PAC as int32), "log1p" (log(PAC + 1)), "none" (checksum only; with return_stats)."""
+    "i32" (PAC as int32), "log1p" (log(PAC + 1)), "none" (checksum only; with return_stats).
+    Zero-inflated fits (out["pi0"]: the G x N matrix of R/ruvIIInb.R:611-626) take the ZIM branches (:52-57,69-70,84-85,95-96)."""
     kinds = [type] if isinstance(type, str) else list(type)
     for t in kinds:
         if t not in ("pearson", "logcounts", "quantile"):
             raise ValueError(f"unknown type '{t}'")
     last = [t for t in ("pearson", "logcounts", "quantile") if t in kinds][-1]
-    if out.get("pi0") is not None:
-        raise NotImplementedError("get.res for zero-inflated fits (ZIM::pzinb / qzinb branch, R/get.res.R:84-105)")
     if np.ndim(out["psi"]) != 1:
         raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
     ranks = ranks or Ranks()
@@ -165,6 +164,14 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
         if not per_cell:
             Mbg[:, :Mb.shape[1]] = Mb
         ctx.set_state("Mb", Mbg)
+        if out.get("pi0") is not None:       # a ZINB fit: out$pi0 = outer(pi0, zeroinf), read as out$pi0[, batch[c]] (R/get.res.R:53,84-85)
+            P = np.asarray(out["pi0"], dtype=np.float64)
+            if P.shape[1] != N_total:
+                raise ValueError("get.res of a zero-inflated fit needs the whole G x N pi0 matrix (its columns are indexed by batch)")
+            zi = (P != 0).any(axis=0)
+            b = np.ones(N_total, dtype=np.int64) if batch is None else np.asarray(batch).astype(np.int64)
+            ctx.set_state("pi0", P.max(axis=1))
+            ctx.set_res_zinb(zi[b[c0:c0 + N] - 1], float(zi.mean()))
         res, st = ctx.get_res_ex(_lib.RES_KINDS[last], block_size=block_size, Mb_cells=Mb if per_cell else None, out_kind=kind)
     return (res, st) if return_stats else res
 

@@ -168,6 +168,7 @@ struct ruvnb_ctx {
   // N_total and ALL genes; what crosses ranks is summed over the communicator (ruvnb_set_cell_shard)
   bool cell_shard = false;
   long long N_total = 0, cell0 = 0;
+  uint8_t* res_zflag = nullptr; double res_zavg = 0.0;   // get.res of a ZINB fit (ruvnb_set_res_zinb)
   uint8_t* d_row_alive = nullptr; int* d_orow = nullptr; int Gout = 0;   // rows reported by get.res / F6 (ruvnb_set_row_mask)
   bool even_shards = false;  // rank r holds rows [r per, min(G, (r+1) per)), per = ceil(G / nranks): slices can be all-gathered
   double* agather = nullptr; // [nranks][per K + 1] alpha slices + the rank's non-finite count (all-gather buffer)

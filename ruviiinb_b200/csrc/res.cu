@@ -106,6 +106,7 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
     a.Gl = Gl; a.K = K; a.m = ctx->m; a.B = B; a.ldB = ldB; a.Gout = Gout; a.N = N; a.Np = ctx->Np; a.c0 = c0; a.Yp = ctx->dY;
     a.alpha = s.alpha; a.gmean = s.gmean; a.psi = s.psi; a.W = s.W; a.Mb = s.Mb; a.mbG = nullptr;
     a.cell2pos = ctx->d_cell2pos; a.chunk_grp = ctx->d_chunk_grp; a.orow = ctx->d_orow; a.wa_mean = wam; a.caps = caps; a.mtabs = ctx->d_mtabs;
+    a.pi0 = ctx->res_zflag ? s.pi0 : nullptr; a.zflag = ctx->res_zflag; a.zavg = ctx->res_zavg;
     if (rr.src == MB_HOST_CELLS) {  // host G x N column-major: the block is one contiguous Gl x B piece == device [B][Gl]
       RET(ev_begin(3));
       CK(cudaMemcpyAsync(mbstage, rr.Mb_cells + (size_t)c0 * Gl, (size_t)Gl * B * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -206,6 +207,20 @@ int ruvnb_get_res_ex(ruvnb_ctx* ctx, int type, int64_t block_size, const double*
   rr.src = Mb_cells ? MB_HOST_CELLS : MB_GROUP; rr.Mb_cells = Mb_cells; rr.lambda_b = 0.0; rr.annot_grp = nullptr; rr.Mb_all_out = nullptr;
   rr.out = out; rr.stats = stats;
   return res_run(ctx, rr);
+}
+
+// get.res of a ZINB fit (R/get.res.R:52-57,69-70,84-85,95-96): the state's "pi0" is used where zflag_of_cell[c] != 0
+int ruvnb_set_res_zinb(ruvnb_ctx* ctx, const uint8_t* zflag_of_cell, double mean_zeroinf) {
+  if (!ctx) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "set_res_zinb: call ruvnb_set_design first");
+  CK(cudaSetDevice(ctx->device));
+  if (!zflag_of_cell) { ctx->res_zflag = nullptr; ctx->res_zavg = 0.0; return RUVNB_OK; }
+  uint8_t* d = nullptr;
+  RET(dev_alloc(ctx, &d, ctx->N));
+  CK(cudaMemcpyAsync(d, zflag_of_cell, (size_t)ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->res_zflag = d; ctx->res_zavg = mean_zeroinf;
+  return RUVNB_OK;
 }
 
 int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out) {

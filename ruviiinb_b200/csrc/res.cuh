@@ -28,6 +28,10 @@ struct ResArgs {
   const double* mbG;                            // [Gl][ldB] per-cell Mb of this block, gene-major (fastruvIII.nb's Mb.all), or nullptr
   const int *cell2pos, *chunk_grp;
   const int* orow;                              // [Gl] output row of every resident row, -1 = row not reported (all-zero gene), or nullptr
+  const double* pi0;                            // [Gl] zero-inflation probability of a ZINB fit, or nullptr (NB fit)
+  const uint8_t* zflag;                         // [N] 1 where omega_gc = pi0_g applies: the reference reads out$pi0[, batch[c]], i.e. the
+                                                //     zero-inflation flag of cell number batch[c] (R/get.res.R:53,84-85)
+  double zavg;                                  // mean(zeroinf): rowMeans(out$pi0) = pi0_g zavg (:95)
   const double* wa_mean;                        // [Gl] a %*% colMeans(W)
   double* caps;                                 // [Gl][3] exp(median + 4 mad) of log mu, log mu.full, log mu.noUV over the block
   const MathTabs* mtabs;
@@ -85,8 +89,10 @@ static __global__ void __launch_bounds__(RS_NT) k_res_caps(ResArgs a, int which)
 __device__ __forceinline__ double res_log_p0(double r, double mu) {
   return r * (r < mu ? log(r / (r + mu)) : log1p(-mu / (r + mu)));
 }
-// percentile-adjusted count of one element
-static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r, const MathTabs* mt) {
+// percentile-adjusted count of one element.  omega / omega_avg: zero-inflation probabilities of a ZINB fit (0 for NB), with ZIM's
+// definitions (ZIM 1.1.0, third-party, restated): dzinb = omega 1[x = 0] + (1 - omega) dnbinom, pzinb(q) = omega + (1 - omega) pnbinom(q)
+// (also for q = -1, where it returns omega), qzinb(p) = qnbinom(max(0, (p - omega)/(1 - omega))).  R/get.res.R:84-99.
+static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r, const MathTabs* mt, double omega, double omega_avg) {
   const double BIG = 1e250, LBIG = 575.64627324851142;  // log(1e250)
   // mid-p under (mu_full, r)
   double ls = res_log_p0(r, mu_full);
@@ -99,12 +105,18 @@ static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r
   }
   double sc = fexp(ls, mt->ex);
   double lo = s * sc, hi = lo + t * sc;      // pnbinom(y - 1), + dnbinom(y)
+  if (omega != 0.0) {                        // pzinb(y - 1), + dzinb(y)
+    const double d = (hi - lo) * (1.0 - omega) + (y == 0 ? omega : 0.0);
+    lo = omega + (1.0 - omega) * lo;
+    hi = lo + d;
+  }
   double p = (lo + hi) / 2.0;
   if (p > 0.995) p = 0.995;
   if (p < 0.005) p = 0.005;
   if (!(p == p)) return p;
+  if (omega_avg != 0.0) { p = (p - omega_avg) / (1.0 - omega_avg); if (p < 0.0) p = 0.0; }   // qzinb
   // qnbinom(p; mu_nouv, r)
-  if (mu_nouv == 0.0) return 0.0;
+  if (mu_nouv == 0.0 || p == 0.0) return 0.0;
   const double target = p * (1.0 - 64.0 * 2.220446049250313e-16);
   ls = res_log_p0(r, mu_nouv);
   const double ratio2 = mu_nouv / (mu_nouv + r);
@@ -144,8 +156,9 @@ static __global__ void __launch_bounds__(256) k_res_elem(ResArgs a, double* tmp,
   double wa = 0.0;
   for (int l = 0; l < a.K; ++l) wa = fma(a.alpha[(long long)g * a.K + l], a.W[(long long)l * a.Np + pos], wa);
   const double gm = a.gmean[g];
+  const double omega = (a.pi0 && a.zflag[a.c0 + c]) ? a.pi0[g] : 0.0;       // out$pi0[, curr.batch], :53,69,84
   if (TYPE == RES_LOGCOUNTS) {
-    v = log((double)y / fexp(wa, mt.ex) + 1.0);                             // :68-74
+    v = log((double)y / (fexp(wa, mt.ex) * (1.0 - omega)) + 1.0);           // :68-74
   } else {
     const double mb = res_mb(a, g, c, pos);
     const double psi = a.psi[g];
@@ -156,13 +169,13 @@ static __global__ void __launch_bounds__(256) k_res_elem(ResArgs a, double* tmp,
       double mu = fexp(wa + gm, mt.ex);
       const double cap0 = a.caps[(long long)g * 3 + 0];
       if (mu > cap0) mu = cap0;                                             // :38-40
-      v = ((double)y - mu) / sqrt(mf * (1.0 + mf * psi));                   // :57
+      v = ((double)y - mu * (1.0 - omega)) / sqrt(mf * (1.0 - omega) * (1.0 + mf * (psi + omega)));   // :53-57
       if (v != v) atomicAdd(nan_count, 1);
     } else {
       double mn = fexp(mb + gm + a.wa_mean[g], mt.ex);
       const double cap2 = a.caps[(long long)g * 3 + 2];
       if (mn > cap2) mn = cap2;                                             // :77-80
-      v = res_pac(y, mf, mn, 1.0 / psi, &mt);                               // :88-99
+      v = res_pac(y, mf, mn, 1.0 / psi, &mt, omega, a.pi0 ? a.pi0[g] * a.zavg : 0.0);   // :84-99
     }
   }
   tmp[(long long)g * a.ldB + c] = v;
