@@ -108,6 +108,9 @@ struct ruvnb_ctx {
          *red = nullptr, *amean = nullptr, *S0 = nullptr, *S1 = nullptr, *Wbar = nullptr,
          *RMW = nullptr, *sumsq = nullptr, *med = nullptr, *mad = nullptr, *ctlpack = nullptr, *alpha_full = nullptr,
          *scal = nullptr;
+  double* Wc = nullptr;      // [Gl][Np] weight cache: huber x sig.inv x wt.zinb of every element, written by pass 1 / the fused sweep and
+  bool Wc_tried = false;     //   read back by pass 2 (kernels.cuh k_pass2w); taken when HBM has the room, RUVNB_NO_WCACHE=1 turns it off
+  double* SWZ = nullptr;     // [nparts][Gl][m] per-group sum w Z of the same sweep
   double* D = nullptr; long long D_rows = 0;  // exact-MAD scratch [D_rows][Np]
   double* rowmax = nullptr; int* rownan = nullptr;  // per scratch slot: max|d|, NaN flag
   double* hint = nullptr;        // [Gl][3] certificate hints lo, hi, tg (k_row_sigma -> k_loglik)

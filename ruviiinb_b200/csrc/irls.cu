@@ -30,6 +30,7 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
     if (P > 1) {  // groups that a part never meets must read as zero
       CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
       CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * ctx->m * ctx->K * 8, ctx->stream));
+      if (ctx->Wc) CK(cudaMemsetAsync(ctx->SWZ, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
     }
     r = launch_ll_pass1(ctx, geom(ctx, Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath);
   } else {
@@ -252,6 +253,26 @@ static __global__ void k_sum_parts5(double* A, long long nA, double* u, long lon
   p[i] = s;
 }
 
+// the weight cache (ctx->Wc): 8 bytes per element, taken once when free HBM covers it plus a reserve for what is allocated later
+// (exact-MAD scratch, the dispersion step's exp(offset) slab, get.res slabs)
+static int ensure_wcache(ruvnb_ctx* ctx) {
+  if (ctx->Wc_tried) return RUVNB_OK;
+  ctx->Wc_tried = true;
+  const char* e = getenv("RUVNB_NO_WCACHE");
+  if (e && *e && *e != '0') return RUVNB_OK;
+  size_t fr = 0, tot = 0;
+  CK(cudaMemGetInfo(&fr, &tot));
+  const size_t need = (size_t)ctx->Gl * (size_t)ctx->Np * 8, reserve = std::max<size_t>((size_t)24 << 30, tot / 4) + need;   // + the exp(offset) slab
+  if (fr > need + reserve) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, need) == cudaSuccess) {
+      ctx->allocs.push_back(q); ctx->Wc = (double*)q;
+      RET(dev_alloc(ctx, &ctx->SWZ, (long long)ctx->nparts * ctx->Gl * ctx->m));
+    } else cudaGetLastError();
+  }
+  return RUVNB_OK;
+}
+
 static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int bad[3]) {
   const int Gl = ctx->Gl, K = ctx->K, m = ctx->m, KK = K * (K + 1) / 2;
   const double kh = o->robust ? 1.345 : 100.0;  // :155
@@ -259,6 +280,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   const bool fuse = fuse_ok(ctx, o);
   CK(cudaMemsetAsync(ctx->flags, 0, 4 * sizeof(int), ctx->stream));
   RET(ensure_ytabs(ctx, c.psi));
+  RET(ensure_wcache(ctx));
   // Huber scale of the current state (:713,723,409): normally left by the log-likelihood sweep that scored it
   if (!c.sig_valid) RET(loglik_of(ctx, o, c, ctx->loglik, nullptr, fuse));
   int nfail = 0, nactive = 0;
@@ -295,6 +317,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
       if (P > 1) {  // groups that a part never meets must read as zero
         CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * m * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
+        if (ctx->Wc) CK(cudaMemsetAsync(ctx->SWZ, 0, (size_t)P * Gl * m * 8, ctx->stream));
       }
       // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
       // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
@@ -311,6 +334,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     if (P > 1) {
       const long long nA = (long long)Gl * KK, nu = (long long)Gl * K, nZ = (long long)Gl * m, nV = (long long)Gl * m * K;
       k_sum_parts5<<<nblk(nA + nu + Gl + nZ + nV, 256), 256, 0, ctx->stream>>>(ctx->A, nA, ctx->u, nu, ctx->sw, Gl, ctx->ZS, nZ, ctx->VS, nV, P); CKL();
+      if (ctx->Wc) { k_sum_parts<<<nblk(nZ, 256), 256, 0, ctx->stream>>>(ctx->SWZ, ctx->SWZ, nZ, P); CKL(); }
     }
     KEV_END(1);
   }
@@ -381,16 +405,32 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   {
     KEV_BEGIN(3);
     ctx->launch_parts = P;
-    if (P > 1) {
-      CK(cudaMemsetAsync(ctx->S0, 0, (size_t)P * Gl * m * 8, ctx->stream));
-      CK(cudaMemsetAsync(ctx->S1, 0, (size_t)P * Gl * m * 8, ctx->stream));
-    }
-    int r = split_rows(ctx, hub, [&](const RowGeom& g, bool huber) { return launch_pass2(ctx, huber, g, c, n, kh); });
-    ctx->launch_parts = 1;
-    RET(r);
-    if (P > 1) {
-      const long long nZ = (long long)Gl * m;
-      k_sum_parts5<<<nblk(2 * nZ, 256), 256, 0, ctx->stream>>>(ctx->S0, nZ, ctx->S1, nZ, nullptr, 0, nullptr, 0, nullptr, 0, P); CKL();
+    if (ctx->Wc) {
+      // pass 1 cached every element's weight and the per-group sum w Z: what is left is S0 = sum w and T = sum w W_new per group
+      if (P > 1) {
+        CK(cudaMemsetAsync(ctx->S0, 0, (size_t)P * Gl * m * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
+      }
+      int r = launch_pass2w(ctx, geom(ctx, Gl, nullptr), n);
+      ctx->launch_parts = 1;
+      RET(r);
+      if (P > 1) {
+        const long long nZ = (long long)Gl * m;
+        k_sum_parts5<<<nblk(nZ + nZ * K, 256), 256, 0, ctx->stream>>>(ctx->S0, nZ, ctx->VS, nZ * K, nullptr, 0, nullptr, 0, nullptr, 0, P); CKL();
+      }
+      k_s1_combine<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(Gl, m, K, ctx->SWZ, ctx->VS, n.alpha, ctx->S1); CKL();
+    } else {
+      if (P > 1) {
+        CK(cudaMemsetAsync(ctx->S0, 0, (size_t)P * Gl * m * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->S1, 0, (size_t)P * Gl * m * 8, ctx->stream));
+      }
+      int r = split_rows(ctx, hub, [&](const RowGeom& g, bool huber) { return launch_pass2(ctx, huber, g, c, n, kh); });
+      ctx->launch_parts = 1;
+      RET(r);
+      if (P > 1) {
+        const long long nZ = (long long)Gl * m;
+        k_sum_parts5<<<nblk(2 * nZ, 256), 256, 0, ctx->stream>>>(ctx->S0, nZ, ctx->S1, nZ, nullptr, 0, nullptr, 0, nullptr, 0, P); CKL();
+      }
     }
     KEV_END(3);
   }

@@ -150,6 +150,33 @@ struct GeneRegs {
   __device__ __forceinline__ double logL(double mu) const { return flog(mu + r, mt->rc, mt->lc); }
 };
 
+// ops that take nothing from the counts (they stream another per-element row) declare `static constexpr bool NO_Y = true`
+template <class T, class = void> struct OpNoY { static constexpr bool value = false; };
+template <class T> struct OpNoY<T, decltype((void)T::NO_Y)> { static constexpr bool value = T::NO_Y; };
+
+// a row of per-element doubles ([Np], same positions as the counts) fetched one 128-cell chunk ahead: a lane's two pairs of
+// chunk c sit at c CH + 2 lane and c CH + 64 + 2 lane (the exp(offset) cache of the dispersion sweeps is read the same way)
+struct RowF64 {
+  const double* base; double2 na, nb, hold; int pre_c, c_end;
+  __device__ __forceinline__ void begin(const double* rowbase, int cend) { base = rowbase; pre_c = -1; c_end = cend; }
+  __device__ __forceinline__ double2 get(int c, int ti) {
+    if (ti & 64) return hold;
+    const int lane2 = 2 * (threadIdx.x & 31);
+    double2 cur;
+    if (pre_c == c) { cur = na; hold = nb; }
+    else {
+      cur = __ldcs(reinterpret_cast<const double2*>(base + (long long)c * CH + lane2));
+      hold = __ldcs(reinterpret_cast<const double2*>(base + (long long)c * CH + 64 + lane2));
+    }
+    if (c + 1 < c_end) {
+      na = __ldcs(reinterpret_cast<const double2*>(base + (long long)(c + 1) * CH + lane2));
+      nb = __ldcs(reinterpret_cast<const double2*>(base + (long long)(c + 1) * CH + 64 + lane2));
+      pre_c = c + 1;
+    }
+    return cur;
+  }
+};
+
 // Op interface: row_begin(row, slot), group_begin(j), pair<FULLCHUNK>(y0, y1, chunk, ti, tile, m0, m1) -- two
 // adjacent cells at tile index ti (even), masks m0/m1 false for padding cells (always true when FULLCHUNK) --
 // group_end(j), row_end(row).  Op::PADS: pair() must also see chunks that hold no real cell.
@@ -191,8 +218,9 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   const int* yrow = geo.Yp + (long long)row * geo.Np;
   int* yring = &sh->ybuf[warp][0][0];
   const int c_end = ntiles * SC;
+  constexpr bool NOY = OpNoY<Op>::value;
   if (t0 < ntiles) {
-    if (active) __pipeline_memcpy_async(yring + ((t0 * SC) & 1) * CH + 4 * lane, yrow + (long long)t0 * SC * CH + 4 * lane, 16);
+    if (active && !NOY) __pipeline_memcpy_async(yring + ((t0 * SC) & 1) * CH + 4 * lane, yrow + (long long)t0 * SC * CH + 4 * lane, 16);
     stage_tile<K, NSETS, NW>(smem, sh->wsets, geo.Np, t0, tid, sh->meta[0], geo.chunk_meta);
   }
   for (int t = t0; t < ntiles; ++t) {
@@ -205,10 +233,13 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
 #pragma unroll 1
       for (int sc = 0; sc < SC; ++sc) {
         const int c = t * SC + sc;
-        if (sc > 0) { __pipeline_wait_prior(0); __syncwarp(); }   // the counts of chunk c have landed (all lanes' pieces)
-        const int* yb = yring + (c & 1) * CH;
-        const int2 y01 = *reinterpret_cast<const int2*>(yb + 2 * lane), y23 = *reinterpret_cast<const int2*>(yb + 64 + 2 * lane);
-        if (c + 1 < c_end) { __pipeline_memcpy_async(yring + ((c + 1) & 1) * CH + 4 * lane, yrow + (long long)(c + 1) * CH + 4 * lane, 16); __pipeline_commit(); }
+        int2 y01 = make_int2(0, 0), y23 = y01;
+        if constexpr (!NOY) {
+          if (sc > 0) { __pipeline_wait_prior(0); __syncwarp(); }   // the counts of chunk c have landed (all lanes' pieces)
+          const int* yb = yring + (c & 1) * CH;
+          y01 = *reinterpret_cast<const int2*>(yb + 2 * lane); y23 = *reinterpret_cast<const int2*>(yb + 64 + 2 * lane);
+          if (c + 1 < c_end) { __pipeline_memcpy_async(yring + ((c + 1) & 1) * CH + 4 * lane, yrow + (long long)(c + 1) * CH + 4 * lane, 16); __pipeline_commit(); }
+        }
         const int mcur = mt_[sc];
         const int nv = mcur & 0xff;
         if (nv == 0 && !Op::PADS) continue;
@@ -675,9 +706,11 @@ struct OpPass1 {
   const double* sigma; double kh, khsig; bool hub;
   double A[KK], u[K], sw, gz, V[K];
   double *A_out, *u_out, *sw_out, *ZS, *VS;
+  double *Wc, *SWZ; double* wrow; double gwz; long long Np;   // weight cache [Gl][Np] + per-group sum w Z (pass 2 reads them back), or nullptr
   int row_; int lane;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); row_ = row; lane = threadIdx.x & 31;
+    wrow = Wc ? Wc + (long long)row * Np : nullptr;
 #pragma unroll
     for (int i = 0; i < KK; ++i) A[i] = 0.0;
 #pragma unroll
@@ -688,7 +721,7 @@ struct OpPass1 {
     if (HUBER) { khsig = kh * sigma[row]; hub = !(khsig > 1.79769313486231570e308); }
   }
   __device__ __forceinline__ void group_begin(int j) {
-    g.mbj = g.mb[j]; gz = 0.0;
+    g.mbj = g.mb[j]; gz = 0.0; gwz = 0.0;
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0.0;
   }
@@ -719,6 +752,10 @@ struct OpPass1 {
     }
     if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
     sw += wt0 + wt1; gz += Z0 + Z1;
+    if (wrow) {   // launch-uniform
+      gwz = fma(wt1, Z1, fma(wt0, Z0, gwz));
+      __stcs(reinterpret_cast<double2*>(wrow + (long long)c * CH + (ti & (CH - 1))), make_double2(wt0, wt1));
+    }
     double2 r[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
@@ -735,6 +772,7 @@ struct OpPass1 {
   __device__ __forceinline__ void group_end(int j) {
     double z = warp_sum(gz);
     if (lane == 0) ZS[(long long)row_ * st.m + j] = z;
+    if (wrow) { double q = warp_sum(gwz); if (lane == 0) SWZ[(long long)row_ * st.m + j] = q; }
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       double v = warp_sum(V[i]);
@@ -755,7 +793,7 @@ struct OpPass1 {
 template <int K, bool HUBER, int NW>
 __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
                                                           const double* sigma, double kh, double* A_out, double* u_out,
-                                                          double* sw_out, double* ZS, double* VS) {
+                                                          double* sw_out, double* ZS, double* VS, double* Wc, double* SWZ) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
@@ -764,6 +802,7 @@ __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> 
   OpPass1<K, HUBER> op;
   op.st = st; op.sigma = sigma; op.kh = kh;
   op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
+  op.Wc = Wc; op.SWZ = SWZ ? SWZ + poff * st.m : nullptr; op.Np = geo.Np;
   stream_rows<K, 2, OpPass1<K, HUBER>, NW>(geo, &sh, op, smem);
 }
 
@@ -792,9 +831,11 @@ struct OpLLPass1 {
   // Gram / score / group sums (OpPass1)
   double A[KK], u[K], sw, gz, V[K];
   double *A_out, *u_out, *sw_out, *ZS, *VS;
+  double *Wc, *SWZ; double* wrow; double gwz; long long Np;   // weight cache + per-group sum w Z for pass 2 (as OpPass1), or nullptr
   int row_, lane;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); row_ = row; lane = threadIdx.x & 31;
+    wrow = Wc ? Wc + (long long)row * Np : nullptr;
     acc = 0.0; rlogr = g.r * log(g.r);
     cert = false; c1 = c2 = c3 = 0; hmaxk = 0; k_lo = k_hi = k_wl = k_wh = 0;
     if (fastpath && certc) {
@@ -812,7 +853,7 @@ struct OpLLPass1 {
     sw = 0.0;
   }
   __device__ __forceinline__ void group_begin(int j) {
-    g.mbj = g.mb[j]; gz = 0.0;
+    g.mbj = g.mb[j]; gz = 0.0; gwz = 0.0;
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0.0;
   }
@@ -864,6 +905,10 @@ struct OpLLPass1 {
       double wt0 = s0, wt1 = s1;
       if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
       sw += wt0 + wt1; gz += Z0 + Z1;
+      if (wrow) {   // launch-uniform
+        gwz = fma(wt1, Z1, fma(wt0, Z0, gwz));
+        __stcs(reinterpret_cast<double2*>(wrow + (long long)c * CH + (ti & (CH - 1))), make_double2(wt0, wt1));
+      }
       double2 r[K];
 #pragma unroll
       for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
@@ -881,6 +926,7 @@ struct OpLLPass1 {
   __device__ __forceinline__ void group_end(int j) {
     double z = warp_sum(gz);
     if (lane == 0) ZS[(long long)row_ * st.m + j] = z;
+    if (wrow) { double q = warp_sum(gwz); if (lane == 0) SWZ[(long long)row_ * st.m + j] = q; }
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       double v = warp_sum(V[i]);
@@ -908,7 +954,7 @@ struct OpLLPass1 {
 template <int K, int NW>
 __global__ void __launch_bounds__(NW * 32, 2) k_ll_pass1(RowGeom geo, GeneState<K> st, const double* RMW, double* ll_out /* [nparts][Gl] */,
                                                          const double* hint, int* certc /* [nparts][Gl][4] or nullptr */, int fastpath,
-                                                         double* A_out, double* u_out, double* sw_out, double* ZS, double* VS) {
+                                                         double* A_out, double* u_out, double* sw_out, double* ZS, double* VS, double* Wc, double* SWZ) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
@@ -917,6 +963,7 @@ __global__ void __launch_bounds__(NW * 32, 2) k_ll_pass1(RowGeom geo, GeneState<
   OpLLPass1<K> op;
   op.st = st; op.ll_out = ll_out + poff; op.hint = hint; op.certc = certc ? certc + poff * 4 : nullptr; op.fastpath = fastpath;
   op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
+  op.Wc = Wc; op.SWZ = SWZ ? SWZ + poff * st.m : nullptr; op.Np = geo.Np;
   stream_rows<K, 2, OpLLPass1<K>, NW>(geo, &sh, op, smem);
 }
 
@@ -1561,6 +1608,75 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState
   op.st = st; op.alpha_new = alpha_new; op.sigma = sigma; op.kh = kh;
   op.S0 = S0 + poff * st.m; op.S1 = S1 + poff * st.m;
   stream_rows<K, 2>(geo, &sh, op, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_pass2w: the same group sums from the weight cache.  Pass 1 (or the fused sweep) of this parameter set left every element's
+// weight w = huber x sig.inv x wt.zinb in Wc[g][pos] and the per-group sum w Z in SWZ; what is left for the gmean / Mb update
+// (:405-420) is  S0_j = sum_{c in j} w_c  and  T_j = sum_{c in j} w_c W_new[c, ]  (then S1_j = SWZ_j - alpha_new . T_j): one add
+// and K FMAs per element instead of a second dot product, exp, reciprocal and working response (42 -> 6 FP64 instructions), 8 bytes
+// read per element and no counts at all -- an HBM-bound sweep.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct OpPass2W {
+  static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
+  static constexpr bool NO_Y = true;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
+  GeneRegs<K> g;   // unused apart from the shared-table pointers the skeleton sets
+  const double* Wc; long long Np; int m, c_end;
+  RowF64 wr;
+  double s0, T[K];
+  double *S0, *TS;
+  int row_, lane;
+  __device__ __forceinline__ void row_begin(int row, int) { row_ = row; lane = threadIdx.x & 31; wr.begin(Wc + (long long)row * Np, c_end); }
+  __device__ __forceinline__ void group_begin(int) {
+    s0 = 0.0;
+#pragma unroll
+    for (int l = 0; l < K; ++l) T[l] = 0.0;
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int, int, int c, int ti, const double* tile, bool, bool) {   // (the cached weight of a pad is 0)
+    const double2 w = wr.get(c, ti);
+    s0 += w.x + w.y;
+#pragma unroll
+    for (int l = 0; l < K; ++l) {
+      const double2 v = *reinterpret_cast<const double2*>(tile + l * CELLS + ti);
+      T[l] = fma(w.y, v.y, fma(w.x, v.x, T[l]));
+    }
+  }
+  __device__ __forceinline__ void group_end(int j) {
+    double a = warp_sum(s0);
+    if (lane == 0) S0[(long long)row_ * m + j] = a;
+#pragma unroll
+    for (int l = 0; l < K; ++l) { double v = warp_sum(T[l]); if (lane == 0) TS[((long long)row_ * m + j) * K + l] = v; }
+  }
+  __device__ __forceinline__ void row_end(int) {}
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 3) k_pass2w(RowGeom geo, int m, const double* W_new, const double* Wc, double* S0, double* TS) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = W_new;
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
+  OpPass2W<K> op;
+  op.Wc = Wc; op.Np = geo.Np; op.m = m; op.S0 = S0 + poff * m; op.TS = TS + poff * m * K;
+  {  // the chunks of this CTA's part end where its tiles end (RowF64 must not prefetch beyond them)
+    constexpr int SC = TileCfg<K>::SC;
+    const int ntiles_all = geo.nchunks / SC, tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;
+    const int part = blockIdx.x % geo.nparts;
+    op.c_end = min(ntiles_all, min(ntiles_all, part * tpp) + tpp) * SC;
+  }
+  stream_rows<K, 1>(geo, &sh, op, smem);
+}
+// S1[g][j] = SWZ[g][j] - alpha_new[g] . TS[g][j]  (sum_c w (Z - alpha_new . W_new) regrouped)
+static __global__ void k_s1_combine(int Gl, int m, int K, const double* SWZ, const double* TS, const double* alpha_new, double* S1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Gl * m) return;
+  const long long g = i / m;
+  double s = SWZ[i];
+  for (int l = 0; l < K; ++l) s = fma(-alpha_new[g * K + l], TS[i * K + l], s);
+  S1[i] = s;
 }
 
 // gmean (R/ruvIIInb.R:405-415) and Mb (:418-420, rowWtAvg :667-675) from the group sums.

@@ -8,7 +8,7 @@ int launch_ll_pass1(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s, double*
   const int nw = ctx->opt_llp1_nw == 8 ? 8 : 6;
 #define LLP1_LAUNCH(NW_)                                                                                                    \
   LAUNCH_ROWS_NW((k_ll_pass1<KT, NW_>), NW_, 2, g.nrows, g, gstate<KT>(ctx, s, true), ctx->RMW, out, ctx->hint, ctx->certc, \
-                 fastpath, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS)
+                 fastpath, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, ctx->Wc, ctx->Wc ? ctx->SWZ : nullptr)
   DISPATCH_K(ctx->K, {
     if (nw == 6) LLP1_LAUNCH(6); else LLP1_LAUNCH(8);
   });

@@ -14,6 +14,8 @@ int launch_signdev(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s);
 int launch_pass1(ruvnb_ctx* ctx, bool huber, const RowGeom& g, const StateSet& c, double kh);
 // k_pass2<HUBER>: group sums S0, S1 of `c` against the new alpha / W of `n`                  (sweep_pass2.cu)
 int launch_pass2(ruvnb_ctx* ctx, bool huber, const RowGeom& g, const StateSet& c, const StateSet& n, double kh);
+// k_pass2w: S0 and T = sum w W_new per group from the weight cache ctx->Wc (into ctx->S0 / ctx->VS)     (sweep_pass2.cu)
+int launch_pass2w(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& n);
 // per-cell W update over cells [pb, pe) (fast certificate kernel + exact kernel)             (sweep_w.cu)
 int launch_w_update(ruvnb_ctx* ctx, const ruvnb_opts* o, const CtlPack& cp, const double* p_psi, const StateSet& c, StateSet& n,
                     double kh, long long pb, long long pe);

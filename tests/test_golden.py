@@ -126,3 +126,29 @@ def test_cuda_matches_residual_golden():
     assert np.abs(pearson - g["pearson"]).max() <= 1e-10 * np.abs(g["pearson"]).max()
     assert np.allclose(logc, g["logcounts"], rtol=1e-12, atol=1e-14)
     assert (pac != g["pac"]).sum() <= 1              # a quantile-boundary tie at most (12 000 entries)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_midsize_fit_with_live_dispersion():
+    """Mid-size whole fit (2000 genes x 10000 cells, k = 5, m = 50) with the dispersion ESTIMATED at every psi refresh on both sides
+    (robust estimateDisp.par), against the oracle's frozen run (tests/golden/make_midsize_fit.py, ~20 min of NumPy): the same
+    accept / halve decisions for all 14 inner iterations of its 3 outer iterations, 1e-6 (north_star) on the log-likelihood trace
+    and on W, alpha, gmean, Mb, psi.  The trace also documents how the reference ends: after the last psi refresh every step is
+    rejected three times (R/ruvIIInb.R:486-509), the restored state is force-accepted, logl.outer repeats its value and the outer
+    loop stops -- the zero-progress last outer iteration seen at BASELINE config 2 is the reference's own behaviour."""
+    from ruviiinb_b200 import _lib, synth
+    g = _load("midsize_fit_k5_m50.npz")
+    G, N, k, m, n_ctl, seed, mu, sd = g["case"]
+    Y, M, ctl, truth = synth.make_counts(int(G), int(N), int(k), int(m), int(n_ctl), seed=int(seed), gmean_mu=float(mu), gmean_sd=float(sd))
+    opts = _lib.default_opts(k=int(k))
+    with _lib.Context(0) as ctx:
+        ctx.set_design(int(G), int(N), truth["grp"], ctl)
+        ctx.upload_counts(Y)
+        logl, recs, stats = ctx.fit_nb(opts, W0=g["W0"])
+        got = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
+    dec = np.array([(r["outer"], r["iter"], r["degener"], r["accepted"]) for r in recs], dtype=np.int32)
+    assert np.array_equal(dec, g["decisions"]), (dec.T, g["decisions"].T)
+    assert np.allclose([r["logl_new"] for r in recs], g["logl_new"], rtol=1e-6, atol=0)
+    assert np.allclose(logl, g["logl"], rtol=1e-6, atol=0) and logl[-1] == logl[-2]
+    for n, key in (("W", "W"), ("alpha", "a"), ("gmean", "gmean"), ("Mb", "Mb"), ("psi", "psi")):
+        assert _rel(got[n], g[key], 1e-6) < 1e-6, n
