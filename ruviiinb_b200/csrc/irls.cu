@@ -5,6 +5,7 @@
 
 // the fused log-likelihood + Gram sweep applies to plain NB fits with the default Huber constant (robust = TRUE makes
 // every Huber weight live, ZINB needs the general instantiation): see kernels.cuh k_ll_pass1
+static int ensure_wcache(ruvnb_ctx* ctx);
 static bool fuse_ok(const ruvnb_ctx* ctx, const ruvnb_opts* o) {
   return o->huber_fastpath && !o->robust && !ctx->zinb_on && !ctx->opt_no_fuse;
 }
@@ -22,7 +23,7 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
   const double kh = o->robust ? 1.345 : 100.0;  // :155
   const int Gl = ctx->Gl, P = ctx->nparts;
   RET(ensure_ytabs(ctx, s.psi));
-  if (with_p1) RET(make_rmw(ctx, s.W));
+  if (with_p1) { RET(ensure_wcache(ctx)); RET(make_rmw(ctx, s.W)); }   // (the cache must exist before the first sweep that fills it)
   KEV_BEGIN(4);
   ctx->launch_parts = P;
   int r;
@@ -550,6 +551,7 @@ int ruvnb_restore_best(ruvnb_ctx* ctx) {
   if (!ctx || ctx->K == 0) return RUVNB_EARG;
   CK(cudaSetDevice(ctx->device));
   RET(copy_set(ctx, ctx->cur, ctx->best));
+  ctx->psi_ver++;   // the restored psi may differ from the one the count tables were built from (set_state / estimate_disp in between)
   // "revert zinb weight" (:494-504): the weights are recomputed from the restored parameters with the CURRENT psi
   if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
