@@ -471,7 +471,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sweep_bytes = {"devstats": 4.0 * Gl * N, "pass1": 4.0 * Gl * N, "pass2": 4.0 * Gl * N, "loglik": 4.0 * Gl * N,
-                   "w_update": 4.0 * n_ctl * N / world, "exact_mad": 0.0}
+                   "w_update": 4.0 * n_ctl * N / world, "exact_mad": 0.0, "gram": 16.0 * Gl * N}
     kern = {}
     for name, (tot, cnt) in ktimes.items():
         if cnt:

@@ -111,6 +111,8 @@ struct ruvnb_ctx {
   double* Wc = nullptr;      // [Gl][Np] weight cache: huber x sig.inv x wt.zinb of every element, written by pass 1 / the fused sweep and
   bool Wc_tried = false;     //   read back by pass 2 (kernels.cuh k_pass2w); taken when HBM has the room, RUVNB_NO_WCACHE=1 turns it off
   double* SWZ = nullptr;     // [nparts][Gl][m] per-group sum w Z of the same sweep
+  double* S0c = nullptr;     // [nparts][Gl][m] per-group sum w of the same sweep (own buffer: ctx->S0 is scratch of other operators)
+  double* WZc = nullptr;     // [Gl][Np] w Z of every element: the fused sweep's second slab (k_ll_w -> k_gram), allocated with Wc
   double* D = nullptr; long long D_rows = 0;  // exact-MAD scratch [D_rows][Np]
   double* rowmax = nullptr; int* rownan = nullptr;  // per scratch slot: max|d|, NaN flag
   double* hint = nullptr;        // [Gl][3] certificate hints lo, hi, tg (k_row_sigma -> k_loglik)

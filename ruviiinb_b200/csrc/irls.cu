@@ -4,10 +4,12 @@
 #include "zinb.cuh"
 
 // the fused log-likelihood + Gram sweep applies to plain NB fits with the default Huber constant (robust = TRUE makes
-// every Huber weight live, ZINB needs the general instantiation): see kernels.cuh k_ll_pass1
+// every Huber weight live, ZINB needs the general instantiation) when the two slabs fit in HBM: see kernels.cuh k_ll_w / k_gram
 static int ensure_wcache(ruvnb_ctx* ctx);
-static bool fuse_ok(const ruvnb_ctx* ctx, const ruvnb_opts* o) {
-  return o->huber_fastpath && !o->robust && !ctx->zinb_on && !ctx->opt_no_fuse;
+static bool fuse_ok(ruvnb_ctx* ctx, const ruvnb_opts* o) {
+  if (!(o->huber_fastpath && !o->robust && !ctx->zinb_on && !ctx->opt_no_fuse)) return false;
+  if (ensure_wcache(ctx) != RUVNB_OK) return false;
+  return ctx->Wc && ctx->WZc;
 }
 // [Sum l | bad_Mb | nan_Mb] of this rank into scal[0..2] (one all-reduce carries the three)
 static __global__ void k_pack_fin(double* scal, const int* flags) {
@@ -16,14 +18,15 @@ static __global__ void k_pack_fin(double* scal, const int* flags) {
 
 // per-gene log-likelihood of parameter set `s` into `out` (R/ruvIIInb.R:276-291) and, in the same sweep, the
 // Huber certificate of `s` (s.sigma: +Inf certified / 0 to be evaluated exactly; the rows left at 0 are listed in
-// ctx->faillist).  with_p1: the sweep also leaves the Gram / score sums of `s` for the next inner iteration (k_ll_pass1).
+// ctx->faillist).  with_p1: the sweep also leaves the working quantities of `s` in the slabs and k_gram takes the Gram / score /
+// group sums of the next inner iteration from them (k_ll_w + k_gram).
 // total != nullptr: the sum over all genes of all ranks is brought to the host (ONE stream synchronisation, which also
 // brings the number of listed rows and, in fin[0..1], the global counts of problematic / NaN Mb entries).
 static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* out, double* total, bool with_p1 = false, double* fin = nullptr) {
   const double kh = o->robust ? 1.345 : 100.0;  // :155
   const int Gl = ctx->Gl, P = ctx->nparts;
   RET(ensure_ytabs(ctx, s.psi));
-  if (with_p1) { RET(ensure_wcache(ctx)); RET(make_rmw(ctx, s.W)); }   // (the cache must exist before the first sweep that fills it)
+  if (with_p1) RET(make_rmw(ctx, s.W));   // (fuse_ok has allocated the slabs)
   KEV_BEGIN(4);
   ctx->launch_parts = P;
   int r;
@@ -31,9 +34,10 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
     if (P > 1) {  // groups that a part never meets must read as zero
       CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
       CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * ctx->m * ctx->K * 8, ctx->stream));
-      if (ctx->Wc) CK(cudaMemsetAsync(ctx->SWZ, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->SWZ, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
+      CK(cudaMemsetAsync(ctx->S0c, 0, (size_t)P * Gl * ctx->m * 8, ctx->stream));
     }
-    r = launch_ll_pass1(ctx, geom(ctx, Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath);
+    r = launch_ll_w(ctx, geom(ctx, Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath);
   } else {
     r = launch_loglik(ctx, geom(ctx, Gl, nullptr), s, P > 1 ? ctx->llparts : out, o->huber_fastpath);
   }
@@ -43,6 +47,14 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
   k_cert_finish<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, P, ctx->certc, ctx->hint, s.sigma, kh, o->huber_fastpath, (long long)ctx->N, ctx->cert_diag);
   CKL();
   KEV_END(4);
+  if (with_p1) {
+    KEV_BEGIN(6);
+    ctx->launch_parts = P;
+    r = launch_gram(ctx, geom(ctx, Gl, nullptr));
+    ctx->launch_parts = 1;
+    RET(r);
+    KEV_END(6);
+  }
   s.sig_valid = true; s.maybe_active = false; s.p1_valid = with_p1; s.nfail = -1;
   if (with_p1) { ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false; s.p1_valid = true; }   // one set of sums
   k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, s.sigma, ctx->faillist, ctx->flags + 4, nullptr);
@@ -269,6 +281,10 @@ static int ensure_wcache(ruvnb_ctx* ctx) {
     if (cudaMalloc(&q, need) == cudaSuccess) {
       ctx->allocs.push_back(q); ctx->Wc = (double*)q;
       RET(dev_alloc(ctx, &ctx->SWZ, (long long)ctx->nparts * ctx->Gl * ctx->m));
+      RET(dev_alloc(ctx, &ctx->S0c, (long long)ctx->nparts * ctx->Gl * ctx->m));
+      // the second slab (w Z) of the fused sweep pair
+      if (fr > 2 * need + reserve && cudaMalloc(&q, need) == cudaSuccess) { ctx->allocs.push_back(q); ctx->WZc = (double*)q; }
+      else cudaGetLastError();
     } else cudaGetLastError();
   }
   return RUVNB_OK;
@@ -318,13 +334,16 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
       if (P > 1) {  // groups that a part never meets must read as zero
         CK(cudaMemsetAsync(ctx->ZS, 0, (size_t)P * Gl * m * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
-        if (ctx->Wc) CK(cudaMemsetAsync(ctx->SWZ, 0, (size_t)P * Gl * m * 8, ctx->stream));
+        if (ctx->Wc) {
+          CK(cudaMemsetAsync(ctx->SWZ, 0, (size_t)P * Gl * m * 8, ctx->stream));
+          CK(cudaMemsetAsync(ctx->S0c, 0, (size_t)P * Gl * m * 8, ctx->stream));
+        }
       }
       // certified rows (sigma = +Inf: every Huber weight is 1) take the lean instantiation, the others the general one;
       // the two lists and their lengths stay on the device (no host round trip), idle CTAs exit at once
       r = split_rows(ctx, hub, [&](const RowGeom& g, bool huber) { return launch_pass1(ctx, huber, g, c, kh); });
     } else if (hub) {
-      // the sums came with the sweep that scored this state (k_ll_pass1, unit Huber weights; ctx->RMW is that of c.W);
+      // the sums came with the sweep pair that scored this state (k_ll_w + k_gram, unit Huber weights; ctx->RMW is that of c.W);
       // only the rows whose weights turned out to be live are redone
       RowGeom gf = geom(ctx, Gl, ctx->list_fin); gf.nrows_dev = ctx->part_counts + 1;
       r = launch_pass1(ctx, true, gf, c, kh);
@@ -335,7 +354,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     if (P > 1) {
       const long long nA = (long long)Gl * KK, nu = (long long)Gl * K, nZ = (long long)Gl * m, nV = (long long)Gl * m * K;
       k_sum_parts5<<<nblk(nA + nu + Gl + nZ + nV, 256), 256, 0, ctx->stream>>>(ctx->A, nA, ctx->u, nu, ctx->sw, Gl, ctx->ZS, nZ, ctx->VS, nV, P); CKL();
-      if (ctx->Wc) { k_sum_parts<<<nblk(nZ, 256), 256, 0, ctx->stream>>>(ctx->SWZ, ctx->SWZ, nZ, P); CKL(); }
+      if (ctx->Wc) { k_sum_parts5<<<nblk(2 * nZ, 256), 256, 0, ctx->stream>>>(ctx->SWZ, nZ, ctx->S0c, nZ, nullptr, 0, nullptr, 0, nullptr, 0, P); CKL(); }
     }
     KEV_END(1);
   }
@@ -407,17 +426,14 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     KEV_BEGIN(3);
     ctx->launch_parts = P;
     if (ctx->Wc) {
-      // pass 1 cached every element's weight and the per-group sum w Z: what is left is S0 = sum w and T = sum w W_new per group
-      if (P > 1) {
-        CK(cudaMemsetAsync(ctx->S0, 0, (size_t)P * Gl * m * 8, ctx->stream));
-        CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
-      }
+      // pass 1 cached every element's weight and left the per-group sums of w and w Z: what is left is T = sum w W_new per group
+      if (P > 1) CK(cudaMemsetAsync(ctx->VS, 0, (size_t)P * Gl * m * K * 8, ctx->stream));
       int r = launch_pass2w(ctx, geom(ctx, Gl, nullptr), n);
       ctx->launch_parts = 1;
       RET(r);
       if (P > 1) {
         const long long nZ = (long long)Gl * m;
-        k_sum_parts5<<<nblk(nZ + nZ * K, 256), 256, 0, ctx->stream>>>(ctx->S0, nZ, ctx->VS, nZ * K, nullptr, 0, nullptr, 0, nullptr, 0, P); CKL();
+        k_sum_parts<<<nblk(nZ * K, 256), 256, 0, ctx->stream>>>(ctx->VS, ctx->VS, nZ * K, P); CKL();
       }
       k_s1_combine<<<nblk((long long)Gl * m, 256), 256, 0, ctx->stream>>>(Gl, m, K, ctx->SWZ, ctx->VS, n.alpha, ctx->S1); CKL();
     } else {
@@ -435,7 +451,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     }
     KEV_END(3);
   }
-  k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
+  k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->Wc ? ctx->S0c : ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
   // "any NA -> the whole Mb reverts" (:424) needs the NaN count of ALL ranks.  NB: it is taken speculatively as this rank's
   // own count; the global count travels with the log-likelihood total, and the tail is redone in the (rare) case they
   // disagree.  ZINB (whose tail holds the Nelder-Mead rounds) settles the count first.

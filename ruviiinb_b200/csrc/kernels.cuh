@@ -706,7 +706,8 @@ struct OpPass1 {
   const double* sigma; double kh, khsig; bool hub;
   double A[KK], u[K], sw, gz, V[K];
   double *A_out, *u_out, *sw_out, *ZS, *VS;
-  double *Wc, *SWZ; double* wrow; double gwz; long long Np;   // weight cache [Gl][Np] + per-group sum w Z (pass 2 reads them back), or nullptr
+  // weight slab [Gl][Np] for k_pass2w + the per-group sums S0 = sum w, SWZ = sum w Z (what k_gram leaves after the fused sweep), or nullptr
+  double *Wc, *S0, *SWZ; double* wrow; double gs0, gwz; long long Np;
   int row_; int lane;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); row_ = row; lane = threadIdx.x & 31;
@@ -721,7 +722,7 @@ struct OpPass1 {
     if (HUBER) { khsig = kh * sigma[row]; hub = !(khsig > 1.79769313486231570e308); }
   }
   __device__ __forceinline__ void group_begin(int j) {
-    g.mbj = g.mb[j]; gz = 0.0; gwz = 0.0;
+    g.mbj = g.mb[j]; gz = 0.0; gs0 = 0.0; gwz = 0.0;
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0.0;
   }
@@ -751,7 +752,7 @@ struct OpPass1 {
       if (m1) wt1 *= g.wz(y1, mu1, pos + 1);
     }
     if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
-    sw += wt0 + wt1; gz += Z0 + Z1;
+    gs0 += wt0 + wt1; gz += Z0 + Z1;
     if (wrow) {   // launch-uniform
       gwz = fma(wt1, Z1, fma(wt0, Z0, gwz));
       __stcs(reinterpret_cast<double2*>(wrow + (long long)c * CH + (ti & (CH - 1))), make_double2(wt0, wt1));
@@ -772,7 +773,11 @@ struct OpPass1 {
   __device__ __forceinline__ void group_end(int j) {
     double z = warp_sum(gz);
     if (lane == 0) ZS[(long long)row_ * st.m + j] = z;
-    if (wrow) { double q = warp_sum(gwz); if (lane == 0) SWZ[(long long)row_ * st.m + j] = q; }
+    sw += gs0;
+    if (wrow) {
+      double a = warp_sum(gs0), q = warp_sum(gwz);
+      if (lane == 0) { S0[(long long)row_ * st.m + j] = a; SWZ[(long long)row_ * st.m + j] = q; }
+    }
 #pragma unroll
     for (int i = 0; i < K; ++i) {
       double v = warp_sum(V[i]);
@@ -793,7 +798,7 @@ struct OpPass1 {
 template <int K, bool HUBER, int NW>
 __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> st, const double* RMW,
                                                           const double* sigma, double kh, double* A_out, double* u_out,
-                                                          double* sw_out, double* ZS, double* VS, double* Wc, double* SWZ) {
+                                                          double* sw_out, double* ZS, double* VS, double* Wc, double* S0, double* SWZ) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
@@ -802,25 +807,28 @@ __global__ void __launch_bounds__(NW * 32, 2) k_pass1(RowGeom geo, GeneState<K> 
   OpPass1<K, HUBER> op;
   op.st = st; op.sigma = sigma; op.kh = kh;
   op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
-  op.Wc = Wc; op.SWZ = SWZ ? SWZ + poff * st.m : nullptr; op.Np = geo.Np;
+  op.Wc = Wc; op.S0 = Wc ? S0 + poff * st.m : nullptr; op.SWZ = Wc ? SWZ + poff * st.m : nullptr; op.Np = geo.Np;
   stream_rows<K, 2, OpPass1<K, HUBER>, NW>(geo, &sh, op, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_ll_pass1: the candidate's log-likelihood sweep (k_loglik, with the Huber certificate counters) FUSED with the Gram /
-// score sweep (k_pass1<HUBER = false>) of the NEXT inner iteration.  Both walk the same row with the same parameter set:
-// when the candidate is accepted (R/ruvIIInb.R:486-516) it becomes the current state, and its lmu, exp(lmu) and
-// sig.inv are exactly what get.coef2 needs one iteration later (:303-354) -- one read of Y, one dot product and one exp
-// per element instead of two.  The pass-1 half is speculative: it assumes (i) the step is accepted -- a rejected
-// candidate is thrown away with its sums -- and (ii) every Huber weight is 1; rows whose certificate fails in this very
-// sweep are redone by k_pass1<HUBER = true> once their exact sigma is known.  The log-likelihood half keeps the arithmetic
-// and the summation order of OpLoglik (same bits as the separate sweep).  NB only (no ZINB).
+// K_ll_w: the candidate's log-likelihood sweep (k_loglik, with the Huber certificate counters) FUSED with the element-wise half
+// of the NEXT inner iteration's get.coef2 (R/ruvIIInb.R:303-354).  Both walk the same row with the same parameter set: when the
+// candidate is accepted (:486-516) it becomes the current state, and its lmu, exp(lmu), sig.inv and working response Z are what
+// the next iteration starts from -- one read of Y, one dot product, one exp per element instead of two.  The sweep leaves, per
+// element, the IRLS weight w (= sig.inv: unit Huber weight) in Wc[g][pos] and w Z in WZc[g][pos], and per group sum Z (ZS).  The
+// reductions that need w, Z and W together run from those two slabs, without counts and without transcendental functions:
+// k_gram (Gram / score / group sums, below) and k_pass2w.  Splitting the sweep this way keeps each kernel's live registers small:
+// with the 27 FP64 accumulators of the Gram in the same kernel as the exp / log arithmetic, 128 registers spilled and 168
+// registers ran 12 warps per SM at 31 % of the FP64 pipe.
+// Speculative in two ways: (i) a rejected candidate is thrown away with its slabs, (ii) every Huber weight is taken as 1; rows
+// whose certificate fails in this very sweep are rewritten by k_pass1<HUBER = true> once their exact sigma is known.  The
+// log-likelihood half keeps the arithmetic and the summation order of OpLoglik (same bits as the separate sweep).  NB only.
 // ------------------------------------------------------------------------------------------------
 template <int K>
-struct OpLLPass1 {
+struct OpLLW {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
-  static constexpr int KK = K * (K + 1) / 2;
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
   GeneRegs<K> g;
@@ -828,14 +836,12 @@ struct OpLLPass1 {
   double acc, rlogr;
   double* ll_out; const double* hint; int* certc; int fastpath;
   int k_lo, k_hi, k_wl, k_wh, hmaxk, c1, c2, c3; bool cert;
-  // Gram / score / group sums (OpPass1)
-  double A[KK], u[K], sw, gz, V[K];
-  double *A_out, *u_out, *sw_out, *ZS, *VS;
-  double *Wc, *SWZ; double* wrow; double gwz; long long Np;   // weight cache + per-group sum w Z for pass 2 (as OpPass1), or nullptr
+  // element-wise working quantities -> slabs
+  double *Wc, *WZc, *ZS; double *wrow, *zrow; double gz; long long Np;
   int row_, lane;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row); row_ = row; lane = threadIdx.x & 31;
-    wrow = Wc ? Wc + (long long)row * Np : nullptr;
+    wrow = Wc + (long long)row * Np; zrow = WZc + (long long)row * Np;
     acc = 0.0; rlogr = g.r * log(g.r);
     cert = false; c1 = c2 = c3 = 0; hmaxk = 0; k_lo = k_hi = k_wl = k_wh = 0;
     if (fastpath && certc) {
@@ -846,17 +852,8 @@ struct OpLLPass1 {
         k_wl = OpLoglik<K>::okey(u_of_d(lo - tg)); k_wh = OpLoglik<K>::okey(u_of_d(hi + tg));
       }
     }
-#pragma unroll
-    for (int i = 0; i < KK; ++i) A[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < K; ++i) u[i] = 0.0;
-    sw = 0.0;
   }
-  __device__ __forceinline__ void group_begin(int j) {
-    g.mbj = g.mb[j]; gz = 0.0; gwz = 0.0;
-#pragma unroll
-    for (int i = 0; i < K; ++i) V[i] = 0.0;
-  }
+  __device__ __forceinline__ void group_begin(int j) { g.mbj = g.mb[j]; gz = 0.0; }
   __device__ __forceinline__ void count(double h, double yd, double mu, bool m) {   // OpLoglik::count
     const int hi = __double2hiint(h);
     const int kraw = m ? (hi & 0x7fffffff) : 0;
@@ -883,66 +880,115 @@ struct OpLLPass1 {
     double l0, l1;
     g.lmu_pair(tile, ti, l0, l1);
     const bool fr = g.fast_range(l0, l1);
-    {   // both cells interleaved (as OpPass1::pair; measured: one cell after the other costs 45 % more, 32.7 vs 22.3 ms at cfg 2)
-      const double* rw = tile + K * CELLS;
-      const double yd0 = (double)y0, yd1 = (double)y1;
-      double mu0, s0, q0, mu1, s1, q1;
-      if (fr) {
-        nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &s0, &q0);
-        nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &s1, &q1);
-      } else {
-        SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
-        mu0 = a.mu; s0 = a.s; q0 = a.q; mu1 = b.mu; s1 = b.s; q1 = b.q;
-      }
-      if (FULLCHUNK && fr && (unsigned)(y0 | y1) < (unsigned)YT) {
-        ll_fast(y0, yd0, l0, mu0);
-        ll_fast(y1, yd1, l1, mu1);
-      } else {
-        if (m0) ll_gen(y0, yd0, l0);
-        if (m1) ll_gen(y1, yd1, l1);
-      }
-      double Z0 = fma(g.step, q0 - 1.0, l0), Z1 = fma(g.step, q1 - 1.0, l1);
-      double wt0 = s0, wt1 = s1;
-      if (!FULLCHUNK) { wt0 = m0 ? wt0 : 0.0; Z0 = m0 ? Z0 : 0.0; wt1 = m1 ? wt1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
-      sw += wt0 + wt1; gz += Z0 + Z1;
-      if (wrow) {   // launch-uniform
-        gwz = fma(wt1, Z1, fma(wt0, Z0, gwz));
-        __stcs(reinterpret_cast<double2*>(wrow + (long long)c * CH + (ti & (CH - 1))), make_double2(wt0, wt1));
-      }
-      double2 r[K];
-#pragma unroll
-      for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(rw + i * CELLS + ti);
-      int idx = 0;
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        double wi0 = wt0 * r[i].x, wi1 = wt1 * r[i].y;
-        V[i] += wi0 + wi1;
-        u[i] = fma(wi1, Z1, fma(wi0, Z0, u[i]));
-#pragma unroll
-        for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi1, r[jx].y, fma(wi0, r[jx].x, A[idx])); ++idx; }
-      }
+    const double yd0 = (double)y0, yd1 = (double)y1;
+    double mu0, s0, q0, mu1, s1, q1;
+    if (fr) {
+      nb_sq_fast(yd0, l0, g.psi, g.mt->ex, &mu0, &s0, &q0);
+      nb_sq_fast(yd1, l1, g.psi, g.mt->ex, &mu1, &s1, &q1);
+    } else {
+      SQ a = nb_sq_slow(yd0, l0, g.psi), b = nb_sq_slow(yd1, l1, g.psi);
+      mu0 = a.mu; s0 = a.s; q0 = a.q; mu1 = b.mu; s1 = b.s; q1 = b.q;
     }
+    if (FULLCHUNK && fr && (unsigned)(y0 | y1) < (unsigned)YT) {
+      ll_fast(y0, yd0, l0, mu0);
+      ll_fast(y1, yd1, l1, mu1);
+    } else {
+      if (m0) ll_gen(y0, yd0, l0);
+      if (m1) ll_gen(y1, yd1, l1);
+    }
+    double Z0 = fma(g.step, q0 - 1.0, l0), Z1 = fma(g.step, q1 - 1.0, l1);
+    if (!FULLCHUNK) { s0 = m0 ? s0 : 0.0; Z0 = m0 ? Z0 : 0.0; s1 = m1 ? s1 : 0.0; Z1 = m1 ? Z1 : 0.0; }
+    gz += Z0 + Z1;
+    const long long off = (long long)c * CH + (ti & (CH - 1));
+    __stcs(reinterpret_cast<double2*>(wrow + off), make_double2(s0, s1));
+    __stcs(reinterpret_cast<double2*>(zrow + off), make_double2(s0 * Z0, s1 * Z1));
   }
   __device__ __forceinline__ void group_end(int j) {
     double z = warp_sum(gz);
     if (lane == 0) ZS[(long long)row_ * st.m + j] = z;
-    if (wrow) { double q = warp_sum(gwz); if (lane == 0) SWZ[(long long)row_ * st.m + j] = q; }
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-      double v = warp_sum(V[i]);
-      if (lane == 0) VS[((long long)row_ * st.m + j) * K + i] = v;
-    }
   }
   __device__ __forceinline__ void row_end(int row) {
-    {
-      double v = warp_sum(acc);
-      if (lane == 0) ll_out[row] = v;
-      if (certc) {
-        int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
-        const int hk = __reduce_max_sync(FULL, hmaxk);
-        if (lane == 0) { int4 o = make_int4(a1, a2, a3, hk); reinterpret_cast<int4*>(certc)[row] = o; }
-      }
+    double v = warp_sum(acc);
+    if (lane == 0) ll_out[row] = v;
+    if (certc) {
+      int a1 = __reduce_add_sync(FULL, c1), a2 = __reduce_add_sync(FULL, c2), a3 = __reduce_add_sync(FULL, c3);
+      const int hk = __reduce_max_sync(FULL, hmaxk);
+      if (lane == 0) { int4 o = make_int4(a1, a2, a3, hk); reinterpret_cast<int4*>(certc)[row] = o; }
     }
+  }
+};
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_ll_w(RowGeom geo, GeneState<K> st, double* ll_out /* [nparts][Gl] */, const double* hint,
+                                                         int* certc /* [nparts][Gl][4] or nullptr */, int fastpath, double* Wc, double* WZc, double* ZS) {
+  extern __shared__ double smem[];
+  __shared__ RowShared sh;
+  if (threadIdx.x == 0) sh.wsets[0] = st.W;
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;   // part-major partial sums
+  OpLLW<K> op;
+  op.st = st; op.ll_out = ll_out + poff; op.hint = hint; op.certc = certc ? certc + poff * 4 : nullptr; op.fastpath = fastpath;
+  op.Wc = Wc; op.WZc = WZc; op.ZS = ZS + poff * st.m; op.Np = geo.Np;
+  stream_rows<K, 1>(geo, &sh, op, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_gram: get.coef2's weighted Gram / score (R/ruvIIInb.R:712-720) and the group sums of `projection` / rowWtAvg (:328-329,667-675)
+// from the slabs of the element-wise sweep: w (Wc) and w Z (WZc) of every (gene, cell), RM_W from shared-memory tiles.
+// Per gene: A = sum w RM_W RM_W' (K(K+1)/2), u = sum w Z RM_W (K), sw = sum w; per gene and group: VS = sum w RM_W (K),
+// S0 = sum w, SWZ = sum w Z.  16 bytes and K(K+1)/2 + 3K + 2 FP64 instructions per element, no counts, no exp / log.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct OpGram {
+  static constexpr bool PADS = false;
+  static constexpr bool QUAD = false;
+  static constexpr bool NO_Y = true;
+  static constexpr int KK = K * (K + 1) / 2;
+  static constexpr int CELLS = TileCfg<K>::CELLS;
+  GeneRegs<K> g;   // only the shared-table pointers the skeleton sets
+  const double *Wc, *WZc; long long Np; int m, c_end;
+  RowF64 wr, zr;
+  double A[KK], u[K], V[K], sw, s0, swz;
+  double *A_out, *u_out, *sw_out, *VS, *S0, *SWZ;
+  int row_, lane;
+  __device__ __forceinline__ void row_begin(int row, int) {
+    row_ = row; lane = threadIdx.x & 31;
+    wr.begin(Wc + (long long)row * Np, c_end); zr.begin(WZc + (long long)row * Np, c_end);
+#pragma unroll
+    for (int i = 0; i < KK; ++i) A[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) u[i] = 0.0;
+    sw = 0.0;
+  }
+  __device__ __forceinline__ void group_begin(int) {
+    s0 = 0.0; swz = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) V[i] = 0.0;
+  }
+  template <bool FULLCHUNK>
+  __device__ __forceinline__ void pair(int, int, int c, int ti, const double* tile, bool, bool) {   // (the cached weight of a pad is 0)
+    const double2 w = wr.get(c, ti), z = zr.get(c, ti);
+    s0 += w.x + w.y; swz += z.x + z.y;
+    double2 r[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) r[i] = *reinterpret_cast<const double2*>(tile + i * CELLS + ti);
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const double wi0 = w.x * r[i].x, wi1 = w.y * r[i].y;
+      V[i] += wi0 + wi1;
+      u[i] = fma(z.y, r[i].y, fma(z.x, r[i].x, u[i]));
+#pragma unroll
+      for (int jx = 0; jx <= i; ++jx) { A[idx] = fma(wi1, r[jx].y, fma(wi0, r[jx].x, A[idx])); ++idx; }
+    }
+  }
+  __device__ __forceinline__ void group_end(int j) {
+    const long long o = (long long)row_ * m + j;
+    double a = warp_sum(s0), b = warp_sum(swz);
+    if (lane == 0) { S0[o] = a; SWZ[o] = b; }
+    sw += s0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) { double v = warp_sum(V[i]); if (lane == 0) VS[o * K + i] = v; }
+  }
+  __device__ __forceinline__ void row_end(int row) {
 #pragma unroll
     for (int i = 0; i < KK; ++i) { double v = warp_sum(A[i]); if (lane == 0) A_out[(long long)row * KK + i] = v; }
 #pragma unroll
@@ -951,20 +997,24 @@ struct OpLLPass1 {
     if (lane == 0) sw_out[row] = v;
   }
 };
-template <int K, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) k_ll_pass1(RowGeom geo, GeneState<K> st, const double* RMW, double* ll_out /* [nparts][Gl] */,
-                                                         const double* hint, int* certc /* [nparts][Gl][4] or nullptr */, int fastpath,
-                                                         double* A_out, double* u_out, double* sw_out, double* ZS, double* VS, double* Wc, double* SWZ) {
+template <int K>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_gram(RowGeom geo, int m, const double* RMW, const double* Wc, const double* WZc, double* A_out,
+                                                         double* u_out, double* sw_out, double* VS, double* S0, double* SWZ) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
-  if (threadIdx.x == 0) { sh.wsets[0] = st.W; sh.wsets[1] = RMW; }
+  if (threadIdx.x == 0) sh.wsets[0] = RMW;
   constexpr int KK = K * (K + 1) / 2;
-  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;   // part-major partial sums
-  OpLLPass1<K> op;
-  op.st = st; op.ll_out = ll_out + poff; op.hint = hint; op.certc = certc ? certc + poff * 4 : nullptr; op.fastpath = fastpath;
-  op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.ZS = ZS + poff * st.m; op.VS = VS + poff * st.m * K;
-  op.Wc = Wc; op.SWZ = SWZ ? SWZ + poff * st.m : nullptr; op.Np = geo.Np;
-  stream_rows<K, 2, OpLLPass1<K>, NW>(geo, &sh, op, smem);
+  const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
+  OpGram<K> op;
+  op.Wc = Wc; op.WZc = WZc; op.Np = geo.Np; op.m = m;
+  op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.VS = VS + poff * m * K; op.S0 = S0 + poff * m; op.SWZ = SWZ + poff * m;
+  {  // the chunks of this CTA's part end where its tiles end (RowF64 must not prefetch beyond them)
+    constexpr int SC = TileCfg<K>::SC;
+    const int ntiles_all = geo.nchunks / SC, tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;
+    const int part = blockIdx.x % geo.nparts;
+    op.c_end = min(ntiles_all, min(ntiles_all, part * tpp) + tpp) * SC;
+  }
+  stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
 // finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its
@@ -1611,11 +1661,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_pass2w: the same group sums from the weight cache.  Pass 1 (or the fused sweep) of this parameter set left every element's
-// weight w = huber x sig.inv x wt.zinb in Wc[g][pos] and the per-group sum w Z in SWZ; what is left for the gmean / Mb update
-// (:405-420) is  S0_j = sum_{c in j} w_c  and  T_j = sum_{c in j} w_c W_new[c, ]  (then S1_j = SWZ_j - alpha_new . T_j): one add
-// and K FMAs per element instead of a second dot product, exp, reciprocal and working response (42 -> 6 FP64 instructions), 8 bytes
-// read per element and no counts at all -- an HBM-bound sweep.
+// K_pass2w: the group sums of the gmean / Mb update (:405-420) from the weight slab.  The element-wise sweep of this parameter set
+// left every element's weight w = huber x sig.inv x wt.zinb in Wc[g][pos]; k_gram already produced S0_j = sum_{c in j} w_c and
+// SWZ_j = sum w Z; what needs the NEW W is T_j = sum_{c in j} w_c W_new[c, ]  (then S1_j = SWZ_j - alpha_new . T_j): K FMAs per
+// element instead of a second dot product, exp, reciprocal and working response (42 -> 5 FP64 instructions), 8 bytes read per
+// element and no counts at all -- an HBM-bound sweep.
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct OpPass2W {
@@ -1626,19 +1676,17 @@ struct OpPass2W {
   GeneRegs<K> g;   // unused apart from the shared-table pointers the skeleton sets
   const double* Wc; long long Np; int m, c_end;
   RowF64 wr;
-  double s0, T[K];
-  double *S0, *TS;
+  double T[K];
+  double* TS;
   int row_, lane;
   __device__ __forceinline__ void row_begin(int row, int) { row_ = row; lane = threadIdx.x & 31; wr.begin(Wc + (long long)row * Np, c_end); }
   __device__ __forceinline__ void group_begin(int) {
-    s0 = 0.0;
 #pragma unroll
     for (int l = 0; l < K; ++l) T[l] = 0.0;
   }
   template <bool FULLCHUNK>
   __device__ __forceinline__ void pair(int, int, int c, int ti, const double* tile, bool, bool) {   // (the cached weight of a pad is 0)
     const double2 w = wr.get(c, ti);
-    s0 += w.x + w.y;
 #pragma unroll
     for (int l = 0; l < K; ++l) {
       const double2 v = *reinterpret_cast<const double2*>(tile + l * CELLS + ti);
@@ -1646,21 +1694,19 @@ struct OpPass2W {
     }
   }
   __device__ __forceinline__ void group_end(int j) {
-    double a = warp_sum(s0);
-    if (lane == 0) S0[(long long)row_ * m + j] = a;
 #pragma unroll
     for (int l = 0; l < K; ++l) { double v = warp_sum(T[l]); if (lane == 0) TS[((long long)row_ * m + j) * K + l] = v; }
   }
   __device__ __forceinline__ void row_end(int) {}
 };
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS, 3) k_pass2w(RowGeom geo, int m, const double* W_new, const double* Wc, double* S0, double* TS) {
+__global__ void __launch_bounds__(ROW_THREADS, 3) k_pass2w(RowGeom geo, int m, const double* W_new, const double* Wc, double* TS) {
   extern __shared__ double smem[];
   __shared__ RowShared sh;
   if (threadIdx.x == 0) sh.wsets[0] = W_new;
   const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
   OpPass2W<K> op;
-  op.Wc = Wc; op.Np = geo.Np; op.m = m; op.S0 = S0 + poff * m; op.TS = TS + poff * m * K;
+  op.Wc = Wc; op.Np = geo.Np; op.m = m; op.TS = TS + poff * m * K;
   {  // the chunks of this CTA's part end where its tiles end (RowF64 must not prefetch beyond them)
     constexpr int SC = TileCfg<K>::SC;
     const int ntiles_all = geo.nchunks / SC, tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;

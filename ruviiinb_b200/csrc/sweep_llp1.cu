@@ -1,17 +1,20 @@
-// sweep_llp1.cu -- launcher of k_ll_pass1: the candidate's log-likelihood + certificate sweep fused with the next iteration's
-// Gram / score sweep (kernels.cuh); see sweeps.cuh
+// sweep_llp1.cu -- launchers of the fused sweep pair (kernels.cuh): k_ll_w, the candidate's log-likelihood + certificate sweep that
+// also leaves the next iteration's element-wise working quantities in two slabs, and k_gram, the Gram / score / group sums taken
+// from those slabs; see sweeps.cuh
 #include "sweeps.cuh"
 
-// rows per CTA: 6 (168 registers per thread, 12 warps per SM: 22.3 ms per sweep at cfg 2) or 8 (128 registers, 16 warps per SM,
-// spills in the pair loop: 30.3 ms); RUVNB_LLP1_NW=8 selects the latter for A/B runs
-int launch_ll_pass1(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s, double* out, int fastpath) {
-  const int nw = ctx->opt_llp1_nw == 8 ? 8 : 6;
-#define LLP1_LAUNCH(NW_)                                                                                                    \
-  LAUNCH_ROWS_NW((k_ll_pass1<KT, NW_>), NW_, 2, g.nrows, g, gstate<KT>(ctx, s, true), ctx->RMW, out, ctx->hint, ctx->certc, \
-                 fastpath, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, ctx->Wc, ctx->Wc ? ctx->SWZ : nullptr)
+int launch_ll_w(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s, double* out, int fastpath) {
   DISPATCH_K(ctx->K, {
-    if (nw == 6) LLP1_LAUNCH(6); else LLP1_LAUNCH(8);
+    LAUNCH_ROWS((k_ll_w<KT>), 1, g.nrows, g, gstate<KT>(ctx, s, true), out, ctx->hint, ctx->certc, fastpath, ctx->Wc, ctx->WZc, ctx->ZS);
   });
-#undef LLP1_LAUNCH
+  return RUVNB_OK;
+}
+
+int launch_gram(ruvnb_ctx* ctx, const RowGeom& g_) {
+  RowGeom g = g_;
+  g.tabL = nullptr; g.tabR = nullptr; g.lgr = nullptr;   // no count tables in this sweep
+  DISPATCH_K(ctx->K, {
+    LAUNCH_ROWS((k_gram<KT>), 1, g.nrows, g, ctx->m, ctx->RMW, ctx->Wc, ctx->WZc, ctx->A, ctx->u, ctx->sw, ctx->VS, ctx->S0c, ctx->SWZ);
+  });
   return RUVNB_OK;
 }

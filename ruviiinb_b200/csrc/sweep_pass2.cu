@@ -10,14 +10,14 @@ int launch_pass2(ruvnb_ctx* ctx, bool huber, const RowGeom& g, const StateSet& c
   return RUVNB_OK;
 }
 
-// the same group sums from the weight cache of pass 1 (kernels.cuh k_pass2w): S0 -> ctx->S0, T -> ctx->VS (free after k_alpha_finish)
+// T = sum w W_new per group from the weight cache of pass 1 (kernels.cuh k_pass2w) -> ctx->VS (free after k_alpha_finish)
 int launch_pass2w(ruvnb_ctx* ctx, const RowGeom& g_, const StateSet& n) {
   RowGeom g = g_;
   g.tabL = nullptr; g.tabR = nullptr; g.lgr = nullptr;   // no count tables in this sweep
   DISPATCH_K(ctx->K, {
     const size_t smem_ = tile_smem<KT>(1);
     CK(cudaFuncSetAttribute(k_pass2w<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));
-    k_pass2w<KT><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, n.W, ctx->Wc, ctx->S0, ctx->VS);
+    k_pass2w<KT><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, n.W, ctx->Wc, ctx->VS);
     CKL();
   });
   return RUVNB_OK;
