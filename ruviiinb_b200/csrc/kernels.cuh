@@ -325,6 +325,116 @@ __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// slab-streaming skeleton: the same walk (one warp per gene row, NWARP rows per CTA, lock-step tiles, group runs) for ops whose
+// per-element input is not the counts but NSLAB rows of doubles ([Gl][Np] slabs written by an earlier sweep).  Everything comes
+// in through the bulk-copy engine (cp.async.bulk, 1-D TMA) with mbarrier completion: thread 0 fetches the K rows of the next W
+// tile, lane 0 of every warp the next tile-wide segment of its row's slabs (CELLS x 8 bytes each) -- one instruction per 2-4 KB,
+// a whole tile in flight per warp while the current one is summed (16 x more bytes in flight than a chunk of register
+// prefetch, no registers held).  Two ring slots; the CTA barrier that closes a tile releases its slot.
+// Op interface: row_begin(row, slot), group_begin(j), pair<FULLCHUNK>(ti, tile, slab) with slab[q * CELLS + ti] the element of
+// slab q at tile index ti (pads hold the 0 the producing sweep wrote), group_end(j), row_end(row).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(b)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+template <int K, int NSLAB>
+static inline size_t slab_smem() {   // host: dynamic shared memory of a slab-streaming kernel
+  return (size_t)(2 * K + NWARP * 2 * NSLAB) * TileCfg<K>::CELLS * sizeof(double) + (2 + NWARP * 2) * sizeof(uint64_t);
+}
+template <int K, int NSLAB, class Op>
+__device__ __forceinline__ void stream_slabs(const RowGeom& geo, const double* wset, const double* const (&slabs)[NSLAB], Op& op, double* smem) {
+  constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS, TILE = K * CELLS, SLOT = NSLAB * CELLS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int part = blockIdx.x % geo.nparts, rblk = blockIdx.x / geo.nparts;
+  const int slot = rblk * NWARP + warp;
+  const int nrows = geo.nrows_dev ? min(geo.nrows, *geo.nrows_dev) : geo.nrows;
+  if (rblk * NWARP >= nrows) return;
+  const bool active = slot < nrows;
+  const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
+  double* tiles = smem;                                        // [2][K][CELLS]
+  double* ring = smem + 2 * TILE + (size_t)warp * 2 * SLOT;    // this warp: [2][NSLAB][CELLS]
+  uint64_t* tile_bar = reinterpret_cast<uint64_t*>(smem + 2 * TILE + (size_t)NWARP * 2 * SLOT);
+  uint64_t* slab_bar = tile_bar + 2 + warp * 2;
+  if (tid == 0) {
+    mbar_init(tile_bar, 1); mbar_init(tile_bar + 1, 1);
+    for (int w = 0; w < NWARP; ++w) { mbar_init(tile_bar + 2 + 2 * w, 1); mbar_init(tile_bar + 3 + 2 * w, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (active) op.row_begin(row, slot);
+  const int ntiles_all = geo.nchunks / SC;
+  const int tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;
+  const int t0 = min(ntiles_all, part * tpp), ntiles = min(ntiles_all, t0 + tpp);
+  const double* srow[NSLAB];
+#pragma unroll
+  for (int q = 0; q < NSLAB; ++q) srow[q] = slabs[q] + (long long)row * geo.Np;
+  auto issue = [&](int t, int s) {
+    if (tid == 0) {
+      mbar_expect_tx(tile_bar + s, (uint32_t)(TILE * sizeof(double)));
+#pragma unroll
+      for (int l = 0; l < K; ++l) bulk_g2s(tiles + s * TILE + l * CELLS, wset + (long long)l * geo.Np + (long long)t * CELLS, CELLS * sizeof(double), tile_bar + s);
+    }
+    if (active && lane == 0) {
+      mbar_expect_tx(slab_bar + s, (uint32_t)(SLOT * sizeof(double)));
+#pragma unroll
+      for (int q = 0; q < NSLAB; ++q) bulk_g2s(ring + s * SLOT + q * CELLS, srow[q] + (long long)t * CELLS, CELLS * sizeof(double), slab_bar + s);
+    }
+  };
+  if (t0 < ntiles) issue(t0, 0);
+  int curj = -1;
+  for (int t = t0; t < ntiles; ++t) {
+    const int i = t - t0, s = i & 1;
+    const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+    if (t + 1 < ntiles) issue(t + 1, s ^ 1);   // slot s ^ 1 was released by the barrier that closed tile t - 1
+    mbar_wait(tile_bar + s, ph);
+    if (active) {
+      mbar_wait(slab_bar + s, ph);
+      const double* tile = tiles + s * TILE;
+      const double* slab = ring + s * SLOT;
+#pragma unroll 1
+      for (int sc = 0; sc < SC; ++sc) {
+        const int mcur = __ldg(geo.chunk_meta + t * SC + sc);
+        const int nv = mcur & 0xff;
+        if (nv == 0) continue;
+        const int j = mcur >> 8;
+        if (j != curj) {
+          if (curj >= 0) op.group_end(curj);
+          curj = j;
+          op.group_begin(j);
+        }
+        const int ti = sc * CH + 2 * lane;
+        op.pair(ti, tile, slab);
+        op.pair(ti + 64, tile, slab);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    if (curj >= 0) op.group_end(curj);
+    op.row_end(row);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K_build_ytabs: per-gene count tables (rebuilt whenever psi changes -- once per outer iteration):
 //   tabL[y] = lgamma(y+r) - lgamma(r) - lgamma(y+1) = sum_{j<y} [log(r+j) - log(j+1)]   (no cancellation)
 //   tabR[y] = log(y + r),  lgr = lgamma(r).   One CTA of YT threads per gene.
@@ -938,20 +1048,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_ll_w(RowGeom geo, GeneState<
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct OpGram {
-  static constexpr bool PADS = false;
-  static constexpr bool QUAD = false;
-  static constexpr bool NO_Y = true;
   static constexpr int KK = K * (K + 1) / 2;
   static constexpr int CELLS = TileCfg<K>::CELLS;
-  GeneRegs<K> g;   // only the shared-table pointers the skeleton sets
-  const double *Wc, *WZc; long long Np; int m, c_end;
-  RowF64 wr, zr;
+  int m;
   double A[KK], u[K], V[K], sw, s0, swz;
   double *A_out, *u_out, *sw_out, *VS, *S0, *SWZ;
   int row_, lane;
   __device__ __forceinline__ void row_begin(int row, int) {
     row_ = row; lane = threadIdx.x & 31;
-    wr.begin(Wc + (long long)row * Np, c_end); zr.begin(WZc + (long long)row * Np, c_end);
 #pragma unroll
     for (int i = 0; i < KK; ++i) A[i] = 0.0;
 #pragma unroll
@@ -963,9 +1067,8 @@ struct OpGram {
 #pragma unroll
     for (int i = 0; i < K; ++i) V[i] = 0.0;
   }
-  template <bool FULLCHUNK>
-  __device__ __forceinline__ void pair(int, int, int c, int ti, const double* tile, bool, bool) {   // (the cached weight of a pad is 0)
-    const double2 w = wr.get(c, ti), z = zr.get(c, ti);
+  __device__ __forceinline__ void pair(int ti, const double* tile, const double* slab) {   // slab 0: w, slab 1: w Z (pads hold 0)
+    const double2 w = *reinterpret_cast<const double2*>(slab + ti), z = *reinterpret_cast<const double2*>(slab + CELLS + ti);
     s0 += w.x + w.y; swz += z.x + z.y;
     double2 r[K];
 #pragma unroll
@@ -997,24 +1100,18 @@ struct OpGram {
     if (lane == 0) sw_out[row] = v;
   }
 };
+// one CTA per SM: 8 warps, each with a whole tile of both slabs (8 KB at k <= 5) in flight
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS, 2) k_gram(RowGeom geo, int m, const double* RMW, const double* Wc, const double* WZc, double* A_out,
+__global__ void __launch_bounds__(ROW_THREADS, 1) k_gram(RowGeom geo, int m, const double* RMW, const double* Wc, const double* WZc, double* A_out,
                                                          double* u_out, double* sw_out, double* VS, double* S0, double* SWZ) {
   extern __shared__ double smem[];
-  __shared__ RowShared sh;
-  if (threadIdx.x == 0) sh.wsets[0] = RMW;
   constexpr int KK = K * (K + 1) / 2;
   const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
   OpGram<K> op;
-  op.Wc = Wc; op.WZc = WZc; op.Np = geo.Np; op.m = m;
+  op.m = m;
   op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.VS = VS + poff * m * K; op.S0 = S0 + poff * m; op.SWZ = SWZ + poff * m;
-  {  // the chunks of this CTA's part end where its tiles end (RowF64 must not prefetch beyond them)
-    constexpr int SC = TileCfg<K>::SC;
-    const int ntiles_all = geo.nchunks / SC, tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;
-    const int part = blockIdx.x % geo.nparts;
-    op.c_end = min(ntiles_all, min(ntiles_all, part * tpp) + tpp) * SC;
-  }
-  stream_rows<K, 1>(geo, &sh, op, smem);
+  const double* const slabs[2] = {Wc, WZc};
+  stream_slabs<K, 2>(geo, RMW, slabs, op, smem);
 }
 
 // finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its
@@ -1669,24 +1766,18 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState
 // ------------------------------------------------------------------------------------------------
 template <int K>
 struct OpPass2W {
-  static constexpr bool PADS = false;
-  static constexpr bool QUAD = false;
-  static constexpr bool NO_Y = true;
   static constexpr int CELLS = TileCfg<K>::CELLS;
-  GeneRegs<K> g;   // unused apart from the shared-table pointers the skeleton sets
-  const double* Wc; long long Np; int m, c_end;
-  RowF64 wr;
+  int m;
   double T[K];
   double* TS;
   int row_, lane;
-  __device__ __forceinline__ void row_begin(int row, int) { row_ = row; lane = threadIdx.x & 31; wr.begin(Wc + (long long)row * Np, c_end); }
+  __device__ __forceinline__ void row_begin(int row, int) { row_ = row; lane = threadIdx.x & 31; }
   __device__ __forceinline__ void group_begin(int) {
 #pragma unroll
     for (int l = 0; l < K; ++l) T[l] = 0.0;
   }
-  template <bool FULLCHUNK>
-  __device__ __forceinline__ void pair(int, int, int c, int ti, const double* tile, bool, bool) {   // (the cached weight of a pad is 0)
-    const double2 w = wr.get(c, ti);
+  __device__ __forceinline__ void pair(int ti, const double* tile, const double* slab) {   // (the cached weight of a pad is 0)
+    const double2 w = *reinterpret_cast<const double2*>(slab + ti);
 #pragma unroll
     for (int l = 0; l < K; ++l) {
       const double2 v = *reinterpret_cast<const double2*>(tile + l * CELLS + ti);
@@ -1700,20 +1791,13 @@ struct OpPass2W {
   __device__ __forceinline__ void row_end(int) {}
 };
 template <int K>
-__global__ void __launch_bounds__(ROW_THREADS, 3) k_pass2w(RowGeom geo, int m, const double* W_new, const double* Wc, double* TS) {
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2w(RowGeom geo, int m, const double* W_new, const double* Wc, double* TS) {
   extern __shared__ double smem[];
-  __shared__ RowShared sh;
-  if (threadIdx.x == 0) sh.wsets[0] = W_new;
   const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
   OpPass2W<K> op;
-  op.Wc = Wc; op.Np = geo.Np; op.m = m; op.TS = TS + poff * m * K;
-  {  // the chunks of this CTA's part end where its tiles end (RowF64 must not prefetch beyond them)
-    constexpr int SC = TileCfg<K>::SC;
-    const int ntiles_all = geo.nchunks / SC, tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;
-    const int part = blockIdx.x % geo.nparts;
-    op.c_end = min(ntiles_all, min(ntiles_all, part * tpp) + tpp) * SC;
-  }
-  stream_rows<K, 1>(geo, &sh, op, smem);
+  op.m = m; op.TS = TS + poff * m * K;
+  const double* const slabs[1] = {Wc};
+  stream_slabs<K, 1>(geo, W_new, slabs, op, smem);
 }
 // S1[g][j] = SWZ[g][j] - alpha_new[g] . TS[g][j]  (sum_c w (Z - alpha_new . W_new) regrouped)
 static __global__ void k_s1_combine(int Gl, int m, int K, const double* SWZ, const double* TS, const double* alpha_new, double* S1) {

@@ -14,7 +14,11 @@ int launch_gram(ruvnb_ctx* ctx, const RowGeom& g_) {
   RowGeom g = g_;
   g.tabL = nullptr; g.tabR = nullptr; g.lgr = nullptr;   // no count tables in this sweep
   DISPATCH_K(ctx->K, {
-    LAUNCH_ROWS((k_gram<KT>), 1, g.nrows, g, ctx->m, ctx->RMW, ctx->Wc, ctx->WZc, ctx->A, ctx->u, ctx->sw, ctx->VS, ctx->S0c, ctx->SWZ);
+    const size_t smem_ = slab_smem<KT, 2>();
+    CK(cudaFuncSetAttribute(k_gram<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));
+    k_gram<KT><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, ctx->RMW, ctx->Wc, ctx->WZc, ctx->A, ctx->u, ctx->sw, ctx->VS,
+                                                                                          ctx->S0c, ctx->SWZ);
+    CKL();
   });
   return RUVNB_OK;
 }

@@ -15,7 +15,7 @@ int launch_pass2w(ruvnb_ctx* ctx, const RowGeom& g_, const StateSet& n) {
   RowGeom g = g_;
   g.tabL = nullptr; g.tabR = nullptr; g.lgr = nullptr;   // no count tables in this sweep
   DISPATCH_K(ctx->K, {
-    const size_t smem_ = tile_smem<KT>(1);
+    const size_t smem_ = slab_smem<KT, 1>();
     CK(cudaFuncSetAttribute(k_pass2w<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));
     k_pass2w<KT><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, n.W, ctx->Wc, ctx->VS);
     CKL();
