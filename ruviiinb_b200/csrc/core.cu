@@ -34,7 +34,7 @@ int ruvnb_create(ruvnb_ctx** out, int device) {
   cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&ctx->ev_ctl, cudaEventDisableTiming);
   { const char* e = getenv("RUVNB_NO_FUSE"); ctx->opt_no_fuse = e && *e && *e != '0'; }
-  { const char* e = getenv("RUVNB_LLP1_NW"); ctx->opt_llp1_nw = e ? atoi(e) : 0; }
+  { const char* e = getenv("RUVNB_SLAB_CFG"); ctx->opt_slab_cfg = e ? atoi(e) : 0; }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;
   return RUVNB_OK;

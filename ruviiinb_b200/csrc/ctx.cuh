@@ -180,7 +180,7 @@ struct ruvnb_ctx {
   cudaEvent_t ev_ctl = nullptr;  // the control-gene parameter exchange on the side stream has finished
   // switches read once from the environment (tuning / A-B measurements)
   bool opt_no_fuse = false;  // RUVNB_NO_FUSE=1: separate log-likelihood and Gram sweeps (three Y sweeps per iteration)
-  int opt_llp1_nw = 0;       // RUVNB_LLP1_NW=6|8: rows per CTA of the fused sweep
+  int opt_slab_cfg = 0;      // RUVNB_SLAB_CFG bit 0: k_gram stage shape B, bit 1: k_pass2w stage shape B (A/B runs)
   // stats of the last iteration
   int last_fail_rows = 0, last_active_rows = 0, last_fail_cells = 0;
   // per-kernel device timing of the sweep kernels (CUDA events on ctx->stream, read at the

@@ -325,14 +325,17 @@ __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// slab-streaming skeleton: the same walk (one warp per gene row, NWARP rows per CTA, lock-step tiles, group runs) for ops whose
-// per-element input is not the counts but NSLAB rows of doubles ([Gl][Np] slabs written by an earlier sweep).  Everything comes
-// in through the bulk-copy engine (cp.async.bulk, 1-D TMA) with mbarrier completion: thread 0 fetches the K rows of the next W
-// tile, lane 0 of every warp the next tile-wide segment of its row's slabs (CELLS x 8 bytes each) -- one instruction per 2-4 KB,
-// a whole tile in flight per warp while the current one is summed (16 x more bytes in flight than a chunk of register
-// prefetch, no registers held).  Two ring slots; the CTA barrier that closes a tile releases its slot.
-// Op interface: row_begin(row, slot), group_begin(j), pair<FULLCHUNK>(ti, tile, slab) with slab[q * CELLS + ti] the element of
-// slab q at tile index ti (pads hold the 0 the producing sweep wrote), group_end(j), row_end(row).
+// slab-streaming skeleton: the same walk (one warp per gene row, NWARP rows per CTA, group runs) for ops whose per-element input
+// is not the counts but NSLAB rows of doubles ([Gl][Np] slabs written by an earlier sweep).  Everything comes in through the
+// bulk-copy engine (cp.async.bulk, 1-D TMA) with mbarrier completion, as a producer / consumer pipeline of D stages of SC
+// chunks: thread 0 fetches the K rows of a W tile (shared by the CTA's rows), lane 0 of every warp the matching segment of its
+// own row's slabs; D - 1 stages are in flight while one is summed, and no register holds a load (the register prefetch of RowF64
+// kept one chunk in flight and cost 12 registers per slab).  A warp releases a W-tile stage by arriving on its `empty` barrier
+// -- there is no CTA-wide barrier inside the row, so the warps of a CTA drift up to D - 1 stages apart.
+// Op interface: row_begin(row, slot), group_begin(j), pair(ti, tile, slab) with slab[q * CELLS + ti] the element of slab q at
+// stage index ti (pads hold the 0 the producing sweep wrote), group_end(j), row_end(row).
+// Measured at cfg 2 (k = 5): k_gram 8.5 ms with RowF64 -> 7.4 ms (512-cell stages, D = 2, CTA barriers, one CTA per SM) -> 6.5 ms
+// (256-cell stages, two CTAs per SM); k_pass2w 4.0 -> 3.55 ms.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -340,6 +343,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
@@ -355,13 +361,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                  : "memory");
   } while (!ok);
 }
-template <int K, int NSLAB>
+template <int SC_, int D_> struct SlabCfg { static constexpr int SC = SC_, D = D_, CELLS = SC_ * CH; };
+template <int K, int NSLAB, class Cfg>
 static inline size_t slab_smem() {   // host: dynamic shared memory of a slab-streaming kernel
-  return (size_t)(2 * K + NWARP * 2 * NSLAB) * TileCfg<K>::CELLS * sizeof(double) + (2 + NWARP * 2) * sizeof(uint64_t);
+  return (size_t)Cfg::D * (K + NWARP * NSLAB) * Cfg::CELLS * sizeof(double) + (size_t)Cfg::D * (2 + NWARP) * sizeof(uint64_t);
 }
-template <int K, int NSLAB, class Op>
+template <int K, int NSLAB, class Cfg, class Op>
 __device__ __forceinline__ void stream_slabs(const RowGeom& geo, const double* wset, const double* const (&slabs)[NSLAB], Op& op, double* smem) {
-  constexpr int SC = TileCfg<K>::SC, CELLS = TileCfg<K>::CELLS, TILE = K * CELLS, SLOT = NSLAB * CELLS;
+  constexpr int SC = Cfg::SC, D = Cfg::D, CELLS = Cfg::CELLS, TILE = K * CELLS, SLOT = NSLAB * CELLS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int part = blockIdx.x % geo.nparts, rblk = blockIdx.x / geo.nparts;
   const int slot = rblk * NWARP + warp;
@@ -369,69 +376,73 @@ __device__ __forceinline__ void stream_slabs(const RowGeom& geo, const double* w
   if (rblk * NWARP >= nrows) return;
   const bool active = slot < nrows;
   const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
-  double* tiles = smem;                                        // [2][K][CELLS]
-  double* ring = smem + 2 * TILE + (size_t)warp * 2 * SLOT;    // this warp: [2][NSLAB][CELLS]
-  uint64_t* tile_bar = reinterpret_cast<uint64_t*>(smem + 2 * TILE + (size_t)NWARP * 2 * SLOT);
-  uint64_t* slab_bar = tile_bar + 2 + warp * 2;
+  double* tiles = smem;                                        // [D][K][CELLS]
+  double* ring = smem + D * TILE + (size_t)warp * D * SLOT;    // this warp: [D][NSLAB][CELLS]
+  uint64_t* tile_full = reinterpret_cast<uint64_t*>(smem + D * TILE + (size_t)NWARP * D * SLOT);
+  uint64_t* tile_empty = tile_full + D;
+  uint64_t* slab_full = tile_empty + D + warp * D;
   if (tid == 0) {
-    mbar_init(tile_bar, 1); mbar_init(tile_bar + 1, 1);
-    for (int w = 0; w < NWARP; ++w) { mbar_init(tile_bar + 2 + 2 * w, 1); mbar_init(tile_bar + 3 + 2 * w, 1); }
+    const int nact = min(NWARP, nrows - rblk * NWARP);   // warps that walk a row (and release the W-tile stages)
+    for (int s = 0; s < D; ++s) { mbar_init(tile_full + s, 1); mbar_init(tile_empty + s, nact); }
+    for (int w = 0; w < NWARP * D; ++w) mbar_init(tile_empty + D + w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (active) op.row_begin(row, slot);
+  if (!active) return;
+  op.row_begin(row, slot);
   const int ntiles_all = geo.nchunks / SC;
   const int tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;
   const int t0 = min(ntiles_all, part * tpp), ntiles = min(ntiles_all, t0 + tpp);
   const double* srow[NSLAB];
 #pragma unroll
   for (int q = 0; q < NSLAB; ++q) srow[q] = slabs[q] + (long long)row * geo.Np;
-  auto issue = [&](int t, int s) {
+  // stage i (tile t0 + i) -> ring slot i % D; its first use needs no `empty` wait
+  auto issue = [&](int i) {
+    const int s = i % D, t = t0 + i;
     if (tid == 0) {
-      mbar_expect_tx(tile_bar + s, (uint32_t)(TILE * sizeof(double)));
+      if (i >= D) mbar_wait(tile_empty + s, (uint32_t)(i / D - 1) & 1u);   // every warp is done with stage i - D
+      mbar_expect_tx(tile_full + s, (uint32_t)(TILE * sizeof(double)));
 #pragma unroll
-      for (int l = 0; l < K; ++l) bulk_g2s(tiles + s * TILE + l * CELLS, wset + (long long)l * geo.Np + (long long)t * CELLS, CELLS * sizeof(double), tile_bar + s);
+      for (int l = 0; l < K; ++l) bulk_g2s(tiles + s * TILE + l * CELLS, wset + (long long)l * geo.Np + (long long)t * CELLS, CELLS * sizeof(double), tile_full + s);
     }
-    if (active && lane == 0) {
-      mbar_expect_tx(slab_bar + s, (uint32_t)(SLOT * sizeof(double)));
+    if (lane == 0) {   // (the warp's own lanes left stage i - D at the __syncwarp that closed it)
+      mbar_expect_tx(slab_full + s, (uint32_t)(SLOT * sizeof(double)));
 #pragma unroll
-      for (int q = 0; q < NSLAB; ++q) bulk_g2s(ring + s * SLOT + q * CELLS, srow[q] + (long long)t * CELLS, CELLS * sizeof(double), slab_bar + s);
+      for (int q = 0; q < NSLAB; ++q) bulk_g2s(ring + s * SLOT + q * CELLS, srow[q] + (long long)t * CELLS, CELLS * sizeof(double), slab_full + s);
     }
   };
-  if (t0 < ntiles) issue(t0, 0);
+  const int nst = ntiles - t0;
+  for (int i = 0; i < D - 1 && i < nst; ++i) issue(i);
   int curj = -1;
-  for (int t = t0; t < ntiles; ++t) {
-    const int i = t - t0, s = i & 1;
-    const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-    if (t + 1 < ntiles) issue(t + 1, s ^ 1);   // slot s ^ 1 was released by the barrier that closed tile t - 1
-    mbar_wait(tile_bar + s, ph);
-    if (active) {
-      mbar_wait(slab_bar + s, ph);
-      const double* tile = tiles + s * TILE;
-      const double* slab = ring + s * SLOT;
-#pragma unroll 1
-      for (int sc = 0; sc < SC; ++sc) {
-        const int mcur = __ldg(geo.chunk_meta + t * SC + sc);
-        const int nv = mcur & 0xff;
-        if (nv == 0) continue;
-        const int j = mcur >> 8;
-        if (j != curj) {
-          if (curj >= 0) op.group_end(curj);
-          curj = j;
-          op.group_begin(j);
-        }
-        const int ti = sc * CH + 2 * lane;
-        op.pair(ti, tile, slab);
-        op.pair(ti + 64, tile, slab);
+  for (int i = 0; i < nst; ++i) {
+    const int s = i % D;
+    const uint32_t ph = (uint32_t)(i / D) & 1u;
+    if (i + D - 1 < nst) issue(i + D - 1);
+    mbar_wait(tile_full + s, ph);
+    mbar_wait(slab_full + s, ph);
+    const double* tile = tiles + s * TILE;
+    const double* slab = ring + s * SLOT;
+#pragma unroll
+    for (int sc = 0; sc < SC; ++sc) {
+      const int mcur = __ldg(geo.chunk_meta + (t0 + i) * SC + sc);
+      const int nv = mcur & 0xff;
+      if (nv == 0) continue;
+      const int j = mcur >> 8;
+      if (j != curj) {
+        if (curj >= 0) op.group_end(curj);
+        curj = j;
+        op.group_begin(j);
       }
+      const int ti = sc * CH + 2 * lane;
+      op.pair(ti, tile, slab);
+      op.pair(ti + 64, tile, slab);
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tile_empty + s);
   }
-  if (active) {
-    if (curj >= 0) op.group_end(curj);
-    op.row_end(row);
-  }
+  if (curj >= 0) op.group_end(curj);
+  op.row_end(row);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1046,10 +1057,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_ll_w(RowGeom geo, GeneState<
 // Per gene: A = sum w RM_W RM_W' (K(K+1)/2), u = sum w Z RM_W (K), sw = sum w; per gene and group: VS = sum w RM_W (K),
 // S0 = sum w, SWZ = sum w Z.  16 bytes and K(K+1)/2 + 3K + 2 FP64 instructions per element, no counts, no exp / log.
 // ------------------------------------------------------------------------------------------------
-template <int K>
+template <int K, class Cfg>
 struct OpGram {
   static constexpr int KK = K * (K + 1) / 2;
-  static constexpr int CELLS = TileCfg<K>::CELLS;
+  static constexpr int CELLS = Cfg::CELLS;
   int m;
   double A[KK], u[K], V[K], sw, s0, swz;
   double *A_out, *u_out, *sw_out, *VS, *S0, *SWZ;
@@ -1100,18 +1111,22 @@ struct OpGram {
     if (lane == 0) sw_out[row] = v;
   }
 };
-// one CTA per SM: 8 warps, each with a whole tile of both slabs (8 KB at k <= 5) in flight
-template <int K>
-__global__ void __launch_bounds__(ROW_THREADS, 1) k_gram(RowGeom geo, int m, const double* RMW, const double* Wc, const double* WZc, double* A_out,
+// stage shapes (RUVNB_SLAB_CFG picks B for A/B runs).  Measured at cfg 2: 128-cell stages 4 deep 7.4 ms, 256-cell stages 3 deep with
+// one CTA per SM 8.3 ms, 256-cell stages 2 deep with CTA barriers 6.5 ms -- the sweep is not short of bytes in flight: FP64 pipe 48 %,
+// shared-memory wavefronts 45 %, DRAM 64 % of peak, so the cheaper stage bookkeeping wins
+using GramCfgA = SlabCfg<2, 2>;   // 256-cell stages, 2 deep: 84 KB at k = 5, two CTAs per SM
+using GramCfgB = SlabCfg<1, 4>;   // 128-cell stages, 4 deep: 84 KB
+template <int K, class Cfg>
+__global__ void __launch_bounds__(ROW_THREADS, 2) k_gram(RowGeom geo, int m, const double* RMW, const double* Wc, const double* WZc, double* A_out,
                                                          double* u_out, double* sw_out, double* VS, double* S0, double* SWZ) {
   extern __shared__ double smem[];
   constexpr int KK = K * (K + 1) / 2;
   const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
-  OpGram<K> op;
+  OpGram<K, Cfg> op;
   op.m = m;
   op.A_out = A_out + poff * KK; op.u_out = u_out + poff * K; op.sw_out = sw_out + poff; op.VS = VS + poff * m * K; op.S0 = S0 + poff * m; op.SWZ = SWZ + poff * m;
   const double* const slabs[2] = {Wc, WZc};
-  stream_slabs<K, 2>(geo, RMW, slabs, op, smem);
+  stream_slabs<K, 2, Cfg>(geo, RMW, slabs, op, smem);
 }
 
 // finish pass 1 per gene: c = RM_W' diag(w) RM_Z with RM_Z = Z - groupmean(Z); normalise w by its
@@ -1764,9 +1779,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2(RowGeom geo, GeneState
 // element instead of a second dot product, exp, reciprocal and working response (42 -> 5 FP64 instructions), 8 bytes read per
 // element and no counts at all -- an HBM-bound sweep.
 // ------------------------------------------------------------------------------------------------
-template <int K>
+template <int K, class Cfg>
 struct OpPass2W {
-  static constexpr int CELLS = TileCfg<K>::CELLS;
+  static constexpr int CELLS = Cfg::CELLS;
   int m;
   double T[K];
   double* TS;
@@ -1790,14 +1805,19 @@ struct OpPass2W {
   }
   __device__ __forceinline__ void row_end(int) {}
 };
-template <int K>
+// Measured at cfg 2: 512-cell stages 2 deep 3.55 ms, 256-cell stages 4 deep 3.84 ms, 128-cell stages 5 deep with three CTAs per SM
+// 4.1 ms.  The limit is the shared-memory pipe (76 % of its wavefront peak): every pair of cells reads 16 bytes of the slab and
+// K x 16 bytes of the W tile back from shared memory, 48 bytes per 8-byte element -- as much time as HBM needs for the element.
+using P2wCfgA = SlabCfg<4, 2>;   // 512-cell stages, 2 deep: 104 KB at k = 5, two CTAs per SM
+using P2wCfgB = SlabCfg<2, 4>;   // 256-cell stages, 4 deep: 104 KB
+template <int K, class Cfg>
 __global__ void __launch_bounds__(ROW_THREADS, 2) k_pass2w(RowGeom geo, int m, const double* W_new, const double* Wc, double* TS) {
   extern __shared__ double smem[];
   const long long poff = (long long)(blockIdx.x % geo.nparts) * geo.Gl;
-  OpPass2W<K> op;
+  OpPass2W<K, Cfg> op;
   op.m = m; op.TS = TS + poff * m * K;
   const double* const slabs[1] = {Wc};
-  stream_slabs<K, 1>(geo, W_new, slabs, op, smem);
+  stream_slabs<K, 1, Cfg>(geo, W_new, slabs, op, smem);
 }
 // S1[g][j] = SWZ[g][j] - alpha_new[g] . TS[g][j]  (sum_c w (Z - alpha_new . W_new) regrouped)
 static __global__ void k_s1_combine(int Gl, int m, int K, const double* SWZ, const double* TS, const double* alpha_new, double* S1) {

@@ -13,12 +13,17 @@ int launch_ll_w(ruvnb_ctx* ctx, const RowGeom& g, const StateSet& s, double* out
 int launch_gram(ruvnb_ctx* ctx, const RowGeom& g_) {
   RowGeom g = g_;
   g.tabL = nullptr; g.tabR = nullptr; g.lgr = nullptr;   // no count tables in this sweep
+#define GRAM_LAUNCH(CFG)                                                                                                           \
+  do {                                                                                                                             \
+    const size_t smem_ = slab_smem<KT, 2, CFG>();                                                                                  \
+    CK(cudaFuncSetAttribute((k_gram<KT, CFG>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));                          \
+    k_gram<KT, CFG><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, ctx->RMW, ctx->Wc, ctx->WZc, ctx->A, \
+                                                                                               ctx->u, ctx->sw, ctx->VS, ctx->S0c, ctx->SWZ);   \
+    CKL();                                                                                                                         \
+  } while (0)
   DISPATCH_K(ctx->K, {
-    const size_t smem_ = slab_smem<KT, 2>();
-    CK(cudaFuncSetAttribute(k_gram<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));
-    k_gram<KT><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, ctx->RMW, ctx->Wc, ctx->WZc, ctx->A, ctx->u, ctx->sw, ctx->VS,
-                                                                                          ctx->S0c, ctx->SWZ);
-    CKL();
+    if (ctx->opt_slab_cfg & 1) GRAM_LAUNCH(GramCfgB); else GRAM_LAUNCH(GramCfgA);
   });
+#undef GRAM_LAUNCH
   return RUVNB_OK;
 }

@@ -14,11 +14,16 @@ int launch_pass2(ruvnb_ctx* ctx, bool huber, const RowGeom& g, const StateSet& c
 int launch_pass2w(ruvnb_ctx* ctx, const RowGeom& g_, const StateSet& n) {
   RowGeom g = g_;
   g.tabL = nullptr; g.tabR = nullptr; g.lgr = nullptr;   // no count tables in this sweep
+#define P2W_LAUNCH(CFG)                                                                                                   \
+  do {                                                                                                                    \
+    const size_t smem_ = slab_smem<KT, 1, CFG>();                                                                         \
+    CK(cudaFuncSetAttribute((k_pass2w<KT, CFG>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));               \
+    k_pass2w<KT, CFG><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, n.W, ctx->Wc, ctx->VS); \
+    CKL();                                                                                                                \
+  } while (0)
   DISPATCH_K(ctx->K, {
-    const size_t smem_ = slab_smem<KT, 1>();
-    CK(cudaFuncSetAttribute(k_pass2w<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_));
-    k_pass2w<KT><<<row_grid(g.nrows) * ctx->launch_parts, ROW_THREADS, smem_, ctx->stream>>>(g, ctx->m, n.W, ctx->Wc, ctx->VS);
-    CKL();
+    if (ctx->opt_slab_cfg & 2) P2W_LAUNCH(P2wCfgB); else P2W_LAUNCH(P2wCfgA);
   });
+#undef P2W_LAUNCH
   return RUVNB_OK;
 }
