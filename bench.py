@@ -470,38 +470,48 @@ def main():
         peaks = json.load(open(pk_path))
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    sweep_bytes = {"devstats": 4.0 * Gl * N, "pass1": 4.0 * Gl * N, "pass2": 4.0 * Gl * N, "loglik": 4.0 * Gl * N,
-                   "w_update": 4.0 * n_ctl * N / world, "exact_mad": 0.0, "gram": 16.0 * Gl * N}
+    fused = not os.environ.get("RUVNB_NO_FUSE") and ktimes.get("gram", (0.0, 0))[1] > 0
+    wcache = fused or not os.environ.get("RUVNB_NO_WCACHE")
+    # algorithmic bytes per element of each sweep: counts are int32 (4 B); the fused sweep k_ll_w also WRITES
+    # the two FP64 slabs (w, w Z: 16 B) that k_gram reads back (16 B) and k_pass2w reads half of (8 B) -- W / alpha / Mb are L2-resident
+    per_elt = {"devstats": 4.0, "pass1": 4.0 + (8.0 if wcache else 0.0), "pass2": 8.0 if wcache else 4.0, "loglik": 20.0 if fused else 4.0,
+               "gram": 16.0, "exact_mad": 0.0}
+    sweep_bytes = {n: v * Gl * N for n, v in per_elt.items()}
+    sweep_bytes["w_update"] = 4.0 * n_ctl * N / world
     kern = {}
     for name, (tot, cnt) in ktimes.items():
         if cnt:
             kern[name] = {"ms": tot / cnt, "launches_per_step": cnt / args.steps,
                           "GBps": sweep_bytes[name] / (tot / cnt * 1e-3) / 1e9 if sweep_bytes[name] else None}
     dom = max((n for n in kern if sweep_bytes[n] > 0), key=lambda n: kern[n]["ms"] * kern[n]["launches_per_step"])
-    fused = not os.environ.get("RUVNB_NO_FUSE")
-    label = {"loglik": "ll_pass1 (log-likelihood + certificate fused with the next iteration's Gram/score sweep)" if fused else "loglik"}
-    # measured DRAM traffic of the dominant kernel (ncu --set full, profiles/traffic.json: bytes per launch over ALL G rows of the
-    # workload), scaled to the rows this rank's launch walks
+    label = {"loglik": "k_ll_w (log-likelihood + certificate + the next iteration's element-wise working quantities -> two slabs)" if fused else "k_loglik",
+             "gram": "k_gram (Gram / score / group sums from the slabs)", "pass2": "k_pass2w (group sums of w W_new from the weight slab)" if wcache else "k_pass2",
+             "pass1": "k_pass1", "w_update": "k_w_update_fast", "exact_mad": "k_signdev + k_row_sigma"}
+    key = {"loglik": "ll_w" if fused else "loglik", "pass2": "pass2w" if wcache else "pass2"}.get(dom, dom)
+    # measured DRAM traffic of the dominant kernel (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per element of the
+    # captured launch, profiles/traffic.json), scaled to the elements this rank's launch walks
     traffic, traffic_src = None, None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    key = ("ll_pass1" if fused else "loglik") if dom == "loglik" else dom
     if os.path.exists(tr_path):
         tr = json.load(open(tr_path))
-        full = tr.get(args.workload, {}).get(key)
-        if full is not None:
-            traffic = full * Gl / G
+        bpe = tr.get("bytes_per_element", {}).get(key)
+        if bpe is not None:
+            traffic = bpe * Gl * N
             traffic_src = tr.get("source")
     instr, instr_src = fp64_instr_table()
     ipe = instr.get(key)
+    step_bytes = sum(sweep_bytes[n] * kern[n]["launches_per_step"] for n in kern if sweep_bytes[n])
     roofline = {"bound": "hbm", "kernel": label.get(dom, dom), "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["GBps"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": sweep_bytes[dom],
-                "note": "FP64-pipe-bound sweep (DESIGN.md section 5): the HBM budget is ~11 FP64 instructions per element",
+                "algorithmic_bytes_per_launch": sweep_bytes[dom], "algorithmic_bytes_per_element": per_elt.get(dom),
+                "note": "the dominant sweep is bound by the FP64 pipe, not by HBM (DESIGN.md section 5): see the fp64 block; k_gram and k_pass2w are the HBM-bound sweeps",
                 "fp64": {"peak_tflops_measured": fp64_peak, "instr_per_element": ipe, "instr_source": instr_src,
                          "achieved_tflops": (2.0 * ipe * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12) if ipe else None,
                          "frac": (2.0 * ipe * Gl * N / (kern[dom]["ms"] * 1e-3) / 1e12 / fp64_peak) if ipe and fp64_peak else None,
                          "what": "FP64-pipe instructions per element counted from ncu (profiles/fp64_instr.json), 2 flops each, against the DFMA-chain peak measured in this run"},
-                "kernels": {label.get(n, n): v for n, v in kern.items()}}
+                "whole_step": {"algorithmic_bytes": step_bytes, "GBps": step_bytes / (ms_max / args.steps * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_max / args.steps * 1e-3) / 1e9 / peak},
+                "kernels": {label.get(n, n): dict(v, frac_hbm=(v["GBps"] / peak if v["GBps"] else None)) for n, v in kern.items()}}
 
     line = {"metric": "NB IRLS gene-fits/sec", "value": value, "unit": "gene-fits/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",

@@ -279,6 +279,12 @@ int ruvnb_set_row_mask(ruvnb_ctx* ctx, const uint8_t* alive);
  * larger than host memory arrives in pieces).  Call ruvnb_upload_counts_done after the last slab. */
 int ruvnb_upload_counts_rows(ruvnb_ctx* ctx, const int32_t* Y_rows, int on_device, int64_t row0, int64_t nrows);
 int ruvnb_upload_counts_done(ruvnb_ctx* ctx);
+/* Counts as the slots of a dgCMatrix (compressed sparse COLUMN, column = cell): what `Matrix::Matrix(Y, sparse = TRUE)` holds, what
+ * ruvIII.nb returns as `counts` (R/ruvIIInb.R:611-612) and what get.res / makeSCE read back (R/get.res.R:14, R/makeSCE.R:22).  A block
+ * of columns [c0, c0 + ncols): p = ncols + 1 offsets into i / x (p[0] need not be 0, so a window of the caller's own slots can be
+ * passed), i = 0-based gene rows, x = counts as doubles (rounded up like :53).  The transpose into the gene-major resident layout
+ * happens on the device; the first block must start at cell 0 (it zero-fills the matrix); finish with ruvnb_upload_counts_done. */
+int ruvnb_upload_counts_csc(ruvnb_ctx* ctx, const int32_t* p, const int32_t* i, const double* x, int64_t c0, int64_t ncols);
 /* The resident (winsorized) counts of `n` local cells (0-based, any order), all local rows: out is G x n column-major int32 --
  * how the subsample of fastruvIII.nb (R/fastruvIIInb.R:118-137) leaves the device without the whole matrix travelling. */
 int ruvnb_get_cells(ruvnb_ctx* ctx, const int64_t* cells, int64_t n, int32_t* out);
@@ -318,6 +324,13 @@ typedef struct ruvnb_res_stats {
  * stats may be NULL. */
 int ruvnb_get_res_ex(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, int out_kind, void* out,
                      int64_t cell_begin, int64_t cell_end, ruvnb_res_stats* stats);
+/* The same into the slots of a dgCMatrix (compressed sparse column, column = cell): what makeSCE stores -- `as(get.res(...),
+ * "sparseMatrix")`, `as(log(get.res(type = 'quantile') + 1), "sparseMatrix")` (R/makeSCE.R:24-38).  Every block is compacted on the
+ * device, so only its non-zero entries cross PCIe.  log1p != 0: values are log(PAC + 1) (type RUVNB_RES_QUANTILE only).  colptr has
+ * (cell_end - cell_begin) + 1 slots, rowidx / values `capacity` slots (0-based rows in ascending order within a column); *nnz returns
+ * the entries written.  RUVNB_ENOMEM when capacity is too small (*nnz = entries needed so far; nothing else is valid then). */
+int ruvnb_get_res_csc(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, int log1p, int64_t cell_begin, int64_t cell_end,
+                      int64_t* colptr, int32_t* rowidx, double* values, int64_t capacity, int64_t* nnz, ruvnb_res_stats* stats);
 /* fastruvIII.nb's tail as ONE pass per block (R/fastruvIIInb.R:719-748 + makeSCE(assays = 'logPAC') -> get.res(type = 'quantile'),
  * R/fastruvIIInb.R:790, R/makeSCE.R:36-38): the block of Mb.all is computed on the device (as ruvnb_fast_Mb_all does), feeds the
  * caps and the PAC of the same block and is dropped -- the 8 bytes per element of Mb.all never cross PCIe (240 GB at 30k x 1M).

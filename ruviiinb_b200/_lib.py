@@ -25,6 +25,7 @@ SYMBOLS = [
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
     "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
     "ruvnb_set_cell_shard", "ruvnb_set_row_mask", "ruvnb_upload_counts_rows", "ruvnb_upload_counts_done", "ruvnb_get_cells",
+    "ruvnb_upload_counts_csc", "ruvnb_get_res_csc",
     "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res", "ruvnb_selftest_squeeze_var", "ruvnb_estimate_disp_r", "ruvnb_set_res_zinb",
 ]
 
@@ -139,6 +140,9 @@ def load():
     lib.ruvnb_host_free.argtypes = [vp]
     lib.ruvnb_host_free.restype = None
     lib.ruvnb_get_res_ex.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(ResStats)]
+    lib.ruvnb_upload_counts_csc.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int64]
+    lib.ruvnb_get_res_csc.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int, C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, C.POINTER(C.c_int64),
+                                      C.POINTER(ResStats)]
     lib.ruvnb_fast_res.argtypes = [vp, C.c_int, C.c_double, vp, C.c_int64, C.c_int, vp, vp, C.c_int64, C.c_int64, C.POINTER(ResStats)]
     for s in SYMBOLS:
         f = getattr(lib, s)
@@ -376,6 +380,21 @@ class Context:
             Y = np.ascontiguousarray(Y_rows, dtype=np.int32)
             self._ck(self.lib.ruvnb_upload_counts_rows(self.h, _ptr(Y), 0, int(row0), Y.shape[0]))
 
+    def upload_counts_csc(self, p, i, x, block_cols=None):
+        """The slots of a dgCMatrix / scipy.sparse.csc_matrix (G x N, column = cell): p (N + 1), i (0-based rows), x (doubles).
+        Uploaded in blocks of `block_cols` columns (default: everything at once) and transposed on the device."""
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        N = p.size - 1
+        if N != self.N:
+            raise ValueError("the column pointer must have one entry per cell plus one")
+        step = N if not block_cols else int(block_cols)
+        for c0 in range(0, max(N, 1), max(step, 1)):
+            nc = min(step, N - c0)
+            self._ck(self.lib.ruvnb_upload_counts_csc(self.h, _ptr(p[c0:c0 + nc + 1]), _ptr(i), _ptr(x), int(c0), int(nc)))
+        self.upload_counts_done()
+
     def upload_counts_done(self):
         self._ck(self.lib.ruvnb_upload_counts_done(self.h))
 
@@ -404,6 +423,29 @@ class Context:
         st = ResStats()
         self._ck(self.lib.ruvnb_get_res_ex(self.h, int(kind), int(block_size), _ptr(mb), int(out_kind), _ptr(out), int(cb), int(ce), C.byref(st)))
         return out, st.as_dict()
+
+    def get_res_csc(self, kind, block_size=5000, Mb_cells=None, log1p=False, cells=None, max_dense_bytes=1 << 31):
+        """`ruvnb_get_res_csc`: (colptr int64, rowidx int32, values f64, stats) -- the slots of the dgCMatrix makeSCE stores.  The pass
+        runs in ranges of whole blocks whose worst case (dense) fits `max_dense_bytes` of host memory, so the sink can never overflow."""
+        cb, ce = (0, self.N) if cells is None else cells
+        rows = getattr(self, "Gout", None) or self.Gl
+        bs = min(int(block_size), max(self.N, 1))
+        blocks_per_call = max(1, int(max_dense_bytes // (12 * rows * bs)))
+        mb = None if Mb_cells is None else np.asfortranarray(Mb_cells, dtype=np.float64)
+        ptrs, idx, val, stats = [np.zeros(1, dtype=np.int64)], [], [], None
+        for b0 in range(cb, ce, blocks_per_call * bs):
+            b1 = min(ce, b0 + blocks_per_call * bs)
+            cap = rows * (b1 - b0)
+            cp = np.empty(b1 - b0 + 1, dtype=np.int64); ri = np.empty(cap, dtype=np.int32); vv = np.empty(cap, dtype=np.float64)
+            nnz = C.c_int64(0)
+            st = ResStats()
+            self._ck(self.lib.ruvnb_get_res_csc(self.h, int(kind), bs, _ptr(mb), int(bool(log1p)), int(b0), int(b1), _ptr(cp), _ptr(ri), _ptr(vv),
+                                                int(cap), C.byref(nnz), C.byref(st)))
+            n = int(nnz.value)
+            ptrs.append(cp[1:] + ptrs[-1][-1]); idx.append(ri[:n].copy()); val.append(vv[:n].copy())
+            d = st.as_dict()
+            stats = d if stats is None else {k: (stats[k] + v if isinstance(v, (int, float)) else v) for k, v in d.items()}
+        return np.concatenate(ptrs), (np.concatenate(idx) if idx else np.empty(0, np.int32)), (np.concatenate(val) if val else np.empty(0)), stats
 
     def fast_res(self, kind, annot_grp, lambda_b=16.0, block_size=5000, out_kind=OUT_F64, cells=None, out=None, want_Mb_all=False):
         """`ruvnb_fast_res`: Mb.all block -> caps -> residual of the same block on the device.  Returns (out, Mb_all or None, stats)."""

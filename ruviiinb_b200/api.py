@@ -15,6 +15,23 @@ import numpy as np
 
 from . import _lib
 
+
+def _is_sparse(Y):
+    """A scipy.sparse matrix: the stand-in for R's dgCMatrix (counts of ruvIII.nb's output list, R/ruvIIInb.R:611-612)."""
+    return hasattr(Y, "tocsc") and hasattr(Y, "nnz")
+
+
+def _upload_any(ctx, Y, rows=None):
+    """Counts into the context: a dense array goes up as int32 rows, a sparse matrix as the slots of its CSC form (the device
+    transposes it into the gene-major resident layout, include/ruvnb.h ruvnb_upload_counts_csc)."""
+    if _is_sparse(Y):
+        Yc = Y.tocsr()[rows].tocsc() if rows is not None else Y.tocsc()
+        Yc.sort_indices()
+        ctx.upload_counts_csc(Yc.indptr, Yc.indices, Yc.data, block_cols=max(1, (1 << 27) // max(1, Yc.shape[0])))
+    else:
+        Yd = np.asarray(Y)
+        ctx.upload_counts(np.ascontiguousarray(np.ceil(Yd[rows] if rows is not None else Yd), dtype=np.int32))
+
 _UNSUPPORTED = "is not part of the B200 path (SURVEY.md section 2: out of scope, off by default in the reference)"
 
 
@@ -62,7 +79,9 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
         raise NotImplementedError("use.pseudosample " + _UNSUPPORTED)
     if ortho_W:
         raise NotImplementedError("ortho.W " + _UNSUPPORTED)
-    Y = np.asarray(Y)
+    sparse_in = _is_sparse(Y)
+    if not sparse_in:
+        Y = np.asarray(Y)
     if Y.ndim != 2:
         raise ValueError("Y must be a genes x cells matrix")
     G, N = Y.shape
@@ -85,12 +104,11 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
     opts = _lib.default_opts(k=int(k), robust=int(bool(robust)), lambda_a=float(lambda_a), lambda_b=float(lambda_b),
                              step_fac=float(step_fac), inner_maxit=int(inner_maxit), outer_maxit=int(outer_maxit),
                              zinb=int(zi.any()))
-    keep = (Y > 0).sum(axis=1) > 0
-    Yk = np.ascontiguousarray(np.ceil(Y[keep]), dtype=np.int32)
+    keep = np.asarray((Y > 0).sum(axis=1)).ravel() > 0
     ctx = _lib.Context(device)
     try:
-        ctx.set_design(Yk.shape[0], N, grp, ctl[keep], zeroinf=zi if zi.any() else None)
-        ctx.upload_counts(Yk)
+        ctx.set_design(int(keep.sum()), N, grp, ctl[keep], zeroinf=zi if zi.any() else None)
+        _upload_any(ctx, Y, rows=np.where(keep)[0])
         _, nz = ctx.winsorize()
         counts = ctx.get_counts()
         if (nz == 0).any():            # rows emptied by the cap: the fit context holds the surviving rows only (:57-62)
@@ -115,6 +133,9 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
     finally:
         ctx.close()
     out["pi0"] = np.outer(pi0, zi.astype(np.float64)) if zi.any() else None   # :611-626
+    if sparse_in:                                                              # :611-612: counts leave as a sparse matrix
+        import scipy.sparse as sp
+        out["counts"] = sp.csc_matrix(out["counts"])
     out["zero_genes"] = ~keep
     if return_trace:
         out["trace"], out["stats"] = recs, stats
@@ -122,7 +143,7 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
 
 
 def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_size=5000, device=0, ranks=None, N_total=None, c0=0,
-            sink="f64", return_stats=False):
+            sink="f64", return_stats=False, sink_file=None):
     """`get.res` (R/get.res.R:12-129).  `type`: like the reference, every requested kind is evaluated in the order
     pearson, logcounts, quantile and the LAST one is returned (:49,68,75), so the default returns the percentile-adjusted
     counts.  out["Mb"] may be G x N (fastruvIII.nb's Mb.all) or G x m (a ruvIII.nb fit: expanded by replicate group --
@@ -130,7 +151,12 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
 
     Cell shards (`ranks`, `N_total`, `c0` as in `fastruvIII_nb`): blocks are independent (:27-126) except for colMeans(W)
     (:36), which the library sums over the ranks; `out` then holds this rank's cells.  sink: "f64" (the reference's doubles),
-    "i32" (PAC as int32), "log1p" (log(PAC + 1)), "none" (checksum only; with return_stats).
+    "i32" (PAC as int32), "log1p" (log(PAC + 1)), "none" (checksum only; with return_stats), "csc" / "csc_log1p" (a
+    scipy.sparse.csc_matrix of the values / of log(PAC + 1): every block is compacted on the device and only its non-zero entries
+    cross PCIe -- the `as(..., "sparseMatrix")` of R/makeSCE.R:24-38).  sink_file: the dense result is realised block by block into a
+    file-backed array (.npy, column-major) instead of host memory -- the role of the reference's HDF5 AutoRealizationSink
+    (R/get.res.R:21-23,125; HDF5 itself is not available in this environment) -- and returned as a numpy.memmap.
+    out["counts"] may be dense or a scipy.sparse matrix (the dgCMatrix ruvIII.nb returns).
     Zero-inflated fits (out["pi0"]: the G x N matrix of R/ruvIIInb.R:611-626) take the ZIM branches (:52-57,69-70,84-85,95-96)."""
     kinds = [type] if isinstance(type, str) else list(type)
     for t in kinds:
@@ -140,7 +166,7 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
     if np.ndim(out["psi"]) != 1:
         raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
     ranks = ranks or Ranks()
-    Y = np.ascontiguousarray(out["counts"], dtype=np.int32)
+    Y = out["counts"] if _is_sparse(out["counts"]) else np.ascontiguousarray(out["counts"], dtype=np.int32)
     G, N = Y.shape
     N_total = N if N_total is None else int(N_total)
     M = np.asarray(out["M"]).astype(bool)
@@ -148,14 +174,15 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
     per_cell = Mb.shape[1] == N and Mb.shape[1] != M.shape[1]
     grp = np.argmax(M, axis=1).astype(np.int32) if (M.sum(axis=1) == 1).all() else np.zeros(N, dtype=np.int32)
     m = max(int(g.max()) for g in ranks.allgather(grp)) + 1
-    kind = {"f64": _lib.OUT_F64, "i32": _lib.OUT_I32, "log1p": _lib.OUT_LOG1P, "none": _lib.OUT_NONE}[sink]
+    kind = {"f64": _lib.OUT_F64, "i32": _lib.OUT_I32, "log1p": _lib.OUT_LOG1P, "none": _lib.OUT_NONE, "csc": _lib.OUT_F64,
+            "csc_log1p": _lib.OUT_LOG1P}[sink]
     with _lib.Context(device) as ctx:
         if ranks.world > 1:
             ctx.comm_init(ranks.unique_id(), ranks.rank, ranks.world)
         ctx.set_design(G, N, grp, np.asarray(out["ctl"], bool), m=m)
         if ranks.world > 1 or N_total != N:
             ctx.set_cell_shard(N_total, c0)
-        ctx.upload_counts(Y)
+        _upload_any(ctx, Y)
         ctx.set_state("W", out["W"])
         ctx.set_state("alpha", out["a"])
         ctx.set_state("gmean", out["gmean"])
@@ -172,19 +199,44 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
             b = np.ones(N_total, dtype=np.int64) if batch is None else np.asarray(batch).astype(np.int64)
             ctx.set_state("pi0", P.max(axis=1))
             ctx.set_res_zinb(zi[b[c0:c0 + N] - 1], float(zi.mean()))
-        res, st = ctx.get_res_ex(_lib.RES_KINDS[last], block_size=block_size, Mb_cells=Mb if per_cell else None, out_kind=kind)
+        if sink.startswith("csc"):
+            import scipy.sparse as sp
+            cp, ri, vv, st = ctx.get_res_csc(_lib.RES_KINDS[last], block_size=block_size, Mb_cells=Mb if per_cell else None,
+                                             log1p=sink == "csc_log1p")
+            res = sp.csc_matrix((vv, ri, cp), shape=(getattr(ctx, "Gout", None) or G, N))
+        else:
+            dst = None
+            if sink_file is not None and kind != _lib.OUT_NONE:
+                dst = np.lib.format.open_memmap(sink_file, mode="w+", dtype=np.int32 if kind == _lib.OUT_I32 else np.float64,
+                                                shape=(G, N), fortran_order=True)
+            res, st = ctx.get_res_ex(_lib.RES_KINDS[last], block_size=block_size, Mb_cells=Mb if per_cell else None, out_kind=kind, out=dst)
+            if dst is not None:
+                dst.flush()
     return (res, st) if return_stats else res
 
 
-def makeSCE(obj, cData=None, batch=None, assays=("pearson", "logPAC")):
-    """`makeSCE` (R/makeSCE.R:12-43): a dict standing in for the SingleCellExperiment -- assays 'counts', and per request
-    'pearson' (Pearson residuals) and 'logPAC' (log(PAC + 1))."""
-    sce = {"assays": {"counts": obj["counts"]}, "colData": cData, "W": obj["W"]}
+def makeSCE(obj, cData=None, batch=None, assays=("pearson", "logPAC"), device=0):
+    """`makeSCE` (R/makeSCE.R:12-43).  There is no SingleCellExperiment class outside R: the return value is a dict with the same
+    parts -- assays (counts, and per request logcounts / pearson / logPAC, each a scipy.sparse.csc_matrix as the reference stores
+    `as(..., "sparseMatrix")`), colData (= cData), rowData (alpha1..alphak and psi, :20-21).  Same argument checks and messages."""
+    import scipy.sparse as sp
+    batch = obj.get("batch")                                                        # :14
+    if cData is None:
+        raise ValueError("'cData' must be a user-specified data frame.")           # :15-16
     want = [assays] if isinstance(assays, str) else list(assays)
+    if any(a not in ("logcounts", "logPAC", "pearson") for a in want):
+        raise ValueError("'Wrong names of corrected assays data was specified. Available corrected data assays are logcounts,logPAC and pearson")
+    a = np.asarray(obj["a"])
+    row_data = {f"alpha{j + 1}": a[:, j] for j in range(a.shape[1])}
+    row_data["obj.psi"] = np.asarray(obj["psi"])
+    counts = obj["counts"] if _is_sparse(obj["counts"]) else sp.csc_matrix(np.asarray(obj["counts"]))
+    sce = {"assays": {"counts": counts}, "colData": cData, "rowData": row_data}
+    if "logcounts" in want:
+        sce["assays"]["logcounts"] = get_res(obj, type="logcounts", batch=batch, sink="csc", device=device)
     if "pearson" in want:
-        sce["assays"]["pearson"] = get_res(obj, type="pearson", batch=batch)
+        sce["assays"]["pearson"] = get_res(obj, type="pearson", batch=batch, sink="csc", device=device)
     if "logPAC" in want:
-        sce["assays"]["logPAC"] = np.log(get_res(obj, type="quantile", batch=batch) + 1.0)   # R/makeSCE.R:36-38
+        sce["assays"]["logPAC"] = get_res(obj, type="quantile", batch=batch, sink="csc_log1p", device=device)   # :36-38
     return sce
 
 

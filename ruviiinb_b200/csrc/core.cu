@@ -480,6 +480,40 @@ int ruvnb_upload_counts_rows(ruvnb_ctx* ctx, const int32_t* Y_rows, int on_devic
   }
   return RUVNB_OK;
 }
+// A block of columns [c0, c0 + ncols) of a dgCMatrix -- what `Matrix::Matrix(Y, sparse = TRUE)` holds and what ruvIII.nb returns as
+// `counts` (R/ruvIIInb.R:611-612): p (ncols + 1 offsets, p[0] need not be 0: a window of the caller's slot), i (0-based gene rows),
+// x (doubles).  The first block (c0 == 0) zero-fills the resident matrix; blocks may arrive in any order after it.
+int ruvnb_upload_counts_csc(ruvnb_ctx* ctx, const int32_t* p, const int32_t* i, const double* x, int64_t c0, int64_t ncols) {
+  if (!ctx || !p || ncols < 0) return RUVNB_EARG;
+  if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "upload_counts_csc: call ruvnb_set_design first");
+  if (ctx->Gl != ctx->G) return ctx->fail(RUVNB_EARG, "upload_counts_csc: gene shards take their rows through ruvnb_upload_counts_csr");
+  if (c0 < 0 || c0 + ncols > ctx->N) return ctx->fail(RUVNB_EARG, "upload_counts_csc: cells [%lld, %lld) outside 0..%lld", (long long)c0, (long long)(c0 + ncols), (long long)ctx->N);
+  const long long nnz = ncols ? (long long)p[ncols] - p[0] : 0;
+  if (nnz < 0 || (nnz && (!i || !x))) return ctx->fail(RUVNB_EARG, "upload_counts_csc: inconsistent p / i / x");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->dY) {
+    if (c0 != 0) return ctx->fail(RUVNB_ESTATE, "upload_counts_csc: the first block must start at cell 0 (it zero-fills the matrix)");
+    RET(dev_alloc(ctx, &ctx->dY, (long long)ctx->Gl * ctx->Np));
+  }
+  if (c0 == 0) { k_fill_pad<<<nblk((long long)ctx->Gl * ctx->Np, 256), 256, 0, ctx->stream>>>(ctx->dY, ctx->Gl, ctx->Np, ctx->d_pos2cell); CKL(); }
+  if (ncols == 0) return RUVNB_OK;
+  ScopedDev own;
+  int *d_p = nullptr, *d_i = nullptr, *d_bad = nullptr; double* d_x = nullptr;
+  CK(own.alloc(&d_p, (size_t)(ncols + 1) * 4)); CK(own.alloc(&d_i, (size_t)std::max(1ll, nnz) * 4)); CK(own.alloc(&d_x, (size_t)std::max(1ll, nnz) * 8));
+  CK(own.alloc(&d_bad, 4));
+  CK(cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
+  CK(cudaMemcpyAsync(d_p, p, (size_t)(ncols + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    CK(cudaMemcpyAsync(d_i, i + p[0], (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_x, x + p[0], (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  k_csc_scatter<<<nblk(ncols * 32, 256), 256, 0, ctx->stream>>>(d_p, d_i, d_x, ncols, c0, p[0], ctx->Gl, ctx->d_cell2pos, ctx->Np, ctx->dY, d_bad); CKL();
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bad) return ctx->fail(RUVNB_EARG, "upload_counts_csc: %d entries with a row outside 0..%d or a negative / non-finite count", bad, ctx->Gl - 1);
+  return RUVNB_OK;
+}
 int ruvnb_upload_counts_done(ruvnb_ctx* ctx) {
   if (!ctx) return RUVNB_EARG;
   if (!ctx->dY) return ctx->fail(RUVNB_ESTATE, "upload_counts_done: no slab uploaded");

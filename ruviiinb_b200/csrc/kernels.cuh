@@ -2054,6 +2054,22 @@ static __global__ void k_csr_scatter(const long long* indptr, const int32_t* ind
   for (long long e = indptr[w] - base + lane; e < indptr[w + 1] - base; e += 32) dst[w * Np + cell2pos[indices[e]]] = values[e];
 }
 
+// a block of columns of a dgCMatrix (compressed sparse COLUMN: p / i / x slots, column = cell) scattered into the gene-major resident
+// layout: one warp per column.  x holds the counts as doubles (R's numeric); ceiling as R/ruvIIInb.R:53 applies it.
+static __global__ void k_csc_scatter(const int* colptr, const int* rowidx, const double* x, long long ncols, long long c0, int base, int Gl,
+                                     const int* cell2pos, long long Np, int32_t* dst, int* bad) {
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= ncols) return;
+  const long long pos = cell2pos[c0 + w];
+  for (int e = colptr[w] - base + lane; e < colptr[w + 1] - base; e += 32) {
+    const int g = rowidx[e];
+    const double v = ceil(x[e]);
+    if (g < 0 || g >= Gl || !(v >= 0.0) || v > 2147483647.0) { atomicAdd(bad, 1); continue; }
+    dst[(long long)g * Np + pos] = (int32_t)v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP64 FMA peak of this device (the governing roofline of the sweeps): 8 independent
 // DFMA chains per thread, 1024 x 8 x 2 flops per thread per call.

@@ -23,6 +23,8 @@ struct ResRun {
   double* Mb_all_out;           // MB_FAST: optional host copy of Mb.all (G x N doubles, column-major)
   void* out;
   ruvnb_res_stats* stats;
+  // sparse sink (out_kind F64 / LOG1P values compacted per block): host slots of a dgCMatrix, or colptr == nullptr
+  int64_t* csc_colptr = nullptr; int32_t* csc_rowidx = nullptr; double* csc_values = nullptr; int64_t csc_capacity = 0; int64_t* csc_nnz = nullptr;
 };
 
 template <int TYPE>
@@ -43,7 +45,10 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
   if (rr.out_kind < RUVNB_OUT_F64 || rr.out_kind > RUVNB_OUT_NONE) return ctx->fail(RUVNB_EARG, "get_res: unknown sink %d", rr.out_kind);
   if ((rr.out_kind == RUVNB_OUT_I32 || rr.out_kind == RUVNB_OUT_LOG1P) && type != RES_QUANTILE)
     return ctx->fail(RUVNB_EARG, "get_res: the int32 / log1p sinks hold percentile-adjusted counts (type 3) only");
-  if (rr.out_kind != RUVNB_OUT_NONE && !rr.out) return ctx->fail(RUVNB_EARG, "get_res: no output buffer");
+  const bool csc = rr.csc_colptr != nullptr;
+  if (csc && (rr.out_kind == RUVNB_OUT_I32 || rr.out_kind == RUVNB_OUT_NONE)) return ctx->fail(RUVNB_EARG, "get_res: the sparse sink stores doubles (sink f64 or log1p)");
+  if (csc && (!rr.csc_rowidx || !rr.csc_values || !rr.csc_nnz || rr.csc_capacity < 0)) return ctx->fail(RUVNB_EARG, "get_res: sparse sink without i / x / nnz slots");
+  if (rr.out_kind != RUVNB_OUT_NONE && !rr.out && !csc) return ctx->fail(RUVNB_EARG, "get_res: no output buffer");
   CK(cudaSetDevice(ctx->device));
   const int Gl = ctx->Gl, K = ctx->K;
   const long long N = ctx->N;
@@ -70,6 +75,16 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
   CK(own.alloc(&hist, SEL_NT * SEL_BINS * 4)); CK(own.alloc(&T, sizeof(SelTargets))); CK(own.alloc(&nanc, 4));
   CK(cudaMemsetAsync(hist, 0, SEL_NT * SEL_BINS * 4, ctx->stream));
   CK(cudaMemsetAsync(sum, 0, 8, ctx->stream));
+  // sparse sink: per slab a compacted copy (row indices + values, worst case dense), the block's column offsets, the running total
+  int *c_cnt = nullptr, *c_ridx[2] = {nullptr, nullptr}; double* c_val[2] = {nullptr, nullptr}; long long *c_ptr[2] = {nullptr, nullptr}, *c_tot = nullptr, *c_blk = nullptr;
+  long long* h_blk = nullptr;   // pinned: nnz of the block just compacted
+  long long csc_done = 0;
+  if (csc) {
+    CK(own.alloc(&c_cnt, (size_t)bs * 4)); CK(own.alloc(&c_tot, 8)); CK(own.alloc(&c_blk, 8));
+    for (int i = 0; i < 2; ++i) { CK(own.alloc(&c_ridx[i], (size_t)Gout * bs * 4)); CK(own.alloc(&c_val[i], (size_t)Gout * bs * 8)); CK(own.alloc(&c_ptr[i], (size_t)bs * 8)); }
+    CK(cudaMemsetAsync(c_tot, 0, 8, ctx->stream));
+    CK(cudaMallocHost((void**)&h_blk, 8));
+  }
   FastMbPrep pr;
   if (rr.src == MB_FAST) RET(fast_mb_prepare(ctx, rr.annot_grp, &own, &pr));
   cudaStream_t copy_stream = nullptr; cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr}, t_begin = nullptr, t_end = nullptr;
@@ -159,6 +174,30 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
       RET(launch_elem<RES_QUANTILE>(ctx, a, rr.out_kind, tmp, slab[sl], nanc, sumptr));
       RET(ev_end());
     }
+    if (csc) {
+      // compact the block on the device; only its non-zero entries cross PCIe.  The host needs the block's count before it can
+      // place the copy: one 8-byte read-back per block (the next block's kernels are queued right after it)
+      k_csc_count<<<nblk((long long)B * 32, 256), 256, 0, ctx->stream>>>((const double*)slab[sl], Gout, B, c_cnt); CKL();
+      k_csc_scan<<<1, 1024, 0, ctx->stream>>>(B, c_cnt, c_tot, c_ptr[sl], c_blk); CKL();
+      k_csc_fill<<<nblk((long long)B * 32, 256), 256, 0, ctx->stream>>>((const double*)slab[sl], Gout, B, c_ptr[sl], csc_done, c_ridx[sl], c_val[sl]); CKL();
+      CK(cudaMemcpyAsync(h_blk, c_blk, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaEventRecord(done[sl], ctx->stream));
+      CK(cudaEventSynchronize(done[sl]));
+      const long long nb = *h_blk;
+      if (csc_done + nb > rr.csc_capacity) {
+        cudaStreamSynchronize(copy_stream); cudaFreeHost(h_blk);
+        *rr.csc_nnz = csc_done + nb;
+        return ctx->fail(RUVNB_ENOMEM, "get_res: the sparse sink holds %lld entries, %lld needed after cell %lld", (long long)rr.csc_capacity, csc_done + nb, (long long)(c0 + B));
+      }
+      CK(cudaMemcpyAsync(rr.csc_colptr + (c0 - cb), c_ptr[sl], (size_t)B * 8, cudaMemcpyDeviceToHost, copy_stream));
+      if (nb) {
+        CK(cudaMemcpyAsync(rr.csc_rowidx + csc_done, c_ridx[sl], (size_t)nb * 4, cudaMemcpyDeviceToHost, copy_stream));
+        CK(cudaMemcpyAsync(rr.csc_values + csc_done, c_val[sl], (size_t)nb * 8, cudaMemcpyDeviceToHost, copy_stream));
+      }
+      CK(cudaEventRecord(copied[sl], copy_stream));
+      csc_done += nb;
+      continue;
+    }
     CK(cudaEventRecord(done[sl], ctx->stream));
     if (rr.out_kind != RUVNB_OUT_NONE || (rr.src == MB_FAST && rr.Mb_all_out)) {
       CK(cudaStreamWaitEvent(copy_stream, done[sl], 0));
@@ -174,6 +213,7 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
   CK(cudaEventRecord(t_end, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(copy_stream));
+  if (csc) { rr.csc_colptr[ce - cb] = csc_done; *rr.csc_nnz = csc_done; CK(cudaFreeHost(h_blk)); }
   if (rr.stats) {
     ruvnb_res_stats* st = rr.stats;
     memset(st, 0, sizeof *st);
@@ -226,6 +266,17 @@ int ruvnb_set_res_zinb(ruvnb_ctx* ctx, const uint8_t* zflag_of_cell, double mean
 int ruvnb_get_res(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, double* out) {
   if (!ctx || !out) return RUVNB_EARG;
   return ruvnb_get_res_ex(ctx, type, block_size, Mb_cells, RUVNB_OUT_F64, out, 0, -1, nullptr);
+}
+
+int ruvnb_get_res_csc(ruvnb_ctx* ctx, int type, int64_t block_size, const double* Mb_cells, int log1p, int64_t cell_begin, int64_t cell_end,
+                      int64_t* colptr, int32_t* rowidx, double* values, int64_t capacity, int64_t* nnz, ruvnb_res_stats* stats) {
+  if (!ctx || !colptr || !nnz) return RUVNB_EARG;
+  ResRun rr;
+  rr.type = type; rr.out_kind = log1p ? RUVNB_OUT_LOG1P : RUVNB_OUT_F64; rr.bs = block_size; rr.cell_begin = cell_begin; rr.cell_end = cell_end;
+  rr.src = Mb_cells ? MB_HOST_CELLS : MB_GROUP; rr.Mb_cells = Mb_cells; rr.lambda_b = 0.0; rr.annot_grp = nullptr; rr.Mb_all_out = nullptr;
+  rr.out = nullptr; rr.stats = stats;
+  rr.csc_colptr = colptr; rr.csc_rowidx = rowidx; rr.csc_values = values; rr.csc_capacity = capacity; rr.csc_nnz = nnz;
+  return res_run(ctx, rr);
 }
 
 int ruvnb_fast_res(ruvnb_ctx* ctx, int type, double lambda_b, const int32_t* annot_grp, int64_t block_size, int out_kind, void* out,

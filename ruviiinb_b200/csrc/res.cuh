@@ -349,3 +349,50 @@ static __global__ void k_res_wamean(int Gl, int K, const double* alpha, const do
   for (int l = 0; l < K; ++l) s = fma(alpha[(long long)g * K + l], wsum[l] * inv_n, s);   // colMeans(W) = colSums / N (all ranks)
   out[g] = s;
 }
+
+// ------------------------------------------------------------------------------------------------
+// sparse sink: the block slab [B][Gout] (R's G x B column-major) compacted into the slots of a dgCMatrix -- what makeSCE stores
+// (`as(log(PAC + 1), "sparseMatrix")`, R/makeSCE.R:36-38).  One warp per cell column; entries keep their row order.
+// ------------------------------------------------------------------------------------------------
+static __global__ void k_csc_count(const double* slab, int Gout, int B, int* cnt) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B) return;
+  const double* col = slab + (long long)w * Gout;
+  int n = 0;
+  for (int g = lane; g < Gout; g += 32) n += col[g] != 0.0;
+  n = __reduce_add_sync(0xffffffffu, n);
+  if (lane == 0) cnt[w] = n;
+}
+// exclusive scan of the B column counts (one CTA): colptr[c] = *total + sum_{c' < c} cnt[c'] for c = 0..B - 1, then *total += block nnz
+// (colptr[B] of the last block is written by the host).  blk_nnz[0] = this block's count.
+static __global__ void __launch_bounds__(1024) k_csc_scan(int B, const int* cnt, long long* total, long long* colptr, long long* blk_nnz) {
+  __shared__ long long part[1024];
+  const int t = threadIdx.x, per = (B + 1023) / 1024;
+  long long s = 0;
+  for (int q = 0; q < per; ++q) { const int c = t * per + q; if (c < B) s += cnt[c]; }
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele inclusive scan
+    long long v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = *total + (t ? part[t - 1] : 0);
+  for (int q = 0; q < per; ++q) { const int c = t * per + q; if (c < B) { colptr[c] = run; run += cnt[c]; } }
+  __syncthreads();
+  if (t == 0) { *blk_nnz = part[1023]; *total += part[1023]; }
+}
+static __global__ void k_csc_fill(const double* slab, int Gout, int B, const long long* colptr, long long base, int* ridx, double* val) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B) return;
+  const double* col = slab + (long long)w * Gout;
+  long long o = colptr[w] - base;
+  for (int g0 = 0; g0 < Gout; g0 += 32) {
+    const int g = g0 + lane;
+    const double v = g < Gout ? col[g] : 0.0;
+    const unsigned bal = __ballot_sync(0xffffffffu, v != 0.0);
+    if (v != 0.0) { const long long q = o + __popc(bal & ((1u << lane) - 1u)); ridx[q] = g; val[q] = v; }
+    o += __popc(bal);
+  }
+}

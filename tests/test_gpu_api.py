@@ -58,6 +58,10 @@ def test_api_argument_errors_mirror_stop():
         api.ruvIII_nb(Y, M, ctl, use_pseudosample=True)
     with pytest.raises(ValueError, match="unknown type"):
         api.get_res(dict(pi0=None, psi=np.ones(3)), type="foo")
+    with pytest.raises(ValueError, match="'cData' must be a user-specified data frame"):       # R/makeSCE.R:15-16
+        api.makeSCE(dict(batch=None))
+    with pytest.raises(ValueError, match="Wrong names of corrected assays"):                   # R/makeSCE.R:17-18
+        api.makeSCE(dict(batch=None), cData={}, assays=("logPAC", "tpm"))
     # estimateDisp.par: the reference's own stop() conditions, then what the device path does not implement
     with pytest.raises(ValueError, match="Incorrect length of group"):
         api.estimateDisp_par(Y, group=np.ones(3))
