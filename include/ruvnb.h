@@ -138,6 +138,21 @@ int ruvnb_comm_init(ruvnb_ctx* ctx, const unsigned char id[128], int rank, int n
 /* grp_of_cell: N labels in 0..m-1 (apply(M,1,which), R/ruvIIInb.R:50); ctl: G flags (:42-45);
  * zeroinf: N flags or NULL (:39-40).  G is the GLOBAL gene count; [g0,g1) the rows this ctx holds
  * (g0 = 0, g1 = G on a single GPU). */
+/* Batch of every cell (0-based, N entries, every batch non-empty, nbatch <= 127) for a BATCH-SPECIFIC dispersion psi[g, batch(c)]
+ * (`batch.disp = TRUE`, R/ruvIIInb.R:213-220,278-283,306-315,542-548; R/get.res.R:59-62,101-121).  Must precede ruvnb_set_design: the
+ * resident cell order keeps the batches of a replicate group apart.  State "psi" / "psi_w" then have G x nbatch entries (column-major,
+ * R's psi matrix); ruvnb_irls_iteration, ruvnb_loglik, ruvnb_fit_nb, ruvnb_zinb_pi0 and ruvnb_get_res index the dispersion by the
+ * cell's batch.  The dispersion estimators (ruvnb_estimate_disp*, ruvnb_disp_apl_grid, ruvnb_disp_newton) and the fastruvIII.nb
+ * operators refuse such a context: the reference calls estimateDisp once per batch on that batch's cells (:213-220), which a host
+ * does with one context per batch (ruvnb_set_psi_callback). */
+int ruvnb_set_batches(ruvnb_ctx* ctx, const int32_t* batch_of_cell, int64_t N, int nbatch);
+int ruvnb_nbatch(const ruvnb_ctx* ctx);
+/* Host hook for every dispersion refresh of ruvnb_fit_nb (R/ruvIIInb.R:205-221,535-565) in place of the built-in estimator: called
+ * with the state to estimate from as the current state; it reads with ruvnb_get_state and writes the new dispersion with
+ * ruvnb_set_state(ctx, "psi", ...) -- keeping the old value where the new one is not finite (:564) is the hook's job.  Returns
+ * RUVNB_OK or a negative error.  fn = NULL removes the hook.  A psi schedule passed to ruvnb_fit_nb takes precedence. */
+typedef int (*ruvnb_psi_fn)(void* user, ruvnb_ctx* ctx);
+int ruvnb_set_psi_callback(ruvnb_ctx* ctx, ruvnb_psi_fn fn, void* user);
 int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t* grp_of_cell,
                      const uint8_t* ctl, const uint8_t* zeroinf, int64_t g0, int64_t g1);
 /* Y: the (g1-g0) x N rows this ctx owns, plus -- when sharded -- Yctl: the n_ctl x N control-gene

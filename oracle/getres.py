@@ -36,7 +36,13 @@ def get_res(out, kind, block_size=5000):
     qnbinom(pmax(0, (p - omega)/(1 - omega))) (third-party, parity unpinned)."""
     Y = np.asarray(out["counts"], dtype=np.float64)
     G, N = Y.shape
-    a, W, gmean, Mb, psi = out["a"], out["W"], out["gmean"], out["Mb"], out["psi"]
+    a, W, gmean, Mb, psi = out["a"], out["W"], out["gmean"], out["Mb"], np.asarray(out["psi"])
+    # a batch-specific fit: psi is G x nbatch and read as out$psi[, curr.batch] (:59-62,101-108); the quantile step uses the
+    # column ref.batch = which.min(colMeans(out$psi)) (:113,120)
+    bpsi = psi.ndim == 2
+    if bpsi:
+        batch = np.asarray(out["batch"]).astype(np.int64)
+        ref = int(np.argmin(psi.mean(axis=0)))
     block_size = min(block_size, N)
     res = np.empty((G, N))
     wa_mean = a @ W.mean(axis=0)                                       # :36
@@ -47,11 +53,12 @@ def get_res(out, kind, block_size=5000):
         mu = _cap_rows(np.exp(Wa + gmean[:, None]))                    # :33,38-40
         mu_full = _cap_rows(np.exp(Wa + gmean[:, None] + Mb[:, s:e]))  # :34,42-44
         om = _omega(out, s, e)
+        psic = psi[:, batch[s:e] - 1] if bpsi else psi[:, None]
         if kind == PEARSON:                                            # :49-67
             if om is None:
-                dev = (Ysub - mu) / np.sqrt(mu_full * (1.0 + mu_full * psi[:, None]))
+                dev = (Ysub - mu) / np.sqrt(mu_full * (1.0 + mu_full * psic))
             else:                                                      # :52-53
-                dev = (Ysub - mu * (1.0 - om)) / np.sqrt(mu_full * (1.0 - om) * (1.0 + mu_full * (psi[:, None] + om)))
+                dev = (Ysub - mu * (1.0 - om)) / np.sqrt(mu_full * (1.0 - om) * (1.0 + mu_full * (psic + om)))
             v = dev[~np.isnan(dev)]
             lims = rstats.r_quantile7(v, [0.005, 0.995])
             dev = np.where(dev < lims[0], lims[0], dev)
@@ -60,7 +67,8 @@ def get_res(out, kind, block_size=5000):
             dev = np.log(Ysub / (np.exp(Wa) * (1.0 if om is None else 1.0 - om)) + 1.0)   # :69-73
         else:                                                          # :75-124
             mu_nouv = _cap_rows(np.exp(Mb[:, s:e] + gmean[:, None] + wa_mean[:, None]))
-            size = (1.0 / psi)[:, None]
+            size = 1.0 / psic
+            size_q = (1.0 / psi[:, ref])[:, None] if bpsi else size
             lo = nmath.pnbinom_mu(Ysub - 1.0, size, mu_full)
             d = nmath.dnbinom_mu(Ysub, size, mu_full)
             if om is not None:                                         # ZIM::pzinb(Ysub - 1), + ZIM::dzinb(Ysub), :84-85
@@ -69,8 +77,8 @@ def get_res(out, kind, block_size=5000):
             hi = lo + d
             p = np.clip((lo + hi) / 2.0, 0.005, 0.995)
             if om is not None:                                         # ZIM::qzinb(p, omega = rowMeans(out$pi0)), :95-96
-                avg = np.asarray(out["pi0"]).mean(axis=1)[:, None]
+                avg = np.asarray(out["pi0"])[:, ref][:, None] if bpsi else np.asarray(out["pi0"]).mean(axis=1)[:, None]   # :112,118 / :95
                 p = np.maximum(0.0, (p - avg) / (1.0 - avg))
-            dev = np.where(p == 0.0, 0.0, nmath.qnbinom_mu(np.where(p == 0.0, 0.5, p), size, mu_nouv))
+            dev = np.where(p == 0.0, 0.0, nmath.qnbinom_mu(np.where(p == 0.0, 0.5, p), size_q, mu_nouv))
         res[:, s:e] = dev
     return res

@@ -7,8 +7,8 @@ Injection seams: the initial W (`irlba`, random start, :16
 dispersion routine (`estimateDisp.par`, third-party edgeR arithmetic, :205-221,:535-565) are
 arguments, because neither can be restated bit-faithfully offline.
 
-Out of scope: pseudo-cells, batch-specific dispersion,
-`ortho.W`.
+Batch-specific dispersion (`batch.disp = TRUE`, :213-220,278-283,306-315,542-548) is an argument of `ruvIII_nb`; the pseudo-cells
+of `use.pseudosample = TRUE` (:83-152) are prepared by oracle/pseudocells.py.  Out of scope: `ortho.W`.
 """
 import numpy as np
 
@@ -99,11 +99,18 @@ def clamp_rows(B):
     return clamp_cols(B.T).T
 
 
+def _psi_cols(psi):
+    """psi as something that broadcasts against G x N: a vector (one dispersion per gene, nbatch == 1: outer(1/psi, ncells),
+    R/ruvIIInb.R:286,309,317) or the G x N matrix psi[, batch] of a batch-specific fit (:280,307,313)."""
+    psi = np.asarray(psi)
+    return psi[:, None] if psi.ndim == 1 else psi
+
+
 def loglik_matrix(Y, lmu, psi, pi0=None, zeroinf=None):
     """Per-element log-likelihood with +-Inf/NaN -> log(DBL_MIN) (R/ruvIIInb.R:276-291)."""
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         mu = np.exp(lmu)
-        size = (1.0 / psi)[:, None]
+        size = 1.0 / _psi_cols(psi)
         if pi0 is None or not np.any(pi0 > 0):
             temp = nmath.dnbinom_mu_log(Y, size, mu)
         else:
@@ -116,12 +123,12 @@ def loglik_matrix(Y, lmu, psi, pi0=None, zeroinf=None):
 
 
 def working_quantities(Y, gmean, Mb, alpha, W, psi, grp, step):
-    """lmu.hat, sig.inv, signdev, Z of R/ruvIIInb.R:303-321 (nbatch == 1, ncells == 1)."""
+    """lmu.hat, sig.inv, signdev, Z of R/ruvIIInb.R:303-321 (ncells == 1; psi a vector, or psi[, batch] as a G x N matrix)."""
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         lmu = gmean[:, None] + Mb[:, grp] + alpha @ W.T
         mu = np.exp(lmu)
-        sig_inv = 1.0 / (np.exp(-lmu) + psi[:, None])
-        size = (1.0 / psi)[:, None]
+        sig_inv = 1.0 / (np.exp(-lmu) + _psi_cols(psi))
+        size = 1.0 / _psi_cols(psi)
         signdev = np.sign(Y - mu) * np.sqrt(
             2.0 * (nmath.dnbinom_mu_log(Y, size, Y) - nmath.dnbinom_mu_log(Y, size, mu)))
         Z = lmu + step[:, None] * ((Y + 0.01) / (mu + 0.01) - 1.0)
@@ -130,7 +137,7 @@ def working_quantities(Y, gmean, Mb, alpha, W, psi, grp, step):
 
 def zinb_weights(Y, mu, psi, pi0, zeroinf, wt_zinb):
     """E-step weights for zero counts in zero-inflated cells (R/ruvIIInb.R:254-264,457-467)."""
-    size = (1.0 / psi)[:, None]
+    size = 1.0 / _psi_cols(psi)
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         d0 = nmath.dnbinom_mu(0.0, size, mu)
         w = 1.0 - pi0[:, None] / (pi0[:, None] + (1.0 - pi0[:, None]) * d0)
@@ -225,7 +232,7 @@ def inner_iteration(Y, state, grp, rep_ind, ctl, k_huber, lambda_a, lambda_b, ze
     if zeroinf is not None and zeroinf.any():
         with np.errstate(over="ignore"):
             mu_new = np.exp(Wa_new + Mb_new[:, grp] + gmean_new[:, None])
-        tmp = pi0_fn(Y[:, zeroinf], mu_new[:, zeroinf], psi)
+        tmp = pi0_fn(Y[:, zeroinf], mu_new[:, zeroinf], psi if np.ndim(psi) == 1 else psi[:, zeroinf])   # :443-445
         pi0_new = np.where(np.isnan(tmp), pi0, tmp)
         wt_zinb_new = zinb_weights(Y, mu_new, psi, pi0_new, zeroinf, wt_zinb)
     # :469-484  candidate log-likelihood
@@ -242,8 +249,12 @@ def inner_iteration(Y, state, grp, rep_ind, ctl, k_huber, lambda_a, lambda_b, ze
 # the driver, R/ruvIIInb.R:27-629
 # --------------------------------------------------------------------------------------
 def ruvIII_nb(Y, M, ctl, k=2, robust=False, lambda_a=0.01, lambda_b=16.0, step_fac=0.5, inner_maxit=50,
-              outer_maxit=25, zeroinf=None, W0=None, psi_fn=None, pi0_fn=None, winsorize=True, trace=None):
-    """Restated `ruvIII.nb` (nbatch == 1, no pseudo-cells, ortho.W = FALSE).
+              outer_maxit=25, zeroinf=None, W0=None, psi_fn=None, pi0_fn=None, winsorize=True, trace=None,
+              batch=None, batch_disp=False):
+    """Restated `ruvIII.nb` (ortho.W = FALSE; pseudo-cells are prepared by the caller, oracle/pseudocells.py).
+
+    batch (N labels, 1..nbatch as in the reference) with batch_disp = TRUE: psi is a G x nbatch matrix, every use reads
+    psi[, batch] (:280,307,313) and every refresh runs psi_fn once per batch on that batch's cells (:213-220,542-548).
 
     Y: G x N counts; M: N x m 0/1 replicate matrix (each cell in exactly one group, :206);
     ctl: length-G bool.  `W0`: injected initial W (N x k) or None -> dense SVD stand-in.
@@ -282,16 +293,39 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, lambda_a=0.01, lambda_b=16.0, step_f
     gmean = coef[:, 0].copy()
     wt_zinb = np.ones((G, N))
     pi0 = np.zeros(G)
+    # :64-81,88-91: without batch labels, or with batch.disp = FALSE, there is ONE dispersion per gene
+    bsel = None
+    if batch is not None and batch_disp:
+        labels, b0 = np.unique(np.asarray(batch), return_inverse=True)
+        if labels.size > 1:
+            bsel = [np.where(b0 == B)[0] for B in range(labels.size)]
+
+    def refresh_psi(offs, wt, psi_old):
+        """estimateDisp.par on all cells (:210,540), or once per batch on that batch's cells (:213-220,542-548)."""
+        if bsel is None:
+            return psi_fn(Y, offs, wt, psi_old)
+        cols = []
+        for B, idx in enumerate(bsel):
+            try:
+                cols.append(psi_fn(Y[:, idx], offs[:, idx], wt[:, idx], None if psi_old is None else psi_old[:, B]))
+            except Exception:           # tryCatch(..., error = function(e) NA), :545
+                cols.append(np.full(G, np.nan))
+        return np.stack(cols, axis=1)
+
+    def cols_of(psi_):
+        """psi as the kernels of this file take it: the vector, or psi[, batch] (G x N)."""
+        return psi_ if bsel is None else psi_[:, b0]
+
     # :205-221  initial psi
     offs = alpha @ W.T + Mb[:, grp]
-    psi = psi_fn(Y, offs, wt_zinb, None)
+    psi = refresh_psi(offs, wt_zinb, None)
     # :237-264  initial pi0 / weights
     if zeroinf.any():
         with np.errstate(over="ignore"):
             mu = np.exp(offs + gmean[:, None])
-        tmp = pi0_fn(Y[:, zeroinf], mu[:, zeroinf], psi)
+        tmp = pi0_fn(Y[:, zeroinf], mu[:, zeroinf], psi if bsel is None else cols_of(psi)[:, zeroinf])
         pi0 = np.where(np.isnan(tmp), pi0, tmp)
-        wt_zinb = zinb_weights(Y, mu, psi, pi0, zeroinf, wt_zinb)
+        wt_zinb = zinb_weights(Y, mu, cols_of(psi), pi0, zeroinf, wt_zinb)
 
     conv = False
     iter_outer = 0
@@ -301,13 +335,13 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, lambda_a=0.01, lambda_b=16.0, step_f
         iter_outer += 1
         logl_beta = []
         lmu = gmean[:, None] + Mb[:, grp] + alpha @ W.T
-        loglik = loglik_matrix(Y, lmu, psi, pi0, zeroinf).sum(axis=1)  # :276-291
+        loglik = loglik_matrix(Y, lmu, cols_of(psi), pi0, zeroinf).sum(axis=1)  # :276-291
         step = np.ones(G)  # :293
         best = dict(W=W, psi=psi, alpha=alpha, Mb=Mb, alpha_dev=alpha_dev, gmean=gmean, pi0=pi0)  # :296
         it, halving = 1, 0
         conv_beta = False
         while not conv_beta:  # :300
-            state = dict(gmean=gmean, Mb=Mb, alpha=alpha, alpha_dev=alpha_dev, W=W, psi=psi, step=step,
+            state = dict(gmean=gmean, Mb=Mb, alpha=alpha, alpha_dev=alpha_dev, W=W, psi=cols_of(psi), step=step,
                          wt_zinb=wt_zinb, pi0=pi0)
             new, loglik_tmp, aux = inner_iteration(Y, state, grp, rep_ind, ctl, k_huber, lambda_a, lambda_b,
                                                    zeroinf, pi0_fn)
@@ -327,7 +361,7 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, lambda_a=0.01, lambda_b=16.0, step_f
                 if zeroinf.any():  # :494-504
                     with np.errstate(over="ignore"):
                         mu = np.exp(alpha @ W.T + Mb[:, grp] + gmean[:, None])
-                    wt_zinb = zinb_weights(Y, mu, psi, pi0, zeroinf, wt_zinb)
+                    wt_zinb = zinb_weights(Y, mu, cols_of(psi), pi0, zeroinf, wt_zinb)
                 halving += 1
                 if halving >= 3:
                     loglik_tmp = loglik
@@ -352,14 +386,14 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, lambda_a=0.01, lambda_b=16.0, step_f
             updt_psi = abs(logl_outer[-1] - logl_outer_tmp) / abs(logl_outer[-1]) > 1e-8
         offs = best["alpha"] @ best["W"].T + best["Mb"][:, grp]
         if updt_psi:
-            psi_new = psi_fn(Y, offs, wt_zinb, psi)
+            psi_new = refresh_psi(offs, wt_zinb, psi)
             okp = np.isfinite(psi_new)
             psi = np.where(okp, psi_new, psi)
         W, alpha, Mb, alpha_dev, gmean, pi0 = (best["W"], best["alpha"], best["Mb"], best["alpha_dev"],
                                                 best["gmean"], best["pi0"])
         best["psi"] = psi
         lmu = gmean[:, None] + Mb[:, grp] + alpha @ W.T
-        logl_outer.append(loglik_matrix(Y, lmu, psi, pi0, zeroinf).sum())  # :577-593
+        logl_outer.append(loglik_matrix(Y, lmu, cols_of(psi), pi0, zeroinf).sum())  # :577-593
         if iter_outer > 1:  # :596-598
             conv = ((logl_outer[-1] - logl_outer[-2]) / abs(logl_outer[-2]) < 1e-4) or iter_outer >= outer_maxit
     return {"counts": Y, "W": W, "M": M, "ctl": ctl, "logl": np.array(logl_outer), "a": alpha, "Mb": Mb,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ruvnb_disp_newton", "ruvnb_fit_nb", "ruvnb_get_res", "ruvnb_fast_W_all", "ruvnb_fast_Mb_all", "ruvnb_fast_cap_psi",
     "ruvnb_fast_init", "ruvnb_fast_begin_outer", "ruvnb_fast_iteration", "ruvnb_fast_halve_steps", "ruvnb_fast_accept",
     "ruvnb_set_cell_shard", "ruvnb_set_row_mask", "ruvnb_upload_counts_rows", "ruvnb_upload_counts_done", "ruvnb_get_cells",
-    "ruvnb_upload_counts_csc", "ruvnb_get_res_csc",
+    "ruvnb_upload_counts_csc", "ruvnb_get_res_csc", "ruvnb_set_batches", "ruvnb_nbatch", "ruvnb_set_psi_callback",
     "ruvnb_host_alloc", "ruvnb_host_free", "ruvnb_get_res_ex", "ruvnb_fast_res", "ruvnb_selftest_squeeze_var", "ruvnb_estimate_disp_r", "ruvnb_set_res_zinb",
 ]
 
@@ -140,6 +140,9 @@ def load():
     lib.ruvnb_host_free.argtypes = [vp]
     lib.ruvnb_host_free.restype = None
     lib.ruvnb_get_res_ex.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int, vp, C.c_int64, C.c_int64, C.POINTER(ResStats)]
+    lib.ruvnb_set_batches.argtypes = [vp, vp, C.c_int64, C.c_int]
+    lib.ruvnb_nbatch.argtypes = [vp]
+    lib.ruvnb_set_psi_callback.argtypes = [vp, PSI_FN, vp]
     lib.ruvnb_upload_counts_csc.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int64]
     lib.ruvnb_get_res_csc.argtypes = [vp, C.c_int, C.c_int64, vp, C.c_int, C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, C.POINTER(C.c_int64),
                                       C.POINTER(ResStats)]
@@ -150,6 +153,9 @@ def load():
             pass
     _lib = lib
     return lib
+
+
+PSI_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)   # ruvnb_psi_fn(user, ctx)
 
 
 class RuvnbError(RuntimeError):
@@ -201,6 +207,30 @@ class Context:
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(uid))
         self._ck(self.lib.ruvnb_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
 
+    def set_batches(self, batch):
+        """Batch label of every cell (any integer labels; renumbered 0.. in sorted order, the reference's 1..max(batch)) for a
+        batch-specific dispersion; before set_design.  Returns the 0-based labels."""
+        lab, b0 = np.unique(np.asarray(batch), return_inverse=True)
+        b0 = np.ascontiguousarray(b0, dtype=np.int32)
+        self._ck(self.lib.ruvnb_set_batches(self.h, _ptr(b0), b0.size, int(lab.size)))
+        self.nbatch = int(lab.size)
+        return b0
+
+    def set_psi_callback(self, fn):
+        """fn(ctx) is called at every dispersion refresh of fit_nb (it reads the state and calls set_state("psi", ...)); None removes it."""
+        if fn is None:
+            self._psi_cb = PSI_FN(0)
+        else:
+            def tramp(_user, _ctx):
+                try:
+                    fn(self)
+                    return 0
+                except Exception as e:      # an exception must not cross the C frame
+                    self._psi_cb_error = e
+                    return -1
+            self._psi_cb = PSI_FN(tramp)
+        self._ck(self.lib.ruvnb_set_psi_callback(self.h, self._psi_cb, None))
+
     def set_design(self, G, N, grp, ctl, zeroinf=None, rows=None, m=None):
         grp = np.ascontiguousarray(grp, dtype=np.int32)
         ctl = np.ascontiguousarray(np.asarray(ctl).astype(np.uint8))
@@ -244,6 +274,9 @@ class Context:
 
     # ---- state ------------------------------------------------------------------------------
     def _shape(self, name):
+        nb = getattr(self, "nbatch", 1)
+        if name in ("psi", "psi_w") and nb > 1:
+            return (self.Gl, nb)
         return {"W": (self.N, self.k), "alpha": (self.Gl, self.k), "alpha_dev": (self.Gl, self.k),
                 "Mb": (self.Gl, self.m), "cell_loglik": (self.N,), "cell_step": (self.N,),
                 "wt_ctl": (self.n_ctl,)}.get(name, (self.Gl,))
@@ -335,13 +368,18 @@ class Context:
         return out
 
     def fit_nb(self, opts, W0=None, psi_inject=None, trace_cap=4096):
-        """`ruvnb_fit_nb`.  psi_inject: (n_psi, Gl) array or None."""
+        """`ruvnb_fit_nb`.  psi_inject: (n_psi, Gl) array or None; with batches (n_psi, Gl, nbatch)."""
         if W0 is not None:
             self.k = int(np.asarray(W0).shape[1])
             W0 = np.asfortranarray(W0, dtype=np.float64)
         n_psi = 0
         if psi_inject is not None:
-            psi_inject = np.ascontiguousarray(np.atleast_2d(psi_inject), dtype=np.float64)
+            nb = getattr(self, "nbatch", 1)
+            if nb > 1:   # every schedule entry as R's G x nbatch matrix, column-major
+                p3 = np.asarray(psi_inject, dtype=np.float64).reshape(-1, self.Gl, nb)
+                psi_inject = np.ascontiguousarray(np.transpose(p3, (0, 2, 1)))
+            else:
+                psi_inject = np.ascontiguousarray(np.atleast_2d(psi_inject), dtype=np.float64)
             n_psi = psi_inject.shape[0]
         trace = (TraceRec * trace_cap)()
         logl = np.full(max(1, opts.outer_maxit), np.nan)

@@ -68,15 +68,76 @@ def init_W(Y, ctl, k):
     return V
 
 
+def _quantcut(x, q):
+    """as.numeric(gtools::quantcut(x, q = q)) (R/ruvIIInb.R:97,120): bin 1..q of every value, breaks at the type-7 quantiles
+    seq(0, 1, length = q + 1), intervals closed on the right, the lowest value included; tied breaks are merged."""
+    x = np.asarray(x, dtype=np.float64)
+    br = np.unique(np.quantile(x, np.linspace(0.0, 1.0, int(q) + 1)))
+    if br.size < 2:
+        return np.ones(x.size, dtype=np.int64)
+    return np.clip(np.searchsorted(br, x, side="left"), 1, br.size - 1).astype(np.int64)
+
+
+def add_pseudocells(Y, M, batch, nc_pool=20, batch_disp=False, rng=None):
+    """The pseudo-cells of `use.pseudosample = TRUE` (R/ruvIIInb.R:83-144) for a (winsorized) G x N count matrix: inside every
+    replicate group (stratum) and batch the cells are binned by library size (gtools::quantcut of sf = colSums(Y)/mean, :54-55,
+    into max(round(n / nc.pool), 1) bins) and every pool adds one cell drawn as rbinom(size = rowSums(pool), prob = 1/ncol(pool))
+    (:122-123); the pseudo-cells of a stratum form a replicate group of their own (a new column of M, :130-135) and get batch
+    btc + max(batch) -- or 2 against 1 for the real cells when batch.disp = FALSE (:138-141).  R's RNG stream cannot be
+    reproduced: `rng` is a numpy Generator (default: seed 0).  Returns (Y_ext, M_ext, batch_ext)."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    Y = np.asarray(Y)
+    M = np.asarray(M).astype(bool)
+    batch = np.asarray(batch).astype(np.int64)
+    G, nsc = Y.shape
+    strata = np.argmax(M, axis=1)                        # apply(M, 1, which), :50
+    sf = Y.sum(axis=0).astype(np.float64)
+    sf = sf / sf.mean()                                  # :54-55
+    bmax = int(batch.max())
+    new_cols, new_batch = [], []
+    Mx = M
+    for st in list(dict.fromkeys(strata.tolist())):      # unique(na.omit(strata)): order of first appearance
+        added = 0
+        for btc in list(dict.fromkeys(batch.tolist())):  # unique(batch)
+            sel = np.where((batch == btc) & (strata == st))[0]
+            if sel.size > 1:                             # :119
+                nq = max(int(np.round(sel.size / nc_pool)), 1)   # R's round(): half to even, like numpy
+                qsf = _quantcut(sf[sel], nq)
+                for qv in range(1, int(qsf.max()) + 1):
+                    pool = Y[:, sel[qsf == qv]]
+                    if pool.shape[1] == 0:
+                        continue
+                    new_cols.append(rng.binomial(pool.sum(axis=1).astype(np.int64), 1.0 / pool.shape[1]))
+                    new_batch.append(btc + bmax)
+                    added += 1
+        if (strata == st).sum() > 1 and added:           # :130-135: a new replicate-group column for this stratum's pseudo-cells
+            rows = Mx.shape[0]
+            Mx = np.vstack([Mx, np.zeros((added, Mx.shape[1]), dtype=bool)])
+            col = np.zeros(Mx.shape[0], dtype=bool)
+            col[rows:] = True
+            Mx = np.hstack([Mx, col[:, None]])
+    if not new_cols:
+        return Y, M, batch
+    Yx = np.concatenate([Y, np.stack(new_cols, axis=1).astype(Y.dtype)], axis=1)
+    bx = np.concatenate([batch, np.asarray(new_batch, dtype=np.int64)])
+    if not batch_disp:
+        bx = np.where(bx > bmax, 2, 1)                   # :138-139
+    return Yx, Mx, bx
+
+
 def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda_b=16, batch=None, step_fac=0.5,
               inner_maxit=50, outer_maxit=25, ncores=2, use_pseudosample=False, nc_pool=20, batch_disp=False,
-              zeroinf=None, W0=None, psi=None, device=0, rownames=None, return_trace=False):
+              zeroinf=None, W0=None, psi=None, device=0, rownames=None, return_trace=False, rng=None, pseudo=None):
     """`ruvIII.nb` (R/ruvIIInb.R:27-629).  Y: G x N counts; M: N x m replicate matrix with exactly one TRUE per row
     (:206); ctl: logical / index vector of control genes.  Extra arguments of the mirror: W0 (injects the initial W
-    instead of the SVD), psi (injects a dispersion vector or schedule instead of estimateDisp), device.
+    instead of the SVD; with pseudo-cells it has one row per cell INCLUDING them), psi (injects a dispersion vector or schedule
+    instead of estimateDisp; G x nbatch per entry for a batch-specific fit), rng (numpy Generator for the pseudo-cell draws) or
+    pseudo = (Y_ext, M_ext, batch_ext) (injects the pseudo-cells themselves: they depend on R's RNG in the reference), device.
     Returns the reference's list as a dict: counts, W, M, ctl, logl, a, Mb, gmean, pi0, psi, L.a, L.b, batch."""
-    if use_pseudosample:
-        raise NotImplementedError("use.pseudosample " + _UNSUPPORTED)
+    if batch is None and batch_disp:            # :65-68
+        batch_disp = False
+    if batch is None and use_pseudosample:      # :71-74
+        use_pseudosample = False
     if ortho_W:
         raise NotImplementedError("ortho.W " + _UNSUPPORTED)
     sparse_in = _is_sparse(Y)
@@ -93,10 +154,12 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
     if (M.sum(axis=0) == 0).any():
         raise ValueError("Each column of M matrix must have at least one non-zero entry")   # R/fastruvIIInb.R:60
     ctl = _as_logical_ctl(ctl, G, rownames)
-    batch = np.ones(N, dtype=np.int64) if batch is None else np.asarray(batch)              # :64-66
-    if batch_disp and len(np.unique(batch)) > 1:
-        raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
+    batch = np.ones(N, dtype=np.int64) if batch is None else np.asarray(batch)              # :77-80
+    if batch.shape[0] != N:
+        raise ValueError("batch must have one entry per cell")
     zi = np.zeros(N, dtype=bool) if zeroinf is None else np.asarray(zeroinf).astype(bool)   # :39-40
+    if use_pseudosample:                        # :147-152: only NB models with pseudo-samples
+        zi = np.zeros(N, dtype=bool)
     # :53-62: Winsorize + ceiling on the device, THEN drop the genes that are all zero (a gene expressed in fewer than 0.5 % of
     # the cells has a 99.5 % quantile of 0: the cap zeroes the whole row, and the reference removes it only after the cap).
     # Genes that are all zero in the raw data are certainly all zero after it: they never travel.
@@ -105,34 +168,94 @@ def ruvIII_nb(Y, M, ctl, k=2, robust=False, ortho_W=False, lambda_a=0.01, lambda
                              step_fac=float(step_fac), inner_maxit=int(inner_maxit), outer_maxit=int(outer_maxit),
                              zinb=int(zi.any()))
     keep = np.asarray((Y > 0).sum(axis=1)).ravel() > 0
+    nb_fit = len(np.unique(batch)) if (batch_disp or use_pseudosample) else 1    # :88-91,145: batch labels only matter for psi
     ctx = _lib.Context(device)
+    bctx = []
     try:
+        if nb_fit > 1 and not use_pseudosample:
+            ctx.set_batches(batch)
         ctx.set_design(int(keep.sum()), N, grp, ctl[keep], zeroinf=zi if zi.any() else None)
         _upload_any(ctx, Y, rows=np.where(keep)[0])
         _, nz = ctx.winsorize()
         counts = ctx.get_counts()
-        if (nz == 0).any():            # rows emptied by the cap: the fit context holds the surviving rows only (:57-62)
+        M_fit, batch_fit, N_fit, counts_fit = M, batch, N, counts
+        if (nz == 0).any() or use_pseudosample:
+            # rows emptied by the cap leave (:57-62), pseudo-cells join (:83-144): the fit context holds that matrix
             ctx.close()
             alive = nz > 0
             keep[np.where(keep)[0][~alive]] = False
-            counts = np.ascontiguousarray(counts[alive])
+            counts = counts_fit = np.ascontiguousarray(counts[alive])
+            if use_pseudosample:
+                counts_fit, M_fit, batch_fit = pseudo if pseudo is not None else add_pseudocells(counts, M, batch, nc_pool, batch_disp, rng)
+                counts_fit = np.ascontiguousarray(counts_fit, dtype=np.int32)
+                N_fit = counts_fit.shape[1]
+                nb_fit = len(np.unique(batch_fit))
+                grp = np.argmax(M_fit, axis=1).astype(np.int32)
+                zi = np.zeros(N_fit, dtype=bool)
             ctx = _lib.Context(device)
-            ctx.set_design(counts.shape[0], N, grp, ctl[keep], zeroinf=zi if zi.any() else None)
-            ctx.upload_counts(counts)   # already capped (the cap of a capped row is the same cap)
+            if nb_fit > 1:
+                ctx.set_batches(batch_fit)
+            ctx.set_design(counts_fit.shape[0], N_fit, grp, ctl[keep], zeroinf=zi if zi.any() else None)
+            ctx.upload_counts(counts_fit)   # already capped (the cap of a capped row is the same cap)
         ctlk = ctl[keep]
         if ctlk.sum() == 0:
             raise ValueError("no control gene is left after removing all-zero genes")
         if W0 is None:
             W0, _, _ = ctx.init_W(int(k))        # H1 on the device (subspace iteration on the resident control rows)
-        psi_inject = None if psi is None else np.atleast_2d(np.asarray(psi, dtype=np.float64))[:, keep]
+        psi_inject = None
+        if psi is not None:
+            psi_inject = np.asarray(psi, dtype=np.float64)
+            psi_inject = (psi_inject.reshape(-1, G, nb_fit) if nb_fit > 1 else np.atleast_2d(psi_inject))[:, keep]
+        elif nb_fit > 1:
+            # one estimateDisp.par per batch on that batch's cells (:213-220,542-548): a context per batch, refreshed through the
+            # fit's dispersion hook
+            b0 = np.unique(batch_fit, return_inverse=True)[1]
+            for B in range(nb_fit):
+                idx = np.where(b0 == B)[0]
+                present, gc = np.unique(grp[idx], return_inverse=True)     # replicate groups that occur in this batch
+                c2 = _lib.Context(device)
+                bctx.append((c2, idx, present))
+                c2.set_design(counts_fit.shape[0], idx.size, gc.astype(np.int32), ctlk, zeroinf=zi[idx] if zi.any() else None)
+                c2.upload_counts(np.ascontiguousarray(counts_fit[:, idx]))
+
+            def refresh(c):
+                W_, a_, Mb_, old = c.get_state("W"), c.get_state("alpha"), c.get_state("Mb"), c.get_state("psi")
+                new = old.copy()
+                for B, (c2, idx, present) in enumerate(bctx):
+                    c2.set_state("W", W_[idx])
+                    c2.set_state("alpha", a_)
+                    c2.set_state("Mb", Mb_[:, present])
+                    if zi.any():
+                        c2.set_state("pi0", c.get_state("pi0"))
+                        c2.set_state("psi_w", c.get_state("psi_w")[:, B])
+                    try:
+                        c2.estimate_disp(opts)
+                        col = c2.get_state("psi")
+                    except _lib.RuvnbError:                                # tryCatch(..., error = function(e) NA), :545
+                        col = np.full(old.shape[0], np.nan)
+                    ok = np.isfinite(col)                                  # :564
+                    new[ok, B] = col[ok]
+                c.set_state("psi", new)
+
+            ctx.set_psi_callback(refresh)
         logl, recs, stats = ctx.fit_nb(opts, W0=np.asarray(W0, dtype=np.float64), psi_inject=psi_inject)
-        out = {"counts": counts, "W": ctx.get_state("W"), "M": M, "ctl": ctlk, "logl": logl, "a": ctx.get_state("alpha"),
-               "Mb": ctx.get_state("Mb"), "gmean": ctx.get_state("gmean"), "psi": ctx.get_state("psi"),
+        psi_out, W_out = ctx.get_state("psi"), ctx.get_state("W")
+        if use_pseudosample:                                               # :618-624: drop what belongs to the pseudo-cells
+            nb_org = len(np.unique(batch)) if batch_disp else 1
+            W_out = W_out[:N]
+            M_fit = M_fit[:N]
+            psi_out = psi_out[:, :nb_org] if psi_out.ndim == 2 else psi_out
+            if psi_out.ndim == 2 and psi_out.shape[1] == 1:
+                psi_out = psi_out[:, 0]
+        out = {"counts": counts, "W": W_out, "M": M_fit, "ctl": ctlk, "logl": logl, "a": ctx.get_state("alpha"),
+               "Mb": ctx.get_state("Mb"), "gmean": ctx.get_state("gmean"), "psi": psi_out,
                "L.a": lambda_a, "L.b": lambda_b, "batch": batch}
         pi0 = ctx.get_state("pi0")
     finally:
         ctx.close()
-    out["pi0"] = np.outer(pi0, zi.astype(np.float64)) if zi.any() else None   # :611-626
+        for c2, _, _ in bctx:
+            c2.close()
+    out["pi0"] = np.outer(pi0, zi[:N].astype(np.float64)) if zi.any() else None   # :611-626
     if sparse_in:                                                              # :611-612: counts leave as a sparse matrix
         import scipy.sparse as sp
         out["counts"] = sp.csc_matrix(out["counts"])
@@ -163,8 +286,17 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
         if t not in ("pearson", "logcounts", "quantile"):
             raise ValueError(f"unknown type '{t}'")
     last = [t for t in ("pearson", "logcounts", "quantile") if t in kinds][-1]
-    if np.ndim(out["psi"]) != 1:
-        raise NotImplementedError("batch-specific dispersion " + _UNSUPPORTED)
+    psi_m = np.asarray(out["psi"], dtype=np.float64)
+    bpsi = psi_m.ndim == 2 and psi_m.shape[1] > 1          # a batch-specific fit: out$psi[, curr.batch] (:59-62,101-121)
+    if psi_m.ndim == 2 and not bpsi:
+        psi_m = psi_m[:, 0]
+    if bpsi:
+        if batch is None:
+            batch = out.get("batch")
+        if batch is None:
+            raise ValueError("a batch-specific dispersion needs the batch of every cell")
+        if sorted(np.unique(batch).tolist()) != list(range(1, psi_m.shape[1] + 1)):
+            raise ValueError("batch must take the values 1..ncol(psi): it indexes the columns of psi (R/get.res.R:60)")
     ranks = ranks or Ranks()
     Y = out["counts"] if _is_sparse(out["counts"]) else np.ascontiguousarray(out["counts"], dtype=np.int32)
     G, N = Y.shape
@@ -179,6 +311,8 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
     with _lib.Context(device) as ctx:
         if ranks.world > 1:
             ctx.comm_init(ranks.unique_id(), ranks.rank, ranks.world)
+        if bpsi:
+            ctx.set_batches(np.asarray(batch)[c0:c0 + N] if len(batch) != N else batch)
         ctx.set_design(G, N, grp, np.asarray(out["ctl"], bool), m=m)
         if ranks.world > 1 or N_total != N:
             ctx.set_cell_shard(N_total, c0)
@@ -186,7 +320,7 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
         ctx.set_state("W", out["W"])
         ctx.set_state("alpha", out["a"])
         ctx.set_state("gmean", out["gmean"])
-        ctx.set_state("psi", out["psi"])
+        ctx.set_state("psi", psi_m)
         Mbg = np.zeros((G, m))
         if not per_cell:
             Mbg[:, :Mb.shape[1]] = Mb
@@ -198,7 +332,8 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
             zi = (P != 0).any(axis=0)
             b = np.ones(N_total, dtype=np.int64) if batch is None else np.asarray(batch).astype(np.int64)
             ctx.set_state("pi0", P.max(axis=1))
-            ctx.set_res_zinb(zi[b[c0:c0 + N] - 1], float(zi.mean()))
+            # the quantile call's omega: rowMeans(out$pi0) (:95), or column ref.batch of out$pi0 with a batch-specific psi (:112-114)
+            ctx.set_res_zinb(zi[b[c0:c0 + N] - 1], float(zi[int(np.argmin(psi_m.mean(axis=0)))]) if bpsi else float(zi.mean()))
         if sink.startswith("csc"):
             import scipy.sparse as sp
             cp, ri, vv, st = ctx.get_res_csc(_lib.RES_KINDS[last], block_size=block_size, Mb_cells=Mb if per_cell else None,

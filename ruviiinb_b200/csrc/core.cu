@@ -153,6 +153,26 @@ int ruvnb_comm_init(ruvnb_ctx* ctx, const unsigned char id[128], int rank, int n
 }
 
 // ---- problem set-up -------------------------------------------------------------------------------
+// batch of every cell (0-based), for a batch-specific dispersion psi[g, batch(c)] (R/ruvIIInb.R:213-220,278-283,306-315,542-548).
+// Must precede ruvnb_set_design: the cell permutation keeps the batches of a replicate group apart.
+int ruvnb_set_batches(ruvnb_ctx* ctx, const int32_t* batch_of_cell, int64_t N, int nbatch) {
+  if (!ctx) return RUVNB_EARG;
+  if (ctx->have_design) return ctx->fail(RUVNB_ESTATE, "set_batches: call it before ruvnb_set_design (the cell order depends on it)");
+  if (nbatch < 1 || nbatch > 127 || (nbatch > 1 && (!batch_of_cell || N <= 0))) return ctx->fail(RUVNB_EARG, "set_batches: nbatch = %d outside 1..127, or no labels", nbatch);
+  ctx->nbatch = nbatch; ctx->batch.clear();
+  if (nbatch == 1) return RUVNB_OK;
+  ctx->batch.assign(batch_of_cell, batch_of_cell + N);
+  std::vector<long long> cnt(nbatch, 0);
+  for (int64_t c = 0; c < N; ++c) {
+    const int b = ctx->batch[c];
+    if (b < 0 || b >= nbatch) { ctx->nbatch = 1; ctx->batch.clear(); return ctx->fail(RUVNB_EARG, "set_batches: batch label %d of cell %lld outside 0..%d", b, (long long)c, nbatch - 1); }
+    cnt[b]++;
+  }
+  for (int b = 0; b < nbatch; ++b) if (!cnt[b]) { ctx->nbatch = 1; ctx->batch.clear(); return ctx->fail(RUVNB_EARG, "set_batches: batch %d has no cell", b); }
+  return RUVNB_OK;
+}
+int ruvnb_nbatch(const ruvnb_ctx* ctx) { return ctx ? ctx->nbatch : 0; }
+
 int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t* grp_of_cell, const uint8_t* ctl,
                      const uint8_t* zeroinf, int64_t g0, int64_t g1) {
   if (!ctx) return RUVNB_EARG;
@@ -177,26 +197,38 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   // (a cell shard may hold no cell of some group: only the IRLS operators need every group, and check_ready refuses them)
   ctx->empty_group = -1;
   for (int j = 0; j < m; ++j) if (ctx->group_n[j] == 0 && ctx->empty_group < 0) ctx->empty_group = j;
+  // runs of cells: one per (group, batch), group-major, each padded to whole chunks -- a group stays one contiguous run of chunks
+  // (its per-batch sub-runs follow each other), and a chunk never mixes batches
+  const int nb = ctx->nbatch;
+  if (nb > 1 && (long long)ctx->batch.size() != N) return ctx->fail(RUVNB_EARG, "set_design: ruvnb_set_batches was given %lld cells, the design has %lld", (long long)ctx->batch.size(), (long long)N);
+  std::vector<int> run_n((size_t)m * nb, 0);
+  ctx->batch_n.assign(nb, 0);
+  for (long long c = 0; c < N; ++c) { const int b = nb > 1 ? ctx->batch[c] : 0; run_n[(size_t)ctx->grp[c] * nb + b]++; ctx->batch_n[b]++; }
   ctx->group_chunk0.assign(m, 0);
+  std::vector<int> run_chunk0((size_t)m * nb, 0);
   int nch = 0;
-  for (int j = 0; j < m; ++j) { ctx->group_chunk0[j] = nch; nch += (ctx->group_n[j] + CH - 1) / CH; }
-  const int nch_real = nch;
+  for (int j = 0; j < m; ++j) {
+    ctx->group_chunk0[j] = nch;
+    for (int b = 0; b < nb; ++b) { run_chunk0[(size_t)j * nb + b] = nch; nch += (run_n[(size_t)j * nb + b] + CH - 1) / CH; }
+  }
+  ctx->group_nch.assign(m, 0);
+  for (int j = 0; j < m; ++j) ctx->group_nch[j] = (j + 1 < m ? ctx->group_chunk0[j + 1] : nch) - ctx->group_chunk0[j];
   nch = (nch + CHPAD - 1) / CHPAD * CHPAD;  // whole tiles: trailing chunks are empty (valid = 0)
   ctx->nchunks = nch; ctx->Np = (long long)nch * CH;
-  ctx->chunk_grp.assign(nch, ctx->m - 1); ctx->chunk_valid.assign(nch, 0);
-  (void)nch_real;
-  for (int j = 0; j < m; ++j) {
-    int nc = (ctx->group_n[j] + CH - 1) / CH;
-    for (int q = 0; q < nc; ++q) {
-      ctx->chunk_grp[ctx->group_chunk0[j] + q] = j;
-      ctx->chunk_valid[ctx->group_chunk0[j] + q] = std::min(CH, ctx->group_n[j] - q * CH);
+  ctx->chunk_grp.assign(nch, ctx->m - 1); ctx->chunk_valid.assign(nch, 0); ctx->chunk_batch.assign(nch, 0);
+  for (int j = 0; j < m; ++j)
+    for (int b = 0; b < nb; ++b) {
+      const int n = run_n[(size_t)j * nb + b], nc = (n + CH - 1) / CH, q0 = run_chunk0[(size_t)j * nb + b];
+      for (int q = 0; q < nc; ++q) {
+        ctx->chunk_grp[q0 + q] = j; ctx->chunk_batch[q0 + q] = b;
+        ctx->chunk_valid[q0 + q] = std::min(CH, n - q * CH);
+      }
     }
-  }
   ctx->pos2cell.assign(ctx->Np, -1); ctx->cell2pos.assign(N, 0);
-  std::vector<long long> fill(m);
-  for (int j = 0; j < m; ++j) fill[j] = (long long)ctx->group_chunk0[j] * CH;
-  for (long long c = 0; c < N; ++c) {  // stable: cells keep their order inside a group
-    long long p = fill[ctx->grp[c]]++;
+  std::vector<long long> fill((size_t)m * nb);
+  for (size_t r = 0; r < fill.size(); ++r) fill[r] = (long long)run_chunk0[r] * CH;
+  for (long long c = 0; c < N; ++c) {  // stable: cells keep their order inside a run
+    long long p = fill[(size_t)ctx->grp[c] * nb + (nb > 1 ? ctx->batch[c] : 0)]++;
     ctx->pos2cell[p] = (int)c; ctx->cell2pos[c] = (int)p;
   }
   ctx->ctl_gene.clear();
@@ -213,10 +245,12 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
   RET(dev_upload(ctx, &ctx->d_chunk_grp, ctx->chunk_grp));
   RET(dev_upload(ctx, &ctx->d_chunk_valid, ctx->chunk_valid));
   {
-    if (m > (1 << 22)) return ctx->fail(RUVNB_EARG, "set_design: more than 2^22 replicate groups");
+    if (m > 65535) return ctx->fail(RUVNB_EARG, "set_design: more than 65535 replicate groups");
     std::vector<int> meta(nch);
-    for (int q = 0; q < nch; ++q) meta[q] = (ctx->chunk_grp[q] << 8) | ctx->chunk_valid[q];
+    for (int q = 0; q < nch; ++q) meta[q] = (ctx->chunk_batch[q] << 24) | (ctx->chunk_grp[q] << 8) | ctx->chunk_valid[q];
     RET(dev_upload(ctx, &ctx->d_chunk_meta, meta));
+    RET(dev_upload(ctx, &ctx->d_chunk_batch, ctx->chunk_batch));
+    RET(dev_upload(ctx, &ctx->d_group_nch, ctx->group_nch));
   }
   RET(dev_upload(ctx, &ctx->d_group_chunk0, ctx->group_chunk0));
   RET(dev_upload(ctx, &ctx->d_group_n, ctx->group_n));
@@ -564,13 +598,13 @@ static int alloc_set(ruvnb_ctx* ctx, StateSet* s) {
   RET(dev_alloc(ctx, &s->alpha, Gl * ctx->K));
   RET(dev_alloc(ctx, &s->adev, Gl * ctx->K));
   RET(dev_alloc(ctx, &s->W, ctx->Np * ctx->K));
-  RET(dev_alloc(ctx, &s->psi, Gl));
+  RET(dev_alloc(ctx, &s->psi, Gl * ctx->nbatch));     // [nbatch][Gl]
   RET(dev_alloc(ctx, &s->pi0, Gl));
   RET(dev_alloc(ctx, &s->sigma, Gl));
-  RET(dev_alloc(ctx, &s->psi_w, Gl));
+  RET(dev_alloc(ctx, &s->psi_w, Gl * ctx->nbatch));
   RET(dev_alloc(ctx, &s->wtctl, ctx->n_ctl));
   CK(cudaMemsetAsync(s->wtctl, 0, (size_t)ctx->n_ctl * 8, ctx->stream));
-  k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(s->psi_w, Gl, 1.0);
+  k_fill<<<nblk(Gl * ctx->nbatch, 256), 256, 0, ctx->stream>>>(s->psi_w, Gl * ctx->nbatch, 1.0);
   CKL();
   CK(cudaMemsetAsync(s->sigma, 0, Gl * 8, ctx->stream));
   s->sig_valid = false;
@@ -580,7 +614,7 @@ static int alloc_set(ruvnb_ctx* ctx, StateSet* s) {
   CK(cudaMemsetAsync(s->adev, 0, Gl * ctx->K * 8, ctx->stream));
   CK(cudaMemsetAsync(s->W, 0, ctx->Np * ctx->K * 8, ctx->stream));
   CK(cudaMemsetAsync(s->pi0, 0, Gl * 8, ctx->stream));
-  k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(s->psi, Gl, 1.0);
+  k_fill<<<nblk(Gl * ctx->nbatch, 256), 256, 0, ctx->stream>>>(s->psi, Gl * ctx->nbatch, 1.0);
   CKL();
   return RUVNB_OK;
 }
@@ -641,10 +675,10 @@ int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->hint, Gl * 3));
   k_fill<<<nblk(Gl * 3, 256), 256, 0, ctx->stream>>>(ctx->hint, Gl * 3, -1.0);  // tg < 0: no hint yet
   CKL();
-  RET(dev_alloc(ctx, &ctx->tabL, Gl * YT));
-  RET(dev_alloc(ctx, &ctx->tabR, Gl * YT));
-  RET(dev_alloc(ctx, &ctx->lgr, Gl));
-  RET(dev_alloc(ctx, &ctx->ctl_tabR, (long long)ctx->n_ctl * YT));
+  RET(dev_alloc(ctx, &ctx->tabL, Gl * ctx->nbatch * YT));   // [nbatch][Gl][YT]
+  RET(dev_alloc(ctx, &ctx->tabR, Gl * ctx->nbatch * YT));
+  RET(dev_alloc(ctx, &ctx->lgr, Gl * ctx->nbatch));
+  RET(dev_alloc(ctx, &ctx->ctl_tabR, (long long)ctx->n_ctl * ctx->nbatch * YT));
   RET(dev_alloc(ctx, &ctx->w_fail, ctx->Np + 1));
   RET(dev_alloc(ctx, &ctx->cert_diag, 8));
   CK(cudaMemsetAsync(ctx->cert_diag, 0, 8 * sizeof(int), ctx->stream));
@@ -661,7 +695,7 @@ int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->sumsq, K));
   RET(dev_alloc(ctx, &ctx->med, K));
   RET(dev_alloc(ctx, &ctx->mad, K));
-  RET(dev_alloc(ctx, &ctx->ctlpack, (long long)ctx->n_ctl * (5 + 2 * K + m)));
+  RET(dev_alloc(ctx, &ctx->ctlpack, (long long)ctx->n_ctl * (3 + 2 * ctx->nbatch + 2 * K + m)));
   RET(dev_alloc(ctx, &ctx->scal, 16));
   if (ctx->nranks > 1) {
     RET(dev_alloc(ctx, &ctx->alpha_full, ctx->G * K + 1));
@@ -671,7 +705,7 @@ int ensure_state(ruvnb_ctx* ctx, int K) {
   return RUVNB_OK;
 }
 
-enum StateKind { SK_VEC, SK_GK, SK_GM, SK_W, SK_CELL, SK_CTL };
+enum StateKind { SK_VEC, SK_GK, SK_GM, SK_W, SK_CELL, SK_CTL, SK_GB };   // SK_GB: Gl x nbatch, column-major on both sides
 static int state_lookup(ruvnb_ctx* ctx, const char* name, double** p, StateKind* kind) {
   StateSet& s = ctx->cur;
   if (!strcmp(name, "W")) { *p = s.W; *kind = SK_W; }
@@ -679,9 +713,9 @@ static int state_lookup(ruvnb_ctx* ctx, const char* name, double** p, StateKind*
   else if (!strcmp(name, "alpha_dev")) { *p = s.adev; *kind = SK_GK; }
   else if (!strcmp(name, "gmean")) { *p = s.gmean; *kind = SK_VEC; }
   else if (!strcmp(name, "Mb")) { *p = s.Mb; *kind = SK_GM; }
-  else if (!strcmp(name, "psi")) { *p = s.psi; *kind = SK_VEC; }
+  else if (!strcmp(name, "psi")) { *p = s.psi; *kind = SK_GB; }
   else if (!strcmp(name, "pi0")) { *p = s.pi0; *kind = SK_VEC; }
-  else if (!strcmp(name, "psi_w")) { *p = s.psi_w; *kind = SK_VEC; }
+  else if (!strcmp(name, "psi_w")) { *p = s.psi_w; *kind = SK_GB; }
   else if (!strcmp(name, "step")) { *p = ctx->step; *kind = SK_VEC; }
   else if (!strcmp(name, "loglik")) { *p = ctx->loglik; *kind = SK_VEC; }
   else if (!strcmp(name, "sigma")) { *p = ctx->sigma_exact; *kind = SK_VEC; }
@@ -705,6 +739,7 @@ int ruvnb_set_state(ruvnb_ctx* ctx, const char* name, const double* host, int k)
   std::vector<double> tmp;
   switch (kind) {
     case SK_VEC: tmp.assign(host, host + Gl); break;
+    case SK_GB: tmp.assign(host, host + Gl * ctx->nbatch); break;
     case SK_GK: tmp.resize(Gl * K); for (long long g = 0; g < Gl; ++g) for (long long l = 0; l < K; ++l) tmp[g * K + l] = host[g + Gl * l]; break;
     case SK_GM: tmp.resize(Gl * m); for (long long g = 0; g < Gl; ++g) for (long long j = 0; j < m; ++j) tmp[g * m + j] = host[g + Gl * j]; break;
     case SK_W:
@@ -732,12 +767,13 @@ int ruvnb_get_state(ruvnb_ctx* ctx, const char* name, double* host) {
   double* p; StateKind kind;
   RET(state_lookup(ctx, name, &p, &kind));
   const long long Gl = ctx->Gl, K = ctx->K, m = ctx->m, N = ctx->N, Np = ctx->Np;
-  long long n = kind == SK_VEC ? Gl : kind == SK_GK ? Gl * K : kind == SK_GM ? Gl * m : kind == SK_CELL ? Np : kind == SK_CTL ? ctx->n_ctl : Np * K;
+  long long n = kind == SK_VEC ? Gl : kind == SK_GB ? Gl * ctx->nbatch : kind == SK_GK ? Gl * K : kind == SK_GM ? Gl * m : kind == SK_CELL ? Np : kind == SK_CTL ? ctx->n_ctl : Np * K;
   std::vector<double> tmp(n);
   CK(cudaMemcpyAsync(tmp.data(), p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   switch (kind) {
     case SK_VEC: memcpy(host, tmp.data(), Gl * 8); break;
+    case SK_GB: memcpy(host, tmp.data(), (size_t)Gl * ctx->nbatch * 8); break;
     case SK_GK: for (long long g = 0; g < Gl; ++g) for (long long l = 0; l < K; ++l) host[g + Gl * l] = tmp[g * K + l]; break;
     case SK_GM: for (long long g = 0; g < Gl; ++g) for (long long j = 0; j < m; ++j) host[g + Gl * j] = tmp[g * m + j]; break;
     case SK_W: for (long long l = 0; l < K; ++l) for (long long c = 0; c < N; ++c) host[c + N * l] = tmp[l * Np + ctx->cell2pos[c]]; break;
@@ -785,7 +821,7 @@ int ensure_roworder(ruvnb_ctx* ctx) {
 int ensure_ytabs(ruvnb_ctx* ctx, const double* psi) {
   RET(ensure_roworder(ctx));
   if (ctx->ytab_ver == ctx->psi_ver && ctx->ytab_psi != nullptr) return RUVNB_OK;
-  k_build_ytabs<<<ctx->Gl, YT, 0, ctx->stream>>>(psi, ctx->Gl, ctx->tabL, ctx->tabR, ctx->lgr);
+  k_build_ytabs<<<ctx->Gl * ctx->nbatch, YT, 0, ctx->stream>>>(psi, ctx->Gl * ctx->nbatch, ctx->tabL, ctx->tabR, ctx->lgr);
   CKL();
   ctx->ytab_ver = ctx->psi_ver; ctx->ytab_psi = psi;
   return RUVNB_OK;

@@ -87,7 +87,16 @@ struct ruvnb_ctx {
   std::vector<int> pos2cell, cell2pos, chunk_grp, chunk_valid, group_chunk0, group_n;
   int *d_pos2cell = nullptr, *d_cell2pos = nullptr, *d_chunk_grp = nullptr, *d_chunk_valid = nullptr,
       *d_group_chunk0 = nullptr, *d_group_n = nullptr;
-  int* d_chunk_meta = nullptr;     // [nchunks] (group << 8) | valid cells: one load per chunk in the row walk
+  int* d_chunk_meta = nullptr;     // [nchunks] (batch << 24) | (group << 8) | valid cells: one load per chunk in the row walk
+  // batch-specific dispersion (R/ruvIIInb.R:278-283,306-315: psi[, batch]): cells carry a batch label, psi / psi_w / the count tables
+  // have one column per batch ([nbatch][Gl], R's G x nbatch column-major), and inside a replicate group the cells are ordered by
+  // batch so that every 128-cell chunk belongs to ONE batch (ruvnb_set_batches, before ruvnb_set_design)
+  ruvnb_psi_fn psi_cb = nullptr; void* psi_cb_user = nullptr;   // ruvnb_set_psi_callback
+  int nbatch = 1;
+  std::vector<int> batch;          // [N] batch of each cell, 0-based (empty: one batch)
+  std::vector<int> chunk_batch, batch_n, group_nch;
+  int* d_chunk_batch = nullptr;    // [nchunks]
+  int* d_group_nch = nullptr;      // [m] chunks of each group's run (its per-batch sub-runs are padded separately)
   // control genes
   int n_ctl = 0;
   std::vector<int> ctl_gene;       // global gene index of each control

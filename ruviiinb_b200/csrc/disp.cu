@@ -163,6 +163,7 @@ extern "C" {
 
 int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double* rowsum) {
   RET(check_ready(ctx, o));
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "this operator has no batch-specific dispersion: run it in one context per batch (see ruvnb_set_psi_callback)");
   RET(disp_grid(ctx, ctx->cur));
   const int Gl = ctx->Gl;
   std::vector<double> h((size_t)Gl * DISP_NG), rs(Gl);
@@ -183,6 +184,7 @@ int ruvnb_disp_apl_grid(ruvnb_ctx* ctx, const ruvnb_opts* o, double* l0, double*
 static int estimate_disp_impl(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, double prior_df_in, double* common_out, double* trended_out,
                               double* prior_df_out, double* prior_df_vec_out) {
   RET(check_ready(ctx, o));
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "this operator has no batch-specific dispersion: run it in one context per batch (see ruvnb_set_psi_callback)");
   StateSet& s = ctx->cur;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_start = now();
@@ -359,6 +361,7 @@ int ruvnb_estimate_disp(ruvnb_ctx* ctx, const ruvnb_opts* o, double* common_out)
 // the north_star variant of the dispersion step: per-gene Newton on log psi at the current fitted means (disp.cuh)
 extern "C" int ruvnb_disp_newton(ruvnb_ctx* ctx, const ruvnb_opts* o, double* psi_out, int maxit) {
   RET(check_ready(ctx, o));
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "this operator has no batch-specific dispersion: run it in one context per batch (see ruvnb_set_psi_callback)");
   if (!psi_out) return RUVNB_EARG;
   RET(disp_ensure(ctx));
   const int Gl = ctx->Gl;

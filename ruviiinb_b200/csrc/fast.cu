@@ -24,6 +24,7 @@ int ruvnb_fast_W_all(ruvnb_ctx* ctx, int k, double lambda_a, const double* wt_ct
                      const double* W_mad, int max_sweeps, double tol, double* W_out, int* n_sweeps, double* crit_out) {
   if (!ctx || !wt_ctl || !W_init || !W_med || !W_mad) return RUVNB_EARG;
   if (!ctx->have_counts) return ctx->fail(RUVNB_ESTATE, "fast_W_all: no counts uploaded");
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "fastruvIII.nb has no batch-specific dispersion");
   if (ctx->nranks > 1 && !ctx->cell_shard) return ctx->fail(RUVNB_ESTATE, "fast_W_all: cells are independent -- shard them (ruvnb_set_cell_shard), not the genes");
   RET(ensure_state(ctx, k));
   CK(cudaSetDevice(ctx->device));
@@ -120,6 +121,7 @@ extern "C" {
 int ruvnb_fast_Mb_all(ruvnb_ctx* ctx, double lambda_b, const int32_t* annot_grp, int64_t block_size, double* Mb_all_out) {
   if (!ctx || !annot_grp || !Mb_all_out) return RUVNB_EARG;
   if (!ctx->have_counts || ctx->K == 0 || !ctx->have_W) return ctx->fail(RUVNB_ESTATE, "fast_Mb_all: needs counts and a state (W, alpha, gmean, Mb, psi)");
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "fastruvIII.nb has no batch-specific dispersion");
   CK(cudaSetDevice(ctx->device));
   const int Gl = ctx->Gl, m = ctx->m; const long long N = ctx->N;
   StateSet& s = ctx->cur;
@@ -309,6 +311,7 @@ int ruvnb_fast_init(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* U0) {
 // steps reset to 1 (:350)
 int ruvnb_fast_begin_outer(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total) {
   RET(check_ready(ctx, o));
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "this operator has no batch-specific dispersion: run it in one context per batch (see ruvnb_set_psi_callback)");
   RET(ff_ensure(ctx));
   StateSet& c = ctx->cur;
   k_fill<<<nblk(ctx->Np, 256), 256, 0, ctx->stream>>>(ctx->ff_step, ctx->Np, 1.0); CKL();
@@ -321,6 +324,7 @@ int ruvnb_fast_begin_outer(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total) {
 // one pass of the inner-loop body (:357-531): cur -> candidate (swapped in), candidate per-cell log-likelihood in the tmp slot
 int ruvnb_fast_iteration(ruvnb_ctx* ctx, const ruvnb_opts* o, double* total_new, int bad[3]) {
   RET(check_ready(ctx, o));
+  if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "this operator has no batch-specific dispersion: run it in one context per batch (see ruvnb_set_psi_callback)");
   RET(ff_ensure(ctx));
   StateSet& c = ctx->cur; StateSet& n = ctx->nw;
   const int Gl = ctx->Gl, K = ctx->K, m = ctx->m; const long long Np = ctx->Np, N = ctx->N;

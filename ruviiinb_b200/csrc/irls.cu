@@ -133,7 +133,7 @@ static int complete_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, doub
 // RM_W = W - groupmean(W) (R/ruvIIInb.R:331-340)
 int make_rmw(ruvnb_ctx* ctx, const double* W) {
   const int K = ctx->K, m = ctx->m;
-  k_wbar<<<nblk((long long)K * m * 32, 256), 256, 0, ctx->stream>>>(W, ctx->Np, K, m, ctx->d_group_chunk0, ctx->d_group_n, ctx->Wbar);
+  k_wbar<<<nblk((long long)K * m * 32, 256), 256, 0, ctx->stream>>>(W, ctx->Np, K, m, ctx->d_group_chunk0, ctx->d_group_n, ctx->d_group_nch, ctx->d_chunk_valid, ctx->Wbar);
   CKL();
   k_rmw<<<nblk(ctx->Np * K, 256), 256, 0, ctx->stream>>>(W, ctx->Np, K, ctx->d_chunk_grp, ctx->d_chunk_valid, ctx->Wbar, ctx->RMW);
   CKL();
@@ -197,27 +197,28 @@ static int split_rows(ruvnb_ctx* ctx, bool hub, Fn fn) {
   return RUVNB_OK;
 }
 
-// control-gene parameters of the CURRENT state gathered into ctx->ctlpack: [gmean | psi | step | alpha_old (K) | alpha_new (K,
-// filled later) | Mb (m) | pi0 | psi_w] x n_ctl; genes of other ranks read 0 (the pack is then summed over the ranks)
-static __global__ void k_gather_ctlpack(int nc, int K, int m, const int* ctl_local, const double* gmean, const double* psi, const double* step,
+// control-gene parameters of the CURRENT state gathered into ctx->ctlpack: [gmean | psi (nb columns) | step | alpha_old (K) |
+// alpha_new (K, filled later) | Mb (m) | pi0 | psi_w (nb columns)] x n_ctl; genes of other ranks read 0 (the pack is then summed over
+// the ranks).  nb = batches (1 unless the dispersion is batch-specific); Gl = stride between the columns of psi / psi_w.
+static __global__ void k_gather_ctlpack(int nc, int K, int m, int nb, long long Gl, const int* ctl_local, const double* gmean, const double* psi, const double* step,
                                         const double* alpha, const double* Mb, const double* pi0, const double* psi_w, double* pk) {
-  const int per = 5 + 2 * K + m;
+  const int per = 3 + 2 * nb + 2 * K + m;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)nc * per) return;
   // field-major layout (as CtlPack expects): locate the field of element i
-  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
-  double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
+  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = p_psi + (long long)nb * nc;
+  double* p_aold = p_step + nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
   double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
   double* dst = pk + i;
   double v = 0.0;
   if (dst < p_psi) { int g = ctl_local[i]; if (g >= 0) v = gmean[g]; }
-  else if (dst < p_step) { int g = ctl_local[i - nc]; if (g >= 0) v = psi[g]; }
-  else if (dst < p_aold) { int g = ctl_local[i - 2 * nc]; if (g >= 0) v = step[g]; }
+  else if (dst < p_step) { long long q = dst - p_psi; int g = ctl_local[q % nc]; if (g >= 0) v = psi[(q / nc) * Gl + g]; }
+  else if (dst < p_aold) { int g = ctl_local[dst - p_step]; if (g >= 0) v = step[g]; }
   else if (dst < p_anew) { long long q = dst - p_aold; int g = ctl_local[q / K]; if (g >= 0) v = alpha[(long long)g * K + q % K]; }
   else if (dst < p_mb) { v = 0.0; }
   else if (dst < p_pi0) { long long q = dst - p_mb; int g = ctl_local[q / m]; if (g >= 0) v = Mb[(long long)g * m + q % m]; }
   else if (dst < p_psiw) { int g = ctl_local[dst - p_pi0]; if (g >= 0) v = pi0[g]; }
-  else { int g = ctl_local[dst - p_psiw]; if (g >= 0) v = psi_w[g]; }
+  else { long long q = dst - p_psiw; int g = ctl_local[q % nc]; if (g >= 0) v = psi_w[(q / nc) * Gl + g]; }
   *dst = v;
 }
 // this rank's slice of the all-gather buffer: [new alpha rows | current alpha rows] (each zero-padded to `per` rows), then
@@ -311,15 +312,17 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   // side stream while pass 1 runs -- nothing of it depends on this iteration's work except alpha_new, filled in later
   const int nc = ctx->n_ctl;
   double* pk = ctx->ctlpack;
-  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = pk + 2 * nc;
-  double* p_aold = pk + 3 * nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
+  const int nb = ctx->nbatch;
+  const long long per = 3 + 2 * nb + 2 * K + m;
+  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = p_psi + (long long)nb * nc;
+  double* p_aold = p_step + nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
   double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
   {
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    k_gather_ctlpack<<<nblk((long long)nc * (5 + 2 * K + m), 256), 256, 0, ctx->stream2>>>(nc, K, m, ctx->d_ctl_local, c.gmean, c.psi, ctx->step, c.alpha, c.Mb, c.pi0, c.psi_w, pk);
+    k_gather_ctlpack<<<nblk((long long)nc * per, 256), 256, 0, ctx->stream2>>>(nc, K, m, nb, Gl, ctx->d_ctl_local, c.gmean, c.psi, ctx->step, c.alpha, c.Mb, c.pi0, c.psi_w, pk);
     CKL();
     if (ctx->nranks > 1) {
-      int r = g_nccl.AllReduce(pk, pk, (size_t)nc * (5 + 2 * K + m), NCCL_F64, NCCL_SUM, ctx->comm, ctx->stream2);
+      int r = g_nccl.AllReduce(pk, pk, (size_t)nc * per, NCCL_F64, NCCL_SUM, ctx->comm, ctx->stream2);
       if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclAllReduce (control-gene pack): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     }
     CK(cudaEventRecord(ctx->ev_ctl, ctx->stream2));
@@ -406,7 +409,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   {
     CtlPack cp;
     cp.gmean = p_gmean; cp.psi = p_psi; cp.step = p_step; cp.alpha_old = p_aold; cp.alpha_new = p_anew; cp.Mb = p_mb;
-    cp.pi0 = p_pi0; cp.psi_w = p_psiw; cp.zinf = ctx->d_zinf; cp.zinb = ctx->zinb_on ? 1 : 0;
+    cp.pi0 = p_pi0; cp.psi_w = p_psiw; cp.zinf = ctx->d_zinf; cp.zinb = ctx->zinb_on ? 1 : 0; cp.chunk_batch = ctx->d_chunk_batch;
     // cells are sharded over the ranks in whole chunks; the slices are summed (disjoint) afterwards
     long long ch_per = (ctx->nchunks + ctx->nranks - 1) / ctx->nranks;
     long long pb = std::min<long long>(ctx->Np, ch_per * ctx->rank * CH), pe = std::min<long long>(ctx->Np, ch_per * (ctx->rank + 1) * CH);
@@ -458,21 +461,22 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   if (ctx->zinb_on) RET(allreduce(ctx, ctx->flags + 2, 2, NCCL_INT32));
   k_mb_finalize<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, m, ctx->flags + 3, c.Mb, n.Mb); CKL();
   // psi is fixed inside the inner loop
-  CK(cudaMemcpyAsync(n.psi, c.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  const size_t psi_bytes = (size_t)Gl * ctx->nbatch * 8;   // [nbatch][Gl]
+  CK(cudaMemcpyAsync(n.psi, c.psi, psi_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   double fin[2] = {0.0, 0.0};
   if (ctx->zinb_on) {
     // step 4a (:435-467): pi0 at the NEW parameters, then the E-step weights -- recomputed on the fly from (pi0, psi_w)
     CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(n.psi_w, c.psi_w, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(n.psi_w, c.psi_w, psi_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     int nbad_pi0 = 0;
     RET(zinb_update_pi0(ctx, n, c.pi0, n.pi0, &nbad_pi0));
     if (nbad_pi0) CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :454
-    CK(cudaMemcpyAsync(n.psi_w, n.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));             // :457-467
+    CK(cudaMemcpyAsync(n.psi_w, n.psi, psi_bytes, cudaMemcpyDeviceToDevice, ctx->stream));             // :457-467
     RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new, false, nullptr));
     fin[0] = ctx->h_flags[2]; fin[1] = ctx->h_flags[3];   // already global
   } else {
     CK(cudaMemcpyAsync(n.pi0, c.pi0, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(n.psi_w, c.psi_w, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(n.psi_w, c.psi_w, psi_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     // candidate log-likelihood (:469-484) + its Huber certificate (+ its Gram / score sums) for the next iteration
     RET(loglik_of(ctx, o, n, ctx->loglik_tmp, logl_new, fuse, fin));
     if (ctx->nranks > 1 && fin[1] > 0.0 && ctx->h_flags[3] == 0) {
@@ -500,10 +504,10 @@ static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
   CK(cudaMemcpyAsync(dst.alpha, src.alpha, Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.adev, src.adev, Gl * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.W, src.W, (size_t)ctx->Np * K * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(dst.psi, src.psi, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.psi, src.psi, Gl * ctx->nbatch * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.pi0, src.pi0, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.sigma, src.sigma, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(dst.psi_w, src.psi_w, Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dst.psi_w, src.psi_w, Gl * ctx->nbatch * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.wtctl, src.wtctl, (size_t)ctx->n_ctl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active; dst.nfail = src.nfail;
   if (ctx->faillist_for == dst.sigma) ctx->faillist_for = nullptr;   // the list was made from what this buffer held before
@@ -549,7 +553,7 @@ int ruvnb_zinb_pi0(ruvnb_ctx* ctx, const ruvnb_opts* o, int* bad) {
   if (!ctx->zinb_on) return ctx->fail(RUVNB_ESTATE, "zinb_pi0: needs opts.zinb and zeroinf flags in ruvnb_set_design");
   int nb = 0;
   RET(zinb_update_pi0(ctx, ctx->cur, ctx->cur.pi0, ctx->cur.pi0, &nb));
-  CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * ctx->nbatch * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->cur.sig_valid = false;
   if (bad) *bad = nb;
@@ -569,7 +573,7 @@ int ruvnb_restore_best(ruvnb_ctx* ctx) {
   RET(copy_set(ctx, ctx->cur, ctx->best));
   ctx->psi_ver++;   // the restored psi may differ from the one the count tables were built from (set_state / estimate_disp in between)
   // "revert zinb weight" (:494-504): the weights are recomputed from the restored parameters with the CURRENT psi
-  if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)ctx->Gl * ctx->nbatch * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return RUVNB_OK;
 }
@@ -578,6 +582,12 @@ int ruvnb_halve_steps(ruvnb_ctx* ctx, const ruvnb_opts* o) {
   CK(cudaSetDevice(ctx->device));
   k_halve<<<nblk(ctx->Gl, 256), 256, 0, ctx->stream>>>(ctx->Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();
   ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false;   // the Gram / score sums were taken with the old steps
+  return RUVNB_OK;
+}
+// host hook for the dispersion refresh of ruvnb_fit_nb (nullptr removes it)
+int ruvnb_set_psi_callback(ruvnb_ctx* ctx, ruvnb_psi_fn fn, void* user) {
+  if (!ctx) return RUVNB_EARG;
+  ctx->psi_cb = fn; ctx->psi_cb_user = user;
   return RUVNB_OK;
 }
 // accept the candidate: loglik <- loglik.tmp (:512)
@@ -598,22 +608,35 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
   const long long launches0 = ctx->launches;
   CK(cudaEventRecord(t0, ctx->stream));
   const int Gl = ctx->Gl;
+  const long long GB = (long long)Gl * ctx->nbatch;   // entries of psi: one column per batch
   double inner_ms = 0.0, disp_ms = 0.0;
   int n_trace = 0, n_inner = 0, psi_used = 0, exact_rows = 0;
   auto refresh_psi = [&](StateSet& target) -> int {
     // the dispersion routine is an injection seam (edgeR/limma/locfit arithmetic)
     if (psi_inject && n_psi > 0) {
-      const double* src = psi_inject + (long long)std::min(psi_used, n_psi - 1) * Gl;
+      const double* src = psi_inject + (long long)std::min(psi_used, n_psi - 1) * GB;
       psi_used++;
-      std::vector<double> tmp(Gl), old(Gl);
-      CK(cudaMemcpyAsync(old.data(), target.psi, (size_t)Gl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      std::vector<double> tmp(GB), old(GB);
+      CK(cudaMemcpyAsync(old.data(), target.psi, (size_t)GB * 8, cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
-      for (int g = 0; g < Gl; ++g) tmp[g] = std::isfinite(src[g]) ? src[g] : old[g];  // :564
-      CK(cudaMemcpyAsync(target.psi, tmp.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
+      for (long long g = 0; g < GB; ++g) tmp[g] = std::isfinite(src[g]) ? src[g] : old[g];  // :564
+      CK(cudaMemcpyAsync(target.psi, tmp.data(), (size_t)GB * 8, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       ctx->psi_ver++; target.sig_valid = false;
       return RUVNB_OK;
     }
+    if (ctx->psi_cb) {
+      // host hook (ruvnb_set_psi_callback): the dispersion of `target` is refreshed by the caller -- batch-specific dispersion runs
+      // estimateDisp once per batch on that batch's cells (R/ruvIIInb.R:213-220,542-548), which the host mirror does in one
+      // context per batch.  The hook reads the state with ruvnb_get_state and writes psi with ruvnb_set_state.
+      if (&target != &ctx->cur) std::swap(ctx->cur, target);
+      int r = ctx->psi_cb(ctx->psi_cb_user, ctx);
+      if (&target != &ctx->cur) std::swap(ctx->cur, target);
+      if (r != RUVNB_OK) return ctx->fail(r < 0 ? r : RUVNB_EARG, "fit_nb: the dispersion callback returned %d", r);
+      ctx->psi_ver++; target.sig_valid = false;
+      return RUVNB_OK;
+    }
+    if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "fit_nb: a batch-specific dispersion needs a psi schedule or ruvnb_set_psi_callback (one estimateDisp per batch)");
     cudaEvent_t d0, d1;
     CK(cudaEventCreate(&d0)); CK(cudaEventCreate(&d1));
     CK(cudaEventRecord(d0, ctx->stream));
@@ -635,7 +658,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
   if (ctx->zinb_on) {  // :237-264: initial pi0 (from pi0 = 0) and E-step
     int nbad_pi0 = 0;
     RET(zinb_update_pi0(ctx, ctx->cur, ctx->cur.pi0, ctx->cur.pi0, &nbad_pi0));
-    CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)GB * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->cur.sig_valid = false;
   }
   k_fill<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(ctx->step, Gl, 1.0); CKL();  // :270
@@ -671,7 +694,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
         k_halve<<<nblk(Gl, 256), 256, 0, ctx->stream>>>(Gl, ctx->loglik, ctx->loglik_tmp, o->step_fac, ctx->step); CKL();  // :490-491
         ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false;
         RET(copy_set(ctx, ctx->cur, ctx->best));  // :492
-        if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :494-504
+        if (ctx->zinb_on) CK(cudaMemcpyAsync(ctx->cur.psi_w, ctx->cur.psi, (size_t)GB * 8, cudaMemcpyDeviceToDevice, ctx->stream));  // :494-504
         halving++;
         if (halving >= 3) { degener = false; }    // :506-509: loglik.tmp <- loglik, accept the restored state
       } else {

@@ -119,6 +119,13 @@ struct GeneRegs {
     mb = st.Mb + (long long)row * st.m;
     mbj = 0.0;
   }
+  // column b of psi / psi_w ([nbatch][Gl]) for this row: what load() took from column 0
+  __device__ __forceinline__ void rebatch(const GeneState<K>& st, int row, int b, int Gl) {
+    psi = st.psi[(long long)b * Gl + row];
+    r = 1.0 / psi;
+    rok = (psi > 1e-100) & (psi < 1e100);
+    if (zi) { rw = 1.0 / st.psi_w[(long long)b * Gl + row]; lrw = log(rw); } else rw = r;
+  }
   __device__ __forceinline__ double lmu(const double* w, int ci) const {
     double s = gmean + mbj;
 #pragma unroll
@@ -150,6 +157,10 @@ struct GeneRegs {
   __device__ __forceinline__ double logL(double mu) const { return flog(mu + r, mt->rc, mt->lc); }
 };
 
+// ops whose arithmetic depends on the dispersion declare `static constexpr bool USES_PSI = true`, keep their GeneState in `st` and
+// provide psi_changed(): the skeleton switches them to the batch of the chunk (batch-specific dispersion, psi[g, batch(c)])
+template <class T, class = void> struct OpUsesPsi { static constexpr bool value = false; };
+template <class T> struct OpUsesPsi<T, decltype((void)T::USES_PSI)> { static constexpr bool value = T::USES_PSI; };
 // ops that take nothing from the counts (they stream another per-element row) declare `static constexpr bool NO_Y = true`
 template <class T, class = void> struct OpNoY { static constexpr bool value = false; };
 template <class T> struct OpNoY<T, decltype((void)T::NO_Y)> { static constexpr bool value = T::NO_Y; };
@@ -211,7 +222,7 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
   const int ntiles_all = geo.nchunks / SC;
   const int tpp = (ntiles_all + geo.nparts - 1) / geo.nparts;           // tiles per part
   const int t0 = min(ntiles_all, part * tpp), ntiles = min(ntiles_all, t0 + tpp);
-  int curj = -1;
+  int curj = -1, curb = 0;
   // The counts travel HBM -> shared memory with cp.async, one 128-cell chunk (16 B per lane) ahead of the arithmetic: no
   // register holds a load in flight (with ~128 live registers ptxas spilled the prefetched values, i.e. waited for them at
   // once).  A lane reads its four cells {2l, 2l+1, 64+2l, 65+2l} back with two conflict-free 8-byte loads.
@@ -243,7 +254,23 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
         const int mcur = mt_[sc];
         const int nv = mcur & 0xff;
         if (nv == 0 && !Op::PADS) continue;
-        const int j = mcur >> 8;
+        if constexpr (OpUsesPsi<Op>::value) {
+          // batch-specific dispersion: the chunk's batch picks the column of psi (and of the count tables) -- rare, warp-uniform
+          const int b = mcur >> 24;
+          if (b != curb && nv > 0) {
+            curb = b;
+            op.g.rebatch(op.st, row, b, geo.Gl);
+            if (geo.tabL) {
+              __syncwarp();
+              const long long tr_ = ((long long)b * geo.Gl + row) * YT;
+              for (int i = lane; i < YT; i += 32) { sh->tl[warp][i] = geo.tabL[tr_ + i]; sh->tr[warp][i] = geo.tabR[tr_ + i]; }
+              __syncwarp();
+            }
+            if (geo.lgr) op.g.lgr = geo.lgr[(long long)b * geo.Gl + row];
+            op.psi_changed();
+          }
+        }
+        const int j = (mcur >> 8) & 0xffff;
         if (j != curj && nv > 0) {
           if (curj >= 0) op.group_end(curj);
           curj = j;
@@ -305,7 +332,7 @@ __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* 
     if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c + 1]; }
     const int nv = mcur & 0xff;
     if (nv == 0) continue;
-    const int j = mcur >> 8;
+    const int j = (mcur >> 8) & 0xffff;
     if (j != curj) {
       if (curj >= 0) op.group_end(curj);
       curj = j;
@@ -428,7 +455,7 @@ __device__ __forceinline__ void stream_slabs(const RowGeom& geo, const double* w
       const int mcur = __ldg(geo.chunk_meta + (t0 + i) * SC + sc);
       const int nv = mcur & 0xff;
       if (nv == 0) continue;
-      const int j = mcur >> 8;
+      const int j = (mcur >> 8) & 0xffff;
       if (j != curj) {
         if (curj >= 0) op.group_end(curj);
         curj = j;
@@ -475,6 +502,8 @@ template <int K>
 struct OpSigndev {
   static constexpr bool PADS = true;
   static constexpr bool QUAD = false;
+  static constexpr bool USES_PSI = true;
+  __device__ __forceinline__ void psi_changed() {}
   GeneState<K> st;
   GeneRegs<K> g;
   double* Drow;
@@ -641,6 +670,8 @@ template <int K>
 struct OpLoglik {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = true;
+  static constexpr bool USES_PSI = true;
+  __device__ __forceinline__ void psi_changed() { rlogr = g.r * log(g.r); }
   GeneState<K> st;
   GeneRegs<K> g;
   double acc, rlogr;
@@ -820,6 +851,8 @@ template <int K, bool HUBER>
 struct OpPass1 {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
+  static constexpr bool USES_PSI = true;
+  __device__ __forceinline__ void psi_changed() {}
   static constexpr int KK = K * (K + 1) / 2;
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
@@ -950,6 +983,8 @@ template <int K>
 struct OpLLW {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = false;
+  static constexpr bool USES_PSI = true;
+  __device__ __forceinline__ void psi_changed() { rlogr = g.r * log(g.r); }
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
   GeneRegs<K> g;
@@ -1310,14 +1345,16 @@ static __global__ void k_clamp_cols(double* X, long long n, int K, const double*
 // ------------------------------------------------------------------------------------------------
 // one warp per (factor l, group j): mean over the group's cells
 static __global__ void k_wbar(const double* W, long long Np, int K, int m, const int* group_chunk0, const int* group_n,
-                       double* Wbar /* [m][K] */) {
+                       const int* group_nch, const int* chunk_valid, double* Wbar /* [m][K] */) {
   int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= K * m) return;
   int l = wid / m, j = wid % m;
-  long long p0 = (long long)group_chunk0[j] * CH;
+  const int c0 = group_chunk0[j];
+  long long p0 = (long long)c0 * CH;
   int n = group_n[j];
   double s = 0.0;
-  for (int i = lane; i < n; i += 32) s += W[(long long)l * Np + p0 + i];
+  // the group's run of chunks (with batches: one padded sub-run per batch); pads are skipped
+  for (int i = lane; i < group_nch[j] * CH; i += 32) if ((i & (CH - 1)) < chunk_valid[c0 + (i >> 7)]) s += W[(long long)l * Np + p0 + i];
   s = warp_sum(s);
   if (lane == 0) Wbar[j * K + l] = s / (double)n;
 }
@@ -1363,14 +1400,15 @@ static __global__ void k_w_scale(double* W, long long Np, int K, const double* s
 // ------------------------------------------------------------------------------------------------
 struct CtlPack {            // control-gene parameters, gathered (and, when sharded, all-reduced)
   const double* __restrict__ gmean;      // [n_ctl]   old gmean
-  const double* __restrict__ psi;        // [n_ctl]
+  const double* __restrict__ psi;        // [nbatch][n_ctl]
   const double* __restrict__ step;       // [n_ctl]
   const double* __restrict__ alpha_old;  // [n_ctl][K]
   const double* __restrict__ alpha_new;  // [n_ctl][K]
   const double* __restrict__ Mb;         // [n_ctl][m] old Mb
   const double* pi0;        // [n_ctl] ZINB only
-  const double* psi_w;      // [n_ctl] ZINB only
+  const double* psi_w;      // [nbatch][n_ctl] ZINB only
   const uint8_t* zinf;      // [Np] or nullptr
+  const int* chunk_batch;   // [nchunks] batch of every chunk (all 0 unless the dispersion is batch-specific)
   int zinb;
 };
 template <int K, bool HUBER>
@@ -1399,6 +1437,8 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
   const int chunk = inb ? (int)(pos >> 7) : 0;
   const bool valid = inb && (int)(pos & (CH - 1)) < chunk_valid[chunk];
   const int j = chunk_grp[chunk];
+  const double* psi_b = cp.psi + (long long)cp.chunk_batch[chunk] * n_ctl;      // psi[ctl, batch of this cell]
+  const double* psiw_b = cp.psi_w + (long long)cp.chunk_batch[chunk] * n_ctl;
   const int nstr = n_ctl | 1;  // odd row stride (doubles): the per-cell deviance rows do not bank-conflict
   double wv[K];
 #pragma unroll
@@ -1413,7 +1453,7 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
 #pragma unroll
         for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
         double mu = exp(lmu);
-        dsm[(long long)cell_i * nstr + gi] = nb_signdev(y, lmu, mu, 1.0 / cp.psi[gi]);
+        dsm[(long long)cell_i * nstr + gi] = nb_signdev(y, lmu, mu, 1.0 / psi_b[gi]);
       }
     }
     __syncthreads();
@@ -1443,12 +1483,12 @@ __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows
 #pragma unroll
       for (int l = 0; l < K; ++l) lmu = fma(cp.alpha_old[(long long)gi * K + l], wv[l], lmu);
       double mu = exp(lmu);
-      double psi = cp.psi[gi];
+      double psi = psi_b[gi];
       double s = 1.0 / (1.0 / mu + psi);
       double z = lmu + cp.step[gi] * (((double)y + 0.01) / (mu + 0.01) - 1.0) - gm;  // (Z - gmean)[ctl], :381
       double wt = s;
       if (cp.zinb && y == 0 && cp.zinf[pos]) {  // wt.zinb of a zero count in a zero-inflated cell (:262,382)
-        double rw = 1.0 / cp.psi_w[gi], p0 = cp.pi0[gi];
+        double rw = 1.0 / psiw_b[gi], p0 = cp.pi0[gi];
         double q = exp(-rw * (log(mu + rw) - log(rw)));
         wt *= 1.0 - p0 / (p0 + (1.0 - p0) * q);
       }
@@ -1545,7 +1585,11 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
   const int chunk = inb ? (int)(pos >> 7) : 0;
   const bool valid = inb && (int)(pos & (CH - 1)) < chunk_valid[chunk];
   // the 64 positions of a CTA lie in one 128-cell chunk, hence in ONE replicate group: Mb[g, j] is a per-gene scalar here
-  const int j = chunk_grp[(int)(min(pos_begin + (long long)blockIdx.x * 64, pos_end - 1) >> 7)];
+  const int cta_chunk = (int)(min(pos_begin + (long long)blockIdx.x * 64, pos_end - 1) >> 7);
+  const int j = chunk_grp[cta_chunk];
+  // ... and in ONE batch: the dispersion column and the log(y + r) tables of the control genes are per CTA, too
+  const double* psi_b = cp.psi + (long long)cp.chunk_batch[cta_chunk] * n_ctl;
+  const double* tabR_b = ctl_tabR + (long long)cp.chunk_batch[cta_chunk] * n_ctl * YT;
   double wv[K];
 #pragma unroll
   for (int l = 0; l < K; ++l) wv[l] = valid ? W_old[(long long)l * Np + pos] : 0.0;
@@ -1561,8 +1605,8 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
       double v = 0.0;
       if (gi < n_ctl) {
         if (f == 0) v = cp.gmean[gi] + cp.Mb[(long long)gi * m + j];
-        else if (f == 1) v = cp.psi[gi];
-        else if (f == 2) v = 1.0 / cp.psi[gi];
+        else if (f == 1) v = psi_b[gi];
+        else if (f == 2) v = 1.0 / psi_b[gi];
         else if (f == 3) v = cp.step[gi];
         else if (f == 4) v = cp.gmean[gi];
         else if (f < 5 + K) v = cp.alpha_old[(long long)gi * K + (f - 5)];
@@ -1587,7 +1631,7 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
 #pragma unroll
         for (int l = 0; l < K; ++l) lmu = fma(gp[t][5 + l], wv[l], lmu);
         const double mu = fexp(lmu, mt.ex), r = gp[t][2];
-        const double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)(g0 + t) * YT, &mt);
+        const double h = nb_devhalf_t(y, (double)y, lmu, flog(mu + r, mt.rc, mt.lc), r, tabR_b + (long long)(g0 + t) * YT, &mt);
         hmax = fmax(hmax, fmax(h, 0.0));
         bad |= !(h == h);
       }
@@ -1621,7 +1665,7 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
         const double mu = fexp(lmu, mt.ex);
         if (certp) {
           const double r = gp[t][2];
-          const double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, ctl_tabR + (long long)(g0 + t) * YT, &mt);
+          const double h = nb_devhalf_t(y, yd, lmu, flog(mu + r, mt.rc, mt.lc), r, tabR_b + (long long)(g0 + t) * YT, &mt);
           const double d = nb_signdev_from_half(h, yd, mu);
           int b = (int)floor((d + mx) * scale);
           b = b < 0 ? 0 : (b > 127 ? 127 : b);
@@ -1676,6 +1720,8 @@ template <int K, bool HUBER>
 struct OpPass2 {
   static constexpr bool PADS = false;
   static constexpr bool QUAD = !HUBER;   // certified rows: the four cells of a lane in one branch-free block
+  static constexpr bool USES_PSI = true;
+  __device__ __forceinline__ void psi_changed() {}
   static constexpr int CELLS = TileCfg<K>::CELLS;
   GeneState<K> st;
   GeneRegs<K> g;

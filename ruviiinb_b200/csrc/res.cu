@@ -60,6 +60,19 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
   if (ctx->cell_shard && ctx->cell0 % bs != 0) return ctx->fail(RUVNB_EARG, "get_res: the cell shard starts at %lld, not on a block of %lld cells", ctx->cell0, bs);
   const int Gout = ctx->d_orow ? ctx->Gout : Gl;
   StateSet& s = ctx->cur;
+  int ref_batch = 0;
+  if (ctx->nbatch > 1) {   // which.min(colMeans(out$psi)), R/get.res.R:113,120
+    if (rr.src == MB_FAST) return ctx->fail(RUVNB_EARG, "fast_res: fastruvIII.nb has no batch-specific dispersion");
+    std::vector<double> hp((size_t)Gl * ctx->nbatch);
+    CK(cudaMemcpyAsync(hp.data(), s.psi, hp.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double best = 0.0;
+    for (int b = 0; b < ctx->nbatch; ++b) {
+      double t = 0.0;
+      for (int g = 0; g < Gl; ++g) t += hp[(size_t)b * Gl + g];
+      if (b == 0 || t < best) { best = t; ref_batch = b; }
+    }
+  }
   const size_t esz = rr.out_kind == RUVNB_OUT_I32 ? 4 : 8;
   ScopedDev own;
   double *wm = nullptr, *wam = nullptr, *caps = nullptr, *mbstage = nullptr, *mbG = nullptr, *mbslab[2] = {nullptr, nullptr}, *sum = nullptr, *tmp = nullptr;
@@ -120,7 +133,7 @@ int res_run(ruvnb_ctx* ctx, const ResRun& rr) {
     ResArgs a;
     a.Gl = Gl; a.K = K; a.m = ctx->m; a.B = B; a.ldB = ldB; a.Gout = Gout; a.N = N; a.Np = ctx->Np; a.c0 = c0; a.Yp = ctx->dY;
     a.alpha = s.alpha; a.gmean = s.gmean; a.psi = s.psi; a.W = s.W; a.Mb = s.Mb; a.mbG = nullptr;
-    a.cell2pos = ctx->d_cell2pos; a.chunk_grp = ctx->d_chunk_grp; a.orow = ctx->d_orow; a.wa_mean = wam; a.caps = caps; a.mtabs = ctx->d_mtabs;
+    a.cell2pos = ctx->d_cell2pos; a.chunk_grp = ctx->d_chunk_grp; a.chunk_batch = ctx->d_chunk_batch; a.ref_batch = ref_batch; a.orow = ctx->d_orow; a.wa_mean = wam; a.caps = caps; a.mtabs = ctx->d_mtabs;
     a.pi0 = ctx->res_zflag ? s.pi0 : nullptr; a.zflag = ctx->res_zflag; a.zavg = ctx->res_zavg;
     if (rr.src == MB_HOST_CELLS) {  // host G x N column-major: the block is one contiguous Gl x B piece == device [B][Gl]
       RET(ev_begin(3));

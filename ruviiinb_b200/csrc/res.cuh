@@ -27,6 +27,8 @@ struct ResArgs {
   const double *alpha, *gmean, *psi, *W, *Mb;   // current parameter set (Mb: [Gl][m])
   const double* mbG;                            // [Gl][ldB] per-cell Mb of this block, gene-major (fastruvIII.nb's Mb.all), or nullptr
   const int *cell2pos, *chunk_grp;
+  const int* chunk_batch;                       // [nchunks] batch of every chunk: psi is [nbatch][Gl] (R/get.res.R:59-62,101-121: out$psi[, curr.batch])
+  int ref_batch;                                // which.min(colMeans(out$psi)) (:113,120): the dispersion column of the quantile call
   const int* orow;                              // [Gl] output row of every resident row, -1 = row not reported (all-zero gene), or nullptr
   const double* pi0;                            // [Gl] zero-inflation probability of a ZINB fit, or nullptr (NB fit)
   const uint8_t* zflag;                         // [N] 1 where omega_gc = pi0_g applies: the reference reads out$pi0[, batch[c]], i.e. the
@@ -92,7 +94,8 @@ __device__ __forceinline__ double res_log_p0(double r, double mu) {
 // percentile-adjusted count of one element.  omega / omega_avg: zero-inflation probabilities of a ZINB fit (0 for NB), with ZIM's
 // definitions (ZIM 1.1.0, third-party, restated): dzinb = omega 1[x = 0] + (1 - omega) dnbinom, pzinb(q) = omega + (1 - omega) pnbinom(q)
 // (also for q = -1, where it returns omega), qzinb(p) = qnbinom(max(0, (p - omega)/(1 - omega))).  R/get.res.R:84-99.
-static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r, const MathTabs* mt, double omega, double omega_avg) {
+// r: size of the mid-p step (the cell's own batch), r_q: size of the quantile step (the reference batch; the same with one batch).
+static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r, double r_q, const MathTabs* mt, double omega, double omega_avg) {
   const double BIG = 1e250, LBIG = 575.64627324851142;  // log(1e250)
   // mid-p under (mu_full, r)
   double ls = res_log_p0(r, mu_full);
@@ -115,9 +118,10 @@ static __device__ double res_pac(int y, double mu_full, double mu_nouv, double r
   if (p < 0.005) p = 0.005;
   if (!(p == p)) return p;
   if (omega_avg != 0.0) { p = (p - omega_avg) / (1.0 - omega_avg); if (p < 0.0) p = 0.0; }   // qzinb
-  // qnbinom(p; mu_nouv, r)
+  // qnbinom(p; mu_nouv, r_q)
   if (mu_nouv == 0.0 || p == 0.0) return 0.0;
   const double target = p * (1.0 - 64.0 * 2.220446049250313e-16);
+  r = r_q;
   ls = res_log_p0(r, mu_nouv);
   const double ratio2 = mu_nouv / (mu_nouv + r);
   sc = fexp(ls, mt->ex);
@@ -161,7 +165,7 @@ static __global__ void __launch_bounds__(256) k_res_elem(ResArgs a, double* tmp,
     v = log((double)y / (fexp(wa, mt.ex) * (1.0 - omega)) + 1.0);           // :68-74
   } else {
     const double mb = res_mb(a, g, c, pos);
-    const double psi = a.psi[g];
+    const double psi = a.psi[(long long)a.chunk_batch[pos >> 7] * a.Gl + g];
     double mf = fexp(wa + gm + mb, mt.ex);
     const double cap1 = a.caps[(long long)g * 3 + 1];
     if (mf > cap1) mf = cap1;                                               // :42-44
@@ -175,7 +179,7 @@ static __global__ void __launch_bounds__(256) k_res_elem(ResArgs a, double* tmp,
       double mn = fexp(mb + gm + a.wa_mean[g], mt.ex);
       const double cap2 = a.caps[(long long)g * 3 + 2];
       if (mn > cap2) mn = cap2;                                             // :77-80
-      v = res_pac(y, mf, mn, 1.0 / psi, &mt, omega, a.pi0 ? a.pi0[g] * a.zavg : 0.0);   // :84-99
+      v = res_pac(y, mf, mn, 1.0 / psi, 1.0 / a.psi[(long long)a.ref_batch * a.Gl + g], &mt, omega, a.pi0 ? a.pi0[g] * a.zavg : 0.0);   // :84-99,101-121
     }
   }
   tmp[(long long)g * a.ldB + c] = v;

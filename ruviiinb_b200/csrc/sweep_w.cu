@@ -14,7 +14,7 @@ int launch_w_update(ruvnb_ctx* ctx, const ruvnb_opts* o, const CtlPack& cp, cons
   if (pe <= pb) return RUVNB_OK;
   const bool fast = o->huber_fastpath && !o->robust && !ctx->zinb_on;
   if (fast) {
-    k_build_ytabs<<<nc, YT, 0, ctx->stream>>>(p_psi, nc, nullptr, ctx->ctl_tabR, nullptr); CKL();
+    k_build_ytabs<<<nc * ctx->nbatch, YT, 0, ctx->stream>>>(p_psi, nc * ctx->nbatch, nullptr, ctx->ctl_tabR, nullptr); CKL();   // [nbatch][n_ctl][YT]
     CK(cudaMemsetAsync(ctx->w_fail, 0, sizeof(int), ctx->stream));
   }
   DISPATCH_K(K, {

@@ -17,6 +17,8 @@ template <int K>
 struct OpZinbQ {
   static constexpr bool PADS = true;
   static constexpr bool QUAD = false;
+  static constexpr bool USES_PSI = true;
+  __device__ __forceinline__ void psi_changed() { rlogr = g.r * log(g.r); }
   GeneState<K> st; GeneRegs<K> g;
   double* Q; long long Np; double* qrow;
   double spos, rlogr; int npos, row_;

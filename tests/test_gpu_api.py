@@ -55,7 +55,9 @@ def test_api_argument_errors_mirror_stop():
     with pytest.raises(ValueError, match="exactly one replicate group|non-zero entry"):
         api.ruvIII_nb(Y, bad, ctl)
     with pytest.raises(NotImplementedError):
-        api.ruvIII_nb(Y, M, ctl, use_pseudosample=True)
+        api.ruvIII_nb(Y, M, ctl, ortho_W=True)
+    with pytest.raises(ValueError, match="one entry per cell"):
+        api.ruvIII_nb(Y, M, ctl, batch=np.ones(3), batch_disp=True)
     with pytest.raises(ValueError, match="unknown type"):
         api.get_res(dict(pi0=None, psi=np.ones(3)), type="foo")
     with pytest.raises(ValueError, match="'cData' must be a user-specified data frame"):       # R/makeSCE.R:15-16
