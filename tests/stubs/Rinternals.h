@@ -32,6 +32,12 @@ int Rf_length(SEXP);
 R_xlen_t Rf_xlength(SEXP);
 Rboolean Rf_isInteger(SEXP);
 Rboolean Rf_isMatrix(SEXP);
+Rboolean Rf_isReal(SEXP);
+SEXP Rf_lang2(SEXP, SEXP);
+SEXP R_tryEval(SEXP, SEXP, int*);
+extern SEXP R_GlobalEnv;
+extern double R_NaReal;
+#define NA_REAL R_NaReal
 int* INTEGER(SEXP);
 int* LOGICAL(SEXP);
 double* REAL(SEXP);

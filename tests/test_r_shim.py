@@ -44,6 +44,7 @@ def test_r_wrappers_keep_the_reference_signatures():
         "fastruvIII.nb": "Y M cData ctl k robust ortho.W lambda.a lambda.b batch step.fac inner.maxit outer.maxit ncores use.pseudosample nc.pool batch.disp pCells.touse block.size",
         "estimateDisp.par": "y design group lib.size offset prior.df trend.method tagwise span min.row.sum grid.length grid.range robust winsor.tail.p tol weights BPPARAM",
         "get.res": "out type batch block.size",
+        "makeSCE": "obj cData batch assays",
     }
     for fn, args in want.items():
         m = re.search(re.escape(fn) + r" <- function\((.*?)\)\s*\{", w, flags=re.S)
@@ -51,5 +52,6 @@ def test_r_wrappers_keep_the_reference_signatures():
         have = set(a.split("=")[0].strip() for a in re.split(r",(?![^()]*\))", m.group(1)))
         assert set(args.split()) <= have, (fn, set(args.split()) - have)
     for text in ("Less than 1% of cells have known annotation", "of the M matrix has zero sum", "Batch variable is not a numeric vector",
-                 "Incorrect length of group.", "Incorrect length of lib.size."):
+                 "Incorrect length of group.", "Incorrect length of lib.size.", "'cData' must be a user-specified data frame.",
+                 "Wrong names of corrected assays data was specified"):
         assert text in w
