@@ -1411,6 +1411,7 @@ struct CtlPack {            // control-gene parameters, gathered (and, when shar
   const int* chunk_batch;   // [nchunks] batch of every chunk (all 0 unless the dispersion is batch-specific)
   int zinb;
 };
+#define W_FAST_DYN_SMEM (128 * 64 * 4)   // k_w_update_fast: the counts of one gene tile x the CTA's 64 cells
 template <int K, bool HUBER>
 __global__ void __launch_bounds__(256) k_w_update(const int32_t* const* ctl_rows, int n_ctl, long long Np,
                                                   const int* chunk_grp, const int* chunk_valid, CtlPack cp, int m,
@@ -1595,11 +1596,22 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
   for (int l = 0; l < K; ++l) wv[l] = valid ? W_old[(long long)l * Np + pos] : 0.0;
   // control-gene parameters are staged GT genes at a time in shared memory (they were ~12 dependent global loads per
   // element): [0] gmean + Mb[g, j], [1] psi, [2] 1/psi, [3] step, [4] gmean, [5..) alpha_old, then alpha_new
+  // The counts of the same GT genes x the CTA's 64 cells travel with them: 256 contiguous bytes per gene row, fetched with cp.async
+  // by the whole CTA at once (32 KB in flight) -- each lane used to load its own 4-byte count one gene ahead and waited for DRAM
+  // at every element (a warp-wide load touched four 32-byte sectors of four rows).
   constexpr int GT = 128, PW = 5 + 2 * K;
   __shared__ double gp[GT][PW];
-  __shared__ const int32_t* rowp[GT];
+  extern __shared__ __align__(16) int ybuf_dyn[];   // [GT][64]: W_FAST_DYN_SMEM bytes of dynamic shared memory
+  int (*ybuf)[64] = reinterpret_cast<int (*)[64]>(ybuf_dyn);
+  const long long cta_pos0 = pos_begin + (long long)blockIdx.x * 64;   // multiple of 64 cells; cta_pos0 + 64 <= Np (Np is a multiple of 512)
+  const int ycol = warp * 8 + cell;
   auto stage = [&](int g0) {
     __syncthreads();
+    for (int idx = tid; idx < GT * 16; idx += 256) {
+      const int t = idx >> 4, piece = idx & 15;
+      if (g0 + t < n_ctl) __pipeline_memcpy_async(&ybuf[t][piece * 4], ctl_rows[g0 + t] + cta_pos0 + piece * 4, 16);
+    }
+    __pipeline_commit();
     for (int idx = tid; idx < GT * PW; idx += 256) {
       const int t = idx / PW, f = idx - t * PW, gi = g0 + t;
       double v = 0.0;
@@ -1614,7 +1626,7 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
       }
       gp[t][f] = v;
     }
-    for (int t = tid; t < GT; t += 256) rowp[t] = (g0 + t < n_ctl) ? ctl_rows[g0 + t] : nullptr;
+    __pipeline_wait_prior(0);
     __syncthreads();
   };
   // sweep A: max half deviance
@@ -1623,10 +1635,8 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
     stage(g0);
     if (valid) {
       const int nt = min(GT, n_ctl - g0);
-      int ynext = slice < nt ? rowp[slice][pos] : 0;     // counts are fetched one gene ahead
       for (int t = slice; t < nt; t += 4) {
-        const int y = ynext;
-        if (t + 4 < nt) ynext = rowp[t + 4][pos];
+        const int y = ybuf[t][ycol];
         double lmu = gp[t][0];
 #pragma unroll
         for (int l = 0; l < K; ++l) lmu = fma(gp[t][5 + l], wv[l], lmu);
@@ -1654,10 +1664,8 @@ __global__ void __launch_bounds__(256) k_w_update_fast(const int32_t* const* ctl
     stage(g0);
     if (valid) {
       const int nt = min(GT, n_ctl - g0);
-      int ynext = slice < nt ? rowp[slice][pos] : 0;
       for (int t = slice; t < nt; t += 4) {
-        const int y = ynext;
-        if (t + 4 < nt) ynext = rowp[t + 4][pos];
+        const int y = ybuf[t][ycol];
         const double yd = (double)y;
         double lmu = gp[t][0];
 #pragma unroll

@@ -20,7 +20,8 @@ int launch_w_update(ruvnb_ctx* ctx, const ruvnb_opts* o, const CtlPack& cp, cons
   DISPATCH_K(K, {
     CK(cudaFuncSetAttribute(k_w_update<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (fast) {
-      k_w_update_fast<KT><<<nblk(pe - pb, 64), 256, 0, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, ctx->ctl_tabR,
+      CK(cudaFuncSetAttribute(k_w_update_fast<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_FAST_DYN_SMEM));
+      k_w_update_fast<KT><<<nblk(pe - pb, 64), 256, W_FAST_DYN_SMEM, ctx->stream>>>(ctx->d_ctl_rows, nc, ctx->Np, ctx->d_chunk_grp, ctx->d_chunk_valid, cp, ctx->ctl_tabR,
                                                                     ctx->d_mtabs, m, c.W, n.W, kh, pb, pe, ctx->w_fail, ctx->w_fail + 1);
       CKL();
       // cells whose certificate failed: exact per-cell MAD (CTAs beyond the failure count exit at once)
