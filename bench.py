@@ -324,8 +324,10 @@ def main():
     Yh_t = torch.empty((Gl, N), dtype=torch.int32, pin_memory=True)
     Yh = Yh_t.numpy()
     gen_rows_gpu(tp, np.arange(g0, g1), Yh, dev)
+    # gene shards: the replicated control-gene slab is fetched from the owning ranks over NCCL by the library (Yctl = None);
+    # RUVNB_BENCH_YCTL_HOST=1 uploads a host copy from every rank instead (the round-1 path)
     Yctl = None
-    if world > 1:
+    if world > 1 and os.environ.get("RUVNB_BENCH_YCTL_HOST"):
         Yctl_t = torch.empty((n_ctl, N), dtype=torch.int32, pin_memory=True)
         Yctl = Yctl_t.numpy()
         gen_rows_gpu(tp, np.arange(n_ctl), Yctl, dev)

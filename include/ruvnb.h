@@ -157,6 +157,8 @@ int ruvnb_set_design(ruvnb_ctx* ctx, int64_t G, int64_t N, int m, const int32_t*
                      const uint8_t* ctl, const uint8_t* zeroinf, int64_t g0, int64_t g1);
 /* Y: the (g1-g0) x N rows this ctx owns, plus -- when sharded -- Yctl: the n_ctl x N control-gene
  * rows (replicated on every rank for the per-cell W update; NULL on a single GPU). */
+/* (gene shards: Yctl = NULL after ruvnb_comm_init makes every rank copy the control rows it owns into the replicated slab and
+ * broadcast them over NCCL -- nothing but the rank's own rows crosses PCIe; the ranks' row ranges must partition 0..G) */
 int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, const int32_t* Yctl);
 /* CSR rows (the sparse / ZINB input, BASELINE.json config 3): indptr (rows+1), indices, values. */
 int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t* indices,

@@ -321,20 +321,56 @@ static int upload_rows(ruvnb_ctx* ctx, const int32_t* Y, int layout, long long n
   return RUVNB_OK;
 }
 
+// The control-gene rows of a gene-sharded fit without a host copy: every control gene is resident on the rank that owns its row, so
+// each rank copies its own control rows into the replicated slab and broadcasts them over NVLink (one ncclBroadcast per owning
+// rank) -- instead of every rank uploading the whole n_ctl x N slab over PCIe (0.4 GB per rank at cfg 2).
+static int exchange_ctl_rows(ruvnb_ctx* ctx) {
+  const int nr = ctx->nranks;
+  long long* d_rg = nullptr;
+  ScopedDev own;
+  CK(own.alloc(&d_rg, (size_t)2 * nr * 8));
+  const long long mine[2] = {ctx->g0, ctx->g1};
+  CK(cudaMemcpyAsync(d_rg + 2 * ctx->rank, mine, 16, cudaMemcpyHostToDevice, ctx->stream));
+  int r = g_nccl.AllGather(d_rg + 2 * ctx->rank, d_rg, 2, NCCL_INT64, ctx->comm, ctx->stream);
+  if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclAllGather (shard ranges): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  std::vector<long long> rg((size_t)2 * nr);
+  CK(cudaMemcpyAsync(rg.data(), d_rg, rg.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  long long covered = 0;
+  for (int q = 0; q < nr; ++q) {
+    // ctl_gene is ascending: the controls of rank q are one run [i0, i1) of the slab
+    const int i0 = (int)(std::lower_bound(ctx->ctl_gene.begin(), ctx->ctl_gene.end(), (int)rg[2 * q]) - ctx->ctl_gene.begin());
+    const int i1 = (int)(std::lower_bound(ctx->ctl_gene.begin(), ctx->ctl_gene.end(), (int)rg[2 * q + 1]) - ctx->ctl_gene.begin());
+    if (i1 <= i0) continue;
+    covered += i1 - i0;
+    if (q == ctx->rank)
+      for (int i = i0; i < i1; ++i)
+        CK(cudaMemcpyAsync(ctx->dYctl + (long long)i * ctx->Np, ctx->dY + (long long)(ctx->ctl_gene[i] - ctx->g0) * ctx->Np, (size_t)ctx->Np * 4,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    int32_t* seg = ctx->dYctl + (long long)i0 * ctx->Np;
+    r = g_nccl.Broadcast(seg, seg, (size_t)(i1 - i0) * ctx->Np, NCCL_INT32, q, ctx->comm, ctx->stream);
+    if (r != 0) return ctx->fail(RUVNB_ENCCL, "ncclBroadcast (control rows): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (covered != ctx->n_ctl) return ctx->fail(RUVNB_EARG, "upload_counts: the ranks' row ranges own %lld of the %d control genes (overlapping or incomplete shards)", covered, ctx->n_ctl);
+  return RUVNB_OK;
+}
+
 int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, const int32_t* Yctl) {
   if (!ctx || !Y) return RUVNB_EARG;
   if (!ctx->have_design) return ctx->fail(RUVNB_ESTATE, "upload_counts: call ruvnb_set_design first");
   if (layout != RUVNB_LAYOUT_GENE_MAJOR && layout != RUVNB_LAYOUT_CELL_MAJOR) return ctx->fail(RUVNB_EARG, "upload_counts: bad layout %d", layout);
   CK(cudaSetDevice(ctx->device));
   const bool sharded = (ctx->Gl != ctx->G);
-  if (sharded && !Yctl) return ctx->fail(RUVNB_EARG, "upload_counts: a gene shard needs the control-gene rows (Yctl)");
+  if (sharded && !Yctl && ctx->nranks < 2) return ctx->fail(RUVNB_EARG, "upload_counts: a gene shard needs the control-gene rows (Yctl), or a communicator to fetch them from the owning ranks");
   if (!ctx->dY) RET(dev_alloc(ctx, &ctx->dY, (long long)ctx->Gl * ctx->Np));
   // Y holds the LOCAL rows (Gl x N)
   RET(upload_rows(ctx, Y, layout, ctx->Gl, nullptr, 0, ctx->Gl, ctx->dY));
   std::vector<const int32_t*> rows(ctx->n_ctl);
   if (sharded) {
     if (!ctx->dYctl) RET(dev_alloc(ctx, &ctx->dYctl, (long long)ctx->n_ctl * ctx->Np));
-    RET(upload_rows(ctx, Yctl, layout, ctx->n_ctl, nullptr, 0, ctx->n_ctl, ctx->dYctl));
+    if (Yctl) RET(upload_rows(ctx, Yctl, layout, ctx->n_ctl, nullptr, 0, ctx->n_ctl, ctx->dYctl));
+    else RET(exchange_ctl_rows(ctx));
     for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dYctl + (long long)i * ctx->Np;
   } else {
     for (int i = 0; i < ctx->n_ctl; ++i) rows[i] = ctx->dY + (long long)ctx->ctl_gene[i] * ctx->Np;

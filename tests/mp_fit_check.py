@@ -41,7 +41,8 @@ def main():
     with _lib.Context(local) as ctx:
         ctx.comm_init(uid, rank, world)
         ctx.set_design(G, N, truth["grp"], ctl, rows=(g0, g1))
-        ctx.upload_counts(Yl, Yctl=Yctl)
+        # the control slab: from a host copy on every rank, or (MP_FIT_YCTL=nccl) from the owning ranks over NCCL
+        ctx.upload_counts(Yl, Yctl=None if os.environ.get("MP_FIT_YCTL") == "nccl" else Yctl)
         logl, recs, stats = ctx.fit_nb(opts, W0=W0, psi_inject=sched[:, g0:g1])
         got = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
         # the dispersion step and get.res on the sharded context: both need quantities of ALL genes (the trend / prior of

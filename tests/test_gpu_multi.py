@@ -9,11 +9,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_rank_fit_matches_oracle():
+@pytest.mark.parametrize("yctl", ["host", "nccl"])
+def test_two_rank_fit_matches_oracle(yctl):
+    """yctl: the replicated control-gene slab comes from a host copy on every rank, or from the owning ranks over NCCL."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "mp_fit_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+           "--master-port", "29517" if yctl == "host" else "29518", os.path.join(ROOT, "tests", "mp_fit_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, MP_FIT_YCTL=yctl))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
