@@ -138,7 +138,7 @@ int ruvnb_comm_init(ruvnb_ctx* ctx, const unsigned char id[128], int rank, int n
 /* grp_of_cell: N labels in 0..m-1 (apply(M,1,which), R/ruvIIInb.R:50); ctl: G flags (:42-45);
  * zeroinf: N flags or NULL (:39-40).  G is the GLOBAL gene count; [g0,g1) the rows this ctx holds
  * (g0 = 0, g1 = G on a single GPU). */
-/* Batch of every cell (0-based, N entries, every batch non-empty, nbatch <= 127) for a BATCH-SPECIFIC dispersion psi[g, batch(c)]
+/* Batch of every cell (0-based, N entries, nbatch <= 127) for a BATCH-SPECIFIC dispersion psi[g, batch(c)]
  * (`batch.disp = TRUE`, R/ruvIIInb.R:213-220,278-283,306-315,542-548; R/get.res.R:59-62,101-121).  Must precede ruvnb_set_design: the
  * resident cell order keeps the batches of a replicate group apart.  State "psi" / "psi_w" then have G x nbatch entries (column-major,
  * R's psi matrix); ruvnb_irls_iteration, ruvnb_loglik, ruvnb_fit_nb, ruvnb_zinb_pi0 and ruvnb_get_res index the dispersion by the

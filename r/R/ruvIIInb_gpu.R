@@ -183,7 +183,7 @@ get.res <- function(out, type = c("logcounts", "pearson", "quantile"), batch = N
   m <- max(grp) + 1L
   bpsi <- !is.null(dim(out$psi)) && ncol(out$psi) > 1                                    # out$psi[, curr.batch], :59-62,101-121
   if (is.null(batch)) batch <- if (is.null(out$batch)) rep(1, N) else out$batch
-  if (bpsi && !setequal(unique(batch), seq_len(ncol(out$psi)))) stop("batch must take the values 1..ncol(out$psi)")
+  if (bpsi && !all(batch %in% seq_len(ncol(out$psi)))) stop("batch must take values in 1..ncol(out$psi)")
   ctx <- .ruvnb_open(Y, grp, m, out$ctl, NULL, if (bpsi) as.integer(batch) - 1L else NULL, TRUE, device)   # (the counts of `out` are already capped)
   on.exit(.Call("ruvnb_R_close", ctx), add = TRUE)
   .Call("ruvnb_R_set_fit", ctx, out$W, out$a, out$gmean, if (per.cell) matrix(0, G, m) else as.matrix(out$Mb)[, seq_len(m), drop = FALSE],

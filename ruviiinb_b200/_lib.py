@@ -207,13 +207,18 @@ class Context:
         buf = (C.c_ubyte * 128).from_buffer_copy(bytes(uid))
         self._ck(self.lib.ruvnb_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
 
-    def set_batches(self, batch):
-        """Batch label of every cell (any integer labels; renumbered 0.. in sorted order, the reference's 1..max(batch)) for a
-        batch-specific dispersion; before set_design.  Returns the 0-based labels."""
-        lab, b0 = np.unique(np.asarray(batch), return_inverse=True)
+    def set_batches(self, batch, nbatch=None):
+        """Batch label of every cell for a batch-specific dispersion; before set_design.  Without `nbatch` any integer labels are
+        renumbered 0.. in sorted order (the reference's 1..max(batch)); with it the labels are taken as they are, 0-based, and some
+        batches may be empty (a cell shard).  Returns the 0-based labels."""
+        if nbatch is None:
+            lab, b0 = np.unique(np.asarray(batch), return_inverse=True)
+            nbatch = int(lab.size)
+        else:
+            b0 = np.asarray(batch)
         b0 = np.ascontiguousarray(b0, dtype=np.int32)
-        self._ck(self.lib.ruvnb_set_batches(self.h, _ptr(b0), b0.size, int(lab.size)))
-        self.nbatch = int(lab.size)
+        self._ck(self.lib.ruvnb_set_batches(self.h, _ptr(b0), b0.size, int(nbatch)))
+        self.nbatch = int(nbatch)
         return b0
 
     def set_psi_callback(self, fn):

@@ -295,8 +295,9 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
             batch = out.get("batch")
         if batch is None:
             raise ValueError("a batch-specific dispersion needs the batch of every cell")
-        if sorted(np.unique(batch).tolist()) != list(range(1, psi_m.shape[1] + 1)):
-            raise ValueError("batch must take the values 1..ncol(psi): it indexes the columns of psi (R/get.res.R:60)")
+        bu = np.unique(batch)
+        if bu.min() < 1 or bu.max() > psi_m.shape[1] or (bu != bu.astype(np.int64)).any():
+            raise ValueError("batch must take values in 1..ncol(psi): it indexes the columns of psi (R/get.res.R:60)")
     ranks = ranks or Ranks()
     Y = out["counts"] if _is_sparse(out["counts"]) else np.ascontiguousarray(out["counts"], dtype=np.int32)
     G, N = Y.shape
@@ -311,8 +312,9 @@ def get_res(out, type=("logcounts", "pearson", "quantile"), batch=None, block_si
     with _lib.Context(device) as ctx:
         if ranks.world > 1:
             ctx.comm_init(ranks.unique_id(), ranks.rank, ranks.world)
-        if bpsi:
-            ctx.set_batches(np.asarray(batch)[c0:c0 + N] if len(batch) != N else batch)
+        if bpsi:   # the labels index the columns of psi as they are (this rank's cells may not meet every batch)
+            bl = np.asarray(batch).astype(np.int64)
+            ctx.set_batches((bl[c0:c0 + N] if len(bl) != N else bl) - 1, nbatch=psi_m.shape[1])
         ctx.set_design(G, N, grp, np.asarray(out["ctl"], bool), m=m)
         if ranks.world > 1 or N_total != N:
             ctx.set_cell_shard(N_total, c0)

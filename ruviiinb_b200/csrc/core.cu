@@ -162,13 +162,11 @@ int ruvnb_set_batches(ruvnb_ctx* ctx, const int32_t* batch_of_cell, int64_t N, i
   ctx->nbatch = nbatch; ctx->batch.clear();
   if (nbatch == 1) return RUVNB_OK;
   ctx->batch.assign(batch_of_cell, batch_of_cell + N);
-  std::vector<long long> cnt(nbatch, 0);
+  // (a batch without a cell is legal: a cell shard of get.res may not meet every batch)
   for (int64_t c = 0; c < N; ++c) {
     const int b = ctx->batch[c];
     if (b < 0 || b >= nbatch) { ctx->nbatch = 1; ctx->batch.clear(); return ctx->fail(RUVNB_EARG, "set_batches: batch label %d of cell %lld outside 0..%d", b, (long long)c, nbatch - 1); }
-    cnt[b]++;
   }
-  for (int b = 0; b < nbatch; ++b) if (!cnt[b]) { ctx->nbatch = 1; ctx->batch.clear(); return ctx->fail(RUVNB_EARG, "set_batches: batch %d has no cell", b); }
   return RUVNB_OK;
 }
 int ruvnb_nbatch(const ruvnb_ctx* ctx) { return ctx ? ctx->nbatch : 0; }
