@@ -480,6 +480,8 @@ def main():
                "gram": 16.0, "exact_mad": 0.0}
     sweep_bytes = {n: v * Gl * N for n, v in per_elt.items()}
     sweep_bytes["w_update"] = 4.0 * n_ctl * N / world
+    for n in ktimes:                     # stream segments between the sweeps (small kernels + collectives): time only
+        sweep_bytes.setdefault(n, 0.0)
     kern = {}
     for name, (tot, cnt) in ktimes.items():
         if cnt:
@@ -488,7 +490,9 @@ def main():
     dom = max((n for n in kern if sweep_bytes[n] > 0), key=lambda n: kern[n]["ms"] * kern[n]["launches_per_step"])
     label = {"loglik": "k_ll_w (log-likelihood + certificate + the next iteration's element-wise working quantities -> two slabs)" if fused else "k_loglik",
              "gram": "k_gram (Gram / score / group sums from the slabs)", "pass2": "k_pass2w (group sums of w W_new from the weight slab)" if wcache else "k_pass2",
-             "pass1": "k_pass1", "w_update": "k_w_update_fast", "exact_mad": "k_signdev + k_row_sigma"}
+             "pass1": "k_pass1", "w_update": "k_w_update_fast", "exact_mad": "k_signdev + k_row_sigma",
+             "seg_alpha": "segment: alpha phase (normalise, all-reduce, solve, all-gather, clamp)", "seg_w": "segment: W exchange (all-reduce, column norms)",
+             "seg_mb": "segment: gmean / Mb finish", "seg_tail": "segment: certificate finish, log-likelihood total, all-reduce"}
     key = {"loglik": "ll_w" if fused else "loglik", "pass2": "pass2w" if wcache else "pass2"}.get(dom, dom)
     # measured DRAM traffic of the dominant kernel (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per element of the
     # captured launch, profiles/traffic.json), scaled to the elements this rank's launch walks

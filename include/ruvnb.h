@@ -99,9 +99,11 @@ long long ruvnb_kernel_launches(const ruvnb_ctx* ctx);
 /* Device time of the Y-streaming sweep kernels, measured with CUDA events on the library's own stream
  * (bench.py's roofline line).  which: 0 unused (the Huber certificate now rides in the log-likelihood sweep),
  * 1 pass1 (Gram/score), 2 w_update (per-cell), 3 pass2 (group sums), 4 loglik + certificate (k_ll_w when fused), 5 exact-MAD (signdev + select),
- * 6 gram (Gram / score / group sums from the slabs of the fused sweep).
+ * 6 gram (Gram / score / group sums from the slabs of the fused sweep); stream segments between the sweeps (small kernels +
+ * collectives, what limits a many-GPU iteration): 7 alpha phase (normalise, all-reduce, solve, all-gather, clamp), 8 W exchange
+ * (all-reduce of the slices, column norms), 9 gmean / Mb finish, 10 tail (certificate finish, log-likelihood total, all-reduce).
  * Accumulated since ruvnb_kernel_time_reset. */
-#define RUVNB_NKERN 7
+#define RUVNB_NKERN 11
 int ruvnb_kernel_time(const ruvnb_ctx* ctx, int which, double* ms_total, long long* launches);
 void ruvnb_kernel_time_reset(ruvnb_ctx* ctx);
 /* The CUDA stream every kernel of this context is launched on (a cudaStream_t), so a host can

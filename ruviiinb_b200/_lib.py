@@ -544,7 +544,7 @@ class Context:
         self._ck(self.lib.ruvnb_fast_Mb_all(self.h, lambda_b, _ptr(ag), int(block_size), _ptr(out)))
         return out
 
-    KERNELS = ("devstats", "pass1", "w_update", "pass2", "loglik", "exact_mad", "gram")
+    KERNELS = ("devstats", "pass1", "w_update", "pass2", "loglik", "exact_mad", "gram", "seg_alpha", "seg_w", "seg_mb", "seg_tail")
 
     def kernel_times(self):
         """{name: (total_ms, launches)} of the sweep kernels since the last reset (CUDA events, lib stream)."""

@@ -55,6 +55,7 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
     RET(r);
     KEV_END(6);
   }
+  KEV_BEGIN(10);
   s.sig_valid = true; s.maybe_active = false; s.p1_valid = with_p1; s.nfail = -1;
   if (with_p1) { ctx->cur.p1_valid = ctx->nw.p1_valid = ctx->best.p1_valid = false; s.p1_valid = true; }   // one set of sums
   k_list_failed<<<1, 1024, 0, ctx->stream>>>(Gl, s.sigma, ctx->faillist, ctx->flags + 4, nullptr);
@@ -68,6 +69,7 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
     CK(cudaMemcpyAsync(ctx->h_scal, ctx->scal, 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_flags, ctx->flags, 5 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_flags + 6, ctx->w_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KEV_END(10);
     CK(cudaStreamSynchronize(ctx->stream));
     kev_collect(ctx);
     *total = ctx->h_scal[0];
@@ -361,6 +363,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     }
     KEV_END(1);
   }
+  KEV_BEGIN(7);
   DISPATCH_K(K, {
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
     CKL();
@@ -405,6 +408,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_ctl, 0));   // the control-gene pack (side stream) is complete
     k_gather_rows<<<nblk((long long)nc * K, 256), 256, 0, ctx->stream>>>(n.alpha, ctx->d_ctl_local, nc, K, p_anew); CKL();
   }
+  KEV_END(7);
   // W ------------------------------------------------------------------------------------------------
   {
     CtlPack cp;
@@ -419,10 +423,12 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
       RET(launch_w_update(ctx, o, cp, p_psi, c, n, kh, pb, pe));
       KEV_END(2);
     }
+    KEV_BEGIN(8);
     RET(allreduce(ctx, n.W, (size_t)ctx->Np * K, NCCL_F64));
     k_w_sumsq<<<K, 1024, 0, ctx->stream>>>(n.W, ctx->Np, ctx->sumsq); CKL();
     k_w_scale<<<nblk(ctx->Np * K, 256), 256, 0, ctx->stream>>>(n.W, ctx->Np, K, ctx->sumsq, ctx->d_chunk_valid, ctx->flags + 1); CKL();
     k_revert_if<<<nblk(ctx->Np * K, 256), 256, 0, ctx->stream>>>(ctx->flags + 1, n.W, c.W, ctx->Np * K); CKL();  // :402
+    KEV_END(8);
   }
   // gmean, Mb ------------------------------------------------------------------------------------------
   {
@@ -454,6 +460,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
     }
     KEV_END(3);
   }
+  KEV_BEGIN(9);
   k_gmean_mb<<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, ctx->Wc ? ctx->S0c : ctx->S0, ctx->S1, c.Mb, o->lambda_b, n.gmean, n.Mb, ctx->flags + 3, ctx->flags + 2); CKL();
   // "any NA -> the whole Mb reverts" (:424) needs the NaN count of ALL ranks.  NB: it is taken speculatively as this rank's
   // own count; the global count travels with the log-likelihood total, and the tail is redone in the (rare) case they
@@ -463,6 +470,7 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   // psi is fixed inside the inner loop
   const size_t psi_bytes = (size_t)Gl * ctx->nbatch * 8;   // [nbatch][Gl]
   CK(cudaMemcpyAsync(n.psi, c.psi, psi_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  KEV_END(9);
   double fin[2] = {0.0, 0.0};
   if (ctx->zinb_on) {
     // step 4a (:435-467): pi0 at the NEW parameters, then the E-step weights -- recomputed on the fly from (pi0, psi_w)
