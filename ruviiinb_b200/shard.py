@@ -7,9 +7,13 @@ import numpy as np
 
 
 def gene_range(G, world, rank):
-    """Rows [g0, g1) of rank `rank`: ceil(G / world) rows per rank, the last ranks may hold fewer (or none)."""
+    """Rows [g0, g1) of rank `rank`: ceil(G / world) rows per rank (the layout the library's all-gather of alpha expects), the last
+    rank may hold fewer.  A rank without rows cannot hold a context (`ruvnb_set_design` refuses g0 >= g1): that is an error here."""
     per = (G + world - 1) // world
-    return min(G, rank * per), min(G, (rank + 1) * per)
+    g0, g1 = min(G, rank * per), min(G, (rank + 1) * per)
+    if g0 >= g1:
+        raise ValueError(f"{G} genes in shards of {per} rows leave rank {rank} of {world} without a row: use at most {(G + per - 1) // per} ranks")
+    return g0, g1
 
 
 def chunk_range(nchunks, world, rank):

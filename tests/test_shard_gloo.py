@@ -74,12 +74,16 @@ def test_gloo_world2_exchange_steps(G, N):
     assert dict(ret) == {0: True, 1: True}
 
 
-def test_shard_ranges_cover_and_handle_more_ranks_than_rows():
-    for G, world in [(20000, 8), (7, 8), (1, 2), (16, 4)]:
+def test_shard_ranges_cover_and_refuse_more_ranks_than_rows():
+    for G, world in [(20000, 8), (7, 7), (17, 4), (16, 4)]:
         r = [shard.gene_range(G, world, k) for k in range(world)]
         assert r[0][0] == 0 and r[-1][1] == G
         assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
-        assert sum(b - a for a, b in r) == G
+        assert sum(b - a for a, b in r) == G and all(b > a for a, b in r)
+    # a rank without rows cannot hold a context (ruvnb_set_design refuses g0 >= g1): an explicit error, not an empty range
+    for G, world, rank in [(7, 8, 7), (1, 2, 1), (9, 8, 5)]:
+        with pytest.raises(ValueError, match="without a row"):
+            shard.gene_range(G, world, rank)
 
 
 def _cells_worker(rank, world, port, ret):
