@@ -27,24 +27,42 @@ def main():
     rng = np.random.default_rng(78)
     sched = np.stack([truth["psi"] * np.exp(0.2 * rng.standard_normal(G) / (i + 1)) for i in range(3)])
     calls = {"i": 0}
+    batched = os.environ.get("MP_FIT_BATCH") == "1"    # a batch-specific dispersion (two batches) on the gene shards
+    batch = None
+    if batched:
+        batch = rng.integers(1, 3, size=N); batch[:2] = [1, 2]
+        sched = np.stack([sched, sched * np.exp(0.4 * rng.standard_normal(sched.shape))], axis=2)    # (3, G, 2)
 
     def psi_fn(Yx, offs, wt, psi_old):
-        i = min(calls["i"], 2)
+        i = calls["i"]
         calls["i"] += 1
-        return sched[i]
+        return sched[min(i // 2, 2)][:, i % 2] if batched else sched[min(i, 2)]
 
     trace = []
-    ref = orc.ruvIII_nb(Yf, M, ctl, k=k, outer_maxit=3, W0=W0, psi_fn=psi_fn, winsorize=False, trace=trace)
+    ref = orc.ruvIII_nb(Yf, M, ctl, k=k, outer_maxit=3, W0=W0, psi_fn=psi_fn, winsorize=False, trace=trace, batch=batch, batch_disp=batched)
     uid = shard.broadcast_unique_id(dist, _lib.load(), device=dev)
     Yl, Yctl, (g0, g1) = shard.local_counts(Y, ctl, world, rank)
     opts = _lib.default_opts(k=k, outer_maxit=3)
     with _lib.Context(local) as ctx:
         ctx.comm_init(uid, rank, world)
+        if batched:
+            ctx.set_batches(batch)
         ctx.set_design(G, N, truth["grp"], ctl, rows=(g0, g1))
         # the control slab: from a host copy on every rank, or (MP_FIT_YCTL=nccl) from the owning ranks over NCCL
         ctx.upload_counts(Yl, Yctl=None if os.environ.get("MP_FIT_YCTL") == "nccl" else Yctl)
         logl, recs, stats = ctx.fit_nb(opts, W0=W0, psi_inject=sched[:, g0:g1])
         got = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
+        if batched:     # (the estimators refuse a batch context; get.res with batch psi is covered on one GPU)
+            dec = [(r["outer"], r["iter"], r["degener"], r["accepted"]) for r in recs]
+            refdec = [(r["outer"], r["iter"], int(r["degener"]), int(r["accepted"])) for r in trace]
+            err = dict(W=relerr(got["W"], ref["W"]), alpha=relerr(got["alpha"], ref["a"][g0:g1]), gmean=relerr(got["gmean"], ref["gmean"][g0:g1]),
+                       Mb=relerr(got["Mb"], ref["Mb"][g0:g1], floor=1e-6), psi=relerr(got["psi"], ref["psi"][g0:g1]), logl=relerr(logl, ref["logl"]))
+            ok = dec == refdec and all(v < 1e-6 for v in err.values())
+            t = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            print(f"rank {rank}/{world} rows [{g0},{g1}) batched ok={ok} err={ {k_: float(f'{v:.2e}') for k_, v in err.items()} }", flush=True)
+            dist.destroy_process_group()
+            sys.exit(0 if int(t.item()) == 1 else 1)
         # the dispersion step and get.res on the sharded context: both need quantities of ALL genes (the trend / prior of
         # estimateDisp, the block-wise Pearson clip limits), gathered over NCCL
         from oracle import edger, getres

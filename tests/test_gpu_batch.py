@@ -170,3 +170,47 @@ def test_pseudosample_fit_matches_oracle():
     err = dict(W=relerr(out["W"], ref["W"][:N]), a=relerr(out["a"], ref["a"]), gmean=relerr(out["gmean"], ref["gmean"]),
                Mb=relerr(out["Mb"], ref["Mb"], floor=1e-6), psi=relerr(out["psi"], ref["psi"][:, 0]), logl=relerr(out["logl"], ref["logl"]))
     assert all(v < 1e-6 for v in err.values()), err
+
+
+@pytest.mark.gpu
+def test_zinb_iteration_with_batch_psi_matches_oracle():
+    """ZINB with a batch-specific dispersion (psivec <- psi[i, batch][zeroinf], R/ruvIIInb.R:243-245,258-262,443-465): pi0 by
+    Nelder-Mead, the E-step weights and one IRLS pass, psi and psi_w read per batch."""
+    from oracle import nelder_mead, ruviiinb as orc
+    from ruviiinb_b200 import _lib, synth
+    from tests.parity import oracle_init, relerr
+    G, N, k, m, nb = 64, 600, 2, 3, 2
+    Y, M, ctl, truth = synth.make_counts(G, N, k, m, 18, seed=71, zinb=True, gmean_mu=0.8, gmean_sd=0.8)
+    grp = truth["grp"]
+    rng = np.random.default_rng(72)
+    batch = rng.integers(1, nb + 1, size=N); batch[:nb] = np.arange(1, nb + 1)
+    psiB = np.stack([truth["psi"] * np.exp(0.4 * rng.standard_normal(G)) for _ in range(nb)], axis=1)
+    psic = psiB[:, batch - 1]
+    zeroinf = np.arange(N) % 4 != 0
+    Yf = Y.astype(np.float64)
+    W0, gmean, alpha, adev = oracle_init(Y, ctl, k)
+    mu = np.exp(gmean[:, None] + alpha @ W0.T)
+    pi0 = nelder_mead.pi0_optim(Yf[:, zeroinf], mu[:, zeroinf], psic[:, zeroinf])
+    pi0 = np.where(np.isnan(pi0), 0.0, pi0)
+    wt = orc.zinb_weights(Yf, mu, psic, pi0, zeroinf, np.ones((G, N)))
+    state = dict(gmean=gmean, Mb=np.zeros((G, m)), alpha=alpha, alpha_dev=adev, W=W0, psi=psic, step=np.ones(G), wt_zinb=wt, pi0=pi0)
+    rep_ind = [np.where(grp == j)[0] for j in range(m)]
+    ll0 = orc.loglik_matrix(Yf, gmean[:, None] + alpha @ W0.T, psic, pi0, zeroinf).sum(axis=1)
+    new, ll1, aux = orc.inner_iteration(Yf, state, grp, rep_ind, ctl, 100.0, 0.01, 16.0, zeroinf=zeroinf, pi0_fn=nelder_mead.pi0_optim)
+    opts = _lib.default_opts(k=k, zinb=1)
+    with _lib.Context(0) as ctx:
+        ctx.set_batches(batch)
+        ctx.set_design(G, N, grp, ctl, zeroinf=zeroinf)
+        ctx.upload_counts(Y)
+        ctx.set_state("W", W0)
+        ctx.init_coef(opts)
+        ctx.set_state("psi", psiB)
+        assert ctx.zinb_pi0(opts) == 0
+        assert relerr(ctx.get_state("pi0"), pi0) < 1e-9
+        assert np.array_equal(ctx.get_state("psi_w"), psiB)
+        ctx.loglik(opts)
+        assert relerr(ctx.get_state("loglik"), ll0) < 1e-10
+        tot1, bad = ctx.irls_iteration(opts)
+        err = {n: relerr(ctx.get_state(n), new[n], floor=1e-6) for n in ("alpha", "W", "gmean", "Mb", "pi0")}
+        err["loglik1"] = abs(tot1 - ll1.sum()) / abs(ll1.sum())
+    assert all(v < 1e-8 for v in err.values()), err
