@@ -442,7 +442,9 @@ def main():
         t_win = time.perf_counter() - t0 - t_up
         W0c, sv, svd_iters = ctx.init_W(k)                      # H1 on the device: a COLD start, as ruvIII.nb does it
         t_init = time.perf_counter() - t0
+        ctx.kernel_time_reset()
         logl_outer, recs, st = ctx.fit_nb(opts, W0=W0c)
+        fit_kernels = {n: {"total_ms": round(tot, 3), "launches": cnt} for n, (tot, cnt) in ctx.kernel_times().items() if cnt}
         res = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb", "psi")}
         barrier()
         dt = time.perf_counter() - t0
@@ -457,6 +459,8 @@ def main():
                     "upload_winsorize_initW_seconds": t_init, "upload_seconds": t_up, "winsorize_seconds": t_win,
                     "initW_seconds": t_init - t_up - t_win, "initW_iterations": svd_iters,
                     "gene_fits_per_s_inner_loops": G * st["n_inner"] / st["inner_seconds"], "logl_outer": [float(x) for x in logl_outer],
+                    "exact_mad_rows": st.get("n_exact_mad_rows"), "inner_loop_brackets": fit_kernels,
+                    "decisions": [[r["outer"], r["iter"], r["halving"], r["accepted"]] for r in recs],
                     "canonical_corr_W_truth": [float(x) for x in np.linalg.svd(np.linalg.qr(res["W"] - res["W"].mean(0))[0].T @ np.linalg.qr(tp["W"] - tp["W"].mean(0))[0], compute_uv=False)] if rank == 0 else None,
                     "what": "upload (pinned host int32) + Winsorize + ruvnb_init_W (truncated SVD of the control rows) + ruvnb_fit_nb with estimateDisp at every psi refresh + read-back; wall clock, max over ranks"}
 
