@@ -189,6 +189,8 @@ struct ruvnb_ctx {
   cudaEvent_t ev_ctl = nullptr;  // the control-gene parameter exchange on the side stream has finished
   // switches read once from the environment (tuning / A-B measurements)
   bool opt_no_fuse = false;  // RUVNB_NO_FUSE=1: separate log-likelihood and Gram sweeps (three Y sweeps per iteration)
+  double opt_hint_half = 0.7;   // RUVNB_HINT_HALF: half-width of a fresh certificate hint window in units of (MAD - t), < 0.85.  Measured on the
+                                // whole fit at cfg 2 (exact-MAD rows / ms): 0.4 67 111 / 127, 0.55 60 472 / 114, 0.7 54 818 / 104, 0.8 62 192 / 118
   int opt_slab_cfg = 0;      // RUVNB_SLAB_CFG bit 0: k_gram stage shape B, bit 1: k_pass2w stage shape B (A/B runs)
   // stats of the last iteration
   int last_fail_rows = 0, last_active_rows = 0, last_fail_cells = 0;

@@ -121,7 +121,7 @@ static int complete_sigma(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, doub
       ctx->launch_parts = 1;
       RET(r);
       k_row_sigma<<<nr, RS_NT, 0, ctx->stream>>>(ctx->D, ctx->Np, (long long)ctx->N, ctx->faillist + r0, ctx->rowmax, ctx->rownan, kh,
-                                                 o->huber_fastpath, s.sigma, ctx->sigma_exact, ctx->hint);
+                                                 o->huber_fastpath, s.sigma, ctx->sigma_exact, ctx->hint, ctx->opt_hint_half);
       CKL();
     }
     KEV_END(5);

@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_signdev(RowGeom geo, GeneSta
 // when k sigma >= max|d|, i.e. every Huber weight pmin(1, k sigma/|d|) is exactly 1.
 static __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, long long Np, long long n, const int* rowlist,
                                                     const double* rowmax, const int* rownan, double kh, int fastpath,
-                                                    double* sigma, double* sigma_exact, double* hint /* [Gl][3] lo, hi, tg */) {
+                                                    double* sigma, double* sigma_exact, double* hint /* [Gl][3] lo, hi, tg */, double hint_half) {
   __shared__ RowSelScratch sc;
   const int slot = blockIdx.x;
   const int row = rowlist ? rowlist[slot] : slot;
@@ -584,9 +584,9 @@ static __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, lon
       double t_now = mx / (kh * C) * (1.0 + 1e-9);
       if (sg > 0.0 && kh * sg >= mx * (1.0 + 1e-9)) out = __longlong_as_double(0x7ff0000000000000ll);
       double slack = madraw - t_now;
-      // window: the median may move by 0.4 slack and max|d| may grow by (1 + 0.15 slack / t) before the row needs
+      // window: the median may move by HINT_HALF slack and max|d| may grow by (1 + 0.15 slack / t) before the row needs
       // another exact evaluation; (hi - lo)/2 + tg stays below madraw so that c3 <= (n-1)/2 is attainable
-      if (slack > 0.0 && mx < 1.79769313486231570e308) { tg = t_now + 0.15 * slack; lo = med - 0.4 * slack; hi = med + 0.4 * slack; }
+      if (slack > 0.0 && mx < 1.79769313486231570e308) { tg = t_now + 0.15 * slack; lo = med - hint_half * slack; hi = med + hint_half * slack; }
     }
     sigma[row] = out;
     hint[(long long)row * 3 + 0] = lo; hint[(long long)row * 3 + 1] = hi; hint[(long long)row * 3 + 2] = tg;
