@@ -701,6 +701,7 @@ int ensure_state(ruvnb_ctx* ctx, int K) {
   RET(dev_alloc(ctx, &ctx->llparts, P * Gl));
   RET(dev_alloc(ctx, &ctx->certc, P * Gl * 4));
   RET(dev_alloc(ctx, &ctx->cvec, Gl * K));
+  RET(dev_alloc(ctx, &ctx->colsum_part, 64 * 64));
   RET(dev_alloc(ctx, &ctx->Ab, Gl * (KK + K)));
   RET(dev_alloc(ctx, &ctx->red, 64));
   RET(dev_alloc(ctx, &ctx->amean, K));

@@ -117,6 +117,7 @@ struct ruvnb_ctx {
          *red = nullptr, *amean = nullptr, *S0 = nullptr, *S1 = nullptr, *Wbar = nullptr,
          *RMW = nullptr, *sumsq = nullptr, *med = nullptr, *mad = nullptr, *ctlpack = nullptr, *alpha_full = nullptr,
          *scal = nullptr;
+  double* colsum_part = nullptr;   // [COLSUM_B][64] partial column sums (k_colsum_part -> k_colsum_fin)
   double* Wc = nullptr;      // [Gl][Np] weight cache: huber x sig.inv x wt.zinb of every element, written by pass 1 / the fused sweep and
   bool Wc_tried = false;     //   read back by pass 2 (kernels.cuh k_pass2w); taken when HBM has the room, RUVNB_NO_WCACHE=1 turns it off
   double* SWZ = nullptr;     // [nparts][Gl][m] per-group sum w Z of the same sweep

@@ -62,7 +62,8 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
   CKL();
   ctx->faillist_for = s.sigma;
   if (total) {
-    k_colsum<<<1, 1024, 0, ctx->stream>>>(out, Gl, 1, ctx->scal);
+    k_colsum_part<<<COLSUM_B, 256, 0, ctx->stream>>>(out, Gl, 1, ctx->colsum_part); CKL();
+    k_colsum_fin<<<1, 64, 0, ctx->stream>>>(ctx->colsum_part, 1, ctx->scal);
     CKL();
     k_pack_fin<<<1, 32, 0, ctx->stream>>>(ctx->scal, ctx->flags); CKL();
     RET(allreduce(ctx, ctx->scal, 3, NCCL_F64));
@@ -367,7 +368,8 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   DISPATCH_K(K, {
     k_alpha_finish<KT><<<nblk(Gl, 128), 128, 0, ctx->stream>>>(Gl, m, (double)ctx->N, ctx->d_group_n, ctx->A, ctx->u, ctx->sw, ctx->ZS, ctx->VS, c.adev, ctx->cvec, ctx->Ab);
     CKL();
-    k_colsum<<<1, 1024, 0, ctx->stream>>>(ctx->Ab, Gl, KK + K, ctx->red);
+    k_colsum_part<<<COLSUM_B, 256, 0, ctx->stream>>>(ctx->Ab, Gl, KK + K, ctx->colsum_part); CKL();
+    k_colsum_fin<<<1, 64, 0, ctx->stream>>>(ctx->colsum_part, KK + K, ctx->red);
     CKL();
     RET(allreduce(ctx, ctx->red, KK + K, NCCL_F64));
     k_alpha_mean<KT><<<1, 32, 0, ctx->stream>>>(ctx->red, ctx->amean);

@@ -1222,6 +1222,35 @@ static __global__ void __launch_bounds__(1024) k_colsum(const double* X, long lo
   }
 }
 
+// The same in two stages for the per-iteration sums over all genes (one CTA walking 20 strided columns of 20 000 rows took 0.24 ms):
+// COLSUM_B CTAs each sum a contiguous slice of rows with coalesced loads -- thread t owns column t % ncol and strides by a multiple
+// of ncol -- then one CTA adds the COLSUM_B partial rows in order.  Deterministic: the slices depend on n only.
+#define COLSUM_B 64
+static __global__ void __launch_bounds__(256) k_colsum_part(const double* X, long long n, int ncol, double* part /* [COLSUM_B][ncol] */) {
+  __shared__ double sm[256];
+  const int T = (256 / ncol) * ncol;                        // active threads: a multiple of ncol
+  const long long per = (n + COLSUM_B - 1) / COLSUM_B;
+  const long long r0 = min(n, (long long)blockIdx.x * per), r1 = min(n, r0 + per);
+  const double* x = X + r0 * ncol;
+  const long long ne = (r1 - r0) * ncol;
+  double s = 0.0;
+  if ((int)threadIdx.x < T) for (long long e = threadIdx.x; e < ne; e += T) s += x[e];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  if ((int)threadIdx.x < ncol) {
+    double t = 0.0;
+    for (int q = threadIdx.x; q < T; q += ncol) t += sm[q];
+    part[(long long)blockIdx.x * ncol + threadIdx.x] = t;
+  }
+}
+static __global__ void k_colsum_fin(const double* part, int ncol, double* out) {
+  const int c = threadIdx.x;
+  if (c >= ncol) return;
+  double t = 0.0;
+  for (int b = 0; b < COLSUM_B; ++b) t += part[(long long)b * ncol + c];
+  out[c] = t;
+}
+
 // small dense solvers ---------------------------------------------------------------------------
 // Gaussian elimination with partial pivoting (what R's solve() / LAPACK dgesv does), n <= 9.
 template <int NMAX>
