@@ -35,6 +35,7 @@ int ruvnb_create(ruvnb_ctx** out, int device) {
   cudaEventCreateWithFlags(&ctx->ev_ctl, cudaEventDisableTiming);
   { const char* e = getenv("RUVNB_NO_FUSE"); ctx->opt_no_fuse = e && *e && *e != '0'; }
   { const char* e = getenv("RUVNB_SLAB_CFG"); ctx->opt_slab_cfg = e ? atoi(e) : 0; }
+  { const char* e = getenv("RUVNB_NO_SEED"); ctx->opt_no_seed = e && *e && *e != '0'; }
   { const char* e = getenv("RUVNB_HINT_HALF"); double v = e ? atof(e) : 0.0; if (v > 0.05 && v < 0.85) ctx->opt_hint_half = v; }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;
@@ -377,7 +378,7 @@ int ruvnb_upload_counts_dense(ruvnb_ctx* ctx, const int32_t* Y, int layout, cons
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
+  ctx->have_counts = true; ctx->hints_seeded = false; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
 
@@ -423,7 +424,7 @@ int ruvnb_upload_counts_csr(ruvnb_ctx* ctx, const int64_t* indptr, const int32_t
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
+  ctx->have_counts = true; ctx->hints_seeded = false; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
 
@@ -592,7 +593,7 @@ int ruvnb_upload_counts_done(ruvnb_ctx* ctx) {
   if (!ctx->d_ctl_rows) RET(dev_alloc(ctx, &ctx->d_ctl_rows, ctx->n_ctl));
   CK(cudaMemcpyAsync((void*)ctx->d_ctl_rows, rows.data(), rows.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->have_counts = true; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
+  ctx->have_counts = true; ctx->hints_seeded = false; ctx->roworder_ready = false; ctx->hist_ready = false; ctx->dp_beta_warm = false;
   return RUVNB_OK;
 }
 

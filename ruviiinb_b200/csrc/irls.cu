@@ -16,6 +16,30 @@ static __global__ void k_pack_fin(double* scal, const int* flags) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { scal[1] = (double)flags[2]; scal[2] = (double)flags[3]; }
 }
 
+// hints for a context whose rows have none (k_hint_sample): 16 whole chunks spread over the non-empty chunks of the row
+static int seed_hints(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s) {
+  ctx->hints_seeded = true;
+  std::vector<int> full;
+  for (int c = 0; c < ctx->nchunks; ++c) if (ctx->chunk_valid[c] > 0) full.push_back(c);
+  const int ns = 16;   // 2048 cells: the sample median is off by ~0.03 MAD, the window is +- 0.7 of the slack
+  if ((int)full.size() < 4 * ns) return RUVNB_OK;   // small problems: the exact path is cheap
+  std::vector<int> pick(ns);
+  long long n_s = 0;
+  for (int i = 0; i < ns; ++i) { pick[i] = full[(size_t)((2 * i + 1) * full.size() / (2 * ns))]; n_s += ctx->chunk_valid[pick[i]]; }
+  const int Gl = ctx->Gl;
+  ScopedDev own;
+  int *d_pick = nullptr, *rn = nullptr; double *Ds = nullptr, *rmx = nullptr, *sg = nullptr;
+  if (own.alloc(&Ds, (size_t)Gl * ns * CH * 8) != cudaSuccess) { cudaGetLastError(); return RUVNB_OK; }   // no room: no hints, the exact path runs
+  CK(own.alloc(&d_pick, ns * 4)); CK(own.alloc(&rn, (size_t)Gl * 4)); CK(own.alloc(&rmx, (size_t)Gl * 8)); CK(own.alloc(&sg, (size_t)Gl * 8));
+  CK(cudaMemcpyAsync(d_pick, pick.data(), ns * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_hint_sample<<<nblk(Gl, 8), 256, 0, ctx->stream>>>(Gl, ctx->K, ctx->m, ctx->Np, ctx->dY, s.gmean, s.Mb, s.alpha, s.psi, s.W, d_pick, ns, ctx->d_chunk_grp,
+                                                      ctx->d_chunk_valid, ctx->d_chunk_batch, Ds, rmx, rn); CKL();
+  const double kh = o->robust ? 1.345 : 100.0;
+  k_row_sigma<<<Gl, RS_NT, 0, ctx->stream>>>(Ds, (long long)ns * CH, n_s, nullptr, rmx, rn, kh, 1, sg, nullptr, ctx->hint, ctx->opt_hint_half); CKL();
+  CK(cudaStreamSynchronize(ctx->stream));   // (scratch leaves with this scope)
+  return RUVNB_OK;
+}
+
 // per-gene log-likelihood of parameter set `s` into `out` (R/ruvIIInb.R:276-291) and, in the same sweep, the
 // Huber certificate of `s` (s.sigma: +Inf certified / 0 to be evaluated exactly; the rows left at 0 are listed in
 // ctx->faillist).  with_p1: the sweep also leaves the working quantities of `s` in the slabs and k_gram takes the Gram / score /
@@ -26,6 +50,7 @@ static int loglik_of(ruvnb_ctx* ctx, const ruvnb_opts* o, StateSet& s, double* o
   const double kh = o->robust ? 1.345 : 100.0;  // :155
   const int Gl = ctx->Gl, P = ctx->nparts;
   RET(ensure_ytabs(ctx, s.psi));
+  if (o->huber_fastpath && !ctx->hints_seeded && !ctx->opt_no_seed) RET(seed_hints(ctx, o, s));
   if (with_p1) RET(make_rmw(ctx, s.W));   // (fuse_ok has allocated the slabs)
   KEV_BEGIN(4);
   ctx->launch_parts = P;

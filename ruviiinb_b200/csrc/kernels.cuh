@@ -593,6 +593,45 @@ static __global__ void __launch_bounds__(RS_NT) k_row_sigma(const double* D, lon
   }
 }
 
+// Certificate hints for a context that has none yet: the signed deviances of a SAMPLE of every row's cells (ns whole chunks spread over
+// the row, 128 ns values per row in Ds, pads = +Inf) -- k_row_sigma then takes the median / MAD of the sample and writes the hint
+// window.  A hint never changes a result (the certificate sweep re-verifies it on all cells): without this, the first sweep of a
+// fit sends every row through the exact path (20 000 row walks + selections at cfg 2, ~45 ms).  One warp per row; plain libm
+// arithmetic (the sample is 2 % of a sweep).
+static __global__ void __launch_bounds__(256) k_hint_sample(int Gl, int K, int m, long long Np, const int32_t* Yp, const double* gmean, const double* Mb,
+                                                    const double* alpha, const double* psi, const double* W, const int* sample_chunks, int ns,
+                                                    const int* chunk_grp, const int* chunk_valid, const int* chunk_batch, double* Ds,
+                                                    double* rowmax, int* rownan) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= Gl) return;
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  const double gm = gmean[row];
+  double al[RUVNB_MAX_K];
+  for (int l = 0; l < K; ++l) al[l] = alpha[(long long)row * K + l];
+  double mx = 0.0; int nan_ = 0;
+  for (int si = 0; si < ns; ++si) {
+    const int c = sample_chunks[si], nv = chunk_valid[c];
+    const double r = 1.0 / psi[(long long)chunk_batch[c] * Gl + row];
+    const double base = gm + Mb[(long long)row * m + chunk_grp[c]];
+    for (int e = 0; e < 4; ++e) {
+      const int cell = e * 32 + lane;
+      const long long pos = (long long)c * CH + cell;
+      double d = inf;
+      if (cell < nv) {
+        double lmu = base;
+        for (int l = 0; l < K; ++l) lmu = fma(al[l], W[(long long)l * Np + pos], lmu);
+        d = nb_signdev(Yp[(long long)row * Np + pos], lmu, exp(lmu), r);
+        if (d != d) nan_ = 1;
+        mx = fmax(mx, fabs(d));
+      }
+      Ds[((long long)row * ns + si) * CH + cell] = d;
+    }
+  }
+  mx = warp_max(mx);
+  nan_ = __any_sync(FULL, nan_);
+  if (lane == 0) { rowmax[row] = mx; rownan[row] = nan_; }
+}
+
 // rows split by their Huber status: sigma = +Inf (every weight provably 1) -> list_inf, anything else (finite or NaN
 // sigma: live weights) -> list_fin; both in launch order `order` (or natural order); one CTA, ordered scan
 static __global__ void __launch_bounds__(1024) k_partition_sigma(int Gl, const double* sigma, const int* order, int* list_inf, int* list_fin,
