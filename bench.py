@@ -407,11 +407,14 @@ def main():
         barrier()
         t0 = time.perf_counter()
         ctx.upload_counts(Yh, Yctl=Yctl)
+        t_e_up = time.perf_counter() - t0
         set_start_state(ctx)
         ctx.loglik(opts)
+        t_e_ll = time.perf_counter() - t0 - t_e_up
         for _ in range(args.steps):
             ctx.irls_iteration(opts)
             ctx.accept()
+        t_e_loop = time.perf_counter() - t0 - t_e_up - t_e_ll
         out = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb")}
         barrier()
         dt = time.perf_counter() - t0
@@ -424,6 +427,7 @@ def main():
         d2h = sum(v.nbytes for v in out.values()) + 8 * args.steps
         e2e = {"value": G * args.steps / dt, "unit": "gene-fits/s", "h2d_bytes_per_step": int(h2d * world / args.steps),
                "d2h_bytes_per_step": int(d2h * world / args.steps),
+               "seconds": {"upload": t_e_up, "start_state_and_first_loglik": t_e_ll, "iterations": t_e_loop, "total": dt},
                "what": "on an existing context: upload_counts (pinned host int32 -> HBM, permuted) + W0/psi upload + init_coef + loglik + K irls_iteration (each returns its log-likelihood) + get_state(W, alpha, gmean, Mb); wall clock, max over ranks"}
 
     # ---- optional: the whole fit, host buffers in, converged parameters out ---------------------------------------

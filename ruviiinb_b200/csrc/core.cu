@@ -793,6 +793,7 @@ int ruvnb_set_state(ruvnb_ctx* ctx, const char* name, const double* host, int k)
   CK(cudaMemcpyAsync(p, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->cur.sig_valid = false;                  // the Huber scale belongs to the parameters it was computed for
+  ctx->best_eq_cur = false;
   if (!strcmp(name, "psi")) ctx->psi_ver++;    // count tables follow psi
   return RUVNB_OK;
 }

@@ -125,6 +125,7 @@ struct ruvnb_ctx {
   double* WZc = nullptr;     // [Gl][Np] w Z of every element: the fused sweep's second slab (k_ll_w -> k_gram), allocated with Wc
   double* D = nullptr; long long D_rows = 0;  // exact-MAD scratch [D_rows][Np]
   double* rowmax = nullptr; int* rownan = nullptr;  // per scratch slot: max|d|, NaN flag
+  bool best_eq_cur = false;      // `best` and `cur` hold the same parameter set (last copy_set between them, nothing changed since)
   bool hints_seeded = false;     // the rows got hints from a sample of their deviances (irls.cu seed_hints); RUVNB_NO_SEED=1 turns it off
   bool opt_no_seed = false;
   double* hint = nullptr;        // [Gl][3] certificate hints lo, hi, tg (k_row_sigma -> k_loglik)

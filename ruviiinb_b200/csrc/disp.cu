@@ -335,7 +335,7 @@ static int estimate_disp_impl(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, d
   for (int g = 0; g < Gl; ++g) if (std::isfinite(tag[g0 + g])) old[g] = tag[g0 + g];
   CK(cudaMemcpyAsync(s.psi, old.data(), (size_t)Gl * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  ctx->psi_ver++; s.sig_valid = false;
+  ctx->psi_ver++; s.sig_valid = false; ctx->best_eq_cur = false;
   if (o->verbose)
     fprintf(stderr, "estimateDisp: grid APL %.3f s (%d NR sweeps + 3 APL sweeps), gather + common %.3f s, AveLogCPM %.3f s (%d sweeps), "
                     "trend %.3f s, prior d.f. %.3f s (%d sweeps + deviance), tagwise %.3f s\n",

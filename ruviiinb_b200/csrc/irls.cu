@@ -332,6 +332,13 @@ static int irls_body(ruvnb_ctx* ctx, const ruvnb_opts* o, double* logl_new, int 
   int nfail = 0, nactive = 0;
   RET(complete_sigma(ctx, o, c, kh, &nfail, &nactive));
   ctx->last_fail_rows = nfail; ctx->last_active_rows = nactive;
+  if (nfail > 0 && ctx->best_eq_cur) {
+    // `best` holds this very parameter set (snapshot or restore just before this pass): it keeps the completed Huber scales, so a
+    // rejected step that restores it does not send the same rows through the exact path again
+    CK(cudaMemcpyAsync(ctx->best.sigma, c.sigma, (size_t)Gl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->best.sig_valid = c.sig_valid; ctx->best.maybe_active = c.maybe_active; ctx->best.nfail = c.nfail;
+  }
+  ctx->best_eq_cur = false;   // the pass ends with a new current state
   const bool hub = nactive > 0 || ctx->zinb_on;   // the general instantiation also carries the ZINB weights
   k_partition_sigma<<<1, 1024, 0, ctx->stream>>>(Gl, c.sigma, ctx->roworder_ready ? ctx->d_roworder : nullptr, ctx->list_inf, ctx->list_fin, ctx->part_counts);
   CKL();
@@ -545,6 +552,7 @@ static int copy_set(ruvnb_ctx* ctx, StateSet& dst, const StateSet& src) {
   CK(cudaMemcpyAsync(dst.psi_w, src.psi_w, Gl * ctx->nbatch * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaMemcpyAsync(dst.wtctl, src.wtctl, (size_t)ctx->n_ctl * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   dst.sig_valid = src.sig_valid; dst.maybe_active = src.maybe_active; dst.nfail = src.nfail;
+  ctx->best_eq_cur = (&dst == &ctx->best && &src == &ctx->cur) || (&dst == &ctx->cur && &src == &ctx->best);
   if (ctx->faillist_for == dst.sigma) ctx->faillist_for = nullptr;   // the list was made from what this buffer held before
   dst.p1_valid = false;   // the Gram / score sums in ctx->A.. belong to one parameter set (and one step vector) only
   return RUVNB_OK;
@@ -657,7 +665,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
       for (long long g = 0; g < GB; ++g) tmp[g] = std::isfinite(src[g]) ? src[g] : old[g];  // :564
       CK(cudaMemcpyAsync(target.psi, tmp.data(), (size_t)GB * 8, cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
-      ctx->psi_ver++; target.sig_valid = false;
+      ctx->psi_ver++; target.sig_valid = false; ctx->best_eq_cur = false;
       return RUVNB_OK;
     }
     if (ctx->psi_cb) {
@@ -668,7 +676,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
       int r = ctx->psi_cb(ctx->psi_cb_user, ctx);
       if (&target != &ctx->cur) std::swap(ctx->cur, target);
       if (r != RUVNB_OK) return ctx->fail(r < 0 ? r : RUVNB_EARG, "fit_nb: the dispersion callback returned %d", r);
-      ctx->psi_ver++; target.sig_valid = false;
+      ctx->psi_ver++; target.sig_valid = false; ctx->best_eq_cur = false;
       return RUVNB_OK;
     }
     if (ctx->nbatch > 1) return ctx->fail(RUVNB_ESTATE, "fit_nb: a batch-specific dispersion needs a psi schedule or ruvnb_set_psi_callback (one estimateDisp per batch)");
@@ -680,7 +688,7 @@ int ruvnb_fit_nb(ruvnb_ctx* ctx, const ruvnb_opts* o, const double* W0, const do
     int r = ruvnb_estimate_disp(ctx, o, nullptr);
     if (&target != &ctx->cur) std::swap(ctx->cur, target);
     RET(r);
-    ctx->psi_ver++; target.sig_valid = false;
+    ctx->psi_ver++; target.sig_valid = false; ctx->best_eq_cur = false;
     CK(cudaEventRecord(d1, ctx->stream));
     CK(cudaEventSynchronize(d1));
     float ms = 0; CK(cudaEventElapsedTime(&ms, d0, d1)); disp_ms += ms;
