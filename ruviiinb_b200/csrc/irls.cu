@@ -234,7 +234,7 @@ static __global__ void k_gather_ctlpack(int nc, int K, int m, int nb, long long 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)nc * per) return;
   // field-major layout (as CtlPack expects): locate the field of element i
-  double* p_gmean = pk; double* p_psi = pk + nc; double* p_step = p_psi + (long long)nb * nc;
+  double* p_psi = pk + nc; double* p_step = p_psi + (long long)nb * nc;
   double* p_aold = p_step + nc; double* p_anew = p_aold + (long long)nc * K; double* p_mb = p_anew + (long long)nc * K;
   double* p_pi0 = p_mb + (long long)nc * m; double* p_psiw = p_pi0 + nc;
   double* dst = pk + i;
