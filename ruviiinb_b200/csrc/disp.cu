@@ -255,23 +255,34 @@ static int estimate_disp_impl(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, d
   std::vector<double> xs(ns); std::vector<int> perm(ns);
   for (int i = 0; i < ns; ++i) { xs[i] = alc[sel[order[i]]]; perm[i] = sel[order[i]]; }
   std::vector<double> m0s((size_t)ns * DISP_NG);
+  int i_min = 0;
+  for (int i = 1; i < ns; ++i) if (alc[sel[i]] < alc[sel[i_min]]) i_min = i;   // which.min(AveLogCPM[sel])
+  // a gene shard needs the trend (and everything after it) for its OWN genes only, plus the gene of lowest abundance whose trended
+  // value the unselected genes take (:143-145): `mine` = their sorted positions (all of them on one GPU)
+  const bool sharded = ctx->nranks > 1;
+  auto is_mine = [&](int gene) { return !sharded || (gene >= g0 && gene < g0 + Gl) || gene == sel[i_min]; };
+  std::vector<int> mine;
+  for (int i = 0; i < ns; ++i) if (is_mine(perm[i])) mine.push_back(i);
   {
     double *d_xs = ctx->dp_xs, *d_m0 = ctx->dp_m0, *d_l0g = nullptr; int* d_perm = ctx->dp_perm;   // ns <= G
-    if (ctx->nranks > 1) d_l0g = tmpA; else d_l0g = ctx->dp_l0;
+    if (sharded) d_l0g = tmpA; else d_l0g = ctx->dp_l0;
     CK(cudaMemcpyAsync(d_xs, xs.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_perm, perm.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, ctx->stream));
-    k_tricube<<<ns, 128, 0, ctx->stream>>>(d_xs, d_perm, ns, q, d_l0g, DISP_NG, d_m0); CKL();
-    CK(cudaMemcpyAsync(m0s.data(), d_m0, m0s.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    int* d_mine = nullptr;
+    if (sharded) {
+      CK(scratch.alloc(&d_mine, std::max<size_t>(1, mine.size()) * 4));
+      CK(cudaMemcpyAsync(d_mine, mine.data(), mine.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!mine.empty()) { k_tricube<<<(unsigned)mine.size(), 128, 0, ctx->stream>>>(d_xs, d_perm, ns, q, d_l0g, DISP_NG, d_m0, d_mine); CKL(); }
+    CK(cudaMemcpyAsync(m0s.data(), d_m0, m0s.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));   // (rows of other ranks' genes: not evaluated, not read)
     CK(cudaStreamSynchronize(ctx->stream));
   }
   // m0 back to gene order; trended dispersion (:140-145)
   std::vector<double> m0((size_t)G * DISP_NG, 0.0), trended(G, 0.0);
-  int i_min = 0;
-  for (int i = 0; i < ns; ++i) {
+  for (int i : mine) {
     memcpy(&m0[(size_t)perm[i] * DISP_NG], &m0s[(size_t)i * DISP_NG], DISP_NG * 8);
     trended[perm[i]] = 0.1 * exp2(maximize_interpolant_h(DISP_NG, pts, &m0s[(size_t)i * DISP_NG]));
   }
-  for (int i = 1; i < ns; ++i) if (alc[sel[i]] < alc[sel[i_min]]) i_min = i;   // which.min(AveLogCPM[sel])
   { std::vector<char> issel(G, 0); for (int i : sel) issel[i] = 1; for (long long g = 0; g < G; ++g) if (!issel[g]) trended[g] = trended[sel[i_min]]; }
   if (trended_out) memcpy(trended_out, trended.data() + g0, (size_t)Gl * 8);
   const double t_trend = now();
@@ -315,6 +326,7 @@ static int estimate_disp_impl(ruvnb_ctx* ctx, const ruvnb_opts* o, int robust, d
       double l0a[DISP_NG];
       for (int q = 0; q < ns; ++q) {
         const int i = sel[q];
+        if (sharded && (i < g0 || i >= g0 + Gl)) continue;   // another rank's gene
         double pn = prior_df_sel[q] / (N - 1.0);
         const bool large = pn > 1e6;
         if (large) { if (robust) continue; pn = 1e6; }

@@ -463,12 +463,13 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_dev(RowGeom geo, GeneSt
 // ---- local-constant tricube smoother (locfit deg = 0 stand-in) -------------------------------------------------------
 // xs: covariate sorted ascending (n), perm: row of l0 for each sorted position; one CTA per sorted position i.  The q
 // nearest neighbours of xs[i] are a contiguous window of the sorted order; bandwidth h = distance to the q-th nearest.
+// idx (nullable): the sorted positions this launch evaluates (a gene shard computes the trend of its own genes only), else all n.
 static __global__ void __launch_bounds__(128) k_tricube(const double* xs, const int* perm, int n, int q, const double* l0, int ld0,
-                                                 double* m0 /* [n][DISP_NG] in sorted order */) {
+                                                 double* m0 /* [n][DISP_NG] in sorted order */, const int* idx) {
   __shared__ double red[4][DISP_NG + 1];
   __shared__ int s_lo;
   __shared__ double s_h;
-  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = idx ? idx[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     const double xi = xs[i];
     // window [lo, lo+q) with lo in [max(0, i-q+1), min(i, n-q)] minimising max(xi - xs[lo], xs[lo+q-1] - xi)
