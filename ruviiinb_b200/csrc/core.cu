@@ -36,6 +36,7 @@ int ruvnb_create(ruvnb_ctx** out, int device) {
   { const char* e = getenv("RUVNB_NO_FUSE"); ctx->opt_no_fuse = e && *e && *e != '0'; }
   { const char* e = getenv("RUVNB_SLAB_CFG"); ctx->opt_slab_cfg = e ? atoi(e) : 0; }
   { const char* e = getenv("RUVNB_NO_SEED"); ctx->opt_no_seed = e && *e && *e != '0'; }
+  { const char* e = getenv("RUVNB_NO_DISP_PARTS"); ctx->opt_no_disp_parts = e && *e && *e != '0'; }
   { const char* e = getenv("RUVNB_HINT_HALF"); double v = e ? atof(e) : 0.0; if (v > 0.05 && v < 0.85) ctx->opt_hint_half = v; }
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;

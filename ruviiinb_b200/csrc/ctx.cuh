@@ -125,6 +125,8 @@ struct ruvnb_ctx {
   double* WZc = nullptr;     // [Gl][Np] w Z of every element: the fused sweep's second slab (k_ll_w -> k_gram), allocated with Wc
   double* D = nullptr; long long D_rows = 0;  // exact-MAD scratch [D_rows][Np]
   double* rowmax = nullptr; int* rownan = nullptr;  // per scratch slot: max|d|, NaN flag
+  double *dp_ps1 = nullptr, *dp_ps2 = nullptr;   // [DISP_MAXP][Gl][DISP_ND] partial sums of a scoring sweep launched with row parts
+  bool opt_no_disp_parts = false;               // RUVNB_NO_DISP_PARTS=1
   bool best_eq_cur = false;      // `best` and `cur` hold the same parameter set (last copy_set between them, nothing changed since)
   bool hints_seeded = false;     // the rows got hints from a sample of their deviances (irls.cu seed_hints); RUVNB_NO_SEED=1 turns it off
   bool opt_no_seed = false;

@@ -51,6 +51,7 @@ static int disp_ensure(ruvnb_ctx* ctx) {
   RET(dev_alloc(ctx, &ctx->dp_dev, Gl)); RET(dev_alloc(ctx, &ctx->dp_tabR2, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_flag, 2));
   RET(dev_alloc(ctx, &ctx->dp_done, Gl)); RET(dev_alloc(ctx, &ctx->dp_live, Gl)); RET(dev_alloc(ctx, &ctx->dp_info, Gl * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_step, Gl * DISP_NG));
   RET(dev_alloc(ctx, &ctx->dp_hist, Gl * YT)); RET(dev_alloc(ctx, &ctx->dp_syo, Gl));
+  RET(dev_alloc(ctx, &ctx->dp_ps1, (long long)DISP_MAXP * Gl * DISP_ND)); RET(dev_alloc(ctx, &ctx->dp_ps2, (long long)DISP_MAXP * Gl * DISP_ND));
   RET(dev_alloc(ctx, &ctx->dp_xs, ctx->G)); RET(dev_alloc(ctx, &ctx->dp_m0, ctx->G * DISP_NG)); RET(dev_alloc(ctx, &ctx->dp_perm, ctx->G));
   CK(cudaMemsetAsync(ctx->dp_zeros, 0, (size_t)Gl * 8, ctx->stream));
   double grid[DISP_NG];
@@ -73,7 +74,20 @@ static int disp_nr(ruvnb_ctx* ctx, const StateSet& s, DispArgs a, int nd) {
   for (int it = 0; it < 50; ++it) {
     const auto t0 = std::chrono::steady_clock::now();
     CK(cudaMemsetAsync(ctx->dp_flag, 0, 2 * sizeof(int), ctx->stream));
-    RET(launch_disp_nr(ctx, geom(ctx, nlive, live), s, a, nd));
+    {
+      // few rows (a small gene shard, the stragglers): cut the rows into parts so that the launch fills the device -- a sweep over
+      // ONE row otherwise costs a whole row walk (1 ms at 100 000 cells)
+      int P = 1;
+      if (a.Ecache && !ctx->opt_no_disp_parts) {
+        const long long ctas = (nlive + NWARP - 1) / NWARP;
+        while (P < DISP_MAXP && ctas * P < 4 * 296 && ctx->nchunks / (2 * P) >= 16) P *= 2;
+      }
+      a.nparts = P; a.Gl = ctx->Gl; a.part_s1 = ctx->dp_ps1; a.part_s2 = ctx->dp_ps2;
+      ctx->launch_parts = P;
+      int r = launch_disp_nr(ctx, geom(ctx, nlive, live), s, a, nd);
+      ctx->launch_parts = 1;
+      RET(r);
+    }
     ctx->disp_nr_sweeps++;
     if (it >= 2) { k_list_zero<<<1, 1024, 0, ctx->stream>>>(ctx->Gl, ctx->dp_done, ctx->dp_live, ctx->dp_flag + 1); CKL(); }
     CK(cudaMemcpyAsync(ctx->h_flags + 6, ctx->dp_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -16,6 +16,7 @@
 
 #define DISP_NG 21
 #define DISP_ND 7   // dispersion values per sweep (3 sweeps cover the grid)
+#define DISP_MAXP 16  // row parts of a scoring sweep over few rows
 
 template <int K, int ND>
 struct DispRowShared {
@@ -47,6 +48,9 @@ struct DispArgs {
                             // rho = |step / step_prev| predicts the next step; a column whose NEXT step would be below tol
                             // stops now -- edgeR would spend one more sweep to apply a change < tol (1e-10) and stop.
                             // Only for |step| < 1e-8: info_out is the information BEFORE the step is applied
+  int Gl = 0;               // rows of the shard (stride of the part buffers)
+  int nparts = 1;           // row parts of this launch (cached sweeps over few rows); > 1: the sweep leaves partial S1, S2 per part in
+  double *part_s1 = nullptr, *part_s2 = nullptr;  // [nparts][Gl][ND] and k_disp_nr_finish applies the Newton step
   int* done;                // [Gl] rows whose ND intercepts have all converged: later sweeps skip them (edgeR stops each
                             // fit at |step| < tol; rows converge after 4-8 steps, a few stragglers need 15-20)
 };
@@ -131,6 +135,24 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_init(RowGeom geo, GeneS
   stream_rows<K, 1>(geo, &sh, op, smem);
 }
 
+// the Newton step of one (row, dispersion) from S1 = sum w y / (1 + phi mu), S2 = sum w E / (1 + phi mu); returns "not converged"
+__device__ __forceinline__ bool disp_nr_update(const DispArgs& a, int row, int d, double s1, double s2, double eb) {
+  s2 *= eb;
+  double step = (s1 - s2) / s2;
+  if (a.info_out) a.info_out[(long long)row * a.ldb + a.d0 + d * a.ds] = s2;
+  double* bp = a.beta + (long long)row * a.ldb + a.d0 + d * a.ds;
+  if (!(step == step)) return false;
+  *bp += step;
+  bool conv = fabs(step) < a.tol;
+  if (a.step_prev) {
+    double* sp = a.step_prev + (long long)row * a.ldb + a.d0 + d * a.ds;
+    const double prev = *sp;
+    *sp = step;
+    if (!conv && prev != 0.0 && fabs(step) < 1e-8) { double rho = fabs(step / prev); conv = rho < 0.5 && rho * fabs(step) < a.tol; }
+  }
+  return !conv;
+}
+
 // ---- one Newton-Raphson step for ND dispersions ------------------------------------------------------------------
 template <int K, int ND, bool CACHED = false>
 struct OpDispNR {
@@ -143,7 +165,10 @@ struct OpDispNR {
   double yadd, escale, egm; bool live; ERow er;
   __device__ __forceinline__ void row_begin(int row, int) {
     g.load(st, row);
-    er.begin(a.Ecache, row, a.Np, a.nchunks);
+    {   // the exp(offset) row must not be prefetched beyond this CTA's part of the row
+      const int per = (a.nchunks + a.nparts - 1) / a.nparts;
+      er.begin(a.Ecache, row, a.Np, min(a.nchunks, min(a.nchunks, (int)(blockIdx.x % a.nparts) * per) + per));
+    }
     live = false;
     egm = g.zi ? exp(a.gm_real[row]) : 1.0;
 #pragma unroll
@@ -202,27 +227,22 @@ struct OpDispNR {
       if (a.done && (threadIdx.x & 31) == 0) a.done[row] = 1;
       return;
     }
+    if (a.nparts > 1) {   // partial sums of this part; the step is applied by k_disp_nr_finish
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        double s1 = warp_sum(dl[d]), s2 = warp_sum(info[d]);
+        if ((threadIdx.x & 31) == 0) {
+          const long long q = ((long long)(blockIdx.x % a.nparts) * a.Gl + row) * ND + d;
+          a.part_s1[q] = s1; a.part_s2[q] = s2;
+        }
+      }
+      return;
+    }
     bool nc = false;
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
       double s1 = warp_sum(dl[d]), s2 = warp_sum(info[d]);
-      if ((threadIdx.x & 31) == 0) {
-        s2 *= eb[d];
-        double step = (s1 - s2) / s2;
-        if (a.info_out) a.info_out[(long long)row * a.ldb + a.d0 + d * a.ds] = s2;
-        double* bp = a.beta + (long long)row * a.ldb + a.d0 + d * a.ds;
-        if (step == step) {
-          *bp += step;
-          bool conv = fabs(step) < a.tol;
-          if (a.step_prev) {
-            double* sp = a.step_prev + (long long)row * a.ldb + a.d0 + d * a.ds;
-            const double prev = *sp;
-            *sp = step;
-            if (!conv && prev != 0.0 && fabs(step) < 1e-8) { double rho = fabs(step / prev); conv = rho < 0.5 && rho * fabs(step) < a.tol; }
-          }
-          nc |= !conv;
-        }
-      }
+      if ((threadIdx.x & 31) == 0) nc |= disp_nr_update(a, row, d, s1, s2, eb[d]);
     }
     nc = __shfl_sync(FULL, nc, 0);
     if (nc) { if ((threadIdx.x & 31) == 0) atomicExch(a.notconv, 1); }
@@ -246,6 +266,22 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr_cached(RowGeom geo, 
   OpDispNR<K, ND, true> op;
   op.st = st; op.a = a;
   stream_rows_lean(geo, &sh, op);
+}
+
+// the Newton steps of a sweep launched with row parts: sums of the parts in a fixed order, then what the sweep's row end does
+template <int ND>
+static __global__ void k_disp_nr_finish(int nrows, const int* rowlist, DispArgs a) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nrows) return;
+  const int row = rowlist ? rowlist[slot] : slot;
+  if (a.done[row]) return;   // converged before this sweep, or nothing to iterate on (the sweep marked it)
+  bool nc = false;
+  for (int d = 0; d < ND; ++d) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < a.nparts; ++p) { const long long q = ((long long)p * a.Gl + row) * ND + d; s1 += a.part_s1[q]; s2 += a.part_s2[q]; }
+    nc |= disp_nr_update(a, row, d, s1, s2, exp(a.beta[(long long)row * a.ldb + a.d0 + d * a.ds]));
+  }
+  if (nc) atomicExch(a.notconv, 1); else a.done[row] = 1;
 }
 
 // ---- adjusted profile likelihood for ND dispersions ---------------------------------------------------------------

@@ -302,12 +302,15 @@ __device__ __forceinline__ void stream_rows(const RowGeom& geo, RowShared* sh, O
 // The same walk for ops that take nothing from the W tiles (the dispersion sweeps on the exp(offset) cache): no tile
 // staging, no CTA barriers inside the row -- a warp only streams its row's counts one chunk ahead.  pair() gets
 // tile == nullptr.
+// geo.nparts > 1: every row is cut into nparts runs of chunks, one CTA per (row block, part) -- for launches over few rows (a small
+// gene shard, the stragglers of an iteration), whose ops leave partial sums per part.
 template <class Op, int NW = NWARP>
 __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* sh, Op& op) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slot = blockIdx.x * NW + warp;
+  const int part = blockIdx.x % geo.nparts, rblk = blockIdx.x / geo.nparts;
+  const int slot = rblk * NW + warp;
   const int nrows = geo.nrows_dev ? min(geo.nrows, *geo.nrows_dev) : geo.nrows;
-  if (blockIdx.x * NW >= nrows) return;
+  if (rblk * NW >= nrows) return;
   const bool active = slot < nrows;
   const int row = active ? (geo.rowlist ? geo.rowlist[slot] : slot) : 0;
   {
@@ -323,13 +326,16 @@ __device__ __forceinline__ void stream_rows_lean(const RowGeom& geo, RowShared* 
   op.row_begin(row, slot);
   const int2* yrow2 = reinterpret_cast<const int2*>(geo.Yp + (long long)row * geo.Np);
   int curj = -1;
-  int2 ya = yrow2[lane], yb = yrow2[32 + lane];
-  int meta = geo.chunk_meta[0];
+  const int per = (geo.nchunks + geo.nparts - 1) / geo.nparts;
+  const int c_lo = min(geo.nchunks, part * per), c_hi = min(geo.nchunks, c_lo + per);
+  int2 ya = make_int2(0, 0), yb = ya;
+  int meta = 0;
+  if (c_lo < c_hi) { ya = yrow2[c_lo * (CH / 2) + lane]; yb = yrow2[c_lo * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c_lo]; }
 #pragma unroll 1
-  for (int c = 0; c < geo.nchunks; ++c) {
+  for (int c = c_lo; c < c_hi; ++c) {
     const int2 y01 = ya, y23 = yb;
     const int mcur = meta;
-    if (c + 1 < geo.nchunks) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c + 1]; }
+    if (c + 1 < c_hi) { ya = yrow2[(c + 1) * (CH / 2) + lane]; yb = yrow2[(c + 1) * (CH / 2) + 32 + lane]; meta = geo.chunk_meta[c + 1]; }
     const int nv = mcur & 0xff;
     if (nv == 0) continue;
     const int j = (mcur >> 8) & 0xffff;
