@@ -10,7 +10,7 @@
 //       3 element-wise sweeps  lmu = gmean + alpha W + Mb;  Z = Mb + (y + .01)/(exp(lmu) + .01) - 1;
 //       Mb = Z wt/(wt + lambda.b), wt = 1/(exp(-lmu) + psi); control genes 0; rows clamped to median +- 4 mad of the
 //       annotated columns.  The three sweeps of an element run in registers.
-// Included by ruvnb.cu only.
+// Included by fast.cu.
 #pragma once
 #include "kernels.cuh"
 

@@ -11,7 +11,7 @@
 //   k_ff_w          Wsub: sequential ridge regressions on the control genes with gene weights wt.ctl           (:443-457)
 //   k_ff_gsums      S0[g,j] = sum_{c in j} sig.inv, S1[g,j] = sum sig.inv (Z - alpha W): gmean / Mb by k_gmean_mb (:478-490)
 //   k_ff_cell_loglik  per-CELL log-likelihood sum_g log dnbinom (the fast fit halves steps per cell)          (:334-346,509-531)
-// Included by ruvnb.cu only.
+// Included by fast.cu.
 #pragma once
 #include "kernels.cuh"
 

@@ -10,7 +10,7 @@
 //             absolute error < 3e-16 (1 + |e|/8).
 //   frcp(x):  MUFU.RCP64H seed (20 bits) + one cubic Newton step: 3 FMA, relative error < 3e-16.
 // Everything is __host__ __device__ so tests/test_fastmath.py checks the SAME source on the CPU against
-// libm (ruvnb_selftest_math in ruvnb.cu); arguments outside the fast range fall back to exp()/log().
+// libm (ruvnb_selftest_math in core.cu); arguments outside the fast range fall back to exp()/log().
 #pragma once
 #include <math.h>
 #include <stdint.h>

@@ -1,4 +1,4 @@
-// kernels.cuh -- the IRLS kernels of libruvnb_b200 (sm_100a).  Included by ruvnb.cu only.
+// kernels.cuh -- the IRLS kernels of libruvnb_b200 (sm_100a).  Included (through launch.cuh) by every translation unit of the library: core.cu, irls.cu, the sweep_*.cu launchers, disp*.cu, res.cu, fast.cu, svd.cu.
 //
 // Data layout in HBM:
 //   Yp   int32 [Gl][Np]   counts, gene-major; cells permuted so that every replicate group is one

@@ -10,7 +10,7 @@
 //   k_res_clip   clip to those limits
 // PAC: mid-p = P(Y < y) + P(Y = y)/2 under (mu.full, r) by the pmf recurrence p(j+1) = p(j) (j + r)/(j + 1) mu/(mu + r),
 // clipped to [.005, .995]; then qnbinom(p; mu.noUV, r) = smallest q with cdf(q) >= p (1 - 64 eps) (R nmath's left-
-// continuity fuzz) by the same recurrence.  Included by ruvnb.cu only.
+// continuity fuzz) by the same recurrence.  Included by res.cu.
 #pragma once
 #include "kernels.cuh"
 

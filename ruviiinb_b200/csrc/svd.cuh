@@ -3,7 +3,7 @@
 // Subspace iteration on A'A: V <- orth(A'(A V)) with A held as a dense FP64 slab (n_ctl x N, 0.8 GB at 1000 x 100k) for the
 // duration of the call; then one Rayleigh-Ritz rotation.  irlba's Lanczos start is random and its tolerance is 1e-5, so the
 // reference's own W0 is only defined up to that (and up to sign); parity runs inject W0.
-// Sign convention: the entry of largest magnitude of every vector is positive.  Included by ruvnb.cu only.
+// Sign convention: the entry of largest magnitude of every vector is positive.  Included by svd.cu.
 #pragma once
 #include "kernels.cuh"
 

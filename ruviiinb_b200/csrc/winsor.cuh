@@ -3,7 +3,7 @@
 // filter (:57).  Per gene: q = type-7 quantile at `prob` = (1-h) x[lo] + h x[hi], lo = floor(1 + (n-1) prob);
 // counts above q become ceil(q), i.e. Y = min(Y, ceil(q)) for integer Y.  One CTA per gene row; the two order
 // statistics come from a counting histogram when the row maximum is < 4096 (one pass), else from a 12/12/8-bit
-// radix descent on the 32-bit value.  Included by ruvnb.cu only.
+// radix descent on the 32-bit value.  Included by core.cu (winsorize).
 #pragma once
 #include "common.cuh"
 

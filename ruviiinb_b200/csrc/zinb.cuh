@@ -7,7 +7,7 @@
 //   f(p) = - [ sum_{y = 0} log(omega + (1 - omega) q_c) + n_pos log(1 - omega) + S_pos ].
 // k_zinb_q writes q_c once (one sweep of the counts); every Nelder-Mead evaluation is then a pass over q only, all genes
 // in lock-step (k_nm_eval), with the simplex logic of each gene as a small state machine (k_nm_step).
-// The E-step weights (H5) are never stored: the sweeps recompute them (GeneRegs::wz).  Included by ruvnb.cu only.
+// The E-step weights (H5) are never stored: the sweeps recompute them (GeneRegs::wz).  Included by irls.cu.
 #pragma once
 #include "kernels.cuh"
 

@@ -17,7 +17,7 @@ def gene_range(G, world, rank):
 
 
 def chunk_range(nchunks, world, rank):
-    """128-cell chunks [c0, c1) whose cells rank `rank` updates in the W step (ruvnb.cu: irls_body)."""
+    """128-cell chunks [c0, c1) whose cells rank `rank` updates in the W step (csrc/irls.cu: irls_body)."""
     per = (nchunks + world - 1) // world
     return min(nchunks, rank * per), min(nchunks, (rank + 1) * per)
 
