@@ -260,8 +260,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr(RowGeom geo, GeneSta
 }
 
 // the same sweep on the exp(offset) cache (a.Ecache != nullptr): nothing is taken from the W tiles
+// (one dispersion per row -- the AveLogCPM and prior-d.f. fits -- is a pure stream of the exp(offset) slab: three CTAs per SM keep
+// more of it in flight)
 template <int K, int ND>
-__global__ void __launch_bounds__(ROW_THREADS, 2) k_disp_nr_cached(RowGeom geo, GeneState<K> st, DispArgs a) {
+__global__ void __launch_bounds__(ROW_THREADS, (ND == 1 ? 3 : 2)) k_disp_nr_cached(RowGeom geo, GeneState<K> st, DispArgs a) {
   __shared__ RowShared sh;
   OpDispNR<K, ND, true> op;
   op.st = st; op.a = a;
