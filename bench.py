@@ -121,6 +121,9 @@ def gen_rows_cpu(tp, rows, seed=SEED, chunk=500):
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
+E2E_REPS = 3
+
+
 class ClockSampler:
     """nvidia-smi polled every 20 ms in the background; only the samples taken between begin() and end() count.  start() returns
     once the first sample has arrived (nvidia-smi needs ~0.5 s to come up), so that even a sub-second region is sampled."""
@@ -403,36 +406,58 @@ def main():
     # ---- end-to-end leg: host buffers through the public API ------------------------------------
     e2e = None
     if not args.no_e2e:
-        ctx = make_ctx()   # context, NCCL communicator and design: one-time set-up, outside the timed region
-        barrier()
-        t0 = time.perf_counter()
-        ctx.upload_counts(Yh, Yctl=Yctl)
-        t_e_up = time.perf_counter() - t0
-        set_start_state(ctx)
-        ctx.loglik(opts)
-        t_e_ll = time.perf_counter() - t0 - t_e_up
-        for _ in range(args.steps):
-            ctx.irls_iteration(opts)
-            ctx.accept()
-        t_e_loop = time.perf_counter() - t0 - t_e_up - t_e_ll
-        out = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb")}
-        barrier()
-        dt = time.perf_counter() - t0
-        ctx.close()
-        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-        dt = float(tdt.item())
+        # three repetitions, the MEDIAN one is reported (all three are listed): the region is a second of host-driven work on a shared
+        # box, and a burst from another tenant (host memory bandwidth, driver calls) has been seen to stretch a single run several-fold
+        runs = []
+        for _rep in range(E2E_REPS):
+            ctx = make_ctx()   # context, NCCL communicator and design: one-time set-up, outside the timed region
+            barrier()
+            t0 = time.perf_counter()
+            ctx.upload_counts(Yh, Yctl=Yctl)
+            t_e_up = time.perf_counter() - t0
+            set_start_state(ctx)
+            ctx.loglik(opts)
+            t_e_ll = time.perf_counter() - t0 - t_e_up
+            for _ in range(args.steps):
+                ctx.irls_iteration(opts)
+                ctx.accept()
+            t_e_loop = time.perf_counter() - t0 - t_e_up - t_e_ll
+            out = {n: ctx.get_state(n) for n in ("W", "alpha", "gmean", "Mb")}
+            barrier()
+            dt = time.perf_counter() - t0
+            ctx.close()
+            tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+            runs.append({"upload": t_e_up, "start_state_and_first_loglik": t_e_ll, "iterations": t_e_loop, "total": float(tdt.item())})
+        med = sorted(runs, key=lambda r: r["total"])[len(runs) // 2]
+        dt = med["total"]
         h2d = Yh.nbytes + (Yctl.nbytes if Yctl is not None else 0) + tp["W0"].nbytes + 8 * Gl + 4 * N + G
         d2h = sum(v.nbytes for v in out.values()) + 8 * args.steps
         e2e = {"value": G * args.steps / dt, "unit": "gene-fits/s", "h2d_bytes_per_step": int(h2d * world / args.steps),
                "d2h_bytes_per_step": int(d2h * world / args.steps),
-               "seconds": {"upload": t_e_up, "start_state_and_first_loglik": t_e_ll, "iterations": t_e_loop, "total": dt},
-               "what": "on an existing context: upload_counts (pinned host int32 -> HBM, permuted) + W0/psi upload + init_coef + loglik + K irls_iteration (each returns its log-likelihood) + get_state(W, alpha, gmean, Mb); wall clock, max over ranks"}
+               "seconds": med, "repetitions": [G * args.steps / r["total"] for r in runs],
+               "what": "on an existing context: upload_counts (pinned host int32 -> HBM, permuted) + W0/psi upload + init_coef + loglik + K irls_iteration (each returns its log-likelihood) + get_state(W, alpha, gmean, Mb); wall clock, max over ranks; median of the repetitions listed"}
 
     # ---- optional: the whole fit, host buffers in, converged parameters out ---------------------------------------
     full_fit = None
     if not args.no_full_fit:
+        # What the warm-up steps are to the iteration line: CUDA loads a kernel's code at its first launch, and Winsorize, init_W and
+        # the dispersion step have not run in this process yet.  A small whole fit (same k, same options, one GPU, no communicator)
+        # pays those one-time costs outside the timed region; its own wall time is reported beside the timed fit.
+        t_w = time.perf_counter()
+        if not os.environ.get("RUVNB_BENCH_NO_WARM_FIT"):
+            Gw, Nw, mw, ncw = 1024, 4096, 8, 128
+            tpw = truth_params(Gw, Nw, k, mw, ncw, seed=SEED + 99)
+            Yw = np.empty((Gw, Nw), dtype=np.int32)
+            gen_rows_gpu(tpw, np.arange(Gw), Yw, dev)
+            with _lib.Context(local) as cw:
+                cw.set_design(Gw, Nw, tpw["grp"], tpw["ctl"])
+                cw.upload_counts(Yw)
+                cw.winsorize()
+                cw.fit_nb(opts, W0=cw.init_W(k)[0])
+                cw.get_state("psi")
+        t_warm_fit = time.perf_counter() - t_w
         ctx = make_ctx()
         fclocks = ClockSampler(local)
         if rank == 0:
@@ -462,11 +487,12 @@ def main():
                     "inner_loop_seconds": st["inner_seconds"], "dispersion_seconds": st["disp_seconds"],
                     "upload_winsorize_initW_seconds": t_init, "upload_seconds": t_up, "winsorize_seconds": t_win,
                     "initW_seconds": t_init - t_up - t_win, "initW_iterations": svd_iters,
+                    "warmup_fit_seconds": t_warm_fit,
                     "gene_fits_per_s_inner_loops": G * st["n_inner"] / st["inner_seconds"], "logl_outer": [float(x) for x in logl_outer],
                     "exact_mad_rows": st.get("n_exact_mad_rows"), "inner_loop_brackets": fit_kernels,
                     "decisions": [[r["outer"], r["iter"], r["halving"], r["accepted"]] for r in recs],
                     "canonical_corr_W_truth": [float(x) for x in np.linalg.svd(np.linalg.qr(res["W"] - res["W"].mean(0))[0].T @ np.linalg.qr(tp["W"] - tp["W"].mean(0))[0], compute_uv=False)] if rank == 0 else None,
-                    "what": "upload (pinned host int32) + Winsorize + ruvnb_init_W (truncated SVD of the control rows) + ruvnb_fit_nb with estimateDisp at every psi refresh + read-back; wall clock, max over ranks"}
+                    "what": "upload (pinned host int32) + Winsorize + ruvnb_init_W (truncated SVD of the control rows) + ruvnb_fit_nb with estimateDisp at every psi refresh + read-back; wall clock, max over ranks; preceded, untimed, by a 1024 x 4096 warm-up fit (warmup_fit_seconds) that triggers the first-launch kernel loads"}
 
     if rank != 0:
         if world > 1:
