@@ -44,6 +44,15 @@ def test_one_iteration_sparse_genes_fail_certificate():
     _check(res)
 
 
+def test_one_iteration_high_counts_beyond_the_tables():
+    """Means of 50-150 with dispersion ~0.3: most counts are >= 128, where the per-gene count tables end and the Stirling
+    series / the general logarithm take over (kernels.cuh: nb_big_lgterm)."""
+    from tests.parity import one_iteration_case
+    res = one_iteration_case(G=128, N=1100, k=2, m=3, n_ctl=32, seed=11, gmean_mu=4.6)
+    _check(res)
+    assert res["bad"] == res["oracle_bad"]
+
+
 def test_cell_major_upload_and_halved_steps():
     from tests.parity import one_iteration_case
     step = np.where(np.arange(160) % 3 == 0, 0.5, 1.0)
