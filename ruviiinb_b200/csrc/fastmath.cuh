@@ -71,16 +71,38 @@ __host__ __device__ __forceinline__ double fexp_nc(double x, const double* __res
   double kf = kd - MAGIC;
   double r = fma(kf, -C_HI, x);                // exact: kf has <= 18 bits, C_HI 29
   r = fma(kf, -C_LO, r);
+  double s = ex[n & (FM_NT - 1)];
+#ifdef FM_ESTRIN
+  // Estrin: e^r - 1 = r + r^2 (1/2 + r/6 + r^2 (1/24 + r/120)); the same six operations as Horner, four levels deep instead of six
+  const double r2 = r * r;
+  const double qa = fma(r, 1.0 / 6.0, 0.5), qb = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  double v = fma(s, fma(r2, fma(r2, qb, qa), r), s);
+#else
   double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
   q = fma(r, q, 1.0 / 6.0);
   q = fma(r, q, 0.5);
   q = fma(r, q, 1.0);
-  double s = ex[n & (FM_NT - 1)];
   double v = fma(s, r * q, s);                 // 2^(j/128) e^r, in [1, 2.01)
+#endif
   int e = n >> 7;                              // floor division; |e| <= 1010 -> result stays normal
   return FM_MK(FM_HI(v) + (e << 20), FM_LO(v));
 }
 
+// log(1 + u) / u for |u| <= 2^-8: 1 - u/2 + u^2/3 - u^3/4 + u^4/5 - u^5/6
+__host__ __device__ __forceinline__ double fm_log_poly(double u) {
+#ifdef FM_ESTRIN
+  // Estrin: (1 - u/2) + u^2 (1/3 - u/4) + u^4 (1/5 - u/6): seven operations three levels deep (Horner: five, five deep)
+  const double u2 = u * u;
+  const double a = fma(u, -0.5, 1.0), b = fma(u, -0.25, 1.0 / 3.0), c = fma(u, -1.0 / 6.0, 0.2);
+  return fma(u2 * u2, c, fma(u2, b, a));
+#else
+  double q = fma(u, -1.0 / 6.0, 0.2);
+  q = fma(u, q, -0.25);
+  q = fma(u, q, 1.0 / 3.0);
+  q = fma(u, q, -0.5);
+  return fma(u, q, 1.0);
+#endif
+}
 __host__ __device__ __forceinline__ double flog_nc(double v, const double* __restrict__ rc, const double* __restrict__ lc);
 __host__ __device__ __forceinline__ double flog(double v, const double* __restrict__ rc, const double* __restrict__ lc) {
   if (!(v > 1e-300 && v < 1e300)) return fm_slow_log(v);  // zero, subnormal, negative, Inf, NaN: libm path
@@ -93,11 +115,7 @@ __host__ __device__ __forceinline__ double flog_nc(double v, const double* __res
   int j = (hi >> 13) & (FM_NT - 1);
   double m = FM_MK((hi & 0x000fffff) | 0x3ff00000, FM_LO(v));
   double u = fma(m, rc[j], -1.0);
-  double q = fma(u, -1.0 / 6.0, 0.2);
-  q = fma(u, q, -0.25);
-  q = fma(u, q, 1.0 / 3.0);
-  q = fma(u, q, -0.5);
-  q = fma(u, q, 1.0);
+  double q = fm_log_poly(u);
   double ed = FM_MK(0x43300000, (int)(0x80000000u ^ (unsigned)e)) - 4503601774854144.0;  // (double)e without I2F
   return fma(ed, 0.6931471805599453, fma(u, q, lc[j]));
 }
@@ -110,11 +128,7 @@ __host__ __device__ __forceinline__ double flog_nc2(double v, const FmRL* __rest
   const FmRL t = rl[(hi >> 13) & (FM_NT - 1)];
   double m = FM_MK((hi & 0x000fffff) | 0x3ff00000, FM_LO(v));
   double u = fma(m, t.rc, -1.0);
-  double q = fma(u, -1.0 / 6.0, 0.2);
-  q = fma(u, q, -0.25);
-  q = fma(u, q, 1.0 / 3.0);
-  q = fma(u, q, -0.5);
-  q = fma(u, q, 1.0);
+  double q = fm_log_poly(u);
   double ed = FM_MK(0x43300000, (int)(0x80000000u ^ (unsigned)e)) - 4503601774854144.0;  // (double)e without I2F
   return fma(ed, 0.6931471805599453, fma(u, q, t.lc));
 }
